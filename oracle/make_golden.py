@@ -1,0 +1,225 @@
+"""Mint golden fixtures from the reference's OWN Python classes (TEST INFRASTRUCTURE).
+
+Run in the build container only (needs /root/reference; the GPU box does not have it):
+
+    python -m oracle.make_golden            # writes tests/golden/*.npz
+
+Each fixture stores only OUTPUTS (inputs/weights are regenerated from oracle/synth.py seeds on
+both sides) plus the seeds used.  What is imported from the reference, unmodified:
+  * inferno.models.DecaFLAME.FLAME / FLAME_mediapipe and inferno.utils.lbs (third_party/inferno)
+  * gdl.utils.lbs.lbs (BlendshapeVisualizer/EMOCA copy)
+  * models.lib.wav2vec.Wav2Vec2Model (subclass of the installed transformers Wav2Vec2Model)
+  * models.faceformer_disentangle: init_biased_mask, enc_dec_mask, PeriodicPositionalEncoding and
+    Faceformer.predict / forward_ff, reached through ``Faceformer.__new__`` because __init__ needs
+    network access, licensed FLAME assets and private paths.  Modules the import pulls in
+    that are absent here (easydict, omegaconf, pytorch3d-based visualisers, DECA, pirender) are stubbed
+    with MagicMock; none of them is touched by predict/forward_ff.
+  * loop_utils.loopback_frames
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+from unittest.mock import MagicMock
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+REF = "/root/reference"
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(os.path.dirname(HERE), "tests", "golden")
+COL_STRIDE = 7  # vertex-coordinate subsampling for the big [T,15069] outputs
+
+
+def _paths():
+    for p in (REF, os.path.join(REF, "third_party", "inferno"), os.path.join(REF, "BlendshapeVisualizer", "EMOCA")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+
+
+def checksum(t: torch.Tensor) -> np.ndarray:
+    d = t.double()
+    return np.array([d.sum().item(), (d * d).sum().item(), d.abs().max().item()])
+
+
+def golden_flame():
+    from inferno.models.DecaFLAME import FLAME, FLAME_mediapipe
+    from . import synth
+    out = {}
+    for n_shape, tag in ((100, "a"), (300, "b")):
+        cfg = synth.write_flame_assets("/tmp/avi_flame_assets")
+        cfg.n_shape = n_shape
+        m = FLAME_mediapipe(cfg) if n_shape == 100 else FLAME(cfg)
+        p = synth.flame_params(4, n_shape=n_shape, seed=3)
+        with torch.no_grad():
+            res = m(p["shape"], p["exp"], p["pose"], p["eye"])
+            # Path-A call convention: pose=[0,0,0,jaw], default eyes (faceformer_disentangle.py:425-433)
+            pose_a = p["pose"].clone()
+            pose_a[:, :3] = 0
+            res_a = m(p["shape"], p["exp"], pose_a)
+        out[f"verts_{tag}"] = res[0].numpy()
+        out[f"lmk2d_{tag}"] = res[1].numpy()
+        out[f"lmk3d_{tag}"] = res[2].numpy()
+        if n_shape == 100:
+            out["lmkmp_a"] = res[3].numpy()
+        out[f"verts_jawonly_{tag}"] = res_a[0].numpy()
+    # the gdl copy of lbs() called directly
+    from gdl.utils.lbs import lbs as gdl_lbs
+    buf = synth.flame_buffers(100, 50)
+    p = synth.flame_params(2, seed=5)
+    betas = torch.cat([p["shape"], p["exp"]], 1)
+    full_pose = torch.cat([p["pose"][:, :3], torch.zeros(2, 3), p["pose"][:, 3:], p["eye"]], 1)
+    v, J = gdl_lbs(betas, full_pose, buf["v_template"][None].expand(2, -1, -1), buf["shapedirs"], buf["posedirs"],
+                   buf["J_regressor"], buf["parents"], buf["lbs_weights"], detach_pose_correctives=False)
+    out["gdl_lbs_verts"] = v.numpy()
+    out["gdl_lbs_joints"] = J.numpy()
+    np.savez(os.path.join(GOLD, "flame.npz"), **out)
+    print("flame.npz", {k: v.shape for k, v in out.items()})
+
+
+def _ref_wav2vec2(sd):
+    from transformers import Wav2Vec2Config
+    from models.lib.wav2vec import Wav2Vec2Model
+    m = Wav2Vec2Model(Wav2Vec2Config(attn_implementation="eager")).eval()
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not missing and not unexpected, (missing, unexpected)
+    return m
+
+
+def golden_wav2vec2():
+    from . import synth
+    sd = synth.wav2vec2_state(0)
+    m = _ref_wav2vec2(sd)
+    out = {}
+    with torch.no_grad():
+        a1 = synth.audio(2, 16000, seed=1234)
+        out["hs_1s"] = m(a1, "vocaset").last_hidden_state.numpy()                 # [2,24,768]
+        out["hs_1s_frame20"] = m(a1, "vocaset", frame_num=20).last_hidden_state.numpy()
+        a4 = synth.audio(1, 64000, seed=1234)
+        out["hs_4s"] = m(a4, "vocaset").last_hidden_state.numpy()                 # [1,99,768] (config C1)
+        feats = m.feature_extractor(a1)                                            # [2,512,49]
+        out["feats_1s"] = feats.numpy()
+    np.savez(os.path.join(GOLD, "w2v.npz"), **out)
+    print("w2v.npz", {k: v.shape for k, v in out.items()})
+
+
+def _import_faceformer():
+    _paths()
+    import gdl.models.DecaFLAME  # noqa: F401  (real module, imported before the stubs go in)
+    stubs = ["easydict", "omegaconf", "scripts", "scripts.meshio", "visualize", "visualize.flame_visualization",
+             "gdl.layers", "gdl.layers.losses", "gdl.layers.losses.DecaLosses", "gdl.utils.DecaUtils",
+             "gdl.models.DECA", "third_party", "third_party.pirender", "third_party.pirender.generators",
+             "third_party.pirender.generators.face_model", "third_party.pirender.config",
+             "third_party.pirender.loss", "third_party.pirender.loss.perceptual",
+             "third_party.pirender.util", "third_party.pirender.util.meters"]
+    for s in stubs:
+        if s not in sys.modules:
+            sys.modules[s] = MagicMock(name=s)
+    import models.faceformer_disentangle as ffd
+    return ffd
+
+
+class _FanStub(nn.Module):
+    """Same 4-tuple API as FanEncoder.forward (pd_fgc_inference encoder.py:116-126). The images carry
+    the frame index in pixel [0,0,0,0]; embeddings come from oracle.synth.fan_embeddings."""
+
+    def __init__(self, emb):
+        super().__init__()
+        self.emb = emb
+
+    def forward(self, img):
+        i = int(round(float(img.reshape(img.shape[0], -1)[0, 0])))
+        return self.emb["head"][i:i + 1], self.emb["eye"][i:i + 1], self.emb["emo"][i:i + 1], None
+
+
+def build_reference_faceformer(ffd, fd, sd_ff, sd_w2v, template, fan_emb, period=30):
+    args = types.SimpleNamespace(dataset="vocaset", feature_dim=fd, vertice_dim=15069, period=period,
+                                 train_subjects="a b c d e f g h", device="cpu", is_concat_mode=0, load_mld=0)
+    m = ffd.Faceformer.__new__(ffd.Faceformer)
+    nn.Module.__init__(m)
+    m.args, m.dataset, m.device = args, "vocaset", "cpu"
+    m.audio_encoder = _ref_wav2vec2(sd_w2v)
+    m.audio_feature_map = nn.Linear(768, fd)
+    m.vertice_map = nn.Linear(15069, fd)
+    m.vertice_map_r = nn.Linear(fd, 15069)
+    m.obj_vector = nn.Linear(8, fd, bias=False)
+    m.PPE = ffd.PeriodicPositionalEncoding(fd, period=period)
+    m.biased_mask = ffd.init_biased_mask(n_head=4, max_seq_len=600, period=period)
+    layer = nn.TransformerDecoderLayer(d_model=fd, nhead=4, dim_feedforward=2 * fd, batch_first=True)
+    m.transformer_decoder = nn.TransformerDecoder(layer, num_layers=1)
+    m.v_merge2hidden = nn.Linear(36 + fd, fd)
+    m.learnable_eye_embed = nn.Parameter(torch.zeros(1, 1, 6))
+    m.template = template
+    m.fan_net = _FanStub(fan_emb)
+    own = {k: v for k, v in m.state_dict().items() if not k.startswith("audio_encoder.") and not k.startswith("PPE.")}
+    assert set(own) == set(sd_ff), (set(own) ^ set(sd_ff))
+    m.load_state_dict(sd_ff, strict=False)
+    ffd.mask_lip = lambda x: x  # image-space lip masking (cv2); the stub ignores pixel content
+    return m.eval()
+
+
+def golden_faceformer():
+    from . import synth
+    ffd = _import_faceformer()
+    out = {}
+    # closed-form pieces
+    out["biased_mask_p30"] = ffd.init_biased_mask(4, 600, 30)[:, :64, :64].numpy()
+    out["biased_mask_p25_full_sum"] = np.array(
+        [torch.nan_to_num(ffd.init_biased_mask(4, 600, 25), neginf=0.0).double().sum().item()])
+    out["enc_dec_mask_voca"] = ffd.enc_dec_mask("cpu", "vocaset", 5, 7).numpy()
+    out["ppe_fd64_p30"] = ffd.PeriodicPositionalEncoding(64, period=30).pe[0, :70].numpy()
+
+    sd_w2v = synth.wav2vec2_state(0)
+    template = synth.flame_buffers()["v_template"].reshape(1, 1, 15069)
+    for fd in (64, 128):
+        sd_ff = synth.faceformer_state(fd=fd, seed=10 + fd)
+        a = synth.audio(1, 16000, seed=1234)                       # 1 s -> T=24
+        T = 24
+        emb = synth.fan_embeddings(T, seed=20)
+        m = build_reference_faceformer(ffd, fd, sd_ff, sd_w2v, template, emb)
+        frames = torch.zeros(T, 3, 4, 4)
+        frames[:, 0, 0, 0] = torch.arange(T).float()
+        v = m.predict(a, frames, frames, frames)                   # [1,24,15069]
+        out[f"predict_fd{fd}_sub"] = v[0, :, ::COL_STRIDE].numpy()
+        out[f"predict_fd{fd}_chk"] = checksum(v)
+        # teacher-forced branch of forward_ff on the same hidden states
+        with torch.no_grad():
+            ha = m.audio_feature_map(m.audio_encoder(a, "vocaset").last_hidden_state)
+            hs = torch.cat([m.learnable_eye_embed.expand(1, T, -1), emb["emo"][None], ha], -1)
+            obj = m.obj_vector(torch.eye(8)[:1])
+            gt = template + 1e-3 * torch.from_numpy(
+                np.random.default_rng(77).normal(size=(1, T, 15069)).astype(np.float32))
+            vt = m.forward_ff(gt, hs, obj, T, teacher_forcing=True)
+        out[f"tf_fd{fd}_sub"] = vt[0, :, ::COL_STRIDE].numpy()
+        out[f"tf_fd{fd}_chk"] = checksum(vt)
+    # config C1: 4 s clip, fd=64, full predict (T=99)
+    sd_ff = synth.faceformer_state(fd=64, seed=74)
+    a = synth.audio(1, 64000, seed=1234)
+    T = 99
+    emb = synth.fan_embeddings(T, seed=20)
+    m = build_reference_faceformer(ffd, 64, sd_ff, sd_w2v, template, emb)
+    frames = torch.zeros(T, 3, 4, 4)
+    frames[:, 0, 0, 0] = torch.arange(T).float()
+    v = m.predict(a, frames, frames, frames)
+    out["predict_c1_sub"] = v[0, :, ::COL_STRIDE].numpy()
+    out["predict_c1_chk"] = checksum(v)
+    # loop_utils.loopback_frames index pattern
+    from loop_utils import calc_loop_idx
+    out["loop_idx_5_17"] = np.array([calc_loop_idx(i, 5) for i in range(17)])
+    np.savez(os.path.join(GOLD, "faceformer.npz"), **out)
+    print("faceformer.npz", {k: v.shape for k, v in out.items()})
+
+
+def main():
+    _paths()
+    os.makedirs(GOLD, exist_ok=True)
+    torch.set_num_threads(8)
+    golden_flame()
+    golden_wav2vec2()
+    golden_faceformer()
+
+
+if __name__ == "__main__":
+    main()

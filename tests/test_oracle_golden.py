@@ -1,0 +1,130 @@
+"""The CPU oracle against the golden vectors minted from the reference's own classes
+(oracle/make_golden.py).  This is what pins the oracle (prompt section 3)."""
+import numpy as np
+import torch
+
+from oracle import faceformer_oracle as ffo
+from oracle import flame_oracle as fo
+from oracle import synth
+from oracle import wav2vec2_oracle as wo
+from oracle.make_golden import COL_STRIDE, checksum
+
+
+def test_flame_matches_reference(golden):
+    g = golden("flame")
+    for n_shape, tag in ((100, "a"), (300, "b")):
+        buf = synth.flame_buffers(n_shape, 50)
+        p = synth.flame_params(4, n_shape=n_shape, seed=3)
+        res = fo.flame_forward(buf, p["shape"], p["exp"], p["pose"], p["eye"], mediapipe=(n_shape == 100))
+        np.testing.assert_allclose(res[0].numpy(), g[f"verts_{tag}"], atol=1e-6, rtol=0)
+        np.testing.assert_allclose(res[1].numpy(), g[f"lmk2d_{tag}"], atol=1e-6, rtol=0)
+        np.testing.assert_allclose(res[2].numpy(), g[f"lmk3d_{tag}"], atol=1e-6, rtol=0)
+        if n_shape == 100:
+            np.testing.assert_allclose(res[3].numpy(), g["lmkmp_a"], atol=1e-6, rtol=0)
+        pose = p["pose"].clone()
+        pose[:, :3] = 0
+        v = fo.flame_forward(buf, p["shape"], p["exp"], pose)[0]
+        np.testing.assert_allclose(v.numpy(), g[f"verts_jawonly_{tag}"], atol=1e-6, rtol=0)
+
+
+def test_gdl_lbs_copy_matches(golden):
+    g = golden("flame")
+    buf = synth.flame_buffers(100, 50)
+    p = synth.flame_params(2, seed=5)
+    betas = torch.cat([p["shape"], p["exp"]], 1)
+    full_pose = torch.cat([p["pose"][:, :3], torch.zeros(2, 3), p["pose"][:, 3:], p["eye"]], 1)
+    v, J = fo.lbs(betas, full_pose, buf["v_template"], buf["shapedirs"], buf["posedirs"], buf["J_regressor"],
+                  buf["parents"], buf["lbs_weights"])
+    np.testing.assert_allclose(v.numpy(), g["gdl_lbs_verts"], atol=1e-6, rtol=0)
+    np.testing.assert_allclose(J.numpy(), g["gdl_lbs_joints"], atol=1e-6, rtol=0)
+
+
+def test_flame_identities():
+    """Known-answer cases: zero everything => template; zero pose => pure blendshape."""
+    buf = synth.flame_buffers(100, 50)
+    z = torch.zeros(2, 100)
+    v = fo.flame_forward(buf, z, torch.zeros(2, 50), torch.zeros(2, 6))[0]
+    np.testing.assert_allclose(v.numpy(), buf["v_template"][None].expand(2, -1, -1).numpy(), atol=2e-7)
+    p = synth.flame_params(2, seed=9)
+    v = fo.flame_forward(buf, p["shape"], p["exp"], torch.zeros(2, 6))[0]
+    want = buf["v_template"] + torch.einsum("bl,mkl->bmk", torch.cat([p["shape"], p["exp"]], 1), buf["shapedirs"])
+    np.testing.assert_allclose(v.numpy(), want.numpy(), atol=5e-7)
+
+
+def test_wav2vec2_matches_reference(golden):
+    g = golden("w2v")
+    sd = synth.wav2vec2_state(0)
+    a1 = synth.audio(2, 16000, seed=1234)
+    np.testing.assert_allclose(wo.feature_extractor(sd, a1).numpy(), g["feats_1s"], atol=2e-5, rtol=0)
+    np.testing.assert_allclose(wo.wav2vec2_forward(sd, a1).numpy(), g["hs_1s"], atol=3e-5, rtol=0)
+    np.testing.assert_allclose(wo.wav2vec2_forward(sd, a1, frame_num=20).numpy(), g["hs_1s_frame20"], atol=3e-5, rtol=0)
+    a4 = synth.audio(1, 64000, seed=1234)
+    assert wo.output_frames(64000) == 99 and wo.output_frames(160000) == 249
+    np.testing.assert_allclose(wo.wav2vec2_forward(sd, a4).numpy(), g["hs_4s"], atol=3e-5, rtol=0)
+
+
+def test_masks_and_ppe_match_reference(golden):
+    g = golden("faceformer")
+    m = ffo.init_biased_mask(4, 600, 30)
+    np.testing.assert_array_equal(m[:, :64, :64].numpy(), g["biased_mask_p30"])
+    s = torch.nan_to_num(ffo.init_biased_mask(4, 600, 25), neginf=0.0).double().sum().item()
+    assert s == g["biased_mask_p25_full_sum"][0]
+    np.testing.assert_array_equal(ffo.enc_dec_mask("vocaset", 5, 7).numpy(), g["enc_dec_mask_voca"])
+    np.testing.assert_array_equal(ffo.ppe_table(64, 30)[0, :70].numpy(), g["ppe_fd64_p30"])
+    # closed form used by the CUDA kernels: mask[h,i,j] = -slope_h * floor((i-j)/period), j<=i
+    i = torch.arange(600)[:, None]
+    j = torch.arange(600)[None]
+    slopes = torch.tensor(ffo.get_slopes(4))
+    closed = torch.where(j <= i, -slopes[:, None, None] * ((i - j) // 30).float()[None], torch.tensor(float("-inf")))
+    assert torch.equal(closed, m)
+    assert ffo.get_slopes(4) == [2 ** -2, 2 ** -4, 2 ** -6, 2 ** -8]
+
+
+def _ff_inputs(fd, seed, n_samples, T):
+    sd_w2v = synth.wav2vec2_state(0)
+    sd_ff = synth.faceformer_state(fd=fd, seed=seed)
+    template = synth.flame_buffers()["v_template"].reshape(1, 1, 15069)
+    a = synth.audio(1, n_samples, seed=1234)
+    emb = synth.fan_embeddings(T, seed=20)
+    return sd_w2v, sd_ff, template, a, emb
+
+
+def test_predict_matches_reference(golden):
+    g = golden("faceformer")
+    for fd in (64, 128):
+        sd_w2v, sd_ff, template, a, emb = _ff_inputs(fd, 10 + fd, 16000, 24)
+        v = ffo.predict(sd_ff, sd_w2v, template, a, emb["emo"][None])
+        np.testing.assert_allclose(v[0, :, ::COL_STRIDE].numpy(), g[f"predict_fd{fd}_sub"], atol=2e-6, rtol=0)
+        np.testing.assert_allclose(checksum(v), g[f"predict_fd{fd}_chk"], rtol=1e-5)
+        # KV-cached O(T) restatement == literal O(T^2) loop
+        vc = ffo.predict(sd_ff, sd_w2v, template, a, emb["emo"][None], cached=True)
+        np.testing.assert_allclose(vc.numpy(), v.numpy(), atol=2e-6, rtol=0)
+
+
+def test_teacher_forced_matches_reference(golden):
+    g = golden("faceformer")
+    for fd in (64, 128):
+        sd_w2v, sd_ff, template, a, emb = _ff_inputs(fd, 10 + fd, 16000, 24)
+        T = 24
+        ha = wo.wav2vec2_forward(sd_w2v, a)
+        ha = torch.nn.functional.linear(ha, sd_ff["audio_feature_map.weight"], sd_ff["audio_feature_map.bias"])
+        hs = torch.cat([sd_ff["learnable_eye_embed"].expand(1, T, -1), emb["emo"][None], ha], -1)
+        obj = torch.nn.functional.linear(torch.eye(8)[:1], sd_ff["obj_vector.weight"])
+        gt = template + 1e-3 * torch.from_numpy(
+            np.random.default_rng(77).normal(size=(1, T, 15069)).astype(np.float32))
+        vt = ffo.forward_ff(sd_ff, template, hs, obj, T, teacher_forcing=True, gt_verts=gt)
+        np.testing.assert_allclose(vt[0, :, ::COL_STRIDE].numpy(), g[f"tf_fd{fd}_sub"], atol=2e-6, rtol=0)
+
+
+def test_predict_c1_matches_reference(golden):
+    """BASELINE config 1: one 4 s clip, batch 1, fd=64 (T=99), via the O(T) restatement."""
+    g = golden("faceformer")
+    sd_w2v, sd_ff, template, a, emb = _ff_inputs(64, 74, 64000, 99)
+    v = ffo.predict(sd_ff, sd_w2v, template, a, emb["emo"][None], cached=True)
+    np.testing.assert_allclose(v[0, :, ::COL_STRIDE].numpy(), g["predict_c1_sub"], atol=3e-6, rtol=0)
+
+
+def test_loopback_frames(golden):
+    from avi_talking_b200.loop_utils import calc_loop_idx
+    g = golden("faceformer")
+    assert [calc_loop_idx(i, 5) for i in range(17)] == list(g["loop_idx_5_17"])
