@@ -1,0 +1,80 @@
+// Shared helpers for the libavi_b200 kernels (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/avi_b200.h"
+
+namespace avi {
+
+constexpr int kNumSMs = 148;  // B200
+
+void set_error(const char* fmt, ...);
+extern std::atomic<int64_t> g_launches;
+
+inline int check_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return 1;
+  }
+  return 0;
+}
+
+#define AVI_REQUIRE(cond, ...)      \
+  do {                              \
+    if (!(cond)) {                  \
+      avi::set_error(__VA_ARGS__);  \
+      return 2;                     \
+    }                               \
+  } while (0)
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Block-wide sum of two values (blockDim.x multiple of 32, <= 1024). red must hold 64 floats.
+__device__ __forceinline__ void block_sum2(float& a, float& b, float* red) {
+  a = warp_sum(a);
+  b = warp_sum(b);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (l == 0) {
+    red[w] = a;
+    red[32 + w] = b;
+  }
+  __syncthreads();
+  a = (l < nw) ? red[l] : 0.f;
+  b = (l < nw) ? red[32 + l] : 0.f;
+  a = warp_sum(a);
+  b = warp_sum(b);
+}
+
+__device__ __forceinline__ float load_as_float(const void* p, int dtype, int64_t i) {
+  return dtype == AVI_DT_BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i])
+                              : reinterpret_cast<const float*>(p)[i];
+}
+__device__ __forceinline__ void store_from_float(void* p, int dtype, int64_t i, float v) {
+  if (dtype == AVI_DT_BF16)
+    reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
+  else
+    reinterpret_cast<float*>(p)[i] = v;
+}
+
+}  // namespace avi

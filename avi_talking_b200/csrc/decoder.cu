@@ -1,0 +1,265 @@
+// FaceFormer decoder kernels (Path A), models/faceformer_disentangle.py:
+//   * avi_ff_decoder_ar  - the autoregressive branch of forward_ff (:461-476) as ONE persistent kernel per clip:
+//     KV-cached (causal => O(T) instead of the reference's O(T^2) prefix recomputation), temporal bias
+//     -slope_h*floor((i-j)/period) (init_biased_mask :56-77) built on the fly, degenerate alignment-masked
+//     cross-attention (enc_dec_mask :80-88 leaves one key => out_proj(v_proj(mem_t))) precomputed by GEMMs,
+//     feedback through the composed vertice_map o vertice_map_r map.
+//   * avi_ff_biased_attn - biased causal self-attention over a whole sequence (teacher-forced branch :445-458).
+// nn.TransformerDecoderLayer semantics: post-LN, ReLU FFN, eps 1e-5 (torch defaults, :195-196).
+#include "common.cuh"
+
+namespace avi {
+
+constexpr int DEC_THREADS = 256;
+constexpr int DEC_NH = 4;
+
+// y[o] = b[o] + sum_k Wt[k*OUT + o] * x[k]   (Wt is the nn.Linear weight transposed: [IN, OUT], coalesced over o)
+// All DEC_THREADS threads must call. x, y in shared memory; red = scratch of DEC_THREADS floats.
+__device__ __forceinline__ void matvec(const float* __restrict__ Wt, const float* __restrict__ b, const float* x, float* y,
+                                       float* red, int IN, int OUT, bool relu) {
+  const int tid = threadIdx.x;
+  if (OUT * 2 <= DEC_THREADS) {
+    const int S = DEC_THREADS / OUT;  // k-split
+    const int g = tid / OUT, o = tid % OUT;
+    float acc = 0.f;
+    if (g < S) {
+      const int k0 = (IN * g) / S, k1 = (IN * (g + 1)) / S;
+#pragma unroll 4
+      for (int k = k0; k < k1; ++k) acc = fmaf(__ldg(Wt + (int64_t)k * OUT + o), x[k], acc);
+    }
+    red[tid] = acc;
+    __syncthreads();
+    if (tid < OUT) {
+      float s = b ? b[tid] : 0.f;
+      for (int q = 0; q < S; ++q) s += red[q * OUT + tid];
+      y[tid] = relu ? fmaxf(s, 0.f) : s;
+    }
+  } else {
+    for (int o = tid; o < OUT; o += DEC_THREADS) {
+      float acc = b ? b[o] : 0.f;
+#pragma unroll 4
+      for (int k = 0; k < IN; ++k) acc = fmaf(__ldg(Wt + (int64_t)k * OUT + o), x[k], acc);
+      y[o] = relu ? fmaxf(acc, 0.f) : acc;
+    }
+  }
+  __syncthreads();
+}
+
+// y = LayerNorm(a + r) * w + b over fd elements (fd <= 256), computed by warp 0; all threads must call.
+__device__ __forceinline__ void add_layernorm(const float* a, const float* r, const float* __restrict__ w,
+                                              const float* __restrict__ b, float* y, int fd) {
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    float v[8];
+    float s = 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int c = lane + 32 * u;
+      v[u] = (c < fd) ? a[c] + r[c] : 0.f;
+      s += v[u];
+    }
+    const float mean = warp_sum(s) / fd;
+    float q = 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int c = lane + 32 * u;
+      if (c < fd) q += (v[u] - mean) * (v[u] - mean);
+    }
+    const float rstd = rsqrtf(warp_sum(q) / fd + 1e-5f);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int c = lane + 32 * u;
+      if (c < fd) y[c] = (v[u] - mean) * rstd * w[c] + b[c];
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ float head_slope(int h) { return exp2f(-2.0f * (float)(h + 1)); }  // 4 heads: 2^-2,2^-4,2^-6,2^-8
+
+__global__ void __launch_bounds__(DEC_THREADS, 1)
+ff_decoder_ar_kernel(const AviDecoderWeights w, const float* __restrict__ cross, const float* __restrict__ style,
+                     float* __restrict__ hidden_out, float* __restrict__ kv_scratch, int T, int fd, int period, int kv_in_smem) {
+  extern __shared__ float sm[];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int dff = 2 * fd, hd = fd / DEC_NH;
+  const int kvs = fd + 1;  // padded row stride (bank-conflict-free column walks)
+  float* xs = sm;               // [fd]    layer input
+  float* qkv = xs + fd;         // [3fd]
+  float* att = qkv + 3 * fd;    // [fd]    attention output (pre out_proj)
+  float* t0 = att + fd;         // [fd]
+  float* x1 = t0 + fd;          // [fd]
+  float* hbuf = x1 + fd;        // [dff]
+  float* emb = hbuf + dff;      // [fd]    next input embedding
+  float* sty = emb + fd;        // [fd]
+  float* red = sty + fd;        // [DEC_THREADS]
+  float* prob = red + DEC_THREADS;         // [NH][T]
+  float* Kc = prob + DEC_NH * T;            // [T][kvs] (smem) or global
+  float* Vc = Kc + (size_t)T * kvs;
+  if (!kv_in_smem) {
+    Kc = kv_scratch + (size_t)b * 2 * T * kvs;
+    Vc = Kc + (size_t)T * kvs;
+  }
+  const float inv_sqrt_hd = rsqrtf((float)hd);
+  for (int c = tid; c < fd; c += DEC_THREADS) {
+    sty[c] = style[(int64_t)b * fd + c];
+    emb[c] = sty[c];
+  }
+  __syncthreads();
+
+  for (int i = 0; i < T; ++i) {
+    // ---- PPE: x = emb + pe[i mod period]  (:466-468; pe repeats with period, PeriodicPositionalEncoding :92-107)
+    for (int c = tid; c < fd; c += DEC_THREADS) xs[c] = emb[c] + w.pe[(i % period) * fd + c];
+    __syncthreads();
+    // ---- self-attention in_proj -> q | k | v
+    matvec(w.sa_in_w, w.sa_in_b, xs, qkv, red, fd, 3 * fd, false);
+    for (int c = tid; c < fd; c += DEC_THREADS) {
+      Kc[(size_t)i * kvs + c] = qkv[fd + c];
+      Vc[(size_t)i * kvs + c] = qkv[2 * fd + c];
+    }
+    __syncthreads();
+    // ---- scores: head h handled by 64 threads, keys strided by 64
+    {
+      const int h = tid >> 6, jl = tid & 63;
+      const float slope = head_slope(h);
+      const float* q = qkv + h * hd;
+      float mx = -INFINITY;
+      for (int j = jl; j <= i; j += 64) {
+        const float* kr = Kc + (size_t)j * kvs + h * hd;
+        float s = 0.f;
+        for (int d = 0; d < hd; ++d) s = fmaf(q[d], kr[d], s);
+        s = s * inv_sqrt_hd - slope * (float)((i - j) / period);
+        prob[h * T + j] = s;
+        mx = fmaxf(mx, s);
+      }
+      mx = warp_max(mx);
+      if ((tid & 31) == 0) red[tid >> 5] = mx;
+      __syncthreads();
+      mx = fmaxf(red[(tid >> 6) * 2], red[(tid >> 6) * 2 + 1]);
+      float sum = 0.f;
+      for (int j = jl; j <= i; j += 64) {
+        const float e = expf(prob[h * T + j] - mx);
+        prob[h * T + j] = e;
+        sum += e;
+      }
+      sum = warp_sum(sum);
+      __syncthreads();
+      if ((tid & 31) == 0) red[8 + (tid >> 5)] = sum;
+      __syncthreads();
+      const float inv = 1.f / (red[8 + (tid >> 6) * 2] + red[8 + (tid >> 6) * 2 + 1]);
+      for (int j = jl; j <= i; j += 64) prob[h * T + j] *= inv;
+      __syncthreads();
+    }
+    // ---- att[c] = sum_j p[h(c)][j] * V[j][c] : DEC_THREADS/fd key groups, then reduce
+    {
+      const int G = DEC_THREADS / fd >= 1 ? DEC_THREADS / fd : 1;
+      if (fd <= DEC_THREADS) {
+        const int g = tid / fd, c = tid % fd;
+        float acc = 0.f;
+        if (g < G) {
+          const float* pr = prob + (c / hd) * T;
+          for (int j = g; j <= i; j += G) acc = fmaf(pr[j], Vc[(size_t)j * kvs + c], acc);
+        }
+        red[tid] = acc;
+        __syncthreads();
+        if (tid < fd) {
+          float s = 0.f;
+          for (int q = 0; q < G; ++q) s += red[q * fd + tid];
+          att[tid] = s;
+        }
+        __syncthreads();
+      }
+    }
+    // ---- out_proj, residual, LN1
+    matvec(w.sa_out_w, w.sa_out_b, att, t0, red, fd, fd, false);
+    add_layernorm(xs, t0, w.ln1_w, w.ln1_b, x1, fd);
+    // ---- cross-attention term (precomputed), LN2
+    for (int c = tid; c < fd; c += DEC_THREADS) t0[c] = cross[((int64_t)b * T + i) * fd + c];
+    __syncthreads();
+    add_layernorm(x1, t0, w.ln2_w, w.ln2_b, xs, fd);
+    // ---- FFN, LN3
+    matvec(w.ff1_w, w.ff1_b, xs, hbuf, red, fd, dff, true);
+    matvec(w.ff2_w, w.ff2_b, hbuf, t0, red, dff, fd, false);
+    add_layernorm(xs, t0, w.ln3_w, w.ln3_b, x1, fd);
+    for (int c = tid; c < fd; c += DEC_THREADS) hidden_out[((int64_t)b * T + i) * fd + c] = x1[c];
+    // ---- feedback: emb_{i+1} = vertice_map(vertice_map_r(y_i)) + style   (:473-476), composed map
+    if (i + 1 < T) {
+      matvec(w.fb_w, w.fb_b, x1, t0, red, fd, fd, false);
+      for (int c = tid; c < fd; c += DEC_THREADS) emb[c] = t0[c] + sty[c];
+    }
+    __syncthreads();
+  }
+}
+
+// Biased causal self-attention for a whole sequence (teacher forcing): one warp per (clip, head, query row).
+// qkv [B,T,3fd] fp32 -> out [B,T,fd].
+__global__ void __launch_bounds__(128) ff_biased_attn_kernel(const float* __restrict__ qkv, float* __restrict__ out, int B, int T,
+                                                             int fd, int period) {
+  extern __shared__ float sm[];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t gw = (int64_t)blockIdx.x * 4 + wib;
+  if (gw >= (int64_t)B * DEC_NH * T) return;
+  const int i = (int)(gw % T);
+  const int h = (int)((gw / T) % DEC_NH);
+  const int b = (int)(gw / ((int64_t)T * DEC_NH));
+  const int hd = fd / DEC_NH;
+  float* p = sm + wib * T;
+  const float* base = qkv + (int64_t)b * T * 3 * fd;
+  const float* q = base + (int64_t)i * 3 * fd + h * hd;
+  const float slope = head_slope(h);
+  const float sc = rsqrtf((float)hd);
+  float mx = -INFINITY;
+  for (int j = lane; j <= i; j += 32) {
+    const float* kr = base + (int64_t)j * 3 * fd + fd + h * hd;
+    float s = 0.f;
+    for (int d = 0; d < hd; ++d) s = fmaf(q[d], kr[d], s);
+    s = s * sc - slope * (float)((i - j) / period);
+    p[j] = s;
+    mx = fmaxf(mx, s);
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int j = lane; j <= i; j += 32) {
+    const float e = expf(p[j] - mx);
+    p[j] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  __syncwarp();
+  const float inv = 1.f / sum;
+  for (int d = lane; d < hd; d += 32) {
+    float acc = 0.f;
+    for (int j = 0; j <= i; ++j) acc = fmaf(p[j], base[(int64_t)j * 3 * fd + 2 * fd + h * hd + d], acc);
+    out[((int64_t)b * T + i) * fd + h * hd + d] = acc * inv;
+  }
+}
+
+}  // namespace avi
+
+using namespace avi;
+
+extern "C" int avi_ff_decoder_ar(const AviDecoderWeights* w, const float* cross, const float* style, float* hidden_out,
+                                 float* kv_scratch, int32_t B, int32_t T, int32_t fd, int32_t period, void* stream) {
+  AVI_REQUIRE(w != nullptr && B > 0 && T > 0 && period > 0, "avi_ff_decoder_ar: bad arguments");
+  AVI_REQUIRE(fd % 32 == 0 && fd >= 32 && fd <= 256 && DEC_THREADS % fd == 0, "avi_ff_decoder_ar: feature_dim %d unsupported (32/64/128/256)", fd);
+  const size_t fixed = sizeof(float) * ((size_t)fd * 9 + 2 * fd + DEC_THREADS + (size_t)DEC_NH * T);
+  const size_t kv = sizeof(float) * 2 * (size_t)T * (fd + 1);
+  int kv_in_smem = (fixed + kv <= 200 * 1024) ? 1 : 0;
+  AVI_REQUIRE(kv_in_smem || kv_scratch != nullptr, "avi_ff_decoder_ar: kv_scratch required for T=%d fd=%d", T, fd);
+  const size_t smem = fixed + (kv_in_smem ? kv : 0);
+  AVI_REQUIRE(smem <= 227 * 1024, "avi_ff_decoder_ar: sequence too long (T=%d)", T);
+  cudaError_t e = cudaFuncSetAttribute(ff_decoder_ar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  AVI_REQUIRE(e == cudaSuccess, "avi_ff_decoder_ar: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  ff_decoder_ar_kernel<<<B, DEC_THREADS, smem, (cudaStream_t)stream>>>(*w, cross, style, hidden_out, kv_scratch, T, fd, period,
+                                                                       kv_in_smem);
+  return check_launch("ff_decoder_ar");
+}
+
+extern "C" int avi_ff_biased_attn(const float* qkv, float* out, int32_t B, int32_t T, int32_t fd, int32_t period, void* stream) {
+  AVI_REQUIRE(B > 0 && T > 0 && fd % DEC_NH == 0 && period > 0, "avi_ff_biased_attn: bad arguments");
+  const int64_t warps = (int64_t)B * DEC_NH * T;
+  const size_t smem = sizeof(float) * 4 * (size_t)T;
+  AVI_REQUIRE(smem <= 48 * 1024, "avi_ff_biased_attn: T=%d too long", T);
+  ff_biased_attn_kernel<<<(unsigned)((warps + 3) / 4), 128, smem, (cudaStream_t)stream>>>(qkv, out, B, T, fd, period);
+  return check_launch("ff_biased_attn");
+}

@@ -1,0 +1,489 @@
+// bf16 tensor-core GEMM for sm_100a: tcgen05.mma (cta_group::1, M=128, N=256, K=16) with the accumulator in TMEM,
+// operands staged in shared memory by TMA (SWIZZLE_128B, K-major), a 4-stage mbarrier ring, two TMEM accumulator
+// stages so the epilogue of tile i overlaps the MMAs of tile i+1, persistent over the SMs.
+//
+//   C[b, r, n] = epi( sum_k A[b, r, k] * W[n, k] + bias[n] ) (+ residual[b, r, n])
+//
+// A is addressed through a 4-D tensor map (channel, phase, super-row, clip) so that a strided Conv1d over
+// time-major activations is the same code path as a plain GEMM: output row r, tap j reads input row
+// r*stride + j = super-row (r + j/stride), phase (j % stride).
+//
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..9 = epilogue
+// (TMEM lane quarter = warp_id % 4, column half = (warp_id - 2) / 4).
+#include <cuda.h>
+
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+
+namespace avi {
+
+constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 64, TC_STAGES = 4, TC_UMMA_K = 16;
+constexpr int TC_THREADS = 320, TC_EPI_WARPS = 8;
+constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 2;   // 16 KB
+constexpr uint32_t TC_B_BYTES = TC_BN * TC_BK * 2;   // 32 KB
+constexpr uint32_t TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
+constexpr uint32_t TC_TRANS_BYTES = TC_EPI_WARPS * 32 * 17 * 4;  // per-warp 32x17 fp32 transpose tiles (unaligned outputs)
+constexpr uint32_t TC_BIAS_BYTES = 2 * TC_BN * 4;
+constexpr uint32_t TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + TC_TRANS_BYTES + TC_BIAS_BYTES + 256 /*barriers*/ + 1024 /*align*/;
+static_assert(TC_SMEM_BYTES <= 232448, "shared memory budget");
+
+struct TcParams {
+  const float* bias;
+  const float* residual;
+  void* C;
+  void* C2;
+  int c_dtype;  // dtype of C; C2 (if any) is the other one
+  int act;
+  int batch, rows, N;
+  int num_kb;           // K / 64
+  int kb_per_tap;       // C_in / 64
+  int conv_stride;
+  int m_tiles, n_tiles, total_tiles;
+  int64_t c_ld, c_batch_stride, res_ld, res_batch_stride;
+  int vec_ok;           // outputs (and residual) are 16-byte addressable per 32-column chunk
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) break;
+    if (clock64() - t0 > 8000000000LL) {  // ~4 s: a protocol bug must not hang the GPU
+      printf("avi gemm_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, SWIZZLE_128B operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart (cute::UMMA::SmemDescriptor).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);   // start address           bits [0,14)
+  d |= (uint64_t)1 << 16;                        // leading byte offset (unused for swizzled K-major) [16,30)
+  d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset      bits [32,46)
+  d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                        // layout type: SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]),
+        "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]),
+        "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == AVI_ACT_GELU) return gelu_erf(v);
+  if (act == AVI_ACT_RELU) return fmaxf(v, 0.f);
+  return v;
+}
+
+// ---------------------------------------------------------------- kernel
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + TC_STAGES * TC_A_BYTES;
+  float* trans = reinterpret_cast<float*>(smem + TC_STAGES * TC_STAGE_BYTES);
+  float* sbias = reinterpret_cast<float*>(smem + TC_STAGES * TC_STAGE_BYTES + TC_TRANS_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES + TC_TRANS_BYTES + TC_BIAS_BYTES);
+  uint64_t* full_bar = bars;                        // [STAGES]
+  uint64_t* empty_bar = bars + TC_STAGES;           // [STAGES]
+  uint64_t* tmem_full = bars + 2 * TC_STAGES;       // [2]
+  uint64_t* tmem_empty = bars + 2 * TC_STAGES + 2;  // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&tmem_full[s]), 1);
+      mbar_init(smem_u32(&tmem_empty[s]), TC_EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // whole warp: allocate all 512 TMEM columns (2 accumulator stages x 256)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const int n_blk = t % p.n_tiles;
+        const int mt = t / p.n_tiles;
+        const int b = mt / p.m_tiles, m_blk = mt % p.m_tiles;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          const uint32_t fb = smem_u32(&full_bar[stage]);
+          mbar_expect_tx(fb, TC_STAGE_BYTES);
+          const int tap = kb / p.kb_per_tap, c0 = (kb % p.kb_per_tap) * TC_BK;
+          tma_load_4d(smem_u32(smem_a + stage * TC_A_BYTES), &map_a, fb, c0, tap % p.conv_stride,
+                      m_blk * TC_BM + tap / p.conv_stride, b);
+          tma_load_2d(smem_u32(smem_b + stage * TC_B_BYTES), &map_w, fb, kb * TC_BK, n_blk * TC_BN);
+          if (++stage == TC_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, both K-major, N=256, M=128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(smem_u32(&tmem_empty[as]), aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * TC_BN;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          tc_fence_after();
+          const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + stage * TC_A_BYTES));
+          const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + stage * TC_B_BYTES));
+#pragma unroll
+          for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
+            // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(smem_u32(&empty_bar[stage]));  // frees the smem slot once these MMAs have read it
+          if (++stage == TC_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(smem_u32(&tmem_full[as]));  // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    const int ew = warp - 2;              // 0..7
+    const int quarter = warp & 3;         // TMEM lanes [32*quarter, +32) are the only ones this warp may touch
+    const int half = ew >> 2;             // columns [128*half, +128)
+    const int etid = threadIdx.x - 64;    // 0..255
+    float* my_trans = trans + ew * (32 * 17);
+    int it = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int n_blk = t % p.n_tiles;
+      const int mt = t / p.n_tiles;
+      const int b = mt / p.m_tiles, m_blk = mt % p.m_tiles;
+      const int n0 = n_blk * TC_BN;
+      // stage the bias slice for this tile (double-buffered with the accumulator stage)
+      {
+        const int n = n0 + etid;
+        sbias[as * TC_BN + etid] = (p.bias != nullptr && n < p.N) ? p.bias[n] : 0.f;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      mbar_wait(smem_u32(&tmem_full[as]), aphase);
+      tc_fence_after();
+      const int row = m_blk * TC_BM + quarter * 32 + lane;
+      const bool row_ok = row < p.rows;
+      const int64_t c_off = (int64_t)b * p.c_batch_stride + (int64_t)row * p.c_ld;
+      const int64_t r_off = (int64_t)b * p.res_batch_stride + (int64_t)row * p.res_ld;
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        const int col0 = half * 128 + ch * 32;
+        if (n0 + col0 >= p.N) break;  // warp-uniform
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * TC_BN + col0), v);
+        float f[32];
+        const float4* bs = reinterpret_cast<const float4*>(sbias + as * TC_BN + col0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 bb = bs[j];
+          f[4 * j + 0] = apply_act(__uint_as_float(v[4 * j + 0]) + bb.x, p.act);
+          f[4 * j + 1] = apply_act(__uint_as_float(v[4 * j + 1]) + bb.y, p.act);
+          f[4 * j + 2] = apply_act(__uint_as_float(v[4 * j + 2]) + bb.z, p.act);
+          f[4 * j + 3] = apply_act(__uint_as_float(v[4 * j + 3]) + bb.w, p.act);
+        }
+        const int n_base = n0 + col0;
+        if (p.vec_ok && n_base + 32 <= p.N) {
+          if (row_ok) {
+            if (p.residual) {
+              const float4* rp = reinterpret_cast<const float4*>(p.residual + r_off + n_base);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 rr = __ldg(rp + j);
+                f[4 * j + 0] += rr.x;
+                f[4 * j + 1] += rr.y;
+                f[4 * j + 2] += rr.z;
+                f[4 * j + 3] += rr.w;
+              }
+            }
+            float* cf = nullptr;
+            __nv_bfloat16* cb = nullptr;
+            if (p.c_dtype == AVI_DT_F32) {
+              cf = reinterpret_cast<float*>(p.C);
+              cb = reinterpret_cast<__nv_bfloat16*>(p.C2);
+            } else {
+              cb = reinterpret_cast<__nv_bfloat16*>(p.C);
+              cf = reinterpret_cast<float*>(p.C2);
+            }
+            if (cf) {
+              float4* o = reinterpret_cast<float4*>(cf + c_off + n_base);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            }
+            if (cb) {
+              uint4* o = reinterpret_cast<uint4*>(cb + c_off + n_base);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(f[8 * j + 0], f[8 * j + 1]);
+                __nv_bfloat162 h1 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]);
+                __nv_bfloat162 h3 = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
+                uint4 u;
+                u.x = *reinterpret_cast<uint32_t*>(&h0);
+                u.y = *reinterpret_cast<uint32_t*>(&h1);
+                u.z = *reinterpret_cast<uint32_t*>(&h2);
+                u.w = *reinterpret_cast<uint32_t*>(&h3);
+                o[j] = u;
+              }
+            }
+          }
+        } else {
+          // unaligned rows / ragged N: transpose the warp's 32x32 block through smem (two 16-column passes) so that
+          // each store instruction writes 16 consecutive elements of two output rows (coalesced 64-byte runs)
+          const int row_base = m_blk * TC_BM + quarter * 32;
+#pragma unroll
+          for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) my_trans[lane * 17 + j] = f[pass * 16 + j];
+            __syncwarp();
+            const int n = n_base + pass * 16 + (lane & 15);
+            for (int r2 = 0; r2 < 16; ++r2) {
+              const int r = 2 * r2 + (lane >> 4);
+              const int rr = row_base + r;
+              if (rr < p.rows && n < p.N) {
+                float val = my_trans[r * 17 + (lane & 15)];
+                const int64_t co = (int64_t)b * p.c_batch_stride + (int64_t)rr * p.c_ld + n;
+                if (p.residual) val += p.residual[(int64_t)b * p.res_batch_stride + (int64_t)rr * p.res_ld + n];
+                if (p.c_dtype == AVI_DT_F32) {
+                  reinterpret_cast<float*>(p.C)[co] = val;
+                  if (p.C2) reinterpret_cast<__nv_bfloat16*>(p.C2)[co] = __float2bfloat16_rn(val);
+                } else {
+                  reinterpret_cast<__nv_bfloat16*>(p.C)[co] = __float2bfloat16_rn(val);
+                  if (p.C2) reinterpret_cast<float*>(p.C2)[co] = val;
+                }
+              }
+            }
+            __syncwarp();
+          }
+        }
+      }
+      // release the accumulator stage back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tmem_empty[as]));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  });
+  return fn;
+}
+
+static int encode_map(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("gemm_bf16_tc: cuTensorMapEncodeTiled entry point not available");
+    return 1;
+  }
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bdim[5], estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+  }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("gemm_bf16_tc: cuTensorMapEncodeTiled failed (CUresult %d) rank=%d dims=[%llu,%llu,%llu,%llu] strides=[%llu,%llu,%llu]",
+              (int)r, rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+              (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0),
+              (unsigned long long)strides_bytes[0], (unsigned long long)(rank > 2 ? strides_bytes[1] : 0),
+              (unsigned long long)(rank > 3 ? strides_bytes[2] : 0));
+    return 1;
+  }
+  return 0;
+}
+
+static const char* tc_check(const AviGemmArgs* a) {
+  if (!a) return "null args";
+  if (a->a_dtype != AVI_DT_BF16) return "A/W must be bf16";
+  if (a->batch <= 0 || a->rows <= 0 || a->N <= 0 || a->K <= 0) return "bad shape";
+  if (a->conv_taps < 1 || a->conv_stride < 1) return "bad conv params";
+  if (a->K % a->conv_taps != 0) return "K must be taps * C_in";
+  const int cin = a->K / a->conv_taps;
+  if (cin % TC_BK != 0) return "C_in (K per tap) must be a multiple of 64";
+  if (a->conv_taps > 1 && a->a_ld != cin) return "conv mode needs a_ld == C_in";
+  if (a->a_ld % 8 != 0 || a->a_batch_stride % 8 != 0) return "a_ld and a_batch_stride must be multiples of 8 elements";
+  if (((uintptr_t)a->A | (uintptr_t)a->W) % 16 != 0) return "A and W must be 16-byte aligned";
+  if (a->a_rows_alloc < (int64_t)(a->rows - 1) * a->conv_stride + a->conv_taps) return "a_rows_alloc smaller than the rows read";
+  if (a->C == nullptr) return "C is null";
+  return nullptr;
+}
+
+}  // namespace avi
+
+using namespace avi;
+
+extern "C" int avi_gemm_bf16_tc_supported(const AviGemmArgs* a) { return tc_check(a) == nullptr ? 1 : 0; }
+
+extern "C" int avi_gemm_bf16_tc(const AviGemmArgs* a, void* stream) {
+  const char* why = tc_check(a);
+  AVI_REQUIRE(why == nullptr, "avi_gemm_bf16_tc: %s", why);
+  const int cin = a->K / a->conv_taps;
+  const int s = a->conv_stride;
+  CUtensorMap map_a, map_w;
+  {
+    // (channel, phase, super-row, clip)
+    const uint64_t q_rows = (uint64_t)(a->a_rows_alloc / s);
+    uint64_t dims[4] = {(uint64_t)cin, (uint64_t)s, q_rows, (uint64_t)a->batch};
+    uint64_t strides[3] = {(uint64_t)a->a_ld * 2, (uint64_t)a->a_ld * s * 2, (uint64_t)a->a_batch_stride * 2};
+    if (a->batch == 1) strides[2] = dims[2] * strides[1];  // unused; keep it well-formed
+    uint32_t box[4] = {TC_BK, 1, TC_BM, 1};
+    if (encode_map(&map_a, a->A, 4, dims, strides, box)) return 1;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->N};
+    uint64_t strides[1] = {(uint64_t)a->K * 2};
+    uint32_t box[2] = {TC_BK, TC_BN};
+    if (encode_map(&map_w, a->W, 2, dims, strides, box)) return 1;
+  }
+  TcParams p;
+  p.bias = a->bias;
+  p.residual = a->residual;
+  p.C = a->C;
+  p.C2 = a->C2;
+  p.c_dtype = a->c_dtype;
+  p.act = a->act;
+  p.batch = a->batch;
+  p.rows = a->rows;
+  p.N = a->N;
+  p.num_kb = a->K / TC_BK;
+  p.kb_per_tap = cin / TC_BK;
+  p.conv_stride = s;
+  p.m_tiles = (a->rows + TC_BM - 1) / TC_BM;
+  p.n_tiles = (a->N + TC_BN - 1) / TC_BN;
+  p.total_tiles = p.m_tiles * p.n_tiles * a->batch;
+  p.c_ld = a->c_ld;
+  p.c_batch_stride = a->c_batch_stride;
+  p.res_ld = a->res_ld;
+  p.res_batch_stride = a->res_batch_stride;
+  // vector path: every 32-column chunk of every row is 16-byte addressable in both output dtypes and the residual
+  bool vec = (a->c_ld % 8 == 0) && (a->c_batch_stride % 8 == 0) && ((uintptr_t)a->C % 16 == 0) &&
+             (a->C2 == nullptr || (uintptr_t)a->C2 % 16 == 0);
+  if (a->residual) vec = vec && (a->res_ld % 4 == 0) && (a->res_batch_stride % 4 == 0) && ((uintptr_t)a->residual % 16 == 0);
+  p.vec_ok = vec ? 1 : 0;
+
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(gemm_bf16_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
+  });
+  AVI_REQUIRE(attr_err == cudaSuccess, "avi_gemm_bf16_tc: cannot opt in to %u bytes of shared memory: %s", TC_SMEM_BYTES,
+              cudaGetErrorString(attr_err));
+  const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
+  gemm_bf16_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, (cudaStream_t)stream>>>(map_a, map_w, p);
+  return check_launch("gemm_bf16_tc");
+}

@@ -1,0 +1,298 @@
+"""Drop-in for models/faceformer_disentangle.py (and the audio-only models/faceformer_vert.py variant):
+``Faceformer`` with the reference's ``predict`` / ``forward_ff`` / ``convert_coeff2verts`` signatures and ``state_dict``
+keys, computed by libavi_b200.so, batched over clips (the reference loops clip by clip, :441-442).
+
+Reference arithmetic (A.3 of SURVEY.md):
+  hidden = v_merge2hidden(cat[eye(6), emo(30), audio_feature_map(wav2vec2(audio))])          :776,808,437
+  per frame i: x = emb_i + pe[i mod period]; biased causal self-attention (4 heads);            :466-472
+               cross-attention degenerates to out_proj(v_proj(hidden_i)) (one visible key, :80-88);
+               FFN; v_i = vertice_map_r(y_i); emb_{i+1} = vertice_map(v_i) + style                :473-476
+  output = v + template                                                                       :481
+"""
+from __future__ import annotations
+
+import math
+import types
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .loop_utils import loopback_frames
+from .ops import ACT_NONE, ACT_RELU, AviDecoderWeights
+from .wav2vec import Wav2Vec2Model, default_precision
+
+N_HEAD = 4
+MAX_SEQ_LEN = 600
+
+
+def get_slopes(n):
+    """ALiBi slopes (faceformer_disentangle.py:57-67); 4 heads -> [2^-2, 2^-4, 2^-6, 2^-8]."""
+    def pow2(n):
+        start = 2 ** (-2 ** -(math.log2(n) - 3))
+        return [start * start ** i for i in range(n)]
+    if math.log2(n).is_integer():
+        return pow2(n)
+    c = 2 ** math.floor(math.log2(n))
+    return pow2(c) + get_slopes(2 * c)[0::2][: n - c]
+
+
+def init_biased_mask(n_head, max_seq_len, period):
+    """Closed form of faceformer_disentangle.py:56-77: mask[h,i,j] = -slope_h*floor((i-j)/period) for j<=i, -inf above the
+    diagonal. Kept for API/state compatibility; the CUDA kernels build the same bias on the fly and never read this tensor."""
+    i = torch.arange(max_seq_len)[:, None]
+    j = torch.arange(max_seq_len)[None]
+    slopes = torch.tensor(get_slopes(n_head), dtype=torch.float32)
+    bias = -slopes[:, None, None] * torch.div(i - j, period, rounding_mode="floor").float()[None]
+    return torch.where(j <= i, bias, torch.tensor(float("-inf")))
+
+
+def enc_dec_mask(device, dataset, T, S):
+    """faceformer_disentangle.py:80-88 (True = masked), vectorised."""
+    mask = torch.ones(T, S, dtype=torch.bool, device=device)
+    i = torch.arange(T, device=device)
+    if dataset == "BIWI":
+        for d in (0, 1):
+            ok = i * 2 + d < S
+            mask[i[ok], (i * 2 + d)[ok]] = False
+    elif dataset == "vocaset":
+        ok = i < S
+        mask[i[ok], i[ok]] = False
+    return mask
+
+
+class PeriodicPositionalEncoding(nn.Module):
+    """faceformer_disentangle.py:92-107 (same ``pe`` buffer; dropout inactive in eval)."""
+
+    def __init__(self, d_model, dropout=0.1, period=25, max_seq_len=600):
+        super().__init__()
+        self.dropout = nn.Dropout(p=dropout)
+        pe = torch.zeros(period, d_model)
+        position = torch.arange(0, period, dtype=torch.float).unsqueeze(1)
+        div_term = torch.exp(torch.arange(0, d_model, 2).float() * (-math.log(10000.0) / d_model))
+        pe[:, 0::2] = torch.sin(position * div_term)
+        pe[:, 1::2] = torch.cos(position * div_term)
+        self.period = period
+        self.register_buffer("pe", pe.unsqueeze(0).repeat(1, max_seq_len // period + 1, 1))
+
+    def forward(self, x):
+        return self.dropout(x + self.pe[:, : x.size(1), :])
+
+
+class Faceformer(nn.Module):
+    """``Faceformer(args)`` as upstream (:158-337). Assets the upstream constructor reads from private paths / the network can be
+    injected instead: ``audio_encoder`` (a Wav2Vec2Model), ``flame`` (an avi_talking_b200.flame.FLAME_mediapipe), ``template``
+    ([1,1,V*3]), ``coeff_mean``/``coeff_std`` ([53]), ``fan_net``."""
+
+    variant = "disentangle"
+
+    def __init__(self, args, audio_encoder=None, flame=None, template=None, coeff_mean=None, coeff_std=None, fan_net=None):
+        super().__init__()
+        self.vertice_scale = 1.0
+        self.args = args
+        self.dataset = args.dataset
+        fd = args.feature_dim
+        if getattr(args, "is_concat_mode", 0) != 0:
+            raise NotImplementedError("is_concat_mode != 0 is not on the published path")
+        if audio_encoder is None:
+            audio_encoder = Wav2Vec2Model.from_pretrained("facebook/wav2vec2-base-960h")     # :168
+        self.audio_encoder = audio_encoder
+        self.audio_encoder.feature_extractor._freeze_parameters()                            # :170
+        self.audio_feature_map = nn.Linear(768, fd)
+        self.vertice_map = nn.Linear(args.vertice_dim, fd)
+        self.vertice_map_r = nn.Linear(fd, args.vertice_dim)
+        self.obj_vector = nn.Linear(len(args.train_subjects.split()), fd, bias=False)
+        self.PPE = PeriodicPositionalEncoding(fd, period=args.period)
+        self.biased_mask = init_biased_mask(n_head=N_HEAD, max_seq_len=MAX_SEQ_LEN, period=args.period)
+        dff = 2 * fd  # d_model + feature_dim (:195)
+        layer = nn.TransformerDecoderLayer(d_model=fd, nhead=N_HEAD, dim_feedforward=dff, batch_first=True)
+        self.transformer_decoder = nn.TransformerDecoder(layer, num_layers=1)
+        self.obj_embedding = nn.Parameter(torch.zeros(1, fd))
+        self.device = getattr(args, "device", "cuda")
+        nn.init.constant_(self.vertice_map_r.weight, 0)                                      # :201-202
+        nn.init.constant_(self.vertice_map_r.bias, 0)
+        self.flame = flame
+        if template is None and flame is not None:
+            template = flame.v_template.reshape(1, 1, args.vertice_dim) * self.vertice_scale   # :213
+        self.template = template
+        self.coeff_mean = None if coeff_mean is None else torch.as_tensor(coeff_mean).float().reshape(1, 1, -1)
+        self.coeff_std = None if coeff_std is None else torch.as_tensor(coeff_std).float().reshape(1, 1, -1)
+        self.fan_net = fan_net
+        if self.variant == "disentangle":
+            self.v_merge2hidden = nn.Linear(6 + 30 + fd, fd)                                 # :241
+            self.learnable_eye_embed = nn.Parameter(torch.zeros(1, 1, 6))                    # :327
+        self.precision = default_precision()
+        self._packed = None
+        self._packed_key = None
+
+    # ------------------------------------------------------------------ packing
+    def _own_params(self):
+        return [p for n, p in self.named_parameters() if not n.startswith("audio_encoder.") and not n.startswith("flame.")]
+
+    @torch.no_grad()
+    def _pack(self):
+        key = (self.precision,) + tuple((p.data_ptr(), p._version) for p in self._own_params()) + (self.PPE.pe.data_ptr(),)
+        if self._packed is not None and key == self._packed_key:
+            return self._packed
+        f32 = lambda t: t.detach().float().contiguous()  # noqa: E731
+        tr = lambda t: t.detach().float().t().contiguous()  # noqa: E731
+        lyr = self.transformer_decoder.layers[0]
+        fd = self.args.feature_dim
+        P = {}
+        # composed feedback map emb_{i+1} = W_m (W_r y + b_r) + b_m + style, composed in fp64 once
+        Wm, bm = self.vertice_map.weight.double(), self.vertice_map.bias.double()
+        Wr, br = self.vertice_map_r.weight.double(), self.vertice_map_r.bias.double()
+        P["fb_w"] = (Wm @ Wr).float().t().contiguous()
+        P["fb_b"] = (Wm @ br + bm).float().contiguous()
+        keep = {
+            "sa_in_w": tr(lyr.self_attn.in_proj_weight), "sa_in_b": f32(lyr.self_attn.in_proj_bias),
+            "sa_out_w": tr(lyr.self_attn.out_proj.weight), "sa_out_b": f32(lyr.self_attn.out_proj.bias),
+            "ff1_w": tr(lyr.linear1.weight), "ff1_b": f32(lyr.linear1.bias),
+            "ff2_w": tr(lyr.linear2.weight), "ff2_b": f32(lyr.linear2.bias),
+            "ln1_w": f32(lyr.norm1.weight), "ln1_b": f32(lyr.norm1.bias),
+            "ln2_w": f32(lyr.norm2.weight), "ln2_b": f32(lyr.norm2.bias),
+            "ln3_w": f32(lyr.norm3.weight), "ln3_b": f32(lyr.norm3.bias),
+            "fb_w": P["fb_w"], "fb_b": P["fb_b"],
+            "pe": f32(self.PPE.pe[0, : self.PPE.period]),
+        }
+        ws = AviDecoderWeights()
+        for k, v in keep.items():
+            setattr(ws, k, v.data_ptr())
+        P["dec_struct"], P["dec_keep"] = ws, keep
+        # untransposed copies for the teacher-forced branch (plain GEMMs)
+        P["sa_in_w"], P["sa_in_b"] = f32(lyr.self_attn.in_proj_weight), keep["sa_in_b"]
+        P["sa_out_w"], P["sa_out_b"] = f32(lyr.self_attn.out_proj.weight), keep["sa_out_b"]
+        P["ff1_w"], P["ff2_w"] = f32(lyr.linear1.weight), f32(lyr.linear2.weight)
+        # degenerate cross-attention: only the value / output projections matter
+        Wc, bc = lyr.multihead_attn.in_proj_weight, lyr.multihead_attn.in_proj_bias
+        P["ca_v_w"], P["ca_v_b"] = f32(Wc[2 * fd:]), f32(bc[2 * fd:])
+        P["ca_o_w"], P["ca_o_b"] = f32(lyr.multihead_attn.out_proj.weight), f32(lyr.multihead_attn.out_proj.bias)
+        P["afm_w"], P["afm_b"] = f32(self.audio_feature_map.weight), f32(self.audio_feature_map.bias)
+        if self.variant == "disentangle":
+            P["merge_w"], P["merge_b"] = f32(self.v_merge2hidden.weight), f32(self.v_merge2hidden.bias)
+        P["vm_w"], P["vm_b"] = f32(self.vertice_map.weight), f32(self.vertice_map.bias)
+        P["obj_w"] = f32(self.obj_vector.weight)
+        P["vr_w32"], P["vr_b"] = f32(self.vertice_map_r.weight), f32(self.vertice_map_r.bias)
+        if self.precision == "bf16":
+            P["vr_w16"] = ops.cast_bf16(self.vertice_map_r.weight)
+        self._packed, self._packed_key = P, key
+        return P
+
+    # ------------------------------------------------------------------ reference API
+    def convert_coeff2verts(self, gt_coeff, gt_pose, gt_shape):
+        """:425-433 (zeroes gt_pose[..., :3] in place, as upstream)."""
+        self.coeff_mean, self.coeff_std = self.coeff_mean.to(gt_coeff), self.coeff_std.to(gt_coeff)
+        n = gt_coeff.shape[-1]
+        gt_coeff_unnorm = gt_coeff * self.coeff_std[0, :, :n] + self.coeff_mean[0, :, :n]
+        gt_pose[..., :3] = 0.0
+        return self.flame.vertices_only(shape_params=gt_shape, expression_params=gt_coeff_unnorm[:, :50].contiguous(),
+                                        pose_params=gt_pose)
+
+    def _vertex_head(self, hidden, P, template):
+        """vertice_map_r over all rows + template (:473,481), one GEMM with bias' = b_r + template."""
+        B, T, fd = hidden.shape
+        bias = (P["vr_b"] + template.reshape(-1).float()).contiguous()
+        out = torch.empty((B, T, self.args.vertice_dim), dtype=torch.float32, device=hidden.device)
+        if self.precision == "bf16" and fd % 64 == 0:
+            a = ops.cast_bf16(hidden.reshape(B * T, fd))
+            ops.gemm(a, P["vr_w16"], bias, out, rows=B * T, N=self.args.vertice_dim, K=fd, a_rows_alloc=B * T)
+        else:
+            ops.gemm(hidden.reshape(B * T, fd), P["vr_w32"], bias, out, rows=B * T, N=self.args.vertice_dim, K=fd)
+        return out
+
+    @torch.no_grad()
+    def forward_ff(self, gt_verts, hidden_states, obj_embedding, frame_num, teacher_forcing):
+        """:435-482, all clips at once."""
+        if not hidden_states.is_cuda:
+            raise RuntimeError("avi_talking_b200.Faceformer runs on CUDA only (no CPU fallback)")
+        P = self._pack()
+        fd = self.args.feature_dim
+        B, T = hidden_states.shape[0], hidden_states.shape[1]
+        template = self.template.to(hidden_states.device)
+        hs = hidden_states.contiguous().float().reshape(B * T, -1)
+        if self.variant == "disentangle":
+            mix = ops.linear(hs, P["merge_w"], P["merge_b"])                                   # :437
+        else:
+            mix = hs
+        cross = ops.linear(ops.linear(mix, P["ca_v_w"], P["ca_v_b"]), P["ca_o_w"], P["ca_o_b"])  # degenerate cross-attn
+        style = obj_embedding.contiguous().float()
+        period = self.args.period
+        if teacher_forcing:
+            n = gt_verts.shape[1]
+            vin = torch.cat([template.expand(B, -1, -1), gt_verts[:, :-1]], 1) - template        # :448-449
+            x = ops.linear(vin.reshape(B * n, -1).contiguous().float(), P["vm_w"], P["vm_b"])       # :450
+            pe = P["dec_keep"]["pe"]
+            x = (x.view(B, n, fd) + style[:, None] + pe[torch.arange(n, device=x.device) % period][None]).reshape(B * n, fd)
+            qkv = ops.linear(x, P["sa_in_w"], P["sa_in_b"])
+            att = ops.ff_biased_attn(qkv, B, n, fd, period).reshape(B * n, fd)
+            y = ops.linear(att, P["sa_out_w"], P["sa_out_b"], residual=x)
+            k = P["dec_keep"]
+            x1, _ = ops.layernorm(y, k["ln1_w"], k["ln1_b"])
+            cr = cross.view(B, T, fd)[:, :n].reshape(B * n, fd).contiguous()
+            x2, _ = ops.layernorm(x1, k["ln2_w"], k["ln2_b"], res=cr)
+            f = ops.linear(x2, P["ff1_w"], k["ff1_b"], act=ACT_RELU)
+            y3 = ops.linear(f, P["ff2_w"], k["ff2_b"], residual=x2)
+            hidden, _ = ops.layernorm(y3, k["ln3_w"], k["ln3_b"])
+            hidden = hidden.view(B, n, fd)
+        else:
+            if frame_num != T:
+                cross = cross.view(B, T, fd)[:, :frame_num].contiguous()
+            hidden = ops.ff_decoder_ar(P["dec_struct"], cross, style, B, frame_num, fd, period)  # :461-476
+        return self._vertex_head(hidden, P, template)                                          # :473,480-481
+
+    @torch.no_grad()
+    def predict_from_embeddings(self, audio, emo_embed=None, eye_embed=None):
+        """predict() after the (out-of-scope) image branch: audio [B,N] -> vertices [B,T,V*3]; emo_embed [B,T,30]."""
+        P = self._pack()
+        B = audio.shape[0]
+        dev = audio.device
+        self.template = self.template.to(audio)
+        one_hot = torch.zeros(B, len(self.args.train_subjects.split()), device=dev)
+        one_hot[:, 0] = 1
+        obj_embedding = ops.linear(one_hot, P["obj_w"], None)                                  # :771-773
+        hs_a = self.audio_encoder(audio, self.dataset).last_hidden_state                      # :775
+        T = hs_a.shape[1]
+        hs_a = ops.linear(hs_a.reshape(B * T, -1), P["afm_w"], P["afm_b"]).view(B, T, -1)       # :776
+        if self.variant == "disentangle":
+            eye = self.learnable_eye_embed.expand(B, T, -1) if eye_embed is None else eye_embed
+            hidden_states = torch.cat([eye, emo_embed[:, :T].to(hs_a), hs_a], dim=-1)          # :808
+        else:
+            hidden_states = hs_a                                                               # faceformer_vert.py:434
+        return self.forward_ff(None, hidden_states, obj_embedding, T, teacher_forcing=False)  # :810
+
+    @torch.no_grad()
+    def predict(self, audio, head_img, eye_img, emotion_img, text=None):
+        """:767-812. The FanEncoder image branch is called exactly as upstream (per frame) when ``fan_net`` is set."""
+        if getattr(self.args, "load_mld", 0):
+            raise NotImplementedError("load_mld (MLD text branch) is not part of this path")
+        from .wav2vec import linear_interpolation_length
+        n = audio.shape[1]
+        for k, s in zip(self.audio_encoder.config.conv_kernel, self.audio_encoder.config.conv_stride):
+            n = (n - k) // s + 1
+        frame_num = linear_interpolation_length(n)
+        # upstream also runs fan_net over head_img / eye_img (:783-790) but never uses those embeddings (:808 takes
+        # learnable_eye_embed and the emotion embedding only), so they are not computed here.
+        emo_embed = None
+        if self.variant == "disentangle":
+            emotion_img = loopback_frames(emotion_img, frame_num)                              # :779-781
+            emo = []
+            for i in range(len(emotion_img)):                                                  # :791-797
+                _, _, emo_i, _ = self.fan_net(emotion_img[i:i + 1])
+                emo.append(emo_i)
+            emo_embed = torch.concat(emo, dim=0).unsqueeze(0)
+        return self.predict_from_embeddings(audio, emo_embed)
+
+    def forward(self, *a, **k):
+        raise NotImplementedError("the training forward (losses, renderers, FanEncoder) is outside the inference hot path; "
+                                  "use forward_ff(..., teacher_forcing=True) for the teacher-forced decoder pass")
+
+
+class FaceformerVert(Faceformer):
+    """models/faceformer_vert.py: audio-only hidden states (:434), no merge layer."""
+    variant = "vert"
+
+
+def make_args(feature_dim=64, vertice_dim=15069, period=30, n_subjects=8, dataset="vocaset", device="cuda"):
+    return types.SimpleNamespace(dataset=dataset, feature_dim=feature_dim, vertice_dim=vertice_dim, period=period,
+                                 train_subjects=" ".join(f"s{i}" for i in range(n_subjects)), device=device,
+                                 is_concat_mode=0, load_mld=0)

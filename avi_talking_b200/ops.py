@@ -1,0 +1,225 @@
+"""Thin torch-tensor wrappers over the C ABI (include/avi_b200.h). torch is used for device memory and the
+current stream only; every computation below runs in libavi_b200.so. No fallbacks."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, DT_BF16, DT_F32, AviDecoderWeights, AviGemmArgs  # noqa: F401
+
+
+# bench.py's roofline pass: when set to a list, every launch made through `_timed` appends
+# (kernel name, start event, end event, algorithmic work) with CUDA events recorded on the launching stream.
+PROFILE = None
+
+
+class _timed:
+    def __init__(self, name, work):
+        self.name, self.work = name, work
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            self.e1.record()
+            PROFILE.append((self.name, self.e0, self.e1, self.work))
+        return False
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return DT_F32
+    if t.dtype == torch.bfloat16:
+        return DT_BF16
+    raise TypeError(f"unsupported dtype {t.dtype}")
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("avi_talking_b200 ops need CUDA tensors (there is no CPU path)")
+
+
+def cast_bf16(src: torch.Tensor) -> torch.Tensor:
+    _need_cuda(src)
+    src = src.contiguous().float()
+    dst = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
+    _lib.check(_lib.load().avi_cast_f32_to_bf16(_ptr(src), _ptr(dst), C.c_int64(src.numel()), _stream()), "avi_cast_f32_to_bf16")
+    return dst
+
+
+def gemm(A, W, bias, out, *, rows, N, K, batch=1, act=ACT_NONE, residual=None, out2=None, conv_taps=1, conv_stride=1,
+         a_ld=None, a_batch_stride=0, a_rows_alloc=None, c_ld=None, c_batch_stride=0, res_ld=None, res_batch_stride=0):
+    """C[b,r,n] = act(sum_k A[b,r,k] W[n,k] + bias[n]) (+ residual). fp32 A/W -> CUDA-core kernel, bf16 -> tcgen05 kernel."""
+    _need_cuda(A, W, bias, out, residual, out2)
+    if A.dtype != W.dtype:
+        raise TypeError("A and W must share a dtype")
+    args = AviGemmArgs()
+    args.A, args.W, args.bias, args.residual = A.data_ptr(), W.data_ptr(), (bias.data_ptr() if bias is not None else None), \
+        (residual.data_ptr() if residual is not None else None)
+    args.C = out.data_ptr()
+    args.C2 = out2.data_ptr() if out2 is not None else None
+    args.batch, args.rows, args.N, args.K = batch, rows, N, K
+    args.conv_taps, args.conv_stride = conv_taps, conv_stride
+    args.a_ld = a_ld if a_ld is not None else K // conv_taps
+    args.a_batch_stride = a_batch_stride
+    args.a_rows_alloc = a_rows_alloc if a_rows_alloc is not None else (rows - 1) * conv_stride + conv_taps
+    args.c_ld = c_ld if c_ld is not None else N
+    args.c_batch_stride = c_batch_stride
+    args.res_ld = res_ld if res_ld is not None else N
+    args.res_batch_stride = res_batch_stride
+    args.a_dtype, args.c_dtype, args.act = _dt(A), _dt(out), act
+    if bias is not None and bias.dtype != torch.float32:
+        raise TypeError("bias must be fp32")
+    if residual is not None and residual.dtype != torch.float32:
+        raise TypeError("residual must be fp32")
+    if out2 is not None and out2.dtype == out.dtype:
+        raise TypeError("out2 must be the other dtype")
+    lib = _lib.load()
+    flops = 2.0 * batch * rows * N * K
+    if A.dtype == torch.bfloat16:
+        with _timed("gemm_bf16_tc", flops):
+            _lib.check(lib.avi_gemm_bf16_tc(C.byref(args), _stream()), "avi_gemm_bf16_tc")
+    else:
+        with _timed("gemm_f32", flops):
+            _lib.check(lib.avi_gemm_f32(C.byref(args), _stream()), "avi_gemm_f32")
+    return out
+
+
+def linear(x2d: torch.Tensor, W: torch.Tensor, bias, *, act=ACT_NONE, residual=None, out_dtype=None, out2_dtype=None,
+           out=None):
+    """nn.Linear on [rows, K] activations: returns out (and out2 if requested)."""
+    rows, K = x2d.shape
+    N = W.shape[0]
+    assert W.shape[1] == K and x2d.is_contiguous() and W.is_contiguous()
+    if out is None:
+        out = torch.empty((rows, N), dtype=out_dtype or torch.float32, device=x2d.device)
+    out2 = torch.empty((rows, N), dtype=out2_dtype, device=x2d.device) if out2_dtype is not None else None
+    gemm(x2d, W, bias, out, rows=rows, N=N, K=K, act=act, residual=residual, out2=out2, a_rows_alloc=rows)
+    return (out, out2) if out2 is not None else out
+
+
+def conv0_gn_gelu(audio, w, gn_w, gn_b, out, out_batch_stride, eps=1e-5):
+    _need_cuda(audio, w, out)
+    B, n = audio.shape
+    Cc = w.shape[0]
+    stats = torch.empty((B, Cc, 2), dtype=torch.float64, device=audio.device)
+    with _timed("conv0_gn_gelu", float(out.numel() * out.element_size())):
+        _lib.check(_lib.load().avi_w2v_conv0_gn_gelu(_ptr(audio), _ptr(w), _ptr(gn_w), _ptr(gn_b), _ptr(stats), _ptr(out),
+                                                     C.c_int32(_dt(out)), C.c_int64(out_batch_stride), C.c_int32(B), C.c_int32(n),
+                                                     C.c_int32(Cc), C.c_float(eps), _stream()), "avi_w2v_conv0_gn_gelu")
+    return out
+
+
+def lerp_layernorm(x, in_batch_stride, B, T_in, T_out, ln_w, ln_b, want_f32, want_bf16, eps=1e-5):
+    _need_cuda(x)
+    Cc = ln_w.numel()
+    o32 = torch.empty((B * T_out, Cc), dtype=torch.float32, device=x.device) if want_f32 else None
+    o16 = torch.empty((B * T_out, Cc), dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    with _timed("lerp_layernorm", 0.0):
+        _lib.check(_lib.load().avi_w2v_lerp_layernorm(_ptr(x), C.c_int32(_dt(x)), C.c_int64(in_batch_stride), _ptr(ln_w), _ptr(ln_b),
+                                                      _ptr(o32), _ptr(o16), C.c_int32(B), C.c_int32(T_in), C.c_int32(T_out),
+                                                      C.c_int32(Cc), C.c_float(eps), _stream()), "avi_w2v_lerp_layernorm")
+    return o32, o16
+
+
+def layernorm(x, w, b, *, res=None, want_f32=True, want_bf16=False, eps=1e-5):
+    _need_cuda(x, res)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    rows, Cc = x.numel() // x.shape[-1], x.shape[-1]
+    o32 = torch.empty_like(x) if want_f32 else None
+    o16 = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    with _timed("layernorm", float(x.numel() * 8)):
+        _lib.check(_lib.load().avi_layernorm(_ptr(x), _ptr(res), _ptr(w), _ptr(b), _ptr(o32), _ptr(o16), C.c_int64(rows),
+                                             C.c_int32(Cc), C.c_float(eps), _stream()), "avi_layernorm")
+    return o32, o16
+
+
+def posconv_ln(x, w_packed, conv_bias, ln_w, ln_b, B, T, groups, k, want_bf16, eps=1e-5):
+    _need_cuda(x)
+    Cc = x.shape[-1]
+    o32 = torch.empty((B * T, Cc), dtype=torch.float32, device=x.device)
+    o16 = torch.empty((B * T, Cc), dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    with _timed("posconv_ln", 2.0 * B * T * Cc * (Cc // groups) * k):
+        _lib.check(_lib.load().avi_w2v_posconv_ln(_ptr(x), _ptr(w_packed), _ptr(conv_bias), _ptr(ln_w), _ptr(ln_b), _ptr(o32),
+                                                  _ptr(o16), C.c_int32(B), C.c_int32(T), C.c_int32(Cc), C.c_int32(groups),
+                                                  C.c_int32(k), C.c_float(eps), _stream()), "avi_w2v_posconv_ln")
+    return o32, o16
+
+
+def mha(qkv, B, T, H, D, scale):
+    _need_cuda(qkv)
+    out = torch.empty((B * T, H * D), dtype=qkv.dtype, device=qkv.device)
+    with _timed("mha", 4.0 * B * H * T * T * D):
+        _lib.check(_lib.load().avi_mha_fwd(_ptr(qkv), _ptr(out), C.c_int32(_dt(qkv)), C.c_int32(B), C.c_int32(T), C.c_int32(H),
+                                           C.c_int32(D), C.c_float(scale), _stream()), "avi_mha_fwd")
+    return out
+
+
+def ff_decoder_ar(wstruct: AviDecoderWeights, cross, style, B, T, fd, period):
+    _need_cuda(cross, style)
+    hidden = torch.empty((B, T, fd), dtype=torch.float32, device=cross.device)
+    kv = torch.empty((B, 2, T, fd + 1), dtype=torch.float32, device=cross.device)
+    with _timed("ff_decoder_ar", 0.0):
+        _lib.check(_lib.load().avi_ff_decoder_ar(C.byref(wstruct), _ptr(cross), _ptr(style), _ptr(hidden), _ptr(kv), C.c_int32(B),
+                                                 C.c_int32(T), C.c_int32(fd), C.c_int32(period), _stream()), "avi_ff_decoder_ar")
+    return hidden
+
+
+def ff_biased_attn(qkv, B, T, fd, period):
+    _need_cuda(qkv)
+    out = torch.empty((B, T, fd), dtype=torch.float32, device=qkv.device)
+    _lib.check(_lib.load().avi_ff_biased_attn(_ptr(qkv), _ptr(out), C.c_int32(B), C.c_int32(T), C.c_int32(fd), C.c_int32(period),
+                                              _stream()), "avi_ff_biased_attn")
+    return out
+
+
+def flame_pack(shapedirs, posedirs, v_template, J_regressor, K_pad):
+    _need_cuda(shapedirs)
+    V, _, NB = shapedirs.shape
+    dirs = torch.empty((K_pad, V * 3), dtype=torch.float32, device=shapedirs.device)
+    jreg = torch.empty((15, NB + 1), dtype=torch.float32, device=shapedirs.device)
+    _lib.check(_lib.load().avi_flame_pack(_ptr(shapedirs), _ptr(posedirs), _ptr(v_template), _ptr(J_regressor), _ptr(dirs),
+                                          _ptr(jreg), C.c_int32(V), C.c_int32(NB), C.c_int32(K_pad), _stream()), "avi_flame_pack")
+    return dirs, jreg
+
+
+def flame_lbs(betas, full_pose, dirs, jreg, lbs_weights, V, NB, K_pad, want_joints=False, want_dyn_rows=False):
+    _need_cuda(betas, full_pose)
+    F = betas.shape[0]
+    dev = betas.device
+    coef = torch.empty((F, K_pad), dtype=torch.float32, device=dev)
+    A = torch.empty((F, 5, 12), dtype=torch.float32, device=dev)
+    verts = torch.empty((F, V, 3), dtype=torch.float32, device=dev)
+    joints = torch.empty((F, 5, 3), dtype=torch.float32, device=dev) if want_joints else None
+    rows = torch.empty((F,), dtype=torch.int32, device=dev) if want_dyn_rows else None
+    with _timed("flame_lbs", float(F) * (V * 12 + 4 * (NB + 6))):  # algorithmic bytes: verts written + coefficients read
+        _lib.check(_lib.load().avi_flame_lbs_fwd(_ptr(betas), _ptr(full_pose), _ptr(dirs), _ptr(jreg), _ptr(lbs_weights),
+                                                 _ptr(coef), _ptr(A), _ptr(verts), _ptr(joints), _ptr(rows), C.c_int32(F),
+                                                 C.c_int32(V), C.c_int32(NB), C.c_int32(K_pad), _stream()), "avi_flame_lbs_fwd")
+    return verts, joints, rows
+
+
+def flame_landmarks(verts, faces, idx, bary, per_frame: bool):
+    _need_cuda(verts, faces, idx, bary)
+    F, V, _ = verts.shape
+    L = idx.shape[-1]
+    out = torch.empty((F, L, 3), dtype=torch.float32, device=verts.device)
+    _lib.check(_lib.load().avi_flame_landmarks(_ptr(verts), _ptr(faces), _ptr(idx), _ptr(bary), _ptr(out), C.c_int32(F),
+                                               C.c_int32(V), C.c_int32(L), C.c_int32(1 if per_frame else 0), _stream()),
+               "avi_flame_landmarks")
+    return out

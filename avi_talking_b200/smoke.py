@@ -1,0 +1,64 @@
+"""One small invocation of the hot path on cuda:0, checked against the CPU oracle (used by __graft_entry__.smoke())."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+
+def build_models(precision: str, fd: int = 64, device: str = "cuda", seed_ff: int = 74, flame_dir: str = "/tmp/avi_flame_assets"):
+    """Drop-in wav2vec2 + Faceformer + FLAME loaded with the seeded synthetic weights/assets (avi_talking_b200.synth)."""
+    from transformers import Wav2Vec2Config
+
+    from . import synth
+    from .faceformer import Faceformer, make_args
+    from .flame import FLAME_mediapipe
+    from .wav2vec import Wav2Vec2Model
+
+    w2v = Wav2Vec2Model(Wav2Vec2Config())
+    w2v.load_state_dict(synth.wav2vec2_state(0), strict=False)
+    flame = FLAME_mediapipe(synth.write_flame_assets(flame_dir))
+    rng = np.random.default_rng(53)
+    model = Faceformer(make_args(feature_dim=fd), audio_encoder=w2v, flame=flame,
+                       coeff_mean=rng.normal(0, 0.3, size=53).astype("float32"),
+                       coeff_std=(0.3 + rng.uniform(size=53)).astype("float32"))
+    model.load_state_dict(synth.faceformer_state(fd=fd, seed=seed_ff), strict=False)
+    model.precision = precision
+    w2v.precision = precision
+    return model.to(device).eval()
+
+
+def run_smoke(verbose: bool = False) -> dict:
+    from oracle import faceformer_oracle as ffo   # checker only
+    from oracle import flame_oracle as fo
+
+    from . import _lib, synth
+
+    _lib.load(check_symbols=True)
+    torch.cuda.set_device(0)
+    res = {}
+    a = synth.audio(2, 16000, seed=1234)
+    emo = torch.stack([synth.fan_embeddings(24, seed=20 + c)["emo"] for c in range(2)])
+    sd_w2v, sd_ff = synth.wav2vec2_state(0), synth.faceformer_state(fd=64, seed=74)
+    buf = synth.flame_buffers()
+    template = buf["v_template"].reshape(1, 1, 15069)
+    ref = ffo.predict(sd_ff, sd_w2v, template, a, emo, cached=True)
+    n0 = _lib.launch_count()
+    m = None
+    for prec, tol in (("fp32", 1e-5), ("bf16", 1e-4)):
+        m = build_models(prec)
+        v = m.predict_from_embeddings(a.cuda(), emo.cuda())
+        torch.cuda.synchronize()
+        err = (v.cpu() - ref).abs().max().item()
+        res[f"predict_{prec}_max_abs_m"] = err
+        assert err < tol, f"{prec} predict: max abs vertex error {err} m exceeds {tol}"
+    p = synth.flame_params(8, seed=3)
+    got = m.flame(p["shape"].cuda(), p["exp"].cuda(), p["pose"].cuda(), p["eye"].cuda())
+    want = fo.flame_forward(buf, p["shape"], p["exp"], p["pose"], p["eye"], mediapipe=True)
+    for name, g, w in zip(("verts", "lmk2d", "lmk3d", "lmk_mp"), got, want):
+        err = (g.cpu() - w).abs().max().item()
+        res[f"flame_{name}_max_abs_m"] = err
+        assert err < 1e-6, f"FLAME {name}: {err}"
+    res["kernel_launches"] = _lib.launch_count() - n0
+    if verbose:
+        print("smoke OK:", res)
+    return res

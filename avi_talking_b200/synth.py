@@ -1,0 +1,247 @@
+"""Seeded synthetic assets, weights and inputs (shared by bench.py, smoke(), the tests and the oracle).
+
+Pure data generation (numpy/torch on the host), no arithmetic of the hot path lives here.
+
+Everything is drawn from ``numpy.random.default_rng`` (PCG64 + ziggurat normal),
+which is bit-reproducible across machines, so the build container (where the
+golden fixtures are minted from the real reference) and the GPU box (where the
+CUDA path is checked) see identical tensors without shipping 377 MB of weights.
+
+Shapes/keys follow the reference:
+  FLAME pickle keys and slicing ........ third_party/inferno/inferno/models/DecaFLAME.py:53-106
+  wav2vec2-base architecture ........... transformers Wav2Vec2Config() defaults (models/lib/wav2vec.py:76-78)
+  Faceformer heads / decoder ........... models/faceformer_disentangle.py:158-241,327
+"""
+from __future__ import annotations
+
+import math
+import pickle
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+N_VERT = 5023
+N_FACE = 9976
+N_JOINT = 5
+
+
+def _t(a) -> torch.Tensor:
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+
+
+# --------------------------------------------------------------------------- FLAME assets
+def flame_model_dict(seed: int = 0) -> dict:
+    """Synthetic stand-in for FLAME ``generic_model.pkl`` (licensed, absent upstream).
+
+    Same key set / shapes / dtypes the reference unpickles (DecaFLAME.py:53-74).
+    Magnitudes: template ~8 cm, blendshape directions ~1 mm per unit coefficient.
+    """
+    rng = np.random.default_rng(seed)
+    v_template = rng.normal(0.0, 0.08, size=(N_VERT, 3))
+    shapedirs = rng.normal(0.0, 1e-3, size=(N_VERT, 3, 400))
+    posedirs = rng.normal(0.0, 1e-3, size=(N_VERT, 3, 36))
+    jr = np.abs(rng.normal(size=(N_JOINT, N_VERT)))
+    jr /= jr.sum(1, keepdims=True)
+    w = np.abs(rng.normal(size=(N_VERT, N_JOINT))) ** 4  # peaky, like real skinning weights
+    w /= w.sum(1, keepdims=True)
+    f = rng.integers(0, N_VERT, size=(N_FACE, 3)).astype(np.uint32)
+    kintree = np.array([[4294967295, 0, 1, 1, 1], [0, 1, 2, 3, 4]], dtype=np.int64)
+    return dict(f=f, v_template=v_template, shapedirs=shapedirs, posedirs=posedirs,
+                J_regressor=jr, kintree_table=kintree, weights=w)
+
+
+def flame_lmk_dict(seed: int = 1) -> dict:
+    """Synthetic ``landmark_embedding.npy`` payload (DecaFLAME.py:87-98)."""
+    rng = np.random.default_rng(seed)
+
+    def bary(*shape):
+        b = np.abs(rng.normal(size=shape + (3,))) + 0.05
+        return (b / b.sum(-1, keepdims=True)).astype(np.float32)
+
+    return dict(
+        static_lmk_faces_idx=rng.integers(0, N_FACE, size=(51,)).astype(np.int64),
+        static_lmk_bary_coords=bary(51),
+        dynamic_lmk_faces_idx=rng.integers(0, N_FACE, size=(79, 17)).astype(np.int64),
+        dynamic_lmk_bary_coords=bary(79, 17),
+        full_lmk_faces_idx=rng.integers(0, N_FACE, size=(1, 68)).astype(np.int64),
+        full_lmk_bary_coords=bary(1, 68),
+    )
+
+
+def flame_mediapipe_lmk_dict(seed: int = 2) -> dict:
+    """Synthetic mediapipe embedding (DecaFLAME.py:276-283): 105 static landmarks."""
+    rng = np.random.default_rng(seed)
+    b = np.abs(rng.normal(size=(105, 3))) + 0.05
+    return dict(lmk_face_idx=rng.integers(0, N_FACE, size=(105,)).astype(np.int64),
+                lmk_b_coords=(b / b.sum(-1, keepdims=True)).astype(np.float32),
+                landmark_indices=np.arange(105))
+
+
+def write_flame_assets(dirpath: str, seed: int = 0) -> SimpleNamespace:
+    """Write the three asset files and return a config like ``misc/flame_cfg.pkl`` would give."""
+    import os
+    os.makedirs(dirpath, exist_ok=True)
+    p_model = os.path.join(dirpath, "generic_model.pkl")
+    p_lmk = os.path.join(dirpath, "landmark_embedding.npy")
+    p_mp = os.path.join(dirpath, "mediapipe_landmark_embedding.npz")
+    with open(p_model, "wb") as fh:
+        pickle.dump(flame_model_dict(seed), fh)
+    np.save(p_lmk, flame_lmk_dict(seed + 1), allow_pickle=True)
+    np.savez(p_mp, **flame_mediapipe_lmk_dict(seed + 2))
+    return SimpleNamespace(flame_model_path=p_model, flame_lmk_embedding_path=p_lmk,
+                           flame_mediapipe_lmk_embedding_path=p_mp, n_shape=100, n_exp=50)
+
+
+def flame_buffers(n_shape: int = 100, n_exp: int = 50, seed: int = 0) -> dict:
+    """The registered buffers FLAME.__init__ derives from the pickle (DecaFLAME.py:60-106)."""
+    m = flame_model_dict(seed)
+    lm = flame_lmk_dict(seed + 1)
+    mp = flame_mediapipe_lmk_dict(seed + 2)
+    sd = np.concatenate([m["shapedirs"][:, :, :n_shape], m["shapedirs"][:, :, 300:300 + n_exp]], 2)
+    pd = np.reshape(m["posedirs"], [-1, 36]).T
+    parents = torch.tensor([-1, 0, 1, 1, 1], dtype=torch.long)
+    return dict(
+        faces_tensor=torch.from_numpy(m["f"].astype(np.int64)),
+        v_template=_t(m["v_template"]), shapedirs=_t(sd), posedirs=_t(pd),
+        J_regressor=_t(m["J_regressor"]), parents=parents, lbs_weights=_t(m["weights"]),
+        lmk_faces_idx=torch.from_numpy(lm["static_lmk_faces_idx"]),
+        lmk_bary_coords=_t(lm["static_lmk_bary_coords"]),
+        dynamic_lmk_faces_idx=torch.from_numpy(lm["dynamic_lmk_faces_idx"]),
+        dynamic_lmk_bary_coords=_t(lm["dynamic_lmk_bary_coords"]),
+        full_lmk_faces_idx=torch.from_numpy(lm["full_lmk_faces_idx"]),
+        full_lmk_bary_coords=_t(lm["full_lmk_bary_coords"]),
+        lmk_faces_idx_mediapipe=torch.from_numpy(mp["lmk_face_idx"]),
+        lmk_bary_coords_mediapipe=_t(mp["lmk_b_coords"]),
+        neck_kin_chain=torch.tensor([1, 0], dtype=torch.long),
+        eye_pose=torch.zeros(1, 6), neck_pose=torch.zeros(1, 3),
+    )
+
+
+def flame_params(n_frames: int, n_shape: int = 100, n_exp: int = 50, seed: int = 3,
+                 zero_shape: bool = False, global_pose: bool = True) -> dict:
+    """exp ~ N(0,1), jaw ~ N(0,0.1^2) rad, small global rotation."""
+    rng = np.random.default_rng(seed)
+    shape = np.zeros((n_frames, n_shape)) if zero_shape else rng.normal(size=(n_frames, n_shape))
+    exp = rng.normal(size=(n_frames, n_exp))
+    pose = np.zeros((n_frames, 6))
+    if global_pose:
+        pose[:, :3] = rng.normal(0, 0.2, size=(n_frames, 3))
+    pose[:, 3:] = rng.normal(0, 0.1, size=(n_frames, 3))
+    eye = rng.normal(0, 0.1, size=(n_frames, 6))
+    return dict(shape=_t(shape), exp=_t(exp), pose=_t(pose), eye=_t(eye))
+
+
+# --------------------------------------------------------------------------- audio
+def audio(n_clips: int, n_samples: int, seed: int = 1234) -> torch.Tensor:
+    """z-normalised noise, as Wav2Vec2Processor leaves it (dataset/voca_data_loader.py:59-60)."""
+    out = np.empty((n_clips, n_samples), dtype=np.float32)
+    for c in range(n_clips):
+        x = np.random.default_rng(seed + c).normal(size=n_samples)
+        # mild low-pass so neighbouring samples correlate like speech does
+        x = np.convolve(x, np.array([0.25, 0.5, 0.25]), mode="same")
+        out[c] = (x - x.mean()) / np.sqrt(x.var() + 1e-7)
+    return torch.from_numpy(out)
+
+
+# --------------------------------------------------------------------------- wav2vec2 weights
+W2V = SimpleNamespace(conv_dim=(512,) * 7, conv_kernel=(10, 3, 3, 3, 3, 2, 2), conv_stride=(5, 2, 2, 2, 2, 2, 2),
+                      hidden=768, heads=12, ffn=3072, layers=12, pos_k=128, pos_groups=16, eps=1e-5)
+
+
+def wav2vec2_state(seed: int = 0, layers: int = 12) -> dict:
+    """State dict with transformers-5.x key names for Wav2Vec2Model(Wav2Vec2Config()).
+
+    Not the HF init (zero biases / std-0.02 Linears give near-uniform attention and
+    leave bias paths untested): Linears ~ N(0, 0.7/sqrt(fan_in)), small non-zero biases,
+    LayerNorm gains 1 +- 0.1, convs Kaiming-normal.
+    """
+    rng = np.random.default_rng(seed)
+    sd = {}
+
+    def lin(name, out_f, in_f, gain=0.7):
+        sd[name + ".weight"] = _t(rng.normal(0, gain / math.sqrt(in_f), size=(out_f, in_f)))
+        sd[name + ".bias"] = _t(rng.normal(0, 0.02, size=(out_f,)))
+
+    def ln(name, c):
+        sd[name + ".weight"] = _t(1.0 + 0.1 * rng.normal(size=(c,)))
+        sd[name + ".bias"] = _t(0.05 * rng.normal(size=(c,)))
+
+    cin = 1
+    for i, (c, k) in enumerate(zip(W2V.conv_dim, W2V.conv_kernel)):
+        sd[f"feature_extractor.conv_layers.{i}.conv.weight"] = _t(
+            rng.normal(0, math.sqrt(2.0 / (cin * k)), size=(c, cin, k)))
+        cin = c
+    ln("feature_extractor.conv_layers.0.layer_norm", 512)
+    ln("feature_projection.layer_norm", 512)
+    lin("feature_projection.projection", 768, 512)
+    sd["masked_spec_embed"] = _t(rng.uniform(size=(768,)))
+    sd["encoder.pos_conv_embed.conv.bias"] = _t(rng.normal(0, 0.02, size=(768,)))
+    v = rng.normal(0, 2 * math.sqrt(1.0 / (128 * 48)), size=(768, 48, 128))
+    sd["encoder.pos_conv_embed.conv.parametrizations.weight.original1"] = _t(v)
+    g = np.sqrt((v ** 2).sum(axis=(0, 1), keepdims=True)) * (1.0 + 0.1 * rng.normal(size=(1, 1, 128)))
+    sd["encoder.pos_conv_embed.conv.parametrizations.weight.original0"] = _t(g)
+    ln("encoder.layer_norm", 768)
+    for l in range(layers):
+        p = f"encoder.layers.{l}."
+        for nm in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            lin(p + "attention." + nm, 768, 768, gain=1.0 if nm in ("q_proj", "k_proj") else 0.7)
+        ln(p + "layer_norm", 768)
+        lin(p + "feed_forward.intermediate_dense", 3072, 768)
+        lin(p + "feed_forward.output_dense", 768, 3072)
+        ln(p + "final_layer_norm", 768)
+    return sd
+
+
+# --------------------------------------------------------------------------- Faceformer (Path A) weights
+def faceformer_state(fd: int = 64, n_subjects: int = 8, vertice_dim: int = N_VERT * 3, seed: int = 10,
+                     head_std: float = 1e-3, variant: str = "disentangle") -> dict:
+    """Heads + 1-layer nn.TransformerDecoder, torch key names (faceformer_disentangle.py:171-202,241,327).
+
+    ``vertice_map_r`` is zero-initialised upstream (:201-202) which would make parity vacuous;
+    it is re-randomised here with ``head_std`` (1e-3 -> ~8 mm rms displacement at fd=64,
+    the magnitude of real facial motion).
+    ``variant='vert'`` follows models/faceformer_vert.py:162 (dim_feedforward = 2*fd, no merge layer).
+    """
+    rng = np.random.default_rng(seed)
+    sd = {}
+
+    def lin(name, out_f, in_f, bias=True, std=None):
+        s = std if std is not None else 0.7 / math.sqrt(in_f)
+        sd[name + ".weight"] = _t(rng.normal(0, s, size=(out_f, in_f)))
+        if bias:
+            sd[name + ".bias"] = _t(rng.normal(0, 0.02, size=(out_f,)))
+
+    def ln(name, c):
+        sd[name + ".weight"] = _t(1.0 + 0.1 * rng.normal(size=(c,)))
+        sd[name + ".bias"] = _t(0.05 * rng.normal(size=(c,)))
+
+    lin("audio_feature_map", fd, 768)
+    # vertice_map sees displacements of ~head_std*sqrt(fd): scale so the fed-back embedding is O(0.3)
+    lin("vertice_map", fd, vertice_dim, std=0.3 / (head_std * math.sqrt(fd) * math.sqrt(vertice_dim)))
+    lin("vertice_map_r", vertice_dim, fd, std=head_std)
+    sd["vertice_map_r.bias"] = _t(rng.normal(0, head_std, size=(vertice_dim,)))
+    lin("obj_vector", fd, n_subjects, bias=False, std=0.35)
+    if variant == "disentangle":
+        lin("v_merge2hidden", fd, 36 + fd)
+        sd["learnable_eye_embed"] = _t(rng.normal(0, 0.3, size=(1, 1, 6)))
+    p = "transformer_decoder.layers.0."
+    sd[p + "self_attn.in_proj_weight"] = _t(rng.normal(0, 1.0 / math.sqrt(fd), size=(3 * fd, fd)))
+    sd[p + "self_attn.in_proj_bias"] = _t(rng.normal(0, 0.02, size=(3 * fd,)))
+    lin(p + "self_attn.out_proj", fd, fd)
+    sd[p + "multihead_attn.in_proj_weight"] = _t(rng.normal(0, 1.0 / math.sqrt(fd), size=(3 * fd, fd)))
+    sd[p + "multihead_attn.in_proj_bias"] = _t(rng.normal(0, 0.02, size=(3 * fd,)))
+    lin(p + "multihead_attn.out_proj", fd, fd)
+    lin(p + "linear1", 2 * fd, fd)
+    lin(p + "linear2", fd, 2 * fd)
+    for i in (1, 2, 3):
+        ln(p + f"norm{i}", fd)
+    return sd
+
+
+def fan_embeddings(n_frames: int, seed: int = 20):
+    """Deterministic stand-in for the FanEncoder image branch (OUT of scope):
+    the 4-tuple (head[6], eye[6], emo[30], None) per frame that predict() consumes (:783-797)."""
+    rng = np.random.default_rng(seed)
+    return dict(head=_t(np.zeros((n_frames, 6))), eye=_t(np.zeros((n_frames, 6))),
+                emo=_t(rng.normal(size=(n_frames, 30))))

@@ -1,0 +1,180 @@
+"""Drop-in for models/lib/wav2vec.py: ``Wav2Vec2Model`` with the reference's forward signature
+(models/lib/wav2vec.py:80-157) whose eval-mode computation runs in libavi_b200.so.
+
+It subclasses the same transformers class the reference subclasses, so ``from_pretrained``, ``config``,
+``feature_extractor._freeze_parameters()`` and every ``state_dict`` key are inherited unchanged; only ``forward`` is
+replaced. Pipeline (time-major activations):
+
+  conv0 + GroupNorm + GELU                      avi_w2v_conv0_gn_gelu
+  conv1..6 (+GELU) as GEMMs over time           avi_gemm_bf16_tc (tcgen05) | avi_gemm_f32
+  50 Hz -> 25 Hz lerp + LayerNorm(512)          avi_w2v_lerp_layernorm
+  projection 512 -> 768                         GEMM
+  positional grouped conv + GELU + res + LN     avi_w2v_posconv_ln
+  12 x [QKV GEMM, MHA, out-proj GEMM(+res), LN, FFN GEMM(GELU), FFN GEMM(+res), LN]
+
+precision = "bf16": GEMM operands bf16 (fp32 accumulate in TMEM), residual stream / LayerNorm / softmax fp32.
+precision = "fp32": every operand fp32 on CUDA cores (the <=1e-5 mode).
+"""
+from __future__ import annotations
+
+import math
+import os
+
+import torch
+import torch.nn.functional as F  # noqa: F401  (kept for parity with the reference module's namespace)
+from transformers import Wav2Vec2Model as _HFWav2Vec2Model
+from transformers.modeling_outputs import BaseModelOutput
+
+from . import ops
+from .ops import ACT_GELU, ACT_NONE
+
+
+def default_precision() -> str:
+    p = os.environ.get("AVI_B200_PRECISION", "bf16").lower()
+    if p not in ("bf16", "fp32"):
+        raise ValueError("AVI_B200_PRECISION must be bf16 or fp32")
+    return p
+
+
+def linear_interpolation_length(t50: int, input_fps=50, output_fps=25, output_len=None) -> int:
+    """models/lib/wav2vec.py:67-71: output_len = int(seq_len / input_fps * output_fps) unless given."""
+    if output_len is not None:
+        return int(output_len)
+    return int(t50 / float(input_fps) * output_fps)
+
+
+class Wav2Vec2Model(_HFWav2Vec2Model):
+    def __init__(self, config):
+        super().__init__(config)
+        self.precision = default_precision()
+        self._packed = None
+        self._packed_key = None
+
+    # ------------------------------------------------------------------ weight packing (once per weight change)
+    def _pack_key(self):
+        return (self.precision,) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def _posconv_weight(self):
+        conv = self.encoder.pos_conv_embed.conv
+        if hasattr(conv, "parametrizations"):
+            g = conv.parametrizations.weight.original0
+            v = conv.parametrizations.weight.original1
+        else:  # transformers 4.x naming
+            g, v = conv.weight_g, conv.weight_v
+        return g * v / v.norm(p=2, dim=(0, 1), keepdim=True)
+
+    @torch.no_grad()
+    def _pack(self):
+        key = self._pack_key()
+        if self._packed is not None and key == self._packed_key:
+            return self._packed
+        cfg = self.config
+        if cfg.feat_extract_norm != "group" or cfg.do_stable_layer_norm or cfg.conv_bias:
+            raise NotImplementedError("only the wav2vec2-base layout (group-norm extractor, post-LN encoder, no conv bias)")
+        bf16 = self.precision == "bf16"
+        wdt = (lambda t: ops.cast_bf16(t)) if bf16 else (lambda t: t.detach().float().contiguous())
+        f32 = lambda t: t.detach().float().contiguous()  # noqa: E731
+        P = {}
+        convs = self.feature_extractor.conv_layers
+        P["conv0_w"] = f32(convs[0].conv.weight.reshape(cfg.conv_dim[0], cfg.conv_kernel[0]))
+        P["gn_w"], P["gn_b"] = f32(convs[0].layer_norm.weight), f32(convs[0].layer_norm.bias)
+        P["conv_w"] = []
+        for i in range(1, len(convs)):
+            w = convs[i].conv.weight  # [Cout, Cin, k] -> [Cout, k*Cin] tap-major (matches time-major activations)
+            P["conv_w"].append(wdt(w.permute(0, 2, 1).reshape(w.shape[0], -1).contiguous()))
+        fp = self.feature_projection
+        P["fp_ln_w"], P["fp_ln_b"] = f32(fp.layer_norm.weight), f32(fp.layer_norm.bias)
+        P["fp_w"], P["fp_b"] = wdt(fp.projection.weight), f32(fp.projection.bias)
+        k, g = cfg.num_conv_pos_embeddings, cfg.num_conv_pos_embedding_groups
+        cg = cfg.hidden_size // g
+        w = self._posconv_weight().float()  # [C, cg, k] -> [g][k][ci][co]
+        P["pos_w"] = w.reshape(g, cg, cg, k).permute(0, 3, 2, 1).contiguous()
+        P["pos_b"] = f32(self.encoder.pos_conv_embed.conv.bias)
+        P["enc_ln_w"], P["enc_ln_b"] = f32(self.encoder.layer_norm.weight), f32(self.encoder.layer_norm.bias)
+        P["layers"] = []
+        for lyr in self.encoder.layers:
+            a = lyr.attention
+            L = {
+                "qkv_w": wdt(torch.cat([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight], 0)),
+                "qkv_b": f32(torch.cat([a.q_proj.bias, a.k_proj.bias, a.v_proj.bias], 0)),
+                "o_w": wdt(a.out_proj.weight), "o_b": f32(a.out_proj.bias),
+                "ln1_w": f32(lyr.layer_norm.weight), "ln1_b": f32(lyr.layer_norm.bias),
+                "ff1_w": wdt(lyr.feed_forward.intermediate_dense.weight), "ff1_b": f32(lyr.feed_forward.intermediate_dense.bias),
+                "ff2_w": wdt(lyr.feed_forward.output_dense.weight), "ff2_b": f32(lyr.feed_forward.output_dense.bias),
+                "ln2_w": f32(lyr.final_layer_norm.weight), "ln2_b": f32(lyr.final_layer_norm.bias),
+            }
+            P["layers"].append(L)
+        self._packed, self._packed_key = P, key
+        return P
+
+    # ------------------------------------------------------------------ stages
+    def _feature_extractor(self, x, P):
+        """[B, N] fp32 -> time-major features [B, La, 512] (La = even-padded length), returns (tensor, T50, La)."""
+        cfg = self.config
+        B, n = x.shape
+        adt = torch.bfloat16 if self.precision == "bf16" else torch.float32
+        Cc = cfg.conv_dim[0]
+        L = (n - cfg.conv_kernel[0]) // cfg.conv_stride[0] + 1
+        La = L + (L & 1)
+        h = torch.empty((B, La, Cc), dtype=adt, device=x.device)
+        ops.conv0_gn_gelu(x, P["conv0_w"], P["gn_w"], P["gn_b"], h, La * Cc)
+        for i in range(1, len(cfg.conv_kernel)):
+            k, s = cfg.conv_kernel[i], cfg.conv_stride[i]
+            Lo = (L - k) // s + 1
+            Loa = Lo + (Lo & 1)
+            Co = cfg.conv_dim[i]
+            o = torch.empty((B, Loa, Co), dtype=adt, device=x.device)
+            ops.gemm(h, P["conv_w"][i - 1], None, o, batch=B, rows=Lo, N=Co, K=k * Cc, act=ACT_GELU, conv_taps=k, conv_stride=s,
+                     a_ld=Cc, a_batch_stride=La * Cc, a_rows_alloc=La, c_ld=Co, c_batch_stride=Loa * Co)
+            h, L, La, Cc = o, Lo, Loa, Co
+        return h, L, La
+
+    def _encoder_layer(self, h32, h16, Lw, B, T):
+        bf16 = self.precision == "bf16"
+        H = self.config.num_attention_heads
+        D = self.config.hidden_size // H
+        a_in = h16 if bf16 else h32
+        adt = torch.bfloat16 if bf16 else torch.float32
+        qkv = ops.linear(a_in, Lw["qkv_w"], Lw["qkv_b"], out_dtype=adt)
+        att = ops.mha(qkv, B, T, H, D, D ** -0.5)
+        y = ops.linear(att, Lw["o_w"], Lw["o_b"], residual=h32, out_dtype=torch.float32)
+        h1_32, h1_16 = ops.layernorm(y, Lw["ln1_w"], Lw["ln1_b"], want_bf16=bf16, eps=self.config.layer_norm_eps)
+        f = ops.linear(h1_16 if bf16 else h1_32, Lw["ff1_w"], Lw["ff1_b"], act=ACT_GELU, out_dtype=adt)
+        y2 = ops.linear(f, Lw["ff2_w"], Lw["ff2_b"], residual=h1_32, out_dtype=torch.float32)
+        return ops.layernorm(y2, Lw["ln2_w"], Lw["ln2_b"], want_bf16=bf16, eps=self.config.layer_norm_eps)
+
+    # ------------------------------------------------------------------ reference signature
+    @torch.no_grad()
+    def forward(self, input_values, dataset=None, attention_mask=None, output_attentions=None, output_hidden_states=None,
+                return_dict=None, frame_num=None):
+        if self.training and (self.config.apply_spec_augment or self.config.layerdrop > 0):
+            raise NotImplementedError("train-mode SpecAugment / LayerDrop are not on the inference hot path; call .eval()")
+        if attention_mask is not None:
+            raise NotImplementedError("attention_mask is never passed on the AVI-Talking path (faceformer_disentangle.py:775)")
+        if not input_values.is_cuda:
+            raise RuntimeError("avi_talking_b200.Wav2Vec2Model runs on CUDA only (no CPU fallback)")
+        cfg = self.config
+        P = self._pack()
+        x = input_values.contiguous().float()
+        B = x.shape[0]
+        bf16 = self.precision == "bf16"
+        feats, T50, La = self._feature_extractor(x, P)                                      # wav2vec.py:97
+        T = linear_interpolation_length(T50, 50, 25, frame_num)                             # :108
+        Cf = cfg.conv_dim[-1]
+        hn32, hn16 = ops.lerp_layernorm(feats, La * Cf, B, T50, T, P["fp_ln_w"], P["fp_ln_b"], want_f32=not bf16,
+                                        want_bf16=bf16, eps=cfg.layer_norm_eps)
+        proj = ops.linear(hn16 if bf16 else hn32, P["fp_w"], P["fp_b"], out_dtype=torch.float32)   # :120
+        h32, h16 = ops.posconv_ln(proj, P["pos_w"], P["pos_b"], P["enc_ln_w"], P["enc_ln_b"], B, T,
+                                  cfg.num_conv_pos_embedding_groups, cfg.num_conv_pos_embeddings, want_bf16=bf16,
+                                  eps=cfg.layer_norm_eps)
+        all_hidden = (h32.view(B, T, -1),) if output_hidden_states else None
+        for Lw in P["layers"]:                                                               # :142-148
+            h32, h16 = self._encoder_layer(h32, h16, Lw, B, T)
+            if output_hidden_states:
+                all_hidden = all_hidden + (h32.view(B, T, -1),)
+        out = h32.view(B, T, cfg.hidden_size)
+        # The reference forces output_attentions=True (:90) but no caller reads them (faceformer_disentangle.py:535,638,775
+        # use .last_hidden_state only); the fused attention kernel never materialises the [B,12,T,T] maps.
+        if return_dict is False:
+            return (out,) + ((all_hidden,) if all_hidden is not None else ())
+        return BaseModelOutput(last_hidden_state=out, hidden_states=all_hidden, attentions=None)

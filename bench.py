@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""Benchmark of the audio -> wav2vec2 -> FaceFormer decoder -> vertices (+ FLAME LBS) hot path.
+
+  python bench.py --gpus N --steps K --warmup W            # product arm (libavi_b200.so on the B200s)
+  python bench.py --impl reference --steps K --warmup W    # the reference's CPU implementation (oracle port) on host cores
+
+One "step" = one pass of the hot path over one batch of synthetic clips:
+  Faceformer.predict (wav2vec2 encoder + autoregressive FaceFormer-disentangle decoder + vertex head, [B,T,15069])
+  followed by Faceformer.convert_coeff2verts (FLAME blendshapes + LBS) on B*T frames of 53-d coefficients.
+Workload at N=1 = BASELINE.json configs[1]: 64 clips x 10 s of 16 kHz audio (T = 249 frames per clip at 25 fps);
+for N>1 each rank processes its own 64 clips (clips shard with no collective: "scaling": "weak", configs[2]).
+Metric: generated FLAME frames per second (one frame = one [5023 x 3] fp32 vertex set of the decoder output).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--clips", type=int, default=64, help="clips per GPU per step")
+    ap.add_argument("--seconds", type=float, default=10.0)
+    ap.add_argument("--fd", type=int, default=64)
+    ap.add_argument("--precision", default=os.environ.get("AVI_B200_PRECISION", "bf16"), choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-clips", type=int, default=2, help="clips in the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            p = json.load(fh)
+        return dict(hbm=float(p["hbm_gbs"]), tc_burst=float(p["bf16_tflops"]), tc=float(p["bf16_tflops_sustained"]), src="measured")
+    except Exception:
+        return dict(hbm=6650.0, tc_burst=1590.0, tc=1400.0, src="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.rows = index, threading.Event(), []
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def n_frames(n_samples):
+    n = n_samples
+    for k, s in zip((10, 3, 3, 3, 3, 2, 2), (5, 2, 2, 2, 2, 2, 2)):
+        n = (n - k) // s + 1
+    return int(n / 50.0 * 25)
+
+
+def make_inputs(clips, n_samples, T, seed):
+    """Synthetic z-normalised audio, emotion embeddings and FLAME coefficients for one step, in PINNED host memory."""
+    rng = np.random.default_rng(seed)
+    a = rng.standard_normal((clips, n_samples), dtype=np.float32)
+    a = (a - a.mean(1, keepdims=True)) / np.sqrt(a.var(1, keepdims=True) + 1e-7)
+    host = dict(
+        audio=torch.from_numpy(a.astype(np.float32)),
+        emo=torch.from_numpy(rng.standard_normal((clips, T, 30), dtype=np.float32)),
+        coeff=torch.from_numpy(rng.standard_normal((clips * T, 53), dtype=np.float32)),
+        pose=torch.from_numpy((0.1 * rng.standard_normal((clips * T, 6))).astype(np.float32)),
+        shape=torch.from_numpy(rng.standard_normal((clips, 100), dtype=np.float32)),
+    )
+    return host
+
+
+# ----------------------------------------------------------------------------------------------------------------- CPU reference arm
+def cpu_reference_step(state, audio, emo, coeff, pose, shape_per_frame):
+    """The reference's own CPU algorithm for one batch (oracle port: faceformer_disentangle.py predict + convert_coeff2verts)."""
+    from oracle import faceformer_oracle as ffo
+    from oracle import flame_oracle as fo
+    v = ffo.predict(state["sd_ff"], state["sd_w2v"], state["template"], audio, emo, cached=True)   # clip by clip inside
+    fv = fo.convert_coeff2verts(state["buf"], state["cmean"], state["cstd"], coeff, pose.clone(), shape_per_frame)
+    return v, fv
+
+
+def cpu_state(fd):
+    from avi_talking_b200 import synth
+    rng = np.random.default_rng(53)
+    buf = synth.flame_buffers()
+    return dict(sd_ff=synth.faceformer_state(fd=fd, seed=74), sd_w2v=synth.wav2vec2_state(0), buf=buf,
+                template=buf["v_template"].reshape(1, 1, 15069),
+                cmean=torch.from_numpy(rng.normal(0, 0.3, size=53).astype("float32")),
+                cstd=torch.from_numpy((0.3 + rng.uniform(size=53)).astype("float32")))
+
+
+def time_cpu(args, n_samples, T, clips, reps):
+    torch.set_num_threads(os.cpu_count() or 1)
+    st = cpu_state(args.fd)
+    host = make_inputs(clips, n_samples, T, seed=4242)
+    shape_pf = host["shape"].repeat_interleave(T, 0)
+    times = []
+    for r in range(reps):
+        t0 = time.perf_counter()
+        cpu_reference_step(st, host["audio"], host["emo"], host["coeff"], host["pose"], shape_pf)
+        times.append(time.perf_counter() - t0)
+    return times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_samples = int(round(args.seconds * 16000))
+    T = n_frames(n_samples)
+    clips = 1  # bounded sample: one 10 s clip per step (the reference decoder is batch-1 anyway, faceformer_disentangle.py:441)
+    times = time_cpu(args, n_samples, T, clips, args.warmup + args.steps)[args.warmup:]
+    dt = sum(times)
+    val = clips * T * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "generated FLAME frames/sec", "value": val, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"FaceFormer-disentangle predict + FLAME LBS, {args.seconds:g} s 16 kHz clips, fd={args.fd} "
+                               f"(bounded sample: {clips} clip per step of the 64-clip batch)", "clips_per_step": clips,
+                   "frames_per_clip": T},
+        "cpu_baseline": {"value": val, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{clips} x {args.seconds:g} s clip per step, oracle restatement of the reference in fp32 torch-CPU "
+                                   "(KV-cached O(T) decoder, i.e. faster than the reference's O(T^2) loop)"},
+        "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------- product arm
+def run_ours(args):
+    import torch.distributed as dist
+    from avi_talking_b200 import _lib, ops
+    from avi_talking_b200.smoke import build_models
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load(check_symbols=True)
+
+    n_samples = int(round(args.seconds * 16000))
+    T = n_frames(n_samples)
+    B = args.clips
+    model = build_models(args.precision, fd=args.fd, device=dev, flame_dir=f"/tmp/avi_flame_assets_r{rank}")
+    host = {k: v.pin_memory() for k, v in make_inputs(B, n_samples, T, seed=1000 + rank).items()}
+    devin = {k: v.to(dev) for k, v in host.items()}
+    out_host = torch.empty((B, T, 15069), dtype=torch.float32).pin_memory()
+    flame_host = torch.empty((B * T, 5023, 3), dtype=torch.float32).pin_memory()
+
+    def step(inp):
+        v = model.predict_from_embeddings(inp["audio"], inp["emo"])
+        fv = model.convert_coeff2verts(inp["coeff"], inp["pose"], inp["shape"].repeat_interleave(T, 0))
+        return v, fv
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # inputs (41 MB audio + activations of several GB per step) are far larger than the 126 MB L2, so no explicit flush
+    for _ in range(max(args.warmup, 3)):
+        step(devin)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    n0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step(devin)
+    e1.record()
+    barrier()
+    dt_ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - n0
+
+    # end to end through the public API with HOST buffers: H2D of the step's inputs and D2H of its results inside the timed region
+    def e2e_step():
+        inp = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        v, fv = step(inp)
+        out_host.copy_(v, non_blocking=True)
+        flame_host.copy_(fv, non_blocking=True)
+
+    e2e_step()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    f1.record()
+    barrier()
+    e2e_ms = f0.elapsed_time(f1)
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+
+    # roofline pass: one extra step with CUDA events around every launch (not part of the timed numbers above)
+    ops.PROFILE = []
+    step(devin)
+    torch.cuda.synchronize()
+    prof = ops.PROFILE
+    ops.PROFILE = None
+    agg = {}
+    for name, a, b, work in prof:
+        t = a.elapsed_time(b)
+        d = agg.setdefault(name, [0, 0.0, 0.0])
+        d[0] += 1
+        d[1] += t
+        d[2] += work
+    step_ms_prof = sum(d[1] for d in agg.values())
+
+    if world > 1:
+        t = torch.tensor([dt_ms, e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt_ms, e2e_ms = t.tolist()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    frames = world * B * T * args.steps
+    value = frames / (dt_ms / 1e3)
+    e2e_val = frames / (e2e_ms / 1e3)
+    g = agg.get("gemm_bf16_tc") or agg.get("gemm_f32")
+    gname = "gemm_bf16_tc" if "gemm_bf16_tc" in agg else "gemm_f32"
+    achieved = g[2] / (g[1] / 1e3) / 1e12
+    roofline = {"kernel": gname, "bound": "tensor", "achieved": achieved, "peak": pk["tc"], "unit": "TFLOP/s",
+                "frac": achieved / pk["tc"], "traffic": None, "peak_source": pk["src"] + " (sustained bf16)",
+                "launches_per_step": g[0], "avg_launch_ms": g[1] / g[0], "share_of_step": g[1] / step_ms_prof}
+    fl = agg.get("flame_lbs")
+    extra = {}
+    if fl:
+        gbs = fl[2] / (fl[1] / 1e3) / 1e9
+        extra["flame_lbs"] = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"]}
+    kernels = {k: {"launches": v[0], "ms": round(v[1], 4)} for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])}
+
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    d2h = out_host.numel() * 4 + flame_host.numel() * 4
+    line = {
+        "metric": "generated FLAME frames/sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": dt_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+        "config": {"workload": f"BASELINE configs[1]: FaceFormer-disentangle predict (wav2vec2 + AR decoder + vertex head) + FLAME LBS, "
+                               f"{B} clips x {args.seconds:g} s per GPU, fd={args.fd}, random-init (seeded) weights",
+                   "clips_per_gpu": B, "frames_per_clip": T, "precision": args.precision, "l2_policy": "inputs larger than L2",
+                   "realtime_factor_25fps": value / 25.0},
+        "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": launches,
+        "clocks": sampler.summary(),
+        "roofline": roofline,
+        "roofline_other": extra,
+        "kernels_ms_per_step": kernels,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        t = time_cpu(args, n_samples, T, args.cpu_clips, 2)
+        cpu_val = args.cpu_clips * T / min(t)
+        line["cpu_baseline"] = {"value": cpu_val, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": f"{args.cpu_clips} of the {B} clips, best of 2 runs, oracle restatement of the reference "
+                                          "(fp32 torch-CPU, KV-cached O(T) decoder)"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device for the product arm (there is no CPU fallback); "
+                             "use --impl reference for the CPU reference arm")
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

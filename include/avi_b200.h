@@ -1,0 +1,158 @@
+/*
+ * avi_b200.h - C ABI of libavi_b200.so: hand-written sm_100a kernels for the
+ * audio -> wav2vec2 -> FaceFormer decoder -> FLAME vertices hot path of
+ * sunyasheng/AVI-Talking.
+ *
+ * The reference has no FFI of its own (it is pure Python/PyTorch); the
+ * seam is its nn.Module classes.  Every entry point below replaces the ATen /
+ * cuBLAS / cuDNN work a reference method does, cited as file:line relative to
+ * the upstream repository root.  The Python drop-in classes under
+ * avi_talking_b200/ bind these with ctypes.
+ *
+ * Conventions (all entry points):
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - plain pointers and sizes only, no torch / C++ types;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *   - return 0 on success, non-zero on error; avi_last_error() gives the message
+ *     (thread-local).  The Python side turns non-zero into RuntimeError;
+ *   - nothing allocates, frees or synchronises; all calls are asynchronous on
+ *     `stream` and re-entrant across streams (the tensor-core GEMM keeps an
+ *     internal, mutex-protected cache of TMA descriptors only);
+ *   - row-major everywhere; activations are time-major [clip, frame, channel].
+ */
+#ifndef AVI_B200_H_
+#define AVI_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AVI_B200_VERSION 100 /* 0.1.0 */
+
+int avi_version(void);
+const char* avi_last_error(void);
+/* number of kernel launches this process has issued through the library (for bench.py's gpu_launches) */
+int64_t avi_launch_count(void);
+
+/* ------------------------------------------------------------------ dense contraction ------------------------------------------------------------------
+ * C[b, r, n] = epi( sum_k A[b, r, k] * W[n, k] + bias[n] ) (+ residual[b, r, n])
+ * Replaces torch.nn.Linear / Conv1d-as-GEMM calls: HF Wav2Vec2 q/k/v/out_proj, feed_forward, feature_projection,
+ * conv_layers[1..6] (models/lib/wav2vec.py:97,120,142 via transformers), audio_feature_map / v_merge2hidden /
+ * vertice_map_r (models/faceformer_disentangle.py:437,473,776).
+ *
+ * A rows may overlap (Conv1d as a GEMM over time-major activations): the row for (b, r) starts at
+ *   A + b*a_batch_stride + r*conv_stride*a_ld  and is conv_taps*a_ld... see AviGemmArgs below.
+ */
+enum { AVI_ACT_NONE = 0, AVI_ACT_GELU = 1 /* exact erf */, AVI_ACT_RELU = 2 };
+enum { AVI_DT_F32 = 0, AVI_DT_BF16 = 1 };
+
+typedef struct AviGemmArgs {
+  const void* A;      /* activations, dtype a_dtype; element (b, row, c) at A + b*a_batch_stride + row*a_ld + c              */
+  const void* W;      /* weights [N, K] row-major (nn.Linear layout; conv weights packed [N, taps*C] tap-major), dtype a_dtype */
+  const float* bias;  /* [N] or NULL                                                                                         */
+  const float* residual; /* fp32 [b, r, n] at residual + b*res_batch_stride + r*res_ld + n, or NULL (added AFTER the activation) */
+  void* C;            /* output, dtype c_dtype; element (b, r, n) at C + b*c_batch_stride + r*c_ld + n                       */
+  void* C2;           /* optional second copy of the output in the other dtype (same strides), or NULL                      */
+  int32_t batch;      /* b extent                                                                                            */
+  int32_t rows;       /* r extent (output rows per batch entry)                                                              */
+  int32_t N;
+  int32_t K;          /* = conv_taps * C_in                                                                                   */
+  int32_t conv_taps;  /* 1 for a plain GEMM                                                                                   */
+  int32_t conv_stride;/* 1 for a plain GEMM; output row r reads input rows r*conv_stride .. +conv_taps-1                      */
+  int64_t a_ld;       /* elements between consecutive INPUT rows (= C_in for a conv, = K for a plain GEMM unless padded)       */
+  int64_t a_batch_stride;
+  int64_t a_rows_alloc; /* input rows that are safely readable per batch entry (tensor-core path: TMA bound)                 */
+  int64_t c_ld, c_batch_stride;
+  int64_t res_ld, res_batch_stride;
+  int32_t a_dtype, c_dtype, act;
+} AviGemmArgs;
+
+/* fp32 CUDA-core path (exact mode, any shape). a_dtype must be AVI_DT_F32. */
+int avi_gemm_f32(const AviGemmArgs* args, void* stream);
+/* bf16 tcgen05/TMEM/TMA path. a_dtype must be AVI_DT_BF16; K % 64 == 0, a_ld % 8 == 0, 16-byte aligned bases. */
+int avi_gemm_bf16_tc(const AviGemmArgs* args, void* stream);
+/* 1 if the tensor-core path accepts these shapes (host-side check only) */
+int avi_gemm_bf16_tc_supported(const AviGemmArgs* args);
+/* fp32 -> bf16 (weights packing / activation staging), n elements */
+int avi_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------ wav2vec2 pieces ------------------------------------------------------------------ */
+/* Conv1d(1->512,k=10,s=5,no bias) + GroupNorm(512 groups) + GELU   (HF Wav2Vec2GroupNormConvLayer; models/lib/wav2vec.py:97).
+ * audio [B, n_samples] fp32 -> out [B, L0, C] (time-major, dtype out_dtype, batch stride out_batch_stride elements).
+ * stats: scratch of B*C*2 doubles (zeroed by the call). */
+int avi_w2v_conv0_gn_gelu(const float* audio, const float* w /*[C,10]*/, const float* gn_w, const float* gn_b,
+                          void* stats, void* out, int32_t out_dtype, int64_t out_batch_stride,
+                          int32_t B, int32_t n_samples, int32_t C, float eps, void* stream);
+
+/* align_corners linear resample over time + LayerNorm(C): models/lib/wav2vec.py:67-73,108 + HF feature_projection.layer_norm.
+ * in [B, T_in, C] (in_dtype, batch stride in elements) -> out_f32 / out_bf16 [B*T_out, C] (either may be NULL). */
+int avi_w2v_lerp_layernorm(const void* in, int32_t in_dtype, int64_t in_batch_stride, const float* ln_w, const float* ln_b,
+                           float* out_f32, void* out_bf16, int32_t B, int32_t T_in, int32_t T_out, int32_t C, float eps,
+                           void* stream);
+
+/* y = LayerNorm(x (+ res)) over the last dim; x, res fp32 [rows, C] (res may be NULL); writes fp32 and/or bf16 copies.
+ * (HF encoder layer_norm / final_layer_norm; nn.TransformerDecoderLayer norm1-3) */
+int avi_layernorm(const float* x, const float* res, const float* w, const float* b, float* out_f32, void* out_bf16, int64_t rows, int32_t C,
+                  float eps, void* stream);
+
+/* h = LayerNorm(x + GELU(grouped_conv1d(x)[..., :-1])) : HF Wav2Vec2PositionalConvEmbedding + encoder.layer_norm.
+ * x fp32 [B, T, C]; w_packed fp32 [groups][k][C/groups in][C/groups out] (weight-norm g*v/||v|| already applied, packed
+ * once at weight-load time); out_f32 is required (doubles as the conv scratch), optional bf16 copy. */
+int avi_w2v_posconv_ln(const float* x, const float* w_packed, const float* conv_bias, const float* ln_w, const float* ln_b,
+                       float* out_f32, void* out_bf16, int32_t B, int32_t T, int32_t C, int32_t groups, int32_t k, float eps,
+                       void* stream);
+
+/* softmax(q k^T * scale) v per (clip, head); qkv [B, T, 3*H*D] packed (q | k | v), dtype qkv_dtype; out [B, T, H*D] same dtype.
+ * (HF Wav2Vec2Attention / eager_attention_forward, no mask) */
+int avi_mha_fwd(const void* qkv, void* out, int32_t dtype, int32_t B, int32_t T, int32_t H, int32_t D, float scale, void* stream);
+
+/* ------------------------------------------------------------------ FaceFormer decoder (Path A) ------------------------------------------------------------------ */
+typedef struct AviDecoderWeights { /* all fp32 device pointers; fd = feature_dim, 4 heads, dff = 2*fd */
+  const float *sa_in_w, *sa_in_b;   /* [3fd, fd], [3fd]  self_attn.in_proj                                   */
+  const float *sa_out_w, *sa_out_b; /* [fd, fd], [fd]                                                        */
+  const float *ff1_w, *ff1_b;       /* [dff, fd]                                                             */
+  const float *ff2_w, *ff2_b;       /* [fd, dff]                                                             */
+  const float *ln1_w, *ln1_b, *ln2_w, *ln2_b, *ln3_w, *ln3_b;
+  const float *fb_w, *fb_b;         /* [fd, fd], [fd]: composed feedback map vertice_map o vertice_map_r (AR only) */
+  /* every *_w above is stored TRANSPOSED, [in, out] */
+  const float *pe;                  /* [period, fd] periodic positional encoding table                       */
+} AviDecoderWeights;
+
+/* Autoregressive branch of Faceformer.forward_ff (models/faceformer_disentangle.py:461-476), KV-cached, one CTA per clip.
+ * All matrices in AviDecoderWeights are TRANSPOSED nn.Linear weights ([in, out], packed once at weight-load time).
+ * cross [B, T, fd]: the (degenerate) cross-attention term out_proj(v_proj(memory_t)) precomputed by GEMMs;
+ * style [B, fd]; hidden_out [B, T, fd] = decoder output rows (input to vertice_map_r).
+ * kv_scratch fp32 [B, 2, T, fd+1]: only used when the K/V cache does not fit in shared memory (may be NULL otherwise). */
+int avi_ff_decoder_ar(const AviDecoderWeights* w, const float* cross, const float* style, float* hidden_out, float* kv_scratch,
+                      int32_t B, int32_t T, int32_t fd, int32_t period, void* stream);
+
+/* Biased causal self-attention over whole sequences (teacher-forced branch :445-458; mask = init_biased_mask :56-77 built on
+ * the fly, 4 heads): qkv fp32 [B, T, 3*fd] (q | k | v) -> out [B, T, fd]. */
+int avi_ff_biased_attn(const float* qkv, float* out, int32_t B, int32_t T, int32_t fd, int32_t period, void* stream);
+
+/* ------------------------------------------------------------------ FLAME ------------------------------------------------------------------ */
+/* One-time packing of the static FLAME buffers (third_party/inferno/inferno/models/DecaFLAME.py:60-74):
+ *   dirs  [NB+36+1 (padded to K_pad), V*3] : rows 0..NB-1 = shapedirs^T, NB..NB+35 = posedirs, NB+36 = v_template
+ *   jreg  [15, NB+1]                       : J_regressor applied to shapedirs (cols 0..NB-1) and to v_template (col NB)  */
+int avi_flame_pack(const float* shapedirs /*[V,3,NB]*/, const float* posedirs /*[36,V*3]*/, const float* v_template /*[V,3]*/,
+                   const float* J_regressor /*[5,V]*/, float* dirs, float* jreg, int32_t V, int32_t NB, int32_t K_pad, void* stream);
+
+/* lbs() with pose2rot=True (third_party/inferno/inferno/utils/lbs.py:142-234) for F frames, 5 joints, parents [-1,0,1,1,1].
+ * betas [F, NB]; full_pose [F, 15]; lbs_weights [V, 5]; coef scratch fp32 [F, K_pad]; A scratch fp32 [F, 5, 12];
+ * verts out [F, V, 3]; joints out [F, 5, 3] or NULL; dyn_rows out int32 [F] or NULL = the row of the dynamic contour
+ * landmark table each frame selects (DecaFLAME.py:110-149, neck_kin_chain = [1, 0]). */
+int avi_flame_lbs_fwd(const float* betas, const float* full_pose, const float* dirs, const float* jreg, const float* lbs_weights,
+                      float* coef, float* A, float* verts, float* joints, int32_t* dyn_rows, int32_t F, int32_t V, int32_t NB,
+                      int32_t K_pad, void* stream);
+
+/* barycentric landmark gather (lbs.py:103-139): out[f, l, :] = sum_c bary[f|0, l, c] * verts[f, faces[idx[f|0, l], c], :].
+ * per_frame = 1 when idx/bary carry a frame dimension (dynamic contour landmarks). */
+int avi_flame_landmarks(const float* verts, const int64_t* faces, const int64_t* idx, const float* bary, float* out,
+                        int32_t F, int32_t V, int32_t L, int32_t per_frame, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AVI_B200_H_ */

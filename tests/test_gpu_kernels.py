@@ -1,0 +1,201 @@
+"""Per-kernel parity tests on the B200 (call through the C ABI via avi_talking_b200.ops).
+References are float64 torch-on-CPU restatements of the same op; tolerances are written per test."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from avi_talking_b200 import ops as _ops
+    return _ops
+
+
+def _rng(seed):
+    return np.random.default_rng(seed)
+
+
+def _t(a, dev="cuda", dt=torch.float32):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dt).to(dev)
+
+
+def _act(x, act):
+    if act == 1:
+        return F.gelu(x)
+    if act == 2:
+        return F.relu(x)
+    return x
+
+
+def _gemm_ref(A, W, bias, act, residual):
+    y = A.double() @ W.double().t()
+    if bias is not None:
+        y = y + bias.double()
+    y = _act(y, act)
+    if residual is not None:
+        y = y + residual.double()
+    return y
+
+
+@pytest.mark.parametrize("rows,N,K,act,use_res", [(70, 100, 36, 0, False), (129, 64, 100, 2, True), (257, 130, 768, 1, True)])
+def test_gemm_f32_plain(ops, rows, N, K, act, use_res):
+    r = _rng(1)
+    A, W, b = r.normal(size=(rows, K)), r.normal(size=(N, K)) / math.sqrt(K), r.normal(size=(N,))
+    res = r.normal(size=(rows, N)) if use_res else None
+    out = ops.linear(_t(A), _t(W), _t(b), act=act, residual=None if res is None else _t(res))
+    ref = _gemm_ref(_t(A, "cpu"), _t(W, "cpu"), _t(b, "cpu"), act, None if res is None else _t(res, "cpu"))
+    assert (out.cpu().double() - ref).abs().max().item() < 2e-5
+
+
+def _conv_ref(x, w, k, s):
+    # x [B, L, C] time-major ; w [Cout, Cin, k]
+    return F.gelu(F.conv1d(x.double().transpose(1, 2), w.double(), stride=s)).transpose(1, 2)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_gemm_conv_mode(ops, dtype):
+    r = _rng(2)
+    B, L, Cin, Cout, k, s = 3, 301, 128, 192, 3, 2
+    La = L + (L & 1)
+    x = torch.zeros(B, La, Cin)
+    x[:, :L] = torch.from_numpy(r.normal(size=(B, L, Cin)).astype(np.float32))
+    w = torch.from_numpy((r.normal(size=(Cout, Cin, k)) / math.sqrt(Cin * k)).astype(np.float32))
+    xq, wq = x.to(dtype).float(), w.to(dtype).float()
+    Lo = (L - k) // s + 1
+    Loa = Lo + (Lo & 1)
+    out = torch.full((B, Loa, Cout), float("nan"), dtype=dtype, device="cuda")
+    wp = w.permute(0, 2, 1).reshape(Cout, k * Cin).contiguous().to(dtype).cuda()
+    ops.gemm(x.to(dtype).cuda(), wp, None, out, batch=B, rows=Lo, N=Cout, K=k * Cin, act=1, conv_taps=k, conv_stride=s,
+             a_ld=Cin, a_batch_stride=La * Cin, a_rows_alloc=La, c_ld=Cout, c_batch_stride=Loa * Cout)
+    ref = _conv_ref(xq[:, :L], wq, k, s)
+    got = out[:, :Lo].float().cpu().double()
+    tol = 2e-5 if dtype == torch.float32 else 2e-2  # bf16 output rounding (2^-9 relative on |y| <~ 4)
+    assert (got - ref).abs().max().item() < tol
+
+
+@pytest.mark.parametrize("rows,N,K,act,use_res,out_dt,out2", [
+    (300, 512, 128, 0, False, torch.float32, False),
+    (1000, 768, 768, 1, False, torch.bfloat16, False),
+    (515, 2304, 768, 0, True, torch.float32, True),
+    (390, 15069, 64, 0, False, torch.float32, False),   # vertex head: ragged N, unaligned rows
+    (128, 256, 3072, 0, True, torch.float32, False),
+])
+def test_gemm_bf16_tc(ops, rows, N, K, act, use_res, out_dt, out2):
+    r = _rng(3)
+    A = torch.from_numpy(r.normal(size=(rows, K)).astype(np.float32)).bfloat16()
+    W = torch.from_numpy((r.normal(size=(N, K)) / math.sqrt(K)).astype(np.float32)).bfloat16()
+    b = torch.from_numpy(r.normal(size=(N,)).astype(np.float32))
+    res = torch.from_numpy(r.normal(size=(rows, N)).astype(np.float32)) if use_res else None
+    o = ops.linear(A.cuda(), W.cuda(), b.cuda(), act=act, residual=None if res is None else res.cuda(), out_dtype=out_dt,
+                   out2_dtype=(torch.bfloat16 if out_dt == torch.float32 else torch.float32) if out2 else None)
+    ref = _gemm_ref(A.float(), W.float(), b, act, res)
+    outs = o if isinstance(o, tuple) else (o,)
+    for t in outs:
+        tol = 1e-4 if t.dtype == torch.float32 else 4e-2
+        err = (t.float().cpu().double() - ref).abs().max().item()
+        assert err < tol, (t.dtype, err)
+
+
+def test_gemm_bf16_tc_many_tiles_persistent(ops):
+    """More tiles than SMs and >2 tiles per CTA: exercises the smem ring wrap and both TMEM accumulator stages."""
+    r = _rng(4)
+    rows, N, K = 128 * 40, 1024, 256   # 160 tiles... x4 n-tiles = 160 -> >148
+    A = torch.from_numpy(r.normal(size=(rows, K)).astype(np.float32)).bfloat16()
+    W = torch.from_numpy((r.normal(size=(N, K)) / math.sqrt(K)).astype(np.float32)).bfloat16()
+    o = ops.linear(A.cuda(), W.cuda(), None, out_dtype=torch.float32)
+    ref = A.float().double() @ W.float().double().t()
+    assert (o.cpu().double() - ref).abs().max().item() < 1e-4
+    rows = 128 * 148 * 3 + 17
+    A = torch.from_numpy(r.normal(size=(rows, 64)).astype(np.float32)).bfloat16()
+    W = torch.from_numpy((r.normal(size=(256, 64)) / 8).astype(np.float32)).bfloat16()
+    o = ops.linear(A.cuda(), W.cuda(), None, out_dtype=torch.float32)
+    ref = A.float().double() @ W.float().double().t()
+    assert (o.cpu().double() - ref).abs().max().item() < 1e-4
+
+
+@pytest.mark.parametrize("out_dt", [torch.float32, torch.bfloat16])
+def test_conv0_gn_gelu(ops, out_dt):
+    r = _rng(5)
+    B, n, C = 2, 4000, 512
+    x = torch.from_numpy(r.normal(size=(B, n)).astype(np.float32))
+    w = torch.from_numpy((r.normal(size=(C, 1, 10)) * 0.4).astype(np.float32))
+    g = torch.from_numpy((1 + 0.1 * r.normal(size=C)).astype(np.float32))
+    bt = torch.from_numpy((0.1 * r.normal(size=C)).astype(np.float32))
+    L = (n - 10) // 5 + 1
+    La = L + (L & 1)
+    out = torch.zeros(B, La, C, dtype=out_dt, device="cuda")
+    ops.conv0_gn_gelu(x.cuda(), w.reshape(C, 10).cuda(), g.cuda(), bt.cuda(), out, La * C)
+    ref = F.gelu(F.group_norm(F.conv1d(x.double()[:, None], w.double(), stride=5), C, g.double(), bt.double(), 1e-5)).transpose(1, 2)
+    tol = 2e-5 if out_dt == torch.float32 else 3e-2
+    assert (out[:, :L].float().cpu().double() - ref).abs().max().item() < tol
+
+
+@pytest.mark.parametrize("T_in,T_out", [(49, 24), (199, 99), (499, 249), (49, 20), (10, 1)])
+def test_lerp_layernorm(ops, T_in, T_out):
+    r = _rng(6)
+    B, C = 2, 512
+    x = torch.from_numpy(r.normal(size=(B, T_in + 1, C)).astype(np.float32))
+    g = torch.from_numpy((1 + 0.1 * r.normal(size=C)).astype(np.float32))
+    bt = torch.from_numpy((0.1 * r.normal(size=C)).astype(np.float32))
+    o32, o16 = ops.lerp_layernorm(x.cuda(), (T_in + 1) * C, B, T_in, T_out, g.cuda(), bt.cuda(), True, True)
+    y = F.interpolate(x[:, :T_in].transpose(1, 2), size=T_out, align_corners=True, mode="linear").transpose(1, 2)
+    ref = F.layer_norm(y, (C,), g, bt, 1e-5).reshape(B * T_out, C)
+    assert (o32.cpu() - ref).abs().max().item() < 1e-5
+    assert (o16.float().cpu() - ref).abs().max().item() < 3e-2
+
+
+def test_layernorm_with_residual(ops):
+    r = _rng(7)
+    x = torch.from_numpy(r.normal(size=(77, 768)).astype(np.float32))
+    rs = torch.from_numpy(r.normal(size=(77, 768)).astype(np.float32))
+    g = torch.from_numpy((1 + 0.1 * r.normal(size=768)).astype(np.float32))
+    bt = torch.from_numpy((0.1 * r.normal(size=768)).astype(np.float32))
+    o, _ = ops.layernorm(x.cuda(), g.cuda(), bt.cuda())
+    assert (o.cpu() - F.layer_norm(x, (768,), g, bt, 1e-5)).abs().max().item() < 1e-5
+    o, o16 = ops.layernorm(x.cuda(), g.cuda(), bt.cuda(), res=rs.cuda(), want_bf16=True)
+    ref = F.layer_norm(x + rs, (768,), g, bt, 1e-5)
+    assert (o.cpu() - ref).abs().max().item() < 1e-5
+    assert (o16.float().cpu() - ref).abs().max().item() < 3e-2
+    x64 = torch.from_numpy(r.normal(size=(5, 64)).astype(np.float32))
+    o, _ = ops.layernorm(x64.cuda(), g[:64].cuda(), bt[:64].cuda())
+    assert (o.cpu() - F.layer_norm(x64, (64,), g[:64], bt[:64], 1e-5)).abs().max().item() < 1e-5
+
+
+@pytest.mark.parametrize("T", [24, 99, 130])
+def test_posconv_ln(ops, T):
+    r = _rng(8)
+    B, C, G, K = 2, 768, 16, 128
+    x = torch.from_numpy(r.normal(size=(B, T, C)).astype(np.float32))
+    w = torch.from_numpy((r.normal(size=(C, C // G, K)) / math.sqrt(48 * 128) * 2).astype(np.float32))
+    cb = torch.from_numpy((0.02 * r.normal(size=C)).astype(np.float32))
+    g = torch.from_numpy((1 + 0.1 * r.normal(size=C)).astype(np.float32))
+    bt = torch.from_numpy((0.1 * r.normal(size=C)).astype(np.float32))
+    wp = w.reshape(G, 48, 48, K).permute(0, 3, 2, 1).contiguous()
+    o32, o16 = ops.posconv_ln(x.reshape(B * T, C).cuda(), wp.cuda(), cb.cuda(), g.cuda(), bt.cuda(), B, T, G, K, True)
+    pc = F.conv1d(x.double().transpose(1, 2), w.double(), cb.double(), padding=K // 2, groups=G)[:, :, :-1]
+    ref = F.layer_norm(x.double() + F.gelu(pc).transpose(1, 2), (C,), g.double(), bt.double(), 1e-5).reshape(B * T, C)
+    assert (o32.cpu().double() - ref).abs().max().item() < 2e-5
+    assert (o16.float().cpu().double() - ref).abs().max().item() < 3e-2
+
+
+@pytest.mark.parametrize("T,dtype", [(24, torch.float32), (249, torch.float32), (300, torch.bfloat16), (129, torch.bfloat16)])
+def test_mha(ops, T, dtype):
+    r = _rng(9)
+    B, H, D = 2, 12, 64
+    qkv = torch.from_numpy(r.normal(size=(B, T, 3 * H * D)).astype(np.float32)).to(dtype)
+    out = ops.mha(qkv.cuda().reshape(B * T, -1), B, T, H, D, D ** -0.5)
+    q, k, v = [t.reshape(B, T, H, D).transpose(1, 2) for t in qkv.float().double().split(H * D, dim=-1)]
+    a = torch.softmax(q @ k.transpose(2, 3) * D ** -0.5, -1)
+    ref = (a @ v).transpose(1, 2).reshape(B * T, H * D)
+    tol = 2e-5 if dtype == torch.float32 else 2e-2
+    assert (out.float().cpu().double() - ref).abs().max().item() < tol
+
+
+def test_cast_bf16(ops):
+    x = torch.from_numpy(_rng(10).normal(size=(1031,)).astype(np.float32))
+    assert torch.equal(ops.cast_bf16(x.cuda()).cpu(), x.bfloat16())

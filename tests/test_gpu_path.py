@@ -1,0 +1,213 @@
+"""End-to-end parity of the CUDA hot path against the oracle and the committed golden vectors
+(outputs of the reference's own classes, tests/golden/, see oracle/make_golden.py).
+
+Tolerances (BASELINE.json north_star): fp32 mode <= 1e-5 (max-abs vertex error in metres, coefficient relative error);
+bf16 mode: max-abs vertex error <= 1e-4 m, coefficient (hidden-state) relative error <= 1e-2."""
+import numpy as np
+import pytest
+import torch
+
+from avi_talking_b200 import synth
+from oracle import faceformer_oracle as ffo
+from oracle import flame_oracle as fo
+from oracle import wav2vec2_oracle as wo
+from oracle.make_golden import COL_STRIDE
+
+from helpers import build_faceformer, build_flame, build_wav2vec
+
+pytestmark = pytest.mark.gpu
+
+
+def relerr(a, b):
+    return ((a - b).norm() / b.norm()).item()
+
+
+# ------------------------------------------------------------------------------------------------ FLAME
+@pytest.mark.parametrize("n_shape,tag", [(100, "a"), (300, "b")])
+def test_flame_matches_reference_golden(golden, n_shape, tag):
+    g = golden("flame")
+    m = build_flame(n_shape, mediapipe=(n_shape == 100))
+    p = {k: v.cuda() for k, v in synth.flame_params(4, n_shape=n_shape, seed=3).items()}
+    res = m(p["shape"], p["exp"], p["pose"], p["eye"])
+    assert np.abs(res[0].cpu().numpy() - g[f"verts_{tag}"]).max() < 1e-6          # metres
+    assert np.abs(res[1].cpu().numpy() - g[f"lmk2d_{tag}"]).max() < 1e-6
+    assert np.abs(res[2].cpu().numpy() - g[f"lmk3d_{tag}"]).max() < 1e-6
+    if n_shape == 100:
+        assert np.abs(res[3].cpu().numpy() - g["lmkmp_a"]).max() < 1e-6
+    pose = p["pose"].clone()
+    pose[:, :3] = 0
+    v = m(p["shape"], p["exp"], pose)[0]
+    assert np.abs(v.cpu().numpy() - g[f"verts_jawonly_{tag}"]).max() < 1e-6
+
+
+def test_flame_lbs_function_and_identities(golden):
+    from avi_talking_b200.flame import lbs
+    g = golden("flame")
+    buf = {k: v.cuda() for k, v in synth.flame_buffers(100, 50).items()}
+    p = synth.flame_params(2, seed=5)
+    betas = torch.cat([p["shape"], p["exp"]], 1).cuda()
+    full_pose = torch.cat([p["pose"][:, :3], torch.zeros(2, 3), p["pose"][:, 3:], p["eye"]], 1).cuda()
+    v, J = lbs(betas, full_pose, buf["v_template"][None].expand(2, -1, -1), buf["shapedirs"], buf["posedirs"],
+               buf["J_regressor"], buf["parents"], buf["lbs_weights"])
+    assert np.abs(v.cpu().numpy() - g["gdl_lbs_verts"]).max() < 1e-6
+    assert np.abs(J.cpu().numpy() - g["gdl_lbs_joints"]).max() < 1e-6
+    # zero betas + zero pose => template ; zero pose => pure blendshape
+    z = torch.zeros(3, 150, device="cuda")
+    v, _ = lbs(z, torch.zeros(3, 15, device="cuda"), buf["v_template"], buf["shapedirs"], buf["posedirs"], buf["J_regressor"],
+               buf["parents"], buf["lbs_weights"])
+    assert (v - buf["v_template"][None]).abs().max().item() < 3e-7
+    v, _ = lbs(betas, torch.zeros(2, 15, device="cuda"), buf["v_template"], buf["shapedirs"], buf["posedirs"],
+               buf["J_regressor"], buf["parents"], buf["lbs_weights"])
+    want = buf["v_template"] + torch.einsum("bl,mkl->bmk", betas, buf["shapedirs"])
+    assert (v - want).abs().max().item() < 1e-6
+
+
+def test_flame_many_frames_and_template_mutation():
+    """Ragged frame/vertex tiles (F=333 is not a multiple of 64) and the in-place v_template mutation callers perform."""
+    m = build_flame(100, mediapipe=False)
+    buf = synth.flame_buffers(100, 50)
+    p = synth.flame_params(333, seed=11)
+    v = m.vertices_only(p["shape"].cuda(), p["exp"].cuda(), p["pose"].cuda(), p["eye"].cuda())
+    ref = fo.flame_forward(buf, p["shape"], p["exp"], p["pose"], p["eye"])[0]
+    assert (v.cpu() - ref).abs().max().item() < 1e-6
+    m.v_template.add_(0.01)    # TalkingHeadWrapper.py:140-158 style mutation must invalidate the packed cache
+    buf["v_template"] = buf["v_template"] + 0.01
+    v = m.vertices_only(p["shape"][:5].cuda(), p["exp"][:5].cuda(), p["pose"][:5].cuda(), p["eye"][:5].cuda())
+    ref = fo.flame_forward(buf, p["shape"][:5], p["exp"][:5], p["pose"][:5], p["eye"][:5])[0]
+    assert (v.cpu() - ref).abs().max().item() < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ wav2vec2
+def test_wav2vec2_fp32_matches_reference_golden(golden):
+    g = golden("w2v")
+    m = build_wav2vec("fp32")
+    a1 = synth.audio(2, 16000, seed=1234).cuda()
+    hs = m(a1, "vocaset").last_hidden_state
+    assert hs.shape == (2, 24, 768)
+    ref = torch.from_numpy(g["hs_1s"])
+    assert relerr(hs.cpu(), ref) < 1e-5 and (hs.cpu() - ref).abs().max().item() < 1e-4
+    hs = m(a1, "vocaset", frame_num=20).last_hidden_state
+    assert relerr(hs.cpu(), torch.from_numpy(g["hs_1s_frame20"])) < 1e-5
+    a4 = synth.audio(1, 64000, seed=1234).cuda()
+    hs = m(a4, "vocaset").last_hidden_state
+    assert hs.shape == (1, 99, 768)
+    assert relerr(hs.cpu(), torch.from_numpy(g["hs_4s"])) < 1e-5
+
+
+def test_wav2vec2_bf16_matches_reference_golden(golden):
+    g = golden("w2v")
+    m = build_wav2vec("bf16")
+    a1 = synth.audio(2, 16000, seed=1234).cuda()
+    hs = m(a1, "vocaset").last_hidden_state
+    e1 = relerr(hs.cpu(), torch.from_numpy(g["hs_1s"]))
+    a4 = synth.audio(1, 64000, seed=1234).cuda()
+    e4 = relerr(m(a4, "vocaset").last_hidden_state.cpu(), torch.from_numpy(g["hs_4s"]))
+    print("bf16 wav2vec2 relative error:", e1, e4)
+    assert e1 < 1e-2 and e4 < 1e-2
+
+
+def test_wav2vec2_feature_extractor_stage(golden):
+    g = golden("w2v")
+    for prec, tol in (("fp32", 1e-5), ("bf16", 1e-2)):
+        m = build_wav2vec(prec)
+        a1 = synth.audio(2, 16000, seed=1234).cuda()
+        feats, T50, La = m._feature_extractor(a1, m._pack())
+        got = feats[:, :T50].float().cpu().transpose(1, 2)
+        assert T50 == 49
+        assert relerr(got, torch.from_numpy(g["feats_1s"])) < tol
+
+
+# ------------------------------------------------------------------------------------------------ decoder
+@pytest.mark.parametrize("fd", [64, 128])
+def test_decoder_ar_matches_oracle(fd):
+    """forward_ff autoregressive branch on given hidden states, batched over 3 clips, against the literal O(T^2) oracle."""
+    m = build_faceformer("fp32", fd=fd, seed=10 + fd)
+    sd = synth.faceformer_state(fd=fd, seed=10 + fd)
+    rng = np.random.default_rng(5)
+    B, T = 3, 40
+    hs = torch.from_numpy(rng.normal(size=(B, T, 36 + fd)).astype(np.float32))
+    obj = torch.from_numpy((0.3 * rng.normal(size=(B, fd))).astype(np.float32))
+    template = synth.flame_buffers()["v_template"].reshape(1, 1, 15069)
+    ref = ffo.forward_ff(sd, template, hs, obj, T, teacher_forcing=False)
+    got = m.forward_ff(None, hs.cuda(), obj.cuda(), T, teacher_forcing=False)
+    assert (got.cpu() - ref).abs().max().item() < 1e-5      # metres
+    disp_ref = ref - template
+    assert relerr(got.cpu() - template, disp_ref) < 1e-4
+
+
+@pytest.mark.parametrize("fd", [64, 128])
+def test_decoder_teacher_forced_matches_oracle(fd):
+    m = build_faceformer("fp32", fd=fd, seed=10 + fd)
+    sd = synth.faceformer_state(fd=fd, seed=10 + fd)
+    rng = np.random.default_rng(6)
+    B, T = 2, 33
+    hs = torch.from_numpy(rng.normal(size=(B, T, 36 + fd)).astype(np.float32))
+    obj = torch.from_numpy((0.3 * rng.normal(size=(B, fd))).astype(np.float32))
+    template = synth.flame_buffers()["v_template"].reshape(1, 1, 15069)
+    gt = template + 1e-3 * torch.from_numpy(rng.normal(size=(B, T, 15069)).astype(np.float32))
+    ref = ffo.forward_ff(sd, template, hs, obj, T, teacher_forcing=True, gt_verts=gt)
+    got = m.forward_ff(gt.cuda(), hs.cuda(), obj.cuda(), T, teacher_forcing=True)
+    assert (got.cpu() - ref).abs().max().item() < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ predict end to end
+@pytest.mark.parametrize("fd", [64, 128])
+def test_predict_fp32_matches_reference_golden(golden, fd):
+    g = golden("faceformer")
+    m = build_faceformer("fp32", fd=fd, seed=10 + fd)
+    a = synth.audio(1, 16000, seed=1234).cuda()
+    emo = synth.fan_embeddings(24, seed=20)["emo"][None].cuda()
+    v = m.predict_from_embeddings(a, emo)
+    assert v.shape == (1, 24, 15069)
+    ref = torch.from_numpy(g[f"predict_fd{fd}_sub"])
+    err = (v[0, :, ::COL_STRIDE].cpu() - ref).abs().max().item()
+    print("fp32 predict max abs vertex error (m):", err)
+    assert err < 1e-5
+
+
+def test_predict_c1_fp32_and_bf16(golden):
+    """BASELINE config 1 (one 4 s clip, T=99) against the reference's own predict()."""
+    g = golden("faceformer")
+    ref = torch.from_numpy(g["predict_c1_sub"])
+    a = synth.audio(1, 64000, seed=1234).cuda()
+    emo = synth.fan_embeddings(99, seed=20)["emo"][None].cuda()
+    template = synth.flame_buffers()["v_template"].reshape(-1)[::COL_STRIDE]
+    for prec, tol_v, tol_rel in (("fp32", 1e-5, 1e-4), ("bf16", 1e-4, 1e-2)):
+        m = build_faceformer(prec, fd=64, seed=74)
+        v = m.predict_from_embeddings(a, emo)
+        got = v[0, :, ::COL_STRIDE].cpu()
+        err = (got - ref).abs().max().item()
+        rel = relerr(got - template, ref - template)
+        print(f"{prec} C1 predict: max abs vertex error {err:.3e} m, displacement relative error {rel:.3e}")
+        assert err < tol_v and rel < tol_rel
+
+
+def test_predict_api_with_fan_stub(golden):
+    """The reference predict(audio, head_img, eye_img, emotion_img) signature, FanEncoder replaced by a stub."""
+    g = golden("faceformer")
+    emb = synth.fan_embeddings(24, seed=20)
+
+    class Fan(torch.nn.Module):
+        def forward(self, img):
+            i = int(round(float(img.reshape(img.shape[0], -1)[0, 0])))
+            return emb["head"][i:i + 1].cuda(), emb["eye"][i:i + 1].cuda(), emb["emo"][i:i + 1].cuda(), None
+
+    m = build_faceformer("fp32", fd=64, seed=74)
+    m.fan_net = Fan()
+    frames = torch.zeros(24, 3, 4, 4, device="cuda")
+    frames[:, 0, 0, 0] = torch.arange(24).float()
+    a = synth.audio(1, 16000, seed=1234).cuda()
+    v = m.predict(a, frames, frames, frames)
+    v2 = m.predict_from_embeddings(a, emb["emo"][None].cuda())
+    assert torch.equal(v, v2)
+
+
+def test_batched_predict_equals_per_clip():
+    """Batching over clips is new behaviour (the reference loops clip by clip): it must not change any clip's result."""
+    m = build_faceformer("bf16", fd=64, seed=74)
+    a = synth.audio(3, 16000, seed=99).cuda()
+    emo = torch.from_numpy(np.random.default_rng(3).normal(size=(3, 24, 30)).astype(np.float32)).cuda()
+    vb = m.predict_from_embeddings(a, emo)
+    for c in range(3):
+        vc = m.predict_from_embeddings(a[c:c + 1], emo[c:c + 1])
+        assert (vb[c] - vc[0]).abs().max().item() < 2e-6
