@@ -343,9 +343,56 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat1
   }
 }
 
+// dst[b, t, :] (bf16, rows_out rows per clip) = t in [front, front+T) ? src[b, t-front, :] : 0
+__global__ void pad_cast_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int T, int C, int front,
+                                int rows_out, int64_t total4) {
+  const int64_t i4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i4 >= total4) return;
+  const int64_t i = i4 * 4;
+  const int c = (int)(i % C);
+  const int64_t r = i / C;
+  const int t = (int)(r % rows_out) - front;
+  const int64_t b = r / rows_out;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (t >= 0 && t < T) v = *reinterpret_cast<const float4*>(src + ((int64_t)b * T + t) * C + c);
+  *reinterpret_cast<__nv_bfloat162*>(dst + i) = __floats2bfloat162_rn(v.x, v.y);
+  *reinterpret_cast<__nv_bfloat162*>(dst + i + 2) = __floats2bfloat162_rn(v.z, v.w);
+}
+
+// split-bf16 operand for near-fp32 GEMMs on the bf16 tensor path: dst[r] = [hi(x) | lo(x) | hi(x)], lo = bf16(x - hi)
+__global__ void split_bf16x3_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t rows, int K) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * K) return;
+  const int64_t r = i / K;
+  const int k = (int)(i % K);
+  const float x = src[i];
+  const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+  __nv_bfloat16* d = dst + r * 3 * K;
+  d[k] = hi;
+  d[K + k] = lo;
+  d[2 * K + k] = hi;
+}
+
 }  // namespace avi
 
 using namespace avi;
+
+extern "C" int avi_pad_cast_bf16(const float* src, void* dst, int32_t B, int32_t T, int32_t C, int32_t front, int32_t rows_out,
+                                 void* stream) {
+  AVI_REQUIRE(B > 0 && T > 0 && C > 0 && C % 4 == 0 && front >= 0 && rows_out >= front + T, "avi_pad_cast_bf16: bad shape");
+  const int64_t total4 = (int64_t)B * rows_out * C / 4;
+  pad_cast_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, T, C, front,
+                                                                                    rows_out, total4);
+  return check_launch("pad_cast");
+}
+
+extern "C" int avi_split_bf16x3(const float* src, void* dst, int64_t rows, int32_t K, void* stream) {
+  AVI_REQUIRE(rows > 0 && K > 0, "avi_split_bf16x3: bad shape");
+  const int64_t n = rows * K;
+  split_bf16x3_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, rows, K);
+  return check_launch("split_bf16x3");
+}
 
 extern "C" int avi_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) {
   if (n <= 0) return 0;
@@ -421,6 +468,14 @@ extern "C" int avi_w2v_posconv_ln(const float* x, const float* w_packed, const f
   const int64_t rows = (int64_t)B * T;
   layernorm_kernel<32, 1><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, out_f32, ln_w, ln_b, out_f32,
                                                                         (__nv_bfloat16*)out_bf16, rows, C, eps);
+  return check_launch("posconv_merge_ln");
+}
+
+extern "C" int avi_w2v_posconv_merge_ln(const float* x, const float* pc, const float* ln_w, const float* ln_b, float* out_f32,
+                                        void* out_bf16, int64_t rows, int32_t C, float eps, void* stream) {
+  AVI_REQUIRE(rows > 0 && C > 0 && C <= 1024, "avi_w2v_posconv_merge_ln: bad shape");
+  layernorm_kernel<32, 1><<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x, pc, ln_w, ln_b, out_f32,
+                                                                                      (__nv_bfloat16*)out_bf16, rows, C, eps);
   return check_launch("posconv_merge_ln");
 }
 

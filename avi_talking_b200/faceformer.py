@@ -174,7 +174,12 @@ class Faceformer(nn.Module):
         P["obj_w"] = f32(self.obj_vector.weight)
         P["vr_w32"], P["vr_b"] = f32(self.vertice_map_r.weight), f32(self.vertice_map_r.bias)
         if self.precision == "bf16":
-            P["vr_w16"] = ops.cast_bf16(self.vertice_map_r.weight)
+            # split-bf16 weights [hi | hi | lo] against activations [hi | lo | hi] (ops.split_bf16x3): the bf16 tensor path then
+            # reproduces the fp32 vertex head to ~2^-16 relative while staying HBM-write-bound (K = 3*fd is tiny)
+            w = self.vertice_map_r.weight.detach().float()
+            hi = w.bfloat16()
+            lo = (w - hi.float()).bfloat16()
+            P["vr_w16x3"] = torch.cat([hi, hi, lo], dim=1).contiguous()
         self._packed, self._packed_key = P, key
         return P
 
@@ -194,8 +199,8 @@ class Faceformer(nn.Module):
         bias = (P["vr_b"] + template.reshape(-1).float()).contiguous()
         out = torch.empty((B, T, self.args.vertice_dim), dtype=torch.float32, device=hidden.device)
         if self.precision == "bf16" and fd % 64 == 0:
-            a = ops.cast_bf16(hidden.reshape(B * T, fd))
-            ops.gemm(a, P["vr_w16"], bias, out, rows=B * T, N=self.args.vertice_dim, K=fd, a_rows_alloc=B * T)
+            a = ops.split_bf16x3(hidden.reshape(B * T, fd))
+            ops.gemm(a, P["vr_w16x3"], bias, out, rows=B * T, N=self.args.vertice_dim, K=3 * fd, a_rows_alloc=B * T)
         else:
             ops.gemm(hidden.reshape(B * T, fd), P["vr_w32"], bias, out, rows=B * T, N=self.args.vertice_dim, K=fd)
         return out

@@ -62,6 +62,25 @@ def cast_bf16(src: torch.Tensor) -> torch.Tensor:
     return dst
 
 
+def pad_cast_bf16(x, B, T, front, rows_out):
+    _need_cuda(x)
+    Cc = x.shape[-1]
+    out = torch.empty((B, rows_out, Cc), dtype=torch.bfloat16, device=x.device)
+    with _timed("pad_cast", 0.0):
+        _lib.check(_lib.load().avi_pad_cast_bf16(_ptr(x), _ptr(out), C.c_int32(B), C.c_int32(T), C.c_int32(Cc), C.c_int32(front),
+                                                 C.c_int32(rows_out), _stream()), "avi_pad_cast_bf16")
+    return out
+
+
+def split_bf16x3(x2d):
+    _need_cuda(x2d)
+    rows, K = x2d.shape
+    out = torch.empty((rows, 3 * K), dtype=torch.bfloat16, device=x2d.device)
+    with _timed("split_bf16x3", 0.0):
+        _lib.check(_lib.load().avi_split_bf16x3(_ptr(x2d), _ptr(out), C.c_int64(rows), C.c_int32(K), _stream()), "avi_split_bf16x3")
+    return out
+
+
 def gemm(A, W, bias, out, *, rows, N, K, batch=1, act=ACT_NONE, residual=None, out2=None, conv_taps=1, conv_stride=1,
          a_ld=None, a_batch_stride=0, a_rows_alloc=None, c_ld=None, c_batch_stride=0, res_ld=None, res_batch_stride=0):
     """C[b,r,n] = act(sum_k A[b,r,k] W[n,k] + bias[n]) (+ residual). fp32 A/W -> CUDA-core kernel, bf16 -> tcgen05 kernel."""
@@ -161,9 +180,27 @@ def posconv_ln(x, w_packed, conv_bias, ln_w, ln_b, B, T, groups, k, want_bf16, e
     return o32, o16
 
 
+def posconv_merge_ln(x, pc, ln_w, ln_b, want_bf16, eps=1e-5):
+    """out = LayerNorm(x + GELU(pc)), written over pc (fp32) plus an optional bf16 copy."""
+    _need_cuda(x, pc)
+    rows, Cc = x.shape
+    o16 = torch.empty((rows, Cc), dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    with _timed("posconv_merge_ln", float(x.numel() * 12)):
+        _lib.check(_lib.load().avi_w2v_posconv_merge_ln(_ptr(x), _ptr(pc), _ptr(ln_w), _ptr(ln_b), _ptr(pc), _ptr(o16),
+                                                        C.c_int64(rows), C.c_int32(Cc), C.c_float(eps), _stream()),
+                   "avi_w2v_posconv_merge_ln")
+    return pc, o16
+
+
 def mha(qkv, B, T, H, D, scale):
     _need_cuda(qkv)
     out = torch.empty((B * T, H * D), dtype=qkv.dtype, device=qkv.device)
+    lib = _lib.load()
+    if lib.avi_mha_fwd_tc_supported(C.c_int32(_dt(qkv)), C.c_int32(T), C.c_int32(D)):
+        with _timed("mha_tc", 4.0 * B * H * T * T * D):
+            _lib.check(lib.avi_mha_fwd_tc(_ptr(qkv), _ptr(out), C.c_int32(B), C.c_int32(T), C.c_int32(H), C.c_int32(D),
+                                          C.c_float(scale), _stream()), "avi_mha_fwd_tc")
+        return out
     with _timed("mha", 4.0 * B * H * T * T * D):
         _lib.check(_lib.load().avi_mha_fwd(_ptr(qkv), _ptr(out), C.c_int32(_dt(qkv)), C.c_int32(B), C.c_int32(T), C.c_int32(H),
                                            C.c_int32(D), C.c_float(scale), _stream()), "avi_mha_fwd")

@@ -90,6 +90,16 @@ class Wav2Vec2Model(_HFWav2Vec2Model):
         w = self._posconv_weight().float()  # [C, cg, k] -> [g][k][ci][co]
         P["pos_w"] = w.reshape(g, cg, cg, k).permute(0, 3, 2, 1).contiguous()
         P["pos_b"] = f32(self.encoder.pos_conv_embed.conv.bias)
+        if bf16 and cg == 48 and g % 4 == 0:
+            # tensor-core route: 4 groups (192 channels = 3 x 64) per GEMM with a block-diagonal weight
+            # Wq[co, j*192 + c] = w[192q + co, c - 48*(co//48), j] if c//48 == co//48 else 0   (K = taps * 192)
+            wg = w.reshape(g, cg, cg, k)                       # [group, co, ci, tap]
+            P["pos_w_bd"] = []
+            for q in range(g // 4):
+                blk = torch.zeros(4, cg, k, 4, cg, dtype=torch.float32, device=w.device)
+                for gl in range(4):
+                    blk[gl, :, :, gl, :] = wg[4 * q + gl].permute(0, 2, 1)   # [co, tap, ci]
+                P["pos_w_bd"].append(ops.cast_bf16(blk.reshape(4 * cg, k * 4 * cg).contiguous()))
         P["enc_ln_w"], P["enc_ln_b"] = f32(self.encoder.layer_norm.weight), f32(self.encoder.layer_norm.bias)
         P["layers"] = []
         for lyr in self.encoder.layers:
@@ -129,6 +139,19 @@ class Wav2Vec2Model(_HFWav2Vec2Model):
             h, L, La, Cc = o, Lo, Loa, Co
         return h, L, La
 
+    def _posconv_tc(self, proj, P, B, T):
+        """Positional grouped conv as 4 block-diagonal conv-mode GEMMs on the tcgen05 path (taps=128, window 192 channels)."""
+        cfg = self.config
+        k, Cc = cfg.num_conv_pos_embeddings, cfg.hidden_size
+        Tp = T + k                                              # rows t-64 .. t+63 around every output row, zero padded
+        xpad = ops.pad_cast_bf16(proj, B, T, k // 2, Tp)
+        pc = torch.empty((B * T, Cc), dtype=torch.float32, device=proj.device)
+        for q, wq in enumerate(P["pos_w_bd"]):
+            c0 = 192 * q
+            ops.gemm(xpad[:, :, c0:], wq, P["pos_b"][c0:c0 + 192], pc[:, c0:], batch=B, rows=T, N=192, K=k * 192, conv_taps=k,
+                     conv_stride=1, a_ld=Cc, a_batch_stride=Tp * Cc, a_rows_alloc=Tp, c_ld=Cc, c_batch_stride=T * Cc)
+        return ops.posconv_merge_ln(proj, pc, P["enc_ln_w"], P["enc_ln_b"], want_bf16=True, eps=cfg.layer_norm_eps)
+
     def _encoder_layer(self, h32, h16, Lw, B, T):
         bf16 = self.precision == "bf16"
         H = self.config.num_attention_heads
@@ -164,9 +187,12 @@ class Wav2Vec2Model(_HFWav2Vec2Model):
         hn32, hn16 = ops.lerp_layernorm(feats, La * Cf, B, T50, T, P["fp_ln_w"], P["fp_ln_b"], want_f32=not bf16,
                                         want_bf16=bf16, eps=cfg.layer_norm_eps)
         proj = ops.linear(hn16 if bf16 else hn32, P["fp_w"], P["fp_b"], out_dtype=torch.float32)   # :120
-        h32, h16 = ops.posconv_ln(proj, P["pos_w"], P["pos_b"], P["enc_ln_w"], P["enc_ln_b"], B, T,
-                                  cfg.num_conv_pos_embedding_groups, cfg.num_conv_pos_embeddings, want_bf16=bf16,
-                                  eps=cfg.layer_norm_eps)
+        if "pos_w_bd" in P:
+            h32, h16 = self._posconv_tc(proj, P, B, T)
+        else:
+            h32, h16 = ops.posconv_ln(proj, P["pos_w"], P["pos_b"], P["enc_ln_w"], P["enc_ln_b"], B, T,
+                                      cfg.num_conv_pos_embedding_groups, cfg.num_conv_pos_embeddings, want_bf16=bf16,
+                                      eps=cfg.layer_norm_eps)
         all_hidden = (h32.view(B, T, -1),) if output_hidden_states else None
         for Lw in P["layers"]:                                                               # :142-148
             h32, h16 = self._encoder_layer(h32, h16, Lw, B, T)

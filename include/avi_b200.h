@@ -78,6 +78,13 @@ int avi_gemm_bf16_tc_supported(const AviGemmArgs* args);
 /* fp32 -> bf16 (weights packing / activation staging), n elements */
 int avi_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
 
+/* zero-padded bf16 copy of a time-major activation: dst[b, t, :] = (front <= t < front+T) ? src[b, t-front, :] : 0, rows_out rows
+ * per clip (stages the input of the positional conv for the tensor-core path). */
+int avi_pad_cast_bf16(const float* src, void* dst, int32_t B, int32_t T, int32_t C, int32_t front, int32_t rows_out, void* stream);
+/* split-bf16 GEMM operand: dst [rows, 3K] = [hi(x) | lo(x) | hi(x)] with lo = bf16(x - hi); against weights packed
+ * [hi(W) | hi(W) | lo(W)] the bf16 tensor path reproduces the fp32 product to ~2^-16 relative (vertex head, bf16 mode). */
+int avi_split_bf16x3(const float* src, void* dst, int64_t rows, int32_t K, void* stream);
+
 /* ------------------------------------------------------------------ wav2vec2 pieces ------------------------------------------------------------------ */
 /* Conv1d(1->512,k=10,s=5,no bias) + GroupNorm(512 groups) + GELU   (HF Wav2Vec2GroupNormConvLayer; models/lib/wav2vec.py:97).
  * audio [B, n_samples] fp32 -> out [B, L0, C] (time-major, dtype out_dtype, batch stride out_batch_stride elements).
@@ -104,9 +111,17 @@ int avi_w2v_posconv_ln(const float* x, const float* w_packed, const float* conv_
                        float* out_f32, void* out_bf16, int32_t B, int32_t T, int32_t C, int32_t groups, int32_t k, float eps,
                        void* stream);
 
+/* second half of the above when the grouped conv itself ran as tensor-core GEMMs: out = LayerNorm(x + GELU(pc)); pc may alias out_f32 */
+int avi_w2v_posconv_merge_ln(const float* x, const float* pc, const float* ln_w, const float* ln_b, float* out_f32, void* out_bf16,
+                             int64_t rows, int32_t C, float eps, void* stream);
+
 /* softmax(q k^T * scale) v per (clip, head); qkv [B, T, 3*H*D] packed (q | k | v), dtype qkv_dtype; out [B, T, H*D] same dtype.
  * (HF Wav2Vec2Attention / eager_attention_forward, no mask) */
 int avi_mha_fwd(const void* qkv, void* out, int32_t dtype, int32_t B, int32_t T, int32_t H, int32_t D, float scale, void* stream);
+
+/* same contract on the tcgen05 path (bf16, D == 64, T <= 256): QK^T and PV on tensor cores with S/O in TMEM, softmax from TMEM */
+int avi_mha_fwd_tc(const void* qkv, void* out, int32_t B, int32_t T, int32_t H, int32_t D, float scale, void* stream);
+int avi_mha_fwd_tc_supported(int32_t dtype, int32_t T, int32_t D);
 
 /* ------------------------------------------------------------------ FaceFormer decoder (Path A) ------------------------------------------------------------------ */
 typedef struct AviDecoderWeights { /* all fp32 device pointers; fd = feature_dim, 4 heads, dff = 2*fd */

@@ -183,7 +183,8 @@ def test_posconv_ln(ops, T):
     assert (o16.float().cpu().double() - ref).abs().max().item() < 3e-2
 
 
-@pytest.mark.parametrize("T,dtype", [(24, torch.float32), (249, torch.float32), (300, torch.bfloat16), (129, torch.bfloat16)])
+@pytest.mark.parametrize("T,dtype", [(24, torch.float32), (249, torch.float32), (300, torch.bfloat16), (129, torch.bfloat16),
+                                     (24, torch.bfloat16), (128, torch.bfloat16), (249, torch.bfloat16), (256, torch.bfloat16)])
 def test_mha(ops, T, dtype):
     r = _rng(9)
     B, H, D = 2, 12, 64
