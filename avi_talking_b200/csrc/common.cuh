@@ -38,6 +38,19 @@ inline int check_launch(const char* what) {
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
+// Branch-free GELU for epilogues whose result is rounded to bf16 anyway: erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7),
+// arranged so the negative tail has no cancellation (1 + erf(z) = poly*exp(-z^2) for z < 0).
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float pe = poly * t * __expf(-z * z);
+  return 0.5f * x * (x < 0.f ? pe : 2.0f - pe);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

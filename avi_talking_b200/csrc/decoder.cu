@@ -191,6 +191,194 @@ ff_decoder_ar_kernel(const AviDecoderWeights w, const float* __restrict__ cross,
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// feature_dim == 64 fast path: 512 threads, ALL decoder weights (36.9k floats) live in registers (80 per thread), so a
+// step is a handful of register-resident mat-vecs with shuffle reductions instead of L2-latency-bound weight streaming.
+// K/V cache, probabilities and the activation vectors live in shared memory.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int A64_THREADS = 512, A64_FD = 64, A64_DFF = 128, A64_HD = 16, A64_KVS = 65;
+
+__device__ __forceinline__ float dot_seg(const float* w, const float* x, int n) {  // n multiple of 4, x 16-byte aligned smem
+  float acc = 0.f;
+  for (int q = 0; q < n; q += 4) {
+    const float4 xv = *reinterpret_cast<const float4*>(x + q);
+    acc = fmaf(w[q], xv.x, acc);
+    acc = fmaf(w[q + 1], xv.y, acc);
+    acc = fmaf(w[q + 2], xv.z, acc);
+    acc = fmaf(w[q + 3], xv.w, acc);
+  }
+  return acc;
+}
+
+__device__ __forceinline__ void ln64(const float* a, const float* r, const float* __restrict__ w, const float* __restrict__ b, float* y) {
+  if (threadIdx.x < 32) {
+    const int l = threadIdx.x;
+    const float v0 = a[l] + r[l], v1 = a[l + 32] + r[l + 32];
+    const float mean = warp_sum(v0 + v1) * (1.f / 64.f);
+    const float d0 = v0 - mean, d1 = v1 - mean;
+    const float rstd = rsqrtf(warp_sum(d0 * d0 + d1 * d1) * (1.f / 64.f) + 1e-5f);
+    y[l] = d0 * rstd * w[l] + b[l];
+    y[l + 32] = d1 * rstd * w[l + 32] + b[l + 32];
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(A64_THREADS, 1)
+ff_decoder_ar64_kernel(const AviDecoderWeights w, const float* __restrict__ cross, const float* __restrict__ style,
+                       float* __restrict__ hidden_out, int T, int period) {
+  extern __shared__ __align__(16) float sm[];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float* xs = sm;                 // [64]
+  float* qkv = xs + 64;           // [192]
+  float* att = qkv + 192;         // [64]
+  float* t0 = att + 64;           // [64]
+  float* x1 = t0 + 64;            // [64]
+  float* hb = x1 + 64;            // [128]
+  float* emb = hb + 128;          // [64]
+  float* sty = emb + 64;          // [64]
+  float* red = sty + 64;          // [32 + 512] warp partials + PV partials
+  float* prob = red + 576;        // [4][T]
+  float* Kc = prob + 4 * T + ((4 - (4 * T) % 4) % 4);  // [T][65]
+  float* Vc = Kc + (size_t)T * A64_KVS;
+
+  // ---- weights -> registers (transposed global layout Wt[k*OUT + o])
+  float w_in[32], w_o[8], w_1[16], w_2[16], w_f[8];
+  const int in_o = tid >> 1, in_s = tid & 1;
+#pragma unroll
+  for (int kk = 0; kk < 32; ++kk) w_in[kk] = (in_o < 192) ? w.sa_in_w[(in_s * 32 + kk) * 192 + in_o] : 0.f;
+  const int o8 = tid >> 3, s8 = tid & 7;
+#pragma unroll
+  for (int kk = 0; kk < 8; ++kk) {
+    w_o[kk] = w.sa_out_w[(s8 * 8 + kk) * 64 + o8];
+    w_f[kk] = w.fb_w[(s8 * 8 + kk) * 64 + o8];
+  }
+  const int o4 = tid >> 2, s4 = tid & 3;
+#pragma unroll
+  for (int kk = 0; kk < 16; ++kk) {
+    w_1[kk] = w.ff1_w[(s4 * 16 + kk) * 128 + o4];
+    w_2[kk] = w.ff2_w[(s8 * 16 + kk) * 64 + o8];
+  }
+  const float b_in = (in_o < 192) ? w.sa_in_b[in_o] : 0.f;
+  const float b_o = w.sa_out_b[o8], b_f = w.fb_b[o8], b_1 = w.ff1_b[o4], b_2 = w.ff2_b[o8];
+
+  if (tid < 64) {
+    sty[tid] = style[(int64_t)b * 64 + tid];
+    emb[tid] = sty[tid];
+  }
+  __syncthreads();
+  const int h = tid >> 7, jl = tid & 127;         // scores: 4 heads x 128 key lanes
+  const float slope = head_slope(h);
+  const int pg = tid >> 6, pc = tid & 63;         // PV: 8 key groups x 64 channels
+
+  for (int i = 0; i < T; ++i) {
+    if (tid < 64) xs[tid] = emb[tid] + w.pe[(i % period) * 64 + tid];
+    __syncthreads();
+    {  // in_proj
+      float acc = dot_seg(w_in, xs + in_s * 32, 32);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      if (in_s == 0 && in_o < 192) {
+        acc += b_in;
+        qkv[in_o] = acc;
+        if (in_o >= 128) Vc[(size_t)i * A64_KVS + in_o - 128] = acc;
+        else if (in_o >= 64) Kc[(size_t)i * A64_KVS + in_o - 64] = acc;
+      }
+    }
+    __syncthreads();
+    // scores + softmax statistics
+    float q[A64_HD];
+#pragma unroll
+    for (int d = 0; d < A64_HD; d += 4) {
+      const float4 qv = *reinterpret_cast<const float4*>(qkv + h * A64_HD + d);
+      q[d] = qv.x; q[d + 1] = qv.y; q[d + 2] = qv.z; q[d + 3] = qv.w;
+    }
+    float sc[2];  // T <= 256 -> at most two keys per thread (guarded on the host)
+    float mx = -INFINITY;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int j = jl + 128 * u;
+      sc[u] = -INFINITY;
+      if (j <= i) {
+        const float* kr = Kc + (size_t)j * A64_KVS + h * A64_HD;
+        float s = 0.f;
+#pragma unroll
+        for (int d = 0; d < A64_HD; ++d) s = fmaf(q[d], kr[d], s);
+        sc[u] = s * 0.25f - slope * (float)((i - j) / period);
+        mx = fmaxf(mx, sc[u]);
+      }
+    }
+    mx = warp_max(mx);
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    mx = fmaxf(fmaxf(red[h * 4], red[h * 4 + 1]), fmaxf(red[h * 4 + 2], red[h * 4 + 3]));
+    float sum = 0.f;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int j = jl + 128 * u;
+      if (j <= i) {
+        const float e = expf(sc[u] - mx);
+        prob[h * T + j] = e;
+        sum += e;
+      }
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) red[16 + warp] = sum;
+    __syncthreads();
+    {  // PV (unnormalised), 8 key groups
+      const float* pr = prob + (pc >> 4) * T;
+      float acc = 0.f;
+      for (int j = pg; j <= i; j += 8) acc = fmaf(pr[j], Vc[(size_t)j * A64_KVS + pc], acc);
+      red[32 + tid] = acc;
+    }
+    __syncthreads();
+    if (tid < 64) {
+      const int hh = tid >> 4;
+      const float inv = 1.f / (red[16 + hh * 4] + red[16 + hh * 4 + 1] + red[16 + hh * 4 + 2] + red[16 + hh * 4 + 3]);
+      float s = 0.f;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) s += red[32 + g * 64 + tid];
+      att[tid] = s * inv;
+    }
+    __syncthreads();
+    {  // out_proj
+      float acc = dot_seg(w_o, att + s8 * 8, 8);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      if (s8 == 0) t0[o8] = acc + b_o;
+    }
+    __syncthreads();
+    ln64(xs, t0, w.ln1_w, w.ln1_b, x1);
+    if (tid < 64) t0[tid] = cross[((int64_t)b * T + i) * 64 + tid];
+    __syncthreads();
+    ln64(x1, t0, w.ln2_w, w.ln2_b, xs);
+    {  // ff1 + ReLU
+      float acc = dot_seg(w_1, xs + s4 * 16, 16);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      if (s4 == 0) hb[o4] = fmaxf(acc + b_1, 0.f);
+    }
+    __syncthreads();
+    {  // ff2
+      float acc = dot_seg(w_2, hb + s8 * 16, 16);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      if (s8 == 0) t0[o8] = acc + b_2;
+    }
+    __syncthreads();
+    ln64(xs, t0, w.ln3_w, w.ln3_b, x1);
+    if (tid < 64) hidden_out[((int64_t)b * T + i) * 64 + tid] = x1[tid];
+    {  // feedback map: emb_{i+1} = fb(y_i) + style
+      float acc = dot_seg(w_f, x1 + s8 * 8, 8);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      if (s8 == 0) emb[o8] = acc + b_f + sty[o8];
+    }
+    __syncthreads();
+  }
+}
+
 // Biased causal self-attention for a whole sequence (teacher forcing): one warp per (clip, head, query row).
 // qkv [B,T,3fd] fp32 -> out [B,T,fd].
 __global__ void __launch_bounds__(128) ff_biased_attn_kernel(const float* __restrict__ qkv, float* __restrict__ out, int B, int T,
@@ -242,6 +430,15 @@ extern "C" int avi_ff_decoder_ar(const AviDecoderWeights* w, const float* cross,
                                  float* kv_scratch, int32_t B, int32_t T, int32_t fd, int32_t period, void* stream) {
   AVI_REQUIRE(w != nullptr && B > 0 && T > 0 && period > 0, "avi_ff_decoder_ar: bad arguments");
   AVI_REQUIRE(fd % 32 == 0 && fd >= 32 && fd <= 256 && DEC_THREADS % fd == 0, "avi_ff_decoder_ar: feature_dim %d unsupported (32/64/128/256)", fd);
+  if (fd == A64_FD && T <= 256) {
+    const size_t sm64 = sizeof(float) * (64 + 192 + 64 * 3 + 128 + 64 * 2 + 576 + 4 * (size_t)T + 4 + 2 * (size_t)T * A64_KVS);
+    if (sm64 <= 227 * 1024) {
+      cudaError_t e64 = cudaFuncSetAttribute(ff_decoder_ar64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      AVI_REQUIRE(e64 == cudaSuccess, "avi_ff_decoder_ar: cudaFuncSetAttribute: %s", cudaGetErrorString(e64));
+      ff_decoder_ar64_kernel<<<B, A64_THREADS, sm64, (cudaStream_t)stream>>>(*w, cross, style, hidden_out, T, period);
+      return check_launch("ff_decoder_ar64");
+    }
+  }
   const size_t fixed = sizeof(float) * ((size_t)fd * 9 + 2 * fd + DEC_THREADS + (size_t)DEC_NH * T);
   const size_t kv = sizeof(float) * 2 * (size_t)T * (fd + 1);
   int kv_in_smem = (fixed + kv <= 200 * 1024) ? 1 : 0;

@@ -276,6 +276,13 @@ extern "C" int avi_flame_pack(const float* shapedirs, const float* posedirs, con
   return check_launch("flame_pack_jreg");
 }
 
+extern "C" int avi_flame_prologue(const float* betas, const float* full_pose, const float* jreg, float* coef, float* A, float* joints,
+                                  int32_t* dyn_rows, int32_t F, int32_t NB, int32_t K_pad, void* stream) {
+  AVI_REQUIRE(F > 0 && NB > 0 && K_pad >= NB + 37, "avi_flame_prologue: bad shape F=%d NB=%d K_pad=%d", F, NB, K_pad);
+  flame_prologue_kernel<<<(F + 3) / 4, 128, 0, (cudaStream_t)stream>>>(betas, full_pose, jreg, coef, A, joints, dyn_rows, F, NB, K_pad);
+  return check_launch("flame_prologue");
+}
+
 extern "C" int avi_flame_lbs_fwd(const float* betas, const float* full_pose, const float* dirs, const float* jreg,
                                  const float* lbs_weights, float* coef, float* A, float* verts, float* joints,
                                  int32_t* dyn_rows, int32_t F, int32_t V, int32_t NB, int32_t K_pad, void* stream) {

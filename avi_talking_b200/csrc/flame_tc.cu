@@ -1,0 +1,323 @@
+// FLAME blendshapes + pose correctives on tcgen05 with linear blend skinning fused as the epilogue (sm_100a).
+//
+//   v_posed[f, v, c] = v_template[v, c] + sum_l coef[f, l] * dirs[l, v, c]          (l = shape | expression | pose feature)
+//   verts[f, v, :]   = sum_j W[v, j] * A[f, j] * [v_posed[f, v, :]; 1]              (lbs.py:188-232)
+//
+// Mapping: vertices are the MMA M dimension (TMEM lane = vertex), frames the N dimension, one accumulator per coordinate
+// (x, y, z), so that after tcgen05.ld a thread holds x/y/z of ITS vertex for 32 frames and applies the per-frame skinning
+// transform with its own 5 skinning weights in registers; consecutive lanes are consecutive vertices, so each frame's
+// 32 x 3 floats leave through a tiny smem transpose as three fully coalesced 128-byte stores.
+// Operands are fp16 (11-bit significand: ~1e-5 m worst case on ~1e-2 m displacements, vs ~1.7e-4 m for bf16); the
+// template is added in fp32 in the epilogue so its 8 cm magnitude never passes through 16-bit rounding.
+// A CTA keeps the direction slab of its 128-vertex tile (3 x [128 x 192] fp16 = 144 KB) resident in shared memory and
+// streams 64-frame tiles of coefficients (24 KB) + joint transforms (15 KB) through a 2-stage ring; two TMEM accumulator
+// stages overlap the MMAs of tile i+1 with the skinning/stores of tile i.  The kernel is HBM-write-bound by design
+// (60 276 B written per frame vs 6.7 MFLOP per frame of 16-bit tensor work).
+#include <cuda_fp16.h>
+
+#include "tc_common.cuh"
+
+namespace avi {
+
+constexpr int FT_BM = 128, FT_NF = 64, FT_K = 192, FT_KC = 64, FT_NCH = FT_K / FT_KC, FT_CHUNK_TILES = 16, FT_NJ = 5;
+constexpr uint32_t FT_DIR_TILE = FT_BM * FT_KC * 2;              // 16 KB per (coord, k-chunk)
+constexpr uint32_t FT_DIRS_BYTES = 3 * FT_NCH * FT_DIR_TILE;     // 144 KB
+constexpr uint32_t FT_COEF_TILE = FT_NF * FT_KC * 2;             // 8 KB per k-chunk
+constexpr uint32_t FT_COEF_BYTES = FT_NCH * FT_COEF_TILE;        // 24 KB per stage
+constexpr uint32_t FT_AS_BYTES = FT_NF * FT_NJ * 12 * 4;         // 15 KB per stage
+constexpr uint32_t FT_TR_BYTES = 8 * 96 * 4;
+constexpr uint32_t FT_OFF_COEF = FT_DIRS_BYTES;
+constexpr uint32_t FT_OFF_AS = FT_OFF_COEF + 2 * FT_COEF_BYTES;
+constexpr uint32_t FT_OFF_TR = FT_OFF_AS + 2 * FT_AS_BYTES;
+constexpr uint32_t FT_OFF_BAR = FT_OFF_TR + FT_TR_BYTES;
+constexpr uint32_t FT_SMEM = FT_OFF_BAR + 128 + 1024;
+static_assert(FT_SMEM <= 232448, "shared memory budget");
+
+struct FlameTcParams {
+  const float* A;          // [F][5][12] relative joint transforms (3x4 each)
+  const float* lbs_w;      // [V][5]
+  const float* v_template; // [V][3]
+  float* verts;            // [F][V][3]
+  int F, V, V_pad;
+  int n_vt, n_ftiles, n_items;
+};
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  umma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);  // same instruction (kind::f16); idesc selects fp16 operands
+}
+
+__global__ void __launch_bounds__(320, 1)
+flame_tc_kernel(const __grid_constant__ CUtensorMap map_dirs, const __grid_constant__ CUtensorMap map_coef, const FlameTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FT_OFF_BAR);
+  uint64_t* dirs_full = bars;          // [1]
+  uint64_t* dirs_empty = bars + 1;     // [1]
+  uint64_t* cf_full = bars + 2;        // [2] coefficients + joint transforms landed
+  uint64_t* coef_empty = bars + 4;     // [2] MMAs done reading the coefficient tiles
+  uint64_t* as_empty = bars + 6;       // [2] epilogue done reading the joint transforms
+  uint64_t* tmem_full = bars + 8;      // [2]
+  uint64_t* tmem_empty = bars + 10;    // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_dirs) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_coef) : "memory");
+    mbar_init(smem_u32(dirs_full), 1);
+    mbar_init(smem_u32(dirs_empty), 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&cf_full[s]), 1);
+      mbar_init(smem_u32(&coef_empty[s]), 1);
+      mbar_init(smem_u32(&as_empty[s]), 8);
+      mbar_init(smem_u32(&tmem_full[s]), 1);
+      mbar_init(smem_u32(&tmem_empty[s]), 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ============ TMA producer ============
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int item_it = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++item_it) {
+        const int vt = item % p.n_vt, chunk = item / p.n_vt;
+        mbar_wait(smem_u32(dirs_empty), (item_it & 1) ^ 1);
+        const uint32_t db = smem_u32(dirs_full);
+        mbar_expect_tx(db, FT_DIRS_BYTES);
+        for (int k = 0; k < 3; ++k)
+          for (int c = 0; c < FT_NCH; ++c)
+            tma_load_2d(smem_u32(smem + (k * FT_NCH + c) * FT_DIR_TILE), &map_dirs, db, c * FT_KC, k * p.V_pad + vt * FT_BM);
+        const int ft0 = chunk * FT_CHUNK_TILES;
+        const int ft1 = min(ft0 + FT_CHUNK_TILES, p.n_ftiles);
+        for (int ft = ft0; ft < ft1; ++ft) {
+          mbar_wait(smem_u32(&coef_empty[stage]), phase ^ 1);
+          mbar_wait(smem_u32(&as_empty[stage]), phase ^ 1);
+          const int f0 = ft * FT_NF;
+          const int nfr = min(FT_NF, p.F - f0);
+          const uint32_t fb = smem_u32(&cf_full[stage]);
+          mbar_expect_tx(fb, FT_COEF_BYTES + (uint32_t)nfr * FT_NJ * 12 * 4);
+          for (int c = 0; c < FT_NCH; ++c)
+            tma_load_2d(smem_u32(smem + FT_OFF_COEF + stage * FT_COEF_BYTES + c * FT_COEF_TILE), &map_coef, fb, c * FT_KC, f0);
+          bulk_load_1d(smem_u32(smem + FT_OFF_AS + stage * FT_AS_BYTES), p.A + (int64_t)f0 * FT_NJ * 12,
+                       (uint32_t)nfr * FT_NJ * 12 * 4, fb);
+          stage ^= 1;
+          if (stage == 0) phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============ MMA issuer ============
+    if (lane == 0) {
+      // D = f32, A = B = fp16 (format 0), both K-major, N = 64, M = 128
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(FT_NF >> 3) << 17) | ((uint32_t)(FT_BM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int item_it = 0, acc_it = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++item_it) {
+        const int chunk = item / p.n_vt;
+        mbar_wait(smem_u32(dirs_full), item_it & 1);
+        tc_fence_after();
+        const int ft0 = chunk * FT_CHUNK_TILES;
+        const int ft1 = min(ft0 + FT_CHUNK_TILES, p.n_ftiles);
+        for (int ft = ft0; ft < ft1; ++ft, ++acc_it) {
+          const int as = acc_it & 1;
+          const uint32_t aph = (acc_it >> 1) & 1;
+          mbar_wait(smem_u32(&tmem_empty[as]), aph ^ 1);
+          mbar_wait(smem_u32(&cf_full[stage]), phase);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+#pragma unroll
+            for (int c = 0; c < FT_NCH; ++c) {
+              const uint64_t ad = umma_desc_sw128(smem_u32(smem + (k * FT_NCH + c) * FT_DIR_TILE));
+              const uint64_t bd = umma_desc_sw128(smem_u32(smem + FT_OFF_COEF + stage * FT_COEF_BYTES + c * FT_COEF_TILE));
+#pragma unroll
+              for (int kk = 0; kk < FT_KC / 16; ++kk)
+                umma_f16(tmem_base + as * (3 * FT_NF) + k * FT_NF, ad + 2 * kk, bd + 2 * kk, idesc, (c | kk) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(smem_u32(&coef_empty[stage]));
+          umma_commit(smem_u32(&tmem_full[as]));
+          stage ^= 1;
+          if (stage == 0) phase ^= 1;
+        }
+        umma_commit(smem_u32(dirs_empty));  // the direction slab may be replaced once every MMA of this item has retired
+      }
+    }
+  } else {
+    // ============ epilogue: template add + skinning + coalesced stores ============
+    const int ew = warp - 2;
+    const int quarter = warp & 3, half = ew >> 2;
+    float* tr = reinterpret_cast<float*>(smem + FT_OFF_TR) + ew * 96;
+    const int V3 = p.V * 3;
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc_it = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      const int vt = item % p.n_vt, chunk = item / p.n_vt;
+      const int vw0 = vt * FT_BM + quarter * 32;  // first vertex of this warp
+      const int v = vw0 + lane;
+      float w[FT_NJ], vtp[3];
+#pragma unroll
+      for (int j = 0; j < FT_NJ; ++j) w[j] = (v < p.V) ? p.lbs_w[(int64_t)v * FT_NJ + j] : 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) vtp[c] = (v < p.V) ? p.v_template[(int64_t)v * 3 + c] : 0.f;
+      const int ft0 = chunk * FT_CHUNK_TILES;
+      const int ft1 = min(ft0 + FT_CHUNK_TILES, p.n_ftiles);
+      for (int ft = ft0; ft < ft1; ++ft, ++acc_it) {
+        const int as = acc_it & 1;
+        const uint32_t aph = (acc_it >> 1) & 1;
+        mbar_wait(smem_u32(&cf_full[stage]), phase);   // joint transforms of this tile are in smem
+        mbar_wait(smem_u32(&tmem_full[as]), aph);
+        tc_fence_after();
+        uint32_t vx[32], vy[32], vz[32];
+        const uint32_t ta = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * (3 * FT_NF) + half * 32);
+        tmem_ld32(ta, vx);
+        tmem_ld32(ta + FT_NF, vy);
+        tmem_ld32(ta + 2 * FT_NF, vz);
+        const float* As = reinterpret_cast<const float*>(smem + FT_OFF_AS + stage * FT_AS_BYTES) + (half * 32) * (FT_NJ * 12);
+        const int fbase = ft * FT_NF + half * 32;
+#pragma unroll
+        for (int n = 0; n < 32; ++n) {
+          const int f = fbase + n;
+          if (f < p.F) {  // warp-uniform
+            float T[12];
+#pragma unroll
+            for (int e = 0; e < 12; ++e) T[e] = 0.f;
+#pragma unroll
+            for (int j = 0; j < FT_NJ; ++j) {
+              const float4* ap = reinterpret_cast<const float4*>(As + n * (FT_NJ * 12) + j * 12);
+#pragma unroll
+              for (int q = 0; q < 3; ++q) {
+                const float4 a = ap[q];
+                T[q * 4 + 0] = fmaf(w[j], a.x, T[q * 4 + 0]);
+                T[q * 4 + 1] = fmaf(w[j], a.y, T[q * 4 + 1]);
+                T[q * 4 + 2] = fmaf(w[j], a.z, T[q * 4 + 2]);
+                T[q * 4 + 3] = fmaf(w[j], a.w, T[q * 4 + 3]);
+              }
+            }
+            const float px = __uint_as_float(vx[n]) + vtp[0], py = __uint_as_float(vy[n]) + vtp[1], pz = __uint_as_float(vz[n]) + vtp[2];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+              tr[lane * 3 + i] = fmaf(T[i * 4 + 0], px, fmaf(T[i * 4 + 1], py, fmaf(T[i * 4 + 2], pz, T[i * 4 + 3])));
+            __syncwarp();
+            float* o = p.verts + (int64_t)f * V3 + (int64_t)vw0 * 3;
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+              const int idx = lane + 32 * u;
+              if (vw0 * 3 + idx < V3) o[idx] = tr[idx];
+            }
+            __syncwarp();
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(smem_u32(&tmem_empty[as]));
+          mbar_arrive(smem_u32(&as_empty[stage]));
+        }
+        stage ^= 1;
+        if (stage == 0) phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// dirs16[c][v][l] = dirs32[l][v*3 + c] for l < n_dirs (shape | expression | pose rows; the template row is excluded), zero padded
+__global__ void flame_pack_tc_kernel(const float* __restrict__ dirs32, __half* __restrict__ dirs16, int V, int V_pad, int n_dirs) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)3 * V_pad * FT_K;
+  if (i >= total) return;
+  const int l = (int)(i % FT_K);
+  const int v = (int)((i / FT_K) % V_pad);
+  const int c = (int)(i / ((int64_t)FT_K * V_pad));
+  float x = 0.f;
+  if (v < V && l < n_dirs) x = dirs32[(int64_t)l * V * 3 + v * 3 + c];
+  dirs16[i] = __float2half_rn(x);
+}
+
+// coef16[f][l] = fp16(coef32[f][l]) for l < n_dirs, zero padded to FT_K
+__global__ void flame_coef16_kernel(const float* __restrict__ coef32, __half* __restrict__ coef16, int F, int K_pad32, int n_dirs) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)F * FT_K) return;
+  const int l = (int)(i % FT_K);
+  const int64_t f = i / FT_K;
+  coef16[i] = __float2half_rn(l < n_dirs ? coef32[f * K_pad32 + l] : 0.f);
+}
+
+}  // namespace avi
+
+using namespace avi;
+
+extern "C" int avi_flame_tc_supported(int32_t NB) { return (NB + 36 <= FT_K) ? 1 : 0; }
+
+extern "C" int avi_flame_pack_tc(const float* dirs32, void* dirs16, int32_t V, int32_t NB, int32_t V_pad, void* stream) {
+  AVI_REQUIRE(V > 0 && NB + 36 <= FT_K && V_pad % FT_BM == 0 && V_pad >= V, "avi_flame_pack_tc: unsupported shape (NB=%d V_pad=%d)", NB, V_pad);
+  const int64_t total = (int64_t)3 * V_pad * FT_K;
+  flame_pack_tc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dirs32, (__half*)dirs16, V, V_pad, NB + 36);
+  return check_launch("flame_pack_tc");
+}
+
+// The prologue (coefficient rows, joints, kinematic chain, optional landmark rows) is avi_flame_lbs_fwd's; this entry replaces
+// only its blend+skin kernel. coef32 [F, K_pad32] and A [F,5,12] must already have been produced by the prologue on `stream`.
+extern "C" int avi_flame_blend_skin_tc(const float* coef32, const float* A, const void* dirs16, const float* lbs_weights,
+                                       const float* v_template, void* coef16, float* verts, int32_t F, int32_t V, int32_t NB,
+                                       int32_t K_pad32, int32_t V_pad, void* stream) {
+  AVI_REQUIRE(F > 0 && V > 0 && NB + 36 <= FT_K && V_pad % FT_BM == 0 && V_pad >= V, "avi_flame_blend_skin_tc: unsupported shape");
+  AVI_REQUIRE(((uintptr_t)A % 16 == 0) && ((uintptr_t)dirs16 % 16 == 0) && ((uintptr_t)coef16 % 16 == 0),
+              "avi_flame_blend_skin_tc: unaligned pointers");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n16 = (int64_t)F * FT_K;
+  flame_coef16_kernel<<<(unsigned)((n16 + 255) / 256), 256, 0, st>>>(coef32, (__half*)coef16, F, K_pad32, NB + 36);
+  if (check_launch("flame_coef16")) return 1;
+  CUtensorMap map_dirs, map_coef;
+  {
+    uint64_t dims[2] = {(uint64_t)FT_K, (uint64_t)3 * V_pad};
+    uint64_t strides[1] = {(uint64_t)FT_K * 2};
+    uint32_t box[2] = {FT_KC, FT_BM};
+    if (encode_map(&map_dirs, dirs16, 2, dims, strides, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT16)) return 1;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)FT_K, (uint64_t)F};
+    uint64_t strides[1] = {(uint64_t)FT_K * 2};
+    uint32_t box[2] = {FT_KC, FT_NF};
+    if (encode_map(&map_coef, coef16, 2, dims, strides, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT16)) return 1;
+  }
+  FlameTcParams p;
+  p.A = A;
+  p.lbs_w = lbs_weights;
+  p.v_template = v_template;
+  p.verts = verts;
+  p.F = F;
+  p.V = V;
+  p.V_pad = V_pad;
+  p.n_vt = V_pad / FT_BM;
+  p.n_ftiles = (F + FT_NF - 1) / FT_NF;
+  const int n_chunks = (p.n_ftiles + FT_CHUNK_TILES - 1) / FT_CHUNK_TILES;
+  p.n_items = p.n_vt * n_chunks;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(flame_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM); });
+  AVI_REQUIRE(attr_err == cudaSuccess, "avi_flame_blend_skin_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
+  const int grid = p.n_items < kNumSMs ? p.n_items : kNumSMs;
+  flame_tc_kernel<<<grid, 320, FT_SMEM, st>>>(map_dirs, map_coef, p);
+  return check_launch("flame_tc");
+}

@@ -19,8 +19,8 @@ constexpr int TC_THREADS = 320, TC_EPI_WARPS = 8;
 constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 2;   // 16 KB
 constexpr uint32_t TC_B_BYTES = TC_BN * TC_BK * 2;   // 32 KB
 constexpr uint32_t TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
-constexpr uint32_t TC_TRANS_BYTES = TC_EPI_WARPS * 32 * 17 * 4;  // per-warp 32x17 fp32 transpose tiles (unaligned outputs)
-constexpr uint32_t TC_BIAS_BYTES = 2 * TC_BN * 4;
+constexpr uint32_t TC_TRANS_BYTES = TC_EPI_WARPS * 32 * 32 * 4;  // per-warp 32x32 fp32 transpose tiles (XOR-swizzled, no padding)
+constexpr uint32_t TC_BIAS_BYTES = TC_BN * 4;
 constexpr uint32_t TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + TC_TRANS_BYTES + TC_BIAS_BYTES + 256 /*barriers*/ + 1024 /*align*/;
 static_assert(TC_SMEM_BYTES <= 232448, "shared memory budget");
 
@@ -54,7 +54,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + TC_STAGES * TC_A_BYTES;
   float* trans = reinterpret_cast<float*>(smem + TC_STAGES * TC_STAGE_BYTES);
-  float* sbias = reinterpret_cast<float*>(smem + TC_STAGES * TC_STAGE_BYTES + TC_TRANS_BYTES);
+  float* sbias = reinterpret_cast<float*>(smem + TC_STAGES * TC_STAGE_BYTES + TC_TRANS_BYTES);  // [BN], single-buffered
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES + TC_TRANS_BYTES + TC_BIAS_BYTES);
   uint64_t* full_bar = bars;                        // [STAGES]
   uint64_t* empty_bar = bars + TC_STAGES;           // [STAGES]
@@ -144,12 +144,15 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       }
     }
   } else {
-    // ===================== epilogue: TMEM -> registers -> global =====================
+    // ===================== epilogue: TMEM -> registers -> smem transpose -> coalesced global =====================
+    // Phase A (thread = accumulator row): tcgen05.ld 32 columns, + bias, activation, into a per-warp 32x32 XOR-swizzled tile.
+    // Phase B (lane = output column): every instruction reads/writes 32 consecutive elements of ONE output row, so the
+    // residual loads and the stores are fully coalesced whatever the row pitch (15069-wide vertex rows included).
     const int ew = warp - 2;              // 0..7
     const int quarter = warp & 3;         // TMEM lanes [32*quarter, +32) are the only ones this warp may touch
     const int half = ew >> 2;             // columns [128*half, +128)
     const int etid = threadIdx.x - 64;    // 0..255
-    float* my_trans = trans + ew * (32 * 17);
+    float* tile = trans + ew * (32 * 32);
     int it = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
       const int as = it & 1;
@@ -158,108 +161,88 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       const int mt = t / p.n_tiles;
       const int b = mt / p.m_tiles, m_blk = mt % p.m_tiles;
       const int n0 = n_blk * TC_BN;
-      // stage the bias slice for this tile (double-buffered with the accumulator stage)
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // previous tile's bias reads are done
       {
         const int n = n0 + etid;
-        sbias[as * TC_BN + etid] = (p.bias != nullptr && n < p.N) ? p.bias[n] : 0.f;
+        sbias[etid] = (p.bias != nullptr && n < p.N) ? p.bias[n] : 0.f;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(smem_u32(&tmem_full[as]), aphase);
       tc_fence_after();
-      const int row = m_blk * TC_BM + quarter * 32 + lane;
-      const bool row_ok = row < p.rows;
-      const int64_t c_off = (int64_t)b * p.c_batch_stride + (int64_t)row * p.c_ld;
-      const int64_t r_off = (int64_t)b * p.res_batch_stride + (int64_t)row * p.res_ld;
+      const int row_base = m_blk * TC_BM + quarter * 32;
+      const int rows_valid = p.rows - row_base;  // may be <= 0 or > 32
+      const int64_t c_row0 = (int64_t)b * p.c_batch_stride + (int64_t)row_base * p.c_ld;
+      const int64_t r_row0 = (int64_t)b * p.res_batch_stride + (int64_t)row_base * p.res_ld;
+      float* cf = nullptr;
+      __nv_bfloat16* cb = nullptr;
+      if (p.c_dtype == AVI_DT_F32) {
+        cf = reinterpret_cast<float*>(p.C);
+        cb = reinterpret_cast<__nv_bfloat16*>(p.C2);
+      } else {
+        cb = reinterpret_cast<__nv_bfloat16*>(p.C);
+        cf = reinterpret_cast<float*>(p.C2);
+      }
 #pragma unroll 1
       for (int ch = 0; ch < 4; ++ch) {
         const int col0 = half * 128 + ch * 32;
-        if (n0 + col0 >= p.N) break;  // warp-uniform
+        const int n_base = n0 + col0;
+        if (n_base >= p.N) break;  // warp-uniform
+        const int n = n_base + lane;
+        const bool n_ok = n < p.N;
+        float res[32];
+        if (p.residual != nullptr) {
+          const float* rp = p.residual + r_row0 + n;
+#pragma unroll
+          for (int r = 0; r < 32; ++r) res[r] = (r < rows_valid && n_ok) ? __ldg(rp + (int64_t)r * p.res_ld) : 0.f;
+        } else {
+#pragma unroll
+          for (int r = 0; r < 32; ++r) res[r] = 0.f;
+        }
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * TC_BN + col0), v);
-        float f[32];
-        const float4* bs = reinterpret_cast<const float4*>(sbias + as * TC_BN + col0);
+        const float4* bs = reinterpret_cast<const float4*>(sbias + col0);
+        float* trow = tile + lane * 32;
+        if (p.act == AVI_ACT_GELU) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 bb = bs[j];
-          f[4 * j + 0] = apply_act(__uint_as_float(v[4 * j + 0]) + bb.x, p.act);
-          f[4 * j + 1] = apply_act(__uint_as_float(v[4 * j + 1]) + bb.y, p.act);
-          f[4 * j + 2] = apply_act(__uint_as_float(v[4 * j + 2]) + bb.z, p.act);
-          f[4 * j + 3] = apply_act(__uint_as_float(v[4 * j + 3]) + bb.w, p.act);
-        }
-        const int n_base = n0 + col0;
-        if (p.vec_ok && n_base + 32 <= p.N) {
-          if (row_ok) {
-            if (p.residual) {
-              const float4* rp = reinterpret_cast<const float4*>(p.residual + r_off + n_base);
+          for (int j = 0; j < 8; ++j) {
+            const float4 bb = bs[j];
+            trow[(4 * j + 0) ^ lane] = gelu_fast(__uint_as_float(v[4 * j + 0]) + bb.x);
+            trow[(4 * j + 1) ^ lane] = gelu_fast(__uint_as_float(v[4 * j + 1]) + bb.y);
+            trow[(4 * j + 2) ^ lane] = gelu_fast(__uint_as_float(v[4 * j + 2]) + bb.z);
+            trow[(4 * j + 3) ^ lane] = gelu_fast(__uint_as_float(v[4 * j + 3]) + bb.w);
+          }
+        } else if (p.act == AVI_ACT_RELU) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 rr = __ldg(rp + j);
-                f[4 * j + 0] += rr.x;
-                f[4 * j + 1] += rr.y;
-                f[4 * j + 2] += rr.z;
-                f[4 * j + 3] += rr.w;
-              }
-            }
-            float* cf = nullptr;
-            __nv_bfloat16* cb = nullptr;
-            if (p.c_dtype == AVI_DT_F32) {
-              cf = reinterpret_cast<float*>(p.C);
-              cb = reinterpret_cast<__nv_bfloat16*>(p.C2);
-            } else {
-              cb = reinterpret_cast<__nv_bfloat16*>(p.C);
-              cf = reinterpret_cast<float*>(p.C2);
-            }
-            if (cf) {
-              float4* o = reinterpret_cast<float4*>(cf + c_off + n_base);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-            }
-            if (cb) {
-              uint4* o = reinterpret_cast<uint4*>(cb + c_off + n_base);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                __nv_bfloat162 h0 = __floats2bfloat162_rn(f[8 * j + 0], f[8 * j + 1]);
-                __nv_bfloat162 h1 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]);
-                __nv_bfloat162 h3 = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
-                uint4 u;
-                u.x = *reinterpret_cast<uint32_t*>(&h0);
-                u.y = *reinterpret_cast<uint32_t*>(&h1);
-                u.z = *reinterpret_cast<uint32_t*>(&h2);
-                u.w = *reinterpret_cast<uint32_t*>(&h3);
-                o[j] = u;
-              }
-            }
+          for (int j = 0; j < 8; ++j) {
+            const float4 bb = bs[j];
+            trow[(4 * j + 0) ^ lane] = fmaxf(__uint_as_float(v[4 * j + 0]) + bb.x, 0.f);
+            trow[(4 * j + 1) ^ lane] = fmaxf(__uint_as_float(v[4 * j + 1]) + bb.y, 0.f);
+            trow[(4 * j + 2) ^ lane] = fmaxf(__uint_as_float(v[4 * j + 2]) + bb.z, 0.f);
+            trow[(4 * j + 3) ^ lane] = fmaxf(__uint_as_float(v[4 * j + 3]) + bb.w, 0.f);
           }
         } else {
-          // unaligned rows / ragged N: transpose the warp's 32x32 block through smem (two 16-column passes) so that
-          // each store instruction writes 16 consecutive elements of two output rows (coalesced 64-byte runs)
-          const int row_base = m_blk * TC_BM + quarter * 32;
 #pragma unroll
-          for (int pass = 0; pass < 2; ++pass) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) my_trans[lane * 17 + j] = f[pass * 16 + j];
-            __syncwarp();
-            const int n = n_base + pass * 16 + (lane & 15);
-            for (int r2 = 0; r2 < 16; ++r2) {
-              const int r = 2 * r2 + (lane >> 4);
-              const int rr = row_base + r;
-              if (rr < p.rows && n < p.N) {
-                float val = my_trans[r * 17 + (lane & 15)];
-                const int64_t co = (int64_t)b * p.c_batch_stride + (int64_t)rr * p.c_ld + n;
-                if (p.residual) val += p.residual[(int64_t)b * p.res_batch_stride + (int64_t)rr * p.res_ld + n];
-                if (p.c_dtype == AVI_DT_F32) {
-                  reinterpret_cast<float*>(p.C)[co] = val;
-                  if (p.C2) reinterpret_cast<__nv_bfloat16*>(p.C2)[co] = __float2bfloat16_rn(val);
-                } else {
-                  reinterpret_cast<__nv_bfloat16*>(p.C)[co] = __float2bfloat16_rn(val);
-                  if (p.C2) reinterpret_cast<float*>(p.C2)[co] = val;
-                }
-              }
-            }
-            __syncwarp();
+          for (int j = 0; j < 8; ++j) {
+            const float4 bb = bs[j];
+            trow[(4 * j + 0) ^ lane] = __uint_as_float(v[4 * j + 0]) + bb.x;
+            trow[(4 * j + 1) ^ lane] = __uint_as_float(v[4 * j + 1]) + bb.y;
+            trow[(4 * j + 2) ^ lane] = __uint_as_float(v[4 * j + 2]) + bb.z;
+            trow[(4 * j + 3) ^ lane] = __uint_as_float(v[4 * j + 3]) + bb.w;
           }
         }
+        __syncwarp();
+        if (n_ok) {
+          const int64_t co = c_row0 + n;
+#pragma unroll
+          for (int r = 0; r < 32; ++r) {
+            if (r < rows_valid) {
+              const float val = tile[r * 32 + (lane ^ r)] + res[r];
+              if (cf) cf[co + (int64_t)r * p.c_ld] = val;
+              if (cb) cb[co + (int64_t)r * p.c_ld] = __float2bfloat16_rn(val);
+            }
+          }
+        }
+        __syncwarp();
       }
       // release the accumulator stage back to the MMA warp
       tc_fence_before();

@@ -18,6 +18,14 @@ from . import ops
 _N_POSE_FEAT = 36
 
 
+def default_precision() -> str:
+    import os
+    p = os.environ.get("AVI_B200_PRECISION", "bf16").lower()
+    if p not in ("bf16", "fp32"):
+        raise ValueError("AVI_B200_PRECISION must be bf16 or fp32")
+    return p
+
+
 def _k_pad(nb: int) -> int:
     return ((nb + _N_POSE_FEAT + 1 + 15) // 16) * 16
 
@@ -28,7 +36,7 @@ class _PackCache:
 
     def __init__(self):
         self.key = None
-        self.dirs = self.jreg = None
+        self.dirs = self.jreg = self.dirs16 = None
 
     def get(self, shapedirs, posedirs, v_template, J_regressor):
         key = tuple((t.data_ptr(), t._version, t.device) for t in (shapedirs, posedirs, v_template, J_regressor))
@@ -36,8 +44,19 @@ class _PackCache:
             nb = shapedirs.shape[2]
             self.dirs, self.jreg = ops.flame_pack(shapedirs.contiguous(), posedirs.contiguous(), v_template.contiguous(),
                                                   J_regressor.contiguous(), _k_pad(nb))
+            self.dirs16 = ops.flame_pack_tc(self.dirs, shapedirs.shape[0], nb) if ops.flame_tc_supported(nb) else None
             self.key = key
         return self.dirs, self.jreg
+
+
+def _run(cache, precision, betas, full_pose, shapedirs, posedirs, v_template, J_regressor, lbs_weights, **kw):
+    """precision 'bf16' -> tcgen05 blend (fp16 operands, ~1e-5 m); 'fp32' -> CUDA-core blend (exact to ~1e-7 m)."""
+    dirs, jreg = cache.get(shapedirs, posedirs, v_template, J_regressor)
+    V, nb = shapedirs.shape[0], shapedirs.shape[2]
+    if precision == "bf16" and cache.dirs16 is not None:
+        return ops.flame_lbs_tc(betas, full_pose, cache.dirs16, jreg, lbs_weights.contiguous(), v_template.contiguous(), V, nb,
+                                _k_pad(nb), **kw)
+    return ops.flame_lbs(betas, full_pose, dirs, jreg, lbs_weights.contiguous(), V, nb, _k_pad(nb), **kw)
 
 
 _lbs_cache = _PackCache()
@@ -56,9 +75,8 @@ def lbs(betas, pose, v_template, shapedirs, posedirs, J_regressor, parents, lbs_
     betas = betas.expand(B, -1).contiguous().float()
     pose = pose.expand(B, -1).contiguous().float()
     cache = _cache if _cache is not None else _lbs_cache
-    dirs, jreg = cache.get(shapedirs, posedirs, vt, J_regressor)
-    V, nb = shapedirs.shape[0], shapedirs.shape[2]
-    verts, joints, _ = ops.flame_lbs(betas, pose, dirs, jreg, lbs_weights.contiguous(), V, nb, _k_pad(nb), want_joints=True)
+    verts, joints, _ = _run(cache, default_precision(), betas, pose, shapedirs, posedirs, vt, J_regressor, lbs_weights,
+                            want_joints=True)
     return verts, joints
 
 
@@ -110,6 +128,7 @@ class FLAME(nn.Module):
         if chain != [1, 0]:
             raise NotImplementedError("unexpected neck kinematic chain")
         self._pack = _PackCache()
+        self.precision = default_precision()
 
     # -- pieces -------------------------------------------------------------------------------------------------
     def _full_pose(self, batch_size, pose_params, eye_pose_params):
@@ -125,11 +144,11 @@ class FLAME(nn.Module):
             expression_params = torch.zeros(B, self.cfg.n_exp, device=shape_params.device)
         betas = torch.cat([shape_params, expression_params], dim=1).contiguous().float()
         full_pose = self._full_pose(B, pose_params, eye_pose_params).contiguous().float()
-        dirs, jreg = self._pack.get(self.shapedirs, self.posedirs, self.v_template, self.J_regressor)
-        V, nb = self.shapedirs.shape[0], self.shapedirs.shape[2]
+        nb = self.shapedirs.shape[2]
         if betas.shape[1] != nb:
             raise ValueError(f"expected {nb} shape+expression coefficients, got {betas.shape[1]}")
-        verts, _, rows = ops.flame_lbs(betas, full_pose, dirs, jreg, self.lbs_weights, V, nb, _k_pad(nb), want_dyn_rows=want_rows)
+        verts, _, rows = _run(self._pack, self.precision, betas, full_pose, self.shapedirs, self.posedirs, self.v_template,
+                              self.J_regressor, self.lbs_weights, want_dyn_rows=want_rows)
         return verts, rows
 
     def _landmarks(self, verts, rows):

@@ -251,6 +251,39 @@ def flame_lbs(betas, full_pose, dirs, jreg, lbs_weights, V, NB, K_pad, want_join
     return verts, joints, rows
 
 
+def flame_tc_supported(NB: int) -> bool:
+    return bool(_lib.load().avi_flame_tc_supported(C.c_int32(NB)))
+
+
+def flame_pack_tc(dirs32, V, NB):
+    V_pad = ((V + 127) // 128) * 128
+    dirs16 = torch.empty((3, V_pad, 192), dtype=torch.float16, device=dirs32.device)
+    _lib.check(_lib.load().avi_flame_pack_tc(_ptr(dirs32), _ptr(dirs16), C.c_int32(V), C.c_int32(NB), C.c_int32(V_pad), _stream()),
+               "avi_flame_pack_tc")
+    return dirs16
+
+
+def flame_lbs_tc(betas, full_pose, dirs16, jreg, lbs_weights, v_template, V, NB, K_pad, want_joints=False, want_dyn_rows=False):
+    """Same results contract as flame_lbs, blend + skinning on the tcgen05 path."""
+    _need_cuda(betas, full_pose)
+    F = betas.shape[0]
+    dev = betas.device
+    coef = torch.empty((F, K_pad), dtype=torch.float32, device=dev)
+    coef16 = torch.empty((F, 192), dtype=torch.float16, device=dev)
+    A = torch.empty((F, 5, 12), dtype=torch.float32, device=dev)
+    verts = torch.empty((F, V, 3), dtype=torch.float32, device=dev)
+    joints = torch.empty((F, 5, 3), dtype=torch.float32, device=dev) if want_joints else None
+    rows = torch.empty((F,), dtype=torch.int32, device=dev) if want_dyn_rows else None
+    lib = _lib.load()
+    with _timed("flame_lbs", float(F) * (V * 12 + 4 * (NB + 6))):
+        _lib.check(lib.avi_flame_prologue(_ptr(betas), _ptr(full_pose), _ptr(jreg), _ptr(coef), _ptr(A), _ptr(joints), _ptr(rows),
+                                          C.c_int32(F), C.c_int32(NB), C.c_int32(K_pad), _stream()), "avi_flame_prologue")
+        _lib.check(lib.avi_flame_blend_skin_tc(_ptr(coef), _ptr(A), _ptr(dirs16), _ptr(lbs_weights), _ptr(v_template), _ptr(coef16),
+                                               _ptr(verts), C.c_int32(F), C.c_int32(V), C.c_int32(NB), C.c_int32(K_pad),
+                                               C.c_int32(dirs16.shape[1]), _stream()), "avi_flame_blend_skin_tc")
+    return verts, joints, rows
+
+
 def flame_landmarks(verts, faces, idx, bary, per_frame: bool):
     _need_cuda(verts, faces, idx, bary)
     F, V, _ = verts.shape

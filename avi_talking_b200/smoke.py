@@ -24,6 +24,7 @@ def build_models(precision: str, fd: int = 64, device: str = "cuda", seed_ff: in
     model.load_state_dict(synth.faceformer_state(fd=fd, seed=seed_ff), strict=False)
     model.precision = precision
     w2v.precision = precision
+    flame.precision = precision
     return model.to(device).eval()
 
 
@@ -43,21 +44,21 @@ def run_smoke(verbose: bool = False) -> dict:
     template = buf["v_template"].reshape(1, 1, 15069)
     ref = ffo.predict(sd_ff, sd_w2v, template, a, emo, cached=True)
     n0 = _lib.launch_count()
-    m = None
-    for prec, tol in (("fp32", 1e-5), ("bf16", 1e-4)):
+    p = synth.flame_params(8, seed=3)
+    want = fo.flame_forward(buf, p["shape"], p["exp"], p["pose"], p["eye"], mediapipe=True)
+    # tolerances: fp32 mode 1e-5 m (vertices) / 1e-6 m (FLAME alone); bf16 mode 1e-4 m / 5e-5 m (fp16 tensor-core blend)
+    for prec, tol, tol_flame in (("fp32", 1e-5, 1e-6), ("bf16", 1e-4, 5e-5)):
         m = build_models(prec)
         v = m.predict_from_embeddings(a.cuda(), emo.cuda())
         torch.cuda.synchronize()
         err = (v.cpu() - ref).abs().max().item()
         res[f"predict_{prec}_max_abs_m"] = err
         assert err < tol, f"{prec} predict: max abs vertex error {err} m exceeds {tol}"
-    p = synth.flame_params(8, seed=3)
-    got = m.flame(p["shape"].cuda(), p["exp"].cuda(), p["pose"].cuda(), p["eye"].cuda())
-    want = fo.flame_forward(buf, p["shape"], p["exp"], p["pose"], p["eye"], mediapipe=True)
-    for name, g, w in zip(("verts", "lmk2d", "lmk3d", "lmk_mp"), got, want):
-        err = (g.cpu() - w).abs().max().item()
-        res[f"flame_{name}_max_abs_m"] = err
-        assert err < 1e-6, f"FLAME {name}: {err}"
+        got = m.flame(p["shape"].cuda(), p["exp"].cuda(), p["pose"].cuda(), p["eye"].cuda())
+        for name, g, w in zip(("verts", "lmk2d", "lmk3d", "lmk_mp"), got, want):
+            err = (g.cpu() - w).abs().max().item()
+            res[f"flame_{prec}_{name}_max_abs_m"] = err
+            assert err < tol_flame, f"FLAME {prec} {name}: {err}"
     res["kernel_launches"] = _lib.launch_count() - n0
     if verbose:
         print("smoke OK:", res)

@@ -162,6 +162,19 @@ int avi_flame_lbs_fwd(const float* betas, const float* full_pose, const float* d
                       float* coef, float* A, float* verts, float* joints, int32_t* dyn_rows, int32_t F, int32_t V, int32_t NB,
                       int32_t K_pad, void* stream);
 
+/* first half of avi_flame_lbs_fwd only (coefficient rows, joints, kinematic chain, landmark rows), for the tensor-core blend below */
+int avi_flame_prologue(const float* betas, const float* full_pose, const float* jreg, float* coef, float* A, float* joints,
+                       int32_t* dyn_rows, int32_t F, int32_t NB, int32_t K_pad, void* stream);
+
+/* tcgen05 blend + fused skinning (fp16 operands, fp32 accumulate/template/skinning; NB + 36 <= 192).
+ *   avi_flame_pack_tc : dirs16 fp16 [3][V_pad][192] from the packed fp32 dirs of avi_flame_pack (V_pad multiple of 128)
+ *   avi_flame_blend_skin_tc : consumes coef [F, K_pad32] and A [F,5,12] written by avi_flame_prologue; coef16 = scratch fp16 [F,192] */
+int avi_flame_tc_supported(int32_t NB);
+int avi_flame_pack_tc(const float* dirs32, void* dirs16, int32_t V, int32_t NB, int32_t V_pad, void* stream);
+int avi_flame_blend_skin_tc(const float* coef32, const float* A, const void* dirs16, const float* lbs_weights,
+                            const float* v_template, void* coef16, float* verts, int32_t F, int32_t V, int32_t NB,
+                            int32_t K_pad32, int32_t V_pad, void* stream);
+
 /* barycentric landmark gather (lbs.py:103-139): out[f, l, :] = sum_c bary[f|0, l, c] * verts[f, faces[idx[f|0, l], c], :].
  * per_frame = 1 when idx/bary carry a frame dimension (dynamic contour landmarks). */
 int avi_flame_landmarks(const float* verts, const int64_t* faces, const int64_t* idx, const float* bary, float* out,

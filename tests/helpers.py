@@ -30,8 +30,10 @@ def build_faceformer(precision, fd=64, seed=74, device="cuda", w2v=None, variant
     return m.to(device).eval()
 
 
-def build_flame(n_shape=100, device="cuda", mediapipe=True, tmpdir="/tmp/avi_flame_assets_test"):
+def build_flame(n_shape=100, device="cuda", mediapipe=True, tmpdir="/tmp/avi_flame_assets_test", precision="fp32"):
     from avi_talking_b200.flame import FLAME, FLAME_mediapipe
     cfg = synth.write_flame_assets(tmpdir)
     cfg.n_shape = n_shape
-    return (FLAME_mediapipe(cfg) if mediapipe else FLAME(cfg)).to(device)
+    m = (FLAME_mediapipe(cfg) if mediapipe else FLAME(cfg)).to(device)
+    m.precision = precision
+    return m

@@ -40,8 +40,9 @@ def test_flame_matches_reference_golden(golden, n_shape, tag):
     assert np.abs(v.cpu().numpy() - g[f"verts_jawonly_{tag}"]).max() < 1e-6
 
 
-def test_flame_lbs_function_and_identities(golden):
+def test_flame_lbs_function_and_identities(golden, monkeypatch):
     from avi_talking_b200.flame import lbs
+    monkeypatch.setenv("AVI_B200_PRECISION", "fp32")   # the free function has no module to carry the mode
     g = golden("flame")
     buf = {k: v.cuda() for k, v in synth.flame_buffers(100, 50).items()}
     p = synth.flame_params(2, seed=5)
@@ -60,21 +61,35 @@ def test_flame_lbs_function_and_identities(golden):
                buf["J_regressor"], buf["parents"], buf["lbs_weights"])
     want = buf["v_template"] + torch.einsum("bl,mkl->bmk", betas, buf["shapedirs"])
     assert (v - want).abs().max().item() < 1e-6
+    monkeypatch.setenv("AVI_B200_PRECISION", "bf16")   # tcgen05 blend (fp16 operands): 5e-5 m
+    v, J = lbs(betas, full_pose, buf["v_template"], buf["shapedirs"], buf["posedirs"], buf["J_regressor"], buf["parents"],
+               buf["lbs_weights"])
+    assert np.abs(v.cpu().numpy() - g["gdl_lbs_verts"]).max() < 5e-5
+    assert np.abs(J.cpu().numpy() - g["gdl_lbs_joints"]).max() < 1e-6
 
 
-def test_flame_many_frames_and_template_mutation():
-    """Ragged frame/vertex tiles (F=333 is not a multiple of 64) and the in-place v_template mutation callers perform."""
-    m = build_flame(100, mediapipe=False)
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-6), ("bf16", 5e-5)])
+def test_flame_many_frames_and_template_mutation(precision, tol):
+    """Ragged frame/vertex tiles (F=333 is not a multiple of 64) and the in-place v_template mutation callers perform.
+    bf16 mode = tcgen05 blend with fp16 operands (tolerance 5e-5 m, inside the 1e-4 m budget); fp32 mode = CUDA-core blend."""
+    m = build_flame(100, mediapipe=False, precision=precision)
     buf = synth.flame_buffers(100, 50)
     p = synth.flame_params(333, seed=11)
     v = m.vertices_only(p["shape"].cuda(), p["exp"].cuda(), p["pose"].cuda(), p["eye"].cuda())
     ref = fo.flame_forward(buf, p["shape"], p["exp"], p["pose"], p["eye"])[0]
-    assert (v.cpu() - ref).abs().max().item() < 1e-6
+    err = (v.cpu() - ref).abs().max().item()
+    print(f"FLAME {precision} F=333 max abs vertex error {err:.3e} m")
+    assert err < tol
+    if precision == "bf16":   # a multi-chunk case: > 16 frame tiles per vertex tile, > 148 work items
+        p2 = synth.flame_params(2500, seed=12)
+        v2 = m.vertices_only(p2["shape"].cuda(), p2["exp"].cuda(), p2["pose"].cuda(), p2["eye"].cuda())
+        ref2 = fo.flame_forward(buf, p2["shape"], p2["exp"], p2["pose"], p2["eye"])[0]
+        assert (v2.cpu() - ref2).abs().max().item() < tol
     m.v_template.add_(0.01)    # TalkingHeadWrapper.py:140-158 style mutation must invalidate the packed cache
     buf["v_template"] = buf["v_template"] + 0.01
     v = m.vertices_only(p["shape"][:5].cuda(), p["exp"][:5].cuda(), p["pose"][:5].cuda(), p["eye"][:5].cuda())
     ref = fo.flame_forward(buf, p["shape"][:5], p["exp"][:5], p["pose"][:5], p["eye"][:5])[0]
-    assert (v.cpu() - ref).abs().max().item() < 1e-6
+    assert (v.cpu() - ref).abs().max().item() < tol
 
 
 # ------------------------------------------------------------------------------------------------ wav2vec2
