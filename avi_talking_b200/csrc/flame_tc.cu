@@ -6,7 +6,7 @@
 // Mapping: vertices are the MMA M dimension (TMEM lane = vertex), frames the N dimension, one accumulator per coordinate
 // (x, y, z), so that after tcgen05.ld a thread holds x/y/z of ITS vertex for 32 frames and applies the per-frame skinning
 // transform with its own 5 skinning weights in registers; consecutive lanes are consecutive vertices, so each frame's
-// 32 x 3 floats leave through a tiny smem transpose as three fully coalesced 128-byte stores.
+// 32 x 3 floats form one contiguous 384-byte run (three 12-byte-strided stores per warp).
 // Operands are fp16 (11-bit significand: ~1e-5 m worst case on ~1e-2 m displacements, vs ~1.7e-4 m for bf16); the
 // template is added in fp32 in the epilogue so its 8 cm magnitude never passes through 16-bit rounding.
 // A CTA keeps the direction slab of its 128-vertex tile (3 x [128 x 192] fp16 = 144 KB) resident in shared memory and
@@ -25,7 +25,8 @@ constexpr uint32_t FT_DIRS_BYTES = 3 * FT_NCH * FT_DIR_TILE;     // 144 KB
 constexpr uint32_t FT_COEF_TILE = FT_NF * FT_KC * 2;             // 8 KB per k-chunk
 constexpr uint32_t FT_COEF_BYTES = FT_NCH * FT_COEF_TILE;        // 24 KB per stage
 constexpr uint32_t FT_AS_BYTES = FT_NF * FT_NJ * 12 * 4;         // 15 KB per stage
-constexpr uint32_t FT_TR_BYTES = 8 * 96 * 4;
+constexpr int FT_EPI_WARPS = 16, FT_THREADS = (2 + FT_EPI_WARPS) * 32;  // 4 epilogue warps per SM sub-partition
+constexpr uint32_t FT_TR_BYTES = 0;
 constexpr uint32_t FT_OFF_COEF = FT_DIRS_BYTES;
 constexpr uint32_t FT_OFF_AS = FT_OFF_COEF + 2 * FT_COEF_BYTES;
 constexpr uint32_t FT_OFF_TR = FT_OFF_AS + 2 * FT_AS_BYTES;
@@ -46,7 +47,7 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
   umma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);  // same instruction (kind::f16); idesc selects fp16 operands
 }
 
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(FT_THREADS, 1)
 flame_tc_kernel(const __grid_constant__ CUtensorMap map_dirs, const __grid_constant__ CUtensorMap map_coef, const FlameTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -69,9 +70,9 @@ flame_tc_kernel(const __grid_constant__ CUtensorMap map_dirs, const __grid_const
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&cf_full[s]), 1);
       mbar_init(smem_u32(&coef_empty[s]), 1);
-      mbar_init(smem_u32(&as_empty[s]), 8);
+      mbar_init(smem_u32(&as_empty[s]), FT_EPI_WARPS);
       mbar_init(smem_u32(&tmem_full[s]), 1);
-      mbar_init(smem_u32(&tmem_empty[s]), 8);
+      mbar_init(smem_u32(&tmem_empty[s]), FT_EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -157,9 +158,9 @@ flame_tc_kernel(const __grid_constant__ CUtensorMap map_dirs, const __grid_const
     }
   } else {
     // ============ epilogue: template add + skinning + coalesced stores ============
+    // 16 warps: TMEM lane quarter = warp % 4 (32 vertices), frame quarter = (warp - 2) / 4 (16 of the tile's 64 frames)
     const int ew = warp - 2;
-    const int quarter = warp & 3, half = ew >> 2;
-    float* tr = reinterpret_cast<float*>(smem + FT_OFF_TR) + ew * 96;
+    const int quarter = warp & 3, fq = ew >> 2;
     const int V3 = p.V * 3;
     int stage = 0;
     uint32_t phase = 0;
@@ -173,6 +174,7 @@ flame_tc_kernel(const __grid_constant__ CUtensorMap map_dirs, const __grid_const
       for (int j = 0; j < FT_NJ; ++j) w[j] = (v < p.V) ? p.lbs_w[(int64_t)v * FT_NJ + j] : 0.f;
 #pragma unroll
       for (int c = 0; c < 3; ++c) vtp[c] = (v < p.V) ? p.v_template[(int64_t)v * 3 + c] : 0.f;
+      const bool v_ok = v < p.V;
       const int ft0 = chunk * FT_CHUNK_TILES;
       const int ft1 = min(ft0 + FT_CHUNK_TILES, p.n_ftiles);
       for (int ft = ft0; ft < ft1; ++ft, ++acc_it) {
@@ -181,26 +183,25 @@ flame_tc_kernel(const __grid_constant__ CUtensorMap map_dirs, const __grid_const
         mbar_wait(smem_u32(&cf_full[stage]), phase);   // joint transforms of this tile are in smem
         mbar_wait(smem_u32(&tmem_full[as]), aph);
         tc_fence_after();
-        uint32_t vx[32], vy[32], vz[32];
-        const uint32_t ta = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * (3 * FT_NF) + half * 32);
-        tmem_ld32(ta, vx);
-        tmem_ld32(ta + FT_NF, vy);
-        tmem_ld32(ta + 2 * FT_NF, vz);
-        const float* As = reinterpret_cast<const float*>(smem + FT_OFF_AS + stage * FT_AS_BYTES) + (half * 32) * (FT_NJ * 12);
-        const int fbase = ft * FT_NF + half * 32;
+        uint32_t vx[16], vy[16], vz[16];
+        const uint32_t ta = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * (3 * FT_NF) + fq * 16);
+        tmem_ld16(ta, vx);
+        tmem_ld16(ta + FT_NF, vy);
+        tmem_ld16(ta + 2 * FT_NF, vz);
+        const uint32_t As = smem_u32(smem + FT_OFF_AS + stage * FT_AS_BYTES) + (fq * 16) * (FT_NJ * 12 * 4);
+        const int fbase = ft * FT_NF + fq * 16;
+        float* o = p.verts + (int64_t)fbase * V3 + (int64_t)v * 3;   // lanes = consecutive vertices: 384 contiguous bytes per frame
 #pragma unroll
-        for (int n = 0; n < 32; ++n) {
-          const int f = fbase + n;
-          if (f < p.F) {  // warp-uniform
+        for (int n = 0; n < 16; ++n) {
+          if (fbase + n < p.F) {  // warp-uniform
             float T[12];
 #pragma unroll
             for (int e = 0; e < 12; ++e) T[e] = 0.f;
 #pragma unroll
             for (int j = 0; j < FT_NJ; ++j) {
-              const float4* ap = reinterpret_cast<const float4*>(As + n * (FT_NJ * 12) + j * 12);
 #pragma unroll
               for (int q = 0; q < 3; ++q) {
-                const float4 a = ap[q];
+                const float4 a = lds128f(As + (n * (FT_NJ * 12) + j * 12 + q * 4) * 4);
                 T[q * 4 + 0] = fmaf(w[j], a.x, T[q * 4 + 0]);
                 T[q * 4 + 1] = fmaf(w[j], a.y, T[q * 4 + 1]);
                 T[q * 4 + 2] = fmaf(w[j], a.z, T[q * 4 + 2]);
@@ -208,18 +209,13 @@ flame_tc_kernel(const __grid_constant__ CUtensorMap map_dirs, const __grid_const
               }
             }
             const float px = __uint_as_float(vx[n]) + vtp[0], py = __uint_as_float(vy[n]) + vtp[1], pz = __uint_as_float(vz[n]) + vtp[2];
+            if (v_ok) {
 #pragma unroll
-            for (int i = 0; i < 3; ++i)
-              tr[lane * 3 + i] = fmaf(T[i * 4 + 0], px, fmaf(T[i * 4 + 1], py, fmaf(T[i * 4 + 2], pz, T[i * 4 + 3])));
-            __syncwarp();
-            float* o = p.verts + (int64_t)f * V3 + (int64_t)vw0 * 3;
-#pragma unroll
-            for (int u = 0; u < 3; ++u) {
-              const int idx = lane + 32 * u;
-              if (vw0 * 3 + idx < V3) o[idx] = tr[idx];
+              for (int i = 0; i < 3; ++i)
+                o[i] = fmaf(T[i * 4 + 0], px, fmaf(T[i * 4 + 1], py, fmaf(T[i * 4 + 2], pz, T[i * 4 + 3])));
             }
-            __syncwarp();
           }
+          o += V3;
         }
         tc_fence_before();
         __syncwarp();
@@ -318,6 +314,6 @@ extern "C" int avi_flame_blend_skin_tc(const float* coef32, const float* A, cons
   std::call_once(once, [] { attr_err = cudaFuncSetAttribute(flame_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM); });
   AVI_REQUIRE(attr_err == cudaSuccess, "avi_flame_blend_skin_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
   const int grid = p.n_items < kNumSMs ? p.n_items : kNumSMs;
-  flame_tc_kernel<<<grid, 320, FT_SMEM, st>>>(map_dirs, map_coef, p);
+  flame_tc_kernel<<<grid, FT_THREADS, FT_SMEM, st>>>(map_dirs, map_coef, p);
   return check_launch("flame_tc");
 }

@@ -145,14 +145,18 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
   } else {
     // ===================== epilogue: TMEM -> registers -> smem transpose -> coalesced global =====================
-    // Phase A (thread = accumulator row): tcgen05.ld 32 columns, + bias, activation, into a per-warp 32x32 XOR-swizzled tile.
-    // Phase B (lane = output column): every instruction reads/writes 32 consecutive elements of ONE output row, so the
-    // residual loads and the stores are fully coalesced whatever the row pitch (15069-wide vertex rows included).
+    // Phase A (thread = accumulator row): tcgen05.ld 32 columns, + bias, activation, written to a per-warp staging tile.
+    // Phase B (lanes span the columns of a few rows): 16-byte shared loads and fully coalesced 16-byte global accesses
+    // (residual read + output write).  Three variants: packed bf16 rows, fp32 rows (+ residual), and a scalar one for
+    // unaligned / ragged outputs (the 15069-wide vertex rows).  The XOR swizzles keep every shared access conflict-free.
     const int ew = warp - 2;              // 0..7
     const int quarter = warp & 3;         // TMEM lanes [32*quarter, +32) are the only ones this warp may touch
     const int half = ew >> 2;             // columns [128*half, +128)
     const int etid = threadIdx.x - 64;    // 0..255
-    float* tile = trans + ew * (32 * 32);
+    const uint32_t tile = smem_u32(trans) + ew * (32 * 32 * 4);
+    const uint32_t sbias_a = smem_u32(sbias);
+    const bool fast_bf16 = p.vec_ok && p.c_dtype == AVI_DT_BF16 && p.C2 == nullptr && p.residual == nullptr;
+    const bool fast_f32 = p.vec_ok && p.c_dtype == AVI_DT_F32 && p.C2 == nullptr;
     int it = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
       const int as = it & 1;
@@ -173,76 +177,115 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       const int rows_valid = p.rows - row_base;  // may be <= 0 or > 32
       const int64_t c_row0 = (int64_t)b * p.c_batch_stride + (int64_t)row_base * p.c_ld;
       const int64_t r_row0 = (int64_t)b * p.res_batch_stride + (int64_t)row_base * p.res_ld;
-      float* cf = nullptr;
-      __nv_bfloat16* cb = nullptr;
-      if (p.c_dtype == AVI_DT_F32) {
-        cf = reinterpret_cast<float*>(p.C);
-        cb = reinterpret_cast<__nv_bfloat16*>(p.C2);
-      } else {
-        cb = reinterpret_cast<__nv_bfloat16*>(p.C);
-        cf = reinterpret_cast<float*>(p.C2);
-      }
 #pragma unroll 1
       for (int ch = 0; ch < 4; ++ch) {
         const int col0 = half * 128 + ch * 32;
         const int n_base = n0 + col0;
         if (n_base >= p.N) break;  // warp-uniform
-        const int n = n_base + lane;
-        const bool n_ok = n < p.N;
-        float res[32];
-        if (p.residual != nullptr) {
-          const float* rp = p.residual + r_row0 + n;
-#pragma unroll
-          for (int r = 0; r < 32; ++r) res[r] = (r < rows_valid && n_ok) ? __ldg(rp + (int64_t)r * p.res_ld) : 0.f;
-        } else {
-#pragma unroll
-          for (int r = 0; r < 32; ++r) res[r] = 0.f;
-        }
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * TC_BN + col0), v);
-        const float4* bs = reinterpret_cast<const float4*>(sbias + col0);
-        float* trow = tile + lane * 32;
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 bb = lds128f(sbias_a + (col0 + 4 * j) * 4);
+          f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + bb.x;
+          f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bb.y;
+          f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bb.z;
+          f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bb.w;
+        }
         if (p.act == AVI_ACT_GELU) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 bb = bs[j];
-            trow[(4 * j + 0) ^ lane] = gelu_fast(__uint_as_float(v[4 * j + 0]) + bb.x);
-            trow[(4 * j + 1) ^ lane] = gelu_fast(__uint_as_float(v[4 * j + 1]) + bb.y);
-            trow[(4 * j + 2) ^ lane] = gelu_fast(__uint_as_float(v[4 * j + 2]) + bb.z);
-            trow[(4 * j + 3) ^ lane] = gelu_fast(__uint_as_float(v[4 * j + 3]) + bb.w);
-          }
+          for (int j = 0; j < 32; ++j) f[j] = gelu_fast(f[j]);
         } else if (p.act == AVI_ACT_RELU) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 bb = bs[j];
-            trow[(4 * j + 0) ^ lane] = fmaxf(__uint_as_float(v[4 * j + 0]) + bb.x, 0.f);
-            trow[(4 * j + 1) ^ lane] = fmaxf(__uint_as_float(v[4 * j + 1]) + bb.y, 0.f);
-            trow[(4 * j + 2) ^ lane] = fmaxf(__uint_as_float(v[4 * j + 2]) + bb.z, 0.f);
-            trow[(4 * j + 3) ^ lane] = fmaxf(__uint_as_float(v[4 * j + 3]) + bb.w, 0.f);
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 bb = bs[j];
-            trow[(4 * j + 0) ^ lane] = __uint_as_float(v[4 * j + 0]) + bb.x;
-            trow[(4 * j + 1) ^ lane] = __uint_as_float(v[4 * j + 1]) + bb.y;
-            trow[(4 * j + 2) ^ lane] = __uint_as_float(v[4 * j + 2]) + bb.z;
-            trow[(4 * j + 3) ^ lane] = __uint_as_float(v[4 * j + 3]) + bb.w;
-          }
+          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
         }
-        __syncwarp();
-        if (n_ok) {
-          const int64_t co = c_row0 + n;
+        const bool full_n = n_base + 32 <= p.N;
+        if (fast_bf16 && full_n) {
+          // tile: 32 rows x 16 packed words, pitch 16 words; 4-word group g of row r lives at group g ^ ((r >> 1) & 3)
 #pragma unroll
-          for (int r = 0; r < 32; ++r) {
+          for (int g = 0; g < 4; ++g) {
+            uint32_t w[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(f[8 * g + 2 * u], f[8 * g + 2 * u + 1]);
+              w[u] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+            sts128(tile + (lane * 16 + 4 * (g ^ ((lane >> 1) & 3))) * 4, w[0], w[1], w[2], w[3]);
+          }
+          __syncwarp();
+          __nv_bfloat16* cb = reinterpret_cast<__nv_bfloat16*>(p.C) + c_row0 + n_base;
+          const int g = lane & 3;
+#pragma unroll
+          for (int i8 = 0; i8 < 4; ++i8) {
+            const int r = i8 * 8 + (lane >> 2);
             if (r < rows_valid) {
-              const float val = tile[r * 32 + (lane ^ r)] + res[r];
-              if (cf) cf[co + (int64_t)r * p.c_ld] = val;
-              if (cb) cb[co + (int64_t)r * p.c_ld] = __float2bfloat16_rn(val);
+              const uint4 q = lds128(tile + (r * 16 + 4 * (g ^ ((r >> 1) & 3))) * 4);
+              *reinterpret_cast<uint4*>(cb + (int64_t)r * p.c_ld + 8 * g) = q;
             }
           }
+          __syncwarp();
+        } else if (fast_f32 && full_n) {
+          // tile: 32 rows x 32 words, pitch 32; 4-word group g of row r lives at group g ^ (r & 7)
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            sts128(tile + (lane * 32 + 4 * (g ^ (lane & 7))) * 4, __float_as_uint(f[4 * g]), __float_as_uint(f[4 * g + 1]),
+                   __float_as_uint(f[4 * g + 2]), __float_as_uint(f[4 * g + 3]));
+          __syncwarp();
+          float* cf = reinterpret_cast<float*>(p.C) + c_row0 + n_base;
+          const float* rp = p.residual ? p.residual + r_row0 + n_base : nullptr;
+          const int g = lane & 7;
+          float4 rr[8];
+#pragma unroll
+          for (int i4 = 0; i4 < 8; ++i4) {
+            const int r = i4 * 4 + (lane >> 3);
+            rr[i4] = (rp != nullptr && r < rows_valid) ? __ldg(reinterpret_cast<const float4*>(rp + (int64_t)r * p.res_ld + 4 * g))
+                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int i4 = 0; i4 < 8; ++i4) {
+            const int r = i4 * 4 + (lane >> 3);
+            if (r < rows_valid) {
+              float4 q = lds128f(tile + (r * 32 + 4 * (g ^ (r & 7))) * 4);
+              q.x += rr[i4].x;
+              q.y += rr[i4].y;
+              q.z += rr[i4].z;
+              q.w += rr[i4].w;
+              *reinterpret_cast<float4*>(cf + (int64_t)r * p.c_ld + 4 * g) = q;
+            }
+          }
+          __syncwarp();
+        } else {
+          // generic: element (row, col j) at word row*32 + (j ^ row); lane = column in phase B
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sts32(tile + (lane * 32 + (j ^ lane)) * 4, __float_as_uint(f[j]));
+          __syncwarp();
+          const int n = n_base + lane;
+          if (n < p.N) {
+            float* cf = nullptr;
+            __nv_bfloat16* cb = nullptr;
+            if (p.c_dtype == AVI_DT_F32) {
+              cf = reinterpret_cast<float*>(p.C);
+              cb = reinterpret_cast<__nv_bfloat16*>(p.C2);
+            } else {
+              cb = reinterpret_cast<__nv_bfloat16*>(p.C);
+              cf = reinterpret_cast<float*>(p.C2);
+            }
+            const int rmax = rows_valid < 32 ? rows_valid : 32;
+            int64_t co = c_row0 + n;
+            int64_t ro = r_row0 + n;
+#pragma unroll 4
+            for (int r = 0; r < rmax; ++r) {
+              float val = __uint_as_float(lds32(tile + (r * 32 + (lane ^ r)) * 4));
+              if (p.residual) val += p.residual[ro];
+              if (cf) cf[co] = val;
+              if (cb) cb[co] = __float2bfloat16_rn(val);
+              co += p.c_ld;
+              ro += p.res_ld;
+            }
+          }
+          __syncwarp();
         }
-        __syncwarp();
       }
       // release the accumulator stage back to the MMA warp
       tc_fence_before();

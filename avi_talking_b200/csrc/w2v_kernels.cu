@@ -184,6 +184,70 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   }
 }
 
+// Vectorised variant for C % 128 == 0 (512 / 768): NV float4 per lane, 16-byte loads/stores, 8-byte bf16 stores.
+template <int NV, int MODE>
+__global__ void __launch_bounds__(256) layernorm_vec_kernel(const float* __restrict__ x, const float* p,  // p may alias out_f32
+                                                            const float* __restrict__ w, const float* __restrict__ bsh,
+                                                            float* out_f32, __nv_bfloat16* __restrict__ out_bf16, int64_t rows,
+                                                            float eps) {
+  constexpr int C = NV * 128;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * C);
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int u = 0; u < NV; ++u) {
+    v[u] = xr[lane + 32 * u];
+    if constexpr (MODE != 0) {
+      const float4 q = reinterpret_cast<const float4*>(p + row * C)[lane + 32 * u];
+      if constexpr (MODE == 1) {
+        v[u].x += gelu_erf(q.x); v[u].y += gelu_erf(q.y); v[u].z += gelu_erf(q.z); v[u].w += gelu_erf(q.w);
+      } else {
+        v[u].x += q.x; v[u].y += q.y; v[u].z += q.z; v[u].w += q.w;
+      }
+    }
+    s += (v[u].x + v[u].y) + (v[u].z + v[u].w);
+  }
+  const float mean = warp_sum(s) * (1.f / C);
+  float q2 = 0.f;
+#pragma unroll
+  for (int u = 0; u < NV; ++u) {
+    const float a = v[u].x - mean, b = v[u].y - mean, c = v[u].z - mean, d = v[u].w - mean;
+    q2 += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(q2) * (1.f / C) + eps);
+#pragma unroll
+  for (int u = 0; u < NV; ++u) {
+    const float4 g = reinterpret_cast<const float4*>(w)[lane + 32 * u];
+    const float4 bb = reinterpret_cast<const float4*>(bsh)[lane + 32 * u];
+    float4 y;
+    y.x = (v[u].x - mean) * rstd * g.x + bb.x;
+    y.y = (v[u].y - mean) * rstd * g.y + bb.y;
+    y.z = (v[u].z - mean) * rstd * g.z + bb.z;
+    y.w = (v[u].w - mean) * rstd * g.w + bb.w;
+    if (out_f32) reinterpret_cast<float4*>(out_f32 + row * C)[lane + 32 * u] = y;
+    if (out_bf16) {
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(y.x, y.y), h1 = __floats2bfloat162_rn(y.z, y.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&h0);
+      pk.y = *reinterpret_cast<uint32_t*>(&h1);
+      reinterpret_cast<uint2*>(out_bf16 + row * C)[lane + 32 * u] = pk;
+    }
+  }
+}
+
+template <int MODE>
+static void launch_layernorm(const float* x, const float* p, const float* w, const float* b, float* o32, __nv_bfloat16* o16,
+                             int64_t rows, int C, float eps, cudaStream_t st) {
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  const bool al = (((uintptr_t)x | (uintptr_t)p | (uintptr_t)w | (uintptr_t)b | (uintptr_t)o32) % 16 == 0) && ((uintptr_t)o16 % 8 == 0);
+  if (al && C == 768) layernorm_vec_kernel<6, MODE><<<grid, 256, 0, st>>>(x, p, w, b, o32, o16, rows, eps);
+  else if (al && C == 512) layernorm_vec_kernel<4, MODE><<<grid, 256, 0, st>>>(x, p, w, b, o32, o16, rows, eps);
+  else layernorm_kernel<32, MODE><<<grid, 256, 0, st>>>(x, p, w, b, o32, o16, rows, C, eps);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Positional grouped conv, CUDA-core fp32: pc[b,t,co] = bias[co] + sum_{j,ci} xpad[b, t+j-pad, g*CG+ci] * wk[g][j][ci][co']
 // Block = (t-tile of 32, group, clip); 192 threads = CG(48) outputs x 4 time sub-tiles of 8 (sliding register window).
@@ -444,11 +508,9 @@ extern "C" int avi_layernorm(const float* x, const float* res, const float* w, c
                              int64_t rows, int32_t C, float eps, void* stream) {
   AVI_REQUIRE(rows > 0 && C > 0 && C <= 1024, "avi_layernorm: bad shape rows=%lld C=%d", (long long)rows, C);
   if (res)
-    layernorm_kernel<32, 2><<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
-        x, res, w, b, out_f32, (__nv_bfloat16*)out_bf16, rows, C, eps);
+    launch_layernorm<2>(x, res, w, b, out_f32, (__nv_bfloat16*)out_bf16, rows, C, eps, (cudaStream_t)stream);
   else
-    layernorm_kernel<32, 0><<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
-        x, nullptr, w, b, out_f32, (__nv_bfloat16*)out_bf16, rows, C, eps);
+    launch_layernorm<0>(x, nullptr, w, b, out_f32, (__nv_bfloat16*)out_bf16, rows, C, eps, (cudaStream_t)stream);
   return check_launch("layernorm");
 }
 
@@ -479,8 +541,7 @@ extern "C" int avi_w2v_posconv_ln(const float* x, const float* w_packed, const f
 extern "C" int avi_w2v_posconv_merge_ln(const float* x, const float* pc, const float* ln_w, const float* ln_b, float* out_f32,
                                         void* out_bf16, int64_t rows, int32_t C, float eps, void* stream) {
   AVI_REQUIRE(rows > 0 && C > 0 && C <= 1024, "avi_w2v_posconv_merge_ln: bad shape");
-  layernorm_kernel<32, 1><<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x, pc, ln_w, ln_b, out_f32,
-                                                                                      (__nv_bfloat16*)out_bf16, rows, C, eps);
+  launch_layernorm<1>(x, pc, ln_w, ln_b, out_f32, (__nv_bfloat16*)out_bf16, rows, C, eps, (cudaStream_t)stream);
   return check_launch("posconv_merge_ln");
 }
 
