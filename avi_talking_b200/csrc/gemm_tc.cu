@@ -95,14 +95,20 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const int n_blk = t % p.n_tiles;
         const int mt = t / p.n_tiles;
         const int b = mt / p.m_tiles, m_blk = mt % p.m_tiles;
+        int kin = 0, ph = 0, sr = 0;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
           const uint32_t fb = smem_u32(&full_bar[stage]);
           mbar_expect_tx(fb, TC_STAGE_BYTES);
-          const int tap = kb / p.kb_per_tap, c0 = (kb % p.kb_per_tap) * TC_BK;
-          tma_load_4d(smem_u32(smem_a + stage * TC_A_BYTES), &map_a, fb, c0, tap % p.conv_stride,
-                      m_blk * TC_BM + tap / p.conv_stride, b);
+          tma_load_4d(smem_u32(smem_a + stage * TC_A_BYTES), &map_a, fb, kin * TC_BK, ph, m_blk * TC_BM + sr, b);
           tma_load_2d(smem_u32(smem_b + stage * TC_B_BYTES), &map_w, fb, kb * TC_BK, n_blk * TC_BN);
+          if (++kin == p.kb_per_tap) {
+            kin = 0;
+            if (++ph == p.conv_stride) {
+              ph = 0;
+              ++sr;
+            }
+          }
           if (++stage == TC_STAGES) {
             stage = 0;
             phase ^= 1;
@@ -322,9 +328,8 @@ static const char* tc_check(const AviGemmArgs* a) {
 
 using namespace avi;
 
-extern "C" int avi_gemm_bf16_tc_supported(const AviGemmArgs* a) { return tc_check(a) == nullptr ? 1 : 0; }
-
-extern "C" int avi_gemm_bf16_tc(const AviGemmArgs* a, void* stream) {
+// single-CTA variant (kept for A/B measurements against the CTA-pair kernel of gemm_tc2.cu: AVI_GEMM_V1=1)
+extern "C" int avi_gemm_bf16_tc_v1(const AviGemmArgs* a, void* stream) {
   const char* why = tc_check(a);
   AVI_REQUIRE(why == nullptr, "avi_gemm_bf16_tc: %s", why);
   const int cin = a->K / a->conv_taps;

@@ -1,0 +1,429 @@
+// bf16 tensor-core GEMM for sm_100a on CTA PAIRS: tcgen05.mma.cta_group::2 (M=256 across two SMs, N=256, K=16) with the
+// accumulator in TMEM, operands staged in shared memory by TMA (SWIZZLE_128B, K-major) through a 4-stage mbarrier ring, two
+// TMEM accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1, persistent over the 74 SM pairs.
+//
+//   C[b, r, n] = epi( sum_k A[b, r, k] * W[n, k] + bias[n] ) (+ residual[b, r, n])
+//
+// Why pairs: the single-CTA 128x256 tile needs 48 KB of operands per 4.2 MFLOP and was pinned at the L2->SM delivery rate
+// (~46 B/clk/SM measured, profiles/); in a pair each CTA stages its own 128 rows of A but only HALF of the W tile (128 of the
+// 256 rows), 32 KB per 4.2 MFLOP, and the MMA reads both halves.
+//
+// A is addressed through a 4-D tensor map (channel, phase, super-row, clip) so that a strided Conv1d over time-major
+// activations is the same code path as a plain GEMM: output row r, tap j reads input row r*stride + j = super-row
+// (r + j/stride), phase (j % stride).
+//
+// Warp roles (576 threads per CTA): warp 0 = TMA producer (both CTAs), warp 1 = TMEM allocator (both) + MMA issuer (leader
+// CTA only), warps 2..17 = epilogue (TMEM lane quarter = warp_id % 4, 64-column slice = (warp_id - 2) / 4).
+// Barriers: full[s] lives in the leader (both CTAs' TMA bytes land on it), empty[s] / tmem_full[a] are multicast to both CTAs
+// by tcgen05.commit, tmem_empty[a] lives in the leader and collects the epilogue warps of both CTAs.
+#include <cstdlib>
+
+#include "tc_common.cuh"
+
+namespace avi {
+
+constexpr int P2_BM = 128, P2_BN = 256, P2_BNH = 128, P2_BK = 64, P2_STAGES = 6, P2_UMMA_K = 16;
+constexpr int P2_EPI_WARPS = 16, P2_THREADS = (2 + P2_EPI_WARPS) * 32, P2_EPI_THREADS = P2_EPI_WARPS * 32;
+constexpr uint32_t P2_A_BYTES = P2_BM * P2_BK * 2;    // 16 KB
+constexpr uint32_t P2_B_BYTES = P2_BNH * P2_BK * 2;   // 16 KB
+constexpr uint32_t P2_STAGE_BYTES = P2_A_BYTES + P2_B_BYTES;
+// The operand ring is what hides the TMA round trip: with 4 stages both this kernel and its single-CTA predecessor sat at
+// ~980 clk per 64-deep k-block (MMA floor 512), i.e. latency-bound; the pair's smaller stages (32 KB instead of 48 KB) buy 6.
+constexpr uint32_t P2_TRANS_WARP = 32 * 16 * 4;                  // per-warp staging tile: 32 rows x 16 words (XOR-swizzled)
+constexpr uint32_t P2_TRANS_BYTES = P2_EPI_WARPS * P2_TRANS_WARP;
+constexpr uint32_t P2_BIAS_BYTES = 2 * P2_BN * 4;                // double-buffered by accumulator stage
+constexpr uint32_t P2_OFF_B = P2_STAGES * P2_A_BYTES;
+constexpr uint32_t P2_OFF_TRANS = P2_STAGES * P2_STAGE_BYTES;
+constexpr uint32_t P2_OFF_BIAS = P2_OFF_TRANS + P2_TRANS_BYTES;
+constexpr uint32_t P2_OFF_BAR = P2_OFF_BIAS + P2_BIAS_BYTES;
+constexpr uint32_t P2_SMEM_BYTES = P2_OFF_BAR + 256 /*barriers*/;
+static_assert(P2_SMEM_BYTES <= 232448, "shared memory budget");
+static_assert(2 * P2_STAGES + 5 <= 32, "barrier block");
+
+struct Tc2Params {
+  const float* bias;
+  const float* residual;
+  void* C;
+  void* C2;
+  int c_dtype;  // dtype of C; C2 (if any) is the other one
+  int act;
+  int batch, rows, N;
+  int num_kb;      // K / 64
+  int kb_per_tap;  // C_in / 64
+  int conv_stride;
+  int m_tiles, n_tiles, total_tiles;  // m_tiles counts 256-row pair tiles per batch entry
+  int64_t c_ld, c_batch_stride, res_ld, res_batch_stride;
+  int vec_ok;      // outputs (and residual) are 16-byte addressable per 32-column chunk
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P2_THREADS, 1)
+gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const Tc2Params p) {
+  extern __shared__ __align__(1024) uint8_t smem[];  // no static shared memory in this kernel: the dynamic window starts aligned
+  if ((smem_u32(smem) & 1023u) != 0) __trap();        // SWIZZLE_128B tiles need 1024-byte alignment
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + P2_OFF_B;
+  float* trans = reinterpret_cast<float*>(smem + P2_OFF_TRANS);
+  float* sbias = reinterpret_cast<float*>(smem + P2_OFF_BIAS);  // [2][BN]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P2_OFF_BAR);
+  uint64_t* full_bar = bars;                        // [STAGES]  (used in the leader CTA)
+  uint64_t* empty_bar = bars + P2_STAGES;           // [STAGES]
+  uint64_t* tmem_full = bars + 2 * P2_STAGES;       // [2]
+  uint64_t* tmem_empty = bars + 2 * P2_STAGES + 2;  // [2]       (used in the leader CTA)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * P2_STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    for (int s = 0; s < P2_STAGES; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&tmem_full[s]), 1);
+      mbar_init(smem_u32(&tmem_empty[s]), 2 * P2_EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // one warp per CTA: all 512 TMEM columns of both SMs (2 accumulator stages x 256)
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();  // barrier inits + TMEM allocation of BOTH CTAs visible before any cross-CTA traffic
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer (each CTA loads its 128 rows of A and its 128 rows of W) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t full_leader = mapa_shared(smem_u32(&full_bar[0]), 0);
+      for (int t = pair; t < p.total_tiles; t += num_pairs) {
+        const int n_blk = t % p.n_tiles;
+        const int mt = t / p.n_tiles;
+        const int b = mt / p.m_tiles, m_blk = mt % p.m_tiles;
+        const int row0 = m_blk * (2 * P2_BM) + (int)rank * P2_BM;
+        const int wrow0 = n_blk * P2_BN + (int)rank * P2_BNH;
+        // tap / phase / super-row / channel-block counters advance incrementally: this single thread paces the whole pipeline,
+        // and four runtime integer divisions per k-block cost about as much as the MMAs of that k-block
+        int kin = 0, ph = 0, sr = 0;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          const uint32_t fb_local = smem_u32(&full_bar[stage]);
+          if (rank == 0) mbar_expect_tx(fb_local, 2 * P2_STAGE_BYTES);
+          tma_load_4d_pair(smem_u32(smem_a + stage * P2_A_BYTES), &map_a, full_leader + stage * 8, kin * P2_BK, ph, row0 + sr, b);
+          tma_load_2d_pair(smem_u32(smem_b + stage * P2_B_BYTES), &map_w, full_leader + stage * 8, kb * P2_BK, wrow0);
+          if (++kin == p.kb_per_tap) {
+            kin = 0;
+            if (++ph == p.conv_stride) {
+              ph = 0;
+              ++sr;
+            }
+          }
+          if (++stage == P2_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA, one thread) =====================
+    if (rank == 0 && lane == 0) {
+      // instruction descriptor: D=f32, A=B=bf16, both K-major, N=256, M=256 (pair)
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P2_BN >> 3) << 17) | ((uint32_t)((2 * P2_BM) >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = pair; t < p.total_tiles; t += num_pairs, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(smem_u32(&tmem_empty[as]), aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * P2_BN;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          tc_fence_after();
+          const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + stage * P2_A_BYTES));
+          const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + stage * P2_B_BYTES));
+#pragma unroll
+          for (int k = 0; k < P2_BK / P2_UMMA_K; ++k)
+            umma_bf16_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_pair(smem_u32(&empty_bar[stage]), 3);  // frees the slot in BOTH CTAs once these MMAs have read it
+          if (++stage == P2_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_pair(smem_u32(&tmem_full[as]), 3);  // accumulator complete -> epilogues of both CTAs
+      }
+    }
+  } else {
+    // ===================== epilogue: TMEM -> registers -> smem transpose -> coalesced global =====================
+    // Phase A (thread = accumulator row): tcgen05.ld 32 columns, + bias, activation, written to a per-warp staging tile.
+    // Phase B (lanes span the columns of a few rows): 16-byte shared loads and fully coalesced 16-byte global accesses.
+    // Three variants: packed bf16 rows, fp32 rows (+ residual), and a scalar one for unaligned / ragged outputs (the
+    // 15069-wide vertex rows).  The XOR swizzles keep every shared access conflict-free.
+    const int ew = warp - 2;              // 0..15
+    const int quarter = warp & 3;         // TMEM lanes [32*quarter, +32) are the only ones this warp may touch
+    const int slice = ew >> 2;            // columns [64*slice, +64)
+    const int etid = threadIdx.x - 64;    // 0..511
+    const uint32_t tile = smem_u32(trans) + ew * P2_TRANS_WARP;
+    const bool fast_bf16 = p.vec_ok && p.c_dtype == AVI_DT_BF16 && p.C2 == nullptr && p.residual == nullptr;
+    const bool fast_f32 = p.vec_ok && p.c_dtype == AVI_DT_F32 && p.C2 == nullptr;
+    const uint32_t te_leader0 = mapa_shared(smem_u32(&tmem_empty[0]), 0);
+    const uint32_t te_leader1 = mapa_shared(smem_u32(&tmem_empty[1]), 0);
+    int it = 0;
+    for (int t = pair; t < p.total_tiles; t += num_pairs, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int n_blk = t % p.n_tiles;
+      const int mt = t / p.n_tiles;
+      const int b = mt / p.m_tiles, m_blk = mt % p.m_tiles;
+      const int n0 = n_blk * P2_BN;
+      const uint32_t sbias_a = smem_u32(sbias) + as * (P2_BN * 4);
+      if (etid < P2_BN) {
+        const int n = n0 + etid;
+        sts32(sbias_a + etid * 4, __float_as_uint((p.bias != nullptr && n < p.N) ? __ldg(p.bias + n) : 0.f));
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(P2_EPI_THREADS) : "memory");
+      mbar_wait(smem_u32(&tmem_full[as]), aphase);
+      tc_fence_after();
+      const int row_base = m_blk * (2 * P2_BM) + (int)rank * P2_BM + quarter * 32;
+      const int rows_valid = p.rows - row_base;  // may be <= 0 or > 32
+      const int64_t c_row0 = (int64_t)b * p.c_batch_stride + (int64_t)row_base * p.c_ld;
+      const int64_t r_row0 = (int64_t)b * p.res_batch_stride + (int64_t)row_base * p.res_ld;
+#pragma unroll 1
+      for (int ch = 0; ch < 2; ++ch) {
+        const int col0 = slice * 64 + ch * 32;
+        const int n_base = n0 + col0;
+        if (n_base >= p.N || rows_valid <= 0) break;  // warp-uniform
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * P2_BN + col0), v);
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 bb = lds128f(sbias_a + (col0 + 4 * j) * 4);
+          f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + bb.x;
+          f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bb.y;
+          f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bb.z;
+          f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bb.w;
+        }
+        if (p.act == AVI_ACT_GELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = gelu_fast(f[j]);
+        } else if (p.act == AVI_ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        const bool full_n = n_base + 32 <= p.N;
+        // staging tile: 32 rows x 16 words (pitch 16); the 4-word group g of row r lives at group g ^ ((r >> 1) & 3), which
+        // keeps the row-per-lane writes and the row-segment reads below conflict-free
+        const uint32_t wr_row = tile + lane * 64, wr_sw = (lane >> 1) & 3;
+        if (fast_bf16 && full_n) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint32_t w[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(f[8 * g + 2 * u], f[8 * g + 2 * u + 1]);
+              w[u] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+            sts128(wr_row + 16 * (g ^ wr_sw), w[0], w[1], w[2], w[3]);
+          }
+          __syncwarp();
+          __nv_bfloat16* cb = reinterpret_cast<__nv_bfloat16*>(p.C) + c_row0 + n_base;
+          const int g = lane & 3;
+#pragma unroll
+          for (int i8 = 0; i8 < 4; ++i8) {
+            const int r = i8 * 8 + (lane >> 2);
+            if (r < rows_valid) {
+              const uint4 q = lds128(tile + (r * 16 + 4 * (g ^ ((r >> 1) & 3))) * 4);
+              *reinterpret_cast<uint4*>(cb + (int64_t)r * p.c_ld + 8 * g) = q;
+            }
+          }
+          __syncwarp();
+        } else if (fast_f32 && full_n) {
+          float* cf = reinterpret_cast<float*>(p.C) + c_row0 + n_base;
+          const float* rp = p.residual ? p.residual + r_row0 + n_base : nullptr;
+          const int g = lane & 3;
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {  // two passes of 16 columns
+            float4 rr[4];
+#pragma unroll
+            for (int i8 = 0; i8 < 4; ++i8) {
+              const int r = i8 * 8 + (lane >> 2);
+              rr[i8] = (rp != nullptr && r < rows_valid)
+                           ? __ldg(reinterpret_cast<const float4*>(rp + (int64_t)r * p.res_ld + 16 * hh + 4 * g))
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int gg = 0; gg < 4; ++gg)
+              sts128(wr_row + 16 * (gg ^ wr_sw), __float_as_uint(f[16 * hh + 4 * gg]), __float_as_uint(f[16 * hh + 4 * gg + 1]),
+                     __float_as_uint(f[16 * hh + 4 * gg + 2]), __float_as_uint(f[16 * hh + 4 * gg + 3]));
+            __syncwarp();
+#pragma unroll
+            for (int i8 = 0; i8 < 4; ++i8) {
+              const int r = i8 * 8 + (lane >> 2);
+              if (r < rows_valid) {
+                float4 q = lds128f(tile + (r * 16 + 4 * (g ^ ((r >> 1) & 3))) * 4);
+                q.x += rr[i8].x;
+                q.y += rr[i8].y;
+                q.z += rr[i8].z;
+                q.w += rr[i8].w;
+                *reinterpret_cast<float4*>(cf + (int64_t)r * p.c_ld + 16 * hh + 4 * g) = q;
+              }
+            }
+            __syncwarp();
+          }
+        } else {
+          // generic (ragged / unaligned rows, second output copy): half a warp per row, 64-byte row segments, scalar accesses
+          float* cf = nullptr;
+          __nv_bfloat16* cb = nullptr;
+          if (p.c_dtype == AVI_DT_F32) {
+            cf = reinterpret_cast<float*>(p.C);
+            cb = reinterpret_cast<__nv_bfloat16*>(p.C2);
+          } else {
+            cb = reinterpret_cast<__nv_bfloat16*>(p.C);
+            cf = reinterpret_cast<float*>(p.C2);
+          }
+          const float* rp = p.residual;
+          const int c = lane & 15, rsub = lane >> 4;
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+            for (int gg = 0; gg < 4; ++gg)
+              sts128(wr_row + 16 * (gg ^ wr_sw), __float_as_uint(f[16 * hh + 4 * gg]), __float_as_uint(f[16 * hh + 4 * gg + 1]),
+                     __float_as_uint(f[16 * hh + 4 * gg + 2]), __float_as_uint(f[16 * hh + 4 * gg + 3]));
+            __syncwarp();
+            const int n = n_base + 16 * hh + c;
+            if (n < p.N) {
+#pragma unroll
+              for (int r8 = 0; r8 < 2; ++r8) {
+                float val[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                  const int r = 2 * (8 * r8 + u) + rsub;
+                  val[u] = __uint_as_float(lds32(tile + (r * 16 + 4 * ((c >> 2) ^ ((r >> 1) & 3)) + (c & 3)) * 4));
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                  const int r = 2 * (8 * r8 + u) + rsub;
+                  if (r < rows_valid) {
+                    const int64_t co = c_row0 + (int64_t)r * p.c_ld + n;
+                    float x = val[u];
+                    if (rp) x += __ldg(rp + r_row0 + (int64_t)r * p.res_ld + n);
+                    if (cf) cf[co] = x;
+                    if (cb) cb[co] = __float2bfloat16_rn(x);
+                  }
+                }
+              }
+            }
+            __syncwarp();
+          }
+        }
+      }
+      // release the accumulator stage back to the MMA warp of the leader CTA
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(as ? te_leader1 : te_leader0);
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // the peer's shared memory / TMEM / barriers stay valid until both CTAs are done
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+static const char* tc2_check(const AviGemmArgs* a) {
+  if (!a) return "null args";
+  if (a->a_dtype != AVI_DT_BF16) return "A/W must be bf16";
+  if (a->batch <= 0 || a->rows <= 0 || a->N <= 0 || a->K <= 0) return "bad shape";
+  if (a->conv_taps < 1 || a->conv_stride < 1) return "bad conv params";
+  if (a->K % a->conv_taps != 0) return "K must be taps * C_in";
+  const int cin = a->K / a->conv_taps;
+  if (cin % P2_BK != 0) return "C_in (K per tap) must be a multiple of 64";
+  if (a->a_ld < cin) return "a_ld smaller than the channel window";
+  if (a->a_ld % 8 != 0 || a->a_batch_stride % 8 != 0) return "a_ld and a_batch_stride must be multiples of 8 elements";
+  if (((uintptr_t)a->A | (uintptr_t)a->W) % 16 != 0) return "A and W must be 16-byte aligned";
+  if (a->a_rows_alloc < (int64_t)(a->rows - 1) * a->conv_stride + a->conv_taps) return "a_rows_alloc smaller than the rows read";
+  if (a->C == nullptr) return "C is null";
+  return nullptr;
+}
+
+}  // namespace avi
+
+using namespace avi;
+
+extern "C" int avi_gemm_bf16_tc_v1(const AviGemmArgs* a, void* stream);
+
+extern "C" int avi_gemm_bf16_tc_supported(const AviGemmArgs* a) { return tc2_check(a) == nullptr ? 1 : 0; }
+
+extern "C" int avi_gemm_bf16_tc(const AviGemmArgs* a, void* stream) {
+  static const bool use_v1 = getenv("AVI_GEMM_V1") != nullptr;
+  if (use_v1) return avi_gemm_bf16_tc_v1(a, stream);
+  const char* why = tc2_check(a);
+  AVI_REQUIRE(why == nullptr, "avi_gemm_bf16_tc: %s", why);
+  const int cin = a->K / a->conv_taps;
+  const int s = a->conv_stride;
+  CUtensorMap map_a, map_w;
+  {
+    // (channel, phase, super-row, clip)
+    const uint64_t q_rows = (uint64_t)(a->a_rows_alloc / s);
+    uint64_t dims[4] = {(uint64_t)cin, (uint64_t)s, q_rows, (uint64_t)a->batch};
+    uint64_t strides[3] = {(uint64_t)a->a_ld * 2, (uint64_t)a->a_ld * s * 2, (uint64_t)a->a_batch_stride * 2};
+    if (a->batch == 1) strides[2] = dims[2] * strides[1];  // unused; keep it well-formed
+    uint32_t box[4] = {P2_BK, 1, P2_BM, 1};
+    if (encode_map(&map_a, a->A, 4, dims, strides, box)) return 1;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->N};
+    uint64_t strides[1] = {(uint64_t)a->K * 2};
+    uint32_t box[2] = {P2_BK, P2_BNH};
+    if (encode_map(&map_w, a->W, 2, dims, strides, box)) return 1;
+  }
+  Tc2Params p;
+  p.bias = a->bias;
+  p.residual = a->residual;
+  p.C = a->C;
+  p.C2 = a->C2;
+  p.c_dtype = a->c_dtype;
+  p.act = a->act;
+  p.batch = a->batch;
+  p.rows = a->rows;
+  p.N = a->N;
+  p.num_kb = a->K / P2_BK;
+  p.kb_per_tap = cin / P2_BK;
+  p.conv_stride = s;
+  p.m_tiles = (a->rows + 2 * P2_BM - 1) / (2 * P2_BM);
+  p.n_tiles = (a->N + P2_BN - 1) / P2_BN;
+  p.total_tiles = p.m_tiles * p.n_tiles * a->batch;
+  p.c_ld = a->c_ld;
+  p.c_batch_stride = a->c_batch_stride;
+  p.res_ld = a->res_ld;
+  p.res_batch_stride = a->res_batch_stride;
+  // vector path: every 32-column chunk of every row is 16-byte addressable in both output dtypes and the residual
+  bool vec = (a->c_ld % 8 == 0) && (a->c_batch_stride % 8 == 0) && ((uintptr_t)a->C % 16 == 0) &&
+             (a->C2 == nullptr || (uintptr_t)a->C2 % 16 == 0);
+  if (a->residual) vec = vec && (a->res_ld % 4 == 0) && (a->res_batch_stride % 4 == 0) && ((uintptr_t)a->residual % 16 == 0);
+  p.vec_ok = vec ? 1 : 0;
+
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(gemm_bf16_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P2_SMEM_BYTES);
+  });
+  AVI_REQUIRE(attr_err == cudaSuccess, "avi_gemm_bf16_tc: cannot opt in to %u bytes of shared memory: %s", P2_SMEM_BYTES,
+              cudaGetErrorString(attr_err));
+  const int pairs = p.total_tiles < kNumSMs / 2 ? p.total_tiles : kNumSMs / 2;
+  gemm_bf16_tc2_kernel<<<2 * pairs, P2_THREADS, P2_SMEM_BYTES, (cudaStream_t)stream>>>(map_a, map_w, p);
+  return check_launch("gemm_bf16_tc");
+}

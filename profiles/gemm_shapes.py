@@ -28,16 +28,23 @@ def rnd(*shape, dtype=torch.bfloat16, scale=1.0):
 
 
 def timeit(fn):
+    """`reps` launches captured in one CUDA graph (no host launch gaps between them), graph replayed 3 times after a warm-up."""
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        for _ in range(reps):
+            fn()
+    graph.replay()
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(reps):
-        fn()
+    for _ in range(3):
+        graph.replay()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / reps
+    return e0.elapsed_time(e1) / (3 * reps)
 
 
 rows = []
