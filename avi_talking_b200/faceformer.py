@@ -200,7 +200,8 @@ class Faceformer(nn.Module):
         out = torch.empty((B, T, self.args.vertice_dim), dtype=torch.float32, device=hidden.device)
         if self.precision == "bf16" and fd % 64 == 0:
             a = ops.split_bf16x3(hidden.reshape(B * T, fd))
-            ops.gemm(a, P["vr_w16x3"], bias, out, rows=B * T, N=self.args.vertice_dim, K=3 * fd, a_rows_alloc=B * T)
+            ops.gemm(a, P["vr_w16x3"], bias, out, rows=B * T, N=self.args.vertice_dim, K=3 * fd, a_rows_alloc=B * T,
+                     algorithmic_flops=2.0 * B * T * self.args.vertice_dim * fd)
         else:
             ops.gemm(hidden.reshape(B * T, fd), P["vr_w32"], bias, out, rows=B * T, N=self.args.vertice_dim, K=fd)
         return out

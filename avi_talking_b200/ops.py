@@ -82,7 +82,8 @@ def split_bf16x3(x2d):
 
 
 def gemm(A, W, bias, out, *, rows, N, K, batch=1, act=ACT_NONE, residual=None, out2=None, conv_taps=1, conv_stride=1,
-         a_ld=None, a_batch_stride=0, a_rows_alloc=None, c_ld=None, c_batch_stride=0, res_ld=None, res_batch_stride=0):
+         a_ld=None, a_batch_stride=0, a_rows_alloc=None, c_ld=None, c_batch_stride=0, res_ld=None, res_batch_stride=0,
+         algorithmic_flops=None):
     """C[b,r,n] = act(sum_k A[b,r,k] W[n,k] + bias[n]) (+ residual). fp32 A/W -> CUDA-core kernel, bf16 -> tcgen05 kernel."""
     _need_cuda(A, W, bias, out, residual, out2)
     if A.dtype != W.dtype:
@@ -109,7 +110,8 @@ def gemm(A, W, bias, out, *, rows, N, K, batch=1, act=ACT_NONE, residual=None, o
     if out2 is not None and out2.dtype == out.dtype:
         raise TypeError("out2 must be the other dtype")
     lib = _lib.load()
-    flops = 2.0 * batch * rows * N * K
+    # bench.py's roofline counts ALGORITHMIC flops: callers that pad the contraction with structural zeros say so
+    flops = 2.0 * batch * rows * N * K if algorithmic_flops is None else float(algorithmic_flops)
     if A.dtype == torch.bfloat16:
         with _timed("gemm_bf16_tc", flops):
             _lib.check(lib.avi_gemm_bf16_tc(C.byref(args), _stream()), "avi_gemm_bf16_tc")

@@ -149,7 +149,8 @@ class Wav2Vec2Model(_HFWav2Vec2Model):
         for q, wq in enumerate(P["pos_w_bd"]):
             c0 = 192 * q
             ops.gemm(xpad[:, :, c0:], wq, P["pos_b"][c0:c0 + 192], pc[:, c0:], batch=B, rows=T, N=192, K=k * 192, conv_taps=k,
-                     conv_stride=1, a_ld=Cc, a_batch_stride=Tp * Cc, a_rows_alloc=Tp, c_ld=Cc, c_batch_stride=T * Cc)
+                     conv_stride=1, a_ld=Cc, a_batch_stride=Tp * Cc, a_rows_alloc=Tp, c_ld=Cc, c_batch_stride=T * Cc,
+                     algorithmic_flops=2.0 * B * T * 192 * k * (Cc // cfg.num_conv_pos_embedding_groups))
         return ops.posconv_merge_ln(proj, pc, P["enc_ln_w"], P["enc_ln_b"], want_bf16=True, eps=cfg.layer_norm_eps)
 
     def _encoder_layer(self, h32, h16, Lw, B, T):

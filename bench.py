@@ -168,9 +168,8 @@ def run_ours(args):
     from avi_talking_b200 import _lib, ops
     from avi_talking_b200.smoke import build_models
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    from avi_talking_b200 import shard
+    rank, local, world = shard.env_rank_world()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -261,10 +260,7 @@ def run_ours(args):
         d[2] += work
     step_ms_prof = sum(d[1] for d in agg.values())
 
-    if world > 1:
-        t = torch.tensor([dt_ms, e2e_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt_ms, e2e_ms = t.tolist()
+    dt_ms, e2e_ms = shard.max_over_ranks([dt_ms, e2e_ms], device=dev)   # identity at N=1
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
