@@ -37,6 +37,12 @@ class AviDecoderWeights(C.Structure):
         "ln1_w", "ln1_b", "ln2_w", "ln2_b", "ln3_w", "ln3_b", "fb_w", "fb_b", "pe")]
 
 
+class AviPriorNet(C.Structure):
+    _fields_ = [("layers", C.c_void_p), ("learned_query", C.c_void_p), ("rel_bias", C.c_void_p), ("rotary", C.c_void_p),
+                ("norm_g", C.c_void_p), ("project_out_t", C.c_void_p),
+                ("dim", C.c_int32), ("depth", C.c_int32), ("heads", C.c_int32), ("dim_head", C.c_int32), ("ff_inner", C.c_int32)]
+
+
 def declared_symbols() -> list[str]:
     """Every function name include/avi_b200.h declares."""
     with open(HEADER_PATH) as fh:

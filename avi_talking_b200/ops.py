@@ -7,7 +7,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, DT_BF16, DT_F32, AviDecoderWeights, AviGemmArgs  # noqa: F401
+from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, DT_BF16, DT_F32, AviDecoderWeights, AviGemmArgs, AviPriorNet  # noqa: F401
 
 
 # bench.py's roofline pass: when set to a list, every launch made through `_timed` appends
@@ -295,3 +295,48 @@ def flame_landmarks(verts, faces, idx, bary, per_frame: bool):
                                                C.c_int32(V), C.c_int32(L), C.c_int32(1 if per_frame else 0), _stream()),
                "avi_flame_landmarks")
     return out
+
+
+# ------------------------------------------------------------------------------------------------ diffusion prior
+def prior_layer_floats() -> int:
+    return int(_lib.load().avi_prior_layer_floats())
+
+
+def prior_time_embed(times, w0t, b0, w1t, b1, w2t, b2):
+    _need_cuda(times, w0t)
+    steps = times.numel()
+    temb = torch.empty((steps, 128), dtype=torch.float32, device=times.device)
+    with _timed("prior_time_embed", 0.0):
+        _lib.check(_lib.load().avi_prior_time_embed(_ptr(times), _ptr(w0t), _ptr(b0), _ptr(w1t), _ptr(b1), _ptr(w2t), _ptr(b2),
+                                                    _ptr(temb), C.c_int32(steps), _stream()), "avi_prior_time_embed")
+    return temb
+
+
+def prior_sample(net: AviPriorNet, temb, sched, text_embed, x_init, noise, out_scale, samples_per_cta=0):
+    """One launch = the whole DDPM/DDIM loop. text_embed/x_init [B,128], noise [steps,B,128], sched [steps,6] -> [B,128]."""
+    _need_cuda(temb, sched, text_embed, x_init, noise)
+    B, steps = text_embed.shape[0], sched.shape[0]
+    for t, shp in ((temb, (steps, 128)), (text_embed, (B, 128)), (x_init, (B, 128)), (noise, (steps, B, 128)), (sched, (steps, 6))):
+        if tuple(t.shape) != shp or t.dtype != torch.float32 or not t.is_contiguous():
+            raise ValueError(f"prior_sample: expected contiguous fp32 {shp}, got {tuple(t.shape)} {t.dtype}")
+    out = torch.empty((B, 128), dtype=torch.float32, device=text_embed.device)
+    # algorithmic work: 12.8 MFLOP per sample-step (SURVEY 8d)
+    with _timed("prior_sample", 12.8e6 * B * steps):
+        _lib.check(_lib.load().avi_prior_sample(C.byref(net), _ptr(temb), _ptr(sched), _ptr(text_embed), _ptr(x_init), _ptr(noise),
+                                                _ptr(out), C.c_int32(B), C.c_int32(steps), C.c_float(out_scale),
+                                                C.c_int32(samples_per_cta), _stream()), "avi_prior_sample")
+    return out
+
+
+def ln_gelu_res(x, w, b, res=None, want_bf16=False, eps=1e-5):
+    """GELU(LayerNorm(x)) (+ res) over the last dim (<= 4096)."""
+    _need_cuda(x, res)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    o32 = torch.empty_like(x)
+    o16 = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    with _timed("ln_gelu_res", float(x.numel() * 8)):
+        _lib.check(_lib.load().avi_ln_gelu_res(_ptr(x), _ptr(w), _ptr(b), _ptr(res), _ptr(o32), _ptr(o16), C.c_int64(rows),
+                                               C.c_int32(Cc), C.c_float(eps), _stream()), "avi_ln_gelu_res")
+    return o32, o16

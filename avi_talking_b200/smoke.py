@@ -28,6 +28,21 @@ def build_models(precision: str, fd: int = 64, device: str = "cuda", seed_ff: in
     return model.to(device).eval()
 
 
+def build_prior(precision: str = "fp32", samples_per_cta: int = 0, device: str = "cuda", seed: int = 30):
+    """Drop-in InstructDiffusionPrior (prior network + BrainNetwork) as constructed at train_diffusion_prior.py:961-991, loaded
+    with the seeded synthetic weights."""
+    from . import synth
+    from .diffusion_prior import BrainNetwork, InstructDiffusionPrior, VersatileDiffusionPriorNetwork
+    brain = BrainNetwork(in_dim=768, out_dim=128, clip_size=128, use_projector=True)
+    net = VersatileDiffusionPriorNetwork(dim=128, depth=6, dim_head=64, heads=8, causal=False, num_tokens=1, learned_query_mode="pos_emb")
+    prior = InstructDiffusionPrior(net=net, image_embed_dim=128, condition_on_text_encodings=False, timesteps=100, cond_drop_prob=0.2,
+                                   image_embed_scale=None, voxel2clip=brain)
+    prior.load_state_dict(synth.prior_state(seed), strict=False)
+    brain.precision = precision
+    prior.samples_per_cta = samples_per_cta
+    return prior.to(device).eval()
+
+
 def run_smoke(verbose: bool = False) -> dict:
     from oracle import faceformer_oracle as ffo   # checker only
     from oracle import flame_oracle as fo

@@ -245,3 +245,73 @@ def fan_embeddings(n_frames: int, seed: int = 20):
     rng = np.random.default_rng(seed)
     return dict(head=_t(np.zeros((n_frames, 6))), eye=_t(np.zeros((n_frames, 6))),
                 emo=_t(rng.normal(size=(n_frames, 30))))
+
+
+# --------------------------------------------------------------------------- diffusion prior (text -> style) weights
+def prior_state(seed: int = 30, dim: int = 128, depth: int = 6, heads: int = 8, dim_head: int = 64, ff_mult: int = 4,
+                brain_in: int = 768, brain_h: int = 4096, brain_blocks: int = 4, with_brain: bool = True) -> dict:
+    """State dict with the key names InstructDiffusionPrior(net=VersatileDiffusionPriorNetwork(...), voxel2clip=BrainNetwork(...))
+    registers (models/diffusion_prior.py:58-117,119-313; construction train_diffusion_prior.py:963-991):
+    ``net.*`` (dalle2_pytorch Attention / FeedForward / RelPosBias / LayerNorm / MLP parameter names) and ``voxel2clip.*``."""
+    rng = np.random.default_rng(seed)
+    sd = {}
+
+    def w(name, out_f, in_f, gain=1.0):
+        sd[name] = _t(rng.normal(0, gain / math.sqrt(in_f), size=(out_f, in_f)))
+
+    def g(name, c):
+        sd[name] = _t(1.0 + 0.1 * rng.normal(size=(c,)))
+
+    inner = dim_head * heads
+    ff_inner = ff_mult * dim
+    t = "net.to_time_embeds.0.1.net."
+    w(t + "0.0.weight", 2 * dim, dim); sd[t + "0.0.bias"] = _t(rng.normal(0, 0.02, size=(2 * dim,)))
+    w(t + "1.0.weight", 2 * dim, 2 * dim); sd[t + "1.0.bias"] = _t(rng.normal(0, 0.02, size=(2 * dim,)))
+    w(t + "2.weight", dim, 2 * dim); sd[t + "2.bias"] = _t(rng.normal(0, 0.02, size=(dim,)))
+    sd["net.learned_query"] = _t(rng.normal(size=(1, dim)) * dim ** -0.5)
+    sd["net.null_brain_embeds"] = _t(rng.normal(size=(1, dim)))
+    sd["net.null_image_embed"] = _t(rng.normal(size=(1, dim)))
+    c = "net.causal_transformer."
+    sd[c + "rel_pos_bias.relative_attention_bias.weight"] = _t(rng.normal(size=(32, heads)))
+    freqs = 1.0 / (10000.0 ** (np.arange(0, 32, 2)[:16].astype(np.float32) / 32.0))
+    for l in range(depth):
+        a = c + f"layers.{l}.0."
+        g(a + "norm.g", dim)
+        sd[a + "null_kv"] = _t(rng.normal(size=(2, dim_head)))
+        w(a + "to_q.weight", inner, dim)
+        w(a + "to_kv.weight", 2 * dim_head, dim)
+        w(a + "to_out.0.weight", dim, inner)
+        g(a + "to_out.1.g", dim)
+        sd[a + "rotary_emb.freqs"] = _t(freqs)
+        f = c + f"layers.{l}.1."
+        g(f + "0.g", dim)
+        w(f + "1.weight", 2 * ff_inner, dim)
+        w(f + "5.weight", dim, ff_inner)
+    g(c + "norm.g", dim)
+    w(c + "project_out.weight", dim, dim)
+    if with_brain:
+        b = "voxel2clip."
+
+        def lin(name, out_f, in_f):
+            w(name + ".weight", out_f, in_f)
+            sd[name + ".bias"] = _t(rng.normal(0, 0.02, size=(out_f,)))
+
+        def ln(name, cdim):
+            sd[name + ".weight"] = _t(1.0 + 0.1 * rng.normal(size=(cdim,)))
+            sd[name + ".bias"] = _t(0.05 * rng.normal(size=(cdim,)))
+
+        lin(b + "lin0.0", brain_h, brain_in); ln(b + "lin0.1", brain_h)
+        for i in range(brain_blocks):
+            lin(b + f"mlp.{i}.0", brain_h, brain_h); ln(b + f"mlp.{i}.1", brain_h)
+        lin(b + "lin1", dim, brain_h)
+        ln(b + "projector.0", dim); lin(b + "projector.2", 2048, dim)
+        ln(b + "projector.3", 2048); lin(b + "projector.5", 2048, 2048)
+        ln(b + "projector.6", 2048); lin(b + "projector.8", dim, 2048)
+    return sd
+
+
+def prior_inputs(batch: int, steps: int, seed: int = 7, dim: int = 128) -> dict:
+    """voxel [B,768] (stand-in for mean-pooled CLIP-L token embeddings), initial image_embed [B,1,128], per-step noise."""
+    rng = np.random.default_rng(seed)
+    return dict(voxel=_t(rng.normal(size=(batch, 768))), image_embed=_t(rng.normal(size=(batch, 1, dim))),
+                noises=_t(rng.normal(size=(steps, batch, 1, dim))))

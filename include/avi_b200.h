@@ -180,6 +180,44 @@ int avi_flame_blend_skin_tc(const float* coef32, const float* A, const void* dir
 int avi_flame_landmarks(const float* verts, const int64_t* faces, const int64_t* idx, const float* bary, float* out,
                         int32_t F, int32_t V, int32_t L, int32_t per_frame, void* stream);
 
+/* ------------------------------------------------------------------ diffusion prior (text embedding -> style embedding) ------------------------------------------------------------------ */
+/* Weights of VersatileDiffusionPriorNetwork as built at train_diffusion_prior.py:963-991 (dim 128, depth <= 8, 8 heads x 64, one
+ * shared K/V head, SwiGLU inner 512), packed once at weight-load time. All fp32 device pointers.
+ *   layers: [depth][avi_prior_layer_floats()] = per layer, in this order, every matrix TRANSPOSED to [in][out]:
+ *     attn norm.g [128] | null_k [64] | null_v [64] | to_q^T [128][512] | to_kv^T [128][128] | to_out.0^T [512][128] | to_out.1.g [128]
+ *     | ff 0.g [128] | ff 1^T [128][1024] | ff 5^T [512][128]
+ *   rel_bias: RelPosBias(n = 3, n + 1 = 4) -> [heads][3][4]; rotary: cos/sin of position * freq, [3][16][2]  */
+typedef struct AviPriorNet {
+  const float* layers;
+  const float* learned_query;   /* [128] (learned_query_mode = "pos_emb")                 */
+  const float* rel_bias;
+  const float* rotary;
+  const float* norm_g;          /* causal_transformer.norm.g (stable LayerNorm)           */
+  const float* project_out_t;   /* causal_transformer.project_out.weight^T [128][128]     */
+  int32_t dim, depth, heads, dim_head, ff_inner;
+} AviPriorNet;
+int avi_prior_layer_floats(void);
+
+/* time-token embeddings for all steps: SinusoidalPosEmb(128) -> MLP(128->256->256->128, SiLU) (models/diffusion_prior.py:186-189);
+ * times [steps] fp32 (the timestep value of each step), weights transposed [in][out]; temb out [steps][128] */
+int avi_prior_time_embed(const float* times, const float* w0t, const float* b0, const float* w1t, const float* b1, const float* w2t,
+                         const float* b2, float* temb, int32_t steps, void* stream);
+
+/* The whole sampling loop of InstructDiffusionPrior.p_sample_loop (models/diffusion_prior.py:329-367 DDPM branch; dalle2_pytorch
+ * DiffusionPrior.p_sample_loop_ddim for fewer steps) in ONE launch, cond_scale == 1:
+ *   text_embed [B][128], x_init [B][128] (initial noise), noise [steps][B][128] (the draw of every step, caller-supplied so the
+ *   reference's generator stream can be reproduced), sched [steps][6] = {mode, p0..p4}:
+ *     mode 0 (DDPM)  x = (p0*x0 + p1*x) + p2*noise         p0,p1 = posterior_mean_coef1/2[t], p2 = [t>0]*exp(0.5*logvar[t])
+ *     mode 1 (DDIM)  e = (p0*x - x0)/p1 ; x = x0*p2 + p3*noise + p4*e
+ *     mode 2         x = x0                               (last DDIM pair)
+ *   out [B][128] = final x * out_scale (1 / image_embed_scale). samples_per_cta: 1, 2, 4 or 0 = choose. */
+int avi_prior_sample(const AviPriorNet* net, const float* temb, const float* sched, const float* text_embed, const float* x_init,
+                     const float* noise, float* out, int32_t B, int32_t steps, float out_scale, int32_t samples_per_cta, void* stream);
+
+/* y = GELU(LayerNorm(x)) (+ res), rows of C <= 4096: BrainNetwork blocks and projector (models/diffusion_prior.py:63-93,104-110) */
+int avi_ln_gelu_res(const float* x, const float* w, const float* b, const float* res, float* out_f32, void* out_bf16, int64_t rows,
+                    int32_t C, float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

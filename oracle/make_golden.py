@@ -212,6 +212,93 @@ def golden_faceformer():
     print("faceformer.npz", {k: v.shape for k, v in out.items()})
 
 
+class _TorchProxy:
+    """`torch` as seen by the reference's class bodies, with randn / randn_like replaced by a queue of injected draws
+    (the reference draws its sampling noise from a CUDA torch.Generator, train_diffusion_prior.py:803-804)."""
+
+    def __init__(self, queue):
+        self._q = queue
+
+    def __getattr__(self, name):
+        return getattr(torch, name)
+
+    def randn(self, *a, **k):   # constructor-time parameter inits run with an empty queue -> real torch.randn
+        return self._q.pop(0) if self._q else torch.randn(*a, **{kk: v for kk, v in k.items() if kk != "generator"})
+
+    def randn_like(self, x):
+        return self._q.pop(0) if self._q else torch.randn_like(x)
+
+
+def _exec_reference_prior_classes(queue):
+    """Execute the reference's OWN class sources from models/diffusion_prior.py (BrainNetwork :58-117, FlaggedCausalTransformer
+    :119-166, VersatileDiffusionPriorNetwork :169-313, InstructDiffusionPrior :315-456) in a namespace where the un-vendored
+    dalle2_pytorch / rotary_embedding_torch names resolve to oracle/dalle2_standin.py. The file itself cannot be imported
+    (clip, dalle2_pytorch, torchvision transforms of PIL...)."""
+    import ast
+    from functools import partial
+
+    from tqdm.auto import tqdm
+
+    from . import dalle2_standin as d2
+    path = os.path.join(REF, "models", "diffusion_prior.py")
+    with open(path) as fh:
+        src = fh.read()
+    tree = ast.parse(src)
+    want = ("BrainNetwork", "FlaggedCausalTransformer", "VersatileDiffusionPriorNetwork", "InstructDiffusionPrior")
+    ns = {k: getattr(d2, k) for k in ("DiffusionPrior", "l2norm", "default", "exists", "RotaryEmbedding", "CausalTransformer",
+                                      "SinusoidalPosEmb", "MLP", "Rearrange", "repeat", "rearrange", "prob_mask_like", "LayerNorm",
+                                      "RelPosBias", "Attention", "FeedForward")}
+    ns.update(torch=_TorchProxy(queue), nn=nn, partial=partial, tqdm=tqdm, random=__import__("random"))
+    for node in tree.body:
+        if isinstance(node, ast.ClassDef) and node.name in want:
+            exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
+    return ns
+
+
+def golden_prior():
+    from . import prior_oracle as po
+    from . import synth
+    sd = synth.prior_state()
+    queue = []
+    ns = _exec_reference_prior_classes(queue)
+    out = {}
+    with torch.no_grad():
+        # BrainNetwork: fully the reference's own code (plain torch)
+        brain = ns["BrainNetwork"](in_dim=768, out_dim=128, clip_size=128, use_projector=True).eval()
+        brain.load_state_dict({k[len("voxel2clip."):]: v for k, v in sd.items() if k.startswith("voxel2clip.")}, strict=True)
+        inp = synth.prior_inputs(4, 100)
+        x, proj = brain(inp["voxel"])
+        out["brain_x"], out["brain_proj"] = x.numpy(), proj.numpy()
+        # prior network + sampler as constructed at train_diffusion_prior.py:972-991
+        net = ns["VersatileDiffusionPriorNetwork"](dim=128, depth=6, dim_head=64, heads=8, causal=False, num_tokens=1,
+                                                   learned_query_mode="pos_emb")
+        prior = ns["InstructDiffusionPrior"](net=net, image_embed_dim=128, condition_on_text_encodings=False, timesteps=100,
+                                             cond_drop_prob=0.2, image_embed_scale=None, voxel2clip=brain).eval()
+        own = {k: v for k, v in prior.state_dict().items() if not k.startswith("noise_scheduler.")}
+        assert set(own) == set(sd), sorted(set(own) ^ set(sd))
+        prior.load_state_dict(sd, strict=False)
+        out["state_keys"] = np.array(sorted(own))
+        text = x.view(4, -1, 128)
+        t = torch.full((4,), 37, dtype=torch.long)
+        out["net_t37"] = net(inp["image_embed"], t, text_embed=text).numpy()
+        # DDPM-100: the reference's p_sample_loop_ddpm / p_sample with injected draws (noises[i] = draw of step i)
+        queue.extend([inp["noises"][i] for i in reversed(range(100))])
+        gen = object()  # any non-None value selects the generator branch of p_sample (:333-337); the proxy ignores it
+        y = prior.p_sample_loop(text.shape, text_cond=dict(text_embed=text), cond_scale=1.0, timesteps=100, generator=gen,
+                                image_embed=inp["image_embed"])
+        assert not queue
+        out["ddpm100"] = y.numpy()
+        # DDIM-64: base-class sampler (stand-in) around the reference's network
+        pairs = po.ddim_time_pairs(100, 64)
+        y = prior.p_sample_loop(text.shape, text_cond=dict(text_embed=text), cond_scale=1.0, timesteps=64,
+                                image_embed=inp["image_embed"], noises=[inp["noises"][k] for k in range(len(pairs))])
+        out["ddim64"] = y.numpy()
+        for name in ("betas", "alphas_cumprod_prev", "posterior_mean_coef1", "posterior_mean_coef2", "posterior_log_variance_clipped"):
+            out["sched_" + name] = getattr(prior.noise_scheduler, name).numpy()
+    np.savez(os.path.join(GOLD, "prior.npz"), **out)
+    print("prior.npz", {k: v.shape for k, v in out.items()})
+
+
 def main():
     _paths()
     os.makedirs(GOLD, exist_ok=True)
@@ -219,6 +306,7 @@ def main():
     golden_flame()
     golden_wav2vec2()
     golden_faceformer()
+    golden_prior()
 
 
 if __name__ == "__main__":

@@ -1,0 +1,79 @@
+"""GPU: diffusion-prior drop-in (BrainNetwork GEMMs + the one-launch DDPM/DDIM sampler) against the oracle and the golden vectors."""
+import numpy as np
+import pytest
+import torch
+
+from avi_talking_b200 import synth
+from oracle import prior_oracle as po
+
+pytestmark = pytest.mark.gpu
+
+
+from avi_talking_b200.smoke import build_prior  # noqa: E402
+
+
+def test_brain_network_fp32_and_bf16(golden):
+    g = golden("prior")
+    inp = synth.prior_inputs(4, 100)
+    for prec, tol in (("fp32", 2e-5), ("bf16", 2e-2)):
+        prior = build_prior(prec)
+        x, proj = prior.voxel2clip(inp["voxel"].cuda())
+        ex = np.abs(x.cpu().numpy() - g["brain_x"]).max() / np.abs(g["brain_x"]).max()
+        ep = np.abs(proj.cpu().numpy() - g["brain_proj"]).max() / np.abs(g["brain_proj"]).max()
+        print(f"BrainNetwork {prec}: relative error x {ex:.3e} projector {ep:.3e}")
+        assert ex < tol and ep < tol
+
+
+def test_prior_network_single_pass(golden):
+    g = golden("prior")
+    inp = synth.prior_inputs(4, 100)
+    prior = build_prior()
+    text = torch.from_numpy(g["brain_x"]).view(4, -1, 128).cuda()
+    o = prior.net(inp["image_embed"].cuda(), torch.full((4,), 37, device="cuda"), text_embed=text)
+    err = np.abs(o.cpu().numpy() - g["net_t37"]).max()
+    print("prior net single pass max abs error", err)
+    assert err < 2e-5
+
+
+@pytest.mark.parametrize("timesteps,key", [(100, "ddpm100"), (64, "ddim64")])
+@pytest.mark.parametrize("spc", [1, 2, 4])
+def test_sampling_loop_matches_reference_golden(golden, timesteps, key, spc):
+    g = golden("prior")
+    inp = synth.prior_inputs(4, 100)
+    prior = build_prior(samples_per_cta=spc)
+    text = torch.from_numpy(g["brain_x"]).view(4, -1, 128).cuda()
+    steps = 100 if timesteps == 100 else 63
+    # noise[k] = draw of the k-th executed step: DDPM runs t = 99..0 and the oracle indexes its draws by t
+    noise = inp["noises"].flip(0) if timesteps == 100 else inp["noises"][:steps]
+    y = prior.p_sample_loop(text.shape, text_cond=dict(text_embed=text), cond_scale=1.0, timesteps=timesteps,
+                            image_embed=inp["image_embed"].cuda(), noise=noise.cuda())
+    err = np.abs(y.cpu().numpy() - g[key]).max()
+    print(f"{key} samples/CTA {spc}: max abs error {err:.3e} (|y| max {np.abs(g[key]).max():.3f})")
+    assert err < 2e-5   # fp32 mode tolerance: <= 1e-5 relative on O(1) embeddings, accumulated over the loop
+
+
+def test_ragged_batch_and_voxel2style_emb():
+    from avi_talking_b200.diffusion_prior import voxel2style_emb
+    B = 11                                   # not a multiple of 4: the last CTA is partly empty
+    sd, inp = synth.prior_state(), synth.prior_inputs(B, 100, seed=9)
+    prior = build_prior("fp32")
+    want = po.voxel2style_emb(sd, inp["voxel"], inp["image_embed"], inp["noises"], timesteps_prior=100)
+    got = voxel2style_emb(inp["voxel"].cuda(), prior, timesteps_prior=100, image_embed=inp["image_embed"].cuda(),
+                          noise=inp["noises"].flip(0).cuda())
+    err = (got.cpu() - want).abs().max().item()
+    print("voxel2style_emb DDPM-100 B=11 max abs error", err)
+    assert got.shape == (B, 1, 128) and err < 5e-5
+    nd = voxel2style_emb(inp["voxel"].cuda(), prior, no_diffusion=True)
+    want_nd = po.voxel2style_emb(sd, inp["voxel"], None, None, no_diffusion=True)
+    assert (nd.cpu() - want_nd).abs().max().item() < 1e-4
+
+
+def test_generator_stream_is_reproducible():
+    prior = build_prior()
+    text = torch.randn(6, 1, 128, device="cuda")
+    outs = []
+    for _ in range(2):
+        gen = torch.Generator(device="cuda")
+        gen.manual_seed(0)
+        outs.append(prior.p_sample_loop(text.shape, text_cond=dict(text_embed=text), timesteps=100, generator=gen))
+    assert torch.equal(outs[0], outs[1]) and torch.isfinite(outs[0]).all()
