@@ -315,3 +315,76 @@ def prior_inputs(batch: int, steps: int, seed: int = 7, dim: int = 128) -> dict:
     rng = np.random.default_rng(seed)
     return dict(voxel=_t(rng.normal(size=(batch, 768))), image_embed=_t(rng.normal(size=(batch, 1, dim))),
                 noises=_t(rng.normal(size=(steps, batch, 1, dim))))
+
+
+# --------------------------------------------------------------------------- EMOTE (Path B) decoder weights and sample dict
+EMOTE = SimpleNamespace(feature_dim=128, nhead=8, bottleneck=256, latent_frame=8, quant_factor=3, l2l_ff=384, n_out=53,
+                        n_expression=8, n_intensities=3, n_identities=32, n_shape=300, n_exp=50)
+
+
+def emote_state(seed: int = 40) -> dict:
+    """Weights of the EMOTE talking-head model below wav2vec2, with the parameter names the reference's module tree registers
+    (TalkingHeadBase: sequence_encoder / sequence_decoder; BertPriorDecoder FaceFormerDecoder.py:987-1075; L2lDecoder
+    L2lMotionPrior.py:361-455). The reference zero-initialises ``decoder`` (:1050-1051); it is re-randomised here."""
+    rng = np.random.default_rng(seed)
+    E = EMOTE
+    sd = {}
+
+    def lin(name, out_f, in_f, gain=0.7):
+        sd[name + ".weight"] = _t(rng.normal(0, gain / math.sqrt(in_f), size=(out_f, in_f)))
+        sd[name + ".bias"] = _t(rng.normal(0, 0.02, size=(out_f,)))
+
+    def ln(name, c):
+        sd[name + ".weight"] = _t(1.0 + 0.1 * rng.normal(size=(c,)))
+        sd[name + ".bias"] = _t(0.05 * rng.normal(size=(c,)))
+
+    def enc_layer(p, d, ff):
+        sd[p + "self_attn.in_proj_weight"] = _t(rng.normal(0, 1.0 / math.sqrt(d), size=(3 * d, d)))
+        sd[p + "self_attn.in_proj_bias"] = _t(rng.normal(0, 0.02, size=(3 * d,)))
+        lin(p + "self_attn.out_proj", d, d)
+        lin(p + "linear1", ff, d)
+        lin(p + "linear2", d, ff)
+        ln(p + "norm1", d)
+        ln(p + "norm2", d)
+
+    lin("sequence_encoder.linear", E.feature_dim, 768)
+    cond = E.n_expression + E.n_intensities + E.n_identities
+    lin("sequence_decoder.obj_vector.map", E.feature_dim, cond, gain=1.0)
+    enc_layer("sequence_decoder.bert_decoder.layers.0.", E.feature_dim, E.feature_dim)
+    lin("sequence_decoder.decoder", E.bottleneck, E.feature_dim)
+    lin("sequence_decoder.squasher_2.linear", E.bottleneck, E.bottleneck * E.latent_frame)
+    m = "sequence_decoder.motion_prior.motion_decoder."
+    for i in range(E.quant_factor):
+        shape = (E.bottleneck, E.bottleneck, 5)   # ConvTranspose1d weight is [in, out, k]; Conv1d [out, in, k] - both square here
+        sd[m + f"expander.{i}.0.weight"] = _t(rng.normal(0, 1.0 / math.sqrt(E.bottleneck * (2.5 if i == 0 else 5)), size=shape))
+        sd[m + f"expander.{i}.0.bias"] = _t(rng.normal(0, 0.02, size=(E.bottleneck,)))
+        sd[m + f"expander.{i}.2.weight"] = _t(1.0 + 0.1 * rng.normal(size=(E.bottleneck,)))
+        sd[m + f"expander.{i}.2.bias"] = _t(0.05 * rng.normal(size=(E.bottleneck,)))
+        sd[m + f"expander.{i}.2.running_mean"] = _t(0.1 * rng.normal(size=(E.bottleneck,)))
+        sd[m + f"expander.{i}.2.running_var"] = _t(0.5 + rng.uniform(size=(E.bottleneck,)))
+        sd[m + f"expander.{i}.2.num_batches_tracked"] = torch.tensor(100, dtype=torch.long)
+    lin(m + "decoder_linear_embedding", E.bottleneck, E.bottleneck)
+    enc_layer(m + "decoder_transformer.layers.0.", E.bottleneck, E.l2l_ff)
+    sd[m + "cross_smooth_layer.weight"] = _t(rng.normal(0, 0.25 / math.sqrt(E.bottleneck * 5), size=(E.n_out, E.bottleneck, 5)))
+    sd[m + "cross_smooth_layer.bias"] = _t(rng.normal(0, 0.02, size=(E.n_out,)))
+    return sd
+
+
+def emote_sample(batch: int, n_frames: int, seed: int = 50) -> dict:
+    """The sample dict TalkingHeadWrapper.forward consumes (evaluation_functions.py:141-161,218-275): raw_audio [B,T,640] (int16 view
+    of the waveform as float), samplerate, gt_shape [B,300], gt_exp [B,T,50], gt_jaw [B,T,3], and the three per-frame condition
+    one-hots (expression / intensity / identity)."""
+    rng = np.random.default_rng(seed)
+    E = EMOTE
+    wav = audio(batch, n_frames * 640, seed=seed + 1)
+    raw = torch.round(wav * 3000.0).clamp(-32767, 32767).reshape(batch, n_frames, 640)
+
+    def one_hot(n):
+        idx = rng.integers(0, n, size=(batch,))
+        return torch.nn.functional.one_hot(torch.from_numpy(idx), n).float()[:, None, :].expand(batch, n_frames, n).contiguous()
+
+    return dict(raw_audio=raw, samplerate=[16000] * batch,
+                gt_shape=_t(rng.normal(size=(batch, E.n_shape))), gt_exp=_t(rng.normal(size=(batch, n_frames, E.n_exp))),
+                gt_jaw=_t(0.1 * rng.normal(size=(batch, n_frames, 3))),
+                gt_expression_label_condition=one_hot(E.n_expression), gt_expression_intensity_condition=one_hot(E.n_intensities),
+                gt_expression_identity_condition=one_hot(E.n_identities))

@@ -299,6 +299,121 @@ def golden_prior():
     print("prior.npz", {k: v.shape for k, v in out.items()})
 
 
+
+def build_reference_talking_head(sd, sd_w2v):
+    """The reference's EMOTE inference graph assembled from its OWN classes (stub-imported, oracle/_inferno_import.py):
+    TalkingHeadBase.forward over Wav2Vec2Encoder/Wav2Vec2ModelResampled, LinearSequenceEncoder, BertPriorDecoder (+ real
+    LinearEmotionCondition, StackLinearSquash), MotionPrior.decoding_step over the real L2lDecoder and FlamePreprocessor/FLAME.
+    Constructors that need checkpoints / cfg.yaml / the network are bypassed with __new__ and the attributes they would set."""
+    from collections import OrderedDict
+
+    from transformers import Wav2Vec2Config, Wav2Vec2FeatureExtractor
+
+    from . import _inferno_import as ii
+    from . import synth
+    Munch = ii.Munch
+    (ffdec, l2l, mp, pre, seqenc, audenc, thb) = ii.load(
+        "inferno.models.talkinghead.FaceFormerDecoder", "inferno.models.temporal.motion_prior.L2lMotionPrior",
+        "inferno.models.temporal.motion_prior.MotionPrior", "inferno.models.temporal.Preprocessors",
+        "inferno.models.temporal.SequenceEncoders", "inferno.models.temporal.AudioEncoders", "inferno.models.talkinghead.TalkingHeadBase")
+    from inferno.models.DecaFLAME import FLAME
+    E = synth.EMOTE
+    fcfg = synth.write_flame_assets("/tmp/avi_flame_assets")
+    fcfg.n_shape, fcfg.n_exp = E.n_shape, E.n_exp
+    flame = FLAME(fcfg)
+    # FlamePreprocessor (Preprocessors.py:27-60)
+    prep = pre.FlamePreprocessor.__new__(pre.FlamePreprocessor)      # a plain object, not an nn.Module (Bases.py:168)
+    prep.cfg = Munch(flame=Munch(n_exp=E.n_exp, n_shape=E.n_shape), use_texture=False, test_time=True)
+    prep.flame, prep.flame_tex = flame, None
+    # L2lDecoder: real constructor (motion_prior_conf l2l_decoder.yaml / l2l_sizes.yaml)
+    dcfg = Munch(feature_dim=E.bottleneck, nhead=8, intermediate_size=E.l2l_ff, activation="gelu", dropout=0.0, num_layers=1,
+                 positional_encoding=Munch(type="none"), temporal_bias=Munch(type="alibi_future", max_len=600))
+    l2l_dec = l2l.L2lDecoder(dcfg, Munch(quant_factor=E.quant_factor, sequence_length=32), E.n_out)
+    mprior = mp.MotionPrior.__new__(mp.MotionPrior)
+    nn.Module.__init__(mprior)
+    mprior.cfg = Munch(model=Munch(sequence_components=OrderedDict([("exp", 50), ("jaw", "rot")]), rotation_representation="aa",
+                                   sizes=Munch(quant_factor=E.quant_factor)))
+    mprior.motion_encoder, mprior.motion_quantizer, mprior.motion_decoder = None, None, l2l_dec
+    mprior.preprocessor = mprior.postprocessor = prep
+    # BertPriorDecoder (FaceFormerDecoder.py:987-1075, bertprior_wild.yaml)
+    scfg = Munch(use_video_expression=False, use_video_feature=False, gt_expression_label=True, gt_expression_intensity=True,
+                 n_intensities=E.n_intensities, gt_expression_identity=True, n_identities=E.n_identities, use_expression=False,
+                 n_expression=E.n_expression, use_valence=False, use_arousal=False, use_emotion_feature=False, use_shape=False, use_bias=True)
+    dec = ffdec.BertPriorDecoder.__new__(ffdec.BertPriorDecoder)
+    nn.Module.__init__(dec)
+    dec.cfg = Munch(feature_dim=E.feature_dim, nhead=8, num_layers=1, post_bug_fix=True, motion_prior=Munch(trainable=False))
+    dec.style_type, dec.style_op, dec.PE = "emotion_linear", "add", None
+    dec.obj_vector = ffdec.LinearEmotionCondition(scfg, E.feature_dim)
+    layer = nn.TransformerEncoderLayer(d_model=E.feature_dim, nhead=8, dim_feedforward=E.feature_dim, activation="gelu", dropout=0.25,
+                                       batch_first=True)
+    dec.bert_decoder = nn.TransformerEncoder(layer, num_layers=1, enable_nested_tensor=False)
+    dec.post_bug_fix, dec.temporal_bias_type, dec.biased_mask = True, "none", None
+    dec.motion_prior, dec.latent_frame_size, dec.flame = mprior, E.latent_frame, flame
+    dec.squasher = None
+    dec.decoder = nn.Linear(E.feature_dim, E.bottleneck)
+    dec.squasher_2 = ffdec.StackLinearSquash(E.bottleneck, E.latent_frame, E.bottleneck)
+    # audio model (AudioEncoders.py:130-166) - real Wav2Vec2ModelResampled, real HF feature extractor as the processor
+    aud = audenc.Wav2Vec2Encoder.__new__(audenc.Wav2Vec2Encoder)
+    nn.Module.__init__(aud)
+    aud.input_processor = Wav2Vec2FeatureExtractor(feature_size=1, sampling_rate=16000, padding_value=0.0, do_normalize=True,
+                                                   return_attention_mask=False)
+    aud.model = audenc.Wav2Vec2ModelResampled(Wav2Vec2Config(attn_implementation="eager"))
+    aud.model.load_state_dict(sd_w2v, strict=False)
+    aud.resampling, aud.dropout, aud.trainable = True, None, False
+    enc = seqenc.LinearSequenceEncoder(Munch(feature_dim=E.feature_dim, input_feature_dim=768))
+
+    class _Base(thb.TalkingHeadBase):
+        device = torch.device("cpu")
+
+    model = _Base.__new__(_Base)
+    nn.Module.__init__(model)
+    model.cfg = Munch(data=Munch(), model=Munch())
+    model.audio_model, model.sequence_encoder, model.sequence_decoder = aud, enc, dec
+    model.preprocessor, model.renderer, model.neural_losses, model.shape_model = prep, None, {}, None
+    own = {k: v for k, v in model.state_dict().items() if k.startswith("sequence_")
+           and ".flame." not in k and "preprocessor" not in k and "postprocessor" not in k}
+    assert set(own) == set(sd), sorted(set(own) ^ set(sd))
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    return model.eval(), sorted(own)
+
+
+def golden_emote():
+    from . import _inferno_import as ii
+    from . import synth
+    sd, sd_w2v = synth.emote_state(), synth.wav2vec2_state(0)
+    model, keys = build_reference_talking_head(sd, sd_w2v)
+    out = {"state_keys": np.array(keys)}
+    # The reference pins torch 1.9.0 (requirements.txt:5), which has no fused "fast path" for nn.TransformerEncoderLayer. The
+    # fast path of the torch installed here (2.11, eval + no_grad) mishandles the 3-D additive float mask the L2L decoder passes
+    # ([B*heads, T, T], L2lMotionPrior.py:477-481): it disagrees with the layer's own reference (slow) path by O(1). The goldens
+    # are therefore minted on the slow path = the arithmetic torch 1.9 performs.
+    torch.backends.mha.set_fastpath_enabled(False)
+    with torch.no_grad():
+        # B = 1 (the only way the reference calls it, evaluation_functions.py:381-383), T = 27 (not a multiple of 8 -> padding path)
+        for tag, T in (("t27", 27), ("t48", 48)):
+            s = synth.emote_sample(1, T, seed=50)
+            r = model(dict(s))
+            for k in ("predicted_exp", "predicted_jaw", "prior_input_sequence"):
+                out[f"{tag}_{k}"] = r[k].numpy()
+            out[f"{tag}_gt_vertices_sub"] = r["gt_vertices"].numpy()[:, :, ::COL_STRIDE]
+            out[f"{tag}_template"] = r["template"].numpy()[:, ::COL_STRIDE]
+            out[f"{tag}_predicted_vertices_sub"] = r["predicted_vertices"].numpy()[:, :, ::COL_STRIDE]
+            out[f"{tag}_predicted_vertices_chk"] = checksum(r["predicted_vertices"])
+        # external style embedding [B,1,128] (what voxel2style_emb feeds, train_diffusion_prior.py:195,218)
+        s = synth.emote_sample(1, 27, seed=50)
+        style = torch.from_numpy(np.random.default_rng(60).normal(0, 0.5, size=(1, 1, 128)).astype(np.float32))
+        r = model(dict(s), style_emb=style, is_external_style_emb=True)
+        out["ext_predicted_exp"], out["ext_predicted_jaw"] = r["predicted_exp"].numpy(), r["predicted_jaw"].numpy()
+        out["ext_predicted_vertices_chk"] = checksum(r["predicted_vertices"])
+        # only_style_emb branch (FaceFormerDecoder.py:599-601)
+        out["style_only"] = model(dict(s), only_style_emb=True).numpy()
+        mask = ii.load("inferno.models.temporal.TransformerMasking")[0].init_alibi_biased_mask_future(8, 600)
+        out["alibi_future_8_40"] = mask[:, :40, :40].numpy()
+    np.savez(os.path.join(GOLD, "emote.npz"), **out)
+    print("emote.npz", {k: v.shape for k, v in out.items()})
+
+
 def main():
     _paths()
     os.makedirs(GOLD, exist_ok=True)
@@ -307,6 +422,7 @@ def main():
     golden_wav2vec2()
     golden_faceformer()
     golden_prior()
+    golden_emote()
 
 
 if __name__ == "__main__":
