@@ -340,3 +340,60 @@ def ln_gelu_res(x, w, b, res=None, want_bf16=False, eps=1e-5):
         _lib.check(_lib.load().avi_ln_gelu_res(_ptr(x), _ptr(w), _ptr(b), _ptr(res), _ptr(o32), _ptr(o16), C.c_int64(rows),
                                                C.c_int32(Cc), C.c_float(eps), _stream()), "avi_ln_gelu_res")
     return o32, o16
+
+
+# ------------------------------------------------------------------------------------------------ EMOTE decoder pieces
+def audio_znorm(x, eps=1e-7):
+    _need_cuda(x)
+    x = x.contiguous().float()
+    y = torch.empty_like(x)
+    with _timed("audio_znorm", float(x.numel() * 8)):
+        _lib.check(_lib.load().avi_audio_znorm(_ptr(x), _ptr(y), C.c_int32(x.shape[0]), C.c_int64(x.shape[1]), C.c_float(eps), _stream()),
+                   "avi_audio_znorm")
+    return y
+
+
+def mha_small(qkv, B, T, H, D, slopes=None, want_bf16=False):
+    """fp32 qkv [B*T, 3*H*D] -> (out fp32 [B*T, H*D], optional bf16 copy); additive -slope_h*|i-j| bias when `slopes` is given."""
+    _need_cuda(qkv, slopes)
+    assert qkv.dtype == torch.float32 and qkv.is_contiguous()
+    o32 = torch.empty((B * T, H * D), dtype=torch.float32, device=qkv.device)
+    o16 = torch.empty((B * T, H * D), dtype=torch.bfloat16, device=qkv.device) if want_bf16 else None
+    with _timed("mha_small", 4.0 * B * H * T * T * D):
+        _lib.check(_lib.load().avi_mha_small_fwd(_ptr(qkv), _ptr(o32), _ptr(o16), C.c_int32(B), C.c_int32(T), C.c_int32(H), C.c_int32(D),
+                                                 C.c_float(D ** -0.5), _ptr(slopes), _stream()), "avi_mha_small_fwd")
+    return o32, o16
+
+
+def stage_rows(src, B, L, Lp, front, mode, dtype=torch.float32):
+    """mode 0 zero pad, 1 replicate pad, 2 zero insertion (see include/avi_b200.h)."""
+    _need_cuda(src)
+    assert src.dtype == torch.float32 and src.is_contiguous()
+    Cc = src.shape[-1]
+    dst = torch.empty((B, Lp, Cc), dtype=dtype, device=src.device)
+    with _timed("stage_rows", 0.0):
+        _lib.check(_lib.load().avi_stage_rows(_ptr(src), _ptr(dst), C.c_int32(_dt(dst)), C.c_int32(B), C.c_int32(L), C.c_int32(Lp),
+                                              C.c_int32(Cc), C.c_int32(front), C.c_int32(mode), _stream()), "avi_stage_rows")
+    return dst
+
+
+def lrelu_bn_repeat(x, bn_scale, bn_shift, B, L, repeat, slope=0.2):
+    _need_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    Cc = x.shape[-1]
+    y = torch.empty((B, L * repeat, Cc), dtype=torch.float32, device=x.device)
+    with _timed("lrelu_bn_repeat", 0.0):
+        _lib.check(_lib.load().avi_lrelu_bn_repeat(_ptr(x), _ptr(bn_scale), _ptr(bn_shift), _ptr(y), C.c_int32(B), C.c_int32(L),
+                                                   C.c_int32(Cc), C.c_int32(repeat), C.c_float(slope), _stream()), "avi_lrelu_bn_repeat")
+    return y
+
+
+def sub_add_rows_(a, neutral, tpl):
+    """In place: a[b, t, :] = (a[b, t, :] - neutral[b, :]) + tpl[b, :]."""
+    _need_cuda(a, neutral, tpl)
+    B, T, Cc = a.shape
+    assert a.is_contiguous() and neutral.is_contiguous() and tpl.is_contiguous() and a.dtype == torch.float32
+    with _timed("sub_add_rows", float(a.numel() * 8)):
+        _lib.check(_lib.load().avi_sub_add_rows(_ptr(a), _ptr(neutral), _ptr(tpl), _ptr(a), C.c_int32(B), C.c_int32(T), C.c_int32(Cc),
+                                                _stream()), "avi_sub_add_rows")
+    return a

@@ -43,6 +43,29 @@ def build_prior(precision: str = "fp32", samples_per_cta: int = 0, device: str =
     return prior.to(device).eval()
 
 
+def build_talking_head(precision: str = "fp32", device: str = "cuda", flame_dir: str = "/tmp/avi_flame_assets_emote"):
+    """Drop-in TalkingHeadWrapper (EMOTE, Path B) with the seeded synthetic wav2vec2 / decoder weights and FLAME(300, 50)."""
+    from transformers import Wav2Vec2Config
+
+    from . import synth
+    from .flame import FLAME
+    from .talking_head import TalkingHeadWrapper, emote_cfg
+    from .wav2vec import Wav2Vec2Model
+    w2v = Wav2Vec2Model(Wav2Vec2Config())
+    w2v.load_state_dict(synth.wav2vec2_state(0), strict=False)
+    fcfg = synth.write_flame_assets(flame_dir)
+    fcfg.n_shape, fcfg.n_exp = synth.EMOTE.n_shape, synth.EMOTE.n_exp
+    flame = FLAME(fcfg)
+    m = TalkingHeadWrapper(w2v, flame, emote_cfg(n_identities=synth.EMOTE.n_identities))
+    missing, unexpected = m.talking_head_model.load_state_dict(synth.emote_state(), strict=False)
+    assert not unexpected, unexpected
+    assert all(k.startswith("audio_model.") or ".flame." in k for k in missing), missing
+    m.talking_head_model.precision = precision
+    w2v.precision = precision
+    flame.precision = precision
+    return m.to(device).eval()
+
+
 def run_smoke(verbose: bool = False) -> dict:
     from oracle import faceformer_oracle as ffo   # checker only
     from oracle import flame_oracle as fo

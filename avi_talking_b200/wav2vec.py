@@ -200,6 +200,7 @@ class Wav2Vec2Model(_HFWav2Vec2Model):
             if output_hidden_states:
                 all_hidden = all_hidden + (h32.view(B, T, -1),)
         out = h32.view(B, T, cfg.hidden_size)
+        self.last_hidden_state_bf16 = h16.view(B, T, cfg.hidden_size) if bf16 else None   # for bf16 consumers (EMOTE encoder)
         # The reference forces output_attentions=True (:90) but no caller reads them (faceformer_disentangle.py:535,638,775
         # use .last_hidden_state only); the fused attention kernel never materialises the [B,12,T,T] maps.
         if return_dict is False:

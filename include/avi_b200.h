@@ -218,6 +218,32 @@ int avi_prior_sample(const AviPriorNet* net, const float* temb, const float* sch
 int avi_ln_gelu_res(const float* x, const float* w, const float* b, const float* res, float* out_f32, void* out_bf16, int64_t rows,
                     int32_t C, float eps, void* stream);
 
+/* ------------------------------------------------------------------ EMOTE talking-head decoder (Path B, third_party/inferno) ------------------------------------------------------------------ */
+/* per-clip zero-mean / unit-variance normalisation of the waveform (Wav2Vec2FeatureExtractor, called at
+ * inferno/models/temporal/AudioEncoders.py:170-178): y = (x - mean) / sqrt(var + eps), x, y fp32 [B, n] */
+int avi_audio_znorm(const float* x, float* y, int32_t B, int64_t n, float eps, void* stream);
+
+/* softmax(q k^T * scale - slope_h * |i - j|) v for small heads (D = 16 or 32): the nn.TransformerEncoderLayer self-attention of
+ * BertPriorDecoder (slopes = NULL, FaceFormerDecoder.py:996-1002) and of the L2L decoder (slopes [H] = ALiBi slopes, bias of
+ * init_alibi_biased_mask_future, TransformerMasking.py:80-98). qkv fp32 [B, T, 3*H*D]; out [B, T, H*D] fp32 and/or bf16. */
+int avi_mha_small_fwd(const float* qkv, float* out_f32, void* out_bf16, int32_t B, int32_t T, int32_t H, int32_t D, float scale,
+                      const float* slopes, void* stream);
+
+/* row staging for conv-mode GEMMs: dst [B, Lp, C] (dst_dtype) from src fp32 [B, L, C];
+ * mode 0 zero padding (front rows of zeros first), 1 replicate padding, 2 zero insertion dst[front + 2t] = src[t]
+ * (ConvTranspose1d(k=5, s=2, p=2, op=1) == zero insertion + 5-tap correlation with the flipped kernel; L2lMotionPrior.py:368-389) */
+int avi_stage_rows(const float* src, void* dst, int32_t dst_dtype, int32_t B, int32_t L, int32_t Lp, int32_t C, int32_t front,
+                   int32_t mode, void* stream);
+
+/* y[b, rep*t + u, c] = bn_scale[c] * LeakyReLU(x[b, t, c]) + bn_shift[c]: expander activation + eval BatchNorm1d + repeat_interleave
+ * (L2lMotionPrior.py:376-389,468-470); x fp32 [B, L, C] -> y fp32 [B, rep*L, C] */
+int avi_lrelu_bn_repeat(const float* x, const float* bn_scale, const float* bn_shift, float* y, int32_t B, int32_t L, int32_t C,
+                        int32_t repeat, float slope, void* stream);
+
+/* out[b, t, :] = (a[b, t, :] - neutral[b, :]) + tpl[b, :]  (vertex offsets from the neutral shape re-attached to the template,
+ * FaceFormerDecoder.py:1173-1175,690-694); out may alias a */
+int avi_sub_add_rows(const float* a, const float* neutral, const float* tpl, float* out, int32_t B, int32_t T, int32_t C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,3 +57,34 @@ def test_dropin_state_dict_keys_match_reference(golden):
     ns = po.noise_schedule(100)
     for k in ("betas", "posterior_mean_coef1", "sqrt_recipm1_alphas_cumprod"):
         assert torch.equal(getattr(prior.noise_scheduler, k), ns[k])
+
+
+def test_emote_oracle_matches_reference_golden(golden):
+    """Path B: the EMOTE oracle against the reference's own TalkingHeadBase.forward (oracle/make_golden.py golden_emote)."""
+    from oracle import emote_oracle as eo
+    g = golden("emote")
+    sd, w, buf = synth.emote_state(), synth.wav2vec2_state(0), synth.flame_buffers(300, 50)
+    o = eo.talking_head_forward(sd, w, buf, synth.emote_sample(1, 27, seed=50))
+    assert np.abs(o["predicted_exp"].numpy() - g["t27_predicted_exp"]).max() < 1e-5
+    assert np.abs(o["predicted_jaw"].numpy() - g["t27_predicted_jaw"]).max() < 1e-5
+    assert np.abs(o["prior_input_sequence"].numpy() - g["t27_prior_input_sequence"]).max() < 1e-5
+    assert np.abs(o["predicted_vertices"].numpy()[:, :, ::7] - g["t27_predicted_vertices_sub"]).max() < 1e-6
+    assert np.abs(o["gt_vertices"].numpy()[:, :, ::7] - g["t27_gt_vertices_sub"]).max() < 1e-6
+    assert np.abs(eo.alibi_future_mask(8, 40).numpy() - g["alibi_future_8_40"]).max() == 0.0
+    style = torch.from_numpy(np.random.default_rng(60).normal(0, 0.5, size=(1, 1, 128)).astype(np.float32))
+    o = eo.talking_head_forward(sd, w, buf, synth.emote_sample(1, 27, seed=50), style_emb=style, is_external_style_emb=True)
+    assert np.abs(o["predicted_exp"].numpy() - g["ext_predicted_exp"]).max() < 1e-5
+
+
+def test_emote_dropin_state_dict_keys_match_reference(golden):
+    from transformers import Wav2Vec2Config
+
+    from avi_talking_b200.flame import FLAME
+    from avi_talking_b200.talking_head import TalkingHeadWrapper, emote_cfg
+    from avi_talking_b200.wav2vec import Wav2Vec2Model
+    g = golden("emote")
+    fcfg = synth.write_flame_assets("/tmp/avi_flame_assets_keys")
+    fcfg.n_shape, fcfg.n_exp = 300, 50
+    m = TalkingHeadWrapper(Wav2Vec2Model(Wav2Vec2Config()), FLAME(fcfg), emote_cfg(n_identities=32))
+    own = sorted(k for k in m.talking_head_model.state_dict() if k.startswith("sequence_") and ".flame." not in k)
+    assert own == list(g["state_keys"])
