@@ -41,7 +41,19 @@ struct FlameTcParams {
   float* verts;            // [F][V][3]
   int F, V, V_pad;
   int n_vt, n_ftiles, n_items;
+  // frame groups (clips): tiles never cross a group, so a per-group template (shape blendshapes hoisted out of the per-frame
+  // contraction) is uniform within a tile. One group of F frames = the plain case.
+  int frames_per_group, tiles_per_group;
+  int64_t template_stride;  // floats between consecutive group templates (0: one global template)
 };
+
+// first frame / number of valid frames of frame tile ft
+__device__ __forceinline__ void flame_tile_frames(const FlameTcParams& p, int ft, int& f0, int& nfr, int& group) {
+  group = ft / p.tiles_per_group;
+  const int t0 = (ft % p.tiles_per_group) * FT_NF;
+  f0 = group * p.frames_per_group + t0;
+  nfr = min(FT_NF, p.frames_per_group - t0);
+}
 
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   umma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);  // same instruction (kind::f16); idesc selects fp16 operands
@@ -104,8 +116,8 @@ flame_tc_kernel(const __grid_constant__ CUtensorMap map_dirs, const __grid_const
         for (int ft = ft0; ft < ft1; ++ft) {
           mbar_wait(smem_u32(&coef_empty[stage]), phase ^ 1);
           mbar_wait(smem_u32(&as_empty[stage]), phase ^ 1);
-          const int f0 = ft * FT_NF;
-          const int nfr = min(FT_NF, p.F - f0);
+          int f0, nfr, group;
+          flame_tile_frames(p, ft, f0, nfr, group);
           const uint32_t fb = smem_u32(&cf_full[stage]);
           mbar_expect_tx(fb, FT_COEF_BYTES + (uint32_t)nfr * FT_NJ * 12 * 4);
           for (int c = 0; c < FT_NCH; ++c)
@@ -170,16 +182,24 @@ flame_tc_kernel(const __grid_constant__ CUtensorMap map_dirs, const __grid_const
       const int vw0 = vt * FT_BM + quarter * 32;  // first vertex of this warp
       const int v = vw0 + lane;
       float w[FT_NJ], vtp[3];
+      const bool v_ok = v < p.V;
 #pragma unroll
       for (int j = 0; j < FT_NJ; ++j) w[j] = (v < p.V) ? p.lbs_w[(int64_t)v * FT_NJ + j] : 0.f;
 #pragma unroll
       for (int c = 0; c < 3; ++c) vtp[c] = (v < p.V) ? p.v_template[(int64_t)v * 3 + c] : 0.f;
-      const bool v_ok = v < p.V;
       const int ft0 = chunk * FT_CHUNK_TILES;
       const int ft1 = min(ft0 + FT_CHUNK_TILES, p.n_ftiles);
       for (int ft = ft0; ft < ft1; ++ft, ++acc_it) {
         const int as = acc_it & 1;
         const uint32_t aph = (acc_it >> 1) & 1;
+        int tf0, tnfr, group;
+        flame_tile_frames(p, ft, tf0, tnfr, group);
+        if (p.template_stride != 0 && v_ok) {  // per-group (per-clip) shaped template
+          const float* tp = p.v_template + (int64_t)group * p.template_stride + (int64_t)v * 3;
+          vtp[0] = __ldg(tp);
+          vtp[1] = __ldg(tp + 1);
+          vtp[2] = __ldg(tp + 2);
+        }
         mbar_wait(smem_u32(&cf_full[stage]), phase);   // joint transforms of this tile are in smem
         mbar_wait(smem_u32(&tmem_full[as]), aph);
         tc_fence_after();
@@ -189,11 +209,12 @@ flame_tc_kernel(const __grid_constant__ CUtensorMap map_dirs, const __grid_const
         tmem_ld16(ta + FT_NF, vy);
         tmem_ld16(ta + 2 * FT_NF, vz);
         const uint32_t As = smem_u32(smem + FT_OFF_AS + stage * FT_AS_BYTES) + (fq * 16) * (FT_NJ * 12 * 4);
-        const int fbase = ft * FT_NF + fq * 16;
+        const int fbase = tf0 + fq * 16;
+        const int flimit = tf0 + tnfr;
         float* o = p.verts + (int64_t)fbase * V3 + (int64_t)v * 3;   // lanes = consecutive vertices: 384 contiguous bytes per frame
 #pragma unroll
         for (int n = 0; n < 16; ++n) {
-          if (fbase + n < p.F) {  // warp-uniform
+          if (fbase + n < flimit) {  // warp-uniform
             float T[12];
 #pragma unroll
             for (int e = 0; e < 12; ++e) T[e] = 0.f;
@@ -238,7 +259,7 @@ flame_tc_kernel(const __grid_constant__ CUtensorMap map_dirs, const __grid_const
 }
 
 // dirs16[c][v][l] = dirs32[l][v*3 + c] for l < n_dirs (shape | expression | pose rows; the template row is excluded), zero padded
-__global__ void flame_pack_tc_kernel(const float* __restrict__ dirs32, __half* __restrict__ dirs16, int V, int V_pad, int n_dirs) {
+__global__ void flame_pack_tc_kernel(const float* __restrict__ dirs32, __half* __restrict__ dirs16, int V, int V_pad, int row0, int n_dirs) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t total = (int64_t)3 * V_pad * FT_K;
   if (i >= total) return;
@@ -246,17 +267,17 @@ __global__ void flame_pack_tc_kernel(const float* __restrict__ dirs32, __half* _
   const int v = (int)((i / FT_K) % V_pad);
   const int c = (int)(i / ((int64_t)FT_K * V_pad));
   float x = 0.f;
-  if (v < V && l < n_dirs) x = dirs32[(int64_t)l * V * 3 + v * 3 + c];
+  if (v < V && l < n_dirs) x = dirs32[(int64_t)(row0 + l) * V * 3 + v * 3 + c];
   dirs16[i] = __float2half_rn(x);
 }
 
 // coef16[f][l] = fp16(coef32[f][l]) for l < n_dirs, zero padded to FT_K
-__global__ void flame_coef16_kernel(const float* __restrict__ coef32, __half* __restrict__ coef16, int F, int K_pad32, int n_dirs) {
+__global__ void flame_coef16_kernel(const float* __restrict__ coef32, __half* __restrict__ coef16, int F, int K_pad32, int col0, int n_dirs) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)F * FT_K) return;
   const int l = (int)(i % FT_K);
   const int64_t f = i / FT_K;
-  coef16[i] = __float2half_rn(l < n_dirs ? coef32[f * K_pad32 + l] : 0.f);
+  coef16[i] = __float2half_rn(l < n_dirs ? coef32[f * K_pad32 + col0 + l] : 0.f);
 }
 
 }  // namespace avi
@@ -265,24 +286,36 @@ using namespace avi;
 
 extern "C" int avi_flame_tc_supported(int32_t NB) { return (NB + 36 <= FT_K) ? 1 : 0; }
 
-extern "C" int avi_flame_pack_tc(const float* dirs32, void* dirs16, int32_t V, int32_t NB, int32_t V_pad, void* stream) {
-  AVI_REQUIRE(V > 0 && NB + 36 <= FT_K && V_pad % FT_BM == 0 && V_pad >= V, "avi_flame_pack_tc: unsupported shape (NB=%d V_pad=%d)", NB, V_pad);
+extern "C" int avi_flame_pack_tc_rows(const float* dirs32, void* dirs16, int32_t V, int32_t row0, int32_t n_dirs, int32_t V_pad,
+                                      void* stream) {
+  AVI_REQUIRE(V > 0 && row0 >= 0 && n_dirs > 0 && n_dirs <= FT_K && V_pad % FT_BM == 0 && V_pad >= V,
+              "avi_flame_pack_tc_rows: unsupported shape (n_dirs=%d V_pad=%d)", n_dirs, V_pad);
   const int64_t total = (int64_t)3 * V_pad * FT_K;
-  flame_pack_tc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dirs32, (__half*)dirs16, V, V_pad, NB + 36);
+  flame_pack_tc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dirs32, (__half*)dirs16, V, V_pad, row0, n_dirs);
   return check_launch("flame_pack_tc");
 }
 
-// The prologue (coefficient rows, joints, kinematic chain, optional landmark rows) is avi_flame_lbs_fwd's; this entry replaces
-// only its blend+skin kernel. coef32 [F, K_pad32] and A [F,5,12] must already have been produced by the prologue on `stream`.
-extern "C" int avi_flame_blend_skin_tc(const float* coef32, const float* A, const void* dirs16, const float* lbs_weights,
-                                       const float* v_template, void* coef16, float* verts, int32_t F, int32_t V, int32_t NB,
-                                       int32_t K_pad32, int32_t V_pad, void* stream) {
-  AVI_REQUIRE(F > 0 && V > 0 && NB + 36 <= FT_K && V_pad % FT_BM == 0 && V_pad >= V, "avi_flame_blend_skin_tc: unsupported shape");
+extern "C" int avi_flame_pack_tc(const float* dirs32, void* dirs16, int32_t V, int32_t NB, int32_t V_pad, void* stream) {
+  AVI_REQUIRE(NB + 36 <= FT_K, "avi_flame_pack_tc: NB + 36 must be <= %d", FT_K);
+  return avi_flame_pack_tc_rows(dirs32, dirs16, V, 0, NB + 36, V_pad, stream);
+}
+
+// Grouped form: frames are G groups (clips) of frames_per_group; `templates` holds one [V,3] template per group (template_stride
+// floats apart; 0 = one global template); the tensor-core contraction runs over coefficient columns [coef_col0, coef_col0 + n_dirs)
+// of coef32 against the n_dirs direction rows packed by avi_flame_pack_tc_rows.
+extern "C" int avi_flame_blend_skin_tc_grouped(const float* coef32, const float* A, const void* dirs16, const float* lbs_weights,
+                                               const float* templates, int64_t template_stride, void* coef16, float* verts, int32_t F,
+                                               int32_t V, int32_t n_dirs, int32_t coef_col0, int32_t K_pad32, int32_t V_pad,
+                                               int32_t frames_per_group, void* stream) {
+  AVI_REQUIRE(F > 0 && V > 0 && n_dirs > 0 && n_dirs <= FT_K && V_pad % FT_BM == 0 && V_pad >= V && coef_col0 >= 0 &&
+                  coef_col0 + n_dirs <= K_pad32,
+              "avi_flame_blend_skin_tc: unsupported shape");
+  AVI_REQUIRE(frames_per_group > 0 && F % frames_per_group == 0, "avi_flame_blend_skin_tc: F must be a multiple of frames_per_group");
   AVI_REQUIRE(((uintptr_t)A % 16 == 0) && ((uintptr_t)dirs16 % 16 == 0) && ((uintptr_t)coef16 % 16 == 0),
               "avi_flame_blend_skin_tc: unaligned pointers");
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t n16 = (int64_t)F * FT_K;
-  flame_coef16_kernel<<<(unsigned)((n16 + 255) / 256), 256, 0, st>>>(coef32, (__half*)coef16, F, K_pad32, NB + 36);
+  flame_coef16_kernel<<<(unsigned)((n16 + 255) / 256), 256, 0, st>>>(coef32, (__half*)coef16, F, K_pad32, coef_col0, n_dirs);
   if (check_launch("flame_coef16")) return 1;
   CUtensorMap map_dirs, map_coef;
   {
@@ -300,13 +333,16 @@ extern "C" int avi_flame_blend_skin_tc(const float* coef32, const float* A, cons
   FlameTcParams p;
   p.A = A;
   p.lbs_w = lbs_weights;
-  p.v_template = v_template;
+  p.v_template = templates;
   p.verts = verts;
   p.F = F;
   p.V = V;
   p.V_pad = V_pad;
   p.n_vt = V_pad / FT_BM;
-  p.n_ftiles = (F + FT_NF - 1) / FT_NF;
+  p.frames_per_group = frames_per_group;
+  p.tiles_per_group = (frames_per_group + FT_NF - 1) / FT_NF;
+  p.template_stride = template_stride;
+  p.n_ftiles = (F / frames_per_group) * p.tiles_per_group;
   const int n_chunks = (p.n_ftiles + FT_CHUNK_TILES - 1) / FT_CHUNK_TILES;
   p.n_items = p.n_vt * n_chunks;
   static std::once_flag once;
@@ -316,4 +352,14 @@ extern "C" int avi_flame_blend_skin_tc(const float* coef32, const float* A, cons
   const int grid = p.n_items < kNumSMs ? p.n_items : kNumSMs;
   flame_tc_kernel<<<grid, FT_THREADS, FT_SMEM, st>>>(map_dirs, map_coef, p);
   return check_launch("flame_tc");
+}
+
+// The prologue (coefficient rows, joints, kinematic chain, optional landmark rows) is avi_flame_lbs_fwd's; this entry replaces
+// only its blend+skin kernel. coef32 [F, K_pad32] and A [F,5,12] must already have been produced by the prologue on `stream`.
+extern "C" int avi_flame_blend_skin_tc(const float* coef32, const float* A, const void* dirs16, const float* lbs_weights,
+                                       const float* v_template, void* coef16, float* verts, int32_t F, int32_t V, int32_t NB,
+                                       int32_t K_pad32, int32_t V_pad, void* stream) {
+  AVI_REQUIRE(NB + 36 <= FT_K, "avi_flame_blend_skin_tc: NB + 36 must be <= %d", FT_K);
+  return avi_flame_blend_skin_tc_grouped(coef32, A, dirs16, lbs_weights, v_template, 0, coef16, verts, F, V, NB + 36, 0, K_pad32, V_pad, F,
+                                         stream);
 }

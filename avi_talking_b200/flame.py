@@ -37,6 +37,7 @@ class _PackCache:
     def __init__(self):
         self.key = None
         self.dirs = self.jreg = self.dirs16 = None
+        self.hoist = None   # (n_shape, dirs16 of the expression + pose rows, shape directions [V*3, n_shape], template [V*3])
 
     def get(self, shapedirs, posedirs, v_template, J_regressor):
         key = tuple((t.data_ptr(), t._version, t.device) for t in (shapedirs, posedirs, v_template, J_regressor))
@@ -45,6 +46,7 @@ class _PackCache:
             self.dirs, self.jreg = ops.flame_pack(shapedirs.contiguous(), posedirs.contiguous(), v_template.contiguous(),
                                                   J_regressor.contiguous(), _k_pad(nb))
             self.dirs16 = ops.flame_pack_tc(self.dirs, shapedirs.shape[0], nb) if ops.flame_tc_supported(nb) else None
+            self.hoist = None
             self.key = key
         return self.dirs, self.jreg
 
@@ -170,6 +172,33 @@ class FLAME(nn.Module):
     def vertices_only(self, shape_params, expression_params=None, pose_params=None, eye_pose_params=None):
         """The mesh without the landmark gathers (what the audio->vertex hot path consumes)."""
         return self._run_lbs(shape_params, expression_params, pose_params, eye_pose_params, want_rows=False)[0]
+
+    @torch.no_grad()
+    def vertices_sequence(self, shape, exp, pose):
+        """Meshes of G clips x T frames that share one shape per clip (how FlamePreprocessor / BertPriorDecoder / convert_coeff2verts
+        call FLAME: Preprocessors.py:136-150): shape [G, n_shape], exp [G, T, n_exp], pose [G, T, 6] -> [G, T, V*3].
+        bf16 mode hoists the shape blendshapes out of the per-frame contraction: one small GEMM gives the G shaped templates and the
+        tensor-core blend covers expression + pose correctives only (60 500 B written per frame, 4*(n_exp+6) B read)."""
+        G, T = exp.shape[:2]
+        V, nb = self.shapedirs.shape[0], self.shapedirs.shape[2]
+        ns = shape.shape[1]
+        pose = pose.reshape(G * T, -1).float()
+        betas = torch.cat([shape[:, None].expand(G, T, ns), exp], dim=2).reshape(G * T, nb).contiguous().float()
+        full_pose = self._full_pose(G * T, pose, None).contiguous().float()
+        n_dirs = nb - ns + _N_POSE_FEAT
+        if self.precision != "bf16" or n_dirs > 192:
+            verts, _, _ = _run(self._pack, self.precision, betas, full_pose, self.shapedirs, self.posedirs, self.v_template,
+                               self.J_regressor, self.lbs_weights)
+            return verts.view(G, T, V * 3)
+        dirs, jreg = self._pack.get(self.shapedirs, self.posedirs, self.v_template, self.J_regressor)
+        if self._pack.hoist is None or self._pack.hoist[0] != ns:
+            w_shape = self.shapedirs[:, :, :ns].reshape(V * 3, ns).contiguous().float()
+            self._pack.hoist = (ns, ops.flame_pack_tc_rows(dirs, V, ns, n_dirs), w_shape, self.v_template.reshape(-1).contiguous().float())
+        _, dirs16_exp, w_shape, tmpl = self._pack.hoist
+        templates = ops.linear(shape.contiguous().float(), w_shape, tmpl)                     # [G, V*3] = v_template + S shape
+        verts = ops.flame_lbs_tc_grouped(betas, full_pose, dirs16_exp, jreg, self.lbs_weights.contiguous(), templates, V, nb, ns,
+                                         _k_pad(nb), T)
+        return verts.view(G, T, V * 3)
 
     @torch.no_grad()
     def forward(self, shape_params=None, expression_params=None, pose_params=None, eye_pose_params=None):

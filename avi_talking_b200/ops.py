@@ -397,3 +397,34 @@ def sub_add_rows_(a, neutral, tpl):
         _lib.check(_lib.load().avi_sub_add_rows(_ptr(a), _ptr(neutral), _ptr(tpl), _ptr(a), C.c_int32(B), C.c_int32(T), C.c_int32(Cc),
                                                 _stream()), "avi_sub_add_rows")
     return a
+
+
+def flame_pack_tc_rows(dirs32, V, row0, n_dirs):
+    V_pad = ((V + 127) // 128) * 128
+    dirs16 = torch.empty((3, V_pad, 192), dtype=torch.float16, device=dirs32.device)
+    _lib.check(_lib.load().avi_flame_pack_tc_rows(_ptr(dirs32), _ptr(dirs16), C.c_int32(V), C.c_int32(row0), C.c_int32(n_dirs),
+                                                  C.c_int32(V_pad), _stream()), "avi_flame_pack_tc_rows")
+    return dirs16
+
+
+def flame_lbs_tc_grouped(betas, full_pose, dirs16_exp, jreg, lbs_weights, templates, V, NB, n_shape, K_pad, frames_per_group):
+    """FLAME with one shape per group of frames: the shape blendshapes are already folded into `templates` [G, V*3]; the
+    tensor-core contraction covers expression + pose-corrective columns only. betas [F, NB] still carries the shape (joints)."""
+    _need_cuda(betas, full_pose, templates)
+    F = betas.shape[0]
+    dev = betas.device
+    coef = torch.empty((F, K_pad), dtype=torch.float32, device=dev)
+    coef16 = torch.empty((F, 192), dtype=torch.float16, device=dev)
+    A = torch.empty((F, 5, 12), dtype=torch.float32, device=dev)
+    verts = torch.empty((F, V, 3), dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    n_dirs = NB - n_shape + 36
+    with _timed("flame_lbs", float(F) * (V * 12 + 4 * (NB - n_shape + 6))):
+        _lib.check(lib.avi_flame_prologue(_ptr(betas), _ptr(full_pose), _ptr(jreg), _ptr(coef), _ptr(A), None, None,
+                                          C.c_int32(F), C.c_int32(NB), C.c_int32(K_pad), _stream()), "avi_flame_prologue")
+        _lib.check(lib.avi_flame_blend_skin_tc_grouped(_ptr(coef), _ptr(A), _ptr(dirs16_exp), _ptr(lbs_weights), _ptr(templates),
+                                                       C.c_int64(V * 3), _ptr(coef16), _ptr(verts), C.c_int32(F), C.c_int32(V),
+                                                       C.c_int32(n_dirs), C.c_int32(n_shape), C.c_int32(K_pad),
+                                                       C.c_int32(dirs16_exp.shape[1]), C.c_int32(frames_per_group), _stream()),
+                   "avi_flame_blend_skin_tc_grouped")
+    return verts

@@ -252,10 +252,8 @@ class TalkingHeadModel(nn.Module):
     def _flame_sequence(self, shape, exp, jaw):
         """FlamePreprocessor._forward (Preprocessors.py:62-186): vertices [B,T,V*3] for per-frame exp / jaw, pose = [0,0,0,jaw]."""
         flame = self.sequence_decoder.flame
-        B, T = exp.shape[:2]
-        pose = torch.cat([torch.zeros_like(jaw), jaw], dim=-1).reshape(B * T, 6)
-        shp = shape[:, None].expand(B, T, shape.shape[1]).reshape(B * T, -1)
-        return flame.vertices_only(shp, exp.reshape(B * T, -1).contiguous(), pose).view(B, T, -1)
+        pose = torch.cat([torch.zeros_like(jaw), jaw], dim=-1)
+        return flame.vertices_sequence(shape, exp.contiguous(), pose)
 
     def _neutral(self, shape):
         flame = self.sequence_decoder.flame

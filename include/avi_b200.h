@@ -175,6 +175,16 @@ int avi_flame_blend_skin_tc(const float* coef32, const float* A, const void* dir
                             const float* v_template, void* coef16, float* verts, int32_t F, int32_t V, int32_t NB,
                             int32_t K_pad32, int32_t V_pad, void* stream);
 
+/* Grouped form with the SHAPE blendshapes hoisted out of the per-frame contraction (FlamePreprocessor / BertPriorDecoder call FLAME
+ * with one shape per clip, Preprocessors.py:136-150): frames = G groups of frames_per_group; templates = one shaped template
+ * [V,3] per group (template_stride floats apart, 0 = one global template); the tensor-core contraction covers coefficient columns
+ * [coef_col0, coef_col0 + n_dirs) of coef32 (expression | pose feature) against direction rows [row0, row0 + n_dirs) of dirs32. */
+int avi_flame_pack_tc_rows(const float* dirs32, void* dirs16, int32_t V, int32_t row0, int32_t n_dirs, int32_t V_pad, void* stream);
+int avi_flame_blend_skin_tc_grouped(const float* coef32, const float* A, const void* dirs16, const float* lbs_weights,
+                                    const float* templates, int64_t template_stride, void* coef16, float* verts, int32_t F, int32_t V,
+                                    int32_t n_dirs, int32_t coef_col0, int32_t K_pad32, int32_t V_pad, int32_t frames_per_group,
+                                    void* stream);
+
 /* barycentric landmark gather (lbs.py:103-139): out[f, l, :] = sum_c bary[f|0, l, c] * verts[f, faces[idx[f|0, l], c], :].
  * per_frame = 1 when idx/bary carry a frame dimension (dynamic contour landmarks). */
 int avi_flame_landmarks(const float* verts, const int64_t* faces, const int64_t* idx, const float* bary, float* out,

@@ -133,3 +133,23 @@ def test_batched_clips_match_oracle(precision):
     if precision == "fp32":
         assert ev < 1e-5
     assert r["predicted_vertices"].shape == (B, T, 15069) and r["gt_vertices"].shape == (B, T, 15069)
+
+
+@pytest.mark.parametrize("n_shape,T", [(300, 43), (100, 130), (300, 64)])
+def test_flame_vertices_sequence_hoisted_shape(n_shape, T):
+    """FLAME.vertices_sequence (shape blendshapes hoisted per clip, grouped tensor-core blend) == per-frame oracle FLAME."""
+    from helpers import build_flame
+    G = 3
+    buf = synth.flame_buffers(n_shape, 50)
+    rng = np.random.default_rng(5)
+    shape = torch.from_numpy(rng.normal(size=(G, n_shape)).astype(np.float32))
+    exp = torch.from_numpy(rng.normal(size=(G, T, 50)).astype(np.float32))
+    jaw = torch.from_numpy((0.1 * rng.normal(size=(G, T, 3))).astype(np.float32))
+    want, _ = eo.flame_from_coeffs(buf, shape, exp, jaw)
+    pose = torch.cat([torch.zeros_like(jaw), jaw], -1)
+    for prec, tol in (("bf16", 5e-5), ("fp32", 1e-6)):
+        m = build_flame(n_shape=n_shape, mediapipe=False, precision=prec)
+        got = m.vertices_sequence(shape.cuda(), exp.cuda(), pose.cuda())
+        err = (got.cpu() - want).abs().max().item()
+        print(f"vertices_sequence n_shape={n_shape} T={T} {prec}: max abs vertex error {err:.3e} m")
+        assert got.shape == (G, T, 15069) and err < tol
