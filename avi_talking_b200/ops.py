@@ -146,6 +146,26 @@ def conv0_gn_gelu(audio, w, gn_w, gn_b, out, out_batch_stride, eps=1e-5):
     return out
 
 
+def conv0_pack_tc(w):
+    _need_cuda(w)
+    wp = torch.empty((512, 64), dtype=torch.bfloat16, device=w.device)
+    _lib.check(_lib.load().avi_w2v_conv0_pack_tc(_ptr(w.contiguous().float()), _ptr(wp), _stream()), "avi_w2v_conv0_pack_tc")
+    return wp
+
+
+def conv0_gn_gelu_tc(audio, w, w_packed, gn_w, gn_b, out, out_batch_stride, eps=1e-5):
+    """conv0 + GroupNorm + GELU on tensor cores (bf16 output, 512 channels)."""
+    _need_cuda(audio, w, out)
+    B, n = audio.shape
+    Cc = w.shape[0]
+    stats = torch.empty((B, Cc, 2), dtype=torch.float64, device=audio.device)
+    with _timed("conv0_gn_gelu", float(out.numel() * out.element_size())):
+        _lib.check(_lib.load().avi_w2v_conv0_gn_gelu_tc(_ptr(audio), _ptr(w), _ptr(w_packed), _ptr(gn_w), _ptr(gn_b), _ptr(stats),
+                                                        _ptr(out), C.c_int64(out_batch_stride), C.c_int32(B), C.c_int32(n),
+                                                        C.c_int32(Cc), C.c_float(eps), _stream()), "avi_w2v_conv0_gn_gelu_tc")
+    return out
+
+
 def lerp_layernorm(x, in_batch_stride, B, T_in, T_out, ln_w, ln_b, want_f32, want_bf16, eps=1e-5):
     _need_cuda(x)
     Cc = ln_w.numel()

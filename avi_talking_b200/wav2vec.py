@@ -78,6 +78,8 @@ class Wav2Vec2Model(_HFWav2Vec2Model):
         convs = self.feature_extractor.conv_layers
         P["conv0_w"] = f32(convs[0].conv.weight.reshape(cfg.conv_dim[0], cfg.conv_kernel[0]))
         P["gn_w"], P["gn_b"] = f32(convs[0].layer_norm.weight), f32(convs[0].layer_norm.bias)
+        if bf16 and cfg.conv_dim[0] == 512 and cfg.conv_kernel[0] == 10 and cfg.conv_stride[0] == 5:
+            P["conv0_w_tc"] = ops.conv0_pack_tc(P["conv0_w"])      # split-bf16 operand of the tensor-core conv0
         P["conv_w"] = []
         for i in range(1, len(convs)):
             w = convs[i].conv.weight  # [Cout, Cin, k] -> [Cout, k*Cin] tap-major (matches time-major activations)
@@ -127,7 +129,10 @@ class Wav2Vec2Model(_HFWav2Vec2Model):
         L = (n - cfg.conv_kernel[0]) // cfg.conv_stride[0] + 1
         La = L + (L & 1)
         h = torch.empty((B, La, Cc), dtype=adt, device=x.device)
-        ops.conv0_gn_gelu(x, P["conv0_w"], P["gn_w"], P["gn_b"], h, La * Cc)
+        if "conv0_w_tc" in P:
+            ops.conv0_gn_gelu_tc(x, P["conv0_w"], P["conv0_w_tc"], P["gn_w"], P["gn_b"], h, La * Cc)
+        else:
+            ops.conv0_gn_gelu(x, P["conv0_w"], P["gn_w"], P["gn_b"], h, La * Cc)
         for i in range(1, len(cfg.conv_kernel)):
             k, s = cfg.conv_kernel[i], cfg.conv_stride[i]
             Lo = (L - k) // s + 1

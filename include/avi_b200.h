@@ -93,6 +93,14 @@ int avi_w2v_conv0_gn_gelu(const float* audio, const float* w /*[C,10]*/, const f
                           void* stats, void* out, int32_t out_dtype, int64_t out_batch_stride,
                           int32_t B, int32_t n_samples, int32_t C, float eps, void* stream);
 
+/* Same layer on the tcgen05 path (bf16 output, C == 512): the 10-tap contraction is a split-bf16 MMA (fp32-accurate to ~2^-16), the
+ * GroupNorm statistics come from 65 audio moments per clip (exact, fp64), GroupNorm + GELU are the MMA epilogue.
+ *   avi_w2v_conv0_pack_tc: w fp32 [512,10] -> w_packed bf16 [512,64] (once per weight version)
+ *   stats: the same scratch as above (B*C*2 doubles). */
+int avi_w2v_conv0_pack_tc(const float* w, void* w_packed, void* stream);
+int avi_w2v_conv0_gn_gelu_tc(const float* audio, const float* w, const void* w_packed, const float* gn_w, const float* gn_b, void* stats,
+                             void* out, int64_t out_batch_stride, int32_t B, int32_t n_samples, int32_t C, float eps, void* stream);
+
 /* align_corners linear resample over time + LayerNorm(C): models/lib/wav2vec.py:67-73,108 + HF feature_projection.layer_norm.
  * in [B, T_in, C] (in_dtype, batch stride in elements) -> out_f32 / out_bf16 [B*T_out, C] (either may be NULL). */
 int avi_w2v_lerp_layernorm(const void* in, int32_t in_dtype, int64_t in_batch_stride, const float* ln_w, const float* ln_b,

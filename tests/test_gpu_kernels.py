@@ -200,3 +200,27 @@ def test_mha(ops, T, dtype):
 def test_cast_bf16(ops):
     x = torch.from_numpy(_rng(10).normal(size=(1031,)).astype(np.float32))
     assert torch.equal(ops.cast_bf16(x.cuda()).cpu(), x.bfloat16())
+
+
+@pytest.mark.parametrize("n", [4000, 16000, 1290])
+def test_conv0_gn_gelu_tensor_core(ops, n):
+    """conv0 as a split-bf16 MMA with analytic GroupNorm statistics == fp64 torch conv + group_norm + gelu (bf16 output rounding)."""
+    r = _rng(6)
+    B, C = 3, 512
+    x = torch.from_numpy(r.normal(size=(B, n)).astype(np.float32))
+    x[1] *= 3.0
+    x[2] += 0.5          # non-zero mean: exercises the mean term of the analytic statistics
+    w = torch.from_numpy((r.normal(size=(C, 1, 10)) * 0.4).astype(np.float32))
+    g = torch.from_numpy((1 + 0.1 * r.normal(size=C)).astype(np.float32))
+    bt = torch.from_numpy((0.1 * r.normal(size=C)).astype(np.float32))
+    L = (n - 10) // 5 + 1
+    La = L + (L & 1)
+    out = torch.zeros(B, La, C, dtype=torch.bfloat16, device="cuda")
+    w2 = w.reshape(C, 10).cuda()
+    ops.conv0_gn_gelu_tc(x.cuda(), w2, ops.conv0_pack_tc(w2), g.cuda(), bt.cuda(), out, La * C)
+    ref = F.gelu(F.group_norm(F.conv1d(x.double()[:, None], w.double(), stride=5), C, g.double(), bt.double(), 1e-5)).transpose(1, 2)
+    got = out[:, :L].float().cpu().double()
+    err = (got - ref).abs()
+    # bf16 output rounding is 2^-9 relative; the arithmetic before it is fp32-accurate
+    assert (err / (1.0 + ref.abs())).max().item() < 6e-3
+    assert err.mean().item() < 1e-3
