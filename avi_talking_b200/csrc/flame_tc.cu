@@ -284,6 +284,16 @@ __global__ void flame_coef16_kernel(const float* __restrict__ coef32, __half* __
 
 using namespace avi;
 
+static std::atomic<int> g_flame_max_ctas{kNumSMs};
+
+// Process-wide cap on the CTAs of the tensor-core FLAME kernel (default: one per SM). A caller that runs FLAME concurrently with
+// a kernel occupying part of the GPU (the 64-CTA autoregressive decoder) sizes it to the SMs left over.
+extern "C" int avi_flame_set_max_ctas(int32_t n) {
+  AVI_REQUIRE(n >= 1 && n <= kNumSMs, "avi_flame_set_max_ctas: n must be in 1..%d", kNumSMs);
+  g_flame_max_ctas.store(n);
+  return 0;
+}
+
 extern "C" int avi_flame_tc_supported(int32_t NB) { return (NB + 36 <= FT_K) ? 1 : 0; }
 
 extern "C" int avi_flame_pack_tc_rows(const float* dirs32, void* dirs16, int32_t V, int32_t row0, int32_t n_dirs, int32_t V_pad,
@@ -349,7 +359,8 @@ extern "C" int avi_flame_blend_skin_tc_grouped(const float* coef32, const float*
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] { attr_err = cudaFuncSetAttribute(flame_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM); });
   AVI_REQUIRE(attr_err == cudaSuccess, "avi_flame_blend_skin_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
-  const int grid = p.n_items < kNumSMs ? p.n_items : kNumSMs;
+  const int cap = g_flame_max_ctas.load();
+  const int grid = p.n_items < cap ? p.n_items : cap;
   flame_tc_kernel<<<grid, FT_THREADS, FT_SMEM, st>>>(map_dirs, map_coef, p);
   return check_launch("flame_tc");
 }

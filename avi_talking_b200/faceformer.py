@@ -124,6 +124,8 @@ class Faceformer(nn.Module):
         self.precision = default_precision()
         self._packed = None
         self._packed_key = None
+        self._before_ar = None
+        self._side_stream = None
 
     # ------------------------------------------------------------------ packing
     def _own_params(self):
@@ -243,6 +245,8 @@ class Faceformer(nn.Module):
         else:
             if frame_num != T:
                 cross = cross.view(B, T, fd)[:, :frame_num].contiguous()
+            if self._before_ar is not None:      # predict_and_convert: side-stream work that overlaps the (64-CTA) AR kernel
+                self._before_ar()
             hidden = ops.ff_decoder_ar(P["dec_struct"], cross, style, B, frame_num, fd, period)  # :461-476
         return self._vertex_head(hidden, P, template)                                          # :473,480-481
 
@@ -265,6 +269,37 @@ class Faceformer(nn.Module):
         else:
             hidden_states = hs_a                                                               # faceformer_vert.py:434
         return self.forward_ff(None, hidden_states, obj_embedding, T, teacher_forcing=False)  # :810
+
+    @torch.no_grad()
+    def predict_and_convert(self, audio, emo_embed, gt_coeff, gt_pose, gt_shape):
+        """predict_from_embeddings(audio, emo_embed) and convert_coeff2verts(gt_coeff, gt_pose, gt_shape) as ONE scheduled unit.
+        The two are independent; the autoregressive decoder is a latency-bound kernel of one CTA per clip, so FLAME is launched
+        on a side stream at the moment the AR kernel starts and sized to the SMs that kernel leaves idle."""
+        B = audio.shape[0]
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(device=audio.device)
+        main, side = torch.cuda.current_stream(), self._side_stream
+        out = {}
+
+        def launch_flame():
+            side.wait_stream(main)
+            free = max(148 - B, 32) if self.precision == "bf16" else 148
+            ops.flame_set_max_ctas(free)
+            try:
+                with torch.cuda.stream(side):
+                    out["fv"] = self.convert_coeff2verts(gt_coeff, gt_pose, gt_shape)
+            finally:
+                ops.flame_set_max_ctas(148)
+
+        self._before_ar = launch_flame
+        try:
+            v = self.predict_from_embeddings(audio, emo_embed)
+        finally:
+            self._before_ar = None
+        # join: everything the side stream read or wrote is ordered before later main-stream work, and the next call's side work
+        # starts with side.wait_stream(main), so no record_stream bookkeeping (which would defeat the caching allocator) is needed
+        main.wait_stream(side)
+        return v, out["fv"]
 
     @torch.no_grad()
     def predict(self, audio, head_img, eye_img, emotion_img, text=None):

@@ -448,3 +448,7 @@ def flame_lbs_tc_grouped(betas, full_pose, dirs16_exp, jreg, lbs_weights, templa
                                                        C.c_int32(dirs16_exp.shape[1]), C.c_int32(frames_per_group), _stream()),
                    "avi_flame_blend_skin_tc_grouped")
     return verts
+
+
+def flame_set_max_ctas(n: int):
+    _lib.check(_lib.load().avi_flame_set_max_ctas(C.c_int32(int(n))), "avi_flame_set_max_ctas")

@@ -186,9 +186,7 @@ def run_ours(args):
     flame_host = torch.empty((B * T, 5023, 3), dtype=torch.float32).pin_memory()
 
     def step(inp):
-        v = model.predict_from_embeddings(inp["audio"], inp["emo"])
-        fv = model.convert_coeff2verts(inp["coeff"], inp["pose"], inp["shape"].repeat_interleave(T, 0))
-        return v, fv
+        return model.predict_and_convert(inp["audio"], inp["emo"], inp["coeff"], inp["pose"], inp["shape"].repeat_interleave(T, 0))
 
     def barrier():
         if world > 1:
@@ -231,7 +229,8 @@ def run_ours(args):
         v.record_stream(copy_stream)
         fv.record_stream(copy_stream)
 
-    e2e_step(0)
+    for i in range(max(args.warmup, 3)):   # lets the caching allocator reach its steady state on every stream
+        e2e_step(i)
     main.wait_stream(copy_stream)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -246,8 +245,10 @@ def run_ours(args):
     sampler.join(timeout=2)
 
     # roofline pass: one extra step with CUDA events around every launch (not part of the timed numbers above)
+    # (the two halves run back to back here, not overlapped, so every kernel is timed alone)
     ops.PROFILE = []
-    step(devin)
+    model.predict_from_embeddings(devin["audio"], devin["emo"])
+    model.convert_coeff2verts(devin["coeff"], devin["pose"], devin["shape"].repeat_interleave(T, 0))
     torch.cuda.synchronize()
     prof = ops.PROFILE
     ops.PROFILE = None

@@ -193,6 +193,9 @@ int avi_flame_blend_skin_tc_grouped(const float* coef32, const float* A, const v
                                     int32_t n_dirs, int32_t coef_col0, int32_t K_pad32, int32_t V_pad, int32_t frames_per_group,
                                     void* stream);
 
+/* cap (1..148, default 148) on the CTAs of the tensor-core FLAME kernel, for running it beside a kernel that occupies part of the GPU */
+int avi_flame_set_max_ctas(int32_t n);
+
 /* barycentric landmark gather (lbs.py:103-139): out[f, l, :] = sum_c bary[f|0, l, c] * verts[f, faces[idx[f|0, l], c], :].
  * per_frame = 1 when idx/bary carry a frame dimension (dynamic contour landmarks). */
 int avi_flame_landmarks(const float* verts, const int64_t* faces, const int64_t* idx, const float* bary, float* out,

@@ -226,3 +226,24 @@ def test_batched_predict_equals_per_clip():
     for c in range(3):
         vc = m.predict_from_embeddings(a[c:c + 1], emo[c:c + 1])
         assert (vb[c] - vc[0]).abs().max().item() < 2e-6
+
+
+@pytest.mark.gpu
+def test_predict_and_convert_overlapped_equals_sequential():
+    """The side-stream FLAME launch (sized to the SMs the AR decoder leaves idle) changes scheduling only."""
+    from avi_talking_b200.smoke import build_models
+    m = build_models("bf16")
+    B, n = 3, 16000
+    a = synth.audio(B, n, seed=5).cuda()
+    T = 24
+    emo = torch.stack([synth.fan_embeddings(T, seed=30 + c)["emo"] for c in range(B)]).cuda()
+    rng = np.random.default_rng(3)
+    coeff = torch.from_numpy(rng.standard_normal((B * T, 53)).astype(np.float32)).cuda()
+    pose = torch.from_numpy((0.1 * rng.standard_normal((B * T, 6))).astype(np.float32)).cuda()
+    shape = torch.from_numpy(rng.standard_normal((B * T, 100)).astype(np.float32)).cuda()
+    v0 = m.predict_from_embeddings(a, emo)
+    f0 = m.convert_coeff2verts(coeff, pose.clone(), shape)
+    for _ in range(3):
+        v1, f1 = m.predict_and_convert(a, emo, coeff, pose.clone(), shape)
+    torch.cuda.synchronize()
+    assert torch.equal(v0, v1) and torch.equal(f0, f1)
