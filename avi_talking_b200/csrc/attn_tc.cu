@@ -17,9 +17,11 @@ constexpr uint32_t AT_Q_BYTES = AT_BM * AT_D * 2;   // 16 KB
 constexpr uint32_t AT_K_BYTES = AT_BN * AT_D * 2;   // 32 KB
 constexpr uint32_t AT_P_BYTES = AT_BM * AT_BN * 2;  // 64 KB, overlays Q | K | pad
 constexpr uint32_t AT_V_OFF = AT_P_BYTES;            // V after the P region
-constexpr uint32_t AT_SMEM = AT_P_BYTES + AT_K_BYTES + 64 + 1024;
+constexpr uint32_t AT_XCH_OFF = AT_P_BYTES + AT_K_BYTES + 64;   // row max / row sum exchange between the two column halves
+constexpr uint32_t AT_SMEM = AT_XCH_OFF + 2 * 2 * AT_BM * 4 + 1024;
+constexpr int AT_THREADS = 288, AT_CTRL_WARP = 8;
 
-__global__ void __launch_bounds__(160, 2)
+__global__ void __launch_bounds__(AT_THREADS, 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
                __nv_bfloat16* __restrict__ out, int T, int H, float scale_log2e) {
   extern __shared__ uint8_t smem_raw[];
@@ -39,11 +41,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   const int q0 = blockIdx.x * AT_BM, h = blockIdx.y, b = blockIdx.z;
   const int E = H * AT_D;
 
-  if (warp == 4) {
+  if (warp == AT_CTRL_WARP) {
     if (lane == 0) {
       mbar_init(smem_u32(bar_load), 1);
       mbar_init(smem_u32(bar_s), 1);
-      mbar_init(smem_u32(bar_p), 128);
+      mbar_init(smem_u32(bar_p), 256);
       mbar_init(smem_u32(bar_o), 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -56,7 +58,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == 4) {
+  if (warp == AT_CTRL_WARP) {
     if (lane == 0) {
       const uint32_t lb = smem_u32(bar_load);
       mbar_expect_tx(lb, AT_Q_BYTES + 2 * AT_K_BYTES);
@@ -84,25 +86,34 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       umma_commit(smem_u32(bar_o));
     }
   } else {
-    // ---------------- softmax warps: thread = query row (TMEM lane) ----------------
-    const int row = warp * 32 + lane;
-    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    // ---------------- softmax warps: two threads per query row (TMEM lane), one per half of the key range ----------------
+    // warps w and w + 4 share TMEM lane quarter w % 4; `half` selects keys [128 half, +128) and output features [32 half, +32)
+    const int row = (warp & 3) * 32 + lane;
+    const int half = warp >> 2;
+    const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    float* xmax = reinterpret_cast<float*>(smem + AT_XCH_OFF);      // [2][128]
+    float* xsum = xmax + 2 * AT_BM;                                 // [2][128]
     mbar_wait(smem_u32(bar_s), 0);
     tc_fence_after();
     float mx = -INFINITY;
     uint32_t v[32];
 #pragma unroll 1
-    for (int c = 0; c < AT_BN / 32; ++c) {
+    for (int cc = 0; cc < 4; ++cc) {
+      const int c = half * 4 + cc;
       if (c * 32 >= T) break;
       tmem_ld32(taddr + c * 32, v);
 #pragma unroll
       for (int j = 0; j < 32; ++j)
         if (c * 32 + j < T) mx = fmaxf(mx, __uint_as_float(v[j]));
     }
+    xmax[half * AT_BM + row] = mx;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    mx = fmaxf(mx, xmax[(half ^ 1) * AT_BM + row]);
     const float mxs = mx * scale_log2e;
     float sum = 0.f;
 #pragma unroll 1
-    for (int c = 0; c < AT_BN / 32; ++c) {
+    for (int cc = 0; cc < 4; ++cc) {
+      const int c = half * 4 + cc;
       uint32_t pk[16];
       if (c * 32 < T) {
         tmem_ld32(taddr + c * 32, v);
@@ -127,16 +138,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         *reinterpret_cast<uint4*>(prow + slot * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
       }
     }
+    xsum[half * AT_BM + row] = sum;
     // make the generic-proxy smem writes visible to the tensor core (async proxy), and order the TMEM reads before MMA 2
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     tc_fence_before();
     mbar_arrive(smem_u32(bar_p));
-    mbar_wait(smem_u32(bar_o), 0);
+    mbar_wait(smem_u32(bar_o), 0);   // completes only after all 256 arrivals above, so both partial sums are visible
     tc_fence_after();
-    const float inv = 1.f / sum;
+    const float inv = 1.f / (sum + xsum[(half ^ 1) * AT_BM + row]);
     const int t = q0 + row;
-#pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
+    {
+      const int c = half;
       tmem_ld32(taddr + c * 32, v);
       if (t < T) {
         uint4* o = reinterpret_cast<uint4*>(out + ((int64_t)b * T + t) * E + h * AT_D + c * 32);
@@ -156,7 +168,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == AT_CTRL_WARP) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
   }
@@ -185,7 +197,7 @@ extern "C" int avi_mha_fwd_tc(const void* qkv, void* out, int32_t B, int32_t T, 
   std::call_once(once, [] { attr_err = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AT_SMEM); });
   AVI_REQUIRE(attr_err == cudaSuccess, "avi_mha_fwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
   dim3 grid((T + AT_BM - 1) / AT_BM, H, B);
-  attn_tc_kernel<<<grid, 160, AT_SMEM, (cudaStream_t)stream>>>(map_q, map_kv, (__nv_bfloat16*)out, T, H,
+  attn_tc_kernel<<<grid, AT_THREADS, AT_SMEM, (cudaStream_t)stream>>>(map_q, map_kv, (__nv_bfloat16*)out, T, H,
                                                              scale * 1.4426950408889634f);
   return check_launch("attn_tc");
 }
