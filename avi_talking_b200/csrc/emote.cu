@@ -207,19 +207,20 @@ namespace avi {
 // out[b, t, c] = (a[b, t, c] - n[b, c]) + tpl[b, c]   (offsets from the neutral shape re-attached to the template,
 // FaceFormerDecoder.py:1173-1175 and :690-694), in place allowed
 __global__ void sub_add_rows_kernel(const float* a, const float* __restrict__ n, const float* __restrict__ tpl, float* out, int T, int C,
-                                    int64_t total) {
+                                    int64_t ld, int64_t total) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int c = (int)(idx % C);
-  const int64_t b = idx / ((int64_t)C * T);
-  out[idx] = (a[idx] - n[b * C + c]) + tpl[b * C + c];
+  const int64_t row = idx / C;
+  const int64_t b = row / T;
+  out[row * ld + c] = (a[row * ld + c] - n[b * C + c]) + tpl[b * C + c];
 }
 }  // namespace avi
 
 extern "C" int avi_sub_add_rows(const float* a, const float* neutral, const float* tpl, float* out, int32_t B, int32_t T, int32_t C,
-                                void* stream) {
-  AVI_REQUIRE(B > 0 && T > 0 && C > 0, "avi_sub_add_rows: bad sizes");
+                                int64_t row_stride, void* stream) {
+  AVI_REQUIRE(B > 0 && T > 0 && C > 0 && row_stride >= C, "avi_sub_add_rows: bad sizes");
   const int64_t total = (int64_t)B * T * C;
-  avi::sub_add_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a, neutral, tpl, out, T, C, total);
+  avi::sub_add_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a, neutral, tpl, out, T, C, row_stride, total);
   return avi::check_launch("sub_add_rows");
 }

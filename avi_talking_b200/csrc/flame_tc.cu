@@ -30,7 +30,8 @@ constexpr uint32_t FT_TR_BYTES = 0;
 constexpr uint32_t FT_OFF_COEF = FT_DIRS_BYTES;
 constexpr uint32_t FT_OFF_AS = FT_OFF_COEF + 2 * FT_COEF_BYTES;
 constexpr uint32_t FT_OFF_TR = FT_OFF_AS + 2 * FT_AS_BYTES;
-constexpr uint32_t FT_OFF_BAR = FT_OFF_TR + FT_TR_BYTES;
+constexpr uint32_t FT_OFF_FLAG = FT_OFF_TR + FT_TR_BYTES;            // per-frame bitmask of joints whose transform is not the identity
+constexpr uint32_t FT_OFF_BAR = FT_OFF_FLAG + 2 * FT_NF * 4;
 constexpr uint32_t FT_SMEM = FT_OFF_BAR + 128 + 1024;
 static_assert(FT_SMEM <= 232448, "shared memory budget");
 
@@ -45,6 +46,7 @@ struct FlameTcParams {
   // contraction) is uniform within a tile. One group of F frames = the plain case.
   int frames_per_group, tiles_per_group;
   int64_t template_stride;  // floats between consecutive group templates (0: one global template)
+  int64_t verts_stride;     // floats between consecutive output frames (>= V*3; a multiple of 4 keeps every frame 16-byte aligned)
 };
 
 // first frame / number of valid frames of frame tile ft
@@ -173,7 +175,7 @@ flame_tc_kernel(const __grid_constant__ CUtensorMap map_dirs, const __grid_const
     // 16 warps: TMEM lane quarter = warp % 4 (32 vertices), frame quarter = (warp - 2) / 4 (16 of the tile's 64 frames)
     const int ew = warp - 2;
     const int quarter = warp & 3, fq = ew >> 2;
-    const int V3 = p.V * 3;
+    const int64_t V3 = p.verts_stride;
     int stage = 0;
     uint32_t phase = 0;
     int acc_it = 0;
@@ -185,6 +187,7 @@ flame_tc_kernel(const __grid_constant__ CUtensorMap map_dirs, const __grid_const
       const bool v_ok = v < p.V;
 #pragma unroll
       for (int j = 0; j < FT_NJ; ++j) w[j] = (v < p.V) ? p.lbs_w[(int64_t)v * FT_NJ + j] : 0.f;
+      const float wsum = (w[0] + w[1]) + (w[2] + w[3]) + w[4];
 #pragma unroll
       for (int c = 0; c < 3; ++c) vtp[c] = (v < p.V) ? p.v_template[(int64_t)v * 3 + c] : 0.f;
       const int ft0 = chunk * FT_CHUNK_TILES;
@@ -201,6 +204,32 @@ flame_tc_kernel(const __grid_constant__ CUtensorMap map_dirs, const __grid_const
           vtp[2] = __ldg(tp + 2);
         }
         mbar_wait(smem_u32(&cf_full[stage]), phase);   // joint transforms of this tile are in smem
+        // Joints whose relative transform is the identity contribute w_j * I: T = (sum_j w_j) I + sum_{active j} w_j (A_j - I).
+        // On this path only the jaw moves (global / neck / eye poses are zero: faceformer_disentangle.py:425-433, Preprocessors.py:80),
+        // so 4 of the 5 joints drop out: 12 FMAs and 3 shared loads per vertex-frame instead of 60 and 15.
+        uint32_t* flags = reinterpret_cast<uint32_t*>(smem + FT_OFF_FLAG) + stage * FT_NF;
+        {
+          const int etid = threadIdx.x - 64;
+          if (etid < FT_NF) {
+            uint32_t m = 0;
+            if (etid < tnfr) {
+              const uint32_t Af = smem_u32(smem + FT_OFF_AS + stage * FT_AS_BYTES) + etid * (FT_NJ * 12 * 4);
+#pragma unroll
+              for (int j = 0; j < FT_NJ; ++j) {
+                float d = 0.f;
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                  const float4 a = lds128f(Af + (j * 12 + q * 4) * 4);
+                  d = fmaxf(d, fmaxf(fmaxf(fabsf(a.x - (q == 0 ? 1.f : 0.f)), fabsf(a.y - (q == 1 ? 1.f : 0.f))),
+                                     fmaxf(fabsf(a.z - (q == 2 ? 1.f : 0.f)), fabsf(a.w))));
+                }
+                if (d > 1e-7f) m |= 1u << j;
+              }
+            }
+            flags[etid] = m;
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(FT_EPI_WARPS * 32) : "memory");
+        }
         mbar_wait(smem_u32(&tmem_full[as]), aph);
         tc_fence_after();
         uint32_t vx[16], vy[16], vz[16];
@@ -215,18 +244,21 @@ flame_tc_kernel(const __grid_constant__ CUtensorMap map_dirs, const __grid_const
 #pragma unroll
         for (int n = 0; n < 16; ++n) {
           if (fbase + n < flimit) {  // warp-uniform
+            const uint32_t active = flags[fq * 16 + n];   // warp-uniform
             float T[12];
 #pragma unroll
-            for (int e = 0; e < 12; ++e) T[e] = 0.f;
+            for (int e = 0; e < 12; ++e) T[e] = (e == 0 || e == 5 || e == 10) ? wsum : 0.f;
 #pragma unroll
             for (int j = 0; j < FT_NJ; ++j) {
+              if (active & (1u << j)) {
 #pragma unroll
-              for (int q = 0; q < 3; ++q) {
-                const float4 a = lds128f(As + (n * (FT_NJ * 12) + j * 12 + q * 4) * 4);
-                T[q * 4 + 0] = fmaf(w[j], a.x, T[q * 4 + 0]);
-                T[q * 4 + 1] = fmaf(w[j], a.y, T[q * 4 + 1]);
-                T[q * 4 + 2] = fmaf(w[j], a.z, T[q * 4 + 2]);
-                T[q * 4 + 3] = fmaf(w[j], a.w, T[q * 4 + 3]);
+                for (int q = 0; q < 3; ++q) {
+                  const float4 a = lds128f(As + (n * (FT_NJ * 12) + j * 12 + q * 4) * 4);
+                  T[q * 4 + 0] = fmaf(w[j], a.x - (q == 0 ? 1.f : 0.f), T[q * 4 + 0]);
+                  T[q * 4 + 1] = fmaf(w[j], a.y - (q == 1 ? 1.f : 0.f), T[q * 4 + 1]);
+                  T[q * 4 + 2] = fmaf(w[j], a.z - (q == 2 ? 1.f : 0.f), T[q * 4 + 2]);
+                  T[q * 4 + 3] = fmaf(w[j], a.w, T[q * 4 + 3]);
+                }
               }
             }
             const float px = __uint_as_float(vx[n]) + vtp[0], py = __uint_as_float(vy[n]) + vtp[1], pz = __uint_as_float(vz[n]) + vtp[2];
@@ -314,9 +346,10 @@ extern "C" int avi_flame_pack_tc(const float* dirs32, void* dirs16, int32_t V, i
 // floats apart; 0 = one global template); the tensor-core contraction runs over coefficient columns [coef_col0, coef_col0 + n_dirs)
 // of coef32 against the n_dirs direction rows packed by avi_flame_pack_tc_rows.
 extern "C" int avi_flame_blend_skin_tc_grouped(const float* coef32, const float* A, const void* dirs16, const float* lbs_weights,
-                                               const float* templates, int64_t template_stride, void* coef16, float* verts, int32_t F,
-                                               int32_t V, int32_t n_dirs, int32_t coef_col0, int32_t K_pad32, int32_t V_pad,
-                                               int32_t frames_per_group, void* stream) {
+                                               const float* templates, int64_t template_stride, void* coef16, float* verts,
+                                               int64_t verts_frame_stride, int32_t F, int32_t V, int32_t n_dirs, int32_t coef_col0,
+                                               int32_t K_pad32, int32_t V_pad, int32_t frames_per_group, void* stream) {
+  AVI_REQUIRE(verts_frame_stride >= (int64_t)V * 3, "avi_flame_blend_skin_tc: verts_frame_stride smaller than V*3");
   AVI_REQUIRE(F > 0 && V > 0 && n_dirs > 0 && n_dirs <= FT_K && V_pad % FT_BM == 0 && V_pad >= V && coef_col0 >= 0 &&
                   coef_col0 + n_dirs <= K_pad32,
               "avi_flame_blend_skin_tc: unsupported shape");
@@ -352,6 +385,7 @@ extern "C" int avi_flame_blend_skin_tc_grouped(const float* coef32, const float*
   p.frames_per_group = frames_per_group;
   p.tiles_per_group = (frames_per_group + FT_NF - 1) / FT_NF;
   p.template_stride = template_stride;
+  p.verts_stride = verts_frame_stride;
   p.n_ftiles = (F / frames_per_group) * p.tiles_per_group;
   const int n_chunks = (p.n_ftiles + FT_CHUNK_TILES - 1) / FT_CHUNK_TILES;
   p.n_items = p.n_vt * n_chunks;
@@ -371,6 +405,6 @@ extern "C" int avi_flame_blend_skin_tc(const float* coef32, const float* A, cons
                                        const float* v_template, void* coef16, float* verts, int32_t F, int32_t V, int32_t NB,
                                        int32_t K_pad32, int32_t V_pad, void* stream) {
   AVI_REQUIRE(NB + 36 <= FT_K, "avi_flame_blend_skin_tc: NB + 36 must be <= %d", FT_K);
-  return avi_flame_blend_skin_tc_grouped(coef32, A, dirs16, lbs_weights, v_template, 0, coef16, verts, F, V, NB + 36, 0, K_pad32, V_pad, F,
-                                         stream);
+  return avi_flame_blend_skin_tc_grouped(coef32, A, dirs16, lbs_weights, v_template, 0, coef16, verts, (int64_t)V * 3, F, V, NB + 36, 0,
+                                         K_pad32, V_pad, F, stream);
 }

@@ -40,6 +40,15 @@ constexpr uint32_t P2_SMEM_BYTES = P2_OFF_BAR + 256 /*barriers*/;
 static_assert(P2_SMEM_BYTES <= 232448, "shared memory budget");
 static_assert(2 * P2_STAGES + 5 <= 32, "barrier block");
 
+#ifdef AVI_GEMM_TIMELINE
+// Build-time instrumentation (python __graft_entry__.py with AVI_NVCC_EXTRA=-DAVI_GEMM_TIMELINE): clock64() stamps of CTA 0's
+// roles for the first tiles, read back with avi_debug_timeline(). Not compiled into the product library.
+__device__ long long g_timeline[3][64][8];
+#define TL(role, tile, slot) do { if (blockIdx.x == 0 && (tile) < 64) g_timeline[role][tile][slot] = clock64(); } while (0)
+#else
+#define TL(role, tile, slot) do { } while (0)
+#endif
+
 struct Tc2Params {
   const float* bias;
   const float* residual;
@@ -112,8 +121,10 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         // tap / phase / super-row / channel-block counters advance incrementally: this single thread paces the whole pipeline,
         // and four runtime integer divisions per k-block cost about as much as the MMAs of that k-block
         int kin = 0, ph = 0, sr = 0;
+        TL(0, (t - pair) / num_pairs, 0);
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          if (kb == 0) TL(0, (t - pair) / num_pairs, 1);
           const uint32_t fb_local = smem_u32(&full_bar[stage]);
           if (rank == 0) mbar_expect_tx(fb_local, 2 * P2_STAGE_BYTES);
           tma_load_4d_pair(smem_u32(smem_a + stage * P2_A_BYTES), &map_a, full_leader + stage * 8, kin * P2_BK, ph, row0 + sr, b);
@@ -143,11 +154,15 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       for (int t = pair; t < p.total_tiles; t += num_pairs, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
+        TL(1, it, 0);
         mbar_wait(smem_u32(&tmem_empty[as]), aphase ^ 1);
+        TL(1, it, 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * P2_BN;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(smem_u32(&full_bar[stage]), phase);
+          if (kb == 0) TL(1, it, 2);
+          if (kb == p.num_kb - 1) TL(1, it, 3);
           tc_fence_after();
           const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + stage * P2_A_BYTES));
           const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + stage * P2_B_BYTES));
@@ -161,6 +176,7 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
           }
         }
         umma_commit_pair(smem_u32(&tmem_full[as]), 3);  // accumulator complete -> epilogues of both CTAs
+        TL(1, it, 4);
       }
     }
   } else {
@@ -176,6 +192,7 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     const uint32_t tile = smem_u32(trans) + ew * P2_TRANS_WARP;
     const bool fast_bf16 = p.vec_ok && p.c_dtype == AVI_DT_BF16 && p.C2 == nullptr && p.residual == nullptr;
     const bool fast_f32 = p.vec_ok && p.c_dtype == AVI_DT_F32 && p.C2 == nullptr;
+    const bool ragged_f32 = !p.vec_ok && p.c_dtype == AVI_DT_F32 && p.C2 == nullptr && p.residual == nullptr;
     const uint32_t te_leader0 = mapa_shared(smem_u32(&tmem_empty[0]), 0);
     const uint32_t te_leader1 = mapa_shared(smem_u32(&tmem_empty[1]), 0);
     int it = 0;
@@ -187,12 +204,16 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       const int b = mt / p.m_tiles, m_blk = mt % p.m_tiles;
       const int n0 = n_blk * P2_BN;
       const uint32_t sbias_a = smem_u32(sbias) + as * (P2_BN * 4);
+      if (ew == 0 && lane == 0) TL(2, it, 0);
       if (etid < P2_BN) {
         const int n = n0 + etid;
         sts32(sbias_a + etid * 4, __float_as_uint((p.bias != nullptr && n < p.N) ? __ldg(p.bias + n) : 0.f));
       }
       asm volatile("bar.sync 1, %0;" ::"n"(P2_EPI_THREADS) : "memory");
-      mbar_wait(smem_u32(&tmem_full[as]), aphase);
+      if (ew == 0 && lane == 0) TL(2, it, 1);
+      if (lane == 0) mbar_wait(smem_u32(&tmem_full[as]), aphase);   // one polling lane per warp: 16 pollers on the barrier, not 512
+      __syncwarp();
+      if (ew == 0 && lane == 0) TL(2, it, 2);
       tc_fence_after();
       const int row_base = m_blk * (2 * P2_BM) + (int)rank * P2_BM + quarter * 32;
       const int rows_valid = p.rows - row_base;  // may be <= 0 or > 32
@@ -205,6 +226,7 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         if (n_base >= p.N || rows_valid <= 0) break;  // warp-uniform
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * P2_BN + col0), v);
+        if (ew == 0 && lane == 0) TL(2, it, 3 + 2 * ch);
         float f[32];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -281,8 +303,37 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             }
             __syncwarp();
           }
+        } else if (ragged_f32) {
+          // fp32 rows that are only 4-byte aligned (the 15069-wide vertex rows), no residual, no second copy: half a warp per row,
+          // 64-byte row segments; pointers advance incrementally and the staging addresses are precomputed, so one pair of rows
+          // costs one shared load, one store and one pointer update per lane (this path is HBM-write bound, not issue bound)
+          const int c = lane & 15, rsub = lane >> 4;
+          const uint32_t rd_base = tile + (rsub * 16 + (c & 3)) * 4;
+          uint32_t xo[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) xo[k] = 16u * (uint32_t)((c >> 2) ^ k);
+          const int64_t step2 = 2 * p.c_ld;
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+            for (int gg = 0; gg < 4; ++gg)
+              sts128(wr_row + 16 * (gg ^ wr_sw), __float_as_uint(f[16 * hh + 4 * gg]), __float_as_uint(f[16 * hh + 4 * gg + 1]),
+                     __float_as_uint(f[16 * hh + 4 * gg + 2]), __float_as_uint(f[16 * hh + 4 * gg + 3]));
+            __syncwarp();
+            const bool col_ok = n_base + 16 * hh + c < p.N;
+            float* cp = reinterpret_cast<float*>(p.C) + c_row0 + n_base + 16 * hh + c + (int64_t)rsub * p.c_ld;
+            float val[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) val[u] = __uint_as_float(lds32(rd_base + u * 128 + xo[u & 3]));
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+              if (col_ok && 2 * u + rsub < rows_valid) *cp = val[u];
+              cp += step2;
+            }
+            __syncwarp();
+          }
         } else {
-          // generic (ragged / unaligned rows, second output copy): half a warp per row, 64-byte row segments, scalar accesses
+          // generic (ragged / unaligned rows, residual, second output copy): half a warp per row, 64-byte row segments, scalar accesses
           float* cf = nullptr;
           __nv_bfloat16* cb = nullptr;
           if (p.c_dtype == AVI_DT_F32) {
@@ -328,6 +379,7 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
           }
         }
       }
+      if (ew == 0 && lane == 0) TL(2, it, 7);
       // release the accumulator stage back to the MMA warp of the leader CTA
       tc_fence_before();
       __syncwarp();
@@ -364,6 +416,12 @@ static const char* tc2_check(const AviGemmArgs* a) {
 using namespace avi;
 
 extern "C" int avi_gemm_bf16_tc_v1(const AviGemmArgs* a, void* stream);
+
+#ifdef AVI_GEMM_TIMELINE
+extern "C" int avi_debug_timeline(long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, g_timeline, sizeof(long long) * 3 * 64 * 8) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 extern "C" int avi_gemm_bf16_tc_supported(const AviGemmArgs* a) { return tc2_check(a) == nullptr ? 1 : 0; }
 

@@ -199,14 +199,15 @@ class Faceformer(nn.Module):
         """vertice_map_r over all rows + template (:473,481), one GEMM with bias' = b_r + template."""
         B, T, fd = hidden.shape
         bias = (P["vr_b"] + template.reshape(-1).float()).contiguous()
-        out = torch.empty((B, T, self.args.vertice_dim), dtype=torch.float32, device=hidden.device)
+        vd = self.args.vertice_dim
+        rows = ops.empty_rows(B * T, vd, hidden.device)      # 16-byte aligned row stride (15072 floats), returned as a [.., 15069] view
         if self.precision == "bf16" and fd % 64 == 0:
             a = ops.split_bf16x3(hidden.reshape(B * T, fd))
-            ops.gemm(a, P["vr_w16x3"], bias, out, rows=B * T, N=self.args.vertice_dim, K=3 * fd, a_rows_alloc=B * T,
-                     algorithmic_flops=2.0 * B * T * self.args.vertice_dim * fd)
+            ops.gemm(a, P["vr_w16x3"], bias, rows, rows=B * T, N=vd, K=3 * fd, a_rows_alloc=B * T, c_ld=rows.stride(0),
+                     algorithmic_flops=2.0 * B * T * vd * fd)
         else:
-            ops.gemm(hidden.reshape(B * T, fd), P["vr_w32"], bias, out, rows=B * T, N=self.args.vertice_dim, K=fd)
-        return out
+            ops.gemm(hidden.reshape(B * T, fd), P["vr_w32"], bias, rows, rows=B * T, N=vd, K=fd, c_ld=rows.stride(0))
+        return rows.view(B, T, vd)
 
     @torch.no_grad()
     def forward_ff(self, gt_verts, hidden_states, obj_embedding, frame_num, teacher_forcing):

@@ -55,9 +55,10 @@ def _run(cache, precision, betas, full_pose, shapedirs, posedirs, v_template, J_
     """precision 'bf16' -> tcgen05 blend (fp16 operands, ~1e-5 m); 'fp32' -> CUDA-core blend (exact to ~1e-7 m)."""
     dirs, jreg = cache.get(shapedirs, posedirs, v_template, J_regressor)
     V, nb = shapedirs.shape[0], shapedirs.shape[2]
+    padded = kw.pop("padded", False)   # 16-byte aligned frame stride (vertices-only callers; the landmark gathers want dense frames)
     if precision == "bf16" and cache.dirs16 is not None:
         return ops.flame_lbs_tc(betas, full_pose, cache.dirs16, jreg, lbs_weights.contiguous(), v_template.contiguous(), V, nb,
-                                _k_pad(nb), **kw)
+                                _k_pad(nb), padded=padded, **kw)
     return ops.flame_lbs(betas, full_pose, dirs, jreg, lbs_weights.contiguous(), V, nb, _k_pad(nb), **kw)
 
 
@@ -140,7 +141,7 @@ class FLAME(nn.Module):
             eye_pose_params = self.eye_pose.expand(batch_size, -1)
         return torch.cat([pose_params[:, :3], self.neck_pose.expand(batch_size, -1), pose_params[:, 3:], eye_pose_params], dim=1)
 
-    def _run_lbs(self, shape_params, expression_params, pose_params, eye_pose_params, want_rows=True):
+    def _run_lbs(self, shape_params, expression_params, pose_params, eye_pose_params, want_rows=True, padded=False):
         B = shape_params.shape[0]
         if expression_params is None:
             expression_params = torch.zeros(B, self.cfg.n_exp, device=shape_params.device)
@@ -150,7 +151,7 @@ class FLAME(nn.Module):
         if betas.shape[1] != nb:
             raise ValueError(f"expected {nb} shape+expression coefficients, got {betas.shape[1]}")
         verts, _, rows = _run(self._pack, self.precision, betas, full_pose, self.shapedirs, self.posedirs, self.v_template,
-                              self.J_regressor, self.lbs_weights, want_dyn_rows=want_rows)
+                              self.J_regressor, self.lbs_weights, want_dyn_rows=want_rows, padded=padded)
         return verts, rows
 
     def _landmarks(self, verts, rows):
@@ -171,7 +172,7 @@ class FLAME(nn.Module):
     @torch.no_grad()
     def vertices_only(self, shape_params, expression_params=None, pose_params=None, eye_pose_params=None):
         """The mesh without the landmark gathers (what the audio->vertex hot path consumes)."""
-        return self._run_lbs(shape_params, expression_params, pose_params, eye_pose_params, want_rows=False)[0]
+        return self._run_lbs(shape_params, expression_params, pose_params, eye_pose_params, want_rows=False, padded=True)[0]
 
     @torch.no_grad()
     def vertices_sequence(self, shape, exp, pose):

@@ -247,6 +247,21 @@ def ff_biased_attn(qkv, B, T, fd, period):
     return out
 
 
+# Vertex rows are 15069 floats = 60276 bytes: only 4-byte aligned, which costs the HBM-write-bound kernels ~40 % (measured:
+# profiles/r1/vhead_align_probe.txt). Outputs are therefore allocated with the row stride rounded up to a multiple of 4 floats and
+# returned as a [..., 15069] view of that buffer (`.contiguous()` gives the dense layout).
+PAD_VERTEX_ROWS = True
+
+
+def padded_cols(n: int) -> int:
+    return ((n + 3) // 4) * 4 if PAD_VERTEX_ROWS else n
+
+
+def empty_rows(rows: int, cols: int, device) -> torch.Tensor:
+    """fp32 [rows, cols] whose row stride is padded to 16 bytes (a view of a [rows, padded] buffer)."""
+    return torch.empty((rows, padded_cols(cols)), dtype=torch.float32, device=device)[:, :cols]
+
+
 def flame_pack(shapedirs, posedirs, v_template, J_regressor, K_pad):
     _need_cuda(shapedirs)
     V, _, NB = shapedirs.shape
@@ -285,7 +300,8 @@ def flame_pack_tc(dirs32, V, NB):
     return dirs16
 
 
-def flame_lbs_tc(betas, full_pose, dirs16, jreg, lbs_weights, v_template, V, NB, K_pad, want_joints=False, want_dyn_rows=False):
+def flame_lbs_tc(betas, full_pose, dirs16, jreg, lbs_weights, v_template, V, NB, K_pad, want_joints=False, want_dyn_rows=False,
+                 padded=False):
     """Same results contract as flame_lbs, blend + skinning on the tcgen05 path."""
     _need_cuda(betas, full_pose)
     F = betas.shape[0]
@@ -293,16 +309,19 @@ def flame_lbs_tc(betas, full_pose, dirs16, jreg, lbs_weights, v_template, V, NB,
     coef = torch.empty((F, K_pad), dtype=torch.float32, device=dev)
     coef16 = torch.empty((F, 192), dtype=torch.float16, device=dev)
     A = torch.empty((F, 5, 12), dtype=torch.float32, device=dev)
-    verts = torch.empty((F, V, 3), dtype=torch.float32, device=dev)
+    vrows = empty_rows(F, V * 3, dev) if padded else torch.empty((F, V * 3), dtype=torch.float32, device=dev)
+    verts = vrows.view(F, V, 3)
     joints = torch.empty((F, 5, 3), dtype=torch.float32, device=dev) if want_joints else None
     rows = torch.empty((F,), dtype=torch.int32, device=dev) if want_dyn_rows else None
     lib = _lib.load()
     with _timed("flame_lbs", float(F) * (V * 12 + 4 * (NB + 6))):
         _lib.check(lib.avi_flame_prologue(_ptr(betas), _ptr(full_pose), _ptr(jreg), _ptr(coef), _ptr(A), _ptr(joints), _ptr(rows),
                                           C.c_int32(F), C.c_int32(NB), C.c_int32(K_pad), _stream()), "avi_flame_prologue")
-        _lib.check(lib.avi_flame_blend_skin_tc(_ptr(coef), _ptr(A), _ptr(dirs16), _ptr(lbs_weights), _ptr(v_template), _ptr(coef16),
-                                               _ptr(verts), C.c_int32(F), C.c_int32(V), C.c_int32(NB), C.c_int32(K_pad),
-                                               C.c_int32(dirs16.shape[1]), _stream()), "avi_flame_blend_skin_tc")
+        _lib.check(lib.avi_flame_blend_skin_tc_grouped(_ptr(coef), _ptr(A), _ptr(dirs16), _ptr(lbs_weights), _ptr(v_template),
+                                                       C.c_int64(0), _ptr(coef16), _ptr(verts), C.c_int64(vrows.stride(0)), C.c_int32(F),
+                                                       C.c_int32(V), C.c_int32(NB + 36), C.c_int32(0), C.c_int32(K_pad),
+                                                       C.c_int32(dirs16.shape[1]), C.c_int32(F), _stream()),
+                   "avi_flame_blend_skin_tc_grouped")
     return verts, joints, rows
 
 
@@ -409,13 +428,13 @@ def lrelu_bn_repeat(x, bn_scale, bn_shift, B, L, repeat, slope=0.2):
 
 
 def sub_add_rows_(a, neutral, tpl):
-    """In place: a[b, t, :] = (a[b, t, :] - neutral[b, :]) + tpl[b, :]."""
+    """In place: a[b, t, :] = (a[b, t, :] - neutral[b, :]) + tpl[b, :]; `a` may have a padded row stride."""
     _need_cuda(a, neutral, tpl)
     B, T, Cc = a.shape
-    assert a.is_contiguous() and neutral.is_contiguous() and tpl.is_contiguous() and a.dtype == torch.float32
+    assert a.dtype == torch.float32 and a.stride(2) == 1 and a.stride(0) == T * a.stride(1) and neutral.is_contiguous() and tpl.is_contiguous()
     with _timed("sub_add_rows", float(a.numel() * 8)):
         _lib.check(_lib.load().avi_sub_add_rows(_ptr(a), _ptr(neutral), _ptr(tpl), _ptr(a), C.c_int32(B), C.c_int32(T), C.c_int32(Cc),
-                                                _stream()), "avi_sub_add_rows")
+                                                C.c_int64(a.stride(1)), _stream()), "avi_sub_add_rows")
     return a
 
 
@@ -436,15 +455,16 @@ def flame_lbs_tc_grouped(betas, full_pose, dirs16_exp, jreg, lbs_weights, templa
     coef = torch.empty((F, K_pad), dtype=torch.float32, device=dev)
     coef16 = torch.empty((F, 192), dtype=torch.float16, device=dev)
     A = torch.empty((F, 5, 12), dtype=torch.float32, device=dev)
-    verts = torch.empty((F, V, 3), dtype=torch.float32, device=dev)
+    vrows = empty_rows(F, V * 3, dev)
+    verts = vrows.view(F, V, 3)
     lib = _lib.load()
     n_dirs = NB - n_shape + 36
     with _timed("flame_lbs", float(F) * (V * 12 + 4 * (NB - n_shape + 6))):
         _lib.check(lib.avi_flame_prologue(_ptr(betas), _ptr(full_pose), _ptr(jreg), _ptr(coef), _ptr(A), None, None,
                                           C.c_int32(F), C.c_int32(NB), C.c_int32(K_pad), _stream()), "avi_flame_prologue")
         _lib.check(lib.avi_flame_blend_skin_tc_grouped(_ptr(coef), _ptr(A), _ptr(dirs16_exp), _ptr(lbs_weights), _ptr(templates),
-                                                       C.c_int64(V * 3), _ptr(coef16), _ptr(verts), C.c_int32(F), C.c_int32(V),
-                                                       C.c_int32(n_dirs), C.c_int32(n_shape), C.c_int32(K_pad),
+                                                       C.c_int64(V * 3), _ptr(coef16), _ptr(verts), C.c_int64(vrows.stride(0)),
+                                                       C.c_int32(F), C.c_int32(V), C.c_int32(n_dirs), C.c_int32(n_shape), C.c_int32(K_pad),
                                                        C.c_int32(dirs16_exp.shape[1]), C.c_int32(frames_per_group), _stream()),
                    "avi_flame_blend_skin_tc_grouped")
     return verts

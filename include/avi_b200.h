@@ -189,7 +189,8 @@ int avi_flame_blend_skin_tc(const float* coef32, const float* A, const void* dir
  * [coef_col0, coef_col0 + n_dirs) of coef32 (expression | pose feature) against direction rows [row0, row0 + n_dirs) of dirs32. */
 int avi_flame_pack_tc_rows(const float* dirs32, void* dirs16, int32_t V, int32_t row0, int32_t n_dirs, int32_t V_pad, void* stream);
 int avi_flame_blend_skin_tc_grouped(const float* coef32, const float* A, const void* dirs16, const float* lbs_weights,
-                                    const float* templates, int64_t template_stride, void* coef16, float* verts, int32_t F, int32_t V,
+                                    const float* templates, int64_t template_stride, void* coef16, float* verts,
+                                    int64_t verts_frame_stride /* floats between output frames, >= V*3 */, int32_t F, int32_t V,
                                     int32_t n_dirs, int32_t coef_col0, int32_t K_pad32, int32_t V_pad, int32_t frames_per_group,
                                     void* stream);
 
@@ -262,8 +263,9 @@ int avi_lrelu_bn_repeat(const float* x, const float* bn_scale, const float* bn_s
                         int32_t repeat, float slope, void* stream);
 
 /* out[b, t, :] = (a[b, t, :] - neutral[b, :]) + tpl[b, :]  (vertex offsets from the neutral shape re-attached to the template,
- * FaceFormerDecoder.py:1173-1175,690-694); out may alias a */
-int avi_sub_add_rows(const float* a, const float* neutral, const float* tpl, float* out, int32_t B, int32_t T, int32_t C, void* stream);
+ * FaceFormerDecoder.py:1173-1175,690-694); a / out rows are row_stride floats apart (>= C); out may alias a */
+int avi_sub_add_rows(const float* a, const float* neutral, const float* tpl, float* out, int32_t B, int32_t T, int32_t C,
+                     int64_t row_stride, void* stream);
 
 #ifdef __cplusplus
 }
