@@ -1,0 +1,416 @@
+// Backward / optimizer kernels of the teacher-forced FaceFormer-vert training step (BASELINE configs[4];
+// models/faceformer_vert.py:360-482: wav2vec2 encoder (feature extractor frozen, :154) -> audio_feature_map -> teacher-forced
+// nn.TransformerDecoderLayer -> vertice_map_r -> MSE x 10). The dense contractions of the backward pass (dX = dY W, dW = dY^T X) run
+// on the tcgen05 GEMM of gemm_tc2.cu after avi_transpose_cast_bf16 has put the contraction dimension innermost; this file holds
+// everything else: LayerNorm / GELU / ReLU / softmax-attention backward, bias column sums, the positional-conv weight gradient
+// with its weight-norm chain rule, the loss and Adam. Clips are short (T ~ 120 frames), so these are small fp32 kernels.
+#include "common.cuh"
+
+namespace avi {
+
+// ------------------------------------------------------------------------------------------------ layout helpers
+// dst[c][r] = bf16(src[r][c]) for r < R, zero for R <= r < R_pad   (src fp32 [R, C] with row stride src_ld)
+__global__ void transpose_cast_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int R, int C, int64_t src_ld, int R_pad) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < R && c < C) ? src[(int64_t)r * src_ld + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < C && r < R_pad) dst[(int64_t)c * R_pad + r] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+  }
+}
+
+// out[n] (+)= sum_r x[r][n]
+__global__ void colsum_kernel(const float* __restrict__ x, float* __restrict__ out, int R, int N, int64_t ld, int accumulate) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float s = 0.f;
+  for (int r = 0; r < R; ++r) s += x[(int64_t)r * ld + n];
+  out[n] = accumulate ? out[n] + s : s;
+}
+
+// ------------------------------------------------------------------------------------------------ activations
+// mode 1 GELU (exact erf), 2 ReLU. fwd: out = act(pre) (fp32 and/or bf16); bwd: dpre = dout * act'(pre)
+__global__ void act_fwd_kernel(const float* __restrict__ pre, float* __restrict__ o32, __nv_bfloat16* __restrict__ o16, int64_t n, int mode) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = pre[i];
+  const float y = mode == 1 ? gelu_erf(x) : fmaxf(x, 0.f);
+  if (o32) o32[i] = y;
+  if (o16) o16[i] = __float2bfloat16_rn(y);
+}
+__global__ void act_bwd_kernel(const float* __restrict__ pre, const float* __restrict__ dout, float* __restrict__ dpre, int64_t n, int mode) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = pre[i];
+  float g;
+  if (mode == 1) {
+    const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752440f));
+    g = cdf + x * 0.3989422804014327f * expf(-0.5f * x * x);
+  } else {
+    g = x > 0.f ? 1.f : 0.f;
+  }
+  dpre[i] = dout[i] * g;
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm backward
+// y = (x - mean) * rstd * w + b over the last dim C (<= 1024). One warp per row:
+//   dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * w ;  dw += sum_rows dy * xhat ; db += sum_rows dy  (atomics)
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                            const float* __restrict__ dy, float* __restrict__ dx, float* __restrict__ dw,
+                                                            float* __restrict__ db, int64_t rows, int C, float eps) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float v[32], g[32];
+  float s = 0.f;
+#pragma unroll
+  for (int u = 0; u < 32; ++u) {
+    const int c = lane + 32 * u;
+    v[u] = c < C ? x[row * C + c] : 0.f;
+    s += v[u];
+  }
+  const float mean = warp_sum(s) / C;
+  float q = 0.f;
+#pragma unroll
+  for (int u = 0; u < 32; ++u) {
+    const int c = lane + 32 * u;
+    if (c < C) q += (v[u] - mean) * (v[u] - mean);
+  }
+  const float rstd = rsqrtf(warp_sum(q) / C + eps);
+  float sg = 0.f, sgx = 0.f;
+#pragma unroll
+  for (int u = 0; u < 32; ++u) {
+    const int c = lane + 32 * u;
+    g[u] = 0.f;
+    if (c < C) {
+      const float xh = (v[u] - mean) * rstd;
+      const float d = dy[row * C + c];
+      g[u] = d * w[c];
+      sg += g[u];
+      sgx += g[u] * xh;
+      if (dw) atomicAdd(dw + c, d * xh);
+      if (db) atomicAdd(db + c, d);
+      v[u] = xh;
+    }
+  }
+  sg = warp_sum(sg) / C;
+  sgx = warp_sum(sgx) / C;
+  if (dx) {
+#pragma unroll
+    for (int u = 0; u < 32; ++u) {
+      const int c = lane + 32 * u;
+      if (c < C) dx[row * C + c] = rstd * (g[u] - sg - v[u] * sgx);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ attention (training, T <= 128)
+// qkv fp32 [B, T, 3*H*D] (q | k | v); bias modes: 0 none, 1 FaceFormer biased causal mask (-slope_h * floor((i-j)/period), j <= i).
+// forward keeps the probabilities P [B, H, T, T] for the backward pass. One CTA per (head, clip).
+__device__ __forceinline__ float ff_slope(int h) { return exp2f(-2.f * (float)(h + 1)); }   // 4 heads: 2^-2, 2^-4, 2^-6, 2^-8
+
+__global__ void __launch_bounds__(256) attn_train_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ out, float* __restrict__ P,
+                                                             int T, int H, int D, float scale, int bias_mode, int period) {
+  extern __shared__ float sm[];
+  float* ks = sm;              // [T][D+1]
+  float* vs = ks + T * (D + 1);  // [T][D]
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int E = H * D;
+  const float* base = qkv + (int64_t)b * T * 3 * E;
+  for (int i = threadIdx.x; i < T * D; i += blockDim.x) {
+    const int t = i / D, d = i % D;
+    ks[t * (D + 1) + d] = base[(int64_t)t * 3 * E + E + h * D + d];
+    vs[t * D + d] = base[(int64_t)t * 3 * E + 2 * E + h * D + d];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* Pb = P + ((int64_t)b * H + h) * T * T;
+  for (int i = warp; i < T; i += blockDim.x >> 5) {
+    const float* q = base + (int64_t)i * 3 * E + h * D;
+    float s[4];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = lane + 32 * u;
+      s[u] = -INFINITY;
+      if (j < T && !(bias_mode == 1 && j > i)) {
+        float a = 0.f;
+        for (int d = 0; d < D; ++d) a = fmaf(q[d], ks[j * (D + 1) + d], a);
+        a *= scale;
+        if (bias_mode == 1) a -= ff_slope(h) * (float)((i - j) / period);
+        s[u] = a;
+      }
+      mx = fmaxf(mx, s[u]);
+    }
+    mx = warp_max(mx);
+    float den = 0.f;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      s[u] = (s[u] == -INFINITY) ? 0.f : expf(s[u] - mx);
+      den += s[u];
+    }
+    den = warp_sum(den);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = lane + 32 * u;
+      if (j < T) Pb[(int64_t)i * T + j] = s[u] / den;
+    }
+    __syncwarp();
+    for (int d = lane; d < D; d += 32) {
+      float a = 0.f;
+      for (int j = 0; j < T; ++j) a = fmaf(Pb[(int64_t)i * T + j], vs[j * D + d], a);
+      out[((int64_t)b * T + i) * E + h * D + d] = a;
+    }
+  }
+}
+
+// dqkv from dout: dV = P^T dO ; dP = dO V^T ; dS = P * (dP - rowsum(dP * P)) ; dQ = scale dS K ; dK = scale dS^T Q
+__global__ void __launch_bounds__(256) attn_train_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ P,
+                                                             const float* __restrict__ dout, float* __restrict__ dqkv, float* __restrict__ dS,
+                                                             int T, int H, int D, float scale) {
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int E = H * D;
+  const float* base = qkv + (int64_t)b * T * 3 * E;
+  float* dbase = dqkv + (int64_t)b * T * 3 * E;
+  const float* Pb = P + ((int64_t)b * H + h) * T * T;
+  float* dSb = dS + ((int64_t)b * H + h) * T * T;
+  const float* dO = dout + (int64_t)b * T * E + h * D;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  // pass 1: dS rows (one warp per query row)
+  for (int i = warp; i < T; i += nw) {
+    float dp[4];
+    float dot = 0.f;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = lane + 32 * u;
+      dp[u] = 0.f;
+      if (j < T) {
+        float a = 0.f;
+        for (int d = 0; d < D; ++d) a = fmaf(dO[(int64_t)i * E + d], base[(int64_t)j * 3 * E + 2 * E + h * D + d], a);
+        dp[u] = a;
+        dot += a * Pb[(int64_t)i * T + j];
+      }
+    }
+    dot = warp_sum(dot);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = lane + 32 * u;
+      if (j < T) dSb[(int64_t)i * T + j] = Pb[(int64_t)i * T + j] * (dp[u] - dot);
+    }
+  }
+  __syncthreads();
+  // pass 2: dQ[i,d] = scale sum_j dS[i,j] K[j,d] ; dK[j,d] = scale sum_i dS[i,j] Q[i,d] ; dV[j,d] = sum_i P[i,j] dO[i,d]
+  for (int idx = threadIdx.x; idx < T * D; idx += blockDim.x) {
+    const int t = idx / D, d = idx % D;
+    float aq = 0.f, ak = 0.f, av = 0.f;
+    for (int j = 0; j < T; ++j) {
+      aq = fmaf(dSb[(int64_t)t * T + j], base[(int64_t)j * 3 * E + E + h * D + d], aq);
+      ak = fmaf(dSb[(int64_t)j * T + t], base[(int64_t)j * 3 * E + h * D + d], ak);
+      av = fmaf(Pb[(int64_t)j * T + t], dO[(int64_t)j * E + d], av);
+    }
+    dbase[(int64_t)t * 3 * E + h * D + d] = aq * scale;
+    dbase[(int64_t)t * 3 * E + E + h * D + d] = ak * scale;
+    dbase[(int64_t)t * 3 * E + 2 * E + h * D + d] = av;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ positional conv (weight-normed, grouped)
+// dW[co][ci][j] = sum_t dpc[b, t, co] * xpad[b, t + j, g*CG + ci],  xpad row r = x row r - pad (zero outside), co in group g
+__global__ void __launch_bounds__(256) posconv_dw_kernel(const float* __restrict__ x, const float* __restrict__ dpc, float* __restrict__ dw,
+                                                         int B, int T, int C, int CG, int k) {
+  const int j = blockIdx.x, g = blockIdx.y;
+  const int pad = k / 2;
+  for (int o = threadIdx.x; o < CG * CG; o += blockDim.x) {
+    const int co = o / CG, ci = o % CG;
+    float a = 0.f;
+    for (int b = 0; b < B; ++b)
+      for (int t = 0; t < T; ++t) {
+        const int r = t + j - pad;
+        if (r >= 0 && r < T) a = fmaf(dpc[((int64_t)b * T + t) * C + g * CG + co], x[((int64_t)b * T + r) * C + g * CG + ci], a);
+      }
+    dw[((int64_t)(g * CG + co) * CG + ci) * k + j] = a;
+  }
+}
+
+// w = g[j] * v / ||v[:, :, j]||  (norm over the first two dims): dg[j] = sum dw v / n ; dv = (g/n) dw - (g/n^3) (sum dw v) v
+__global__ void __launch_bounds__(256) weightnorm_bwd_kernel(const float* __restrict__ v, const float* __restrict__ g, const float* __restrict__ dw,
+                                                             float* __restrict__ dv, float* __restrict__ dg, int n_rows, int k) {
+  __shared__ float red[64];
+  const int j = blockIdx.x;
+  float nn = 0.f, dot = 0.f;
+  for (int r = threadIdx.x; r < n_rows; r += blockDim.x) {
+    const float vv = v[(int64_t)r * k + j];
+    nn += vv * vv;
+    dot += dw[(int64_t)r * k + j] * vv;
+  }
+  block_sum2(nn, dot, red);
+  const float n = sqrtf(nn);
+  const float gj = g[j];
+  if (threadIdx.x == 0) dg[j] = dot / n;
+  for (int r = threadIdx.x; r < n_rows; r += blockDim.x) {
+    const float vv = v[(int64_t)r * k + j];
+    dv[(int64_t)r * k + j] = gj / n * dw[(int64_t)r * k + j] - gj * dot / (n * n * n) * vv;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ loss, optimizer, misc
+// loss = mean((out - gt)^2) * loss_scale ; dout = 2 * loss_scale / n * (out - gt)
+__global__ void __launch_bounds__(256) mse_loss_grad_kernel(const float* __restrict__ out, const float* __restrict__ gt, float* __restrict__ dout,
+                                                            double* __restrict__ loss, int64_t rows, int C, int64_t out_ld, int64_t gt_ld,
+                                                            float loss_scale) {
+  __shared__ float red[64];
+  const int64_t n = rows * C;
+  float acc = 0.f, dummy = 0.f;
+  const float k = 2.f * loss_scale / (float)n;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / C;
+    const int c = (int)(i % C);
+    const float d = out[r * out_ld + c] - gt[r * gt_ld + c];
+    acc = fmaf(d, d, acc);
+    dout[i] = k * d;
+  }
+  block_sum2(acc, dummy, red);
+  if (threadIdx.x == 0) atomicAdd(loss, (double)acc * (double)loss_scale / (double)n);
+}
+
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
+                            float lr, float b1, float b2, float eps, float bc1, float bc2, float grad_scale) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gi = g[i] * grad_scale;
+  const float mi = b1 * m[i] + (1.f - b1) * gi;
+  const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  // torch.optim.Adam: p -= lr / bc1 * m / (sqrt(v) / sqrt(bc2) + eps)
+  p[i] -= lr / bc1 * mi / (sqrtf(vi) / sqrtf(bc2) + eps);
+}
+
+// y[i] = a[i] + b[i]
+__global__ void add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = a[i] + b[i];
+}
+
+// align_corners linear resample over time (models/lib/wav2vec.py:67-73), fp32 output, no LayerNorm (the training path keeps the
+// pre-norm activations for the LayerNorm backward). in [B, T_in, C] (in_dtype) -> out fp32 [B*T_out, C]
+__global__ void lerp_kernel(const void* __restrict__ in, int in_dtype, int64_t in_batch_stride, float* __restrict__ out, int B, int T_in,
+                            int T_out, int C) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)B * T_out * C) return;
+  const int c = (int)(idx % C);
+  const int t = (int)((idx / C) % T_out);
+  const int b = (int)(idx / ((int64_t)C * T_out));
+  const float scale = T_out > 1 ? (float)(T_in - 1) / (float)(T_out - 1) : 0.f;
+  const float src = scale * (float)t;
+  const int i0 = (int)src;
+  const int i1 = i0 + (i0 < T_in - 1 ? 1 : 0);
+  const float l1 = src - (float)i0, l0 = 1.f - l1;
+  const int64_t base = (int64_t)b * in_batch_stride;
+  out[idx] = l0 * load_as_float(in, in_dtype, base + (int64_t)i0 * C + c) + l1 * load_as_float(in, in_dtype, base + (int64_t)i1 * C + c);
+}
+
+}  // namespace avi
+
+using namespace avi;
+
+extern "C" int avi_transpose_cast_bf16(const float* src, void* dst, int32_t R, int32_t C, int64_t src_ld, int32_t R_pad, void* stream) {
+  AVI_REQUIRE(R > 0 && C > 0 && R_pad >= R && src_ld >= C, "avi_transpose_cast_bf16: bad shape");
+  dim3 grid((C + 31) / 32, (R_pad + 31) / 32), block(32, 8);
+  transpose_cast_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), R, C, src_ld, R_pad);
+  return check_launch("transpose_cast");
+}
+
+extern "C" int avi_colsum(const float* x, float* out, int32_t R, int32_t N, int64_t ld, int32_t accumulate, void* stream) {
+  AVI_REQUIRE(R > 0 && N > 0 && ld >= N, "avi_colsum: bad shape");
+  colsum_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(x, out, R, N, ld, accumulate);
+  return check_launch("colsum");
+}
+
+extern "C" int avi_act_fwd(const float* pre, float* out_f32, void* out_bf16, int64_t n, int32_t act, void* stream) {
+  AVI_REQUIRE(n > 0 && (act == AVI_ACT_GELU || act == AVI_ACT_RELU), "avi_act_fwd: bad arguments");
+  act_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(pre, out_f32, reinterpret_cast<__nv_bfloat16*>(out_bf16), n, act);
+  return check_launch("act_fwd");
+}
+
+extern "C" int avi_act_bwd(const float* pre, const float* dout, float* dpre, int64_t n, int32_t act, void* stream) {
+  AVI_REQUIRE(n > 0 && (act == AVI_ACT_GELU || act == AVI_ACT_RELU), "avi_act_bwd: bad arguments");
+  act_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(pre, dout, dpre, n, act);
+  return check_launch("act_bwd");
+}
+
+extern "C" int avi_layernorm_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, float* db, int64_t rows, int32_t C,
+                                 float eps, void* stream) {
+  AVI_REQUIRE(rows > 0 && C > 0 && C <= 1024, "avi_layernorm_bwd: bad shape");
+  layernorm_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x, w, dy, dx, dw, db, rows, C, eps);
+  return check_launch("layernorm_bwd");
+}
+
+extern "C" int avi_attn_train_fwd(const float* qkv, float* out, float* P, int32_t B, int32_t T, int32_t H, int32_t D, float scale,
+                                  int32_t bias_mode, int32_t period, void* stream) {
+  AVI_REQUIRE(B > 0 && T > 0 && T <= 128 && H > 0 && D > 0 && D <= 64, "avi_attn_train_fwd: T <= 128 and D <= 64 (T=%d D=%d)", T, D);
+  const size_t smem = ((size_t)T * (D + 1) + (size_t)T * D) * sizeof(float);
+  static cudaError_t attr_err = cudaFuncSetAttribute(attn_train_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 129 * 4);
+  AVI_REQUIRE(attr_err == cudaSuccess, "avi_attn_train_fwd: cudaFuncSetAttribute failed");
+  attn_train_fwd_kernel<<<dim3(H, B), 256, smem, (cudaStream_t)stream>>>(qkv, out, P, T, H, D, scale, bias_mode, period > 0 ? period : 1);
+  return check_launch("attn_train_fwd");
+}
+
+extern "C" int avi_attn_train_bwd(const float* qkv, const float* P, const float* dout, float* dqkv, float* dS_scratch, int32_t B, int32_t T,
+                                  int32_t H, int32_t D, float scale, void* stream) {
+  AVI_REQUIRE(B > 0 && T > 0 && T <= 128 && H > 0 && D > 0, "avi_attn_train_bwd: bad shape");
+  attn_train_bwd_kernel<<<dim3(H, B), 256, 0, (cudaStream_t)stream>>>(qkv, P, dout, dqkv, dS_scratch, T, H, D, scale);
+  return check_launch("attn_train_bwd");
+}
+
+extern "C" int avi_posconv_dw(const float* x, const float* dpc, float* dw, int32_t B, int32_t T, int32_t C, int32_t groups, int32_t k,
+                              void* stream) {
+  AVI_REQUIRE(B > 0 && T > 0 && C > 0 && groups > 0 && C % groups == 0 && k > 0, "avi_posconv_dw: bad shape");
+  posconv_dw_kernel<<<dim3(k, groups), 256, 0, (cudaStream_t)stream>>>(x, dpc, dw, B, T, C, C / groups, k);
+  return check_launch("posconv_dw");
+}
+
+extern "C" int avi_weightnorm_bwd(const float* v, const float* g, const float* dw, float* dv, float* dg, int32_t n_rows, int32_t k,
+                                  void* stream) {
+  AVI_REQUIRE(n_rows > 0 && k > 0, "avi_weightnorm_bwd: bad shape");
+  weightnorm_bwd_kernel<<<k, 256, 0, (cudaStream_t)stream>>>(v, g, dw, dv, dg, n_rows, k);
+  return check_launch("weightnorm_bwd");
+}
+
+extern "C" int avi_mse_loss_grad(const float* out, const float* gt, float* dout, double* loss, int64_t rows, int32_t C, int64_t out_ld,
+                                 int64_t gt_ld, float loss_scale, void* stream) {
+  AVI_REQUIRE(rows > 0 && C > 0 && out_ld >= C && gt_ld >= C, "avi_mse_loss_grad: bad shape");
+  if (cudaMemsetAsync(loss, 0, sizeof(double), (cudaStream_t)stream) != cudaSuccess) {
+    set_error("avi_mse_loss_grad: memset failed");
+    return 1;
+  }
+  mse_loss_grad_kernel<<<kNumSMs * 4, 256, 0, (cudaStream_t)stream>>>(out, gt, dout, loss, rows, C, out_ld, gt_ld, loss_scale);
+  return check_launch("mse_loss_grad");
+}
+
+extern "C" int avi_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                             int32_t step, float grad_scale, void* stream) {
+  AVI_REQUIRE(n > 0 && step >= 1, "avi_adam_step: bad arguments");
+  const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+  adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, bc1, bc2, grad_scale);
+  return check_launch("adam");
+}
+
+extern "C" int avi_add_f32(const float* a, const float* b, float* y, int64_t n, void* stream) {
+  AVI_REQUIRE(n > 0, "avi_add_f32: bad size");
+  add_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a, b, y, n);
+  return check_launch("add");
+}
+
+extern "C" int avi_w2v_lerp(const void* in, int32_t in_dtype, int64_t in_batch_stride, float* out, int32_t B, int32_t T_in, int32_t T_out,
+                            int32_t C, void* stream) {
+  AVI_REQUIRE(B > 0 && T_in > 0 && T_out > 0 && C > 0, "avi_w2v_lerp: bad shape");
+  const int64_t n = (int64_t)B * T_out * C;
+  lerp_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in, in_dtype, in_batch_stride, out, B, T_in, T_out, C);
+  return check_launch("lerp");
+}

@@ -472,3 +472,124 @@ def flame_lbs_tc_grouped(betas, full_pose, dirs16_exp, jreg, lbs_weights, templa
 
 def flame_set_max_ctas(n: int):
     _lib.check(_lib.load().avi_flame_set_max_ctas(C.c_int32(int(n))), "avi_flame_set_max_ctas")
+
+
+# ------------------------------------------------------------------------------------------------ training-step pieces
+def _chk(rc, name):
+    _lib.check(rc, name)
+
+
+def transpose_cast_bf16(x2d, R_pad=None):
+    """fp32 [R, C] (row stride allowed) -> bf16 [C, R_pad] with zero padding (R_pad defaults to R rounded up to 64)."""
+    _need_cuda(x2d)
+    R, Cc = x2d.shape
+    assert x2d.dtype == torch.float32 and x2d.stride(1) == 1
+    R_pad = R_pad or ((R + 63) // 64) * 64
+    out = torch.empty((Cc, R_pad), dtype=torch.bfloat16, device=x2d.device)
+    _chk(_lib.load().avi_transpose_cast_bf16(_ptr(x2d), _ptr(out), C.c_int32(R), C.c_int32(Cc), C.c_int64(x2d.stride(0)), C.c_int32(R_pad),
+                                             _stream()), "avi_transpose_cast_bf16")
+    return out
+
+
+def colsum(x2d, out=None, accumulate=False):
+    _need_cuda(x2d)
+    R, N = x2d.shape
+    if out is None:
+        out = torch.empty((N,), dtype=torch.float32, device=x2d.device)
+    _chk(_lib.load().avi_colsum(_ptr(x2d), _ptr(out), C.c_int32(R), C.c_int32(N), C.c_int64(x2d.stride(0)), C.c_int32(1 if accumulate else 0),
+                                _stream()), "avi_colsum")
+    return out
+
+
+def act_fwd(pre, act, want_f32=True, want_bf16=False):
+    _need_cuda(pre)
+    o32 = torch.empty_like(pre) if want_f32 else None
+    o16 = torch.empty(pre.shape, dtype=torch.bfloat16, device=pre.device) if want_bf16 else None
+    _chk(_lib.load().avi_act_fwd(_ptr(pre), _ptr(o32), _ptr(o16), C.c_int64(pre.numel()), C.c_int32(act), _stream()), "avi_act_fwd")
+    return o32, o16
+
+
+def act_bwd(pre, dout, act):
+    _need_cuda(pre, dout)
+    dpre = torch.empty_like(pre)
+    _chk(_lib.load().avi_act_bwd(_ptr(pre), _ptr(dout.contiguous()), _ptr(dpre), C.c_int64(pre.numel()), C.c_int32(act), _stream()), "avi_act_bwd")
+    return dpre
+
+
+def layernorm_bwd(x, w, dy, dw, db, want_dx=True, eps=1e-5):
+    """dw / db are accumulated into (pre-zeroed fp32 buffers)."""
+    _need_cuda(x, dy)
+    rows, Cc = x.numel() // x.shape[-1], x.shape[-1]
+    dx = torch.empty_like(x) if want_dx else None
+    _chk(_lib.load().avi_layernorm_bwd(_ptr(x.contiguous()), _ptr(w), _ptr(dy.contiguous()), _ptr(dx), _ptr(dw), _ptr(db), C.c_int64(rows),
+                                       C.c_int32(Cc), C.c_float(eps), _stream()), "avi_layernorm_bwd")
+    return dx
+
+
+def attn_train_fwd(qkv, B, T, H, D, bias_mode=0, period=1):
+    _need_cuda(qkv)
+    out = torch.empty((B * T, H * D), dtype=torch.float32, device=qkv.device)
+    P = torch.empty((B, H, T, T), dtype=torch.float32, device=qkv.device)
+    _chk(_lib.load().avi_attn_train_fwd(_ptr(qkv), _ptr(out), _ptr(P), C.c_int32(B), C.c_int32(T), C.c_int32(H), C.c_int32(D),
+                                        C.c_float(D ** -0.5), C.c_int32(bias_mode), C.c_int32(period), _stream()), "avi_attn_train_fwd")
+    return out, P
+
+
+def attn_train_bwd(qkv, P, dout, B, T, H, D):
+    _need_cuda(qkv, P, dout)
+    dqkv = torch.empty_like(qkv)
+    dS = torch.empty_like(P)
+    _chk(_lib.load().avi_attn_train_bwd(_ptr(qkv), _ptr(P), _ptr(dout.contiguous()), _ptr(dqkv), _ptr(dS), C.c_int32(B), C.c_int32(T),
+                                        C.c_int32(H), C.c_int32(D), C.c_float(D ** -0.5), _stream()), "avi_attn_train_bwd")
+    return dqkv
+
+
+def posconv_dw(x, dpc, B, T, groups, k):
+    _need_cuda(x, dpc)
+    Cc = x.shape[-1]
+    dw = torch.empty((Cc, Cc // groups, k), dtype=torch.float32, device=x.device)
+    _chk(_lib.load().avi_posconv_dw(_ptr(x.contiguous()), _ptr(dpc.contiguous()), _ptr(dw), C.c_int32(B), C.c_int32(T), C.c_int32(Cc),
+                                    C.c_int32(groups), C.c_int32(k), _stream()), "avi_posconv_dw")
+    return dw
+
+
+def weightnorm_bwd(v, g, dw):
+    _need_cuda(v, g, dw)
+    k = v.shape[-1]
+    dv = torch.empty_like(v)
+    dg = torch.empty((k,), dtype=torch.float32, device=v.device)
+    _chk(_lib.load().avi_weightnorm_bwd(_ptr(v.contiguous()), _ptr(g.contiguous()), _ptr(dw), _ptr(dv), _ptr(dg), C.c_int32(v.numel() // k),
+                                        C.c_int32(k), _stream()), "avi_weightnorm_bwd")
+    return dv, dg.view(g.shape)
+
+
+def mse_loss_grad(out2d, gt2d, loss_scale):
+    """out2d / gt2d fp32 [rows, C] (row strides allowed) -> (loss fp64 device scalar, dout dense [rows, C])."""
+    _need_cuda(out2d, gt2d)
+    rows, Cc = out2d.shape
+    dout = torch.empty((rows, Cc), dtype=torch.float32, device=out2d.device)
+    loss = torch.empty((1,), dtype=torch.float64, device=out2d.device)
+    _chk(_lib.load().avi_mse_loss_grad(_ptr(out2d), _ptr(gt2d), _ptr(dout), _ptr(loss), C.c_int64(rows), C.c_int32(Cc), C.c_int64(out2d.stride(0)),
+                                       C.c_int64(gt2d.stride(0)), C.c_float(loss_scale), _stream()), "avi_mse_loss_grad")
+    return loss, dout
+
+
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):
+    _need_cuda(p, g, m, v)
+    _chk(_lib.load().avi_adam_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), C.c_int64(p.numel()), C.c_float(lr), C.c_float(beta1), C.c_float(beta2),
+                                   C.c_float(eps), C.c_int32(step), C.c_float(grad_scale), _stream()), "avi_adam_step")
+
+
+def add_f32(a, b):
+    _need_cuda(a, b)
+    y = torch.empty_like(a)
+    _chk(_lib.load().avi_add_f32(_ptr(a.contiguous()), _ptr(b.contiguous()), _ptr(y), C.c_int64(a.numel()), _stream()), "avi_add_f32")
+    return y
+
+
+def w2v_lerp(x, in_batch_stride, B, T_in, T_out, Cc):
+    _need_cuda(x)
+    out = torch.empty((B * T_out, Cc), dtype=torch.float32, device=x.device)
+    _chk(_lib.load().avi_w2v_lerp(_ptr(x), C.c_int32(_dt(x)), C.c_int64(in_batch_stride), _ptr(out), C.c_int32(B), C.c_int32(T_in),
+                                  C.c_int32(T_out), C.c_int32(Cc), _stream()), "avi_w2v_lerp")
+    return out

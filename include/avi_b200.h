@@ -267,6 +267,40 @@ int avi_lrelu_bn_repeat(const float* x, const float* bn_scale, const float* bn_s
 int avi_sub_add_rows(const float* a, const float* neutral, const float* tpl, float* out, int32_t B, int32_t T, int32_t C,
                      int64_t row_stride, void* stream);
 
+/* ------------------------------------------------------------------ training step (BASELINE configs[4]) ------------------------------------------------------------------
+ * Backward / optimizer pieces of the teacher-forced faceformer_vert step (models/faceformer_vert.py:360-482; feature extractor
+ * frozen :154). Dense backward contractions use avi_gemm_bf16_tc on operands laid out by avi_transpose_cast_bf16. */
+/* dst bf16 [C, R_pad] = transpose(src fp32 [R, C], row stride src_ld), zero padded to R_pad rows of the source */
+int avi_transpose_cast_bf16(const float* src, void* dst, int32_t R, int32_t C, int64_t src_ld, int32_t R_pad, void* stream);
+/* out[n] (+)= sum_r x[r, n]   (bias gradients) */
+int avi_colsum(const float* x, float* out, int32_t R, int32_t N, int64_t ld, int32_t accumulate, void* stream);
+/* act = AVI_ACT_GELU | AVI_ACT_RELU: out = act(pre) ; dpre = dout * act'(pre) */
+int avi_act_fwd(const float* pre, float* out_f32, void* out_bf16, int64_t n, int32_t act, void* stream);
+int avi_act_bwd(const float* pre, const float* dout, float* dpre, int64_t n, int32_t act, void* stream);
+/* LayerNorm backward over the last dim: dx (may be NULL), dw += , db += (may be NULL; accumulate with atomics, zero them first) */
+int avi_layernorm_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, float* db, int64_t rows, int32_t C, float eps,
+                      void* stream);
+/* attention for training (T <= 128): forward keeps P [B,H,T,T]; bias_mode 0 none, 1 FaceFormer biased causal mask
+ * (init_biased_mask, faceformer_vert.py via :56-77 of faceformer_disentangle.py). qkv fp32 [B,T,3*H*D] */
+int avi_attn_train_fwd(const float* qkv, float* out, float* P, int32_t B, int32_t T, int32_t H, int32_t D, float scale, int32_t bias_mode,
+                       int32_t period, void* stream);
+int avi_attn_train_bwd(const float* qkv, const float* P, const float* dout, float* dqkv, float* dS_scratch /* [B,H,T,T] */, int32_t B,
+                       int32_t T, int32_t H, int32_t D, float scale, void* stream);
+/* positional conv: dW [C, C/groups, k] from x [B,T,C] and d(pre-activation) [B,T,C]; weight-norm chain rule (dim = 2) */
+int avi_posconv_dw(const float* x, const float* dpc, float* dw, int32_t B, int32_t T, int32_t C, int32_t groups, int32_t k, void* stream);
+int avi_weightnorm_bwd(const float* v, const float* g, const float* dw, float* dv, float* dg, int32_t n_rows /* C * C/groups */, int32_t k,
+                       void* stream);
+/* loss = mean((out - gt)^2) * loss_scale (fp64 scalar on the device) ; dout = d loss / d out (dense [rows, C]) */
+int avi_mse_loss_grad(const float* out, const float* gt, float* dout, double* loss, int64_t rows, int32_t C, int64_t out_ld, int64_t gt_ld,
+                      float loss_scale, void* stream);
+/* torch.optim.Adam step on a flat fp32 buffer; grad_scale multiplies the gradient first (1 / world_size after a sum all-reduce) */
+int avi_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps, int32_t step,
+                  float grad_scale, void* stream);
+int avi_add_f32(const float* a, const float* b, float* y, int64_t n, void* stream);
+/* align_corners linear resample over time only (models/lib/wav2vec.py:67-73), fp32 output [B*T_out, C] */
+int avi_w2v_lerp(const void* in, int32_t in_dtype, int64_t in_batch_stride, float* out, int32_t B, int32_t T_in, int32_t T_out, int32_t C,
+                 void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -414,6 +414,103 @@ def golden_emote():
     print("emote.npz", {k: v.shape for k, v in out.items()})
 
 
+def build_reference_faceformer_vert(ffv, fd, sd_ff, sd_w2v, flame, fan_emb, period=30):
+    """models/faceformer_vert.Faceformer through __new__ (the constructor needs the network and private assets), carrying exactly
+    the attributes forward_switch_frame reads (:360-519)."""
+    args = types.SimpleNamespace(dataset="vocaset", feature_dim=fd, vertice_dim=15069, period=period,
+                                 train_subjects="a b c d e f g h", device="cpu", is_only_emo=True)
+    m = ffv.Faceformer.__new__(ffv.Faceformer)
+    nn.Module.__init__(m)
+    m.args, m.dataset, m.device, m.vertice_scale = args, "vocaset", "cpu", 1.0
+    m.audio_encoder = _ref_wav2vec2(sd_w2v)
+    m.audio_encoder.feature_extractor._freeze_parameters()                       # :154
+    m.audio_feature_map = nn.Linear(768, fd)
+    m.vertice_map = nn.Linear(15069, fd)
+    m.vertice_map_r = nn.Linear(fd, 15069)
+    m.obj_vector = nn.Linear(8, fd, bias=False)
+    m.PPE = ffv.PeriodicPositionalEncoding(fd, period=period)
+    m.biased_mask = ffv.init_biased_mask(n_head=4, max_seq_len=600, period=period)
+    layer = nn.TransformerDecoderLayer(d_model=fd, nhead=4, dim_feedforward=2 * fd, batch_first=True)
+    m.transformer_decoder = nn.TransformerDecoder(layer, num_layers=1)
+    m.flame = flame
+    m.template = flame.v_template.reshape(1, 1, 15069) * m.vertice_scale         # :184
+    m.fan_net = _FanStub(fan_emb)
+    m.meters, m.losses_dict = {}, {}
+    own = {k: v for k, v in m.state_dict().items()
+           if not k.startswith(("audio_encoder.", "PPE.", "flame."))}
+    assert set(own) == set(sd_ff), (set(own) ^ set(sd_ff))
+    m.load_state_dict(sd_ff, strict=False)
+    ffv.mask_lip = lambda x: x
+    return m.eval()          # dropout / SpecAugment / LayerDrop inactive: the step is then a deterministic function of its inputs
+
+
+GRAD_STRIDE = 509  # big gradient tensors are stored flattened [::GRAD_STRIDE]
+
+
+def train_inputs(B, T, seed=90):
+    """coeff [B,T,53] normalised, pose [B,T,6], shape [B,T,100], coeff_mean/std [1,1,53] (config 5 inputs)."""
+    rng = np.random.default_rng(seed)
+    f = lambda *s, sc=1.0: torch.from_numpy((sc * rng.normal(size=s)).astype(np.float32))  # noqa: E731
+    coeff = f(B, T, 53)
+    pose = torch.cat([f(B, T, 3, sc=0.2), f(B, T, 3, sc=0.1)], -1)
+    shape = f(B, T, 100)
+    mean = f(1, 1, 53, sc=0.1)
+    std = 0.5 + 0.1 * f(1, 1, 53).abs()
+    std[..., 50:] = 0.1
+    return coeff, pose, shape, mean, std
+
+
+def golden_train():
+    """The reference's OWN faceformer_vert forward_switch_frame (:360-542) -> loss.backward() -> torch.optim.Adam step."""
+    import pdb
+    from gdl.models.DecaFLAME import FLAME_mediapipe
+    from . import synth
+    _import_faceformer()
+    import models.faceformer_vert as ffv
+    pdb.set_trace = lambda *a, **k: None                     # left enabled upstream at :541
+    cwd = os.getcwd()
+    os.chdir("/tmp")                                           # the debug visualisation makes ./intermediate_res (:527-528)
+    out = {}
+    try:
+        sd_w2v = synth.wav2vec2_state(0)
+        cfg = synth.write_flame_assets("/tmp/avi_flame_assets")
+        cfg.n_shape = 100
+        flame = FLAME_mediapipe(cfg)
+        for tag, fd, B, n_samples, T in (("a", 64, 2, 16000, 24), ("b", 128, 1, 16000, 20)):
+            sd_ff = synth.faceformer_state(fd=fd, seed=200 + fd, variant="vert")
+            m = build_reference_faceformer_vert(ffv, fd, sd_ff, sd_w2v, flame, synth.fan_embeddings(T, seed=20))
+            coeff, pose, shape, mean, std = train_inputs(B, T, seed=90 + fd)
+            m.coeff_mean, m.coeff_std = mean, std
+            audio = synth.audio(B, n_samples, seed=4321)
+            img = torch.zeros(B, T, 3, 4, 4)
+            img[:, :, 0, 0, 0] = torch.arange(T).float()
+            opt = torch.optim.Adam([p for p in m.parameters() if p.requires_grad], lr=1e-4)
+            opt.zero_grad(set_to_none=True)
+            loss = m.forward_switch_frame(audio, coeff, pose.clone(), shape, img=img, criterion=nn.MSELoss(reduction="none"),
+                                          teacher_forcing=True)
+            loss.backward()
+            out[f"{tag}_loss"] = np.array([loss.item()])
+            names = [n for n, p in m.named_parameters() if p.requires_grad]
+            for n, p in m.named_parameters():
+                if not p.requires_grad:
+                    continue
+                g = p.grad if p.grad is not None else torch.zeros_like(p)
+                out[f"{tag}_gchk/{n}"] = checksum(g)
+                out[f"{tag}_g/{n}"] = (g.reshape(-1)[::GRAD_STRIDE] if g.numel() > 4096 else g.reshape(-1)).numpy().copy()
+            before = {n: p.detach().clone() for n, p in m.named_parameters() if p.requires_grad}
+            opt.step()
+            for n, p in m.named_parameters():
+                if p.requires_grad:
+                    q = p.detach() - before[n]          # the Adam update itself (|dp| ~ lr), not the parameter
+                    out[f"{tag}_dp/{n}"] = (q.reshape(-1)[::GRAD_STRIDE] if q.numel() > 4096 else q.reshape(-1)).numpy().copy()
+            out[f"{tag}_names"] = np.array(names)
+            print("train", tag, "loss", loss.item(), "trainable tensors", len(names))
+    finally:
+        os.chdir(cwd)
+    np.savez_compressed(os.path.join(GOLD, "train.npz"), **out)
+    print("train.npz", len(out), "arrays")
+
+
 def main():
     _paths()
     os.makedirs(GOLD, exist_ok=True)
@@ -423,6 +520,7 @@ def main():
     golden_faceformer()
     golden_prior()
     golden_emote()
+    golden_train()
 
 
 if __name__ == "__main__":

@@ -128,3 +128,43 @@ def test_loopback_frames(golden):
     from avi_talking_b200.loop_utils import calc_loop_idx
     g = golden("faceformer")
     assert [calc_loop_idx(i, 5) for i in range(17)] == list(g["loop_idx_5_17"])
+
+
+def _train_case(tag, fd, B, n_samples, T):
+    from oracle.make_golden import train_inputs
+    sd_w2v = synth.wav2vec2_state(0)
+    sd_ff = synth.faceformer_state(fd=fd, seed=200 + fd, variant="vert")
+    coeff, pose, shape, mean, std = train_inputs(B, T, seed=90 + fd)
+    buf = synth.flame_buffers(100, 50)
+    gt = fo.convert_coeff2verts(buf, mean.reshape(-1), std.reshape(-1), coeff.reshape(-1, 53), pose.reshape(-1, 6).clone(),
+                                torch.zeros(B * T, 100)).reshape(B, T, 15069)               # faceformer_vert.py:408-412
+    audio = synth.audio(B, n_samples, seed=4321)
+    return sd_ff, sd_w2v, buf["v_template"].reshape(1, 1, 15069), audio, gt
+
+
+def sub(t, stride):
+    t = t.reshape(-1)
+    return (t[::stride] if t.numel() > 4096 else t).numpy()
+
+
+def test_train_step_matches_reference(golden):
+    """oracle/train_oracle.py against the reference's own forward_switch_frame + backward + Adam (tests/golden/train.npz)."""
+    from oracle import train_oracle as to
+    from oracle.make_golden import GRAD_STRIDE
+    g = golden("train")
+    for tag, fd, B, n, T in (("a", 64, 2, 16000, 24), ("b", 128, 1, 16000, 20)):
+        sd_ff, sd_w2v, template, audio, gt = _train_case(tag, fd, B, n, T)
+        before = to.trainable(sd_ff, sd_w2v)
+        losses, grads, after = to.train_step(sd_ff, sd_w2v, template, audio, gt, lr=1e-4)
+        np.testing.assert_allclose(losses[0], g[f"{tag}_loss"][0], rtol=2e-5)
+        names = [str(x) for x in g[f"{tag}_names"]]
+        assert set(names) - {"audio_encoder.masked_spec_embed"} == set(grads)
+        for nme in grads:
+            ref = g[f"{tag}_g/{nme}"]
+            got = sub(grads[nme], GRAD_STRIDE)
+            scale = max(np.abs(ref).max(), 1e-12)
+            assert np.abs(got - ref).max() <= 2e-4 * scale + 1e-9, (nme, np.abs(got - ref).max(), scale)
+            dp = sub(after[nme] - before[nme], GRAD_STRIDE)
+            # Adam's first step is lr * g / (|g| + eps): compare where the reference's |g| is not at the eps floor
+            ok = np.abs(ref) > 1e-6 * scale + 1e-7
+            np.testing.assert_allclose(dp[ok], g[f"{tag}_dp/{nme}"][ok], atol=2e-7, rtol=0, err_msg=nme)
