@@ -10,7 +10,15 @@ namespace avi {
 
 // ------------------------------------------------------------------------------------------------ layout helpers
 // dst[c][r] = bf16(src[r][c]) for r < R, zero for R <= r < R_pad   (src fp32 [R, C] with row stride src_ld)
-__global__ void transpose_cast_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int R, int C, int64_t src_ld, int R_pad) {
+template <typename OutT>
+__device__ __forceinline__ OutT to_out(float v);
+template <>
+__device__ __forceinline__ float to_out<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __nv_bfloat16 to_out<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+template <typename OutT>
+__global__ void transpose_cast_kernel(const float* __restrict__ src, OutT* __restrict__ dst, int R, int C, int64_t src_ld, int R_pad) {
   __shared__ float tile[32][33];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -20,8 +28,40 @@ __global__ void transpose_cast_kernel(const float* __restrict__ src, __nv_bfloat
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int c = c0 + i, r = r0 + threadIdx.x;
-    if (c < C && r < R_pad) dst[(int64_t)c * R_pad + r] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+    if (c < C && r < R_pad) dst[(int64_t)c * R_pad + r] = to_out<OutT>(tile[threadIdx.x][i]);
   }
+}
+
+// dst[r][c] = src[r][c] for r < R, c < C, zero elsewhere in [R_pad, C_pad]
+template <typename OutT>
+__global__ void cast_pad2d_kernel(const float* __restrict__ src, OutT* __restrict__ dst, int R, int C, int64_t src_ld, int R_pad, int C_pad) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)R_pad * C_pad) return;
+  const int r = (int)(i / C_pad), c = (int)(i % C_pad);
+  dst[i] = to_out<OutT>((r < R && c < C) ? src[(int64_t)r * src_ld + c] : 0.f);
+}
+
+// teacher-forcing input rows (faceformer_vert.py:443-444): row (b, t) = gt[b, t-1] - template for t >= 1, zero for t = 0
+__global__ void tf_input_rows_kernel(const float* __restrict__ gt, int64_t gt_ld, const float* __restrict__ tpl, float* __restrict__ out,
+                                     int B, int T, int C, int C_pad) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * T * C_pad) return;
+  const int c = (int)(i % C_pad);
+  const int64_t row = i / C_pad;
+  const int t = (int)(row % T);
+  // cat([template, gt[:, :-1]]) - template : the first row is template - template
+  out[i] = (c < C && t > 0) ? gt[(row - 1) * gt_ld + c] - tpl[c] : 0.f;
+}
+
+// x[b, t, :] += style[b or 0, :] + pe[t mod period, :]   (faceformer_vert.py:446-447, PeriodicPositionalEncoding :92-107)
+__global__ void add_style_pe_kernel(float* __restrict__ x, const float* __restrict__ style, int64_t style_stride, const float* __restrict__ pe,
+                                    int B, int T, int fd, int period) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * T * fd) return;
+  const int c = (int)(i % fd);
+  const int t = (int)((i / fd) % T);
+  const int b = (int)(i / ((int64_t)fd * T));
+  x[i] += style[b * style_stride + c] + pe[(t % period) * fd + c];
 }
 
 // out[n] (+)= sum_r x[r][n]
@@ -319,11 +359,44 @@ __global__ void lerp_kernel(const void* __restrict__ in, int in_dtype, int64_t i
 
 using namespace avi;
 
-extern "C" int avi_transpose_cast_bf16(const float* src, void* dst, int32_t R, int32_t C, int64_t src_ld, int32_t R_pad, void* stream) {
-  AVI_REQUIRE(R > 0 && C > 0 && R_pad >= R && src_ld >= C, "avi_transpose_cast_bf16: bad shape");
+extern "C" int avi_transpose_cast(const float* src, void* dst, int32_t dst_dtype, int32_t R, int32_t C, int64_t src_ld, int32_t R_pad,
+                                  void* stream) {
+  AVI_REQUIRE(R > 0 && C > 0 && R_pad >= R && src_ld >= C, "avi_transpose_cast: bad shape");
+  AVI_REQUIRE((R_pad + 31) / 32 <= 65535, "avi_transpose_cast: too many rows");
   dim3 grid((C + 31) / 32, (R_pad + 31) / 32), block(32, 8);
-  transpose_cast_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), R, C, src_ld, R_pad);
+  if (dst_dtype == AVI_DT_BF16)
+    transpose_cast_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), R, C, src_ld, R_pad);
+  else
+    transpose_cast_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src, reinterpret_cast<float*>(dst), R, C, src_ld, R_pad);
   return check_launch("transpose_cast");
+}
+
+extern "C" int avi_cast_pad2d(const float* src, void* dst, int32_t dst_dtype, int32_t R, int32_t C, int64_t src_ld, int32_t R_pad,
+                              int32_t C_pad, void* stream) {
+  AVI_REQUIRE(R > 0 && C > 0 && R_pad >= R && C_pad >= C && src_ld >= C, "avi_cast_pad2d: bad shape");
+  const int64_t n = (int64_t)R_pad * C_pad;
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  if (dst_dtype == AVI_DT_BF16)
+    cast_pad2d_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), R, C, src_ld, R_pad, C_pad);
+  else
+    cast_pad2d_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, reinterpret_cast<float*>(dst), R, C, src_ld, R_pad, C_pad);
+  return check_launch("cast_pad2d");
+}
+
+extern "C" int avi_tf_input_rows(const float* gt, int64_t gt_ld, const float* tpl, float* out, int32_t B, int32_t T, int32_t C,
+                                 int32_t C_pad, void* stream) {
+  AVI_REQUIRE(B > 0 && T > 0 && C > 0 && C_pad >= C && gt_ld >= C, "avi_tf_input_rows: bad shape");
+  const int64_t n = (int64_t)B * T * C_pad;
+  tf_input_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(gt, gt_ld, tpl, out, B, T, C, C_pad);
+  return check_launch("tf_input_rows");
+}
+
+extern "C" int avi_ff_add_style_pe(float* x, const float* style, int64_t style_stride, const float* pe, int32_t B, int32_t T, int32_t fd,
+                                   int32_t period, void* stream) {
+  AVI_REQUIRE(B > 0 && T > 0 && fd > 0 && period > 0, "avi_ff_add_style_pe: bad shape");
+  const int64_t n = (int64_t)B * T * fd;
+  add_style_pe_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, style, style_stride, pe, B, T, fd, period);
+  return check_launch("add_style_pe");
 }
 
 extern "C" int avi_colsum(const float* x, float* out, int32_t R, int32_t N, int64_t ld, int32_t accumulate, void* stream) {

@@ -133,7 +133,7 @@ class Faceformer(nn.Module):
 
     @torch.no_grad()
     def _pack(self):
-        key = (self.precision,) + tuple((p.data_ptr(), p._version) for p in self._own_params()) + (self.PPE.pe.data_ptr(),)
+        key = (self.precision, ops.WEIGHT_EPOCH) + tuple((p.data_ptr(), p._version) for p in self._own_params()) + (self.PPE.pe.data_ptr(),)
         if self._packed is not None and key == self._packed_key:
             return self._packed
         f32 = lambda t: t.detach().float().contiguous()  # noqa: E731
@@ -324,9 +324,35 @@ class Faceformer(nn.Module):
             emo_embed = torch.concat(emo, dim=0).unsqueeze(0)
         return self.predict_from_embeddings(audio, emo_embed)
 
-    def forward(self, *a, **k):
-        raise NotImplementedError("the training forward (losses, renderers, FanEncoder) is outside the inference hot path; "
-                                  "use forward_ff(..., teacher_forcing=True) for the teacher-forced decoder pass")
+    def forward(self, audio, coeff, pose, shape, cam=None, motion_des=None, img=None, ref_img=None, criterion=None, file_name=None,
+                text_desc=None, teacher_forcing=True):
+        """The training forward of models/faceformer_vert.py (:339-346 -> forward_switch_frame :360-482): returns the loss
+        `mean(criterion(out + template, gt_verts)) * 10`; `loss.backward()` fills every trainable parameter's `.grad` with the
+        hand-written backward of avi_talking_b200/train.py. Built for the audio-only (vert) variant, teacher forcing, MSE.
+        The FanEncoder loops of :374-401 run under no_grad and their embeddings are never used (:434), so they are skipped; the
+        debug visualisation / pdb.set_trace() of :521-541 is not reproduced."""
+        if self.variant != "vert":
+            raise NotImplementedError("the disentangle training forward (render / emotion / landmark losses, FanEncoder) is outside "
+                                      "the hot path; use FaceformerVert, or forward_ff(..., teacher_forcing=True) for the decoder pass")
+        if not teacher_forcing:
+            raise NotImplementedError("scheduled-sampling training (teacher_forcing=False) is not built")
+        if criterion is not None and not isinstance(criterion, nn.MSELoss):
+            raise NotImplementedError("criterion must be nn.MSELoss (the loss/gradient kernel is the mean squared error)")
+        from . import train
+        B, T = coeff.shape[0], coeff.shape[1]
+        with torch.no_grad():
+            gt_coeffs = coeff[:, :, :53].reshape(-1, 53)                                       # :405-410
+            gt_poses = pose.reshape(-1, pose.shape[-1])
+            gt_shapes = torch.zeros_like(shape.reshape(-1, shape.shape[-1]))
+            gt_verts = (self.convert_coeff2verts(gt_coeffs, gt_poses, gt_shapes) * self.vertice_scale).reshape(B, T, -1)
+        return self.training_loss(audio, gt_verts)
+
+    def training_loss(self, audio, gt_verts):
+        """Loss of the teacher-forced step for ground-truth vertices given directly (the VOCASET flavour)."""
+        from . import train
+        if getattr(self, "_train_step", None) is None:
+            self._train_step = train.TrainStep(self)
+        return train.training_loss(self._train_step, audio, gt_verts)
 
 
 class FaceformerVert(Faceformer):

@@ -14,6 +14,9 @@ from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, DT_BF16, DT_F32, AviDecoderWeigh
 # (kernel name, start event, end event, algorithmic work) with CUDA events recorded on the launching stream.
 PROFILE = None
 
+# incremented whenever a kernel of this library rewrites model weights in place (train.FlatAdam.step): part of every pack key
+WEIGHT_EPOCH = 0
+
 
 class _timed:
     def __init__(self, name, work):
@@ -479,16 +482,46 @@ def _chk(rc, name):
     _lib.check(rc, name)
 
 
-def transpose_cast_bf16(x2d, R_pad=None):
-    """fp32 [R, C] (row stride allowed) -> bf16 [C, R_pad] with zero padding (R_pad defaults to R rounded up to 64)."""
+def transpose_cast(x2d, dtype, R_pad=None):
+    """fp32 [R, C] (row stride allowed) -> dtype [C, R_pad] with zero padding (R_pad defaults to R rounded up to 64)."""
     _need_cuda(x2d)
     R, Cc = x2d.shape
     assert x2d.dtype == torch.float32 and x2d.stride(1) == 1
     R_pad = R_pad or ((R + 63) // 64) * 64
-    out = torch.empty((Cc, R_pad), dtype=torch.bfloat16, device=x2d.device)
-    _chk(_lib.load().avi_transpose_cast_bf16(_ptr(x2d), _ptr(out), C.c_int32(R), C.c_int32(Cc), C.c_int64(x2d.stride(0)), C.c_int32(R_pad),
-                                             _stream()), "avi_transpose_cast_bf16")
+    out = torch.empty((Cc, R_pad), dtype=dtype, device=x2d.device)
+    _chk(_lib.load().avi_transpose_cast(_ptr(x2d), _ptr(out), C.c_int32(_dt(out)), C.c_int32(R), C.c_int32(Cc), C.c_int64(x2d.stride(0)),
+                                        C.c_int32(R_pad), _stream()), "avi_transpose_cast")
     return out
+
+
+def cast_pad2d(x2d, dtype, R_pad=None, C_pad=None):
+    _need_cuda(x2d)
+    R, Cc = x2d.shape
+    assert x2d.dtype == torch.float32 and x2d.stride(1) == 1
+    R_pad, C_pad = R_pad or R, C_pad or Cc
+    out = torch.empty((R_pad, C_pad), dtype=dtype, device=x2d.device)
+    _chk(_lib.load().avi_cast_pad2d(_ptr(x2d), _ptr(out), C.c_int32(_dt(out)), C.c_int32(R), C.c_int32(Cc), C.c_int64(x2d.stride(0)),
+                                    C.c_int32(R_pad), C.c_int32(C_pad), _stream()), "avi_cast_pad2d")
+    return out
+
+
+def tf_input_rows(gt, template, C_pad):
+    """gt fp32 [B, T, C] (uniform row stride) -> fp32 [B*T, C_pad]: cat([template, gt[:, :-1]]) - template, zero padded."""
+    _need_cuda(gt, template)
+    B, T, Cc = gt.shape
+    assert gt.stride(2) == 1 and gt.stride(0) == T * gt.stride(1)
+    out = torch.empty((B * T, C_pad), dtype=torch.float32, device=gt.device)
+    _chk(_lib.load().avi_tf_input_rows(_ptr(gt), C.c_int64(gt.stride(1)), _ptr(template), _ptr(out), C.c_int32(B), C.c_int32(T), C.c_int32(Cc),
+                                       C.c_int32(C_pad), _stream()), "avi_tf_input_rows")
+    return out
+
+
+def ff_add_style_pe(x, style, pe, B, T, fd, period):
+    _need_cuda(x, style, pe)
+    stride = 0 if style.shape[0] == 1 else style.stride(0)
+    _chk(_lib.load().avi_ff_add_style_pe(_ptr(x), _ptr(style), C.c_int64(stride), _ptr(pe), C.c_int32(B), C.c_int32(T), C.c_int32(fd),
+                                         C.c_int32(period), _stream()), "avi_ff_add_style_pe")
+    return x
 
 
 def colsum(x2d, out=None, accumulate=False):

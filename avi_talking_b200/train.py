@@ -1,0 +1,493 @@
+"""The teacher-forced faceformer_vert training step (BASELINE configs[4]) on libavi_b200.so.
+
+Reference: models/faceformer_vert.py  Faceformer.forward_switch_frame :360-371 (style, wav2vec2 with frame_num, audio_feature_map),
+:405-412 (gt_verts = convert_coeff2verts(coeff[..., :53], pose, zeros)), :437-454 (teacher-forced decoder), :475-482 (loss =
+mean(criterion(out + template, gt)) * 10); the conv feature extractor is frozen (:154). No trainer for this class is published
+(SURVEY 3.3): Adam (torch.optim.Adam semantics) and the data-parallel gradient all-reduce are assembled here.
+
+Design (B200-first, not a port of autograd):
+  * forward keeps exactly the tensors the hand-written backward needs (pre-LayerNorm sums, pre-activations, attention
+    probabilities); all clips of the step are batched, rows = clips x frames;
+  * every dense contraction, forward and backward (dX = dY W, dW = dY^T X), runs on the tcgen05 GEMM (bf16 operands, fp32
+    accumulation; `precision="fp32"` routes the same calls to the CUDA-core GEMM for the <=1e-5 parity mode). Operands whose
+    contraction dimension is not innermost are laid out by avi_transpose_cast; 15069 is padded to 15104 (= 236 x 64);
+  * gradients are written straight into ONE flat fp32 buffer laid out in backward-completion order (`FlatLayout`), so that the
+    data-parallel all-reduce is a few large NCCL calls on contiguous ranges launched while backward is still running
+    (`GradBuckets`), and Adam is ONE kernel over the flat parameter / gradient / moment buffers (`FlatAdam`);
+  * q/k/v weights of an encoder layer are adjacent in the flat buffers: the fused [2304, 768] QKV weight and its gradient are
+    views, no concatenation per step.
+
+Regularisers (dropout 0.1 in the decoder layer / PPE / wav2vec2, SpecAugment, LayerDrop) are NOT applied: the step is the
+deterministic function the oracle and the golden fixture (the reference's own forward_switch_frame under .eval()) pin.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .ops import ACT_GELU, ACT_RELU
+
+V3_PAD = 64  # contraction dims are padded to a multiple of this (tcgen05 GEMM k-block)
+
+
+def _pad(n, m=V3_PAD):
+    return ((n + m - 1) // m) * m
+
+
+# ------------------------------------------------------------------------------------------------ flat parameter / gradient layout
+class FlatLayout:
+    """Order and offsets of the trainable parameters inside the flat buffers. Order = the order in which backward finishes
+    their gradients (head and decoder first, wav2vec2 layer 11 .. 0, positional conv, feature projection last), so that a
+    bucket of the all-reduce is a contiguous range that is complete once backward has passed its last member."""
+
+    def __init__(self, model):
+        w2v = model.audio_encoder
+        named = dict(model.named_parameters())
+        lyr = "transformer_decoder.layers.0."
+        order = ["vertice_map_r.weight", "vertice_map_r.bias"]
+        order += [lyr + n for n in ("norm3.weight", "norm3.bias", "linear2.weight", "linear2.bias", "linear1.weight", "linear1.bias",
+                                    "norm2.weight", "norm2.bias", "multihead_attn.out_proj.weight", "multihead_attn.out_proj.bias",
+                                    "multihead_attn.in_proj_weight", "multihead_attn.in_proj_bias", "norm1.weight", "norm1.bias",
+                                    "self_attn.out_proj.weight", "self_attn.out_proj.bias", "self_attn.in_proj_weight",
+                                    "self_attn.in_proj_bias")]
+        order += ["vertice_map.weight", "vertice_map.bias", "obj_vector.weight", "audio_feature_map.weight", "audio_feature_map.bias"]
+        self.segments = [len(order)]                        # parameter-count boundaries where a bucket may end
+        for l in reversed(range(len(w2v.encoder.layers))):
+            p = f"audio_encoder.encoder.layers.{l}."
+            order += [p + n for n in ("final_layer_norm.weight", "final_layer_norm.bias", "feed_forward.output_dense.weight",
+                                      "feed_forward.output_dense.bias", "feed_forward.intermediate_dense.weight",
+                                      "feed_forward.intermediate_dense.bias", "layer_norm.weight", "layer_norm.bias",
+                                      "attention.out_proj.weight", "attention.out_proj.bias",
+                                      "attention.q_proj.weight", "attention.k_proj.weight", "attention.v_proj.weight",
+                                      "attention.q_proj.bias", "attention.k_proj.bias", "attention.v_proj.bias")]
+            self.segments.append(len(order))
+        pc = "audio_encoder.encoder.pos_conv_embed.conv."
+        g_name = pc + ("parametrizations.weight.original0" if pc + "parametrizations.weight.original0" in named else "weight_g")
+        v_name = pc + ("parametrizations.weight.original1" if pc + "parametrizations.weight.original1" in named else "weight_v")
+        self.pos_g, self.pos_v = g_name, v_name
+        order += ["audio_encoder.encoder.layer_norm.weight", "audio_encoder.encoder.layer_norm.bias", pc + "bias", g_name, v_name,
+                  "audio_encoder.feature_projection.projection.weight", "audio_encoder.feature_projection.projection.bias",
+                  "audio_encoder.feature_projection.layer_norm.weight", "audio_encoder.feature_projection.layer_norm.bias"]
+        self.segments.append(len(order))
+        missing = [n for n in order if n not in named]
+        if missing:
+            raise RuntimeError(f"FlatLayout: model lacks parameters {missing}")
+        # everything else that requires grad gets no gradient from this step (masked_spec_embed: SpecAugment only; obj_embedding,
+        # and for the disentangle variant v_merge2hidden / learnable_eye_embed, which forward_switch_frame never touches)
+        self.unused = [n for n, p in named.items() if p.requires_grad and n not in order]
+        frozen = [n for n in order if not named[n].requires_grad]
+        if frozen:
+            raise RuntimeError(f"FlatLayout: parameters on the trained path are frozen: {frozen}")
+        self.names = order
+        self.offsets, off = {}, 0
+        for n in order:
+            self.offsets[n] = off
+            k = named[n].numel()
+            # keep q|k|v (weights and biases) densely adjacent; everything else starts on a 64-element (256 B) boundary
+            dense = n.endswith(("attention.q_proj.weight", "attention.k_proj.weight", "attention.q_proj.bias", "attention.k_proj.bias"))
+            off += k if dense else _pad(k, 64)
+        self.total = off
+        self.shapes = {n: tuple(named[n].shape) for n in order}
+
+    def view(self, flat, name):
+        o = self.offsets[name]
+        shp = self.shapes[name]
+        n = 1
+        for s in shp:
+            n *= s
+        return flat[o:o + n].view(shp)
+
+    def span(self, flat, first, rows, cols):
+        """[rows, cols] view starting at parameter `first` (fused q|k|v)."""
+        o = self.offsets[first]
+        return flat[o:o + rows * cols].view(rows, cols)
+
+    def bucket_ranges(self, max_buckets=8):
+        """<= max_buckets contiguous element ranges [a, b) in backward-completion order, ending on segment boundaries."""
+        ends = [(self.offsets[self.names[s]] if s < len(self.names) else self.total) for s in self.segments]
+        ends[-1] = self.total
+        per = -(-len(ends) // max_buckets)
+        picked = [ends[min(i + per - 1, len(ends) - 1)] for i in range(0, len(ends), per)]
+        ranges, a = [], 0
+        for b in picked:
+            if b > a:
+                ranges.append((a, b))
+                a = b
+        return ranges
+
+
+def flatten_parameters(model, layout=None):
+    """Move the trainable parameters into one flat fp32 buffer (each nn.Parameter becomes a view; values preserved)."""
+    layout = layout or FlatLayout(model)
+    named = dict(model.named_parameters())
+    dev = named[layout.names[0]].device
+    flat = torch.zeros(layout.total, dtype=torch.float32, device=dev)
+    with torch.no_grad():
+        for n in layout.names:
+            v = layout.view(flat, n)
+            v.copy_(named[n].data)
+            named[n].data = v
+    model._flat_params, model._flat_layout = flat, layout
+    return flat, layout
+
+
+class GradBuckets:
+    """Data-parallel gradient exchange: sum all-reduce of contiguous ranges of the flat gradient buffer, each launched
+    on a communication stream as soon as backward has finished the range; the optimizer divides by the world size."""
+
+    def __init__(self, layout: FlatLayout, group=None, max_buckets=8):
+        self.ranges = layout.bucket_ranges(max_buckets)
+        self.group = group
+        self.works = []
+        self.stream = None
+        self._next = 0
+
+    @property
+    def world(self):
+        return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
+
+    def begin(self):
+        self.works, self._next = [], 0
+
+    def ready(self, flat_grad, upto):
+        """Backward has finished every gradient whose flat offset is < upto: launch the buckets that are now complete."""
+        if self.world == 1:
+            return
+        while self._next < len(self.ranges) and self.ranges[self._next][1] <= upto:
+            a, b = self.ranges[self._next]
+            self._next += 1
+            if flat_grad.is_cuda:
+                if self.stream is None:
+                    self.stream = torch.cuda.Stream(device=flat_grad.device)
+                self.stream.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(self.stream):
+                    self.works.append(dist.all_reduce(flat_grad[a:b], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            else:
+                self.works.append(dist.all_reduce(flat_grad[a:b], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def finish(self, flat_grad):
+        self.ready(flat_grad, flat_grad.numel())
+        for w in self.works:
+            w.wait()
+        if self.stream is not None:
+            torch.cuda.current_stream().wait_stream(self.stream)
+        self.works = []
+        return 1.0 / self.world
+
+
+class FlatAdam:
+    """torch.optim.Adam (no weight decay, no amsgrad) as one kernel over the flat parameter / gradient / moment buffers."""
+
+    def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8):
+        if getattr(model, "_flat_params", None) is None:
+            flatten_parameters(model)
+        self.model = model
+        self.p = model._flat_params
+        self.m = torch.zeros_like(self.p)
+        self.v = torch.zeros_like(self.p)
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.t = 0
+
+    def zero_grad(self, set_to_none=True):
+        self.model._flat_grad = None
+        for p in self.model.parameters():
+            p.grad = None
+
+    def step(self, grad_scale=1.0):
+        g = getattr(self.model, "_flat_grad", None)
+        if g is None:
+            raise RuntimeError("FlatAdam.step: no gradient (run the training forward and loss.backward() first)")
+        self.t += 1
+        ops.adam_step(self.p, g, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps, self.t, grad_scale)
+        ops.WEIGHT_EPOCH += 1          # the kernel rewrote the weights in place: every cached operand pack is stale
+
+
+# ------------------------------------------------------------------------------------------------ the step
+class _Lin:
+    """Operand plumbing of one precision."""
+
+    def __init__(self, bf16):
+        self.bf16 = bf16
+        self.dt = torch.bfloat16 if bf16 else torch.float32
+
+    def a(self, x32):                     # [M, K] fp32 contiguous -> GEMM operand
+        return ops.cast_bf16(x32) if self.bf16 else x32
+
+    def t(self, x32, R_pad=None):         # [R, C] fp32 -> operand [C, R_pad]
+        return ops.transpose_cast(x32, self.dt, R_pad)
+
+    def fwd(self, x_op, W32, b, residual=None, act=0):
+        return ops.linear(x_op, self.a(W32), b, residual=residual, act=act, out_dtype=torch.float32)
+
+    def bwd(self, dy32, x32, W32, gW, gb, Mp, want_dx=True, residual=None, dy_op=None, xT=None):
+        """y = x W^T + b. gW [N, K] <- dy^T x ; gb [N] <- colsum(dy) ; returns dx = dy W (+ residual) or None."""
+        M, N = dy32.shape
+        K = W32.shape[1]
+        dyT = self.t(dy32, Mp)
+        xT = self.t(x32, Mp) if xT is None else xT
+        ops.gemm(dyT, xT, None, gW, rows=N, N=K, K=Mp, a_rows_alloc=N, c_ld=gW.stride(0))
+        if gb is not None:
+            ops.colsum(dy32, out=gb)
+        if not want_dx:
+            return None
+        dy_op = self.a(dy32) if dy_op is None else dy_op
+        WT = self.t(W32, N)                # [K, N]
+        return ops.linear(dy_op, WT, None, residual=residual, out_dtype=torch.float32)
+
+
+class TrainStep:
+    """forward -> loss, backward -> flat gradient, for a FaceformerVert drop-in. `precision` follows the model."""
+
+    def __init__(self, model, buckets: GradBuckets | None = None):
+        if getattr(model, "variant", None) != "vert":
+            raise NotImplementedError("the training step follows models/faceformer_vert.py (audio-only hidden states)")
+        self.model = model
+        if getattr(model, "_flat_params", None) is None:
+            flatten_parameters(model)
+        self.layout = model._flat_layout
+        self.buckets = buckets
+        self.saved = None
+
+    # ---------------------------------------------------------------------------- positional conv (grouped, weight-normed)
+    def _posconv(self, x32, w, B, T, flip, bias=None):
+        """Grouped Conv1d(k=128, pad=64, groups=16)[..., :-1] over time as 4 block-diagonal conv-mode GEMMs (4 groups = 192 channels
+        each). flip=False: forward, out[t] = sum_j x[t + j - 64] w[:, :, j]. flip=True: the input gradient,
+        dx[r] = sum_j dpc[r + 64 - j] w[:, :, j]^T (a correlation with the tap-flipped, channel-transposed weight)."""
+        cfg = self.model.audio_encoder.config
+        k, g, Cc = cfg.num_conv_pos_embeddings, cfg.num_conv_pos_embedding_groups, cfg.hidden_size
+        cg = Cc // g
+        if cg * 4 % 64 != 0 or g % 4 != 0:
+            raise NotImplementedError("positional conv layout other than 16 groups x 48 channels")
+        front = k - 1 - k // 2 if flip else k // 2
+        Tp = T + k
+        xpad = torch.zeros((B, Tp, Cc), dtype=torch.float32, device=x32.device)
+        xpad[:, front:front + T] = x32.view(B, T, Cc)
+        wg = w.reshape(g, cg, cg, k)                                   # [group, co, ci, tap]
+        out = torch.empty((B * T, Cc), dtype=torch.float32, device=x32.device)
+        lin = self.lin
+        W4 = 4 * cg
+        for q in range(g // 4):
+            blk = torch.zeros(4, cg, k, 4, cg, dtype=torch.float32, device=w.device)
+            for gl in range(4):
+                blk[gl, :, :, gl, :] = wg[4 * q + gl].flip(-1).permute(1, 2, 0) if flip else wg[4 * q + gl].permute(0, 2, 1)
+            wq = lin.a(blk.reshape(W4, k * W4).contiguous())
+            xs = lin.a(xpad[:, :, W4 * q:W4 * (q + 1)].contiguous())
+            ops.gemm(xs, wq, None if bias is None else bias[W4 * q:W4 * (q + 1)], out[:, W4 * q:], batch=B, rows=T, N=W4, K=k * W4, conv_taps=k, conv_stride=1, a_ld=W4,
+                     a_batch_stride=Tp * W4, a_rows_alloc=Tp, c_ld=Cc, c_batch_stride=T * Cc,
+                     algorithmic_flops=2.0 * B * T * W4 * k * cg)
+        return out
+
+    # ---------------------------------------------------------------------------- forward
+    @torch.no_grad()
+    def forward(self, audio, gt_verts):
+        """audio [B, N] fp32, gt_verts [B, T, V*3] fp32 (row stride may be padded) -> loss (0-dim fp32 tensor)."""
+        m = self.model
+        w2v, cfg = m.audio_encoder, m.audio_encoder.config
+        if not audio.is_cuda:
+            raise RuntimeError("avi_talking_b200 training runs on CUDA only (no CPU fallback)")
+        bf16 = m.precision == "bf16"
+        fd = m.args.feature_dim
+        if bf16 and fd % 64 != 0:
+            raise NotImplementedError("bf16 training needs feature_dim % 64 == 0 (use precision='fp32')")
+        self.lin = lin = _Lin(bf16)
+        B, T, V3 = gt_verts.shape
+        M = B * T
+        if T > 128:
+            raise NotImplementedError("training clips of more than 128 frames (VOCASET clips are ~100-150 at 30 fps; split longer ones)")
+        S = {"B": B, "T": T, "M": M}
+        eps = cfg.layer_norm_eps
+        H, D = cfg.num_attention_heads, cfg.hidden_size // cfg.num_attention_heads
+        # -- frozen conv feature extractor (no gradient, :154) and the 50 -> frame_num resample (wav2vec.py:97-108)
+        w2v.precision = m.precision
+        feats, T50, La = w2v._feature_extractor(audio.contiguous().float(), w2v._pack_extractor())
+        Cf = cfg.conv_dim[-1]
+        S["h"] = h = ops.w2v_lerp(feats, La * Cf, B, T50, T, Cf)
+        fp = w2v.feature_projection
+        hn, _ = ops.layernorm(h, fp.layer_norm.weight, fp.layer_norm.bias, eps=eps)
+        S["hn"] = hn
+        S["proj"] = proj = lin.fwd(lin.a(hn), fp.projection.weight, fp.projection.bias)             # wav2vec.py:120
+        # -- positional conv embedding + encoder LayerNorm
+        S["pos_w"] = pos_w = w2v._posconv_weight().float().contiguous()
+        S["pc"] = pcb = self._posconv(proj, pos_w, B, T, flip=False, bias=w2v.encoder.pos_conv_embed.conv.bias)
+        gpc, _ = ops.act_fwd(pcb, ACT_GELU)
+        S["h0pre"] = h0pre = ops.add_f32(proj, gpc)
+        x, _ = ops.layernorm(h0pre, w2v.encoder.layer_norm.weight, w2v.encoder.layer_norm.bias, eps=eps)
+        # -- 12 post-LN encoder layers (fused q|k|v weight = a view of the flat parameter buffer)
+        P, lay = m._flat_params, self.layout
+        S["layers"] = []
+        for l, lyr in enumerate(w2v.encoder.layers):
+            pre = f"audio_encoder.encoder.layers.{l}.attention."
+            Wqkv = lay.span(P, pre + "q_proj.weight", 3 * cfg.hidden_size, cfg.hidden_size)
+            bqkv = lay.span(P, pre + "q_proj.bias", 1, 3 * cfg.hidden_size).view(-1)
+            a = lyr.attention
+            L = {"x": x, "Wqkv": Wqkv}
+            L["qkv"] = qkv = lin.fwd(lin.a(x), Wqkv, bqkv)
+            L["att"], L["P"] = att, _ = ops.attn_train_fwd(qkv, B, T, H, D)
+            L["y"] = y = lin.fwd(lin.a(att), a.out_proj.weight, a.out_proj.bias, residual=x)
+            L["h1"] = h1 = ops.layernorm(y, lyr.layer_norm.weight, lyr.layer_norm.bias, eps=eps)[0]
+            ff = lyr.feed_forward
+            L["fpre"] = fpre = lin.fwd(lin.a(h1), ff.intermediate_dense.weight, ff.intermediate_dense.bias)
+            L["f"] = f = ops.act_fwd(fpre, ACT_GELU)[0]
+            L["y2"] = y2 = lin.fwd(lin.a(f), ff.output_dense.weight, ff.output_dense.bias, residual=h1)
+            x = ops.layernorm(y2, lyr.final_layer_norm.weight, lyr.final_layer_norm.bias, eps=eps)[0]
+            S["layers"].append(L)
+        S["h12"] = x
+        # -- heads and the teacher-forced decoder layer (faceformer_vert.py:369,437-454)
+        S["mem"] = mem = lin.fwd(lin.a(x), m.audio_feature_map.weight, m.audio_feature_map.bias)
+        V3p = _pad(V3)
+        template = m.template.to(audio.device).reshape(-1).float().contiguous()
+        S["vin"] = vin = ops.tf_input_rows(gt_verts, template, V3p)                                    # :443-444
+        Wvm_p = ops.cast_pad2d(m.vertice_map.weight, lin.dt, C_pad=V3p)
+        xd = ops.linear(lin.a(vin), Wvm_p, m.vertice_map.bias, out_dtype=torch.float32)               # :445
+        style = m.obj_vector.weight[:, 0].contiguous().view(1, fd)                                     # one_hot[:, 0] = 1 (:361-365)
+        period = m.args.period
+        ops.ff_add_style_pe(xd, style, m.PPE.pe[0, :period].contiguous(), B, T, fd, period)            # :446-447
+        dl = m.transformer_decoder.layers[0]
+        S["xd"] = xd
+        S["dqkv_in"] = qkv = lin.fwd(lin.a(xd), dl.self_attn.in_proj_weight, dl.self_attn.in_proj_bias)
+        S["datt"], S["dP"] = att, _ = ops.attn_train_fwd(qkv, B, T, 4, fd // 4, bias_mode=1, period=period)
+        S["dy1"] = y1 = lin.fwd(lin.a(att), dl.self_attn.out_proj.weight, dl.self_attn.out_proj.bias, residual=xd)
+        S["x1"] = x1 = ops.layernorm(y1, dl.norm1.weight, dl.norm1.bias, eps=1e-5)[0]
+        # cross-attention with enc_dec_mask (:80-88) sees exactly one key per query: softmax == 1, output = out_proj(v_proj(mem_t)),
+        # and the q / k projections get exactly zero gradient
+        Wc, bc = dl.multihead_attn.in_proj_weight, dl.multihead_attn.in_proj_bias
+        S["cv"] = cv = lin.fwd(lin.a(mem), Wc[2 * fd:], bc[2 * fd:])
+        S["dy2"] = y2 = lin.fwd(lin.a(cv), dl.multihead_attn.out_proj.weight, dl.multihead_attn.out_proj.bias, residual=x1)
+        S["x2"] = x2 = ops.layernorm(y2, dl.norm2.weight, dl.norm2.bias, eps=1e-5)[0]
+        S["f1pre"] = f1pre = lin.fwd(lin.a(x2), dl.linear1.weight, dl.linear1.bias)
+        S["f1"] = f1 = ops.act_fwd(f1pre, ACT_RELU)[0]
+        S["dy3"] = y3 = lin.fwd(lin.a(f1), dl.linear2.weight, dl.linear2.bias, residual=x2)
+        S["x3"] = x3 = ops.layernorm(y3, dl.norm3.weight, dl.norm3.bias, eps=1e-5)[0]
+        out = ops.empty_rows(M, V3, audio.device)
+        bias = (m.vertice_map_r.bias + template).contiguous()                                          # + template (:475)
+        ops.gemm(lin.a(x3), lin.a(m.vertice_map_r.weight), bias, out, rows=M, N=V3, K=fd, a_rows_alloc=M, c_ld=out.stride(0))
+        loss64, dout = ops.mse_loss_grad(out, gt_verts.reshape(M, V3), 10.0)                           # :481-482
+        S["dout"] = dout
+        self.saved = S
+        return loss64.float().reshape(())
+
+    # ---------------------------------------------------------------------------- backward
+    @torch.no_grad()
+    def backward(self, grad_scale=1.0):
+        """Gradient of `grad_scale * loss` into a fresh flat buffer; sets model._flat_grad and every parameter's .grad view."""
+        S, m, lin, lay = self.saved, self.model, self.lin, self.layout
+        if S is None:
+            raise RuntimeError("TrainStep.backward without a forward")
+        w2v, cfg = m.audio_encoder, m.audio_encoder.config
+        B, T, M = S["B"], S["T"], S["M"]
+        Mp = _pad(M)
+        fd = m.args.feature_dim
+        eps = cfg.layer_norm_eps
+        G = torch.zeros(lay.total, dtype=torch.float32, device=S["h"].device)
+        g = lambda n: lay.view(G, n)  # noqa: E731
+        bk = self.buckets
+        if bk is not None:
+            bk.begin()
+        dout = S["dout"]
+        if grad_scale != 1.0:
+            dout = dout * grad_scale
+        dl = m.transformer_decoder.layers[0]
+        d = "transformer_decoder.layers.0."
+        V3 = dout.shape[1]
+        V3p = _pad(V3)
+        # vertice_map_r: out = x3 Wr^T + br
+        ops.gemm(lin.t(dout, Mp), lin.t(S["x3"], Mp), None, g("vertice_map_r.weight"), rows=V3, N=fd, K=Mp, a_rows_alloc=V3)
+        ops.colsum(dout, out=g("vertice_map_r.bias"))
+        WrT = ops.transpose_cast(m.vertice_map_r.weight, lin.dt, V3p)                                   # [fd, 15104]
+        dx3 = ops.linear(ops.cast_pad2d(dout, lin.dt, C_pad=V3p), WrT, None, out_dtype=torch.float32)
+        dy3 = ops.layernorm_bwd(S["dy3"], dl.norm3.weight, dx3, g(d + "norm3.weight"), g(d + "norm3.bias"), eps=1e-5)
+        df1 = lin.bwd(dy3, S["f1"], dl.linear2.weight, g(d + "linear2.weight"), g(d + "linear2.bias"), Mp)
+        df1pre = ops.act_bwd(S["f1pre"], df1, ACT_RELU)
+        dx2 = lin.bwd(df1pre, S["x2"], dl.linear1.weight, g(d + "linear1.weight"), g(d + "linear1.bias"), Mp, residual=dy3)
+        dy2 = ops.layernorm_bwd(S["dy2"], dl.norm2.weight, dx2, g(d + "norm2.weight"), g(d + "norm2.bias"), eps=1e-5)
+        dcv = lin.bwd(dy2, S["cv"], dl.multihead_attn.out_proj.weight, g(d + "multihead_attn.out_proj.weight"),
+                      g(d + "multihead_attn.out_proj.bias"), Mp)
+        Wc = dl.multihead_attn.in_proj_weight
+        dmem = lin.bwd(dcv, S["mem"], Wc[2 * fd:], g(d + "multihead_attn.in_proj_weight")[2 * fd:],
+                       g(d + "multihead_attn.in_proj_bias")[2 * fd:], Mp)
+        dy1 = ops.layernorm_bwd(S["dy1"], dl.norm1.weight, dy2, g(d + "norm1.weight"), g(d + "norm1.bias"), eps=1e-5)
+        datt = lin.bwd(dy1, S["datt"], dl.self_attn.out_proj.weight, g(d + "self_attn.out_proj.weight"),
+                       g(d + "self_attn.out_proj.bias"), Mp)
+        dqkv = ops.attn_train_bwd(S["dqkv_in"], S["dP"], datt, B, T, 4, fd // 4)
+        dxd = lin.bwd(dqkv, S["xd"], dl.self_attn.in_proj_weight, g(d + "self_attn.in_proj_weight"), g(d + "self_attn.in_proj_bias"),
+                      Mp, residual=dy1)
+        # xd = vin Wvm^T + bvm + style + pe
+        vinT = lin.t(S["vin"][:, :V3], Mp)                                                              # [15069, Mp]
+        ops.gemm(lin.t(dxd, Mp), vinT, None, g("vertice_map.weight"), rows=fd, N=V3, K=Mp, a_rows_alloc=fd, c_ld=V3)
+        ops.colsum(dxd, out=g("vertice_map.bias"))
+        gobj = torch.empty(fd, dtype=torch.float32, device=G.device)
+        ops.colsum(dxd, out=gobj)
+        g("obj_vector.weight")[:, 0] = gobj                                                              # other subjects: one_hot = 0
+        # audio_feature_map
+        dh = lin.bwd(dmem, S["h12"], m.audio_feature_map.weight, g("audio_feature_map.weight"), g("audio_feature_map.bias"), Mp)
+        if bk is not None:
+            bk.ready(G, lay.offsets[lay.names[lay.segments[0]]])
+        H, D = cfg.num_attention_heads, cfg.hidden_size // cfg.num_attention_heads
+        C = cfg.hidden_size
+        nl = len(w2v.encoder.layers)
+        for l in reversed(range(nl)):
+            lyr, L = w2v.encoder.layers[l], S["layers"][l]
+            p = f"audio_encoder.encoder.layers.{l}."
+            ff, a = lyr.feed_forward, lyr.attention
+            dy2 = ops.layernorm_bwd(L["y2"], lyr.final_layer_norm.weight, dh, g(p + "final_layer_norm.weight"),
+                                    g(p + "final_layer_norm.bias"), eps=eps)
+            df = lin.bwd(dy2, L["f"], ff.output_dense.weight, g(p + "feed_forward.output_dense.weight"),
+                         g(p + "feed_forward.output_dense.bias"), Mp)
+            dfpre = ops.act_bwd(L["fpre"], df, ACT_GELU)
+            dh1 = lin.bwd(dfpre, L["h1"], ff.intermediate_dense.weight, g(p + "feed_forward.intermediate_dense.weight"),
+                          g(p + "feed_forward.intermediate_dense.bias"), Mp, residual=dy2)
+            dy = ops.layernorm_bwd(L["y"], lyr.layer_norm.weight, dh1, g(p + "layer_norm.weight"), g(p + "layer_norm.bias"), eps=eps)
+            datt = lin.bwd(dy, L["att"], a.out_proj.weight, g(p + "attention.out_proj.weight"), g(p + "attention.out_proj.bias"), Mp)
+            dqkv = ops.attn_train_bwd(L["qkv"], L["P"], datt, B, T, H, D)
+            gW = lay.span(G, p + "attention.q_proj.weight", 3 * C, C)
+            gb = lay.span(G, p + "attention.q_proj.bias", 1, 3 * C).view(-1)
+            dh = lin.bwd(dqkv, L["x"], L["Wqkv"], gW, gb, Mp, residual=dy)
+            if bk is not None:
+                seg = lay.segments[nl - l]
+                bk.ready(G, lay.offsets[lay.names[seg]] if seg < len(lay.names) else lay.total)
+        # encoder LayerNorm, positional conv (weight norm), feature projection
+        dh0pre = ops.layernorm_bwd(S["h0pre"], w2v.encoder.layer_norm.weight, dh, g("audio_encoder.encoder.layer_norm.weight"),
+                                   g("audio_encoder.encoder.layer_norm.bias"), eps=eps)
+        dpc = ops.act_bwd(S["pc"], dh0pre, ACT_GELU)
+        ops.colsum(dpc, out=g("audio_encoder.encoder.pos_conv_embed.conv.bias"))
+        k, groups = cfg.num_conv_pos_embeddings, cfg.num_conv_pos_embedding_groups
+        dw = ops.posconv_dw(S["proj"], dpc, B, T, groups, k)
+        named = dict(m.named_parameters())
+        dv, dg = ops.weightnorm_bwd(named[lay.pos_v], named[lay.pos_g], dw)
+        g(lay.pos_v).copy_(dv)
+        g(lay.pos_g).copy_(dg)
+        dproj = ops.add_f32(dh0pre, self._posconv(dpc, S["pos_w"], B, T, flip=True))
+        fp = w2v.feature_projection
+        fpn = "audio_encoder.feature_projection."
+        dhn = lin.bwd(dproj, S["hn"], fp.projection.weight, g(fpn + "projection.weight"), g(fpn + "projection.bias"), Mp)
+        ops.layernorm_bwd(S["h"], fp.layer_norm.weight, dhn, g(fpn + "layer_norm.weight"), g(fpn + "layer_norm.bias"), want_dx=False,
+                          eps=eps)
+        scale = bk.finish(G) if bk is not None else 1.0
+        m._flat_grad = G
+        for n in lay.names:
+            named[n].grad = lay.view(G, n)
+        self.saved = None
+        return scale
+
+
+class _LossFn(torch.autograd.Function):
+    """`loss = model(...)` / `loss.backward()` as upstream: backward runs TrainStep.backward and fills the parameters' .grad."""
+
+    @staticmethod
+    def forward(ctx, anchor, step, audio, gt):
+        ctx.step = step
+        return step.forward(audio, gt)
+
+    @staticmethod
+    def backward(ctx, gloss):
+        step = ctx.step
+        s = float(gloss) if gloss.numel() == 1 else 1.0
+        step.grad_divisor = step.backward(grad_scale=s)
+        return None, None, None, None
+
+
+def training_loss(step: TrainStep, audio, gt_verts):
+    """Differentiable-looking loss: a 0-dim tensor whose .backward() fills every trainable parameter's .grad (flat views)."""
+    anchor = torch.zeros((), device=audio.device, requires_grad=True)
+    return _LossFn.apply(anchor, step, audio, gt_verts)

@@ -52,7 +52,8 @@ class Wav2Vec2Model(_HFWav2Vec2Model):
 
     # ------------------------------------------------------------------ weight packing (once per weight change)
     def _pack_key(self):
-        return (self.precision,) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+        # ops.WEIGHT_EPOCH: bumped by the fused optimizer (train.FlatAdam), whose kernel updates weights without touching _version
+        return (self.precision, ops.WEIGHT_EPOCH) + tuple((p.data_ptr(), p._version) for p in self.parameters())
 
     def _posconv_weight(self):
         conv = self.encoder.pos_conv_embed.conv
@@ -64,11 +65,13 @@ class Wav2Vec2Model(_HFWav2Vec2Model):
         return g * v / v.norm(p=2, dim=(0, 1), keepdim=True)
 
     @torch.no_grad()
-    def _pack(self):
-        key = self._pack_key()
-        if self._packed is not None and key == self._packed_key:
-            return self._packed
+    def _pack_extractor(self):
+        """The (frozen, faceformer_vert.py:154) conv feature extractor's operands; cached on its own parameters only so that the
+        training step, which rewrites every other weight each iteration, does not repack it."""
         cfg = self.config
+        key = (self.precision,) + tuple((p.data_ptr(), p._version) for p in self.feature_extractor.parameters())
+        if getattr(self, "_packed_fx", None) is not None and self._packed_fx_key == key:
+            return self._packed_fx
         if cfg.feat_extract_norm != "group" or cfg.do_stable_layer_norm or cfg.conv_bias:
             raise NotImplementedError("only the wav2vec2-base layout (group-norm extractor, post-LN encoder, no conv bias)")
         bf16 = self.precision == "bf16"
@@ -84,6 +87,19 @@ class Wav2Vec2Model(_HFWav2Vec2Model):
         for i in range(1, len(convs)):
             w = convs[i].conv.weight  # [Cout, Cin, k] -> [Cout, k*Cin] tap-major (matches time-major activations)
             P["conv_w"].append(wdt(w.permute(0, 2, 1).reshape(w.shape[0], -1).contiguous()))
+        self._packed_fx, self._packed_fx_key = P, key
+        return P
+
+    @torch.no_grad()
+    def _pack(self):
+        key = self._pack_key()
+        if self._packed is not None and key == self._packed_key:
+            return self._packed
+        cfg = self.config
+        bf16 = self.precision == "bf16"
+        wdt = (lambda t: ops.cast_bf16(t)) if bf16 else (lambda t: t.detach().float().contiguous())
+        f32 = lambda t: t.detach().float().contiguous()  # noqa: E731
+        P = dict(self._pack_extractor())
         fp = self.feature_projection
         P["fp_ln_w"], P["fp_ln_b"] = f32(fp.layer_norm.weight), f32(fp.layer_norm.bias)
         P["fp_w"], P["fp_b"] = wdt(fp.projection.weight), f32(fp.projection.bias)

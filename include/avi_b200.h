@@ -270,8 +270,18 @@ int avi_sub_add_rows(const float* a, const float* neutral, const float* tpl, flo
 /* ------------------------------------------------------------------ training step (BASELINE configs[4]) ------------------------------------------------------------------
  * Backward / optimizer pieces of the teacher-forced faceformer_vert step (models/faceformer_vert.py:360-482; feature extractor
  * frozen :154). Dense backward contractions use avi_gemm_bf16_tc on operands laid out by avi_transpose_cast_bf16. */
-/* dst bf16 [C, R_pad] = transpose(src fp32 [R, C], row stride src_ld), zero padded to R_pad rows of the source */
-int avi_transpose_cast_bf16(const float* src, void* dst, int32_t R, int32_t C, int64_t src_ld, int32_t R_pad, void* stream);
+/* dst (dst_dtype) [C, R_pad] = transpose(src fp32 [R, C], row stride src_ld), zero padded to R_pad rows of the source */
+int avi_transpose_cast(const float* src, void* dst, int32_t dst_dtype, int32_t R, int32_t C, int64_t src_ld, int32_t R_pad, void* stream);
+/* dst (dst_dtype) [R_pad, C_pad] = src fp32 [R, C] zero padded (contraction dims that are not multiples of 64: 15069 -> 15104) */
+int avi_cast_pad2d(const float* src, void* dst, int32_t dst_dtype, int32_t R, int32_t C, int64_t src_ld, int32_t R_pad, int32_t C_pad,
+                   void* stream);
+/* teacher-forcing input (faceformer_vert.py:443-444): out[b*T+t, :C] = gt[b, t-1] - template (zero row for t = 0), zero pad columns.
+ * gt rows of all clips are gt_ld floats apart */
+int avi_tf_input_rows(const float* gt, int64_t gt_ld, const float* tpl, float* out, int32_t B, int32_t T, int32_t C, int32_t C_pad,
+                      void* stream);
+/* x[b,t,:] += style[b*style_stride + :] + pe[t mod period, :]  (faceformer_vert.py:445-447) */
+int avi_ff_add_style_pe(float* x, const float* style, int64_t style_stride, const float* pe, int32_t B, int32_t T, int32_t fd,
+                        int32_t period, void* stream);
 /* out[n] (+)= sum_r x[r, n]   (bias gradients) */
 int avi_colsum(const float* x, float* out, int32_t R, int32_t N, int64_t ld, int32_t accumulate, void* stream);
 /* act = AVI_ACT_GELU | AVI_ACT_RELU: out = act(pre) ; dpre = dout * act'(pre) */

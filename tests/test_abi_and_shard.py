@@ -77,3 +77,73 @@ def test_world_size_2_gloo():
     assert m0 == [0, 2, 4, 6, 8] and m1 == [1, 3, 5, 7]
     assert c0 == c1 == [5, 4]
     assert t0 == t1 == [11.0, 3.0]
+
+
+# ---------------------------------------------------------------------------------------------- training: flat layout + gradient buckets
+def _tiny_vert_model():
+    """FaceformerVert drop-in with a 2-layer wav2vec2 encoder on CPU (layout / bucket logic only; no kernels run)."""
+    from transformers import Wav2Vec2Config
+    from avi_talking_b200.faceformer import FaceformerVert, make_args
+    from avi_talking_b200.wav2vec import Wav2Vec2Model
+    torch.manual_seed(0)
+    w2v = Wav2Vec2Model(Wav2Vec2Config(num_hidden_layers=2))
+    return FaceformerVert(make_args(feature_dim=64), audio_encoder=w2v, template=torch.zeros(1, 1, 15069))
+
+
+def test_flat_layout_and_flatten():
+    from avi_talking_b200 import train
+    m = _tiny_vert_model()
+    before = {n: p.detach().clone() for n, p in m.named_parameters()}
+    flat, lay = train.flatten_parameters(m)
+    named = dict(m.named_parameters())
+    for n in lay.names:                                       # values preserved, parameters are views of the flat buffer
+        assert torch.equal(named[n], before[n])
+        assert named[n].data_ptr() == flat.data_ptr() + 4 * lay.offsets[n]
+    assert not any(n.startswith("audio_encoder.feature_extractor.") for n in lay.names)        # frozen (faceformer_vert.py:154)
+    assert "audio_encoder.masked_spec_embed" in lay.unused
+    # fused q|k|v views are exactly cat(q, k, v)
+    p = "audio_encoder.encoder.layers.1.attention."
+    fused = lay.span(flat, p + "q_proj.weight", 3 * 768, 768)
+    assert torch.equal(fused, torch.cat([before[p + f"{x}_proj.weight"] for x in "qkv"], 0))
+    # buckets: contiguous, ordered, cover the whole buffer, end on segment boundaries
+    r = lay.bucket_ranges(8)
+    assert 1 <= len(r) <= 8 and r[0][0] == 0 and r[-1][1] == lay.total
+    assert all(a < b for a, b in r) and all(r[i][1] == r[i + 1][0] for i in range(len(r) - 1))
+
+
+def _bucket_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from avi_talking_b200 import train
+        m = _tiny_vert_model()
+        flat, lay = train.flatten_parameters(m)
+        bk = train.GradBuckets(lay, max_buckets=4)
+        g = torch.arange(lay.total, dtype=torch.float32) * (rank + 1)         # rank r holds (r+1) * arange
+        bk.begin()
+        # backward reports progress in completion order; buckets launch as soon as their range is complete
+        launched = []
+        for s in lay.segments:
+            upto = lay.offsets[lay.names[s]] if s < len(lay.names) else lay.total
+            bk.ready(g, upto)
+            launched.append(len(bk.works))
+        scale = bk.finish(g)
+        out.put((rank, launched, scale, float((g * scale - torch.arange(lay.total) * 1.5).abs().max())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_grad_buckets_world_size_2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_bucket_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, launched, scale, err in res:
+        assert scale == 0.5 and err == 0.0                      # mean over the two ranks of (r+1)*arange = 1.5*arange
+        assert launched == sorted(launched) and launched[0] >= 1 and launched[-1] == 4   # overlapped: first bucket leaves early
