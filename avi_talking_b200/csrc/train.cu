@@ -64,13 +64,23 @@ __global__ void add_style_pe_kernel(float* __restrict__ x, const float* __restri
   x[i] += style[b * style_stride + c] + pe[(t % period) * fd + c];
 }
 
-// out[n] (+)= sum_r x[r][n]
-__global__ void colsum_kernel(const float* __restrict__ x, float* __restrict__ out, int R, int N, int64_t ld, int accumulate) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
+// out[n] (+)= sum_r x[r][n]. Block (32 columns x 8 row lanes); gridDim.y splits the rows (atomics into a zeroed / accumulating out)
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, float* __restrict__ out, int R, int N, int64_t ld,
+                                                     int rows_per_block, int use_atomic, int accumulate) {
+  __shared__ float red[8][33];
+  const int n = blockIdx.x * 32 + threadIdx.x;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(R, r0 + rows_per_block);
   float s = 0.f;
-  for (int r = 0; r < R; ++r) s += x[(int64_t)r * ld + n];
-  out[n] = accumulate ? out[n] + s : s;
+  if (n < N)
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) s += x[(int64_t)r * ld + n];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && n < N) {
+#pragma unroll
+    for (int y = 1; y < 8; ++y) s += red[y][threadIdx.x];
+    if (use_atomic) atomicAdd(out + n, s);
+    else out[n] = accumulate ? out[n] + s : s;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ activations
@@ -151,27 +161,42 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
 
 // ------------------------------------------------------------------------------------------------ attention (training, T <= 128)
 // qkv fp32 [B, T, 3*H*D] (q | k | v); bias modes: 0 none, 1 FaceFormer biased causal mask (-slope_h * floor((i-j)/period), j <= i).
-// forward keeps the probabilities P [B, H, T, T] for the backward pass. One CTA per (head, clip).
+// forward keeps the probabilities P [B, H, T, T] for the backward pass. Clips are short (T ~ 120) and there are only B*H
+// (head, clip) problems, so every kernel is tiled over ATT_ROWS query (or key) rows as well: grid = (H, B, ceil(T / ATT_ROWS)),
+// K / V (or Q / dO) of the head staged in shared memory with a D+1 pitch (conflict-free both along keys and along channels).
 __device__ __forceinline__ float ff_slope(int h) { return exp2f(-2.f * (float)(h + 1)); }   // 4 heads: 2^-2, 2^-4, 2^-6, 2^-8
+constexpr int ATT_ROWS = 16;      // rows per CTA: 8 warps x 2 rows
+constexpr int ATT_MAXT = 128;
+
+__device__ __forceinline__ void att_stage(float* dst, const float* __restrict__ src, int T, int D, int row_stride) {
+  // dst[t][d] (pitch D+1) = src[t * row_stride + d]
+  for (int i = threadIdx.x; i < T * D; i += blockDim.x) {
+    const int t = i / D, d = i - t * D;
+    dst[t * (D + 1) + d] = src[(int64_t)t * row_stride + d];
+  }
+}
 
 __global__ void __launch_bounds__(256) attn_train_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ out, float* __restrict__ P,
                                                              int T, int H, int D, float scale, int bias_mode, int period) {
   extern __shared__ float sm[];
-  float* ks = sm;              // [T][D+1]
-  float* vs = ks + T * (D + 1);  // [T][D]
-  const int h = blockIdx.x, b = blockIdx.y;
+  float* ks = sm;                        // [T][D+1]
+  float* vs = ks + T * (D + 1);          // [T][D+1]
+  float* qs = vs + T * (D + 1);          // [8 warps][D]
+  float* ps = qs + 8 * 64;               // [8 warps][ATT_MAXT]
+  const int h = blockIdx.x, b = blockIdx.y, i0 = blockIdx.z * ATT_ROWS;
   const int E = H * D;
-  const float* base = qkv + (int64_t)b * T * 3 * E;
-  for (int i = threadIdx.x; i < T * D; i += blockDim.x) {
-    const int t = i / D, d = i % D;
-    ks[t * (D + 1) + d] = base[(int64_t)t * 3 * E + E + h * D + d];
-    vs[t * D + d] = base[(int64_t)t * 3 * E + 2 * E + h * D + d];
-  }
+  const float* base = qkv + (int64_t)b * T * 3 * E + h * D;
+  att_stage(ks, base + E, T, D, 3 * E);
+  att_stage(vs, base + 2 * E, T, D, 3 * E);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* Pb = P + ((int64_t)b * H + h) * T * T;
-  for (int i = warp; i < T; i += blockDim.x >> 5) {
-    const float* q = base + (int64_t)i * 3 * E + h * D;
+  float* q = qs + warp * 64;
+  float* pr = ps + warp * ATT_MAXT;
+  const float slope = ff_slope(h);
+  for (int i = i0 + warp; i < min(i0 + ATT_ROWS, T); i += 8) {
+    for (int d = lane; d < D; d += 32) q[d] = base[(int64_t)i * 3 * E + d] * scale;
+    __syncwarp();
     float s[4];
     float mx = -INFINITY;
 #pragma unroll
@@ -180,9 +205,9 @@ __global__ void __launch_bounds__(256) attn_train_fwd_kernel(const float* __rest
       s[u] = -INFINITY;
       if (j < T && !(bias_mode == 1 && j > i)) {
         float a = 0.f;
-        for (int d = 0; d < D; ++d) a = fmaf(q[d], ks[j * (D + 1) + d], a);
-        a *= scale;
-        if (bias_mode == 1) a -= ff_slope(h) * (float)((i - j) / period);
+        const float* kr = ks + j * (D + 1);
+        for (int d = 0; d < D; ++d) a = fmaf(q[d], kr[d], a);
+        if (bias_mode == 1) a -= slope * (float)((i - j) / period);
         s[u] = a;
       }
       mx = fmaxf(mx, s[u]);
@@ -194,68 +219,123 @@ __global__ void __launch_bounds__(256) attn_train_fwd_kernel(const float* __rest
       s[u] = (s[u] == -INFINITY) ? 0.f : expf(s[u] - mx);
       den += s[u];
     }
-    den = warp_sum(den);
+    den = 1.f / warp_sum(den);
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int j = lane + 32 * u;
-      if (j < T) Pb[(int64_t)i * T + j] = s[u] / den;
+      if (j < T) {
+        const float p = s[u] * den;
+        pr[j] = p;
+        Pb[(int64_t)i * T + j] = p;
+      }
     }
     __syncwarp();
     for (int d = lane; d < D; d += 32) {
       float a = 0.f;
-      for (int j = 0; j < T; ++j) a = fmaf(Pb[(int64_t)i * T + j], vs[j * D + d], a);
+      for (int j = 0; j < T; ++j) a = fmaf(pr[j], vs[j * (D + 1) + d], a);
       out[((int64_t)b * T + i) * E + h * D + d] = a;
     }
+    __syncwarp();
   }
 }
 
-// dqkv from dout: dV = P^T dO ; dP = dO V^T ; dS = P * (dP - rowsum(dP * P)) ; dQ = scale dS K ; dK = scale dS^T Q
-__global__ void __launch_bounds__(256) attn_train_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ P,
-                                                             const float* __restrict__ dout, float* __restrict__ dqkv, float* __restrict__ dS,
-                                                             int T, int H, int D, float scale) {
-  const int h = blockIdx.x, b = blockIdx.y;
+// backward, query-tiled half: dP = dO V^T ; dS = P * (dP - rowsum(dP * P)) -> scratch [B,H,T,T] ; dQ = scale dS K
+__global__ void __launch_bounds__(256) attn_train_bwd_q_kernel(const float* __restrict__ qkv, const float* __restrict__ P,
+                                                               const float* __restrict__ dout, float* __restrict__ dqkv,
+                                                               float* __restrict__ dS, int T, int H, int D, float scale) {
+  extern __shared__ float sm[];
+  float* ks = sm;                        // [T][D+1]
+  float* vs = ks + T * (D + 1);          // [T][D+1]
+  float* gs = vs + T * (D + 1);          // dO row per warp [8][64]
+  float* ds = gs + 8 * 64;               // dS row per warp [8][ATT_MAXT]
+  const int h = blockIdx.x, b = blockIdx.y, i0 = blockIdx.z * ATT_ROWS;
   const int E = H * D;
-  const float* base = qkv + (int64_t)b * T * 3 * E;
-  float* dbase = dqkv + (int64_t)b * T * 3 * E;
+  const float* base = qkv + (int64_t)b * T * 3 * E + h * D;
+  att_stage(ks, base + E, T, D, 3 * E);
+  att_stage(vs, base + 2 * E, T, D, 3 * E);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* Pb = P + ((int64_t)b * H + h) * T * T;
   float* dSb = dS + ((int64_t)b * H + h) * T * T;
-  const float* dO = dout + (int64_t)b * T * E + h * D;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  // pass 1: dS rows (one warp per query row)
-  for (int i = warp; i < T; i += nw) {
-    float dp[4];
+  float* go = gs + warp * 64;
+  float* dr = ds + warp * ATT_MAXT;
+  for (int i = i0 + warp; i < min(i0 + ATT_ROWS, T); i += 8) {
+    for (int d = lane; d < D; d += 32) go[d] = dout[((int64_t)b * T + i) * E + h * D + d];
+    __syncwarp();
+    float dp[4], pp[4];
     float dot = 0.f;
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int j = lane + 32 * u;
       dp[u] = 0.f;
+      pp[u] = 0.f;
       if (j < T) {
+        pp[u] = Pb[(int64_t)i * T + j];
         float a = 0.f;
-        for (int d = 0; d < D; ++d) a = fmaf(dO[(int64_t)i * E + d], base[(int64_t)j * 3 * E + 2 * E + h * D + d], a);
+        const float* vr = vs + j * (D + 1);
+        for (int d = 0; d < D; ++d) a = fmaf(go[d], vr[d], a);
         dp[u] = a;
-        dot += a * Pb[(int64_t)i * T + j];
+        dot = fmaf(a, pp[u], dot);
       }
     }
     dot = warp_sum(dot);
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int j = lane + 32 * u;
-      if (j < T) dSb[(int64_t)i * T + j] = Pb[(int64_t)i * T + j] * (dp[u] - dot);
+      if (j < T) {
+        const float v = pp[u] * (dp[u] - dot);
+        dr[j] = v;
+        dSb[(int64_t)i * T + j] = v;
+      }
     }
+    __syncwarp();
+    for (int d = lane; d < D; d += 32) {
+      float a = 0.f;
+      for (int j = 0; j < T; ++j) a = fmaf(dr[j], ks[j * (D + 1) + d], a);
+      dqkv[((int64_t)b * T + i) * 3 * E + h * D + d] = a * scale;
+    }
+    __syncwarp();
+  }
+}
+
+// backward, key-tiled half: dK[j] = scale sum_i dS[i,j] Q[i] ; dV[j] = sum_i P[i,j] dO[i]
+__global__ void __launch_bounds__(256) attn_train_bwd_kv_kernel(const float* __restrict__ qkv, const float* __restrict__ P,
+                                                                const float* __restrict__ dout, float* __restrict__ dqkv,
+                                                                const float* __restrict__ dS, int T, int H, int D, float scale) {
+  extern __shared__ float sm[];
+  float* qs = sm;                        // Q  [T][D+1]
+  float* gs = qs + T * (D + 1);          // dO [T][D+1]
+  float* dst = gs + T * (D + 1);         // dS^T tile [ATT_ROWS][ATT_MAXT]
+  float* pst = dst + ATT_ROWS * ATT_MAXT;  // P^T tile  [ATT_ROWS][ATT_MAXT]
+  const int h = blockIdx.x, b = blockIdx.y, j0 = blockIdx.z * ATT_ROWS;
+  const int E = H * D;
+  const float* base = qkv + (int64_t)b * T * 3 * E + h * D;
+  att_stage(qs, base, T, D, 3 * E);
+  att_stage(gs, dout + (int64_t)b * T * E + h * D, T, D, E);
+  const float* Pb = P + ((int64_t)b * H + h) * T * T;
+  const float* dSb = dS + ((int64_t)b * H + h) * T * T;
+  for (int idx = threadIdx.x; idx < T * ATT_ROWS; idx += blockDim.x) {
+    const int i = idx / ATT_ROWS, jj = idx - i * ATT_ROWS;
+    const int j = j0 + jj;
+    dst[jj * ATT_MAXT + i] = j < T ? dSb[(int64_t)i * T + j] : 0.f;
+    pst[jj * ATT_MAXT + i] = j < T ? Pb[(int64_t)i * T + j] : 0.f;
   }
   __syncthreads();
-  // pass 2: dQ[i,d] = scale sum_j dS[i,j] K[j,d] ; dK[j,d] = scale sum_i dS[i,j] Q[i,d] ; dV[j,d] = sum_i P[i,j] dO[i,d]
-  for (int idx = threadIdx.x; idx < T * D; idx += blockDim.x) {
-    const int t = idx / D, d = idx % D;
-    float aq = 0.f, ak = 0.f, av = 0.f;
-    for (int j = 0; j < T; ++j) {
-      aq = fmaf(dSb[(int64_t)t * T + j], base[(int64_t)j * 3 * E + E + h * D + d], aq);
-      ak = fmaf(dSb[(int64_t)j * T + t], base[(int64_t)j * 3 * E + h * D + d], ak);
-      av = fmaf(Pb[(int64_t)j * T + t], dO[(int64_t)j * E + d], av);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int jj = warp; jj < ATT_ROWS; jj += 8) {
+    const int j = j0 + jj;
+    if (j >= T) break;
+    const float* dcol = dst + jj * ATT_MAXT;
+    const float* pcol = pst + jj * ATT_MAXT;
+    for (int d = lane; d < D; d += 32) {
+      float ak = 0.f, av = 0.f;
+      for (int i = 0; i < T; ++i) {
+        ak = fmaf(dcol[i], qs[i * (D + 1) + d], ak);
+        av = fmaf(pcol[i], gs[i * (D + 1) + d], av);
+      }
+      dqkv[((int64_t)b * T + j) * 3 * E + E + h * D + d] = ak * scale;
+      dqkv[((int64_t)b * T + j) * 3 * E + 2 * E + h * D + d] = av;
     }
-    dbase[(int64_t)t * 3 * E + h * D + d] = aq * scale;
-    dbase[(int64_t)t * 3 * E + E + h * D + d] = ak * scale;
-    dbase[(int64_t)t * 3 * E + 2 * E + h * D + d] = av;
   }
 }
 
@@ -318,17 +398,48 @@ __global__ void __launch_bounds__(256) mse_loss_grad_kernel(const float* __restr
   if (threadIdx.x == 0) atomicAdd(loss, (double)acc * (double)loss_scale / (double)n);
 }
 
-__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
-                            float lr, float b1, float b2, float eps, float bc1, float bc2, float grad_scale) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float gi = g[i] * grad_scale;
-  const float mi = b1 * m[i] + (1.f - b1) * gi;
-  const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-  m[i] = mi;
-  v[i] = vi;
-  // torch.optim.Adam: p -= lr / bc1 * m / (sqrt(v) / sqrt(bc2) + eps)
-  p[i] -= lr / bc1 * mi / (sqrtf(vi) / sqrtf(bc2) + eps);
+// 4 elements per thread (16-byte loads / stores: the kernel is pure HBM streaming, 28 B per parameter + 2 B for the bf16 shadow)
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                   float* __restrict__ v, __nv_bfloat16* __restrict__ p16, int64_t n, float lr, float b1,
+                                                   float b2, float eps, float bc1, float bc2, float grad_scale) {
+  const int64_t i4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i4 >= n) return;
+  const float step = lr / bc1, rs2 = rsqrtf(bc2);
+  if (i4 + 4 <= n) {
+    const float4 gg = *reinterpret_cast<const float4*>(g + i4);
+    float4 mm = *reinterpret_cast<const float4*>(m + i4), vv = *reinterpret_cast<const float4*>(v + i4);
+    float4 pp = *reinterpret_cast<const float4*>(p + i4);
+    const float ga[4] = {gg.x * grad_scale, gg.y * grad_scale, gg.z * grad_scale, gg.w * grad_scale};
+    float ma[4] = {mm.x, mm.y, mm.z, mm.w}, va[4] = {vv.x, vv.y, vv.z, vv.w}, pa[4] = {pp.x, pp.y, pp.z, pp.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      ma[k] = b1 * ma[k] + (1.f - b1) * ga[k];
+      va[k] = b2 * va[k] + (1.f - b2) * ga[k] * ga[k];
+      // torch.optim.Adam: p -= lr / bc1 * m / (sqrt(v) / sqrt(bc2) + eps)
+      pa[k] -= step * ma[k] / (sqrtf(va[k]) * rs2 + eps);
+    }
+    *reinterpret_cast<float4*>(m + i4) = make_float4(ma[0], ma[1], ma[2], ma[3]);
+    *reinterpret_cast<float4*>(v + i4) = make_float4(va[0], va[1], va[2], va[3]);
+    *reinterpret_cast<float4*>(p + i4) = make_float4(pa[0], pa[1], pa[2], pa[3]);
+    if (p16) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(pa[0], pa[1]), hi = __floats2bfloat162_rn(pa[2], pa[3]);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(p16 + i4) = pk;
+    }
+  } else {
+    for (int64_t i = i4; i < n; ++i) {
+      const float gi = g[i] * grad_scale;
+      const float mi = b1 * m[i] + (1.f - b1) * gi;
+      const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+      m[i] = mi;
+      v[i] = vi;
+      const float pn = p[i] - step * mi / (sqrtf(vi) * rs2 + eps);
+      p[i] = pn;
+      if (p16) p16[i] = __float2bfloat16_rn(pn);
+    }
+  }
 }
 
 // y[i] = a[i] + b[i]
@@ -401,7 +512,15 @@ extern "C" int avi_ff_add_style_pe(float* x, const float* style, int64_t style_s
 
 extern "C" int avi_colsum(const float* x, float* out, int32_t R, int32_t N, int64_t ld, int32_t accumulate, void* stream) {
   AVI_REQUIRE(R > 0 && N > 0 && ld >= N, "avi_colsum: bad shape");
-  colsum_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(x, out, R, N, ld, accumulate);
+  int splits = (R + 127) / 128;
+  if (splits > 64) splits = 64;
+  const int rows_per_block = (R + splits - 1) / splits;
+  if (splits > 1 && !accumulate && cudaMemsetAsync(out, 0, sizeof(float) * (size_t)N, (cudaStream_t)stream) != cudaSuccess) {
+    set_error("avi_colsum: memset failed");
+    return 1;
+  }
+  colsum_kernel<<<dim3((N + 31) / 32, splits), dim3(32, 8), 0, (cudaStream_t)stream>>>(x, out, R, N, ld, rows_per_block, splits > 1 ? 1 : 0,
+                                                                                       accumulate);
   return check_launch("colsum");
 }
 
@@ -424,21 +543,34 @@ extern "C" int avi_layernorm_bwd(const float* x, const float* w, const float* dy
   return check_launch("layernorm_bwd");
 }
 
+static size_t att_smem_fwd(int T, int D) { return ((size_t)2 * T * (D + 1) + 8 * 64 + 8 * ATT_MAXT) * sizeof(float); }
+static size_t att_smem_kv(int T, int D) { return ((size_t)2 * T * (D + 1) + 2 * ATT_ROWS * ATT_MAXT) * sizeof(float); }
+
 extern "C" int avi_attn_train_fwd(const float* qkv, float* out, float* P, int32_t B, int32_t T, int32_t H, int32_t D, float scale,
                                   int32_t bias_mode, int32_t period, void* stream) {
-  AVI_REQUIRE(B > 0 && T > 0 && T <= 128 && H > 0 && D > 0 && D <= 64, "avi_attn_train_fwd: T <= 128 and D <= 64 (T=%d D=%d)", T, D);
-  const size_t smem = ((size_t)T * (D + 1) + (size_t)T * D) * sizeof(float);
-  static cudaError_t attr_err = cudaFuncSetAttribute(attn_train_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 129 * 4);
+  AVI_REQUIRE(B > 0 && T > 0 && T <= ATT_MAXT && H > 0 && D > 0 && D <= 64, "avi_attn_train_fwd: T <= 128 and D <= 64 (T=%d D=%d)", T, D);
+  AVI_REQUIRE(bias_mode == 0 || H == 4, "avi_attn_train_fwd: the FaceFormer bias mask is defined for 4 heads");
+  static cudaError_t attr_err = cudaFuncSetAttribute(attn_train_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     (int)att_smem_fwd(ATT_MAXT, 64));
   AVI_REQUIRE(attr_err == cudaSuccess, "avi_attn_train_fwd: cudaFuncSetAttribute failed");
-  attn_train_fwd_kernel<<<dim3(H, B), 256, smem, (cudaStream_t)stream>>>(qkv, out, P, T, H, D, scale, bias_mode, period > 0 ? period : 1);
+  attn_train_fwd_kernel<<<dim3(H, B, (T + ATT_ROWS - 1) / ATT_ROWS), 256, att_smem_fwd(T, D), (cudaStream_t)stream>>>(
+      qkv, out, P, T, H, D, scale, bias_mode, period > 0 ? period : 1);
   return check_launch("attn_train_fwd");
 }
 
 extern "C" int avi_attn_train_bwd(const float* qkv, const float* P, const float* dout, float* dqkv, float* dS_scratch, int32_t B, int32_t T,
                                   int32_t H, int32_t D, float scale, void* stream) {
-  AVI_REQUIRE(B > 0 && T > 0 && T <= 128 && H > 0 && D > 0, "avi_attn_train_bwd: bad shape");
-  attn_train_bwd_kernel<<<dim3(H, B), 256, 0, (cudaStream_t)stream>>>(qkv, P, dout, dqkv, dS_scratch, T, H, D, scale);
-  return check_launch("attn_train_bwd");
+  AVI_REQUIRE(B > 0 && T > 0 && T <= ATT_MAXT && H > 0 && D > 0 && D <= 64, "avi_attn_train_bwd: T <= 128 and D <= 64 (T=%d D=%d)", T, D);
+  static cudaError_t e1 = cudaFuncSetAttribute(attn_train_bwd_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)att_smem_fwd(ATT_MAXT, 64));
+  static cudaError_t e2 = cudaFuncSetAttribute(attn_train_bwd_kv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)att_smem_kv(ATT_MAXT, 64));
+  AVI_REQUIRE(e1 == cudaSuccess && e2 == cudaSuccess, "avi_attn_train_bwd: cudaFuncSetAttribute failed");
+  const dim3 grid(H, B, (T + ATT_ROWS - 1) / ATT_ROWS);
+  attn_train_bwd_q_kernel<<<grid, 256, att_smem_fwd(T, D), (cudaStream_t)stream>>>(qkv, P, dout, dqkv, dS_scratch, T, H, D, scale);
+  if (check_launch("attn_train_bwd_q")) return 1;
+  attn_train_bwd_kv_kernel<<<grid, 256, att_smem_kv(T, D), (cudaStream_t)stream>>>(qkv, P, dout, dqkv, dS_scratch, T, H, D, scale);
+  return check_launch("attn_train_bwd_kv");
 }
 
 extern "C" int avi_posconv_dw(const float* x, const float* dpc, float* dw, int32_t B, int32_t T, int32_t C, int32_t groups, int32_t k,
@@ -466,11 +598,15 @@ extern "C" int avi_mse_loss_grad(const float* out, const float* gt, float* dout,
   return check_launch("mse_loss_grad");
 }
 
-extern "C" int avi_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
-                             int32_t step, float grad_scale, void* stream) {
+extern "C" int avi_adam_step(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr, float beta1, float beta2,
+                             float eps, int32_t step, float grad_scale, void* stream) {
   AVI_REQUIRE(n > 0 && step >= 1, "avi_adam_step: bad arguments");
+  AVI_REQUIRE((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) % 16) == 0 && ((uintptr_t)p_bf16 % 8) == 0,
+              "avi_adam_step: buffers must be 16-byte aligned");
   const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
-  adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, bc1, bc2, grad_scale);
+  const int64_t n4 = (n + 3) / 4;
+  adam_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, reinterpret_cast<__nv_bfloat16*>(p_bf16), n, lr, beta1,
+                                                                            beta2, eps, bc1, bc2, grad_scale);
   return check_launch("adam");
 }
 

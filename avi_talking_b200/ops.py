@@ -57,10 +57,10 @@ def _need_cuda(*ts):
             raise RuntimeError("avi_talking_b200 ops need CUDA tensors (there is no CPU path)")
 
 
-def cast_bf16(src: torch.Tensor) -> torch.Tensor:
+def cast_bf16(src: torch.Tensor, out=None) -> torch.Tensor:
     _need_cuda(src)
     src = src.contiguous().float()
-    dst = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
+    dst = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device) if out is None else out
     _lib.check(_lib.load().avi_cast_f32_to_bf16(_ptr(src), _ptr(dst), C.c_int64(src.numel()), _stream()), "avi_cast_f32_to_bf16")
     return dst
 
@@ -607,10 +607,10 @@ def mse_loss_grad(out2d, gt2d, loss_scale):
     return loss, dout
 
 
-def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):
-    _need_cuda(p, g, m, v)
-    _chk(_lib.load().avi_adam_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), C.c_int64(p.numel()), C.c_float(lr), C.c_float(beta1), C.c_float(beta2),
-                                   C.c_float(eps), C.c_int32(step), C.c_float(grad_scale), _stream()), "avi_adam_step")
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0, p_bf16=None):
+    _need_cuda(p, g, m, v, p_bf16)
+    _chk(_lib.load().avi_adam_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(p_bf16), C.c_int64(p.numel()), C.c_float(lr), C.c_float(beta1),
+                                   C.c_float(beta2), C.c_float(eps), C.c_int32(step), C.c_float(grad_scale), _stream()), "avi_adam_step")
 
 
 def add_f32(a, b):

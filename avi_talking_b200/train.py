@@ -176,6 +176,26 @@ class GradBuckets:
         return 1.0 / self.world
 
 
+def shadow_tag(model):
+    """What the bf16 shadow of the flat parameter buffer is valid for: the fused optimizer's epoch and every parameter's version."""
+    lay = model._flat_layout
+    named = dict(model.named_parameters())
+    return (ops.WEIGHT_EPOCH, model._flat_params.data_ptr()) + tuple(named[n]._version for n in lay.names)
+
+
+def bf16_shadow(model):
+    """bf16 copy of the flat parameter buffer (same offsets): refreshed by the Adam kernel itself, or here by one cast launch when
+    the weights were changed by anything else (load_state_dict, a torch optimizer)."""
+    tag = shadow_tag(model)
+    if getattr(model, "_flat_params_bf16", None) is None:
+        model._flat_params_bf16 = torch.empty(model._flat_params.shape, dtype=torch.bfloat16, device=model._flat_params.device)
+        model._flat_params_bf16_tag = None
+    if model._flat_params_bf16_tag != tag:                  # in place: a captured graph may hold views of this buffer
+        ops.cast_bf16(model._flat_params, out=model._flat_params_bf16)
+        model._flat_params_bf16_tag = tag
+    return model._flat_params_bf16
+
+
 class FlatAdam:
     """torch.optim.Adam (no weight decay, no amsgrad) as one kernel over the flat parameter / gradient / moment buffers."""
 
@@ -199,17 +219,34 @@ class FlatAdam:
         if g is None:
             raise RuntimeError("FlatAdam.step: no gradient (run the training forward and loss.backward() first)")
         self.t += 1
-        ops.adam_step(self.p, g, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps, self.t, grad_scale)
+        bf16 = getattr(self.model, "precision", "bf16") == "bf16"
+        if bf16 and getattr(self.model, "_flat_params_bf16", None) is None:
+            self.model._flat_params_bf16 = torch.empty(self.p.shape, dtype=torch.bfloat16, device=self.p.device)
+        p16 = self.model._flat_params_bf16 if bf16 else None
+        ops.adam_step(self.p, g, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps, self.t, grad_scale, p_bf16=p16)
         ops.WEIGHT_EPOCH += 1          # the kernel rewrote the weights in place: every cached operand pack is stale
+        if bf16:                       # ... except the bf16 shadow of the flat buffer, which the same kernel just refreshed
+            self.model._flat_params_bf16_tag = shadow_tag(self.model)
 
 
 # ------------------------------------------------------------------------------------------------ the step
 class _Lin:
     """Operand plumbing of one precision."""
 
-    def __init__(self, bf16):
+    def __init__(self, bf16, flat32=None, flat16=None):
         self.bf16 = bf16
         self.dt = torch.bfloat16 if bf16 else torch.float32
+        self.flat32, self.flat16 = flat32, flat16
+
+    def w(self, W32):
+        """GEMM operand of a weight: for a dense view of the flat parameter buffer, the same view of its bf16 shadow (no launch)."""
+        if not self.bf16:
+            return W32
+        if self.flat16 is not None and W32.is_contiguous():
+            off = (W32.data_ptr() - self.flat32.data_ptr()) // 4
+            if 0 <= off and off + W32.numel() <= self.flat32.numel():
+                return self.flat16[off:off + W32.numel()].view(W32.shape)
+        return ops.cast_bf16(W32)
 
     def a(self, x32):                     # [M, K] fp32 contiguous -> GEMM operand
         return ops.cast_bf16(x32) if self.bf16 else x32
@@ -218,7 +255,7 @@ class _Lin:
         return ops.transpose_cast(x32, self.dt, R_pad)
 
     def fwd(self, x_op, W32, b, residual=None, act=0):
-        return ops.linear(x_op, self.a(W32), b, residual=residual, act=act, out_dtype=torch.float32)
+        return ops.linear(x_op, self.w(W32), b, residual=residual, act=act, out_dtype=torch.float32)
 
     def bwd(self, dy32, x32, W32, gW, gb, Mp, want_dx=True, residual=None, dy_op=None, xT=None):
         """y = x W^T + b. gW [N, K] <- dy^T x ; gb [N] <- colsum(dy) ; returns dx = dy W (+ residual) or None."""
@@ -290,7 +327,7 @@ class TrainStep:
         fd = m.args.feature_dim
         if bf16 and fd % 64 != 0:
             raise NotImplementedError("bf16 training needs feature_dim % 64 == 0 (use precision='fp32')")
-        self.lin = lin = _Lin(bf16)
+        self.lin = lin = _Lin(bf16, m._flat_params, bf16_shadow(m) if bf16 else None)
         B, T, V3 = gt_verts.shape
         M = B * T
         if T > 128:
@@ -336,7 +373,10 @@ class TrainStep:
         # -- heads and the teacher-forced decoder layer (faceformer_vert.py:369,437-454)
         S["mem"] = mem = lin.fwd(lin.a(x), m.audio_feature_map.weight, m.audio_feature_map.bias)
         V3p = _pad(V3)
-        template = m.template.to(audio.device).reshape(-1).float().contiguous()
+        if getattr(self, "_template", None) is None or self._template_src is not m.template:
+            self._template_src = m.template                   # cached on the device (no H2D inside a graph capture)
+            self._template = m.template.to(audio.device).reshape(-1).float().contiguous()
+        template = self._template
         S["vin"] = vin = ops.tf_input_rows(gt_verts, template, V3p)                                    # :443-444
         Wvm_p = ops.cast_pad2d(m.vertice_map.weight, lin.dt, C_pad=V3p)
         xd = ops.linear(lin.a(vin), Wvm_p, m.vertice_map.bias, out_dtype=torch.float32)               # :445
@@ -361,7 +401,7 @@ class TrainStep:
         S["x3"] = x3 = ops.layernorm(y3, dl.norm3.weight, dl.norm3.bias, eps=1e-5)[0]
         out = ops.empty_rows(M, V3, audio.device)
         bias = (m.vertice_map_r.bias + template).contiguous()                                          # + template (:475)
-        ops.gemm(lin.a(x3), lin.a(m.vertice_map_r.weight), bias, out, rows=M, N=V3, K=fd, a_rows_alloc=M, c_ld=out.stride(0))
+        ops.gemm(lin.a(x3), lin.w(m.vertice_map_r.weight), bias, out, rows=M, N=V3, K=fd, a_rows_alloc=M, c_ld=out.stride(0))
         loss64, dout = ops.mse_loss_grad(out, gt_verts.reshape(M, V3), 10.0)                           # :481-482
         S["dout"] = dout
         self.saved = S
@@ -491,3 +531,57 @@ def training_loss(step: TrainStep, audio, gt_verts):
     """Differentiable-looking loss: a 0-dim tensor whose .backward() fills every trainable parameter's .grad (flat views)."""
     anchor = torch.zeros((), device=audio.device, requires_grad=True)
     return _LossFn.apply(anchor, step, audio, gt_verts)
+
+
+class GraphedTrainStep:
+    """forward + backward of one fixed-shape step captured ONCE in a CUDA graph (the batch-1 step is ~700 short launches: replaying
+    the graph removes the per-launch host cost). Adam stays outside the graph (its bias corrections depend on the step count):
+
+        gstep = GraphedTrainStep(model, audio.shape, gt.shape); opt = FlatAdam(model)
+        loss = gstep(audio, gt); opt.step()
+
+    Single-process only (the bucketed all-reduce of the data-parallel path runs eagerly, see TrainStep)."""
+
+    def __init__(self, model, audio_shape, gt_shape, warmup=2):
+        self.model = model
+        self.step = TrainStep(model)
+        dev = model._flat_params.device
+        self.audio = torch.zeros(audio_shape, dtype=torch.float32, device=dev)
+        self.gt = torch.zeros(gt_shape, dtype=torch.float32, device=dev)
+        self.graph = None
+        self.warmup = warmup
+        self.tag = None
+
+    def _capture(self):
+        m = self.model
+        if m.precision == "bf16":
+            bf16_shadow(m)
+        side = torch.cuda.Stream(device=self.audio.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(self.warmup):                       # one-time attribute calls, allocator warm-up
+                self.step.forward(self.audio, self.gt)
+                self.step.backward()
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self.step.forward(self.audio, self.gt)
+            self.step.backward()
+        self.grad = m._flat_grad
+        self.tag = (m.precision, m._flat_params.data_ptr())
+
+    def __call__(self, audio, gt_verts):
+        m = self.model
+        self.audio.copy_(audio)
+        self.gt.copy_(gt_verts)
+        if self.graph is None or self.tag != (m.precision, m._flat_params.data_ptr()):
+            self._capture()
+        if m.precision == "bf16":
+            bf16_shadow(m)                                     # refreshed in place by FlatAdam; re-cast here only if someone else wrote
+        self.graph.replay()
+        m._flat_grad = self.grad
+        lay = m._flat_layout
+        for n, p in m.named_parameters():
+            if n in lay.offsets:
+                p.grad = lay.view(self.grad, n)
+        return self.loss

@@ -303,9 +303,10 @@ int avi_weightnorm_bwd(const float* v, const float* g, const float* dw, float* d
 /* loss = mean((out - gt)^2) * loss_scale (fp64 scalar on the device) ; dout = d loss / d out (dense [rows, C]) */
 int avi_mse_loss_grad(const float* out, const float* gt, float* dout, double* loss, int64_t rows, int32_t C, int64_t out_ld, int64_t gt_ld,
                       float loss_scale, void* stream);
-/* torch.optim.Adam step on a flat fp32 buffer; grad_scale multiplies the gradient first (1 / world_size after a sum all-reduce) */
-int avi_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps, int32_t step,
-                  float grad_scale, void* stream);
+/* torch.optim.Adam step on a flat fp32 buffer; grad_scale multiplies the gradient first (1 / world_size after a sum all-reduce);
+ * p_bf16 (may be NULL) receives the bf16 copy of the updated parameters (the GEMM operands of the next step) */
+int avi_adam_step(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr, float beta1, float beta2, float eps,
+                  int32_t step, float grad_scale, void* stream);
 int avi_add_f32(const float* a, const float* b, float* y, int64_t n, void* stream);
 /* align_corners linear resample over time only (models/lib/wav2vec.py:67-73), fp32 output [B*T_out, C] */
 int avi_w2v_lerp(const void* in, int32_t in_dtype, int64_t in_batch_stride, float* out, int32_t B, int32_t T_in, int32_t T_out, int32_t C,

@@ -160,3 +160,30 @@ def test_three_adam_steps_track_the_oracle_and_refresh_inference_packs():
         assert d <= 1.5e-4, (nme, d)            # 3 steps of lr 1e-4: sign flips of near-zero gradients cost at most ~1 lr each
     v1 = m.predict_from_embeddings(audio)
     assert (v1 - v0).abs().max().item() > 0.0
+
+
+def test_graphed_step_matches_eager():
+    """The CUDA-graph replay of forward + backward gives the eager step's loss and gradients (atomics reorder sums only)."""
+    fd, B, n, T = 64, 2, 16000, 24
+    template = synth.flame_buffers()["v_template"].reshape(1, 1, 15069)
+    gt = (template + 1e-3 * torch.from_numpy(np.random.default_rng(6).normal(size=(B, T, 15069)).astype(np.float32))).cuda()
+    audio = synth.audio(B, n, seed=98).cuda()
+    res = []
+    for graphed in (False, True):
+        m = build_vert("bf16", fd, 264)
+        opt = train.FlatAdam(m, lr=1e-4)
+        gstep = train.GraphedTrainStep(m, audio.shape, gt.shape) if graphed else None
+        losses = []
+        for _ in range(3):
+            if graphed:
+                loss = gstep(audio, gt)
+            else:
+                opt.zero_grad()
+                loss = m.training_loss(audio, gt)
+                loss.backward()
+            losses.append(float(loss.detach()))
+            opt.step()
+        torch.cuda.synchronize()
+        res.append((losses, m._flat_params.clone()))
+    np.testing.assert_allclose(res[0][0], res[1][0], rtol=2e-3)
+    assert (res[0][1] - res[1][1]).abs().max().item() <= 2.5e-4      # 3 Adam steps of lr 1e-4: sign noise of ~zero gradients only
