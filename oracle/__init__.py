@@ -16,8 +16,14 @@ Pinning status (see DESIGN.md "Oracle"):
     /root/reference in the build container and commits their outputs on seeded
     inputs under ``tests/golden/``; ``tests/test_oracle_golden.py`` checks the
     restatement against them.
-  * dalle2_pytorch-based diffusion prior sampler and the INFERNO EMOTE decoder
-    (un-importable here: dalle2_pytorch / pytorch_lightning / omegaconf are not
-    vendored nor installed): PARITY UNPINNED - restated from the reference's
-    call sites and the published algorithm.
+  * INFERNO EMOTE decoder (emote_oracle.py): PINNED - the reference's own classes
+    run through oracle/_inferno_import.py (pytorch_lightning / omegaconf / munch
+    stubbed at import) -> tests/golden/emote.npz.
+  * faceformer_vert training step (train_oracle.py): PINNED - the reference's own
+    forward_switch_frame + loss.backward() + torch.optim.Adam -> tests/golden/train.npz
+    (deterministic mode: dropout / SpecAugment / LayerDrop inactive).
+  * Diffusion prior (prior_oracle.py): the reference's own class sources are pinned
+    (executed over oracle/dalle2_standin.py -> tests/golden/prior.npz); the stand-in
+    for the un-vendored, un-pinned dalle2_pytorch / rotary_embedding_torch is a
+    restatement of the published modules: PARITY UNPINNED for that part.
 """
