@@ -63,10 +63,12 @@ struct Tc2Params {
   int m_tiles, n_tiles, total_tiles;  // m_tiles counts 256-row pair tiles per batch entry
   int64_t c_ld, c_batch_stride, res_ld, res_batch_stride;
   int vec_ok;      // outputs (and residual) are 16-byte addressable per 32-column chunk
+  int tma_store;   // 0: threads store; 1: staged tiles leave through TMA stores (map_c); 2: TMA reduce-add (C += ..., residual == C)
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P2_THREADS, 1)
-gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const Tc2Params p) {
+gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                     const __grid_constant__ CUtensorMap map_c, const Tc2Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];  // no static shared memory in this kernel: the dynamic window starts aligned
   if ((smem_u32(smem) & 1023u) != 0) __trap();        // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* smem_a = smem;
@@ -87,6 +89,7 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
     for (int s = 0; s < P2_STAGES; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 1);
       mbar_init(smem_u32(&empty_bar[s]), 1);
@@ -247,7 +250,49 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         // staging tile: 32 rows x 16 words (pitch 16); the 4-word group g of row r lives at group g ^ ((r >> 1) & 3), which
         // keeps the row-per-lane writes and the row-segment reads below conflict-free
         const uint32_t wr_row = tile + lane * 64, wr_sw = (lane >> 1) & 3;
-        if (fast_bf16 && full_n) {
+        if (p.tma_store) {
+          // The staging tile (32 rows x 64 bytes, 16-byte chunk g of row r at g ^ ((r >> 1) & 3)) IS the SWIZZLE_64B shared-memory
+          // box of map_c: one thread hands it to the TMA unit, which clips rows >= p.rows and columns >= p.N. No shared loads,
+          // no global store instructions: the LSU pipe carries the st.shared traffic only.
+          if (p.c_dtype == AVI_DT_BF16) {
+            if (lane == 0) bulk_wait_read0();
+            __syncwarp();
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint32_t w[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(f[8 * g + 2 * u], f[8 * g + 2 * u + 1]);
+                w[u] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+              sts128(wr_row + 16 * (g ^ wr_sw), w[0], w[1], w[2], w[3]);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_3d(tile, &map_c, n_base, row_base, b);
+              bulk_commit();
+            }
+          } else {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              if (n_base + 16 * hh >= p.N) break;
+              if (lane == 0) bulk_wait_read0();
+              __syncwarp();
+#pragma unroll
+              for (int gg = 0; gg < 4; ++gg)
+                sts128(wr_row + 16 * (gg ^ wr_sw), __float_as_uint(f[16 * hh + 4 * gg]), __float_as_uint(f[16 * hh + 4 * gg + 1]),
+                       __float_as_uint(f[16 * hh + 4 * gg + 2]), __float_as_uint(f[16 * hh + 4 * gg + 3]));
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                if (p.tma_store == 2) tma_reduce_add_3d(tile, &map_c, n_base + 16 * hh, row_base, b);
+                else tma_store_3d(tile, &map_c, n_base + 16 * hh, row_base, b);
+                bulk_commit();
+              }
+            }
+          }
+        } else if (fast_bf16 && full_n) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             uint32_t w[4];
@@ -385,6 +430,7 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(as ? te_leader1 : te_leader0);
     }
+    if (p.tma_store && lane == 0) bulk_wait_all();   // every store of this thread's bulk groups has been performed
   }
 
   tc_fence_before();
@@ -473,6 +519,26 @@ extern "C" int avi_gemm_bf16_tc(const AviGemmArgs* a, void* stream) {
              (a->C2 == nullptr || (uintptr_t)a->C2 % 16 == 0);
   if (a->residual) vec = vec && (a->res_ld % 4 == 0) && (a->res_batch_stride % 4 == 0) && ((uintptr_t)a->residual % 16 == 0);
   p.vec_ok = vec ? 1 : 0;
+  // TMA-store epilogue: single output, 16-byte addressable rows; a residual is supported when it IS the output (in-place update
+  // of the fp32 residual stream through TMA reduce-add)
+  static const bool no_tma_store = getenv("AVI_GEMM_NO_TMA_STORE") != nullptr;
+  const bool inplace_res = a->residual != nullptr && (const void*)a->residual == (const void*)a->C && a->c_dtype == AVI_DT_F32 &&
+                           a->res_ld == a->c_ld && a->res_batch_stride == a->c_batch_stride;
+  p.tma_store = 0;
+  CUtensorMap map_c = map_a;
+  if (!no_tma_store && vec && a->C2 == nullptr && (a->residual == nullptr || inplace_res)) {
+    const uint64_t es = a->c_dtype == AVI_DT_F32 ? 4 : 2;
+    uint64_t dims[3] = {(uint64_t)a->N, (uint64_t)a->rows, (uint64_t)a->batch};
+    uint64_t strides[2] = {(uint64_t)a->c_ld * es, (uint64_t)a->c_batch_stride * es};
+    if (a->batch == 1) strides[1] = dims[1] * strides[0];
+    uint32_t box[3] = {a->c_dtype == AVI_DT_F32 ? 16u : 32u, 32u, 1u};
+    if (encode_map(&map_c, a->C, 3, dims, strides, box,
+                   a->c_dtype == AVI_DT_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                   CU_TENSOR_MAP_SWIZZLE_64B))
+      return 1;
+    p.tma_store = inplace_res ? 2 : 1;
+    if (inplace_res) p.residual = nullptr;   // the memory system performs the addition
+  }
 
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
@@ -482,6 +548,6 @@ extern "C" int avi_gemm_bf16_tc(const AviGemmArgs* a, void* stream) {
   AVI_REQUIRE(attr_err == cudaSuccess, "avi_gemm_bf16_tc: cannot opt in to %u bytes of shared memory: %s", P2_SMEM_BYTES,
               cudaGetErrorString(attr_err));
   const int pairs = p.total_tiles < kNumSMs / 2 ? p.total_tiles : kNumSMs / 2;
-  gemm_bf16_tc2_kernel<<<2 * pairs, P2_THREADS, P2_SMEM_BYTES, (cudaStream_t)stream>>>(map_a, map_w, p);
+  gemm_bf16_tc2_kernel<<<2 * pairs, P2_THREADS, P2_SMEM_BYTES, (cudaStream_t)stream>>>(map_a, map_w, map_c, p);
   return check_launch("gemm_bf16_tc");
 }

@@ -174,7 +174,9 @@ class Wav2Vec2Model(_HFWav2Vec2Model):
                      algorithmic_flops=2.0 * B * T * 192 * k * (Cc // cfg.num_conv_pos_embedding_groups))
         return ops.posconv_merge_ln(proj, pc, P["enc_ln_w"], P["enc_ln_b"], want_bf16=True, eps=cfg.layer_norm_eps)
 
-    def _encoder_layer(self, h32, h16, Lw, B, T):
+    def _encoder_layer(self, h32, h16, Lw, B, T, inplace=False):
+        """inplace (bf16 tensor-core path only): the two residual additions update the fp32 residual stream where it lies - the
+        GEMM epilogue leaves through TMA reduce-add, so the residual is never read by an SM nor written to a second buffer."""
         bf16 = self.precision == "bf16"
         H = self.config.num_attention_heads
         D = self.config.hidden_size // H
@@ -182,10 +184,10 @@ class Wav2Vec2Model(_HFWav2Vec2Model):
         adt = torch.bfloat16 if bf16 else torch.float32
         qkv = ops.linear(a_in, Lw["qkv_w"], Lw["qkv_b"], out_dtype=adt)
         att = ops.mha(qkv, B, T, H, D, D ** -0.5)
-        y = ops.linear(att, Lw["o_w"], Lw["o_b"], residual=h32, out_dtype=torch.float32)
+        y = ops.linear(att, Lw["o_w"], Lw["o_b"], residual=h32, out_dtype=torch.float32, out=h32 if inplace else None)
         h1_32, h1_16 = ops.layernorm(y, Lw["ln1_w"], Lw["ln1_b"], want_bf16=bf16, eps=self.config.layer_norm_eps)
         f = ops.linear(h1_16 if bf16 else h1_32, Lw["ff1_w"], Lw["ff1_b"], act=ACT_GELU, out_dtype=adt)
-        y2 = ops.linear(f, Lw["ff2_w"], Lw["ff2_b"], residual=h1_32, out_dtype=torch.float32)
+        y2 = ops.linear(f, Lw["ff2_w"], Lw["ff2_b"], residual=h1_32, out_dtype=torch.float32, out=h1_32 if inplace else None)
         return ops.layernorm(y2, Lw["ln2_w"], Lw["ln2_b"], want_bf16=bf16, eps=self.config.layer_norm_eps)
 
     # ------------------------------------------------------------------ reference signature
@@ -217,7 +219,7 @@ class Wav2Vec2Model(_HFWav2Vec2Model):
                                       eps=cfg.layer_norm_eps)
         all_hidden = (h32.view(B, T, -1),) if output_hidden_states else None
         for Lw in P["layers"]:                                                               # :142-148
-            h32, h16 = self._encoder_layer(h32, h16, Lw, B, T)
+            h32, h16 = self._encoder_layer(h32, h16, Lw, B, T, inplace=bf16 and not output_hidden_states)
             if output_hidden_states:
                 all_hidden = all_hidden + (h32.view(B, T, -1),)
         out = h32.view(B, T, cfg.hidden_size)

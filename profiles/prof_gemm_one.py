@@ -27,12 +27,20 @@ if which == "conv1":
 else:
     n, k, act, odt, res = {"qkv": (2304, 768, ACT_NONE, torch.bfloat16, False), "oproj": (768, 768, ACT_NONE, torch.float32, True),
                            "ffn1": (3072, 768, ACT_GELU, torch.bfloat16, False), "ffn2": (768, 3072, ACT_NONE, torch.float32, True),
-                           "vhead": (15069, 192, ACT_NONE, torch.float32, False)}[which]
+                           "vhead": (15069, 192, ACT_NONE, torch.float32, False), "vheadp": (15069, 192, ACT_NONE, torch.float32, False),
+                           "vhead64": (15069, 64, ACT_NONE, torch.float32, False)}[which]
     a, w, bias = rnd(M, k), rnd(n, k, scale=0.03), rnd(n, dtype=torch.float32)
     r = rnd(M, n, dtype=torch.float32) if res else None
-    o = torch.empty((M, n), dtype=odt, device=dev)
-    fn = lambda: ops.gemm(a, w, bias, o, rows=M, N=n, K=k, act=act, residual=r, a_rows_alloc=M)  # noqa: E731
+    ld = 15072 if which in ("vheadp", "vhead64") else n      # 16-byte aligned vertex rows (ops.empty_rows)
+    o = torch.empty((M, ld), dtype=odt, device=dev)
+    fn = lambda: ops.gemm(a, w, bias, o, rows=M, N=n, K=k, act=act, residual=r, a_rows_alloc=M, c_ld=ld)  # noqa: E731
 for _ in range(3):
     fn()
 torch.cuda.synchronize()
-print("ok", which)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(10):
+    fn()
+e1.record()
+torch.cuda.synchronize()
+print("ok", which, "%.4f ms" % (e0.elapsed_time(e1) / 10))
