@@ -9,8 +9,9 @@
 //             fp32 convolution to ~2^-16 relative; only lo*lo is dropped)
 //   D       : four TMEM accumulators of 128 lanes x 128 columns (one per 128-channel group), each released as soon as its epilogue
 //             warps have drained it, so the MMAs of tile i+1 overlap the epilogue of tile i
-//   epilogue: 16 warps; y = acc * scale[b,c] + shift[b,c] (GroupNorm folded into one FMA), branch-free GELU, bf16, smem transpose,
-//             16-byte coalesced stores.
+//   epilogue: 16 warps; y = acc * scale[b,c] + shift[b,c] (GroupNorm folded into one FMA), branch-free GELU, bf16, written row-per-lane
+//             into a double-buffered SWIZZLE_64B staging tile that one lane hands to the TMA unit (no shared loads, no global store
+//             instructions: the LSU pipe carries the st.shared traffic only).
 // GroupNorm statistics are exact and cost one pass over the AUDIO only: y is linear in the 10-sample window, so
 //   sum_t y = w . S1,  sum_t y^2 = w^T R w   with  S1[j] = sum_t x[5t+j],  R[j][j'] = sum_t x[5t+j] x[5t+j']   (65 moments / clip, fp64).
 #include "tc_common.cuh"
@@ -26,12 +27,15 @@ constexpr uint32_t CZ_OFF_W = 2 * CZ_A_BYTES;
 constexpr uint32_t CZ_OFF_X = CZ_OFF_W + CZ_W_BYTES;    // audio staging: 2 stages x 656 floats
 constexpr uint32_t CZ_X_FLOATS = 656;
 constexpr uint32_t CZ_OFF_SS = CZ_OFF_X + 2 * CZ_X_FLOATS * 4;   // scale | shift of the current clip: 2 x 512 floats, 2 stages
-constexpr uint32_t CZ_OFF_TRANS = CZ_OFF_SS + 2 * 2 * CZ_C * 4;
-constexpr uint32_t CZ_TRANS_WARP = 32 * 16 * 4;
+// epilogue staging: two 2 KB tiles per warp (32 rows x 64 bytes, SWIZZLE_64B boxes of the output tensor map), 1 KB aligned so that
+// the hardware swizzle (address bits [7,9) into bits [4,6)) is the (row >> 1) & 3 pattern the writers use
+constexpr uint32_t CZ_OFF_TRANS = (CZ_OFF_SS + 2 * 2 * CZ_C * 4 + 1023) / 1024 * 1024;
+constexpr uint32_t CZ_TRANS_TILE = 32 * 16 * 4;
+constexpr uint32_t CZ_TRANS_WARP = 2 * CZ_TRANS_TILE;
 constexpr uint32_t CZ_OFF_BAR = CZ_OFF_TRANS + CZ_EPI_WARPS * CZ_TRANS_WARP;
 constexpr uint32_t CZ_SMEM = CZ_OFF_BAR + 256;
 static_assert(CZ_SMEM <= 232448, "shared memory budget");
-static_assert(CZ_OFF_X % 16 == 0 && CZ_OFF_SS % 16 == 0 && CZ_OFF_TRANS % 16 == 0 && CZ_OFF_BAR % 8 == 0, "alignment");
+static_assert(CZ_OFF_X % 16 == 0 && CZ_OFF_SS % 16 == 0 && CZ_OFF_TRANS % 1024 == 0 && CZ_OFF_BAR % 8 == 0, "alignment");
 
 // ---------------------------------------------------------------------------------------------- GroupNorm statistics
 __global__ void __launch_bounds__(256) conv0_moments_kernel(const float* __restrict__ audio, double* __restrict__ mom, int n_samples,
@@ -127,7 +131,8 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-__global__ void __launch_bounds__(CZ_THREADS, 1) conv0_tc_kernel(const __grid_constant__ CUtensorMap map_w, const Conv0Params p) {
+__global__ void __launch_bounds__(CZ_THREADS, 1) conv0_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_out,
+                                                                 const Conv0Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + CZ_OFF_BAR);
@@ -143,6 +148,7 @@ __global__ void __launch_bounds__(CZ_THREADS, 1) conv0_tc_kernel(const __grid_co
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_out) : "memory");
     mbar_init(smem_u32(w_full), 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&a_full[s]), CZ_BUILD_WARPS);
@@ -250,7 +256,6 @@ __global__ void __launch_bounds__(CZ_THREADS, 1) conv0_tc_kernel(const __grid_co
       mbar_wait(smem_u32(&tmem_full[q]), it & 1);
       tc_fence_after();
       const uint32_t ssa = smem_u32(smem + CZ_OFF_SS) + s * (2 * CZ_C * 4);
-      __nv_bfloat16* ob = p.out + (int64_t)b * p.out_batch_stride + (int64_t)(t0 + quarter * 32) * CZ_C + q * CZ_BN;
 #pragma unroll 1
       for (int ch = 0; ch < 4; ++ch) {
         const int c0 = q * CZ_BN + ch * 32;
@@ -266,22 +271,20 @@ __global__ void __launch_bounds__(CZ_THREADS, 1) conv0_tc_kernel(const __grid_co
           f[4 * j + 2] = gelu_fast(fmaf(__uint_as_float(v[4 * j + 2]), sc.z, sh.z));
           f[4 * j + 3] = gelu_fast(fmaf(__uint_as_float(v[4 * j + 3]), sc.w, sh.w));
         }
-        const uint32_t wr_row = tile + lane * 64, wr_sw = (lane >> 1) & 3;
+        const uint32_t buf = tile + (ch & 1) * CZ_TRANS_TILE;
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store that used this buffer has read it
+        __syncwarp();
+        const uint32_t wr_row = buf + lane * 64, wr_sw = (lane >> 1) & 3;
 #pragma unroll
         for (int g = 0; g < 4; ++g)
           sts128(wr_row + 16 * (g ^ wr_sw), pack_bf16x2(f[8 * g], f[8 * g + 1]), pack_bf16x2(f[8 * g + 2], f[8 * g + 3]),
                  pack_bf16x2(f[8 * g + 4], f[8 * g + 5]), pack_bf16x2(f[8 * g + 6], f[8 * g + 7]));
+        fence_proxy_async_smem();
         __syncwarp();
-        const int g = lane & 3;
-#pragma unroll
-        for (int i8 = 0; i8 < 4; ++i8) {
-          const int r = i8 * 8 + (lane >> 2);
-          if (r < rows_valid) {
-            const uint4 qv = lds128(tile + (r * 16 + 4 * (g ^ ((r >> 1) & 3))) * 4);
-            *reinterpret_cast<uint4*>(ob + (int64_t)r * CZ_C + ch * 32 + 8 * g) = qv;
-          }
+        if (lane == 0 && rows_valid > 0) {                     // rows >= L0 are clipped by the tensor map
+          tma_store_3d(buf, &map_out, c0, t0 + quarter * 32, b);
+          bulk_commit();
         }
-        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
@@ -292,6 +295,7 @@ __global__ void __launch_bounds__(CZ_THREADS, 1) conv0_tc_kernel(const __grid_co
     }
   }
 
+  if (warp > CZ_BUILD_WARPS && lane == 0) bulk_wait_all();
   tc_fence_before();
   __syncthreads();
   if (warp == CZ_BUILD_WARPS) {
@@ -338,6 +342,13 @@ extern "C" int avi_w2v_conv0_gn_gelu_tc(const float* audio, const float* w, cons
     uint32_t box[2] = {64, CZ_BN};
     if (encode_map(&map_w, w_packed, 2, dims, strides, box)) return 1;
   }
+  CUtensorMap map_out;
+  {
+    uint64_t dims[3] = {(uint64_t)CZ_C, (uint64_t)L0, (uint64_t)B};
+    uint64_t strides[2] = {(uint64_t)CZ_C * 2, (uint64_t)out_batch_stride * 2};
+    uint32_t box[3] = {32, 32, 1};
+    if (encode_map(&map_out, out, 3, dims, strides, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+  }
   Conv0Params p;
   p.audio = audio;
   p.scale = scale;
@@ -353,6 +364,6 @@ extern "C" int avi_w2v_conv0_gn_gelu_tc(const float* audio, const float* w, cons
   std::call_once(once, [] { attr_err = cudaFuncSetAttribute(conv0_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CZ_SMEM); });
   AVI_REQUIRE(attr_err == cudaSuccess, "avi_w2v_conv0_gn_gelu_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
   const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
-  conv0_tc_kernel<<<grid, CZ_THREADS, CZ_SMEM, st>>>(map_w, p);
+  conv0_tc_kernel<<<grid, CZ_THREADS, CZ_SMEM, st>>>(map_w, map_out, p);
   return check_launch("conv0_tc");
 }

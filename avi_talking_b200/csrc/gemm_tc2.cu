@@ -120,7 +120,10 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         const int mt = t / p.n_tiles;
         const int b = mt / p.m_tiles, m_blk = mt % p.m_tiles;
         const int row0 = m_blk * (2 * P2_BM) + (int)rank * P2_BM;
-        const int wrow0 = n_blk * P2_BN + (int)rank * P2_BNH;
+        // the last n-tile may be narrower than 256: the MMA is issued with N = n_eff (a multiple of 32), of which each CTA of the pair
+        // supplies n_eff / 2 rows of W (the box still brings 128 rows; the surplus is not read)
+        const int n_eff = min(P2_BN, ((p.N - n_blk * P2_BN + 31) >> 5) << 5);
+        const int wrow0 = n_blk * P2_BN + (int)rank * (n_eff >> 1);
         // tap / phase / super-row / channel-block counters advance incrementally: this single thread paces the whole pipeline,
         // and four runtime integer divisions per k-block cost about as much as the MMAs of that k-block
         int kin = 0, ph = 0, sr = 0;
@@ -149,14 +152,16 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA, one thread) =====================
     if (rank == 0 && lane == 0) {
-      // instruction descriptor: D=f32, A=B=bf16, both K-major, N=256, M=256 (pair)
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P2_BN >> 3) << 17) | ((uint32_t)((2 * P2_BM) >> 4) << 24);
+      // instruction descriptor: D=f32, A=B=bf16, both K-major, N=n_eff (256 except in a narrower last n-tile), M=256 (pair)
+      const uint32_t idesc_base = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * P2_BM) >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
       for (int t = pair; t < p.total_tiles; t += num_pairs, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
+        const int n_eff = min(P2_BN, ((p.N - (t % p.n_tiles) * P2_BN + 31) >> 5) << 5);
+        const uint32_t idesc = idesc_base | ((uint32_t)(n_eff >> 3) << 17);
         TL(1, it, 0);
         mbar_wait(smem_u32(&tmem_empty[as]), aphase ^ 1);
         TL(1, it, 1);

@@ -170,6 +170,8 @@ class Faceformer(nn.Module):
         P["ca_v_w"], P["ca_v_b"] = f32(Wc[2 * fd:]), f32(bc[2 * fd:])
         P["ca_o_w"], P["ca_o_b"] = f32(lyr.multihead_attn.out_proj.weight), f32(lyr.multihead_attn.out_proj.bias)
         P["afm_w"], P["afm_b"] = f32(self.audio_feature_map.weight), f32(self.audio_feature_map.bias)
+        if self.precision == "bf16":
+            P["afm_w16"] = ops.cast_bf16(self.audio_feature_map.weight)
         if self.variant == "disentangle":
             P["merge_w"], P["merge_b"] = f32(self.v_merge2hidden.weight), f32(self.v_merge2hidden.bias)
         P["vm_w"], P["vm_b"] = f32(self.vertice_map.weight), f32(self.vertice_map.bias)
@@ -263,7 +265,12 @@ class Faceformer(nn.Module):
         obj_embedding = ops.linear(one_hot, P["obj_w"], None)                                  # :771-773
         hs_a = self.audio_encoder(audio, self.dataset).last_hidden_state                      # :775
         T = hs_a.shape[1]
-        hs_a = ops.linear(hs_a.reshape(B * T, -1), P["afm_w"], P["afm_b"]).view(B, T, -1)       # :776
+        h16 = getattr(self.audio_encoder, "last_hidden_state_bf16", None)
+        if self.precision == "bf16" and h16 is not None and "afm_w16" in P:
+            # the encoder already produced the bf16 copy of its output for the next tensor-core contraction
+            hs_a = ops.linear(h16.reshape(B * T, -1), P["afm_w16"], P["afm_b"], out_dtype=torch.float32).view(B, T, -1)   # :776
+        else:
+            hs_a = ops.linear(hs_a.reshape(B * T, -1), P["afm_w"], P["afm_b"]).view(B, T, -1)   # :776
         if self.variant == "disentangle":
             eye = self.learnable_eye_embed.expand(B, T, -1) if eye_embed is None else eye_embed
             hidden_states = torch.cat([eye, emo_embed[:, :T].to(hs_a), hs_a], dim=-1)          # :808
