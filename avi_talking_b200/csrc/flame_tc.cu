@@ -241,34 +241,63 @@ flame_tc_kernel(const __grid_constant__ CUtensorMap map_dirs, const __grid_const
         const int fbase = tf0 + fq * 16;
         const int flimit = tf0 + tnfr;
         float* o = p.verts + (int64_t)fbase * V3 + (int64_t)v * 3;   // lanes = consecutive vertices: 384 contiguous bytes per frame
+        // union of the non-identity joints over this warp's 16 frames: warp-uniform, hoisted out of the frame loop. A joint that is
+        // the identity in SOME of those frames contributes w_j * (A_j - I) = exact zeros there, so the result is bit-identical to
+        // testing every frame, without the ~30 branch / predicate instructions per frame that dominated the issue slots (ncu r1i).
+        const uint32_t wmask = __reduce_or_sync(0xffffffffu, lane < 16 ? flags[fq * 16 + lane] : 0u);
+        if ((wmask & (wmask - 1)) == 0) {
+          // ---- at most ONE moving joint (the jaw, on every path of this repo): T = wsum I + w_j (A_j - I) ----
+          const int j0 = wmask ? (31 - __clz((int)wmask)) : 0;
+          const float wj = wmask ? w[0] * (j0 == 0) + w[1] * (j0 == 1) + w[2] * (j0 == 2) + w[3] * (j0 == 3) + w[4] * (j0 == 4) : 0.f;
+          const uint32_t Aj = As + (j0 * 12) * 4;
 #pragma unroll
-        for (int n = 0; n < 16; ++n) {
-          if (fbase + n < flimit) {  // warp-uniform
-            const uint32_t active = flags[fq * 16 + n];   // warp-uniform
-            float T[12];
-#pragma unroll
-            for (int e = 0; e < 12; ++e) T[e] = (e == 0 || e == 5 || e == 10) ? wsum : 0.f;
-#pragma unroll
-            for (int j = 0; j < FT_NJ; ++j) {
-              if (active & (1u << j)) {
-#pragma unroll
-                for (int q = 0; q < 3; ++q) {
-                  const float4 a = lds128f(As + (n * (FT_NJ * 12) + j * 12 + q * 4) * 4);
-                  T[q * 4 + 0] = fmaf(w[j], a.x - (q == 0 ? 1.f : 0.f), T[q * 4 + 0]);
-                  T[q * 4 + 1] = fmaf(w[j], a.y - (q == 1 ? 1.f : 0.f), T[q * 4 + 1]);
-                  T[q * 4 + 2] = fmaf(w[j], a.z - (q == 2 ? 1.f : 0.f), T[q * 4 + 2]);
-                  T[q * 4 + 3] = fmaf(w[j], a.w, T[q * 4 + 3]);
-                }
+          for (int n = 0; n < 16; ++n) {
+            if (fbase + n < flimit) {  // warp-uniform
+              const float4 r0 = lds128f(Aj + (n * (FT_NJ * 12)) * 4);
+              const float4 r1 = lds128f(Aj + (n * (FT_NJ * 12) + 4) * 4);
+              const float4 r2 = lds128f(Aj + (n * (FT_NJ * 12) + 8) * 4);
+              const float px = __uint_as_float(vx[n]) + vtp[0], py = __uint_as_float(vy[n]) + vtp[1], pz = __uint_as_float(vz[n]) + vtp[2];
+              // same association as the generic path: T[e] = fma(w_j, A_e - I_e, wsum I_e), then the row . [p; 1] as nested fmas
+              const float t00 = fmaf(wj, r0.x - 1.f, wsum), t01 = fmaf(wj, r0.y, 0.f), t02 = fmaf(wj, r0.z, 0.f), t03 = fmaf(wj, r0.w, 0.f);
+              const float t10 = fmaf(wj, r1.x, 0.f), t11 = fmaf(wj, r1.y - 1.f, wsum), t12 = fmaf(wj, r1.z, 0.f), t13 = fmaf(wj, r1.w, 0.f);
+              const float t20 = fmaf(wj, r2.x, 0.f), t21 = fmaf(wj, r2.y, 0.f), t22 = fmaf(wj, r2.z - 1.f, wsum), t23 = fmaf(wj, r2.w, 0.f);
+              if (v_ok) {
+                o[0] = fmaf(t00, px, fmaf(t01, py, fmaf(t02, pz, t03)));
+                o[1] = fmaf(t10, px, fmaf(t11, py, fmaf(t12, pz, t13)));
+                o[2] = fmaf(t20, px, fmaf(t21, py, fmaf(t22, pz, t23)));
               }
             }
-            const float px = __uint_as_float(vx[n]) + vtp[0], py = __uint_as_float(vy[n]) + vtp[1], pz = __uint_as_float(vz[n]) + vtp[2];
-            if (v_ok) {
-#pragma unroll
-              for (int i = 0; i < 3; ++i)
-                o[i] = fmaf(T[i * 4 + 0], px, fmaf(T[i * 4 + 1], py, fmaf(T[i * 4 + 2], pz, T[i * 4 + 3])));
-            }
+            o += V3;
           }
-          o += V3;
+        } else {
+#pragma unroll
+          for (int n = 0; n < 16; ++n) {
+            if (fbase + n < flimit) {  // warp-uniform
+              float T[12];
+#pragma unroll
+              for (int e = 0; e < 12; ++e) T[e] = (e == 0 || e == 5 || e == 10) ? wsum : 0.f;
+#pragma unroll
+              for (int j = 0; j < FT_NJ; ++j) {
+                if (wmask & (1u << j)) {
+#pragma unroll
+                  for (int q = 0; q < 3; ++q) {
+                    const float4 a = lds128f(As + (n * (FT_NJ * 12) + j * 12 + q * 4) * 4);
+                    T[q * 4 + 0] = fmaf(w[j], a.x - (q == 0 ? 1.f : 0.f), T[q * 4 + 0]);
+                    T[q * 4 + 1] = fmaf(w[j], a.y - (q == 1 ? 1.f : 0.f), T[q * 4 + 1]);
+                    T[q * 4 + 2] = fmaf(w[j], a.z - (q == 2 ? 1.f : 0.f), T[q * 4 + 2]);
+                    T[q * 4 + 3] = fmaf(w[j], a.w, T[q * 4 + 3]);
+                  }
+                }
+              }
+              const float px = __uint_as_float(vx[n]) + vtp[0], py = __uint_as_float(vy[n]) + vtp[1], pz = __uint_as_float(vz[n]) + vtp[2];
+              if (v_ok) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+                  o[i] = fmaf(T[i * 4 + 0], px, fmaf(T[i * 4 + 1], py, fmaf(T[i * 4 + 2], pz, T[i * 4 + 3])));
+              }
+            }
+            o += V3;
+          }
         }
         tc_fence_before();
         __syncwarp();

@@ -309,6 +309,14 @@ class Faceformer(nn.Module):
         main.wait_stream(side)
         return v, out["fv"]
 
+    def graphed_predict_and_convert(self, audio, emo_embed, gt_coeff, gt_pose, gt_shape):
+        """predict_and_convert replayed from a CUDA graph (captured once per input signature and weight version). The returned tensors
+        are the graph's static outputs: they are overwritten by the next call with the same signature."""
+        from .graphs import GraphedCall
+        if getattr(self, "_graphed_pc", None) is None:
+            self._graphed_pc = GraphedCall(self.predict_and_convert, weight_modules=(self,))
+        return self._graphed_pc(audio, emo_embed, gt_coeff, gt_pose, gt_shape)
+
     @torch.no_grad()
     def predict(self, audio, head_img, eye_img, emotion_img, text=None):
         """:767-812. The FanEncoder image branch is called exactly as upstream (per frame) when ``fan_net`` is set."""

@@ -40,7 +40,22 @@ def parse():
     ap.add_argument("--precision", default=os.environ.get("AVI_B200_PRECISION", "bf16"), choices=["bf16", "fp32"])
     ap.add_argument("--cpu-clips", type=int, default=2, help="clips in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying its CUDA graph")
     return ap.parse_args()
+
+
+def ncu_traffic(kernel_substr):
+    """DRAM bytes per launch (read + write) of a kernel from the committed ncu pass over this same command
+    (profiles/r1/traffic.json, written by profiles/summarise_launches.py); None when no capture is committed."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1", "traffic.json")) as fh:
+            t = json.load(fh)
+        for k, v in t.items():
+            if kernel_substr in k:
+                return float(v["dram_bytes_per_launch"])
+    except Exception:
+        pass
+    return None
 
 
 def peaks():
@@ -86,7 +101,7 @@ def workload_config(args, T, precision):
     """The `config` object: identical for the product arm and the --impl reference arm (same workload, BASELINE configs[1])."""
     return {"workload": f"BASELINE configs[1]: FaceFormer-disentangle predict (wav2vec2 + AR decoder + vertex head) + FLAME LBS, "
                         f"{args.clips} clips x {args.seconds:g} s per GPU, fd={args.fd}, random-init (seeded) weights",
-            "clips_per_gpu": args.clips, "frames_per_clip": T, "precision": precision, "l2_policy": "inputs larger than L2"}
+            "clips_per_gpu": args.clips, "frames_per_clip": T, "precision": precision, "l2_policy": "inputs larger than L2", "launch": "eager" if getattr(args, "no_graph", False) else "cuda graph replay"}
 
 
 def n_frames(n_samples):
@@ -192,8 +207,16 @@ def run_ours(args):
         return t._base if t._base is not None else t
 
 
-    def step(inp):
+    def step_eager(inp):
+        # one public call per step: wav2vec2 + AR decoder + vertex head, and FLAME on the frames' coefficients (side stream)
         return model.predict_and_convert(inp["audio"], inp["emo"], inp["coeff"], inp["pose"], inp["shape"].repeat_interleave(T, 0))
+
+    def step(inp):
+        # the device-resident `value`: the same call replayed from its CUDA graph (static outputs, overwritten by the next replay)
+        if args.no_graph:
+            return step_eager(inp)
+        return model.graphed_predict_and_convert(inp["audio"], inp["emo"], inp["coeff"], inp["pose"],
+                                                 inp["shape"].repeat_interleave(T, 0))
 
     def barrier():
         if world > 1:
@@ -216,10 +239,16 @@ def run_ours(args):
     barrier()
     dt_ms = e0.elapsed_time(e1)
     launches = _lib.launch_count() - n0
+    if not args.no_graph:
+        # a graph replay makes no C-ABI calls: count the kernels of one eager step (what the graph captured) x steps
+        n1 = _lib.launch_count()
+        step_eager(devin)
+        torch.cuda.synchronize()
+        launches = (_lib.launch_count() - n1) * args.steps
 
     # end to end through the public API with HOST buffers: H2D of the step's inputs and D2H of BOTH results inside the timed
     # region. The D2H of step i runs on a copy stream and overlaps the compute of step i+1 (double-buffered pinned outputs).
-    v0, fv0 = step(devin)
+    v0, fv0 = step_eager(devin)
     out_host = [torch.empty(base(v0).shape, dtype=torch.float32).pin_memory() for _ in range(2)]
     flame_host = [torch.empty(base(fv0).shape, dtype=torch.float32).pin_memory() for _ in range(2)]
     del v0, fv0
@@ -228,7 +257,7 @@ def run_ours(args):
 
     def e2e_step(i):
         inp = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-        v, fv = step(inp)
+        v, fv = step_eager(inp)          # the public drop-in call (fresh outputs every step, so the D2H of step i overlaps step i+1)
         ev = torch.cuda.Event()
         ev.record(main)
         with torch.cuda.stream(copy_stream):
@@ -284,7 +313,7 @@ def run_ours(args):
     gname = "gemm_bf16_tc" if "gemm_bf16_tc" in agg else "gemm_f32"
     achieved = g[2] / (g[1] / 1e3) / 1e12
     roofline = {"kernel": gname, "bound": "tensor", "achieved": achieved, "peak": pk["tc"], "unit": "TFLOP/s",
-                "frac": achieved / pk["tc"], "traffic": None, "peak_source": pk["src"] + " (sustained bf16)",
+                "frac": achieved / pk["tc"], "traffic": ncu_traffic("gemm_bf16_tc2_kernel"), "traffic_unit": "DRAM bytes per launch (ncu)", "peak_source": pk["src"] + " (sustained bf16)",
                 "launches_per_step": g[0], "avg_launch_ms": g[1] / g[0], "share_of_step": g[1] / step_ms_prof}
     fl = agg.get("flame_lbs")
     extra = {}

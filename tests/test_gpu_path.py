@@ -247,3 +247,25 @@ def test_predict_and_convert_overlapped_equals_sequential():
         v1, f1 = m.predict_and_convert(a, emo, coeff, pose.clone(), shape)
     torch.cuda.synchronize()
     assert torch.equal(v0, v1) and torch.equal(f0, f1)
+
+
+@pytest.mark.gpu
+def test_graphed_predict_and_convert_matches_eager():
+    """CUDA-graph replay of predict_and_convert (avi_talking_b200/graphs.py) returns what the eager call returns, also after the
+    inputs change and after the weights change (re-capture keyed on parameter versions)."""
+    from avi_talking_b200.smoke import build_models
+    m = build_models("bf16")
+    B, n, T = 3, 16000, 24
+    g = torch.Generator().manual_seed(5)
+    for trial in range(3):
+        audio = synth.audio(B, n, seed=300 + trial).cuda()
+        emo = torch.randn(B, T, 30, generator=g).cuda()
+        coeff = torch.randn(B * T, 53, generator=g).cuda()
+        pose = (0.1 * torch.randn(B * T, 6, generator=g)).cuda()
+        shape = torch.randn(B * T, 100, generator=g).cuda()
+        if trial == 2:
+            with torch.no_grad():
+                m.audio_feature_map.bias.add_(0.01)          # bumps _version: the graph must be re-captured with new packs
+        v0, f0 = m.predict_and_convert(audio, emo, coeff, pose.clone(), shape)
+        v1, f1 = m.graphed_predict_and_convert(audio, emo, coeff, pose.clone(), shape)
+        assert torch.equal(v0, v1) and torch.equal(f0, f1)
