@@ -12,6 +12,7 @@ Reference arithmetic (A.3 of SURVEY.md):
 from __future__ import annotations
 
 import math
+import os
 import types
 
 import torch
@@ -122,6 +123,10 @@ class Faceformer(nn.Module):
             self.v_merge2hidden = nn.Linear(6 + 30 + fd, fd)                                 # :241
             self.learnable_eye_embed = nn.Parameter(torch.zeros(1, 1, 6))                    # :327
         self.precision = default_precision()
+        # audio_feature_map (768 -> fd): fp32 CUDA-core GEMM on the fp32 encoder output by default. AVI_B200_AFM_TC=1 runs it on the
+        # tensor cores from the encoder's bf16 output (-0.1 ms per 64-clip step) at the price of ~1.2e-5 m of the 1e-4 m bf16-mode
+        # vertex budget (measured: 8.5e-5 -> 9.8e-5 m max error on the smoke case), so it is opt-in
+        self.afm_tensor_core = os.environ.get("AVI_B200_AFM_TC", "0") == "1"
         self._packed = None
         self._packed_key = None
         self._before_ar = None
@@ -266,7 +271,7 @@ class Faceformer(nn.Module):
         hs_a = self.audio_encoder(audio, self.dataset).last_hidden_state                      # :775
         T = hs_a.shape[1]
         h16 = getattr(self.audio_encoder, "last_hidden_state_bf16", None)
-        if self.precision == "bf16" and h16 is not None and "afm_w16" in P:
+        if self.precision == "bf16" and h16 is not None and "afm_w16" in P and self.afm_tensor_core:
             # the encoder already produced the bf16 copy of its output for the next tensor-core contraction
             hs_a = ops.linear(h16.reshape(B * T, -1), P["afm_w16"], P["afm_b"], out_dtype=torch.float32).view(B, T, -1)   # :776
         else:
