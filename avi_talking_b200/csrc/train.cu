@@ -165,176 +165,258 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
 // (head, clip) problems, so every kernel is tiled over ATT_ROWS query (or key) rows as well: grid = (H, B, ceil(T / ATT_ROWS)),
 // K / V (or Q / dO) of the head staged in shared memory with a D+1 pitch (conflict-free both along keys and along channels).
 __device__ __forceinline__ float ff_slope(int h) { return exp2f(-2.f * (float)(h + 1)); }   // 4 heads: 2^-2, 2^-4, 2^-6, 2^-8
-constexpr int ATT_ROWS = 16;      // rows per CTA: 8 warps x 2 rows
+constexpr int ATT_ROWS = 16;      // rows per CTA: 8 warps x 2 rows, processed together so that every K / V (Q / dO) load feeds two rows
 constexpr int ATT_MAXT = 128;
+constexpr int ATT_PAD = 4;        // row pitch HD + 4 floats: 16-byte aligned rows, and lanes = consecutive rows hit distinct bank groups
 
-__device__ __forceinline__ void att_stage(float* dst, const float* __restrict__ src, int T, int D, int row_stride) {
-  // dst[t][d] (pitch D+1) = src[t * row_stride + d]
-  for (int i = threadIdx.x; i < T * D; i += blockDim.x) {
-    const int t = i / D, d = i - t * D;
-    dst[t * (D + 1) + d] = src[(int64_t)t * row_stride + d];
+template <int HD>
+__device__ __forceinline__ void att_stage(float* dst, const float* __restrict__ src, int T, int row_stride) {
+  // dst[t][d] (pitch HD + ATT_PAD) = src[t * row_stride + d]
+  for (int i = threadIdx.x; i < T * (HD / 4); i += blockDim.x) {
+    const int t = i / (HD / 4), d4 = i - t * (HD / 4);
+    *reinterpret_cast<float4*>(dst + t * (HD + ATT_PAD) + 4 * d4) = *reinterpret_cast<const float4*>(src + (int64_t)t * row_stride + 4 * d4);
+  }
+}
+__device__ __forceinline__ float dot4(const float4 a, const float4 b, float acc) {
+  return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, acc))));
+}
+
+// scores of two query rows (vectors xa, xb in shared memory) against the staged rows `mat`, keys lane, lane+32, ...
+template <int HD>
+__device__ __forceinline__ void att_two_row_scores(const float* mat, const float* xa, const float* xb, int T, int lane, float (&sa)[4],
+                                                   float (&sb)[4]) {
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int j = lane + 32 * u;
+    sa[u] = 0.f;
+    sb[u] = 0.f;
+    if (j < T) {
+      const float* kr = mat + j * (HD + ATT_PAD);
+      float a = 0.f, b = 0.f;
+#pragma unroll
+      for (int d = 0; d < HD; d += 4) {
+        const float4 k4 = *reinterpret_cast<const float4*>(kr + d);
+        a = dot4(k4, *reinterpret_cast<const float4*>(xa + d), a);
+        b = dot4(k4, *reinterpret_cast<const float4*>(xb + d), b);
+      }
+      sa[u] = a;
+      sb[u] = b;
+    }
   }
 }
 
+// ya[d] = sum_j pa[j] mat[j][d], yb likewise, for d = lane, lane + 32 (< HD); pa / pb in shared memory, zero padded to a multiple of 4
+template <int HD>
+__device__ __forceinline__ void att_two_row_mix(const float* mat, const float* pa, const float* pb, int T, int lane, float (&ya)[2],
+                                                float (&yb)[2]) {
+  ya[0] = ya[1] = yb[0] = yb[1] = 0.f;
+  const int T4 = (T + 3) & ~3;
+  for (int j = 0; j < T4; j += 4) {
+    const float4 a4 = *reinterpret_cast<const float4*>(pa + j), b4 = *reinterpret_cast<const float4*>(pb + j);
+    const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      if (j + jj < T) {
+#pragma unroll
+        for (int h = 0; h < (HD + 31) / 32; ++h) {
+          const int d = lane + 32 * h;
+          if (d < HD) {
+            const float m = mat[(j + jj) * (HD + ATT_PAD) + d];
+            ya[h] = fmaf(av[jj], m, ya[h]);
+            yb[h] = fmaf(bv[jj], m, yb[h]);
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int HD>
 __global__ void __launch_bounds__(256) attn_train_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ out, float* __restrict__ P,
-                                                             int T, int H, int D, float scale, int bias_mode, int period) {
-  extern __shared__ float sm[];
-  float* ks = sm;                        // [T][D+1]
-  float* vs = ks + T * (D + 1);          // [T][D+1]
-  float* qs = vs + T * (D + 1);          // [8 warps][D]
-  float* ps = qs + 8 * 64;               // [8 warps][ATT_MAXT]
+                                                             int T, int H, float scale, int bias_mode, int period) {
+  extern __shared__ __align__(16) float sm[];
+  float* ks = sm;                              // [T][HD+4]
+  float* vs = ks + T * (HD + ATT_PAD);         // [T][HD+4]
+  float* qs = vs + T * (HD + ATT_PAD);         // [8 warps][2][HD]
+  float* ps = qs + 8 * 2 * HD;                 // [8 warps][2][ATT_MAXT]
   const int h = blockIdx.x, b = blockIdx.y, i0 = blockIdx.z * ATT_ROWS;
-  const int E = H * D;
-  const float* base = qkv + (int64_t)b * T * 3 * E + h * D;
-  att_stage(ks, base + E, T, D, 3 * E);
-  att_stage(vs, base + 2 * E, T, D, 3 * E);
+  const int E = H * HD;
+  const float* base = qkv + (int64_t)b * T * 3 * E + h * HD;
+  att_stage<HD>(ks, base + E, T, 3 * E);
+  att_stage<HD>(vs, base + 2 * E, T, 3 * E);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* Pb = P + ((int64_t)b * H + h) * T * T;
-  float* q = qs + warp * 64;
-  float* pr = ps + warp * ATT_MAXT;
+  float* qa = qs + warp * 2 * HD, *qb = qa + HD;
+  float* pa = ps + warp * 2 * ATT_MAXT, *pb = pa + ATT_MAXT;
   const float slope = ff_slope(h);
-  for (int i = i0 + warp; i < min(i0 + ATT_ROWS, T); i += 8) {
-    for (int d = lane; d < D; d += 32) q[d] = base[(int64_t)i * 3 * E + d] * scale;
-    __syncwarp();
-    float s[4];
-    float mx = -INFINITY;
+  const int ia = i0 + warp, ib = i0 + warp + 8;
+  if (ia >= T) return;                         // warp-uniform; no block-wide barrier follows
+  const bool b_ok = ib < T;
+  for (int d = lane; d < HD; d += 32) {
+    qa[d] = base[(int64_t)ia * 3 * E + d] * scale;
+    qb[d] = b_ok ? base[(int64_t)ib * 3 * E + d] * scale : 0.f;
+  }
+  __syncwarp();
+  float sa[4], sb[4];
+  att_two_row_scores<HD>(ks, qa, qb, T, lane, sa, sb);
+  float ma = -INFINITY, mb = -INFINITY;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int j = lane + 32 * u;
-      s[u] = -INFINITY;
-      if (j < T && !(bias_mode == 1 && j > i)) {
-        float a = 0.f;
-        const float* kr = ks + j * (D + 1);
-        for (int d = 0; d < D; ++d) a = fmaf(q[d], kr[d], a);
-        if (bias_mode == 1) a -= slope * (float)((i - j) / period);
-        s[u] = a;
-      }
-      mx = fmaxf(mx, s[u]);
+  for (int u = 0; u < 4; ++u) {
+    const int j = lane + 32 * u;
+    const bool va = j < T && !(bias_mode == 1 && j > ia), vb = j < T && !(bias_mode == 1 && j > ib);
+    if (bias_mode == 1) {
+      sa[u] -= slope * (float)((ia - j) / period);
+      sb[u] -= slope * (float)((ib - j) / period);
     }
-    mx = warp_max(mx);
-    float den = 0.f;
+    sa[u] = va ? sa[u] : -INFINITY;
+    sb[u] = vb ? sb[u] : -INFINITY;
+    ma = fmaxf(ma, sa[u]);
+    mb = fmaxf(mb, sb[u]);
+  }
+  ma = warp_max(ma);
+  mb = warp_max(mb);
+  float da = 0.f, db = 0.f;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      s[u] = (s[u] == -INFINITY) ? 0.f : expf(s[u] - mx);
-      den += s[u];
-    }
-    den = 1.f / warp_sum(den);
+  for (int u = 0; u < 4; ++u) {
+    sa[u] = (sa[u] == -INFINITY) ? 0.f : expf(sa[u] - ma);
+    sb[u] = (sb[u] == -INFINITY) ? 0.f : expf(sb[u] - mb);
+    da += sa[u];
+    db += sb[u];
+  }
+  da = 1.f / warp_sum(da);
+  db = 1.f / fmaxf(warp_sum(db), 1e-30f);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int j = lane + 32 * u;
-      if (j < T) {
-        const float p = s[u] * den;
-        pr[j] = p;
-        Pb[(int64_t)i * T + j] = p;
-      }
+  for (int u = 0; u < 4; ++u) {
+    const int j = lane + 32 * u;        // j < ATT_MAXT always: the padding up to a multiple of 4 is written as zeros
+    pa[j] = sa[u] * da;
+    pb[j] = sb[u] * db;
+    if (j < T) {
+      Pb[(int64_t)ia * T + j] = sa[u] * da;
+      if (b_ok) Pb[(int64_t)ib * T + j] = sb[u] * db;
     }
-    __syncwarp();
-    for (int d = lane; d < D; d += 32) {
-      float a = 0.f;
-      for (int j = 0; j < T; ++j) a = fmaf(pr[j], vs[j * (D + 1) + d], a);
-      out[((int64_t)b * T + i) * E + h * D + d] = a;
+  }
+  __syncwarp();
+  float ya[2], yb[2];
+  att_two_row_mix<HD>(vs, pa, pb, T, lane, ya, yb);
+#pragma unroll
+  for (int hh = 0; hh < (HD + 31) / 32; ++hh) {
+    const int d = lane + 32 * hh;
+    if (d < HD) {
+      out[((int64_t)b * T + ia) * E + h * HD + d] = ya[hh];
+      if (b_ok) out[((int64_t)b * T + ib) * E + h * HD + d] = yb[hh];
     }
-    __syncwarp();
   }
 }
 
 // backward, query-tiled half: dP = dO V^T ; dS = P * (dP - rowsum(dP * P)) -> scratch [B,H,T,T] ; dQ = scale dS K
+template <int HD>
 __global__ void __launch_bounds__(256) attn_train_bwd_q_kernel(const float* __restrict__ qkv, const float* __restrict__ P,
                                                                const float* __restrict__ dout, float* __restrict__ dqkv,
-                                                               float* __restrict__ dS, int T, int H, int D, float scale) {
-  extern __shared__ float sm[];
-  float* ks = sm;                        // [T][D+1]
-  float* vs = ks + T * (D + 1);          // [T][D+1]
-  float* gs = vs + T * (D + 1);          // dO row per warp [8][64]
-  float* ds = gs + 8 * 64;               // dS row per warp [8][ATT_MAXT]
+                                                               float* __restrict__ dS, int T, int H, float scale) {
+  extern __shared__ __align__(16) float sm[];
+  float* ks = sm;
+  float* vs = ks + T * (HD + ATT_PAD);
+  float* gs = vs + T * (HD + ATT_PAD);         // dO rows of the two queries per warp [8][2][HD]
+  float* ds = gs + 8 * 2 * HD;                 // dS rows [8][2][ATT_MAXT]
   const int h = blockIdx.x, b = blockIdx.y, i0 = blockIdx.z * ATT_ROWS;
-  const int E = H * D;
-  const float* base = qkv + (int64_t)b * T * 3 * E + h * D;
-  att_stage(ks, base + E, T, D, 3 * E);
-  att_stage(vs, base + 2 * E, T, D, 3 * E);
+  const int E = H * HD;
+  const float* base = qkv + (int64_t)b * T * 3 * E + h * HD;
+  att_stage<HD>(ks, base + E, T, 3 * E);
+  att_stage<HD>(vs, base + 2 * E, T, 3 * E);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* Pb = P + ((int64_t)b * H + h) * T * T;
   float* dSb = dS + ((int64_t)b * H + h) * T * T;
-  float* go = gs + warp * 64;
-  float* dr = ds + warp * ATT_MAXT;
-  for (int i = i0 + warp; i < min(i0 + ATT_ROWS, T); i += 8) {
-    for (int d = lane; d < D; d += 32) go[d] = dout[((int64_t)b * T + i) * E + h * D + d];
-    __syncwarp();
-    float dp[4], pp[4];
-    float dot = 0.f;
+  float* ga = gs + warp * 2 * HD, *gb = ga + HD;
+  float* ra = ds + warp * 2 * ATT_MAXT, *rb = ra + ATT_MAXT;
+  const int ia = i0 + warp, ib = i0 + warp + 8;
+  if (ia >= T) return;
+  const bool b_ok = ib < T;
+  for (int d = lane; d < HD; d += 32) {
+    ga[d] = dout[((int64_t)b * T + ia) * E + h * HD + d];
+    gb[d] = b_ok ? dout[((int64_t)b * T + ib) * E + h * HD + d] : 0.f;
+  }
+  __syncwarp();
+  float pa[4], pb[4], qa[4], qb[4];
+  att_two_row_scores<HD>(vs, ga, gb, T, lane, pa, pb);      // dP rows
+  float dota = 0.f, dotb = 0.f;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int j = lane + 32 * u;
-      dp[u] = 0.f;
-      pp[u] = 0.f;
-      if (j < T) {
-        pp[u] = Pb[(int64_t)i * T + j];
-        float a = 0.f;
-        const float* vr = vs + j * (D + 1);
-        for (int d = 0; d < D; ++d) a = fmaf(go[d], vr[d], a);
-        dp[u] = a;
-        dot = fmaf(a, pp[u], dot);
-      }
-    }
-    dot = warp_sum(dot);
+  for (int u = 0; u < 4; ++u) {
+    const int j = lane + 32 * u;
+    qa[u] = j < T ? Pb[(int64_t)ia * T + j] : 0.f;
+    qb[u] = (j < T && b_ok) ? Pb[(int64_t)ib * T + j] : 0.f;
+    dota = fmaf(pa[u], qa[u], dota);
+    dotb = fmaf(pb[u], qb[u], dotb);
+  }
+  dota = warp_sum(dota);
+  dotb = warp_sum(dotb);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int j = lane + 32 * u;
-      if (j < T) {
-        const float v = pp[u] * (dp[u] - dot);
-        dr[j] = v;
-        dSb[(int64_t)i * T + j] = v;
-      }
+  for (int u = 0; u < 4; ++u) {
+    const int j = lane + 32 * u;
+    const float va = qa[u] * (pa[u] - dota), vb = qb[u] * (pb[u] - dotb);
+    ra[j] = va;
+    rb[j] = vb;
+    if (j < T) {
+      dSb[(int64_t)ia * T + j] = va;
+      if (b_ok) dSb[(int64_t)ib * T + j] = vb;
     }
-    __syncwarp();
-    for (int d = lane; d < D; d += 32) {
-      float a = 0.f;
-      for (int j = 0; j < T; ++j) a = fmaf(dr[j], ks[j * (D + 1) + d], a);
-      dqkv[((int64_t)b * T + i) * 3 * E + h * D + d] = a * scale;
+  }
+  __syncwarp();
+  float ya[2], yb[2];
+  att_two_row_mix<HD>(ks, ra, rb, T, lane, ya, yb);
+#pragma unroll
+  for (int hh = 0; hh < (HD + 31) / 32; ++hh) {
+    const int d = lane + 32 * hh;
+    if (d < HD) {
+      dqkv[((int64_t)b * T + ia) * 3 * E + h * HD + d] = ya[hh] * scale;
+      if (b_ok) dqkv[((int64_t)b * T + ib) * 3 * E + h * HD + d] = yb[hh] * scale;
     }
-    __syncwarp();
   }
 }
 
-// backward, key-tiled half: dK[j] = scale sum_i dS[i,j] Q[i] ; dV[j] = sum_i P[i,j] dO[i]
+// backward, key-tiled half: dK[j] = scale sum_i dS[i,j] Q[i] ; dV[j] = sum_i P[i,j] dO[i]   (two keys per warp)
+template <int HD>
 __global__ void __launch_bounds__(256) attn_train_bwd_kv_kernel(const float* __restrict__ qkv, const float* __restrict__ P,
                                                                 const float* __restrict__ dout, float* __restrict__ dqkv,
-                                                                const float* __restrict__ dS, int T, int H, int D, float scale) {
-  extern __shared__ float sm[];
-  float* qs = sm;                        // Q  [T][D+1]
-  float* gs = qs + T * (D + 1);          // dO [T][D+1]
-  float* dst = gs + T * (D + 1);         // dS^T tile [ATT_ROWS][ATT_MAXT]
-  float* pst = dst + ATT_ROWS * ATT_MAXT;  // P^T tile  [ATT_ROWS][ATT_MAXT]
+                                                                const float* __restrict__ dS, int T, int H, float scale) {
+  extern __shared__ __align__(16) float sm[];
+  float* qs = sm;                               // Q  [T][HD+4]
+  float* gs = qs + T * (HD + ATT_PAD);          // dO [T][HD+4]
+  float* dst = gs + T * (HD + ATT_PAD);         // dS^T tile [ATT_ROWS][ATT_MAXT]
+  float* pst = dst + ATT_ROWS * ATT_MAXT;       // P^T tile  [ATT_ROWS][ATT_MAXT]
   const int h = blockIdx.x, b = blockIdx.y, j0 = blockIdx.z * ATT_ROWS;
-  const int E = H * D;
-  const float* base = qkv + (int64_t)b * T * 3 * E + h * D;
-  att_stage(qs, base, T, D, 3 * E);
-  att_stage(gs, dout + (int64_t)b * T * E + h * D, T, D, E);
+  const int E = H * HD;
+  const float* base = qkv + (int64_t)b * T * 3 * E + h * HD;
+  att_stage<HD>(qs, base, T, 3 * E);
+  att_stage<HD>(gs, dout + (int64_t)b * T * E + h * HD, T, E);
   const float* Pb = P + ((int64_t)b * H + h) * T * T;
   const float* dSb = dS + ((int64_t)b * H + h) * T * T;
-  for (int idx = threadIdx.x; idx < T * ATT_ROWS; idx += blockDim.x) {
+  for (int idx = threadIdx.x; idx < ATT_MAXT * ATT_ROWS; idx += blockDim.x) {
     const int i = idx / ATT_ROWS, jj = idx - i * ATT_ROWS;
     const int j = j0 + jj;
-    dst[jj * ATT_MAXT + i] = j < T ? dSb[(int64_t)i * T + j] : 0.f;
-    pst[jj * ATT_MAXT + i] = j < T ? Pb[(int64_t)i * T + j] : 0.f;
+    const bool ok = i < T && j < T;
+    dst[jj * ATT_MAXT + i] = ok ? dSb[(int64_t)i * T + j] : 0.f;
+    pst[jj * ATT_MAXT + i] = ok ? Pb[(int64_t)i * T + j] : 0.f;
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int jj = warp; jj < ATT_ROWS; jj += 8) {
-    const int j = j0 + jj;
-    if (j >= T) break;
-    const float* dcol = dst + jj * ATT_MAXT;
-    const float* pcol = pst + jj * ATT_MAXT;
-    for (int d = lane; d < D; d += 32) {
-      float ak = 0.f, av = 0.f;
-      for (int i = 0; i < T; ++i) {
-        ak = fmaf(dcol[i], qs[i * (D + 1) + d], ak);
-        av = fmaf(pcol[i], gs[i * (D + 1) + d], av);
+  const int ja = j0 + warp, jb = j0 + warp + 8;
+  if (ja >= T) return;
+  const bool b_ok = jb < T;
+  float ka[2], kb[2], va[2], vb[2];
+  att_two_row_mix<HD>(qs, dst + warp * ATT_MAXT, dst + (warp + 8) * ATT_MAXT, T, lane, ka, kb);
+  att_two_row_mix<HD>(gs, pst + warp * ATT_MAXT, pst + (warp + 8) * ATT_MAXT, T, lane, va, vb);
+#pragma unroll
+  for (int hh = 0; hh < (HD + 31) / 32; ++hh) {
+    const int d = lane + 32 * hh;
+    if (d < HD) {
+      dqkv[((int64_t)b * T + ja) * 3 * E + E + h * HD + d] = ka[hh] * scale;
+      dqkv[((int64_t)b * T + ja) * 3 * E + 2 * E + h * HD + d] = va[hh];
+      if (b_ok) {
+        dqkv[((int64_t)b * T + jb) * 3 * E + E + h * HD + d] = kb[hh] * scale;
+        dqkv[((int64_t)b * T + jb) * 3 * E + 2 * E + h * HD + d] = vb[hh];
       }
-      dqkv[((int64_t)b * T + j) * 3 * E + E + h * D + d] = ak * scale;
-      dqkv[((int64_t)b * T + j) * 3 * E + 2 * E + h * D + d] = av;
     }
   }
 }
@@ -354,6 +436,29 @@ __global__ void __launch_bounds__(256) posconv_dw_kernel(const float* __restrict
         if (r >= 0 && r < T) a = fmaf(dpc[((int64_t)b * T + t) * C + g * CG + co], x[((int64_t)b * T + r) * C + g * CG + ci], a);
       }
     dw[((int64_t)(g * CG + co) * CG + ci) * k + j] = a;
+  }
+}
+
+// Transposed unfold for the tensor-core weight gradient of the positional conv: for a block of CW channels starting at c0,
+//   out[(j * CW + ci), b * Tq + t] = xpad[b, t + j, c0 + ci]   (t < T; zero for T <= t < Tq),   xpad row r = x row r - pad (zero outside)
+// so that dW_block[co, (j, ci)] = sum_{b,t} dpc[b, t, co] * out[(j, ci), (b, t)] is ONE GEMM with the (clip, frame) index as the
+// contraction. Tiles of 32 channels x 32 frames go through shared memory: reads coalesced over channels, writes over frames.
+template <typename OutT>
+__global__ void __launch_bounds__(256) posconv_unfold_t_kernel(const float* __restrict__ x, OutT* __restrict__ out, int B, int T, int Tq,
+                                                               int C, int c0, int CW, int k) {
+  __shared__ float tile[32][33];
+  const int j = blockIdx.z % k, b = blockIdx.z / k;
+  const int ci0 = blockIdx.x * 32, t0 = blockIdx.y * 32;
+  const int pad = k / 2;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int t = t0 + i, r = t + j - pad, ci = ci0 + tx;
+    tile[i][tx] = (t < T && r >= 0 && r < T && ci < CW) ? x[((int64_t)b * T + r) * C + c0 + ci] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int ci = ci0 + i, t = t0 + tx;
+    if (ci < CW && t < Tq) out[((int64_t)j * CW + ci) * ((int64_t)B * Tq) + (int64_t)b * Tq + t] = to_out<OutT>(tile[tx][i]);
   }
 }
 
@@ -543,34 +648,56 @@ extern "C" int avi_layernorm_bwd(const float* x, const float* w, const float* dy
   return check_launch("layernorm_bwd");
 }
 
-static size_t att_smem_fwd(int T, int D) { return ((size_t)2 * T * (D + 1) + 8 * 64 + 8 * ATT_MAXT) * sizeof(float); }
-static size_t att_smem_kv(int T, int D) { return ((size_t)2 * T * (D + 1) + 2 * ATT_ROWS * ATT_MAXT) * sizeof(float); }
+static size_t att_smem_fwd(int T, int D) { return ((size_t)2 * T * (D + ATT_PAD) + 8 * 2 * D + 8 * 2 * ATT_MAXT) * sizeof(float); }
+static size_t att_smem_kv(int T, int D) { return ((size_t)2 * T * (D + ATT_PAD) + 2 * ATT_ROWS * ATT_MAXT) * sizeof(float); }
+
+template <int HD>
+static int attn_fwd_launch(const float* qkv, float* out, float* P, int B, int T, int H, float scale, int bias_mode, int period,
+                           cudaStream_t st) {
+  static cudaError_t attr_err = cudaFuncSetAttribute(attn_train_fwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     (int)att_smem_fwd(ATT_MAXT, HD));
+  AVI_REQUIRE(attr_err == cudaSuccess, "avi_attn_train_fwd: cudaFuncSetAttribute failed");
+  attn_train_fwd_kernel<HD><<<dim3(H, B, (T + ATT_ROWS - 1) / ATT_ROWS), 256, att_smem_fwd(T, HD), st>>>(qkv, out, P, T, H, scale, bias_mode,
+                                                                                                        period > 0 ? period : 1);
+  return check_launch("attn_train_fwd");
+}
+
+template <int HD>
+static int attn_bwd_launch(const float* qkv, const float* P, const float* dout, float* dqkv, float* dS, int B, int T, int H, float scale,
+                           cudaStream_t st) {
+  static cudaError_t e1 = cudaFuncSetAttribute(attn_train_bwd_q_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)att_smem_fwd(ATT_MAXT, HD));
+  static cudaError_t e2 = cudaFuncSetAttribute(attn_train_bwd_kv_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)att_smem_kv(ATT_MAXT, HD));
+  AVI_REQUIRE(e1 == cudaSuccess && e2 == cudaSuccess, "avi_attn_train_bwd: cudaFuncSetAttribute failed");
+  const dim3 grid(H, B, (T + ATT_ROWS - 1) / ATT_ROWS);
+  attn_train_bwd_q_kernel<HD><<<grid, 256, att_smem_fwd(T, HD), st>>>(qkv, P, dout, dqkv, dS, T, H, scale);
+  if (check_launch("attn_train_bwd_q")) return 1;
+  attn_train_bwd_kv_kernel<HD><<<grid, 256, att_smem_kv(T, HD), st>>>(qkv, P, dout, dqkv, dS, T, H, scale);
+  return check_launch("attn_train_bwd_kv");
+}
 
 extern "C" int avi_attn_train_fwd(const float* qkv, float* out, float* P, int32_t B, int32_t T, int32_t H, int32_t D, float scale,
                                   int32_t bias_mode, int32_t period, void* stream) {
-  AVI_REQUIRE(B > 0 && T > 0 && T <= ATT_MAXT && H > 0 && D > 0 && D <= 64, "avi_attn_train_fwd: T <= 128 and D <= 64 (T=%d D=%d)", T, D);
+  AVI_REQUIRE(B > 0 && T > 0 && T <= ATT_MAXT && H > 0 && (D == 16 || D == 32 || D == 64),
+              "avi_attn_train_fwd: T <= 128 and head dim 16 / 32 / 64 (T=%d D=%d)", T, D);
   AVI_REQUIRE(bias_mode == 0 || H == 4, "avi_attn_train_fwd: the FaceFormer bias mask is defined for 4 heads");
-  static cudaError_t attr_err = cudaFuncSetAttribute(attn_train_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                     (int)att_smem_fwd(ATT_MAXT, 64));
-  AVI_REQUIRE(attr_err == cudaSuccess, "avi_attn_train_fwd: cudaFuncSetAttribute failed");
-  attn_train_fwd_kernel<<<dim3(H, B, (T + ATT_ROWS - 1) / ATT_ROWS), 256, att_smem_fwd(T, D), (cudaStream_t)stream>>>(
-      qkv, out, P, T, H, D, scale, bias_mode, period > 0 ? period : 1);
-  return check_launch("attn_train_fwd");
+  AVI_REQUIRE(((uintptr_t)qkv % 16) == 0, "avi_attn_train_fwd: qkv must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (D == 64) return attn_fwd_launch<64>(qkv, out, P, B, T, H, scale, bias_mode, period, st);
+  if (D == 32) return attn_fwd_launch<32>(qkv, out, P, B, T, H, scale, bias_mode, period, st);
+  return attn_fwd_launch<16>(qkv, out, P, B, T, H, scale, bias_mode, period, st);
 }
 
 extern "C" int avi_attn_train_bwd(const float* qkv, const float* P, const float* dout, float* dqkv, float* dS_scratch, int32_t B, int32_t T,
                                   int32_t H, int32_t D, float scale, void* stream) {
-  AVI_REQUIRE(B > 0 && T > 0 && T <= ATT_MAXT && H > 0 && D > 0 && D <= 64, "avi_attn_train_bwd: T <= 128 and D <= 64 (T=%d D=%d)", T, D);
-  static cudaError_t e1 = cudaFuncSetAttribute(attn_train_bwd_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               (int)att_smem_fwd(ATT_MAXT, 64));
-  static cudaError_t e2 = cudaFuncSetAttribute(attn_train_bwd_kv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               (int)att_smem_kv(ATT_MAXT, 64));
-  AVI_REQUIRE(e1 == cudaSuccess && e2 == cudaSuccess, "avi_attn_train_bwd: cudaFuncSetAttribute failed");
-  const dim3 grid(H, B, (T + ATT_ROWS - 1) / ATT_ROWS);
-  attn_train_bwd_q_kernel<<<grid, 256, att_smem_fwd(T, D), (cudaStream_t)stream>>>(qkv, P, dout, dqkv, dS_scratch, T, H, D, scale);
-  if (check_launch("attn_train_bwd_q")) return 1;
-  attn_train_bwd_kv_kernel<<<grid, 256, att_smem_kv(T, D), (cudaStream_t)stream>>>(qkv, P, dout, dqkv, dS_scratch, T, H, D, scale);
-  return check_launch("attn_train_bwd_kv");
+  AVI_REQUIRE(B > 0 && T > 0 && T <= ATT_MAXT && H > 0 && (D == 16 || D == 32 || D == 64),
+              "avi_attn_train_bwd: T <= 128 and head dim 16 / 32 / 64 (T=%d D=%d)", T, D);
+  AVI_REQUIRE((((uintptr_t)qkv | (uintptr_t)dout) % 16) == 0, "avi_attn_train_bwd: qkv / dout must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (D == 64) return attn_bwd_launch<64>(qkv, P, dout, dqkv, dS_scratch, B, T, H, scale, st);
+  if (D == 32) return attn_bwd_launch<32>(qkv, P, dout, dqkv, dS_scratch, B, T, H, scale, st);
+  return attn_bwd_launch<16>(qkv, P, dout, dqkv, dS_scratch, B, T, H, scale, st);
 }
 
 extern "C" int avi_posconv_dw(const float* x, const float* dpc, float* dw, int32_t B, int32_t T, int32_t C, int32_t groups, int32_t k,
@@ -578,6 +705,18 @@ extern "C" int avi_posconv_dw(const float* x, const float* dpc, float* dw, int32
   AVI_REQUIRE(B > 0 && T > 0 && C > 0 && groups > 0 && C % groups == 0 && k > 0, "avi_posconv_dw: bad shape");
   posconv_dw_kernel<<<dim3(k, groups), 256, 0, (cudaStream_t)stream>>>(x, dpc, dw, B, T, C, C / groups, k);
   return check_launch("posconv_dw");
+}
+
+extern "C" int avi_posconv_unfold_t(const float* x, void* out, int32_t out_dtype, int32_t B, int32_t T, int32_t Tq, int32_t C, int32_t c0,
+                                    int32_t CW, int32_t k, void* stream) {
+  AVI_REQUIRE(B > 0 && T > 0 && Tq >= T && C > 0 && c0 >= 0 && CW > 0 && c0 + CW <= C && k > 0 && (int64_t)B * k <= 65535,
+              "avi_posconv_unfold_t: bad shape");
+  const dim3 grid((CW + 31) / 32, (Tq + 31) / 32, B * k);
+  if (out_dtype == AVI_DT_BF16)
+    posconv_unfold_t_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, reinterpret_cast<__nv_bfloat16*>(out), B, T, Tq, C, c0, CW, k);
+  else
+    posconv_unfold_t_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, reinterpret_cast<float*>(out), B, T, Tq, C, c0, CW, k);
+  return check_launch("posconv_unfold_t");
 }
 
 extern "C" int avi_weightnorm_bwd(const float* v, const float* g, const float* dw, float* dv, float* dg, int32_t n_rows, int32_t k,

@@ -586,6 +586,15 @@ def posconv_dw(x, dpc, B, T, groups, k):
     return dw
 
 
+def posconv_unfold_t(x, B, T, Tq, c0, CW, k, dtype):
+    _need_cuda(x)
+    Cc = x.shape[-1]
+    out = torch.empty((k * CW, B * Tq), dtype=dtype, device=x.device)
+    _chk(_lib.load().avi_posconv_unfold_t(_ptr(x.contiguous()), _ptr(out), C.c_int32(_dt(out)), C.c_int32(B), C.c_int32(T), C.c_int32(Tq),
+                                          C.c_int32(Cc), C.c_int32(c0), C.c_int32(CW), C.c_int32(k), _stream()), "avi_posconv_unfold_t")
+    return out
+
+
 def weightnorm_bwd(v, g, dw):
     _need_cuda(v, g, dw)
     k = v.shape[-1]

@@ -315,6 +315,31 @@ class TrainStep:
                      algorithmic_flops=2.0 * B * T * W4 * k * cg)
         return out
 
+    def _posconv_dw(self, x32, dpc32, B, T):
+        """dW [C, C/groups, k] of the grouped positional conv on the tensor cores: per block of 4 groups (192 channels),
+        dW_blk[co, (j, ci)] = sum_{b,t} dpc[b,t,co] * xpad[b,t+j,ci] is one GEMM (rows = 192 output channels, N = k*192, contraction
+        = clips x frames padded to 64 per clip) over the transposed unfold of x; the 4 diagonal 48x48 blocks per tap are the groups'
+        gradients (the off-diagonal ones are cross-group products that the grouped conv does not have)."""
+        cfg = self.model.audio_encoder.config
+        k, g, Cc = cfg.num_conv_pos_embeddings, cfg.num_conv_pos_embedding_groups, cfg.hidden_size
+        cg = Cc // g
+        W4 = 4 * cg
+        Tq = _pad(T)
+        lin = self.lin
+        dw = torch.empty((Cc, cg, k), dtype=torch.float32, device=x32.device)
+        dpc_pad = torch.zeros((B, Tq, Cc), dtype=torch.float32, device=x32.device)
+        dpc_pad[:, :T] = dpc32.view(B, T, Cc)
+        dpc_pad = dpc_pad.view(B * Tq, Cc)
+        for q in range(g // 4):
+            xu = ops.posconv_unfold_t(x32, B, T, Tq, W4 * q, W4, k, lin.dt)                      # [k*192, B*Tq]
+            dT = lin.t(dpc_pad[:, W4 * q:W4 * (q + 1)], B * Tq)                                    # [192, B*Tq]
+            blk = torch.empty((W4, k * W4), dtype=torch.float32, device=x32.device)
+            ops.gemm(dT, xu, None, blk, rows=W4, N=k * W4, K=B * Tq, a_rows_alloc=W4)
+            blk = blk.view(4, cg, k, 4, cg)                                                        # [gl_out, co, tap, gl_in, ci]
+            for gl in range(4):
+                dw[(4 * q + gl) * cg:(4 * q + gl + 1) * cg] = blk[gl, :, :, gl, :].permute(0, 2, 1)  # [co, ci, tap]
+        return dw
+
     # ---------------------------------------------------------------------------- forward
     @torch.no_grad()
     def forward(self, audio, gt_verts):
@@ -492,7 +517,7 @@ class TrainStep:
         dpc = ops.act_bwd(S["pc"], dh0pre, ACT_GELU)
         ops.colsum(dpc, out=g("audio_encoder.encoder.pos_conv_embed.conv.bias"))
         k, groups = cfg.num_conv_pos_embeddings, cfg.num_conv_pos_embedding_groups
-        dw = ops.posconv_dw(S["proj"], dpc, B, T, groups, k)
+        dw = self._posconv_dw(S["proj"], dpc, B, T)
         named = dict(m.named_parameters())
         dv, dg = ops.weightnorm_bwd(named[lay.pos_v], named[lay.pos_g], dw)
         g(lay.pos_v).copy_(dv)

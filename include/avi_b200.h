@@ -298,6 +298,10 @@ int avi_attn_train_bwd(const float* qkv, const float* P, const float* dout, floa
                        int32_t T, int32_t H, int32_t D, float scale, void* stream);
 /* positional conv: dW [C, C/groups, k] from x [B,T,C] and d(pre-activation) [B,T,C]; weight-norm chain rule (dim = 2) */
 int avi_posconv_dw(const float* x, const float* dpc, float* dw, int32_t B, int32_t T, int32_t C, int32_t groups, int32_t k, void* stream);
+/* transposed unfold of the positional conv input for a block of CW channels starting at c0:
+ * out[(j*CW + ci), b*Tq + t] = xpad[b, t + j, c0 + ci] (zero for T <= t < Tq); dW of the block is then one GEMM over (clip, frame) */
+int avi_posconv_unfold_t(const float* x, void* out, int32_t out_dtype, int32_t B, int32_t T, int32_t Tq, int32_t C, int32_t c0, int32_t CW,
+                         int32_t k, void* stream);
 int avi_weightnorm_bwd(const float* v, const float* g, const float* dw, float* dv, float* dg, int32_t n_rows /* C * C/groups */, int32_t k,
                        void* stream);
 /* loss = mean((out - gt)^2) * loss_scale (fp64 scalar on the device) ; dout = d loss / d out (dense [rows, C]) */
