@@ -531,8 +531,16 @@ extern "C" int avi_gemm_bf16_tc(const AviGemmArgs* a, void* stream) {
                            a->res_ld == a->c_ld && a->res_batch_stride == a->c_batch_stride;
   p.tma_store = 0;
   CUtensorMap map_c = map_a;
-  if (!no_tma_store && vec && a->C2 == nullptr && (a->residual == nullptr || inplace_res)) {
-    const uint64_t es = a->c_dtype == AVI_DT_F32 ? 4 : 2;
+  // The TMA unit clips stores at the tensor bounds in 16-byte granules of the innermost dimension (measured:
+  // profiles/probes/tma_clip_probe.py): with N * elemsize not a multiple of 16 the granule holding column N-1 is written whole
+  // (zeros in the surplus columns). That is only acceptable when those columns are the row's own padding, i.e. the pitch ends
+  // exactly at that granule (the 15069-wide vertex rows on their 15072 pitch); a narrower window inside a wider buffer keeps the
+  // per-thread store path.
+  const uint64_t es_c = a->c_dtype == AVI_DT_F32 ? 4 : 2;
+  const uint64_t row_bytes = (uint64_t)a->N * es_c, row_bytes16 = (row_bytes + 15) / 16 * 16;
+  const bool clip_ok = row_bytes == row_bytes16 || row_bytes16 == (uint64_t)a->c_ld * es_c;
+  if (!no_tma_store && vec && clip_ok && a->C2 == nullptr && (a->residual == nullptr || inplace_res)) {
+    const uint64_t es = es_c;
     uint64_t dims[3] = {(uint64_t)a->N, (uint64_t)a->rows, (uint64_t)a->batch};
     uint64_t strides[2] = {(uint64_t)a->c_ld * es, (uint64_t)a->c_batch_stride * es};
     if (a->batch == 1) strides[1] = dims[1] * strides[0];

@@ -95,6 +95,10 @@ class Faceformer(nn.Module):
         fd = args.feature_dim
         if getattr(args, "is_concat_mode", 0) != 0:
             raise NotImplementedError("is_concat_mode != 0 is not on the published path")
+        if args.dataset != "vocaset":
+            # enc_dec_mask(:80-88) leaves ONE visible key per query for vocaset (cross-attention = out_proj(v_proj(mem_t)), which the
+            # kernels exploit); BIWI leaves two keys per query at a 2x memory rate and is not built
+            raise NotImplementedError(f"dataset {args.dataset!r}: only the 'vocaset' alignment mask is built")
         if audio_encoder is None:
             audio_encoder = Wav2Vec2Model.from_pretrained("facebook/wav2vec2-base-960h")     # :168
         self.audio_encoder = audio_encoder

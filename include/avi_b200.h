@@ -71,7 +71,9 @@ typedef struct AviGemmArgs {
 
 /* fp32 CUDA-core path (exact mode, any shape). a_dtype must be AVI_DT_F32. */
 int avi_gemm_f32(const AviGemmArgs* args, void* stream);
-/* bf16 tcgen05/TMEM/TMA path. a_dtype must be AVI_DT_BF16; K % 64 == 0, a_ld % 8 == 0, 16-byte aligned bases. */
+/* bf16 tcgen05/TMEM/TMA path. a_dtype must be AVI_DT_BF16; K % 64 == 0, a_ld % 8 == 0, 16-byte aligned bases.
+ * Output rows whose pitch c_ld ends exactly at the 16-byte granule holding column N-1 (padded rows, e.g. N = 15069 on c_ld = 15072)
+ * get zeros in those padding columns; nothing else outside [rows, N] is written. residual == C (fp32) updates C in place. */
 int avi_gemm_bf16_tc(const AviGemmArgs* args, void* stream);
 /* 1 if the tensor-core path accepts these shapes (host-side check only) */
 int avi_gemm_bf16_tc_supported(const AviGemmArgs* args);

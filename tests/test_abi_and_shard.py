@@ -147,3 +147,13 @@ def test_grad_buckets_world_size_2_gloo():
     for rank, launched, scale, err in res:
         assert scale == 0.5 and err == 0.0                      # mean over the two ranks of (r+1)*arange = 1.5*arange
         assert launched == sorted(launched) and launched[0] >= 1 and launched[-1] == 4   # overlapped: first bucket leaves early
+
+
+def test_unsupported_configurations_raise():
+    """No silent approximation: configurations whose kernels are not built refuse loudly."""
+    from avi_talking_b200.faceformer import Faceformer, make_args
+    with pytest.raises(NotImplementedError, match="vocaset"):
+        Faceformer(make_args(dataset="BIWI"), audio_encoder=_tiny_vert_model().audio_encoder, template=torch.zeros(1, 1, 15069))
+    m = _tiny_vert_model()
+    with pytest.raises(NotImplementedError):
+        m(torch.zeros(1, 16000), torch.zeros(1, 4, 53), torch.zeros(1, 4, 6), torch.zeros(1, 4, 100), teacher_forcing=False)

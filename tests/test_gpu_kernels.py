@@ -224,3 +224,49 @@ def test_conv0_gn_gelu_tensor_core(ops, n):
     # bf16 output rounding is 2^-9 relative; the arithmetic before it is fp32-accurate
     assert (err / (1.0 + ref.abs())).max().item() < 6e-3
     assert err.mean().item() < 1e-3
+
+
+@pytest.mark.parametrize("rows,N,K,ld", [
+    (390, 15069, 64, 15072),     # vertex rows on a 16-byte aligned pitch: TMA-store epilogue, last n-tile 221 -> MMA N = 224
+    (517, 192, 128, 768),        # positional-conv block: N = 192 < one n-tile, output is a column window of a wider buffer
+    (260, 96, 64, 96),           # N = 96: narrow MMA (n_eff 96), bf16-friendly pitch
+    (130, 45, 64, 768),          # unaligned window inside a wider buffer: must fall back to per-thread stores (neighbours intact)
+])
+def test_gemm_bf16_tc_tma_store_windows_and_narrow_tiles(ops, rows, N, K, ld):
+    """Nothing outside the [rows, N] window is touched - except the row's own padding when the pitch ends at the 16-byte granule of
+    column N-1 (the TMA unit clips in 16-byte granules: include/avi_b200.h) - and narrow last n-tiles are exact."""
+    r = _rng(7)
+    A = torch.from_numpy(r.normal(size=(rows, K)).astype(np.float32)).bfloat16()
+    W = torch.from_numpy((r.normal(size=(N, K)) / math.sqrt(K)).astype(np.float32)).bfloat16()
+    b = torch.from_numpy(r.normal(size=(N,)).astype(np.float32))
+    ref = _gemm_ref(A.float(), W.float(), b, 0, None)
+    for dt, tol in ((torch.float32, 1e-4), (torch.bfloat16, 4e-2)):
+        buf = torch.full((rows + 3, ld), 7.0, dtype=dt, device="cuda")          # sentinel everywhere
+        ops.gemm(A.cuda(), W.cuda(), b.cuda(), buf, rows=rows, N=N, K=K, a_rows_alloc=rows, c_ld=ld)
+        got = buf.float().cpu()
+        assert (got[:rows, :N].double() - ref).abs().max().item() < tol
+        es = 4 if dt == torch.float32 else 2
+        pad_end = -(-N * es // 16) * 16 // es                      # end of the 16-byte granule holding column N-1
+        own_padding = pad_end == ld
+        assert torch.all(got[rows:] == 7.0)
+        assert torch.all(got[:rows, (pad_end if own_padding else N):] == 7.0)
+        if own_padding:
+            assert torch.all((got[:rows, N:pad_end] == 7.0) | (got[:rows, N:pad_end] == 0.0))
+
+
+def test_gemm_bf16_tc_inplace_residual_reduce_add(ops):
+    """residual is out: the epilogue updates the fp32 residual stream in place through TMA reduce-add; same numbers as the
+    out-of-place residual epilogue (one fp32 addition either way)."""
+    r = _rng(8)
+    rows, N, K = 700, 768, 768
+    A = torch.from_numpy(r.normal(size=(rows, K)).astype(np.float32)).bfloat16().cuda()
+    W = torch.from_numpy((r.normal(size=(N, K)) / math.sqrt(K)).astype(np.float32)).bfloat16().cuda()
+    b = torch.from_numpy(r.normal(size=(N,)).astype(np.float32)).cuda()
+    res = torch.from_numpy(r.normal(size=(rows, N)).astype(np.float32)).cuda()
+    sep = ops.linear(A, W, b, residual=res, out_dtype=torch.float32)
+    inplace = res.clone()
+    out = ops.linear(A, W, b, residual=inplace, out_dtype=torch.float32, out=inplace)
+    assert out.data_ptr() == inplace.data_ptr()
+    ref = _gemm_ref(A.float().cpu(), W.float().cpu(), b.cpu(), 0, res.cpu())
+    assert (inplace.cpu().double() - ref).abs().max().item() < 1e-4
+    assert torch.equal(inplace, sep)
