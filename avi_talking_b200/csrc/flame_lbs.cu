@@ -73,25 +73,46 @@ __global__ void __launch_bounds__(128) flame_prologue_kernel(const float* __rest
   const int lane = threadIdx.x & 31;
   if (f >= F) return;
   __shared__ float sJ[4][16];
+  __shared__ float sR[4][FL_NJ * 9];
   float* J = sJ[threadIdx.x >> 5];
+  float* Rs = sR[threadIdx.x >> 5];
   float* cf = coef + (int64_t)f * K_pad;
   for (int l = lane; l < K_pad; l += 32) {
     if (l < NB) cf[l] = betas[(int64_t)f * NB + l];
     else if (l == NB + 36) cf[l] = 1.f;
     else if (l > NB + 36) cf[l] = 0.f;
   }
-  if (lane < 15) {
-    const float* jr = jreg + (int64_t)lane * (NB + 1);
+  {
+    // joints = jreg [15, NB+1] . [betas; 1]: the NB-long contraction is split over the lanes (coalesced reads of both operands),
+    // 15 butterfly reductions finish it; the five Rodrigues rotations run on lanes 0..4 meanwhile
     const float* bt = betas + (int64_t)f * NB;
-    float acc = jr[NB];
-    for (int l = 0; l < NB; ++l) acc = fmaf(jr[l], bt[l], acc);
-    J[lane] = acc;
+    float part[15];
+#pragma unroll
+    for (int c = 0; c < 15; ++c) part[c] = 0.f;
+    for (int l = lane; l < NB; l += 32) {
+      const float bv = bt[l];
+#pragma unroll
+      for (int c = 0; c < 15; ++c) part[c] = fmaf(jreg[(int64_t)c * (NB + 1) + l], bv, part[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < 15; ++c) {
+      const float tot = warp_sum(part[c]);
+      if (lane == c) J[c] = tot + jreg[(int64_t)c * (NB + 1) + NB];
+    }
+    if (lane < FL_NJ) {
+      float Rl[9];
+      rodrigues(full_pose + (int64_t)f * 15 + lane * 3, Rl);
+#pragma unroll
+      for (int e = 0; e < 9; ++e) Rs[lane * 9 + e] = Rl[e];
+    }
   }
   __syncwarp();
   if (lane == 0) {
     float R[FL_NJ][9];
 #pragma unroll
-    for (int j = 0; j < FL_NJ; ++j) rodrigues(full_pose + (int64_t)f * 15 + j * 3, R[j]);
+    for (int j = 0; j < FL_NJ; ++j)
+#pragma unroll
+      for (int e = 0; e < 9; ++e) R[j][e] = Rs[j * 9 + e];
     if (dyn_rows) {
       // DecaFLAME.py:110-149 with neck_kin_chain = [neck, global]: rel = R_global R_neck; yaw in degrees picks the contour row
       float r00 = 0.f, r10 = 0.f, r20 = 0.f;

@@ -219,9 +219,13 @@ flame_tc_kernel(const __grid_constant__ CUtensorMap map_dirs, const __grid_const
                 float d = 0.f;
 #pragma unroll
                 for (int q = 0; q < 3; ++q) {
-                  const float4 a = lds128f(Af + (j * 12 + q * 4) * 4);
-                  d = fmaxf(d, fmaxf(fmaxf(fabsf(a.x - (q == 0 ? 1.f : 0.f)), fabsf(a.y - (q == 1 ? 1.f : 0.f))),
-                                     fmaxf(fabsf(a.z - (q == 2 ? 1.f : 0.f)), fabsf(a.w))));
+                  float4 a = lds128f(Af + (j * 12 + q * 4) * 4);
+                  // stored back as D = A - I: the epilogue below works on the deviation from the identity
+                  a.x -= (q == 0 ? 1.f : 0.f);
+                  a.y -= (q == 1 ? 1.f : 0.f);
+                  a.z -= (q == 2 ? 1.f : 0.f);
+                  sts128(Af + (j * 12 + q * 4) * 4, __float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(a.z), __float_as_uint(a.w));
+                  d = fmaxf(d, fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))));
                 }
                 if (d > 1e-7f) m |= 1u << j;
               }
@@ -253,18 +257,15 @@ flame_tc_kernel(const __grid_constant__ CUtensorMap map_dirs, const __grid_const
 #pragma unroll
           for (int n = 0; n < 16; ++n) {
             if (fbase + n < flimit) {  // warp-uniform
+              // verts = sum_j w_j A_j [p; 1] = wsum p + w_j (D [p; 1]),  D = A_j - I (prepared in shared memory above)
               const float4 r0 = lds128f(Aj + (n * (FT_NJ * 12)) * 4);
               const float4 r1 = lds128f(Aj + (n * (FT_NJ * 12) + 4) * 4);
               const float4 r2 = lds128f(Aj + (n * (FT_NJ * 12) + 8) * 4);
               const float px = __uint_as_float(vx[n]) + vtp[0], py = __uint_as_float(vy[n]) + vtp[1], pz = __uint_as_float(vz[n]) + vtp[2];
-              // same association as the generic path: T[e] = fma(w_j, A_e - I_e, wsum I_e), then the row . [p; 1] as nested fmas
-              const float t00 = fmaf(wj, r0.x - 1.f, wsum), t01 = fmaf(wj, r0.y, 0.f), t02 = fmaf(wj, r0.z, 0.f), t03 = fmaf(wj, r0.w, 0.f);
-              const float t10 = fmaf(wj, r1.x, 0.f), t11 = fmaf(wj, r1.y - 1.f, wsum), t12 = fmaf(wj, r1.z, 0.f), t13 = fmaf(wj, r1.w, 0.f);
-              const float t20 = fmaf(wj, r2.x, 0.f), t21 = fmaf(wj, r2.y, 0.f), t22 = fmaf(wj, r2.z - 1.f, wsum), t23 = fmaf(wj, r2.w, 0.f);
               if (v_ok) {
-                o[0] = fmaf(t00, px, fmaf(t01, py, fmaf(t02, pz, t03)));
-                o[1] = fmaf(t10, px, fmaf(t11, py, fmaf(t12, pz, t13)));
-                o[2] = fmaf(t20, px, fmaf(t21, py, fmaf(t22, pz, t23)));
+                o[0] = fmaf(wj, fmaf(r0.x, px, fmaf(r0.y, py, fmaf(r0.z, pz, r0.w))), wsum * px);
+                o[1] = fmaf(wj, fmaf(r1.x, px, fmaf(r1.y, py, fmaf(r1.z, pz, r1.w))), wsum * py);
+                o[2] = fmaf(wj, fmaf(r2.x, px, fmaf(r2.y, py, fmaf(r2.z, pz, r2.w))), wsum * pz);
               }
             }
             o += V3;
@@ -282,9 +283,9 @@ flame_tc_kernel(const __grid_constant__ CUtensorMap map_dirs, const __grid_const
 #pragma unroll
                   for (int q = 0; q < 3; ++q) {
                     const float4 a = lds128f(As + (n * (FT_NJ * 12) + j * 12 + q * 4) * 4);
-                    T[q * 4 + 0] = fmaf(w[j], a.x - (q == 0 ? 1.f : 0.f), T[q * 4 + 0]);
-                    T[q * 4 + 1] = fmaf(w[j], a.y - (q == 1 ? 1.f : 0.f), T[q * 4 + 1]);
-                    T[q * 4 + 2] = fmaf(w[j], a.z - (q == 2 ? 1.f : 0.f), T[q * 4 + 2]);
+                    T[q * 4 + 0] = fmaf(w[j], a.x, T[q * 4 + 0]);
+                    T[q * 4 + 1] = fmaf(w[j], a.y, T[q * 4 + 1]);
+                    T[q * 4 + 2] = fmaf(w[j], a.z, T[q * 4 + 2]);
                     T[q * 4 + 3] = fmaf(w[j], a.w, T[q * 4 + 3]);
                   }
                 }
