@@ -511,6 +511,46 @@ def golden_train():
     print("train.npz", len(out), "arrays")
 
 
+def _exec_reference_functions(path, names, extra_globals):
+    """Compile only the named top-level functions of a reference file (its imports need librosa / pytorch_lightning / ...)."""
+    import ast
+    src = open(path).read()
+    tree = ast.parse(src)
+    keep = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names]
+    assert len(keep) == len(names), [n.name for n in keep]
+    g = {"np": np, "__name__": "reference_subset"}
+    g.update(extra_globals)
+    exec(compile(ast.Module(body=keep, type_ignores=[]), path, "exec"), g)
+    return g
+
+
+def frontend_wav(n, seed):
+    return (np.random.default_rng(seed).normal(size=n) * 3000).clip(-32767, 32767).astype(np.int16)
+
+
+def golden_frontend():
+    """The reference's OWN process_audio / create_base_sample (evaluation_functions.py:141-160,690-714), compiled from source."""
+    path = os.path.join(REF, "third_party", "inferno", "inferno_apps", "TalkingHead", "evaluation", "evaluation_functions.py")
+    cur = {}
+    g = _exec_reference_functions(path, ["process_audio", "create_base_sample"], {
+        "read_audio": lambda p: (cur["wav"], 16000),
+        "create_condition": lambda th, sample: sample,
+    })
+    th = types.SimpleNamespace(cfg=types.SimpleNamespace(data=types.SimpleNamespace(reconstruction_type=["rec"])))
+    out = {}
+    for i, (n, kw) in enumerate([(16000 * 4 + 123, {}), (16000 * 2, dict(smallest_unit=8)), (9999, dict(silent_frames_start=3, silent_frames_end=2)),
+                                 (640 * 7, dict(smallest_unit=4, silence_all=True)), (100, {})]):
+        cur["wav"] = frontend_wav(n, 700 + i)
+        pa = g["process_audio"](cur["wav"], 16000, 25)
+        out[f"pa_{i}"] = pa["raw_audio"]
+        s = g["create_base_sample"](th, "unused.wav", **kw)
+        out[f"cbs_{i}_raw"] = s["raw_audio"]
+        for k in ("gt_exp", "gt_shape", "gt_jaw", "gt_tex"):
+            out[f"cbs_{i}_{k}_shape"] = np.array(s["reconstruction"]["rec"][k].shape)
+    np.savez_compressed(os.path.join(GOLD, "frontend.npz"), **out)
+    print("frontend.npz", {k: v.shape for k, v in out.items() if "raw" in k or k.startswith("pa_")})
+
+
 def main():
     _paths()
     os.makedirs(GOLD, exist_ok=True)
@@ -521,6 +561,7 @@ def main():
     golden_prior()
     golden_emote()
     golden_train()
+    golden_frontend()
 
 
 if __name__ == "__main__":

@@ -153,3 +153,30 @@ def test_flame_vertices_sequence_hoisted_shape(n_shape, T):
         err = (got.cpu() - want).abs().max().item()
         print(f"vertices_sequence n_shape={n_shape} T={T} {prec}: max abs vertex error {err:.3e} m")
         assert got.shape == (G, T, 15069) and err < tol
+
+
+def test_frontend_batch_and_result_sink():
+    """Row 8f-2: int16 framing on the host, cast + z-norm on the GPU, results through the double-buffered pinned sink."""
+    from avi_talking_b200 import frontend as fe
+    from oracle.make_golden import frontend_wav
+    samples = [fe.create_base_sample(frontend_wav(16000 * 2, 800 + c)) for c in range(3)]
+    batch = fe.batch_samples(samples)
+    assert batch["raw_audio"].is_cuda and batch["raw_audio"].dtype == torch.float32
+    ref = np.stack([s["raw_audio"] for s in samples]).astype(np.float32)
+    assert np.array_equal(batch["raw_audio"].cpu().numpy(), ref)                     # int16 -> fp32 is exact
+    sink = fe.ResultSink(("predicted_exp", "predicted_jaw"))
+    outs = []
+    g = torch.Generator().manual_seed(1)
+    sent = []
+    for i in range(4):
+        res = {"predicted_exp": torch.randn(3, 51 + i, 50, generator=g).cuda(), "predicted_jaw": torch.randn(3, 51 + i, 3, generator=g).cuda()}
+        sent.append({k: v.cpu().clone() for k, v in res.items()})
+        prev = sink.push(res)
+        if prev is not None:
+            outs.append({k: v.clone() for k, v in prev.items()})
+    outs.append({k: v.clone() for k, v in sink.flush().items()})
+    assert len(outs) == 4
+    for a, b in zip(sent, outs):
+        assert torch.equal(a["predicted_exp"], b["predicted_exp"]) and torch.equal(a["predicted_jaw"], b["predicted_jaw"])
+    d = fe.ResultSink.flame_dicts(outs[0], np.zeros((3, 300), np.float32))
+    assert len(d) == 3 and d[0]["expression"].shape == (51, 50) and not d[0]["global_pose"].any()

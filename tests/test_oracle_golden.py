@@ -168,3 +168,21 @@ def test_train_step_matches_reference(golden):
             # Adam's first step is lr * g / (|g| + eps): compare where the reference's |g| is not at the eps floor
             ok = np.abs(ref) > 1e-6 * scale + 1e-7
             np.testing.assert_allclose(dp[ok], g[f"{tag}_dp/{nme}"][ok], atol=2e-7, rtol=0, err_msg=nme)
+
+
+def test_frontend_matches_reference_bit_exact(golden):
+    """avi_talking_b200.frontend (host-side framing of the audio, integer work) against the reference's own process_audio /
+    create_base_sample compiled from source (oracle/make_golden.golden_frontend): bit-exact, including upstream's np.pad quirk."""
+    from avi_talking_b200 import frontend as fe
+    from oracle.make_golden import frontend_wav
+    g = golden("frontend")
+    cases = [(16000 * 4 + 123, {}), (16000 * 2, dict(smallest_unit=8)), (9999, dict(silent_frames_start=3, silent_frames_end=2)),
+             (640 * 7, dict(smallest_unit=4, silence_all=True)), (100, {})]
+    for i, (n, kw) in enumerate(cases):
+        wav = frontend_wav(n, 700 + i)
+        pa = fe.process_audio(wav, 16000, 25)
+        assert pa["raw_audio"].dtype == np.int16 and np.array_equal(pa["raw_audio"], g[f"pa_{i}"])
+        s = fe.create_base_sample(wav, **kw)
+        assert np.array_equal(s["raw_audio"], g[f"cbs_{i}_raw"])
+        for k in ("gt_exp", "gt_shape", "gt_jaw", "gt_tex"):
+            assert tuple(s[k].shape) == tuple(g[f"cbs_{i}_{k}_shape"]) and not s[k].any()
