@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libavi_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "avi_b200.h")
 
-ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
+ACT_NONE, ACT_GELU, ACT_RELU, ACT_QUICK_GELU = 0, 1, 2, 3
 DT_F32, DT_BF16 = 0, 1
 
 _lib = None

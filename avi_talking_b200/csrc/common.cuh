@@ -54,6 +54,9 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return fmaf(-a, poly * t * e, fmaxf(x, 0.f));
 }
 
+// CLIP's quick_gelu: x * sigmoid(1.702 x)
+__device__ __forceinline__ float quick_gelu(float x) { return x / (1.f + __expf(-1.702f * x)); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

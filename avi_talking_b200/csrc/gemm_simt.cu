@@ -72,6 +72,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const SimtParams p) {
       float v = acc[i][j] + (p.bias ? p.bias[n] : 0.f);
       if (p.act == AVI_ACT_GELU) v = gelu_erf(v);
       else if (p.act == AVI_ACT_RELU) v = fmaxf(v, 0.f);
+      else if (p.act == AVI_ACT_QUICK_GELU) v = quick_gelu(v);
       if (p.residual) v += p.residual[(int64_t)b * p.res_batch_stride + (int64_t)r * p.res_ld + n];
       const int64_t o = (int64_t)b * p.c_batch_stride + (int64_t)r * p.c_ld + n;
       if (p.C) p.C[o] = v;

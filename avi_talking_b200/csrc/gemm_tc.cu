@@ -43,6 +43,7 @@ struct TcParams {
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == AVI_ACT_GELU) return gelu_erf(v);
   if (act == AVI_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == AVI_ACT_QUICK_GELU) return quick_gelu(v);
   return v;
 }
 
@@ -205,6 +206,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         } else if (p.act == AVI_ACT_RELU) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+        } else if (p.act == AVI_ACT_QUICK_GELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = quick_gelu(f[j]);
         }
         const bool full_n = n_base + 32 <= p.N;
         if (fast_bf16 && full_n) {

@@ -250,6 +250,9 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         } else if (p.act == AVI_ACT_RELU) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+        } else if (p.act == AVI_ACT_QUICK_GELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = quick_gelu(f[j]);
         }
         const bool full_n = n_base + 32 <= p.N;
         // staging tile: 32 rows x 16 words (pitch 16); the 4-word group g of row r lives at group g ^ ((r >> 1) & 3), which

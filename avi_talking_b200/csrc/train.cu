@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(256) attn_train_fwd_kernel(const float* __rest
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
     const int j = lane + 32 * u;
-    const bool va = j < T && !(bias_mode == 1 && j > ia), vb = j < T && !(bias_mode == 1 && j > ib);
+    const bool va = j < T && !(bias_mode != 0 && j > ia), vb = j < T && !(bias_mode != 0 && j > ib);
     if (bias_mode == 1) {
       sa[u] -= slope * (float)((ia - j) / period);
       sb[u] -= slope * (float)((ib - j) / period);
@@ -571,9 +571,47 @@ __global__ void lerp_kernel(const void* __restrict__ in, int in_dtype, int64_t i
   out[idx] = l0 * load_as_float(in, in_dtype, base + (int64_t)i0 * C + c) + l1 * load_as_float(in, in_dtype, base + (int64_t)i1 * C + c);
 }
 
+// CLIPTextEmbeddings: out[b*T + t, :] = tok_emb[ids[b, t], :] + pos_emb[t, :]
+__global__ void embed_tokens_kernel(const int64_t* __restrict__ ids, const float* __restrict__ tok, const float* __restrict__ pos,
+                                    float* __restrict__ out, int T, int C, int vocab, int64_t n4) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const int c4 = (int)(i % (C / 4));
+  const int64_t row = i / (C / 4);
+  const int t = (int)(row % T);
+  int64_t id = ids[row];
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+  const float4 a = reinterpret_cast<const float4*>(tok + id * C)[c4];
+  const float4 b = reinterpret_cast<const float4*>(pos + (int64_t)t * C)[c4];
+  reinterpret_cast<float4*>(out + row * C)[c4] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+
+// out[b, c] = mean_t x[b*T + t, c]
+__global__ void token_mean_kernel(const float* __restrict__ x, float* __restrict__ out, int T, int C) {
+  const int b = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int t = 0; t < T; ++t) s += x[((int64_t)b * T + t) * C + c];
+  out[(int64_t)b * C + c] = s / (float)T;
+}
+
 }  // namespace avi
 
 using namespace avi;
+
+extern "C" int avi_embed_tokens(const int64_t* ids, const float* tok_emb, const float* pos_emb, float* out, int32_t B, int32_t T,
+                                int32_t C, int32_t vocab, void* stream) {
+  AVI_REQUIRE(B > 0 && T > 0 && C > 0 && C % 4 == 0 && vocab > 0, "avi_embed_tokens: bad shape");
+  const int64_t n4 = (int64_t)B * T * (C / 4);
+  embed_tokens_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ids, tok_emb, pos_emb, out, T, C, vocab, n4);
+  return check_launch("embed_tokens");
+}
+
+extern "C" int avi_token_mean(const float* x, float* out, int32_t B, int32_t T, int32_t C, void* stream) {
+  AVI_REQUIRE(B > 0 && T > 0 && C > 0 && B <= 65535, "avi_token_mean: bad shape");
+  token_mean_kernel<<<dim3((C + 127) / 128, B), 128, 0, (cudaStream_t)stream>>>(x, out, T, C);
+  return check_launch("token_mean");
+}
 
 extern "C" int avi_transpose_cast(const float* src, void* dst, int32_t dst_dtype, int32_t R, int32_t C, int64_t src_ld, int32_t R_pad,
                                   void* stream) {
@@ -681,7 +719,8 @@ extern "C" int avi_attn_train_fwd(const float* qkv, float* out, float* P, int32_
                                   int32_t bias_mode, int32_t period, void* stream) {
   AVI_REQUIRE(B > 0 && T > 0 && T <= ATT_MAXT && H > 0 && (D == 16 || D == 32 || D == 64),
               "avi_attn_train_fwd: T <= 128 and head dim 16 / 32 / 64 (T=%d D=%d)", T, D);
-  AVI_REQUIRE(bias_mode == 0 || H == 4, "avi_attn_train_fwd: the FaceFormer bias mask is defined for 4 heads");
+  AVI_REQUIRE(bias_mode >= 0 && bias_mode <= 2, "avi_attn_train_fwd: bias_mode 0 (none), 1 (FaceFormer biased causal), 2 (causal)");
+  AVI_REQUIRE(bias_mode != 1 || H == 4, "avi_attn_train_fwd: the FaceFormer bias mask is defined for 4 heads");
   AVI_REQUIRE(((uintptr_t)qkv % 16) == 0, "avi_attn_train_fwd: qkv must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   if (D == 64) return attn_fwd_launch<64>(qkv, out, P, B, T, H, scale, bias_mode, period, st);

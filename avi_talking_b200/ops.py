@@ -7,7 +7,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, DT_BF16, DT_F32, AviDecoderWeights, AviGemmArgs, AviPriorNet  # noqa: F401
+from ._lib import ACT_GELU, ACT_NONE, ACT_QUICK_GELU, ACT_RELU, DT_BF16, DT_F32, AviDecoderWeights, AviGemmArgs, AviPriorNet  # noqa: F401
 
 
 # bench.py's roofline pass: when set to a list, every launch made through `_timed` appends
@@ -634,4 +634,23 @@ def w2v_lerp(x, in_batch_stride, B, T_in, T_out, Cc):
     out = torch.empty((B * T_out, Cc), dtype=torch.float32, device=x.device)
     _chk(_lib.load().avi_w2v_lerp(_ptr(x), C.c_int32(_dt(x)), C.c_int64(in_batch_stride), _ptr(out), C.c_int32(B), C.c_int32(T_in),
                                   C.c_int32(T_out), C.c_int32(Cc), _stream()), "avi_w2v_lerp")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ CLIP text tower pieces
+def embed_tokens(ids, tok_emb, pos_emb):
+    _need_cuda(ids, tok_emb, pos_emb)
+    B, T = ids.shape
+    Cc = tok_emb.shape[1]
+    out = torch.empty((B * T, Cc), dtype=torch.float32, device=ids.device)
+    _chk(_lib.load().avi_embed_tokens(_ptr(ids.contiguous().long()), _ptr(tok_emb), _ptr(pos_emb), _ptr(out), C.c_int32(B), C.c_int32(T),
+                                      C.c_int32(Cc), C.c_int32(tok_emb.shape[0]), _stream()), "avi_embed_tokens")
+    return out
+
+
+def token_mean(x2d, B, T):
+    _need_cuda(x2d)
+    Cc = x2d.shape[-1]
+    out = torch.empty((B, Cc), dtype=torch.float32, device=x2d.device)
+    _chk(_lib.load().avi_token_mean(_ptr(x2d.contiguous()), _ptr(out), C.c_int32(B), C.c_int32(T), C.c_int32(Cc), _stream()), "avi_token_mean")
     return out

@@ -388,3 +388,47 @@ def emote_sample(batch: int, n_frames: int, seed: int = 50) -> dict:
                 gt_jaw=_t(0.1 * rng.normal(size=(batch, n_frames, 3))),
                 gt_expression_label_condition=one_hot(E.n_expression), gt_expression_intensity_condition=one_hot(E.n_intensities),
                 gt_expression_identity_condition=one_hot(E.n_identities))
+
+
+# --------------------------------------------------------------------------- CLIP-L text tower
+CLIP_TEXT = SimpleNamespace(vocab=49408, hidden=768, heads=12, ffn=3072, layers=12, max_pos=77, eps=1e-5)
+
+
+def clip_text_state(seed: int = 60, layers: int = 12, vocab: int = CLIP_TEXT.vocab) -> dict:
+    """State dict with transformers' CLIPTextModel key names (text_model.*), seeded; same spirit as wav2vec2_state (non-trivial
+    biases / LayerNorm gains so every path is exercised)."""
+    rng = np.random.default_rng(seed)
+    sd = {}
+    C, Fd = CLIP_TEXT.hidden, CLIP_TEXT.ffn
+    sd["text_model.embeddings.token_embedding.weight"] = _t(rng.normal(0, 0.5, size=(vocab, C)))
+    sd["text_model.embeddings.position_embedding.weight"] = _t(rng.normal(0, 0.3, size=(CLIP_TEXT.max_pos, C)))
+
+    def lin(name, out_f, in_f, gain=0.7):
+        sd[name + ".weight"] = _t(rng.normal(0, gain / math.sqrt(in_f), size=(out_f, in_f)))
+        sd[name + ".bias"] = _t(rng.normal(0, 0.02, size=(out_f,)))
+
+    def ln(name, c):
+        sd[name + ".weight"] = _t(1.0 + 0.1 * rng.normal(size=(c,)))
+        sd[name + ".bias"] = _t(0.05 * rng.normal(size=(c,)))
+
+    for l in range(layers):
+        p = f"text_model.encoder.layers.{l}."
+        for nm in ("k_proj", "v_proj", "q_proj", "out_proj"):
+            lin(p + "self_attn." + nm, C, C, gain=1.0 if nm in ("q_proj", "k_proj") else 0.7)
+        ln(p + "layer_norm1", C)
+        lin(p + "mlp.fc1", Fd, C)
+        lin(p + "mlp.fc2", C, Fd)
+        ln(p + "layer_norm2", C)
+    ln("text_model.final_layer_norm", C)
+    return sd
+
+
+def clip_tokens(batch: int, seed: int = 61, vocab: int = CLIP_TEXT.vocab) -> torch.Tensor:
+    """Synthetic token ids [B, 77] shaped like CLIPTokenizer output: BOS, a few words, EOS, padding (= EOS id)."""
+    rng = np.random.default_rng(seed)
+    ids = np.full((batch, CLIP_TEXT.max_pos), vocab - 1, dtype=np.int64)
+    ids[:, 0] = vocab - 2
+    for b in range(batch):
+        n = int(rng.integers(3, 40))
+        ids[b, 1:1 + n] = rng.integers(0, vocab - 2, size=n)
+    return torch.from_numpy(ids)

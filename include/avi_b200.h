@@ -45,7 +45,7 @@ int64_t avi_launch_count(void);
  * A rows may overlap (Conv1d as a GEMM over time-major activations): the row for (b, r) starts at
  *   A + b*a_batch_stride + r*conv_stride*a_ld  and is conv_taps*a_ld... see AviGemmArgs below.
  */
-enum { AVI_ACT_NONE = 0, AVI_ACT_GELU = 1 /* exact erf */, AVI_ACT_RELU = 2 };
+enum { AVI_ACT_NONE = 0, AVI_ACT_GELU = 1 /* exact erf */, AVI_ACT_RELU = 2, AVI_ACT_QUICK_GELU = 3 /* x * sigmoid(1.702 x), CLIP */ };
 enum { AVI_DT_F32 = 0, AVI_DT_BF16 = 1 };
 
 typedef struct AviGemmArgs {
@@ -269,6 +269,13 @@ int avi_lrelu_bn_repeat(const float* x, const float* bn_scale, const float* bn_s
 int avi_sub_add_rows(const float* a, const float* neutral, const float* tpl, float* out, int32_t B, int32_t T, int32_t C,
                      int64_t row_stride, void* stream);
 
+/* ------------------------------------------------------------------ CLIP text tower (models/diffusion_prior.py:30-55 -> HF CLIPTextModel)
+ * out[b*T + t, :] = tok_emb[ids[b, t], :] + pos_emb[t, :]   (CLIPTextEmbeddings) */
+int avi_embed_tokens(const int64_t* ids, const float* tok_emb, const float* pos_emb, float* out, int32_t B, int32_t T, int32_t C,
+                     int32_t vocab, void* stream);
+/* out[b, :] = mean_t x[b*T + t, :]   (the 77-token mean pooling of train_diffusion_prior.py:439,711) */
+int avi_token_mean(const float* x, float* out, int32_t B, int32_t T, int32_t C, void* stream);
+
 /* ------------------------------------------------------------------ training step (BASELINE configs[4]) ------------------------------------------------------------------
  * Backward / optimizer pieces of the teacher-forced faceformer_vert step (models/faceformer_vert.py:360-482; feature extractor
  * frozen :154). Dense backward contractions use avi_gemm_bf16_tc on operands laid out by avi_transpose_cast_bf16. */
@@ -293,7 +300,7 @@ int avi_act_bwd(const float* pre, const float* dout, float* dpre, int64_t n, int
 int avi_layernorm_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, float* db, int64_t rows, int32_t C, float eps,
                       void* stream);
 /* attention for training (T <= 128): forward keeps P [B,H,T,T]; bias_mode 0 none, 1 FaceFormer biased causal mask
- * (init_biased_mask, faceformer_vert.py via :56-77 of faceformer_disentangle.py). qkv fp32 [B,T,3*H*D] */
+ * (init_biased_mask, faceformer_vert.py via :56-77 of faceformer_disentangle.py), 2 plain causal mask (CLIP text). qkv fp32 [B,T,3*H*D] */
 int avi_attn_train_fwd(const float* qkv, float* out, float* P, int32_t B, int32_t T, int32_t H, int32_t D, float scale, int32_t bias_mode,
                        int32_t period, void* stream);
 int avi_attn_train_bwd(const float* qkv, const float* P, const float* dout, float* dqkv, float* dS_scratch /* [B,H,T,T] */, int32_t B,

@@ -551,6 +551,27 @@ def golden_frontend():
     print("frontend.npz", {k: v.shape for k, v in out.items() if "raw" in k or k.startswith("pa_")})
 
 
+def golden_clip_text():
+    """transformers.CLIPTextModel - the class models/diffusion_prior.py:19,37 instantiates - on the seeded synthetic state dict."""
+    from transformers import CLIPTextConfig, CLIPTextModel
+    from . import synth
+    out = {}
+    for tag, layers, B in (("l12", 12, 3), ("l2", 2, 2)):
+        cfg = CLIPTextConfig(vocab_size=synth.CLIP_TEXT.vocab, hidden_size=768, intermediate_size=3072, num_hidden_layers=layers,
+                             num_attention_heads=12, max_position_embeddings=77, hidden_act="quick_gelu", projection_dim=768)
+        m = CLIPTextModel(cfg).eval()
+        missing, unexpected = m.load_state_dict(synth.clip_text_state(60, layers), strict=False)
+        assert not unexpected and all("position_ids" in k for k in missing), (missing, unexpected)
+        ids = synth.clip_tokens(B, seed=61)
+        with torch.no_grad():
+            o = m(input_ids=ids)
+        out[f"{tag}_last_sub"] = o.last_hidden_state[:, ::4, ::3].numpy()
+        out[f"{tag}_voxel"] = o.last_hidden_state.mean(dim=1).numpy()
+        out[f"{tag}_chk"] = checksum(o.last_hidden_state)
+    np.savez_compressed(os.path.join(GOLD, "clip_text.npz"), **out)
+    print("clip_text.npz", {k: v.shape for k, v in out.items()})
+
+
 def main():
     _paths()
     os.makedirs(GOLD, exist_ok=True)
@@ -562,6 +583,7 @@ def main():
     golden_emote()
     golden_train()
     golden_frontend()
+    golden_clip_text()
 
 
 if __name__ == "__main__":

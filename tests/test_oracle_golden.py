@@ -186,3 +186,16 @@ def test_frontend_matches_reference_bit_exact(golden):
         assert np.array_equal(s["raw_audio"], g[f"cbs_{i}_raw"])
         for k in ("gt_exp", "gt_shape", "gt_jaw", "gt_tex"):
             assert tuple(s[k].shape) == tuple(g[f"cbs_{i}_{k}_shape"]) and not s[k].any()
+
+
+def test_clip_text_oracle_matches_transformers(golden):
+    """oracle/clip_oracle.py against transformers.CLIPTextModel (the class models/diffusion_prior.py:37 instantiates)."""
+    from oracle import clip_oracle as co
+    g = golden("clip_text")
+    for tag, layers, B in (("l12", 12, 3), ("l2", 2, 2)):
+        sd = synth.clip_text_state(60, layers)
+        ids = synth.clip_tokens(B, seed=61)
+        with torch.no_grad():
+            last = co.clip_text_forward(sd, ids, layers)
+        np.testing.assert_allclose(last[:, ::4, ::3].numpy(), g[f"{tag}_last_sub"], atol=2e-5, rtol=0)
+        np.testing.assert_allclose(last.mean(dim=1).numpy(), g[f"{tag}_voxel"], atol=1e-5, rtol=0)
