@@ -22,6 +22,11 @@ Pinning status (see DESIGN.md "Oracle"):
   * faceformer_vert training step (train_oracle.py): PINNED - the reference's own
     forward_switch_frame + loss.backward() + torch.optim.Adam -> tests/golden/train.npz
     (deterministic mode: dropout / SpecAugment / LayerDrop inactive).
+  * CLIP text tower (clip_oracle.py): PINNED on transformers.CLIPTextModel, the class
+    models/diffusion_prior.py:37 instantiates -> tests/golden/clip_text.npz.
+  * Audio front end (avi_talking_b200/frontend.py is host logic, checked directly):
+    PINNED on the reference's own process_audio / create_base_sample compiled from
+    source -> tests/golden/frontend.npz.
   * Diffusion prior (prior_oracle.py): the reference's own class sources are pinned
     (executed over oracle/dalle2_standin.py -> tests/golden/prior.npz); the stand-in
     for the un-vendored, un-pinned dalle2_pytorch / rotary_embedding_torch is a
