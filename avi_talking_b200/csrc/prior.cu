@@ -64,32 +64,48 @@ __device__ __forceinline__ void matmul_rows(const float* __restrict__ Wt, int K,
 #pragma unroll
     for (int v = 0; v < V; ++v) acc[r][v] = 0.f;
   const float* wp = Wt + (int64_t)k0 * N + cg * V;
-#pragma unroll 4
-  for (int k = 0; k < kchunk; ++k) {
-    float w[V];
-    if constexpr (V == 2) {
-      const float2 t = __ldg(reinterpret_cast<const float2*>(wp + (int64_t)k * N));
-      w[0] = t.x;
-      w[1] = t.y;
-    } else {
-      w[0] = __ldg(wp + (int64_t)k * N);
-    }
-    const float* xr = inT + (k0 + k) * R;
-    float x[R];
-    if constexpr (R % 4 == 0) {
+  // The weights come from L2 (every CTA streams the same 8 MB per denoising step) and each thread walks its own column: with a
+  // handful of loads in flight per thread the loop ran at L2 LATENCY (~51 GB/s per SM). Issue PR_WB independent loads first, then
+  // consume them: 16 x 512 threads x 4-8 bytes in flight per SM.
+  constexpr int PR_WB = 16;
+  for (int kb = 0; kb < kchunk; kb += PR_WB) {
+    float w[PR_WB][V];
 #pragma unroll
-      for (int q = 0; q < R / 4; ++q) {
-        const float4 t = reinterpret_cast<const float4*>(xr)[q];
-        x[4 * q] = t.x; x[4 * q + 1] = t.y; x[4 * q + 2] = t.z; x[4 * q + 3] = t.w;
+    for (int u = 0; u < PR_WB; ++u) {
+      if (kb + u < kchunk) {
+        if constexpr (V == 2) {
+          const float2 t = __ldg(reinterpret_cast<const float2*>(wp + (int64_t)(kb + u) * N));
+          w[u][0] = t.x;
+          w[u][1] = t.y;
+        } else {
+          w[u][0] = __ldg(wp + (int64_t)(kb + u) * N);
+        }
+      } else {
+#pragma unroll
+        for (int v = 0; v < V; ++v) w[u][v] = 0.f;
       }
-    } else {
-#pragma unroll
-      for (int r = 0; r < R; ++r) x[r] = xr[r];
     }
 #pragma unroll
-    for (int r = 0; r < R; ++r)
+    for (int u = 0; u < PR_WB; ++u) {
+      if (kb + u < kchunk) {
+        const float* xr = inT + (k0 + kb + u) * R;
+        float x[R];
+        if constexpr (R % 4 == 0) {
 #pragma unroll
-      for (int v = 0; v < V; ++v) acc[r][v] = fmaf(x[r], w[v], acc[r][v]);
+          for (int q = 0; q < R / 4; ++q) {
+            const float4 t = reinterpret_cast<const float4*>(xr)[q];
+            x[4 * q] = t.x; x[4 * q + 1] = t.y; x[4 * q + 2] = t.z; x[4 * q + 3] = t.w;
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < R; ++r) x[r] = xr[r];
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int v = 0; v < V; ++v) acc[r][v] = fmaf(x[r], w[u][v], acc[r][v]);
+      }
+    }
   }
   if (ksplit == 1) {
 #pragma unroll
