@@ -269,3 +269,33 @@ def test_graphed_predict_and_convert_matches_eager():
         v0, f0 = m.predict_and_convert(audio, emo, coeff, pose.clone(), shape)
         v1, f1 = m.graphed_predict_and_convert(audio, emo, coeff, pose.clone(), shape)
         assert torch.equal(v0, v1) and torch.equal(f0, f1)
+
+
+@pytest.mark.gpu
+def test_long_and_ragged_clips_take_the_general_kernels():
+    """Clips beyond the fast paths' limits: 12 s of audio -> T = 299 frames (> 256: generic AR decoder and generic attention), a
+    batch of 3 such clips, and the shortest clip the conv stack admits one frame for. fp32 mode against the CPU oracle."""
+    n = 192000
+    a = synth.audio(3, n, seed=77)
+    T = 299
+    emo = torch.stack([synth.fan_embeddings(T, seed=30 + c)["emo"] for c in range(3)])
+    sd_w2v, sd_ff = synth.wav2vec2_state(0), synth.faceformer_state(fd=64, seed=74)
+    template = synth.flame_buffers()["v_template"].reshape(1, 1, 15069)
+    ref = ffo.predict(sd_ff, sd_w2v, template, a[:1], emo[:1], cached=True)
+    assert ref.shape[1] == T
+    m = build_faceformer("fp32", fd=64, seed=74)
+    v = m.predict_from_embeddings(a.cuda(), emo.cuda())
+    assert tuple(v.shape) == (3, T, 15069)
+    assert (v[:1].cpu() - ref).abs().max().item() < 1e-5
+    m16 = build_faceformer("bf16", fd=64, seed=74)
+    v16 = m16.predict_from_embeddings(a.cuda(), emo.cuda())
+    assert (v16[:1].cpu() - ref).abs().max().item() < 1.5e-4      # 299 sequential decoder steps on bf16 audio features
+    assert (v16[1:] - v[1:]).abs().max().item() < 1.5e-4
+    # one second and a bit: T = 4 frames; and a clip so short that the encoder yields a single frame
+    for n_s, T_s in ((3000, 4), (1000, 1)):
+        a_s = synth.audio(2, n_s, seed=78)
+        emo_s = torch.zeros(2, max(T_s, 1), 30)
+        ref_s = ffo.predict(sd_ff, sd_w2v, template, a_s, emo_s, cached=True)
+        assert ref_s.shape[1] == T_s
+        v_s = m.predict_from_embeddings(a_s.cuda(), emo_s.cuda())
+        assert (v_s.cpu() - ref_s).abs().max().item() < 1e-5
