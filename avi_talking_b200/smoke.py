@@ -1,4 +1,5 @@
-"""One small invocation of the hot path on cuda:0, checked against the CPU oracle (used by __graft_entry__.smoke())."""
+"""Builders of the drop-in models loaded with the seeded synthetic weights / assets (avi_talking_b200.synth): used by
+__graft_entry__.smoke(), bench.py, the profiles/ scripts and the tests. Nothing here touches the oracle."""
 from __future__ import annotations
 
 import numpy as np
@@ -64,40 +65,3 @@ def build_talking_head(precision: str = "fp32", device: str = "cuda", flame_dir:
     w2v.precision = precision
     flame.precision = precision
     return m.to(device).eval()
-
-
-def run_smoke(verbose: bool = False) -> dict:
-    from oracle import faceformer_oracle as ffo   # checker only
-    from oracle import flame_oracle as fo
-
-    from . import _lib, synth
-
-    _lib.load(check_symbols=True)
-    torch.cuda.set_device(0)
-    res = {}
-    a = synth.audio(2, 16000, seed=1234)
-    emo = torch.stack([synth.fan_embeddings(24, seed=20 + c)["emo"] for c in range(2)])
-    sd_w2v, sd_ff = synth.wav2vec2_state(0), synth.faceformer_state(fd=64, seed=74)
-    buf = synth.flame_buffers()
-    template = buf["v_template"].reshape(1, 1, 15069)
-    ref = ffo.predict(sd_ff, sd_w2v, template, a, emo, cached=True)
-    n0 = _lib.launch_count()
-    p = synth.flame_params(8, seed=3)
-    want = fo.flame_forward(buf, p["shape"], p["exp"], p["pose"], p["eye"], mediapipe=True)
-    # tolerances: fp32 mode 1e-5 m (vertices) / 1e-6 m (FLAME alone); bf16 mode 1e-4 m / 5e-5 m (fp16 tensor-core blend)
-    for prec, tol, tol_flame in (("fp32", 1e-5, 1e-6), ("bf16", 1e-4, 5e-5)):
-        m = build_models(prec)
-        v = m.predict_from_embeddings(a.cuda(), emo.cuda())
-        torch.cuda.synchronize()
-        err = (v.cpu() - ref).abs().max().item()
-        res[f"predict_{prec}_max_abs_m"] = err
-        assert err < tol, f"{prec} predict: max abs vertex error {err} m exceeds {tol}"
-        got = m.flame(p["shape"].cuda(), p["exp"].cuda(), p["pose"].cuda(), p["eye"].cuda())
-        for name, g, w in zip(("verts", "lmk2d", "lmk3d", "lmk_mp"), got, want):
-            err = (g.cpu() - w).abs().max().item()
-            res[f"flame_{prec}_{name}_max_abs_m"] = err
-            assert err < tol_flame, f"FLAME {prec} {name}: {err}"
-    res["kernel_launches"] = _lib.launch_count() - n0
-    if verbose:
-        print("smoke OK:", res)
-    return res

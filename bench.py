@@ -41,6 +41,9 @@ def parse():
     ap.add_argument("--cpu-clips", type=int, default=2, help="clips in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying its CUDA graph")
+    ap.add_argument("--cpu-baseline", default=None, choices=["prior", "train", "clip"],
+                    help="only time the CPU oracle of another BASELINE config on a bounded sample (the cpu_baseline leg of the "
+                         "profiles/*_bench.py GPU scripts, which themselves never touch oracle/) and print one JSON line")
     return ap.parse_args()
 
 
@@ -157,6 +160,45 @@ def time_cpu(args, n_samples, T, clips, reps):
         cpu_reference_step(st, host["audio"], host["emo"], host["coeff"], host["pose"], shape_pf)
         times.append(time.perf_counter() - t0)
     return times
+
+
+def best_of(fn, reps=2):
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        fn()
+        ts.append(time.perf_counter() - t0)
+    return min(ts)
+
+
+def cpu_baseline_other(which):
+    """cpu_baseline leg for the configs measured by profiles/{prior,train,clip}_bench.py: the oracle port on all host threads, bounded."""
+    from avi_talking_b200 import synth
+    torch.set_num_threads(os.cpu_count() or 1)
+    if which == "prior":      # BASELINE configs[3]: DDIM-64 from 768-d instruction embeddings
+        from oracle import prior_oracle as po
+        nb = 16
+        inp, sd = synth.prior_inputs(nb, 64), synth.prior_state()
+        dt = best_of(lambda: po.voxel2style_emb(sd, inp["voxel"], inp["image_embed"], inp["noises"][:63], timesteps_prior=64))
+        val, unit, sample = nb / dt, "samples/s", f"DDIM-64 prior sampling of {nb} instruction embeddings"
+    elif which == "clip":     # SURVEY 8f row 3: CLIP-L text tower + 77-token mean
+        from oracle import clip_oracle as co
+        nb = 16
+        sd, ids = synth.clip_text_state(60, 12), synth.clip_tokens(nb, seed=61)
+        with torch.no_grad():
+            dt = best_of(lambda: co.text_to_voxel(sd, ids))
+        val, unit, sample = nb / dt, "instructions/s", f"CLIP-L text tower + token mean on {nb} instructions (77 tokens each)"
+    else:                     # BASELINE configs[4]: one teacher-forced faceformer_vert step (autograd + Adam) on one 4 s clip
+        from oracle import train_oracle as to
+        fd, T, N = 64, 120, 64000
+        sd_w2v, sd_ff = synth.wav2vec2_state(0), synth.faceformer_state(fd=fd, seed=264, variant="vert")
+        template = synth.flame_buffers()["v_template"].reshape(1, 1, 15069)
+        gt = template + 1e-3 * torch.from_numpy(np.random.default_rng(7).normal(size=(1, T, 15069)).astype(np.float32))
+        audio = synth.audio(1, N, seed=500)
+        dt = best_of(lambda: to.train_step(sd_ff, sd_w2v, template, audio, gt, lr=1e-4))
+        val, unit, sample = 1.0 / dt, "steps/s", "one training step (forward, autograd backward, Adam) on one 4 s / 120-frame clip"
+    print(json.dumps({"impl": "reference", "workload": which, "cpu_baseline": {"value": val, "unit": unit, "cores": torch.get_num_threads(),
+                                                                               "kind": "port", "sample": sample, "seconds": dt}}), flush=True)
 
 
 def run_reference(args):
@@ -351,7 +393,9 @@ def run_ours(args):
 
 def main():
     args = parse()
-    if args.impl == "reference":
+    if args.cpu_baseline:
+        cpu_baseline_other(args.cpu_baseline)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         if not torch.cuda.is_available():

@@ -2,7 +2,6 @@
 batch 256 (BASELINE configs[3] with its text front end). Usage (GPU box): python profiles/clip_bench.py [batch]"""
 import os
 import sys
-import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
@@ -46,11 +45,4 @@ for prec in ("fp32", "bf16"):
     flops = 2.0 * B * 77 * 12 * (768 * 2304 + 768 * 768 + 2 * 768 * 3072) + 4.0 * B * 12 * 12 * 77 * 77 * 64
     print(f"{prec} B={B}: CLIP text tower {ms_clip:.3f} ms ({flops / ms_clip / 1e9:.0f} TFLOP/s), tokens -> style embedding {ms_all:.3f} ms "
           f"({B / ms_all * 1e3:.0f} instructions/s)")
-from oracle import clip_oracle as co  # noqa: E402
-sd = synth.clip_text_state(60, 12)
-torch.set_num_threads(os.cpu_count() or 1)
-t0 = time.perf_counter()
-with torch.no_grad():
-    co.text_to_voxel(sd, ids[:16].cpu())
-dt = time.perf_counter() - t0
-print(f"CPU oracle ({torch.get_num_threads()} threads) CLIP text tower on 16 instructions: {dt * 1e3:.1f} ms -> {16 / dt:.1f} instructions/s")
+print("CPU oracle of the text tower: python bench.py --cpu-baseline clip")

@@ -1,9 +1,8 @@
 """BASELINE configs[3]: diffusion-prior sampling, batch 256, DDIM-64 and DDPM-100, from 768-d instruction embeddings
 (BrainNetwork -> one-launch sampler). Prints samples/s, ms per call and the achieved fraction of 12.8 MFLOP/sample-step; also
-times the CPU oracle on a bounded sample. Usage (GPU box): python profiles/prior_bench.py [batch]"""
+the CPU oracle of the same config is timed by `python bench.py --cpu-baseline prior`. Usage (GPU box): python profiles/prior_bench.py [batch]"""
 import os
 import sys
-import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
@@ -35,12 +34,4 @@ for prec in ("fp32", "bf16"):
             ms = e0.elapsed_time(e1) / 5
             print(f"{prec} B={B} timesteps={timesteps} samples/CTA={spc}: {ms:8.3f} ms/call  {B / ms * 1e3:10.0f} samples/s  "
                   f"{12.8e6 * B * steps / ms / 1e9:7.2f} TFLOP/s (denoiser, algorithmic)")
-# CPU oracle, bounded sample
-from oracle import prior_oracle as po  # noqa: E402
-sd = synth.prior_state()
-nb = 16
-torch.set_num_threads(os.cpu_count() or 1)
-t0 = time.perf_counter()
-po.voxel2style_emb(sd, inp["voxel"][:nb], inp["image_embed"][:nb], inp["noises"][:, :nb], timesteps_prior=64)
-dt = time.perf_counter() - t0
-print(f"CPU oracle ({torch.get_num_threads()} threads) DDIM-64 on {nb} samples: {dt * 1e3:.1f} ms -> {nb / dt:.1f} samples/s")
+print("CPU oracle of the same sampler: python bench.py --cpu-baseline prior")

@@ -6,7 +6,7 @@ with the bucketed NCCL all-reduce of train.GradBuckets. One VOCASET-like clip = 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P profiles/train_bench.py
 
 Prints one JSON line (rank 0): clips/s and frames/s over all ranks (weak scaling: C clips per rank per step), ms per step as the max
-over ranks (CUDA events), the per-phase split measured in a separate pass, and the CPU oracle's step time on one clip."""
+over ranks (CUDA events), the per-phase split measured in a separate pass, (the CPU oracle's step is timed by `python bench.py --cpu-baseline train`)."""
 import argparse
 import json
 import os
@@ -119,15 +119,6 @@ if rank == 0:
             "phases": phases, "loss": float(loss.detach()), "cuda_graph": gstep is not None, "ranks_in_sync": in_sync,
             # Adam alone moves 7 fp32 words per parameter (read p, g, m, v; write p, m, v)
             "adam_hbm_gbs": 28.0 * n_par / (phases["adam_ms"] * 1e-3) / 1e9}
-    if not args.no_cpu and world == 1:
-        from oracle import train_oracle as to
-        torch.set_num_threads(os.cpu_count() or 1)
-        sd_w2v, sd_ff = synth.wav2vec2_state(0), synth.faceformer_state(fd=fd, seed=264, variant="vert")
-        t0 = time.perf_counter()
-        to.train_step(sd_ff, sd_w2v, template, audio[:1].cpu(), gt[:1].cpu(), lr=1e-4)
-        dt = time.perf_counter() - t0
-        line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "steps/s (1 clip)", "cores": torch.get_num_threads(), "kind": "port",
-                                "sample": "one step on one 4 s clip, torch autograd over the CPU oracle"}
     print(json.dumps(line), flush=True)
 if world > 1:
     dist.destroy_process_group()
