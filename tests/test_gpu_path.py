@@ -299,3 +299,44 @@ def test_long_and_ragged_clips_take_the_general_kernels():
         assert ref_s.shape[1] == T_s
         v_s = m.predict_from_embeddings(a_s.cuda(), emo_s.cuda())
         assert (v_s.cpu() - ref_s).abs().max().item() < 1e-5
+
+
+@pytest.mark.gpu
+def test_full_size_configs1_properties():
+    """BASELINE configs[1] at full size (64 clips x 10 s = 15 936 frames, bf16 mode), through size-independent properties:
+    (1) clips are independent: rows of the batched result equal the same clips run alone (first, middle, last);
+    (2) FLAME linearity in the blend: with zero pose the skinning is the identity, so verts(shape, exp) - template is additive in
+        (shape, exp) and the zero-coefficient mesh is the template;
+    (3) every output is finite and the vertex head adds the template exactly once (mean displacement << template scale);
+    (4) one clip checked against the CPU oracle end to end (1e-4 m)."""
+    from avi_talking_b200.smoke import build_models
+    from bench import make_inputs, n_frames
+    m = build_models("bf16")
+    B, n = 64, 160000
+    T = n_frames(n)
+    assert T == 249
+    inp = {k: v.cuda() for k, v in make_inputs(B, n, T, seed=1000).items()}
+    v, fv = m.predict_and_convert(inp["audio"], inp["emo"], inp["coeff"], inp["pose"].clone(), inp["shape"].repeat_interleave(T, 0))
+    assert tuple(v.shape) == (B, T, 15069) and tuple(fv.shape)[0] == B * T
+    assert torch.isfinite(v).all() and torch.isfinite(fv).all()
+    for c in (0, 31, 63):                                                                                   # (1)
+        vc = m.predict_from_embeddings(inp["audio"][c:c + 1], inp["emo"][c:c + 1])
+        assert (v[c] - vc[0]).abs().max().item() < 2e-6, c
+    template = m.template.reshape(-1).to(v.device)
+    disp = v - template
+    assert disp.abs().mean().item() < 0.05 and disp.abs().max().item() < 1.0                                # (3)
+    flame = m.flame
+    F_ = 512                                                                                                 # (2)
+    g = torch.Generator().manual_seed(2)
+    s1, e1 = torch.randn(F_, 100, generator=g).cuda(), torch.randn(F_, 50, generator=g).cuda()
+    s2, e2 = torch.randn(F_, 100, generator=g).cuda(), torch.randn(F_, 50, generator=g).cuda()
+    zp = torch.zeros(F_, 6, device="cuda")
+    tpl = flame.v_template.reshape(1, -1)
+    d = lambda s, e: flame.vertices_only(shape_params=s, expression_params=e, pose_params=zp).reshape(F_, -1) - tpl  # noqa: E731
+    z = torch.zeros_like(s1), torch.zeros_like(e1)
+    assert d(*z).abs().max().item() < 1e-6
+    assert (d(s1 + s2, e1 + e2) - d(s1, e1) - d(s2, e2)).abs().max().item() < 2e-4       # fp16 operand rounding of the blend, 3 terms
+    sd_w2v, sd_ff = synth.wav2vec2_state(0), synth.faceformer_state(fd=64, seed=74)                         # (4)
+    ref = ffo.predict(sd_ff, sd_w2v, synth.flame_buffers()["v_template"].reshape(1, 1, 15069), inp["audio"][5:6].cpu(),
+                      inp["emo"][5:6].cpu(), cached=True)
+    assert (v[5:6].cpu() - ref).abs().max().item() < 1e-4
