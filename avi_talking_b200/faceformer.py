@@ -214,8 +214,9 @@ class Faceformer(nn.Module):
         rows = ops.empty_rows(B * T, vd, hidden.device)      # 16-byte aligned row stride (15072 floats), returned as a [.., 15069] view
         if self.precision == "bf16" and fd % 64 == 0:
             a = ops.split_bf16x3(hidden.reshape(B * T, fd))
+            # HBM-write bound (60 276 B per frame out, 4*fd B in): profiled against the HBM roofline, not the tensor pipe
             ops.gemm(a, P["vr_w16x3"], bias, rows, rows=B * T, N=vd, K=3 * fd, a_rows_alloc=B * T, c_ld=rows.stride(0),
-                     algorithmic_flops=2.0 * B * T * vd * fd)
+                     profile=("vertex_head", float(B * T) * (vd * 4 + fd * 4)))
         else:
             ops.gemm(hidden.reshape(B * T, fd), P["vr_w32"], bias, rows, rows=B * T, N=vd, K=fd, c_ld=rows.stride(0))
         return rows.view(B, T, vd)

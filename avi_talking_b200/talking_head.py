@@ -149,7 +149,8 @@ def emote_cfg(n_identities=32, n_expression=8, n_intensities=3):
                             gt_expression_label=True, gt_expression_intensity=True, gt_expression_identity=True, use_bias=True)
     dec = SimpleNamespace(type="BertPriorDecoder", feature_dim=128, nhead=8, num_layers=1, activation="gelu", post_bug_fix=True,
                           squash_after=True, squash_type="stack_linear", style_op="add", style_embedding=style)
-    return SimpleNamespace(model=SimpleNamespace(sequence_decoder=dec), data=SimpleNamespace())
+    data = SimpleNamespace(data_class="MEADPseudo3DDM", split="random_by_identityV2_sorted_70_15_15", reconstruction_type=["EMICA-MEAD_flame2020"])
+    return SimpleNamespace(model=SimpleNamespace(sequence_decoder=dec), data=data)
 
 
 # ------------------------------------------------------------------------------------------------ the model
@@ -367,6 +368,31 @@ class TalkingHeadWrapper(nn.Module):
 
     def get_num_identities(self):
         return self.cfg.model.sequence_decoder.style_embedding.n_identities
+
+    MEAD_IDENTITIES = ("M003 M005 M007 M009 M011 M012 M013 M019 M022 M023 M024 M025 M026 M027 M028 M029 M030 M031 M032 M033 M034 M035 "
+                       "M037 M039 M040 M041 M042 W009 W011 W014 W015 W016 W017 W018 W019 W021 W023 W024 W025 W026 W028 W029 W033 W035 "
+                       "W036 W037 W038 W040")
+
+    def get_subject_labels(self, train_val_test):
+        """TalkingHeadWrapper.py:168-236: the MEAD identity split named by cfg.data.split (male and female lists are cut separately;
+        upstream's `random` shuffle is applied to a list that is not used afterwards, so both variants give the sorted split)."""
+        assert self.cfg.data.data_class == "MEADPseudo3DDM"
+        assert "random_by_identityV2" in self.cfg.data.split
+        res = self.cfg.data.split.split("_")
+        assert res[3] in ("random", "sorted"), f"Unknown random_or_sorted value: '{res[3]}'"
+        train, val, test = float(res[-3]), float(res[-2]), float(res[-1])
+        train_, val_ = train / (train + val + test), val / (train + val + test)
+        ids = sorted(TalkingHeadWrapper.MEAD_IDENTITIES.split())
+        male, female = [i for i in ids if i.startswith("M")], [i for i in ids if i.startswith("W")]
+        out = {"training": [], "validation": [], "testing": []}
+        for grp in (male, female):
+            a, b = int(len(grp) * train_), int(len(grp) * (train_ + val_))
+            out["training"] += grp[:a]
+            out["validation"] += grp[a:b]
+            out["testing"] += grp[b:]
+        if train_val_test not in out:
+            raise RuntimeError(f"Unknown set_type: '{train_val_test}'")
+        return out[train_val_test]
 
     def forward(self, sample, style_emb=None, only_style_emb=False, is_external_style_emb=False):
         return self.talking_head_model(sample, style_emb=style_emb, only_style_emb=only_style_emb,

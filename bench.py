@@ -357,11 +357,13 @@ def run_ours(args):
     roofline = {"kernel": gname, "bound": "tensor", "achieved": achieved, "peak": pk["tc"], "unit": "TFLOP/s",
                 "frac": achieved / pk["tc"], "traffic": ncu_traffic("gemm_bf16_tc2_kernel"), "traffic_unit": "DRAM bytes per launch (ncu)", "peak_source": pk["src"] + " (sustained bf16)",
                 "launches_per_step": g[0], "avg_launch_ms": g[1] / g[0], "share_of_step": g[1] / step_ms_prof}
-    fl = agg.get("flame_lbs")
     extra = {}
-    if fl:
-        gbs = fl[2] / (fl[1] / 1e3) / 1e9
-        extra["flame_lbs"] = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"]}
+    for name in ("vertex_head", "flame_lbs", "conv0_gn_gelu", "layernorm"):     # HBM-bound kernels: algorithmic bytes / launch time
+        k = agg.get(name)
+        if k and k[2] > 0:
+            gbs = k[2] / (k[1] / 1e3) / 1e9
+            extra[name] = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
+                           "ms": k[1], "launches": k[0]}
     kernels = {k: {"launches": v[0], "ms": round(v[1], 4)} for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])}
 
     h2d = sum(v.numel() * v.element_size() for v in host.values())

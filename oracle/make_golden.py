@@ -572,6 +572,24 @@ def golden_clip_text():
     print("clip_text.npz", {k: v.shape for k, v in out.items()})
 
 
+def golden_subject_labels():
+    """The reference's own TalkingHeadWrapper.get_subject_labels (TalkingHeadWrapper.py:168-236), compiled from source."""
+    import ast
+    import json
+    import random
+    path = os.path.join(REF, "third_party", "inferno", "inferno_apps", "TalkingHead", "evaluation", "TalkingHeadWrapper.py")
+    cls = [n for n in ast.parse(open(path).read()).body if isinstance(n, ast.ClassDef) and n.name == "TalkingHeadWrapper"][0]
+    fn = [n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name == "get_subject_labels"][0]
+    g = {"rand": random}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), path, "exec"), g)
+    res = {}
+    for split in ("random_by_identityV2_sorted_70_15_15", "random_by_identityV2_random_70_15_15", "random_by_identityV2_sorted_85_15_0"):
+        me = types.SimpleNamespace(cfg=types.SimpleNamespace(data=types.SimpleNamespace(data_class="MEADPseudo3DDM", split=split)))
+        for which in ("training", "validation", "testing"):
+            res[f"{split}/{which}"] = g["get_subject_labels"](me, which)
+    json.dump(res, open(os.path.join(GOLD, "subject_labels.json"), "w"), indent=0)
+
+
 def main():
     _paths()
     os.makedirs(GOLD, exist_ok=True)
@@ -584,6 +602,7 @@ def main():
     golden_train()
     golden_frontend()
     golden_clip_text()
+    golden_subject_labels()
 
 
 if __name__ == "__main__":

@@ -199,3 +199,18 @@ def test_clip_text_oracle_matches_transformers(golden):
             last = co.clip_text_forward(sd, ids, layers)
         np.testing.assert_allclose(last[:, ::4, ::3].numpy(), g[f"{tag}_last_sub"], atol=2e-5, rtol=0)
         np.testing.assert_allclose(last.mean(dim=1).numpy(), g[f"{tag}_voxel"], atol=1e-5, rtol=0)
+
+
+def test_get_subject_labels_matches_reference():
+    """TalkingHeadWrapper.get_subject_labels (host logic) against lists minted from the reference's own method compiled from source
+    (tests/golden/subject_labels.json, oracle/make_golden.golden_subject_labels; TalkingHeadWrapper.py:168-236)."""
+    import json
+    import os
+    import types
+    from avi_talking_b200.talking_head import TalkingHeadWrapper, emote_cfg
+    ref = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "subject_labels.json")))
+    for key, want in ref.items():
+        split, which = key.split("/")
+        cfg = emote_cfg()
+        cfg.data.split = split
+        assert TalkingHeadWrapper.get_subject_labels(types.SimpleNamespace(cfg=cfg), which) == want
