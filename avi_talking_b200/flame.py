@@ -65,10 +65,19 @@ def _run(cache, precision, betas, full_pose, shapedirs, posedirs, v_template, J_
 _lbs_cache = _PackCache()
 
 
+def _refuse_grad(*tensors):
+    """The kernels are forward-only: a caller that differentiates through FLAME (MotionPrior.postprocess(with_grad=True),
+    MotionPrior.py:345 - EMOTE training, not one of the BASELINE configs) must not silently get a detached mesh."""
+    if torch.is_grad_enabled() and any(t is not None and torch.is_tensor(t) and t.requires_grad for t in tensors):
+        raise NotImplementedError("avi_talking_b200 FLAME / lbs are forward-only (no backward kernel): detach the inputs or wrap the "
+                                  "call in torch.no_grad()")
+
+
 def lbs(betas, pose, v_template, shapedirs, posedirs, J_regressor, parents, lbs_weights, pose2rot=True,
         dtype=torch.float32, detach_pose_correctives=False, _cache=None):
     """lbs.py:142-234. v_template may be [V,3] or the reference's expanded [B,V,3] (row 0 is used: the reference expands one
     template over the batch, DecaFLAME.py:243). Returns (verts [B,V,3], J_transformed [B,5,3])."""
+    _refuse_grad(betas, pose, v_template)
     if not pose2rot:
         raise NotImplementedError("pose2rot=False (rotation-matrix input) is not used on the AVI-Talking path")
     if J_regressor.shape[0] != 5 or [int(p) for p in parents] != [-1, 0, 1, 1, 1]:
@@ -142,6 +151,7 @@ class FLAME(nn.Module):
         return torch.cat([pose_params[:, :3], self.neck_pose.expand(batch_size, -1), pose_params[:, 3:], eye_pose_params], dim=1)
 
     def _run_lbs(self, shape_params, expression_params, pose_params, eye_pose_params, want_rows=True, padded=False):
+        _refuse_grad(shape_params, expression_params, pose_params, eye_pose_params)
         B = shape_params.shape[0]
         if expression_params is None:
             expression_params = torch.zeros(B, self.cfg.n_exp, device=shape_params.device)

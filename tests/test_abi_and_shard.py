@@ -157,3 +157,13 @@ def test_unsupported_configurations_raise():
     m = _tiny_vert_model()
     with pytest.raises(NotImplementedError):
         m(torch.zeros(1, 16000), torch.zeros(1, 4, 53), torch.zeros(1, 4, 6), torch.zeros(1, 4, 100), teacher_forcing=False)
+
+
+def test_flame_refuses_to_drop_gradients():
+    from avi_talking_b200.flame import _refuse_grad
+    x = torch.zeros(2, 3, requires_grad=True)
+    with pytest.raises(NotImplementedError, match="forward-only"):
+        _refuse_grad(None, x)
+    with torch.no_grad():
+        _refuse_grad(x)                      # fine: the caller does not expect a gradient
+    _refuse_grad(torch.zeros(2, 3), None)
