@@ -35,7 +35,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   uint64_t* bar_s = bars + 1;      // S complete
   uint64_t* bar_p = bars + 2;      // P written by all 128 softmax threads
   uint64_t* bar_o = bars + 3;      // O complete
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4);
+  uint64_t* bar_v = bars + 4;      // V landed (not needed before the second MMA: kept off the critical path to S and the softmax)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 5);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * AT_BM, h = blockIdx.y, b = blockIdx.z;
@@ -47,6 +48,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       mbar_init(smem_u32(bar_s), 1);
       mbar_init(smem_u32(bar_p), 256);
       mbar_init(smem_u32(bar_o), 1);
+      mbar_init(smem_u32(bar_v), 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -60,11 +62,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 
   if (warp == AT_CTRL_WARP) {
     if (lane == 0) {
-      const uint32_t lb = smem_u32(bar_load);
-      mbar_expect_tx(lb, AT_Q_BYTES + 2 * AT_K_BYTES);
+      const uint32_t lb = smem_u32(bar_load), vb = smem_u32(bar_v);
+      mbar_expect_tx(lb, AT_Q_BYTES + AT_K_BYTES);
       tma_load_2d(smem_u32(sQ), &map_q, lb, h * AT_D, b * T + q0);
       tma_load_2d(smem_u32(sK), &map_kv, lb, E + h * AT_D, b * T);
-      tma_load_2d(smem_u32(sV), &map_kv, lb, 2 * E + h * AT_D, b * T);
+      mbar_expect_tx(vb, AT_K_BYTES);
+      tma_load_2d(smem_u32(sV), &map_kv, vb, 2 * E + h * AT_D, b * T);
       mbar_wait(lb, 0);
       tc_fence_after();
       // S = Q K^T : D=f32, A=B=bf16 K-major, M=128, N=256
@@ -75,6 +78,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       umma_commit(smem_u32(bar_s));
       // O = P V : A = P (K-major over keys, 4 chunks of 64 keys), B = V (MN-major: d contiguous), M=128, N=64
       mbar_wait(smem_u32(bar_p), 0);
+      mbar_wait(smem_u32(bar_v), 0);
       tc_fence_after();
       const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(AT_D >> 3) << 17) | ((uint32_t)(AT_BM >> 4) << 24);
       const uint64_t vd = umma_desc_sw128_mn(smem_u32(sV));
