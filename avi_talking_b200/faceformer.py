@@ -341,12 +341,24 @@ class Faceformer(nn.Module):
         # learnable_eye_embed and the emotion embedding only), so they are not computed here.
         emo_embed = None
         if self.variant == "disentangle":
-            emotion_img = loopback_frames(emotion_img, frame_num)                              # :779-781
-            emo = []
-            for i in range(len(emotion_img)):                                                  # :791-797
-                _, _, emo_i, _ = self.fan_net(emotion_img[i:i + 1])
-                emo.append(emo_i)
-            emo_embed = torch.concat(emo, dim=0).unsqueeze(0)
+            n_src = emotion_img.shape[0]
+            if getattr(self.fan_net, "training", False):
+                # a train-mode provider (BatchNorm batch statistics) is called exactly as upstream: frame by frame (:779-797)
+                looped = loopback_frames(emotion_img, frame_num)
+                emo = []
+                for i in range(len(looped)):
+                    _, _, emo_i, _ = self.fan_net(looped[i:i + 1])
+                    emo.append(emo_i)
+                emo_embed = torch.concat(emo, dim=0).unsqueeze(0)
+            else:
+                # the looped clip (loopback_frames) only ever shows its n_src source frames, and in eval mode the
+                # encoder is a per-image function - ONE batched call over the source frames, then the ping-pong gather on the
+                # 30-d embeddings instead of frame_num single-image calls on 224x224 images
+                from .loop_utils import calc_loop_idx
+                n_used = min(n_src, frame_num)
+                _, _, emo_src, _ = self.fan_net(emotion_img[:n_used])
+                idx = torch.tensor([calc_loop_idx(i, n_src) for i in range(frame_num)], dtype=torch.long, device=emo_src.device)
+                emo_embed = emo_src.index_select(0, idx).unsqueeze(0)
         return self.predict_from_embeddings(audio, emo_embed)
 
     def forward(self, audio, coeff, pose, shape, cam=None, motion_des=None, img=None, ref_img=None, criterion=None, file_name=None,

@@ -203,18 +203,35 @@ def test_predict_api_with_fan_stub(golden):
     emb = synth.fan_embeddings(24, seed=20)
 
     class Fan(torch.nn.Module):
+        """A per-image function (what FanEncoder is in eval mode): the frame index travels in pixel [0,0,0]."""
+        calls = 0
+
         def forward(self, img):
-            i = int(round(float(img.reshape(img.shape[0], -1)[0, 0])))
-            return emb["head"][i:i + 1].cuda(), emb["eye"][i:i + 1].cuda(), emb["emo"][i:i + 1].cuda(), None
+            Fan.calls += 1
+            i = img.reshape(img.shape[0], -1)[:, 0].round().long().cpu()
+            return emb["head"][i].cuda(), emb["eye"][i].cuda(), emb["emo"][i].cuda(), None
 
     m = build_faceformer("fp32", fd=64, seed=74)
-    m.fan_net = Fan()
+    m.fan_net = Fan().eval()
     frames = torch.zeros(24, 3, 4, 4, device="cuda")
     frames[:, 0, 0, 0] = torch.arange(24).float()
     a = synth.audio(1, 16000, seed=1234).cuda()
     v = m.predict(a, frames, frames, frames)
     v2 = m.predict_from_embeddings(a, emb["emo"][None].cuda())
-    assert torch.equal(v, v2)
+    assert torch.equal(v, v2) and Fan.calls == 1                     # ONE batched encoder call (SURVEY 8f row 1)
+    # a 5-frame emotion clip played ping-pong over the 24 output frames (loop_utils.loopback_frames, golden index pattern):
+    # batched-unique path (eval) == upstream's frame-by-frame path (taken for a train-mode provider)
+    idx = torch.from_numpy(g["loop_idx_5_17"]).long()
+    from avi_talking_b200.loop_utils import calc_loop_idx
+    assert [calc_loop_idx(i, 5) for i in range(17)] == idx.tolist()
+    Fan.calls = 0
+    v_eval = m.predict(a, frames[:5], frames[:5], frames[:5])
+    assert Fan.calls == 1
+    m.fan_net.train()
+    v_train = m.predict(a, frames[:5], frames[:5], frames[:5])
+    assert Fan.calls == 1 + 24 and torch.equal(v_eval, v_train)
+    want = emb["emo"][torch.tensor([calc_loop_idx(i, 5) for i in range(24)])][None].cuda()
+    assert torch.equal(v_eval, m.predict_from_embeddings(a, want))
 
 
 def test_batched_predict_equals_per_clip():
