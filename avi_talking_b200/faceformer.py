@@ -20,7 +20,7 @@ import torch.nn as nn
 
 from . import ops
 from .loop_utils import loopback_frames
-from .ops import ACT_NONE, ACT_RELU, AviDecoderWeights
+from .ops import ACT_RELU, AviDecoderWeights
 from .wav2vec import Wav2Vec2Model, default_precision
 
 N_HEAD = 4
@@ -375,7 +375,6 @@ class Faceformer(nn.Module):
             raise NotImplementedError("scheduled-sampling training (teacher_forcing=False) is not built")
         if criterion is not None and not isinstance(criterion, nn.MSELoss):
             raise NotImplementedError("criterion must be nn.MSELoss (the loss/gradient kernel is the mean squared error)")
-        from . import train
         B, T = coeff.shape[0], coeff.shape[1]
         with torch.no_grad():
             gt_coeffs = coeff[:, :, :53].reshape(-1, 53)                                       # :405-410
