@@ -659,3 +659,43 @@ def token_mean(x2d, B, T):
     out = torch.empty((B, Cc), dtype=torch.float32, device=x2d.device)
     _chk(_lib.load().avi_token_mean(_ptr(x2d.contiguous()), _ptr(out), C.c_int32(B), C.c_int32(T), C.c_int32(Cc), _stream()), "avi_token_mean")
     return out
+
+
+# ------------------------------------------------------------------------------------------------ FanEncoder image branch pieces
+def im2col_affine(x, N, H, W, Cc, k, stride, pad, Kpad, dtype, pre=None):
+    """x fp32 rows [N*H*W, C] (row stride allowed) -> cols [N*Ho*Wo, Kpad] of `dtype`; pre = (scale, shift) applies relu(x*scale+shift)."""
+    _need_cuda(x)
+    assert x.dtype == torch.float32 and x.stride(1) == 1
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    cols = torch.empty((N * Ho * Wo, Kpad), dtype=dtype, device=x.device)
+    sc, sh = pre if pre is not None else (None, None)
+    with _timed("im2col", float(cols.numel() * cols.element_size())):
+        _chk(_lib.load().avi_im2col_affine(_ptr(x), C.c_int64(x.stride(0)), _ptr(cols), C.c_int32(_dt(cols)), C.c_int32(N), C.c_int32(H),
+                                           C.c_int32(W), C.c_int32(Cc), C.c_int32(k), C.c_int32(stride), C.c_int32(pad), C.c_int32(Kpad),
+                                           _ptr(sc), _ptr(sh), _stream()), "avi_im2col_affine")
+    return cols
+
+
+def maxpool2x2(x, N, H, W, Cc):
+    _need_cuda(x)
+    y = torch.empty((N * (H // 2) * (W // 2), Cc), dtype=torch.float32, device=x.device)
+    _chk(_lib.load().avi_maxpool2x2(_ptr(x.contiguous()), _ptr(y), C.c_int32(N), C.c_int32(H), C.c_int32(W), C.c_int32(Cc), _stream()),
+         "avi_maxpool2x2")
+    return y
+
+
+def upsample_bilinear_add(low, up1, N, Hi, Wi, Ho, Wo, Cc):
+    _need_cuda(low, up1)
+    out = torch.empty_like(up1)
+    _chk(_lib.load().avi_upsample_bilinear_add(_ptr(low.contiguous()), _ptr(up1.contiguous()), _ptr(out), C.c_int32(N), C.c_int32(Hi),
+                                               C.c_int32(Wi), C.c_int32(Ho), C.c_int32(Wo), C.c_int32(Cc), _stream()),
+         "avi_upsample_bilinear_add")
+    return out
+
+
+def affine_act(x, scale, shift, relu):
+    _need_cuda(x, scale, shift)
+    assert x.is_contiguous() and x.dtype == torch.float32
+    _chk(_lib.load().avi_affine_act(_ptr(x), _ptr(scale), _ptr(shift), C.c_int64(x.numel() // x.shape[-1]), C.c_int32(x.shape[-1]),
+                                    C.c_int32(1 if relu else 0), _stream()), "avi_affine_act")
+    return x

@@ -432,3 +432,35 @@ def clip_tokens(batch: int, seed: int = 61, vocab: int = CLIP_TEXT.vocab) -> tor
         n = int(rng.integers(3, 40))
         ids[b, 1:1 + n] = rng.integers(0, vocab - 2, size=n)
     return torch.from_numpy(ids)
+
+
+# --------------------------------------------------------------------------- FanEncoder image branch
+def fan_state(seed: int = 80) -> dict:
+    """Seeded state dict for FanEncoder (keys of the reference module tree): Kaiming-normal convolutions / Linears (gain chosen so that
+    activations stay O(1) through 60 layers), non-trivial BatchNorm affine parameters AND running statistics (eval mode uses them)."""
+    import torch.nn as nn
+    from .fan_encoder import FanEncoder
+    rng = np.random.default_rng(seed)
+    sd = {}
+    for mod_name, mod in FanEncoder().named_modules():
+        pre = mod_name + "." if mod_name else ""
+        if isinstance(mod, (nn.BatchNorm1d, nn.BatchNorm2d)):
+            c = mod.num_features
+            sd[pre + "weight"] = _t(1.0 + 0.1 * rng.normal(size=c))
+            sd[pre + "bias"] = _t(0.05 * rng.normal(size=c))
+            sd[pre + "running_mean"] = _t(0.1 * rng.normal(size=c))
+            sd[pre + "running_var"] = _t(1.0 + 0.2 * rng.uniform(-1, 1, size=c))
+            sd[pre + "num_batches_tracked"] = torch.tensor(100, dtype=torch.long)
+        elif isinstance(mod, (nn.Conv2d, nn.Linear)):
+            shape = tuple(mod.weight.shape)
+            sd[pre + "weight"] = _t(rng.normal(0, math.sqrt(1.6 / int(np.prod(shape[1:]))), size=shape))
+            if mod.bias is not None:
+                sd[pre + "bias"] = _t(0.02 * rng.normal(size=shape[0]))
+    return sd
+
+
+def fan_images(n: int, seed: int = 81, size: int = 224) -> torch.Tensor:
+    """[n,3,size,size] in [-1,1]-ish: smooth random fields (low-pass noise) so that neighbouring pixels correlate like an image."""
+    rng = np.random.default_rng(seed)
+    x = rng.normal(size=(n, 3, size // 8, size // 8)).astype(np.float32)
+    return torch.nn.functional.interpolate(torch.from_numpy(x), size=(size, size), mode="bilinear", align_corners=False).contiguous()

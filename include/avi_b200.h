@@ -276,6 +276,20 @@ int avi_embed_tokens(const int64_t* ids, const float* tok_emb, const float* pos_
 /* out[b, :] = mean_t x[b*T + t, :]   (the 77-token mean pooling of train_diffusion_prior.py:439,711) */
 int avi_token_mean(const float* x, float* out, int32_t B, int32_t T, int32_t C, void* stream);
 
+/* ------------------------------------------------------------------ FanEncoder image branch (SURVEY 8f row 1;
+ * third_party/pd_fgc_inference/lib/models/networks/FAN_feature_extractor.py:13-163, encoder.py:89-126). NHWC fp32 rows [N*H*W, C].
+ * cols[(n,oy,ox), (ky,kx,c)] = act(x[n, oy*stride-pad+ky, ox*stride-pad+kx, c]) (zero outside the image), act = relu(x*scale+shift)
+ * when scale != NULL (ConvBlock's pre-activation BatchNorm + ReLU, :38-48); rows of x are x_ld floats apart; Kpad >= k*k*C */
+int avi_im2col_affine(const float* x, int64_t x_ld, void* cols, int32_t cols_dtype, int32_t N, int32_t H, int32_t W, int32_t C, int32_t k,
+                      int32_t stride, int32_t pad, int32_t Kpad, const float* scale, const float* shift, void* stream);
+/* F.max_pool2d(x, 2, stride=2) (:86, :142) */
+int avi_maxpool2x2(const float* x, float* y, int32_t N, int32_t H, int32_t W, int32_t C, void* stream);
+/* out = up1 + bilinear upsample of low to (Ho, Wo), align_corners=False (HourGlass._forward :97-101) */
+int avi_upsample_bilinear_add(const float* low, const float* up1, float* out, int32_t N, int32_t Hi, int32_t Wi, int32_t Ho, int32_t Wo,
+                              int32_t C, void* stream);
+/* in place x = act(x * scale[c] + shift[c]) (eval BatchNorm after a GEMM; scale == shift == NULL: activation only) */
+int avi_affine_act(float* x, const float* scale, const float* shift, int64_t rows, int32_t C, int32_t relu, void* stream);
+
 /* ------------------------------------------------------------------ training step (BASELINE configs[4]) ------------------------------------------------------------------
  * Backward / optimizer pieces of the teacher-forced faceformer_vert step (models/faceformer_vert.py:360-482; feature extractor
  * frozen :154). Dense backward contractions use avi_gemm_bf16_tc on operands laid out by avi_transpose_cast_bf16. */

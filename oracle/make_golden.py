@@ -590,6 +590,37 @@ def golden_subject_labels():
     json.dump(res, open(os.path.join(GOLD, "subject_labels.json"), "w"), indent=0)
 
 
+def _import_reference_fan():
+    """third_party/pd_fgc_inference ... encoder.FanEncoder; its constructor only reads pose_dim / eye_dim from a YAML through omegaconf
+    (absent here): a two-field stand-in for omegaconf.OmegaConf.load is registered before the import."""
+    _paths()
+    om = types.ModuleType("omegaconf")
+    net_motion = types.SimpleNamespace(pose_dim=6, eye_dim=6, motion_dim=18)
+    om.OmegaConf = types.SimpleNamespace(load=lambda path: types.SimpleNamespace(model=types.SimpleNamespace(net_motion=net_motion)))
+    saved = sys.modules.get("omegaconf")
+    sys.modules["omegaconf"] = om
+    try:
+        import third_party.pd_fgc_inference.lib.models.networks.encoder as enc
+    finally:
+        if saved is not None:
+            sys.modules["omegaconf"] = saved
+    return enc
+
+
+def golden_fan():
+    from . import synth
+    enc = _import_reference_fan()
+    m = enc.FanEncoder().eval()
+    missing, unexpected = m.load_state_dict(synth.fan_state(80), strict=True)
+    x = synth.fan_images(3, seed=81)
+    with torch.no_grad():
+        head, eye, emo, mouth = m(x)
+        feat = m.forward_feature(x)
+    out = dict(head=head.numpy(), eye=eye.numpy(), emo=emo.numpy(), mouth=mouth.numpy(), feat=feat.numpy())
+    np.savez_compressed(os.path.join(GOLD, "fan.npz"), **out)
+    print("fan.npz", {k: (v.shape, float(np.abs(v).max())) for k, v in out.items()})
+
+
 def main():
     _paths()
     os.makedirs(GOLD, exist_ok=True)
@@ -603,6 +634,7 @@ def main():
     golden_frontend()
     golden_clip_text()
     golden_subject_labels()
+    golden_fan()
 
 
 if __name__ == "__main__":

@@ -1,0 +1,54 @@
+"""GPU parity of the FanEncoder image-branch drop-in against the reference's own FanEncoder outputs
+(tests/golden/fan.npz) and the CPU oracle. fp32 mode: relative error <= 1e-4 (60 conv layers, outputs O(50)); bf16 GEMM mode: <= 2e-2."""
+import numpy as np
+import pytest
+import torch
+
+from avi_talking_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def build(precision):
+    from avi_talking_b200.fan_encoder import FanEncoder
+    m = FanEncoder()
+    m.load_state_dict(synth.fan_state(80), strict=True)
+    m.precision = precision
+    return m.cuda().eval()
+
+
+def rel(a, b):
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-12))
+
+
+def test_fan_encoder_matches_reference_golden(golden):
+    g = golden("fan")
+    x = synth.fan_images(3, seed=81).cuda()
+    for prec, tol in (("fp32", 1e-4), ("bf16", 2e-2)):
+        m = build(prec)
+        head, eye, emo, mouth = m(x)
+        errs = {k: rel(t.cpu().numpy(), g[k]) for k, t in zip(("head", "eye", "emo", "mouth"), (head, eye, emo, mouth))}
+        errs["feat"] = rel(m.forward_feature(x).cpu().numpy(), g["feat"])
+        print(f"FanEncoder {prec}: relative L2 errors {errs}")
+        assert max(errs.values()) <= tol, errs
+        assert tuple(emo.shape) == (3, 30) and tuple(mouth.shape) == (3, 512)
+
+
+def test_fan_encoder_chunking_and_predict_integration():
+    """More images than one chunk (max_images_per_call) give the same rows; as `fan_net` of Faceformer.predict the drop-in is called
+    once on the source frames of the looped emotion clip."""
+    from helpers import build_faceformer
+    m = build("bf16")
+    x = synth.fan_images(5, seed=82).cuda()
+    full = m(x)[2]
+    m.max_images_per_call = 2
+    chunked = m(x)[2]
+    assert torch.equal(full, chunked)
+    ff = build_faceformer("bf16", fd=64, seed=74)
+    ff.fan_net = m
+    a = synth.audio(1, 16000, seed=1234).cuda()
+    v = ff.predict(a, x, x, x)                                  # 5 source frames played ping-pong over T = 24
+    from avi_talking_b200.loop_utils import calc_loop_idx
+    idx = torch.tensor([calc_loop_idx(i, 5) for i in range(24)], device="cuda")
+    v2 = ff.predict_from_embeddings(a, full.index_select(0, idx)[None])
+    assert torch.equal(v, v2)

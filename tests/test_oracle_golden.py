@@ -214,3 +214,12 @@ def test_get_subject_labels_matches_reference():
         cfg = emote_cfg()
         cfg.data.split = split
         assert TalkingHeadWrapper.get_subject_labels(types.SimpleNamespace(cfg=cfg), which) == want
+
+
+def test_fan_encoder_oracle_matches_reference(golden):
+    """oracle/fan_oracle.py against the reference's own FanEncoder (tests/golden/fan.npz, oracle/make_golden.golden_fan)."""
+    from oracle import fan_oracle as fo2
+    g = golden("fan")
+    out = fo2.fan_encoder_forward(synth.fan_state(80), synth.fan_images(3, seed=81))
+    for k, t in zip(("head", "eye", "emo", "mouth"), out):
+        np.testing.assert_allclose(t.numpy(), g[k], atol=2e-4, rtol=1e-5)
