@@ -24,6 +24,8 @@ Pinning status (see DESIGN.md "Oracle"):
     (deterministic mode: dropout / SpecAugment / LayerDrop inactive).
   * CLIP text tower (clip_oracle.py): PINNED on transformers.CLIPTextModel, the class
     models/diffusion_prior.py:37 instantiates -> tests/golden/clip_text.npz.
+  * FanEncoder image branch (fan_oracle.py): PINNED - equals the reference's own
+    FanEncoder class (omegaconf YAML read stubbed) bit for bit -> tests/golden/fan.npz.
   * Audio front end (avi_talking_b200/frontend.py is host logic, checked directly):
     PINNED on the reference's own process_audio / create_base_sample compiled from
     source -> tests/golden/frontend.npz.
