@@ -39,3 +39,31 @@ def gather_clip_counts(n_local: int, device="cpu") -> list[int]:
     t[dist.get_rank()] = n_local
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return t.tolist()
+
+
+def bind_to_gpu_numa(local_rank: int) -> dict:
+    """Pin the calling process to the CPUs (and thereby, under Linux first-touch, the host memory) closest to GPU `local_rank`.
+
+    One process per GPU on a two-socket host otherwise allocates every rank's pinned staging buffers wherever the launcher happened to
+    run: measured on an 8 x B200 box, the end-to-end (host-buffer) throughput then stops scaling beyond 2 GPUs - per-GPU D2H drops from
+    50 GB/s to 11 GB/s - while the device-resident number scales 8.06x. NVML knows the ideal CPU set of each GPU
+    (nvmlDeviceSetCpuAffinity); binding before the first pinned allocation keeps each rank's PCIe traffic on its own socket.
+    Best effort: returns {"bound": False, "why": ...} when NVML or the affinity call is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            index = local_rank
+            if visible:
+                ids = [v.strip() for v in visible.split(",") if v.strip()]
+                if local_rank < len(ids) and ids[local_rank].isdigit():
+                    index = int(ids[local_rank])
+            handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            pynvml.nvmlDeviceSetCpuAffinity(handle)
+            cpus = sorted(os.sched_getaffinity(0))
+            return {"bound": True, "cpus": f"{cpus[0]}-{cpus[-1]} ({len(cpus)})" if cpus else ""}
+        finally:
+            pynvml.nvmlShutdown()
+    except Exception as e:  # noqa: BLE001 - NVML missing / container without the capability: run unbound
+        return {"bound": False, "why": f"{type(e).__name__}: {e}"[:120]}

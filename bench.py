@@ -233,6 +233,7 @@ def run_ours(args):
 
     from avi_talking_b200 import shard
     rank, local, world = shard.env_rank_world()
+    numa = shard.bind_to_gpu_numa(local)     # before any pinned allocation: host staging buffers on the GPU's own socket
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -377,6 +378,7 @@ def run_ours(args):
         "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": launches,
+        "host_affinity": numa,
         "clocks": sampler.summary(),
         "roofline": roofline,
         "roofline_other": extra,
