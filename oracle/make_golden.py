@@ -599,11 +599,18 @@ def _import_reference_fan():
     om.OmegaConf = types.SimpleNamespace(load=lambda path: types.SimpleNamespace(model=types.SimpleNamespace(net_motion=net_motion)))
     saved = sys.modules.get("omegaconf")
     sys.modules["omegaconf"] = om
+    # _import_faceformer() registers MagicMock stand-ins for `third_party` / `third_party.pirender...`: lift them while the REAL
+    # third_party.pd_fgc_inference package is imported, then put them back
+    mocks = {k: v for k, v in sys.modules.items() if (k == "third_party" or k.startswith("third_party.")) and isinstance(v, MagicMock)}
+    for k in mocks:
+        del sys.modules[k]
     try:
         import third_party.pd_fgc_inference.lib.models.networks.encoder as enc
     finally:
         if saved is not None:
             sys.modules["omegaconf"] = saved
+        for k, v in mocks.items():
+            sys.modules.setdefault(k, v)
     return enc
 
 
