@@ -223,6 +223,29 @@ __device__ __forceinline__ void ln64(const float* a, const float* r, const float
   __syncthreads();
 }
 
+// y = LN2( LN1(a + r) + c ): the two post-LN residual steps around the (degenerate) cross-attention in one warp-level phase, the
+// cross row c coming straight from global memory (its loads are issued before the first reduction)
+__device__ __forceinline__ void ln64x2(const float* a, const float* r, const float* __restrict__ c, const float* __restrict__ w1,
+                                       const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2, float* y) {
+  if (threadIdx.x < 32) {
+    const int l = threadIdx.x;
+    const float c0 = c[l], c1 = c[l + 32];
+    float v0 = a[l] + r[l], v1 = a[l + 32] + r[l + 32];
+    float mean = warp_sum(v0 + v1) * (1.f / 64.f);
+    float d0 = v0 - mean, d1 = v1 - mean;
+    float rstd = rsqrtf(warp_sum(d0 * d0 + d1 * d1) * (1.f / 64.f) + 1e-5f);
+    v0 = d0 * rstd * w1[l] + b1[l] + c0;
+    v1 = d1 * rstd * w1[l + 32] + b1[l + 32] + c1;
+    mean = warp_sum(v0 + v1) * (1.f / 64.f);
+    d0 = v0 - mean;
+    d1 = v1 - mean;
+    rstd = rsqrtf(warp_sum(d0 * d0 + d1 * d1) * (1.f / 64.f) + 1e-5f);
+    y[l] = d0 * rstd * w2[l] + b2[l];
+    y[l + 32] = d1 * rstd * w2[l + 32] + b2[l + 32];
+  }
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(A64_THREADS, 1)
 ff_decoder_ar64_kernel(const AviDecoderWeights w, const float* __restrict__ cross, const float* __restrict__ style,
                        float* __restrict__ hidden_out, int T, int period) {
@@ -263,7 +286,7 @@ ff_decoder_ar64_kernel(const AviDecoderWeights w, const float* __restrict__ cros
 
   if (tid < 64) {
     sty[tid] = style[(int64_t)b * 64 + tid];
-    emb[tid] = sty[tid];
+    xs[tid] = sty[tid] + w.pe[tid];                     // x_0 = style + pe[0]
   }
   __syncthreads();
   const int h = tid >> 7, jl = tid & 127;         // scores: 4 heads x 128 key lanes
@@ -271,9 +294,7 @@ ff_decoder_ar64_kernel(const AviDecoderWeights w, const float* __restrict__ cros
   const int pg = tid >> 6, pc = tid & 63;         // PV: 8 key groups x 64 channels
 
   for (int i = 0; i < T; ++i) {
-    if (tid < 64) xs[tid] = emb[tid] + w.pe[(i % period) * 64 + tid];
-    __syncthreads();
-    {  // in_proj
+    {  // in_proj (xs = emb_i + pe[i mod period] was written by the feedback phase of the previous frame)
       float acc = dot_seg(w_in, xs + in_s * 32, 32);
       acc += __shfl_xor_sync(0xffffffffu, acc, 1);
       if (in_s == 0 && in_o < 192) {
@@ -347,10 +368,7 @@ ff_decoder_ar64_kernel(const AviDecoderWeights w, const float* __restrict__ cros
       if (s8 == 0) t0[o8] = acc + b_o;
     }
     __syncthreads();
-    ln64(xs, t0, w.ln1_w, w.ln1_b, x1);
-    if (tid < 64) t0[tid] = cross[((int64_t)b * T + i) * 64 + tid];
-    __syncthreads();
-    ln64(x1, t0, w.ln2_w, w.ln2_b, xs);
+    ln64x2(xs, t0, cross + ((int64_t)b * T + i) * 64, w.ln1_w, w.ln1_b, w.ln2_w, w.ln2_b, xs);
     {  // ff1 + ReLU
       float acc = dot_seg(w_1, xs + s4 * 16, 16);
       acc += __shfl_xor_sync(0xffffffffu, acc, 1);
@@ -373,7 +391,8 @@ ff_decoder_ar64_kernel(const AviDecoderWeights w, const float* __restrict__ cros
       acc += __shfl_xor_sync(0xffffffffu, acc, 1);
       acc += __shfl_xor_sync(0xffffffffu, acc, 2);
       acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-      if (s8 == 0) emb[o8] = acc + b_f + sty[o8];
+      // x_{i+1} = emb_{i+1} + pe[(i+1) mod period]: the LN3 phase above was the last reader of xs (its residual input)
+      if (s8 == 0) xs[o8] = acc + b_f + sty[o8] + w.pe[((i + 1) % period) * 64 + o8];
     }
     __syncthreads();
   }
