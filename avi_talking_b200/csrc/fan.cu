@@ -14,7 +14,14 @@ __device__ __forceinline__ __nv_bfloat16 fan_out<__nv_bfloat16>(float v) { retur
 // cols[(n, oy, ox), (ky, kx, c)] = act(x[n, oy*s - p + ky, ox*s - p + kx, c]) (zero outside the image: F.conv2d pads the ACTIVATED
 // tensor), act(v) = relu(v * scale[c] + shift[c]) when scale != nullptr (the pre-activation BatchNorm + ReLU of ConvBlock), else v.
 // Columns K..Kpad-1 are zero. One thread per 4 consecutive channels of one tap (C % 4 == 0) or per element otherwise.
-template <typename OutT, int VEC>
+// round-to-nearest to the 10-bit TF32 significand (the kind::tf32 MMA ignores the low 13 bits of its fp32 operands)
+__device__ __forceinline__ float round_tf32(float v) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+  return __uint_as_float(u);
+}
+
+template <typename OutT, int VEC, bool RTF32 = false>
 __global__ void __launch_bounds__(256) im2col_affine_kernel(const float* __restrict__ x, int64_t x_ld, OutT* __restrict__ cols, int N, int H,
                                                             int W, int C, int k, int stride, int pad, int Ho, int Wo, int Kpad,
                                                             const float* __restrict__ scale, const float* __restrict__ shift) {
@@ -37,7 +44,7 @@ __global__ void __launch_bounds__(256) im2col_affine_kernel(const float* __restr
       for (int u = 0; u < VEC; ++u) {
         float t = src[u];
         if (scale) t = fmaxf(fmaf(t, scale[c + u], shift[c + u]), 0.f);
-        v[u] = t;
+        v[u] = RTF32 ? round_tf32(t) : t;
       }
     }
   }
@@ -106,6 +113,9 @@ extern "C" int avi_im2col_affine(const float* x, int64_t x_ld, void* cols, int32
   if (cols_dtype == AVI_DT_BF16) {
     if (vec) im2col_affine_kernel<__nv_bfloat16, 4><<<blocks, 256, 0, st>>>(x, x_ld, (__nv_bfloat16*)cols, N, H, W, C, k, stride, pad, Ho, Wo, Kpad, scale, shift);
     else im2col_affine_kernel<__nv_bfloat16, 1><<<blocks, 256, 0, st>>>(x, x_ld, (__nv_bfloat16*)cols, N, H, W, C, k, stride, pad, Ho, Wo, Kpad, scale, shift);
+  } else if (cols_dtype == AVI_DT_TF32) {
+    if (vec) im2col_affine_kernel<float, 4, true><<<blocks, 256, 0, st>>>(x, x_ld, (float*)cols, N, H, W, C, k, stride, pad, Ho, Wo, Kpad, scale, shift);
+    else im2col_affine_kernel<float, 1, true><<<blocks, 256, 0, st>>>(x, x_ld, (float*)cols, N, H, W, C, k, stride, pad, Ho, Wo, Kpad, scale, shift);
   } else {
     if (vec) im2col_affine_kernel<float, 4><<<blocks, 256, 0, st>>>(x, x_ld, (float*)cols, N, H, W, C, k, stride, pad, Ho, Wo, Kpad, scale, shift);
     else im2col_affine_kernel<float, 1><<<blocks, 256, 0, st>>>(x, x_ld, (float*)cols, N, H, W, C, k, stride, pad, Ho, Wo, Kpad, scale, shift);

@@ -66,8 +66,12 @@ struct Tc2Params {
   int tma_store;   // 0: threads store; 1: staged tiles leave through TMA stores (map_c); 2: TMA reduce-add (C += ..., residual == C)
 };
 
+// TF32 = true: operands are fp32 in shared memory (32 elements per 128-byte swizzle row instead of 64), consumed by
+// tcgen05.mma.kind::tf32 (10-bit significand, fp32 accumulate): the same pipeline at half the MMA rate, for callers that need more
+// than bf16's 8 bits (the 60-convolution FanEncoder). Everything below is written in BYTES per k-block (128) and in elements via BK.
+template <bool TF32>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P2_THREADS, 1)
-gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                      const __grid_constant__ CUtensorMap map_c, const Tc2Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];  // no static shared memory in this kernel: the dynamic window starts aligned
   if ((smem_u32(smem) & 1023u) != 0) __trap();        // SWIZZLE_128B tiles need 1024-byte alignment
@@ -133,8 +137,9 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
           if (kb == 0) TL(0, (t - pair) / num_pairs, 1);
           const uint32_t fb_local = smem_u32(&full_bar[stage]);
           if (rank == 0) mbar_expect_tx(fb_local, 2 * P2_STAGE_BYTES);
-          tma_load_4d_pair(smem_u32(smem_a + stage * P2_A_BYTES), &map_a, full_leader + stage * 8, kin * P2_BK, ph, row0 + sr, b);
-          tma_load_2d_pair(smem_u32(smem_b + stage * P2_B_BYTES), &map_w, full_leader + stage * 8, kb * P2_BK, wrow0);
+          constexpr int BK = TF32 ? P2_BK / 2 : P2_BK;   // elements per 128-byte k-block row
+          tma_load_4d_pair(smem_u32(smem_a + stage * P2_A_BYTES), &map_a, full_leader + stage * 8, kin * BK, ph, row0 + sr, b);
+          tma_load_2d_pair(smem_u32(smem_b + stage * P2_B_BYTES), &map_w, full_leader + stage * 8, kb * BK, wrow0);
           if (++kin == p.kb_per_tap) {
             kin = 0;
             if (++ph == p.conv_stride) {
@@ -153,7 +158,9 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     // ===================== MMA issuer (leader CTA, one thread) =====================
     if (rank == 0 && lane == 0) {
       // instruction descriptor: D=f32, A=B=bf16, both K-major, N=n_eff (256 except in a narrower last n-tile), M=256 (pair)
-      const uint32_t idesc_base = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * P2_BM) >> 4) << 24);
+      // (formats: kind::f16 -> 1 = bf16; kind::tf32 -> 2 = tf32)
+      const uint32_t fmt = TF32 ? 2u : 1u;
+      const uint32_t idesc_base = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)((2 * P2_BM) >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -175,8 +182,10 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
           const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + stage * P2_A_BYTES));
           const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + stage * P2_B_BYTES));
 #pragma unroll
-          for (int k = 0; k < P2_BK / P2_UMMA_K; ++k)
-            umma_bf16_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < P2_BK / P2_UMMA_K; ++k) {   // four MMAs of 32 bytes of K each (16 bf16 or 8 tf32 elements)
+            if constexpr (TF32) umma_tf32_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_bf16_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
           umma_commit_pair(smem_u32(&empty_bar[stage]), 3);  // frees the slot in BOTH CTAs once these MMAs have read it
           if (++stage == P2_STAGES) {
             stage = 0;
@@ -449,16 +458,17 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   }
 }
 
-static const char* tc2_check(const AviGemmArgs* a) {
+static const char* tc2_check(const AviGemmArgs* a, bool tf32 = false) {
   if (!a) return "null args";
-  if (a->a_dtype != AVI_DT_BF16) return "A/W must be bf16";
+  if (a->a_dtype != (tf32 ? AVI_DT_F32 : AVI_DT_BF16)) return tf32 ? "A/W must be fp32" : "A/W must be bf16";
   if (a->batch <= 0 || a->rows <= 0 || a->N <= 0 || a->K <= 0) return "bad shape";
   if (a->conv_taps < 1 || a->conv_stride < 1) return "bad conv params";
   if (a->K % a->conv_taps != 0) return "K must be taps * C_in";
   const int cin = a->K / a->conv_taps;
-  if (cin % P2_BK != 0) return "C_in (K per tap) must be a multiple of 64";
+  const int bk = tf32 ? P2_BK / 2 : P2_BK, al = tf32 ? 4 : 8;   // elements per k-block; elements per 16 bytes
+  if (cin % bk != 0) return tf32 ? "C_in (K per tap) must be a multiple of 32" : "C_in (K per tap) must be a multiple of 64";
   if (a->a_ld < cin) return "a_ld smaller than the channel window";
-  if (a->a_ld % 8 != 0 || a->a_batch_stride % 8 != 0) return "a_ld and a_batch_stride must be multiples of 8 elements";
+  if (a->a_ld % al != 0 || a->a_batch_stride % al != 0) return "a_ld and a_batch_stride must be multiples of 16 bytes";
   if (((uintptr_t)a->A | (uintptr_t)a->W) % 16 != 0) return "A and W must be 16-byte aligned";
   if (a->a_rows_alloc < (int64_t)(a->rows - 1) * a->conv_stride + a->conv_taps) return "a_rows_alloc smaller than the rows read";
   if (a->C == nullptr) return "C is null";
@@ -479,11 +489,13 @@ extern "C" int avi_debug_timeline(long long* host_out) {
 
 extern "C" int avi_gemm_bf16_tc_supported(const AviGemmArgs* a) { return tc2_check(a) == nullptr ? 1 : 0; }
 
-extern "C" int avi_gemm_bf16_tc(const AviGemmArgs* a, void* stream) {
-  static const bool use_v1 = getenv("AVI_GEMM_V1") != nullptr;
-  if (use_v1) return avi_gemm_bf16_tc_v1(a, stream);
-  const char* why = tc2_check(a);
-  AVI_REQUIRE(why == nullptr, "avi_gemm_bf16_tc: %s", why);
+template <bool TF32>
+static int gemm_tc2_launch(const AviGemmArgs* a, void* stream) {
+  const char* why = tc2_check(a, TF32);
+  AVI_REQUIRE(why == nullptr, "%s: %s", TF32 ? "avi_gemm_tf32_tc" : "avi_gemm_bf16_tc", why);
+  constexpr int BK = TF32 ? P2_BK / 2 : P2_BK;
+  constexpr uint64_t ES = TF32 ? 4 : 2;
+  constexpr CUtensorMapDataType DT = TF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   const int cin = a->K / a->conv_taps;
   const int s = a->conv_stride;
   CUtensorMap map_a, map_w;
@@ -491,16 +503,16 @@ extern "C" int avi_gemm_bf16_tc(const AviGemmArgs* a, void* stream) {
     // (channel, phase, super-row, clip)
     const uint64_t q_rows = (uint64_t)(a->a_rows_alloc / s);
     uint64_t dims[4] = {(uint64_t)cin, (uint64_t)s, q_rows, (uint64_t)a->batch};
-    uint64_t strides[3] = {(uint64_t)a->a_ld * 2, (uint64_t)a->a_ld * s * 2, (uint64_t)a->a_batch_stride * 2};
+    uint64_t strides[3] = {(uint64_t)a->a_ld * ES, (uint64_t)a->a_ld * s * ES, (uint64_t)a->a_batch_stride * ES};
     if (a->batch == 1) strides[2] = dims[2] * strides[1];  // unused; keep it well-formed
-    uint32_t box[4] = {P2_BK, 1, P2_BM, 1};
-    if (encode_map(&map_a, a->A, 4, dims, strides, box)) return 1;
+    uint32_t box[4] = {BK, 1, P2_BM, 1};
+    if (encode_map(&map_a, a->A, 4, dims, strides, box, DT)) return 1;
   }
   {
     uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->N};
-    uint64_t strides[1] = {(uint64_t)a->K * 2};
-    uint32_t box[2] = {P2_BK, P2_BNH};
-    if (encode_map(&map_w, a->W, 2, dims, strides, box)) return 1;
+    uint64_t strides[1] = {(uint64_t)a->K * ES};
+    uint32_t box[2] = {BK, P2_BNH};
+    if (encode_map(&map_w, a->W, 2, dims, strides, box, DT)) return 1;
   }
   Tc2Params p;
   p.bias = a->bias;
@@ -512,8 +524,8 @@ extern "C" int avi_gemm_bf16_tc(const AviGemmArgs* a, void* stream) {
   p.batch = a->batch;
   p.rows = a->rows;
   p.N = a->N;
-  p.num_kb = a->K / P2_BK;
-  p.kb_per_tap = cin / P2_BK;
+  p.num_kb = a->K / BK;
+  p.kb_per_tap = cin / BK;
   p.conv_stride = s;
   p.m_tiles = (a->rows + 2 * P2_BM - 1) / (2 * P2_BM);
   p.n_tiles = (a->N + P2_BN - 1) / P2_BN;
@@ -559,11 +571,19 @@ extern "C" int avi_gemm_bf16_tc(const AviGemmArgs* a, void* stream) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(gemm_bf16_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P2_SMEM_BYTES);
+    attr_err = cudaFuncSetAttribute(gemm_tc2_kernel<TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P2_SMEM_BYTES);
   });
   AVI_REQUIRE(attr_err == cudaSuccess, "avi_gemm_bf16_tc: cannot opt in to %u bytes of shared memory: %s", P2_SMEM_BYTES,
               cudaGetErrorString(attr_err));
   const int pairs = p.total_tiles < kNumSMs / 2 ? p.total_tiles : kNumSMs / 2;
-  gemm_bf16_tc2_kernel<<<2 * pairs, P2_THREADS, P2_SMEM_BYTES, (cudaStream_t)stream>>>(map_a, map_w, map_c, p);
-  return check_launch("gemm_bf16_tc");
+  gemm_tc2_kernel<TF32><<<2 * pairs, P2_THREADS, P2_SMEM_BYTES, (cudaStream_t)stream>>>(map_a, map_w, map_c, p);
+  return check_launch(TF32 ? "gemm_tf32_tc" : "gemm_bf16_tc");
 }
+
+extern "C" int avi_gemm_bf16_tc(const AviGemmArgs* a, void* stream) {
+  static const bool use_v1 = getenv("AVI_GEMM_V1") != nullptr;
+  if (use_v1) return avi_gemm_bf16_tc_v1(a, stream);
+  return gemm_tc2_launch<false>(a, stream);
+}
+
+extern "C" int avi_gemm_tf32_tc(const AviGemmArgs* a, void* stream) { return gemm_tc2_launch<true>(a, stream); }

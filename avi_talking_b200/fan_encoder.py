@@ -10,7 +10,8 @@ Data layout: activations are NHWC fp32 rows [N*H*W, C]. Every convolution is an 
   * the three convolutions of a ConvBlock write their raw outputs straight into channel slices of the concatenated tensor (c_ld = C_out),
     the residual (identity or the bn-relu-1x1 `downsample`) is added afterwards;
   * max-pool, bilinear upsample + add (hourglass skip connections) and per-channel affine (+ReLU) are small row kernels.
-precision "bf16": tcgen05 GEMMs on bf16 operands (fp32 accumulate); "fp32": CUDA-core GEMMs.
+precision "tf32" (default): the tcgen05 GEMM on fp32 operands rounded to TF32 (fp32 accumulate); "fp32": CUDA-core GEMMs; "bf16":
+tcgen05 GEMMs on bf16 operands.
 """
 from __future__ import annotations
 
@@ -104,13 +105,14 @@ class FanEncoder(nn.Module):
         self.eye_embed = nn.Sequential(nn.ReLU(), nn.Linear(512, eye_dim))
         self.to_emo = head()
         self.emo_embed = nn.Sequential(nn.ReLU(), nn.Linear(512, 30))
-        # fp32 by default: 60 stacked convolutions on bf16 operands leave ~2 % relative error on the embeddings (measured,
-        # tests/test_gpu_fan.py), more than the 1e-2 the bf16 mode of the audio path is held to; predict() calls the encoder on the
-        # few SOURCE frames of the looped emotion clip only, so the CUDA-core GEMMs cost milliseconds. AVI_B200_FAN_PRECISION=bf16
-        # (or .precision = "bf16") selects the tcgen05 path.
-        self.precision = os.environ.get("AVI_B200_FAN_PRECISION", "fp32").lower()
-        if self.precision not in ("bf16", "fp32"):
-            raise ValueError("AVI_B200_FAN_PRECISION must be bf16 or fp32")
+        # 60 stacked convolutions on bf16 operands leave ~2 % relative error on the embeddings (measured, tests/test_gpu_fan.py) - more
+        # than the 1e-2 the bf16 mode of the audio path is held to - so the tensor-core default here is TF32 (fp32 operands rounded to
+        # a 10-bit significand, tcgen05.mma.kind::tf32: 3e-3 measured, 2.8x the CUDA-core fp32 rate). AVI_B200_PRECISION=fp32 keeps
+        # the exact CUDA-core path; AVI_B200_FAN_PRECISION={fp32,tf32,bf16} (or .precision) overrides.
+        self.precision = os.environ.get("AVI_B200_FAN_PRECISION",
+                                        "fp32" if os.environ.get("AVI_B200_PRECISION", "bf16").lower() == "fp32" else "tf32").lower()
+        if self.precision not in ("bf16", "tf32", "fp32"):
+            raise ValueError("AVI_B200_FAN_PRECISION must be bf16, tf32 or fp32")
         self.max_images_per_call = 16          # im2col operands of one chunk: <= 16 x 56 x 56 x 2304 x 2 B = 231 MB
         self._packed, self._packed_key = None, None
 
@@ -121,6 +123,7 @@ class FanEncoder(nn.Module):
         if self._packed is not None and key == self._packed_key:
             return self._packed
         bf16 = self.precision == "bf16"
+        tf32 = self.precision == "tf32"
         dt = torch.bfloat16 if bf16 else torch.float32
 
         def conv_w(conv):
@@ -132,7 +135,7 @@ class FanEncoder(nn.Module):
             Kp = (K + 63) // 64 * 64
             out = torch.zeros(co, Kp, dtype=torch.float32, device=w.device)
             out[:, :K] = flat
-            return (ops.cast_bf16(out) if bf16 else out.contiguous()), Kp
+            return (ops.cast_bf16(out) if bf16 else (ops.round_tf32(out) if tf32 else out.contiguous())), Kp
 
         def lin_w(lin):
             w = lin.weight.detach().float().contiguous()
@@ -142,7 +145,7 @@ class FanEncoder(nn.Module):
                 wp = torch.zeros(w.shape[0], Kp, dtype=torch.float32, device=w.device)
                 wp[:, :K] = w
                 w = wp
-            return (ops.cast_bf16(w) if bf16 else w), Kp
+            return (ops.cast_bf16(w) if bf16 else (ops.round_tf32(w) if tf32 else w)), Kp
 
         def block(cb):
             d = {"bn": [_bn_affine(cb.bn1), _bn_affine(cb.bn2), _bn_affine(cb.bn3)],
@@ -185,12 +188,12 @@ class FanEncoder(nn.Module):
         """conv(k x k, stride, pad) of [relu(x * scale + shift) if pre else x] -> (rows [N*Ho*Wo, cout] or `out`, Ho, Wo)."""
         w, Kp = wk
         Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
-        cols = ops.im2col_affine(x, N, H, W, C, k, stride, pad, Kp, w.dtype, pre)
+        cols = ops.im2col_affine(x, N, H, W, C, k, stride, pad, Kp, w.dtype, pre, tf32=self.precision == "tf32")
         rows = N * Ho * Wo
         if out is None:
             out = torch.empty((rows, cout), dtype=torch.float32, device=x.device)
         ops.gemm(cols, w, bias, out, rows=rows, N=cout, K=Kp, act=act, a_rows_alloc=rows, c_ld=out.stride(0),
-                 algorithmic_flops=2.0 * rows * cout * k * k * C)
+                 algorithmic_flops=2.0 * rows * cout * k * k * C, tf32=self.precision == "tf32")
         return out, Ho, Wo
 
     def _block(self, x, N, H, W, cin, B):
@@ -245,7 +248,7 @@ class FanEncoder(nn.Module):
         rows, K = x.shape
         xo = ops.cast_pad2d(x, w.dtype, C_pad=Kp) if (Kp != K or w.dtype != torch.float32) else x
         out = torch.empty((rows, w.shape[0]), dtype=torch.float32, device=x.device)
-        ops.gemm(xo, w, b, out, rows=rows, N=w.shape[0], K=Kp, act=act, a_rows_alloc=rows)
+        ops.gemm(xo, w, b, out, rows=rows, N=w.shape[0], K=Kp, act=act, a_rows_alloc=rows, tf32=self.precision == "tf32")
         return out
 
     def _head(self, x, Hd):

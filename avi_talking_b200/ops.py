@@ -86,7 +86,7 @@ def split_bf16x3(x2d):
 
 def gemm(A, W, bias, out, *, rows, N, K, batch=1, act=ACT_NONE, residual=None, out2=None, conv_taps=1, conv_stride=1,
          a_ld=None, a_batch_stride=0, a_rows_alloc=None, c_ld=None, c_batch_stride=0, res_ld=None, res_batch_stride=0,
-         algorithmic_flops=None, profile=None):
+         algorithmic_flops=None, profile=None, tf32=False):
     """C[b,r,n] = act(sum_k A[b,r,k] W[n,k] + bias[n]) (+ residual). fp32 A/W -> CUDA-core kernel, bf16 -> tcgen05 kernel."""
     _need_cuda(A, W, bias, out, residual, out2)
     if A.dtype != W.dtype:
@@ -115,6 +115,12 @@ def gemm(A, W, bias, out, *, rows, N, K, batch=1, act=ACT_NONE, residual=None, o
     lib = _lib.load()
     # bench.py's roofline counts ALGORITHMIC flops: callers that pad the contraction with structural zeros say so
     flops = 2.0 * batch * rows * N * K if algorithmic_flops is None else float(algorithmic_flops)
+    if tf32:                     # fp32 operands on the tensor cores as TF32 (10-bit significand), same kernel as the bf16 path
+        if A.dtype != torch.float32:
+            raise TypeError("tf32 GEMM takes fp32 operands")
+        with _timed("gemm_tf32_tc", flops):
+            _lib.check(lib.avi_gemm_tf32_tc(C.byref(args), _stream()), "avi_gemm_tf32_tc")
+        return out
     if profile is not None:      # (name, work): a launch whose roofline is not the tensor pipe (the HBM-write-bound vertex head)
         with _timed(profile[0], float(profile[1])):
             _lib.check((lib.avi_gemm_bf16_tc if A.dtype == torch.bfloat16 else lib.avi_gemm_f32)(C.byref(args), _stream()), "avi_gemm")
@@ -662,7 +668,13 @@ def token_mean(x2d, B, T):
 
 
 # ------------------------------------------------------------------------------------------------ FanEncoder image branch pieces
-def im2col_affine(x, N, H, W, Cc, k, stride, pad, Kpad, dtype, pre=None):
+def round_tf32(t):
+    """fp32 tensor rounded to nearest TF32 (10 explicit significand bits), for weights packed once; data movement level bit math."""
+    u = t.detach().float().contiguous().view(torch.int32)
+    return ((u + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def im2col_affine(x, N, H, W, Cc, k, stride, pad, Kpad, dtype, pre=None, tf32=False):
     """x fp32 rows [N*H*W, C] (row stride allowed) -> cols [N*Ho*Wo, Kpad] of `dtype`; pre = (scale, shift) applies relu(x*scale+shift)."""
     _need_cuda(x)
     assert x.dtype == torch.float32 and x.stride(1) == 1
@@ -670,7 +682,7 @@ def im2col_affine(x, N, H, W, Cc, k, stride, pad, Kpad, dtype, pre=None):
     cols = torch.empty((N * Ho * Wo, Kpad), dtype=dtype, device=x.device)
     sc, sh = pre if pre is not None else (None, None)
     with _timed("im2col", float(cols.numel() * cols.element_size())):
-        _chk(_lib.load().avi_im2col_affine(_ptr(x), C.c_int64(x.stride(0)), _ptr(cols), C.c_int32(_dt(cols)), C.c_int32(N), C.c_int32(H),
+        _chk(_lib.load().avi_im2col_affine(_ptr(x), C.c_int64(x.stride(0)), _ptr(cols), C.c_int32(2 if tf32 else _dt(cols)), C.c_int32(N), C.c_int32(H),
                                            C.c_int32(W), C.c_int32(Cc), C.c_int32(k), C.c_int32(stride), C.c_int32(pad), C.c_int32(Kpad),
                                            _ptr(sc), _ptr(sh), _stream()), "avi_im2col_affine")
     return cols

@@ -46,7 +46,7 @@ int64_t avi_launch_count(void);
  *   A + b*a_batch_stride + r*conv_stride*a_ld  and is conv_taps*a_ld... see AviGemmArgs below.
  */
 enum { AVI_ACT_NONE = 0, AVI_ACT_GELU = 1 /* exact erf */, AVI_ACT_RELU = 2, AVI_ACT_QUICK_GELU = 3 /* x * sigmoid(1.702 x), CLIP */ };
-enum { AVI_DT_F32 = 0, AVI_DT_BF16 = 1 };
+enum { AVI_DT_F32 = 0, AVI_DT_BF16 = 1, AVI_DT_TF32 = 2 /* fp32 storage rounded to TF32 (operand producers only) */ };
 
 typedef struct AviGemmArgs {
   const void* A;      /* activations, dtype a_dtype; element (b, row, c) at A + b*a_batch_stride + row*a_ld + c              */
@@ -75,6 +75,9 @@ int avi_gemm_f32(const AviGemmArgs* args, void* stream);
  * Output rows whose pitch c_ld ends exactly at the 16-byte granule holding column N-1 (padded rows, e.g. N = 15069 on c_ld = 15072)
  * get zeros in those padding columns; nothing else outside [rows, N] is written. residual == C (fp32) updates C in place. */
 int avi_gemm_bf16_tc(const AviGemmArgs* args, void* stream);
+/* same kernel on fp32 operands read as TF32 (tcgen05.mma.kind::tf32: 10-bit significand, fp32 accumulate; half the MMA rate).
+ * a_dtype must be AVI_DT_F32; K per tap % 32 == 0, a_ld % 4 == 0, 16-byte aligned bases. */
+int avi_gemm_tf32_tc(const AviGemmArgs* args, void* stream);
 /* 1 if the tensor-core path accepts these shapes (host-side check only) */
 int avi_gemm_bf16_tc_supported(const AviGemmArgs* args);
 /* fp32 -> bf16 (weights packing / activation staging), n elements */
@@ -279,7 +282,8 @@ int avi_token_mean(const float* x, float* out, int32_t B, int32_t T, int32_t C, 
 /* ------------------------------------------------------------------ FanEncoder image branch (SURVEY 8f row 1;
  * third_party/pd_fgc_inference/lib/models/networks/FAN_feature_extractor.py:13-163, encoder.py:89-126). NHWC fp32 rows [N*H*W, C].
  * cols[(n,oy,ox), (ky,kx,c)] = act(x[n, oy*stride-pad+ky, ox*stride-pad+kx, c]) (zero outside the image), act = relu(x*scale+shift)
- * when scale != NULL (ConvBlock's pre-activation BatchNorm + ReLU, :38-48); rows of x are x_ld floats apart; Kpad >= k*k*C */
+ * when scale != NULL (ConvBlock's pre-activation BatchNorm + ReLU, :38-48); rows of x are x_ld floats apart; Kpad >= k*k*C;
+ * cols_dtype AVI_DT_TF32 writes fp32 rounded to nearest TF32 (operand of avi_gemm_tf32_tc, whose MMA truncates) */
 int avi_im2col_affine(const float* x, int64_t x_ld, void* cols, int32_t cols_dtype, int32_t N, int32_t H, int32_t W, int32_t C, int32_t k,
                       int32_t stride, int32_t pad, int32_t Kpad, const float* scale, const float* shift, void* stream);
 /* F.max_pool2d(x, 2, stride=2) (:86, :142) */

@@ -11,12 +11,12 @@ cap() {  # name regex skip
 }
 # GEMM launch order inside one step: conv1..6 (0-5), feature projection (6), 4 pos-conv blocks (7-10), per encoder layer l:
 # qkv 11+4l, out-proj 12+4l, ffn1 13+4l, ffn2 14+4l; vertex head 59. Second step = +60.
-cap gemm_conv1 gemm_bf16_tc2 60
-cap gemm_qkv gemm_bf16_tc2 71
-cap gemm_oproj gemm_bf16_tc2 72
-cap gemm_ffn1 gemm_bf16_tc2 73
-cap gemm_ffn2 gemm_bf16_tc2 74
-cap gemm_vhead gemm_bf16_tc2 119
+cap gemm_conv1 gemm_tc2_kernel 60
+cap gemm_qkv gemm_tc2_kernel 71
+cap gemm_oproj gemm_tc2_kernel 72
+cap gemm_ffn1 gemm_tc2_kernel 73
+cap gemm_ffn2 gemm_tc2_kernel 74
+cap gemm_vhead gemm_tc2_kernel 119
 cap conv0 conv0_tc 1
 cap attn attn_tc 12
 cap ar_decoder ff_decoder_ar64 1

@@ -11,7 +11,7 @@ from avi_talking_b200.fan_encoder import FanEncoder  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 x = synth.fan_images(n, seed=81).cuda()
-for prec in ("fp32", "bf16"):
+for prec in ("fp32", "tf32", "bf16"):
     m = FanEncoder()
     m.load_state_dict(synth.fan_state(80))
     m.precision = prec
@@ -36,7 +36,7 @@ for prec in ("fp32", "bf16"):
         d[1] += a.elapsed_time(b)
         d[2] += work
     ops.PROFILE = None
-    gk = "gemm_bf16_tc" if prec == "bf16" else "gemm_f32"
+    gk = {"bf16": "gemm_bf16_tc", "tf32": "gemm_tf32_tc", "fp32": "gemm_f32"}[prec]
     print(f"{prec}: {ms:.3f} ms per {n} images = {n / ms * 1e3:.0f} images/s; " +
           ", ".join(f"{k}: {v[0]} launches {v[1]:.3f} ms" for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])) +
           f"; GEMM {agg[gk][2] / agg[gk][1] / 1e9:.1f} TFLOP/s algorithmic ({agg[gk][2] / n / 1e9:.2f} GFLOP per image)")

@@ -1,6 +1,6 @@
 """GPU parity of the FanEncoder image-branch drop-in against the reference's own FanEncoder outputs
-(tests/golden/fan.npz) and the CPU oracle. fp32 mode (the default of this drop-in): relative L2 error <= 1e-4 (measured 4e-6); bf16 GEMM mode: <= 4e-2 (measured 1.5-2.9e-2: 60
-stacked convolutions on bf16 operands - above the 1e-2 of the audio path, which is why it is opt-in here)."""
+(tests/golden/fan.npz) and the CPU oracle. fp32 mode: relative L2 error <= 1e-4 (measured 4e-6); TF32 tensor-core mode (the default): <= 1e-2 (measured 2.4-3.9e-3); bf16 GEMM
+mode: <= 4e-2 (measured 1.5-2.9e-2: 60 stacked convolutions on bf16 operands - above the 1e-2 of the audio path, hence opt-in)."""
 import numpy as np
 import pytest
 import torch
@@ -25,7 +25,7 @@ def rel(a, b):
 def test_fan_encoder_matches_reference_golden(golden):
     g = golden("fan")
     x = synth.fan_images(3, seed=81).cuda()
-    for prec, tol in (("fp32", 1e-4), ("bf16", 4e-2)):
+    for prec, tol in (("fp32", 1e-4), ("tf32", 1e-2), ("bf16", 4e-2)):
         m = build(prec)
         head, eye, emo, mouth = m(x)
         errs = {k: rel(t.cpu().numpy(), g[k]) for k, t in zip(("head", "eye", "emo", "mouth"), (head, eye, emo, mouth))}
@@ -39,7 +39,7 @@ def test_fan_encoder_chunking_and_predict_integration():
     """More images than one chunk (max_images_per_call) give the same rows; as `fan_net` of Faceformer.predict the drop-in is called
     once on the source frames of the looped emotion clip."""
     from helpers import build_faceformer
-    m = build("bf16")
+    m = build("tf32")
     x = synth.fan_images(5, seed=82).cuda()
     full = m(x)[2]
     m.max_images_per_call = 2

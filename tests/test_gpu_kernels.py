@@ -270,3 +270,29 @@ def test_gemm_bf16_tc_inplace_residual_reduce_add(ops):
     ref = _gemm_ref(A.float().cpu(), W.float().cpu(), b.cpu(), 0, res.cpu())
     assert (inplace.cpu().double() - ref).abs().max().item() < 1e-4
     assert torch.equal(inplace, sep)
+
+
+@pytest.mark.parametrize("rows,N,K,act,use_res", [(300, 512, 128, 0, False), (1000, 768, 96, 1, False), (515, 192, 2304, 0, True),
+                                                  (390, 15069, 64, 0, False)])
+def test_gemm_tf32_tc(ops, rows, N, K, act, use_res):
+    """tcgen05.mma.kind::tf32 on fp32 operands (same pipeline as the bf16 GEMM, 32 elements per k-block): compared with the exact
+    product of the TF32-truncated operands (1e-4) and with the fp32 product (10-bit significand: 2e-3 on O(1) outputs)."""
+    r = _rng(9)
+    A = torch.from_numpy(r.normal(size=(rows, K)).astype(np.float32))
+    W = torch.from_numpy((r.normal(size=(N, K)) / math.sqrt(K)).astype(np.float32))
+    b = torch.from_numpy(r.normal(size=(N,)).astype(np.float32))
+    res = torch.from_numpy(r.normal(size=(rows, N)).astype(np.float32)) if use_res else None
+    ld = 15072 if N == 15069 else N
+    out = torch.empty((rows, ld), dtype=torch.float32, device="cuda")
+    ops.gemm(A.cuda(), W.cuda(), b.cuda(), out, rows=rows, N=N, K=K, act=act, residual=None if res is None else res.cuda(),
+             a_rows_alloc=rows, c_ld=ld, tf32=True)
+    got = out[:, :N].cpu().double()
+
+    def trunc(t):   # TF32 keeps 10 explicit significand bits: the hardware ignores the low 13 bits of the fp32 word
+        return (t.view(torch.int32) & ~0x1FFF).view(torch.float32)
+
+    ref_t = _gemm_ref(trunc(A), trunc(W), b, act, res)
+    ref = _gemm_ref(A, W, b, act, res)
+    e_t, e = (got - ref_t).abs().max().item(), (got - ref).abs().max().item()
+    print(f"tf32 GEMM {rows}x{N}x{K}: max err vs truncated-operand product {e_t:.2e}, vs fp32 product {e:.2e}")
+    assert e_t < 1e-4 and e < 1e-2
