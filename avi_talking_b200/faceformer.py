@@ -131,6 +131,7 @@ class Faceformer(nn.Module):
         # tensor cores from the encoder's bf16 output (-0.1 ms per 64-clip step) at the price of ~1.2e-5 m of the 1e-4 m bf16-mode
         # vertex budget (measured: 8.5e-5 -> 9.8e-5 m max error on the smoke case), so it is opt-in
         self.afm_tensor_core = os.environ.get("AVI_B200_AFM_TC", "0") == "1"
+        self.small_linears_tf32 = os.environ.get("AVI_B200_SMALL_TF32", "0") == "1"
         self._packed = None
         self._packed_key = None
         self._before_ar = None
@@ -181,6 +182,13 @@ class Faceformer(nn.Module):
         P["afm_w"], P["afm_b"] = f32(self.audio_feature_map.weight), f32(self.audio_feature_map.bias)
         if self.precision == "bf16":
             P["afm_w16"] = ops.cast_bf16(self.audio_feature_map.weight)
+            # the small fp32 Linears between the encoder and the AR decoder (768 -> fd, fd -> fd twice) run on the tensor cores as
+            # TF32 (weights rounded to nearest here, activations truncated by the MMA: ~1e-3 relative, an order below the bf16 GEMMs
+            # upstream of them) instead of the CUDA-core fp32 GEMM. Opt-in (AVI_B200_SMALL_TF32=1): -0.09 ms per 64-clip step, but the
+            # MMA truncates its fp32 activations (biased), which costs 5e-6 m of the 1e-4 m bf16-mode vertex budget (8.5e-5 -> 9.1e-5)
+            P["tf32"] = fd % 32 == 0 and self.small_linears_tf32
+            if P["tf32"]:
+                P["afm_w"], P["ca_v_w"], P["ca_o_w"] = (ops.round_tf32(P[k]) for k in ("afm_w", "ca_v_w", "ca_o_w"))
         if self.variant == "disentangle":
             P["merge_w"], P["merge_b"] = f32(self.v_merge2hidden.weight), f32(self.v_merge2hidden.bias)
         P["vm_w"], P["vm_b"] = f32(self.vertice_map.weight), f32(self.vertice_map.bias)
@@ -235,7 +243,8 @@ class Faceformer(nn.Module):
             mix = ops.linear(hs, P["merge_w"], P["merge_b"])                                   # :437
         else:
             mix = hs
-        cross = ops.linear(ops.linear(mix, P["ca_v_w"], P["ca_v_b"]), P["ca_o_w"], P["ca_o_b"])  # degenerate cross-attn
+        t32 = bool(P.get("tf32"))
+        cross = ops.linear(ops.linear(mix, P["ca_v_w"], P["ca_v_b"], tf32=t32), P["ca_o_w"], P["ca_o_b"], tf32=t32)  # degenerate cross-attn
         style = obj_embedding.contiguous().float()
         period = self.args.period
         if teacher_forcing:
@@ -280,7 +289,7 @@ class Faceformer(nn.Module):
             # the encoder already produced the bf16 copy of its output for the next tensor-core contraction
             hs_a = ops.linear(h16.reshape(B * T, -1), P["afm_w16"], P["afm_b"], out_dtype=torch.float32).view(B, T, -1)   # :776
         else:
-            hs_a = ops.linear(hs_a.reshape(B * T, -1), P["afm_w"], P["afm_b"]).view(B, T, -1)   # :776
+            hs_a = ops.linear(hs_a.reshape(B * T, -1), P["afm_w"], P["afm_b"], tf32=bool(P.get("tf32"))).view(B, T, -1)   # :776
         if self.variant == "disentangle":
             eye = self.learnable_eye_embed.expand(B, T, -1) if eye_embed is None else eye_embed
             hidden_states = torch.cat([eye, emo_embed[:, :T].to(hs_a), hs_a], dim=-1)          # :808

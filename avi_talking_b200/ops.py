@@ -135,7 +135,7 @@ def gemm(A, W, bias, out, *, rows, N, K, batch=1, act=ACT_NONE, residual=None, o
 
 
 def linear(x2d: torch.Tensor, W: torch.Tensor, bias, *, act=ACT_NONE, residual=None, out_dtype=None, out2_dtype=None,
-           out=None):
+           out=None, tf32=False):
     """nn.Linear on [rows, K] activations: returns out (and out2 if requested)."""
     rows, K = x2d.shape
     N = W.shape[0]
@@ -143,7 +143,7 @@ def linear(x2d: torch.Tensor, W: torch.Tensor, bias, *, act=ACT_NONE, residual=N
     if out is None:
         out = torch.empty((rows, N), dtype=out_dtype or torch.float32, device=x2d.device)
     out2 = torch.empty((rows, N), dtype=out2_dtype, device=x2d.device) if out2_dtype is not None else None
-    gemm(x2d, W, bias, out, rows=rows, N=N, K=K, act=act, residual=residual, out2=out2, a_rows_alloc=rows)
+    gemm(x2d, W, bias, out, rows=rows, N=N, K=K, act=act, residual=residual, out2=out2, a_rows_alloc=rows, tf32=tf32)
     return (out, out2) if out2 is not None else out
 
 
