@@ -28,6 +28,7 @@ class AviGemmArgs(C.Structure):
         ("c_ld", C.c_int64), ("c_batch_stride", C.c_int64),
         ("res_ld", C.c_int64), ("res_batch_stride", C.c_int64),
         ("a_dtype", C.c_int32), ("c_dtype", C.c_int32), ("act", C.c_int32),
+        ("conv_taps_x", C.c_int32), ("conv_row_pitch", C.c_int32),
     ]
 
 

@@ -18,6 +18,8 @@ struct SimtParams {
   int64_t a_row_stride, a_batch_stride, c_ld, c_batch_stride, res_ld, res_batch_stride;
   int act;
   int m_tiles;  // per batch entry
+  int kx_span;      // 2-D taps: elements of one line of the window (taps_x * C_in); 0 = contiguous window
+  int64_t kx_skip;  // elements to skip between the lines of the window ((row_pitch - taps_x) * a_ld)
 };
 
 __global__ void __launch_bounds__(256) gemm_f32_kernel(const SimtParams p) {
@@ -40,7 +42,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const SimtParams p) {
   for (int k0 = 0; k0 < p.K; k0 += SG_BK) {
     {
       const int r = m0 + lr;
-      const float* src = Ab + (int64_t)r * p.a_row_stride + k0 + lk;
+      const float* src = Ab + (int64_t)r * p.a_row_stride + k0 + lk + (p.kx_span ? (int64_t)((k0 + lk) / p.kx_span) * p.kx_skip : 0);
 #pragma unroll
       for (int u = 0; u < 4; ++u) As[lk + u][lr] = (r < p.rows && k0 + lk + u < p.K) ? src[u] : 0.f;
       const int n = n0 + lr;
@@ -93,6 +95,9 @@ extern "C" int avi_gemm_f32(const AviGemmArgs* a, void* stream) {
   AVI_REQUIRE(a->conv_taps >= 1 && a->conv_stride >= 1, "avi_gemm_f32: bad conv params");
   AVI_REQUIRE(a->conv_taps == 1 || a->K == a->conv_taps * a->a_ld,
               "avi_gemm_f32: conv mode needs contiguous input rows (K == taps * a_ld)");
+  AVI_REQUIRE(a->conv_taps_x == 0 || (a->conv_taps_x > 0 && a->conv_stride == 1 && a->conv_taps % a->conv_taps_x == 0 &&
+                                      a->conv_row_pitch >= a->conv_taps_x && (a->conv_taps_x * a->a_ld) % 4 == 0),
+              "avi_gemm_f32: 2-D taps need conv_stride 1, conv_taps a multiple of conv_taps_x, line span a multiple of 4 elements");
   SimtParams p;
   p.A = (const float*)a->A;
   p.W = (const float*)a->W;
@@ -112,6 +117,8 @@ extern "C" int avi_gemm_f32(const AviGemmArgs* a, void* stream) {
   p.res_batch_stride = a->res_batch_stride;
   p.act = a->act;
   p.m_tiles = (a->rows + SG_BM - 1) / SG_BM;
+  p.kx_span = a->conv_taps_x != 0 ? a->conv_taps_x * (int)a->a_ld : 0;
+  p.kx_skip = a->conv_taps_x != 0 ? (int64_t)(a->conv_row_pitch - a->conv_taps_x) * a->a_ld : 0;
   dim3 grid((unsigned)(p.m_tiles * a->batch), (unsigned)((a->N + SG_BN - 1) / SG_BN));
   AVI_REQUIRE(grid.y <= 65535, "avi_gemm_f32: N too large");
   gemm_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);

@@ -324,6 +324,7 @@ static const char* tc_check(const AviGemmArgs* a) {
   if (a->a_ld % 8 != 0 || a->a_batch_stride % 8 != 0) return "a_ld and a_batch_stride must be multiples of 8 elements";
   if (((uintptr_t)a->A | (uintptr_t)a->W) % 16 != 0) return "A and W must be 16-byte aligned";
   if (a->a_rows_alloc < (int64_t)(a->rows - 1) * a->conv_stride + a->conv_taps) return "a_rows_alloc smaller than the rows read";
+  if (a->conv_taps_x != 0) return "2-D taps are not built in the single-CTA kernel";
   if (a->C == nullptr) return "C is null";
   return nullptr;
 }

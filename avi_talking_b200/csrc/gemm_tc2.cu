@@ -60,6 +60,7 @@ struct Tc2Params {
   int num_kb;      // K / 64
   int kb_per_tap;  // C_in / 64
   int conv_stride;
+  int taps_x, row_skip;  // 2-D taps: after every taps_x taps the input row advances by row_skip more (row pitch - taps_x); 0 = 1-D
   int m_tiles, n_tiles, total_tiles;  // m_tiles counts 256-row pair tiles per batch entry
   int64_t c_ld, c_batch_stride, res_ld, res_batch_stride;
   int vec_ok;      // outputs (and residual) are 16-byte addressable per 32-column chunk
@@ -130,7 +131,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         const int wrow0 = n_blk * P2_BN + (int)rank * (n_eff >> 1);
         // tap / phase / super-row / channel-block counters advance incrementally: this single thread paces the whole pipeline,
         // and four runtime integer divisions per k-block cost about as much as the MMAs of that k-block
-        int kin = 0, ph = 0, sr = 0;
+        int kin = 0, ph = 0, sr = 0, tx = 0;
         TL(0, (t - pair) / num_pairs, 0);
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
@@ -145,6 +146,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             if (++ph == p.conv_stride) {
               ph = 0;
               ++sr;
+            }
+            if (p.taps_x != 0 && ++tx == p.taps_x) {   // next line of a k x k window
+              tx = 0;
+              sr += p.row_skip;
             }
           }
           if (++stage == P2_STAGES) {
@@ -470,7 +475,14 @@ static const char* tc2_check(const AviGemmArgs* a, bool tf32 = false) {
   if (a->a_ld < cin) return "a_ld smaller than the channel window";
   if (a->a_ld % al != 0 || a->a_batch_stride % al != 0) return "a_ld and a_batch_stride must be multiples of 16 bytes";
   if (((uintptr_t)a->A | (uintptr_t)a->W) % 16 != 0) return "A and W must be 16-byte aligned";
-  if (a->a_rows_alloc < (int64_t)(a->rows - 1) * a->conv_stride + a->conv_taps) return "a_rows_alloc smaller than the rows read";
+  if (a->conv_taps_x != 0) {
+    if (a->conv_taps_x < 0 || a->conv_stride != 1 || a->conv_taps % a->conv_taps_x != 0 || a->conv_row_pitch < a->conv_taps_x)
+      return "2-D taps need conv_stride 1, conv_taps a multiple of conv_taps_x and conv_row_pitch >= conv_taps_x";
+    if (a->a_rows_alloc < (int64_t)(a->rows - 1) + (int64_t)(a->conv_taps / a->conv_taps_x - 1) * a->conv_row_pitch + a->conv_taps_x)
+      return "a_rows_alloc smaller than the rows read";
+  } else if (a->a_rows_alloc < (int64_t)(a->rows - 1) * a->conv_stride + a->conv_taps) {
+    return "a_rows_alloc smaller than the rows read";
+  }
   if (a->C == nullptr) return "C is null";
   return nullptr;
 }
@@ -527,6 +539,8 @@ static int gemm_tc2_launch(const AviGemmArgs* a, void* stream) {
   p.num_kb = a->K / BK;
   p.kb_per_tap = cin / BK;
   p.conv_stride = s;
+  p.taps_x = a->conv_taps_x;
+  p.row_skip = a->conv_taps_x != 0 ? a->conv_row_pitch - a->conv_taps_x : 0;
   p.m_tiles = (a->rows + 2 * P2_BM - 1) / (2 * P2_BM);
   p.n_tiles = (a->N + P2_BN - 1) / P2_BN;
   p.total_tiles = p.m_tiles * p.n_tiles * a->batch;

@@ -4,9 +4,12 @@ reference (the nn.Modules below are parameter containers; their computation runs
 `forward(x [N,3,224,224]) -> (headpose_emb [N,6], eye_embed [N,6], emo_embed [N,30], mouth_feat [N,512])`, eval mode (BatchNorm with
 running statistics: what `Faceformer.predict` uses under no_grad).
 
-Data layout: activations are NHWC fp32 rows [N*H*W, C]. Every convolution is an im2col + GEMM:
-  * `avi_im2col_affine` builds the GEMM operand rows [N*Ho*Wo, k*k*C (padded to 64)] and applies the PRE-activation BatchNorm + ReLU of the
-    ConvBlock on the fly (FAN_feature_extractor.py:38-48: conv(relu(bn(x)))), zero padding taps after the activation as F.conv2d does;
+Data layout: activations are NHWC fp32 rows in a PADDED-WIDTH layout [N*H*(W+2), C] (the last two pixels of every image line are
+don't-care). Every 3x3 convolution is implicit: `avi_pad_act` writes the activated input once, with a zero one-pixel border and the same
+line pitch (it applies the PRE-activation BatchNorm + ReLU of the ConvBlock, FAN_feature_extractor.py:38-48: conv(relu(bn(x))), and pads
+after the activation as F.conv2d does), so that output pixel r and tap (ky, kx) read operand row r + ky*(W+2) + kx - ONE conv-mode GEMM with
+2-D taps (AviGemmArgs.conv_taps_x / conv_row_pitch) per convolution. No 9x im2col.
+  * the 7x7 stride-2 stem, the 3x3 stride-2 tail conv and 32-channel layers in bf16 mode (k-block of 64) use `avi_im2col_affine` + GEMM;
   * the three convolutions of a ConvBlock write their raw outputs straight into channel slices of the concatenated tensor (c_ld = C_out),
     the residual (identity or the bn-relu-1x1 `downsample`) is added afterwards;
   * max-pool, bilinear upsample + add (hourglass skip connections) and per-channel affine (+ReLU) are small row kernels.
@@ -113,7 +116,7 @@ class FanEncoder(nn.Module):
                                         "fp32" if os.environ.get("AVI_B200_PRECISION", "bf16").lower() == "fp32" else "tf32").lower()
         if self.precision not in ("bf16", "tf32", "fp32"):
             raise ValueError("AVI_B200_FAN_PRECISION must be bf16, tf32 or fp32")
-        self.max_images_per_call = 16          # im2col operands of one chunk: <= 16 x 56 x 56 x 2304 x 2 B = 231 MB
+        self.max_images_per_call = 16          # bounds the transient operand buffers of one chunk
         self._packed, self._packed_key = None, None
 
     # ------------------------------------------------------------------ packing
@@ -147,9 +150,20 @@ class FanEncoder(nn.Module):
                 w = wp
             return (ops.cast_bf16(w) if bf16 else (ops.round_tf32(w) if tf32 else w)), Kp
 
+        def conv_w3(conv):
+            """3x3 weights for the implicit convolution: [Cout, 9*Cin] with columns (ky, kx, c); None when the channel count does not
+            fill a k-block of this precision (then the im2col path is used)."""
+            w = conv.weight.detach().float()
+            cin = w.shape[1]
+            if cin % (64 if bf16 else 32) != 0:
+                return None
+            m = w.permute(0, 2, 3, 1).reshape(w.shape[0], 9 * cin).contiguous()
+            return ops.cast_bf16(m) if bf16 else (ops.round_tf32(m) if tf32 else m)
+
         def block(cb):
             d = {"bn": [_bn_affine(cb.bn1), _bn_affine(cb.bn2), _bn_affine(cb.bn3)],
                  "w": [conv_w(cb.conv1), conv_w(cb.conv2), conv_w(cb.conv3)],
+                 "w3": [conv_w3(cb.conv1), conv_w3(cb.conv2), conv_w3(cb.conv3)],
                  "cout": [cb.conv1.out_channels, cb.conv2.out_channels, cb.conv3.out_channels], "down": None}
             if cb.downsample is not None:
                 d["down"] = (_bn_affine(cb.downsample[0]), conv_w(cb.downsample[2]))
@@ -183,28 +197,46 @@ class FanEncoder(nn.Module):
         self._packed, self._packed_key = P, key
         return P
 
-    # ------------------------------------------------------------------ pieces (rows = NHWC fp32 [N*H*W, C])
-    def _conv(self, x, N, H, W, C, wk, cout, k, stride, pad, pre=None, out=None, bias=None, act=ACT_NONE):
-        """conv(k x k, stride, pad) of [relu(x * scale + shift) if pre else x] -> (rows [N*Ho*Wo, cout] or `out`, Ho, Wo)."""
+    # ------------------------------------------------------------------ pieces (rows = NHWC fp32, padded-width lines of W + 2 pixels)
+    def _conv(self, x, N, H, W, C, wk, cout, k, stride, pad, pre=None, out=None, bias=None, act=ACT_NONE, Wp_in=None, Wo_extra=0):
+        """im2col + GEMM convolution of [relu(x * scale + shift) if pre else x] -> (rows [N*Ho*(Wo+Wo_extra), cout] or `out`, Ho, Wo)."""
         w, Kp = wk
+        tf32 = self.precision == "tf32"
         Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
-        cols = ops.im2col_affine(x, N, H, W, C, k, stride, pad, Kp, w.dtype, pre, tf32=self.precision == "tf32")
-        rows = N * Ho * Wo
+        cols = ops.im2col_affine(x, N, H, W, C, k, stride, pad, Kp, w.dtype, pre, tf32=tf32, Wp_in=Wp_in, Wo_extra=Wo_extra)
+        rows = N * Ho * (Wo + Wo_extra)
         if out is None:
             out = torch.empty((rows, cout), dtype=torch.float32, device=x.device)
         ops.gemm(cols, w, bias, out, rows=rows, N=cout, K=Kp, act=act, a_rows_alloc=rows, c_ld=out.stride(0),
-                 algorithmic_flops=2.0 * rows * cout * k * k * C, tf32=self.precision == "tf32")
+                 algorithmic_flops=2.0 * N * Ho * Wo * cout * k * k * C, tf32=tf32)
         return out, Ho, Wo
 
+    def _conv3x3(self, x, N, H, W, C, w3, wk, cout, pre, out):
+        """3x3 / stride 1 / pad 1 convolution in the padded-width layout, implicit (one 2-D-tap conv-mode GEMM over the activated operand);
+        `out` [N*H*(W+2), cout] may be a channel slice of a wider buffer."""
+        Wp = W + 2
+        if w3 is None:       # channel count below one k-block of this precision: explicit im2col
+            return self._conv(x, N, H, W, C, wk, cout, 3, 1, 1, pre=pre, out=out, Wp_in=Wp, Wo_extra=2)[0]
+        tf32 = self.precision == "tf32"
+        a = ops.pad_act(x, N, H, W, C, w3.dtype, pre, tf32=tf32)
+        rows = H * Wp
+        ld = out.stride(0)
+        # ONE contraction over the 9 taps: tap (ky, kx) of output pixel r reads operand row r + ky*Wp + kx (2-D taps of the GEMM)
+        ops.gemm(a, w3, None, out, batch=N, rows=rows, N=cout, K=9 * C, conv_taps=9, conv_stride=1, conv_taps_x=3, conv_row_pitch=Wp,
+                 a_ld=C, a_batch_stride=(H + 2) * Wp * C, a_rows_alloc=(H + 2) * Wp + 2, c_ld=ld, c_batch_stride=rows * ld, tf32=tf32,
+                 algorithmic_flops=2.0 * N * H * W * cout * 9 * C)
+        return out
+
     def _block(self, x, N, H, W, cin, B):
-        """ConvBlock.forward (FAN_feature_extractor.py:35-59)."""
+        """ConvBlock.forward (FAN_feature_extractor.py:35-59) on padded-width rows [N*H*(W+2), cin]."""
         c1, c2, c3 = B["cout"]
-        cat = torch.empty((N * H * W, c1 + c2 + c3), dtype=torch.float32, device=x.device)
-        self._conv(x, N, H, W, cin, B["w"][0], c1, 3, 1, 1, pre=B["bn"][0], out=cat[:, :c1])
-        self._conv(cat[:, :c1], N, H, W, c1, B["w"][1], c2, 3, 1, 1, pre=B["bn"][1], out=cat[:, c1:c1 + c2])
-        self._conv(cat[:, c1:c1 + c2], N, H, W, c2, B["w"][2], c3, 3, 1, 1, pre=B["bn"][2], out=cat[:, c1 + c2:])
-        if B["down"] is not None:
-            res, _, _ = self._conv(x, N, H, W, cin, B["down"][1], c1 + c2 + c3, 1, 1, 0, pre=B["down"][0])
+        Wp = W + 2
+        cat = torch.empty((N * H * Wp, c1 + c2 + c3), dtype=torch.float32, device=x.device)
+        self._conv3x3(x, N, H, W, cin, B["w3"][0], B["w"][0], c1, B["bn"][0], cat[:, :c1])
+        self._conv3x3(cat[:, :c1], N, H, W, c1, B["w3"][1], B["w"][1], c2, B["bn"][1], cat[:, c1:c1 + c2])
+        self._conv3x3(cat[:, c1:c1 + c2], N, H, W, c2, B["w3"][2], B["w"][2], c3, B["bn"][2], cat[:, c1 + c2:])
+        if B["down"] is not None:     # bn -> relu -> 1x1 conv: a row-wise GEMM, the don't-care pixels ride along
+            res, _, _ = self._conv(x, N, H, Wp, cin, B["down"][1], c1 + c2 + c3, 1, 1, 0, pre=B["down"][0])
         else:
             res = x
         return ops.add_f32(cat, res if res.is_contiguous() else res.contiguous())
@@ -212,35 +244,36 @@ class FanEncoder(nn.Module):
     def _hourglass(self, level, x, N, H, W, P):
         """HourGlass._forward (:81-101); dropout inactive in eval."""
         up1 = self._block(x, N, H, W, 256, P["hg"][f"b1_{level}"])
-        low1 = ops.maxpool2x2(x, N, H, W, 256)
         H2, W2 = H // 2, W // 2
+        low1 = ops.maxpool2x2(x, N, H, W, 256, Wp_in=W + 2, Wp_out=W2 + 2)
         low1 = self._block(low1, N, H2, W2, 256, P["hg"][f"b2_{level}"])
         if level > 1:
             low2 = self._hourglass(level - 1, low1, N, H2, W2, P)
         else:
             low2 = self._block(low1, N, H2, W2, 256, P["hg"][f"b2_plus_{level}"])
         low3 = self._block(low2, N, H2, W2, 256, P["hg"][f"b3_{level}"])
-        return ops.upsample_bilinear_add(low3, up1, N, H2, W2, H, W, 256)
+        return ops.upsample_bilinear_add(low3, up1, N, H2, W2, H, W, 256, Wp_in=W2 + 2, Wp_out=W + 2)
 
     def _features(self, img, P):
         """FAN_use.forward (:139-163): [n,3,224,224] -> [n,512]."""
         n, _, H, W = img.shape
-        x = img.permute(0, 2, 3, 1).contiguous().float().reshape(n * H * W, 3)                       # NHWC rows
-        x, H, W = self._conv(x, n, H, W, 3, P["conv1_w"], 64, 7, 2, 3)
+        x = img.permute(0, 2, 3, 1).contiguous().float().reshape(n * H * W, 3)                       # dense NHWC rows of the image
+        x, H, W = self._conv(x, n, H, W, 3, P["conv1_w"], 64, 7, 2, 3, Wo_extra=2)                   # -> padded-width rows
         ops.affine_act(x, *P["conv1_aff"], relu=True)                                                # relu(bn1(conv1(x)))
         x = self._block(x, n, H, W, 64, P["conv2"])
-        x = ops.maxpool2x2(x, n, H, W, 128)
+        x = ops.maxpool2x2(x, n, H, W, 128, Wp_in=W + 2, Wp_out=W // 2 + 2)
         H, W = H // 2, W // 2
         x = self._block(x, n, H, W, 128, P["conv3"])
         x = self._block(x, n, H, W, 128, P["conv4"])
         hg = self._hourglass(4, x, n, H, W, P)
         ll = self._block(hg, n, H, W, 256, P["top"])
-        ll, _, _ = self._conv(ll, n, H, W, 256, P["last_w"], 256, 1, 1, 0)
+        Wp = W + 2
+        ll, _, _ = self._conv(ll, n, H, Wp, 256, P["last_w"], 256, 1, 1, 0)
         ops.affine_act(ll, *P["last_aff"], relu=True)                                                # relu(bn_end(conv_last(ll)))
-        t, _, _ = self._conv(ll, n, H, W, 256, P["l_w"], 68, 1, 1, 0)
+        t, _, _ = self._conv(ll, n, H, Wp, 256, P["l_w"], 68, 1, 1, 0)
         ops.affine_act(t, *P["l_aff"], relu=True)                                                    # relu(bn5(l(.)))
-        net, Ho, Wo = self._conv(t, n, H, W, 68, P["conv6_w"], 1, 3, 2, 1, bias=P["conv6_b"], act=ACT_RELU)
-        net = net.view(n, Ho * Wo)                                                                   # [n, 784]
+        net, Ho, Wo = self._conv(t, n, H, W, 68, P["conv6_w"], 1, 3, 2, 1, bias=P["conv6_b"], act=ACT_RELU, Wp_in=Wp)
+        net = net.view(n, Ho * Wo)                                                                   # [n, 784] (dense again)
         return self._linear(net, P["fc_w"], P["fc_b"])
 
     def _linear(self, x, wk, b, act=ACT_NONE):

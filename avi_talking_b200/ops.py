@@ -86,7 +86,7 @@ def split_bf16x3(x2d):
 
 def gemm(A, W, bias, out, *, rows, N, K, batch=1, act=ACT_NONE, residual=None, out2=None, conv_taps=1, conv_stride=1,
          a_ld=None, a_batch_stride=0, a_rows_alloc=None, c_ld=None, c_batch_stride=0, res_ld=None, res_batch_stride=0,
-         algorithmic_flops=None, profile=None, tf32=False):
+         algorithmic_flops=None, profile=None, tf32=False, conv_taps_x=0, conv_row_pitch=0):
     """C[b,r,n] = act(sum_k A[b,r,k] W[n,k] + bias[n]) (+ residual). fp32 A/W -> CUDA-core kernel, bf16 -> tcgen05 kernel."""
     _need_cuda(A, W, bias, out, residual, out2)
     if A.dtype != W.dtype:
@@ -98,9 +98,11 @@ def gemm(A, W, bias, out, *, rows, N, K, batch=1, act=ACT_NONE, residual=None, o
     args.C2 = out2.data_ptr() if out2 is not None else None
     args.batch, args.rows, args.N, args.K = batch, rows, N, K
     args.conv_taps, args.conv_stride = conv_taps, conv_stride
+    args.conv_taps_x, args.conv_row_pitch = conv_taps_x, conv_row_pitch
     args.a_ld = a_ld if a_ld is not None else K // conv_taps
     args.a_batch_stride = a_batch_stride
-    args.a_rows_alloc = a_rows_alloc if a_rows_alloc is not None else (rows - 1) * conv_stride + conv_taps
+    args.a_rows_alloc = a_rows_alloc if a_rows_alloc is not None else (
+        (rows - 1) * conv_stride + conv_taps if conv_taps_x == 0 else rows - 1 + (conv_taps // conv_taps_x - 1) * conv_row_pitch + conv_taps_x)
     args.c_ld = c_ld if c_ld is not None else N
     args.c_batch_stride = c_batch_stride
     args.res_ld = res_ld if res_ld is not None else N
@@ -674,34 +676,55 @@ def round_tf32(t):
     return ((u + 0x1000) & ~0x1FFF).view(torch.float32)
 
 
-def im2col_affine(x, N, H, W, Cc, k, stride, pad, Kpad, dtype, pre=None, tf32=False):
-    """x fp32 rows [N*H*W, C] (row stride allowed) -> cols [N*Ho*Wo, Kpad] of `dtype`; pre = (scale, shift) applies relu(x*scale+shift)."""
+def im2col_affine(x, N, H, W, Cc, k, stride, pad, Kpad, dtype, pre=None, tf32=False, Wp_in=None, Wo_extra=0):
+    """x fp32 rows [N*H*Wp_in, C] (row stride allowed) -> cols [N*Ho*(Wo+Wo_extra), Kpad] of `dtype`; pre = (scale, shift) applies
+    relu(x*scale+shift); tf32 rounds the fp32 output to TF32."""
     _need_cuda(x)
     assert x.dtype == torch.float32 and x.stride(1) == 1
-    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    Wp_in = W if Wp_in is None else Wp_in
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1 + Wo_extra
     cols = torch.empty((N * Ho * Wo, Kpad), dtype=dtype, device=x.device)
     sc, sh = pre if pre is not None else (None, None)
     with _timed("im2col", float(cols.numel() * cols.element_size())):
         _chk(_lib.load().avi_im2col_affine(_ptr(x), C.c_int64(x.stride(0)), _ptr(cols), C.c_int32(2 if tf32 else _dt(cols)), C.c_int32(N), C.c_int32(H),
                                            C.c_int32(W), C.c_int32(Cc), C.c_int32(k), C.c_int32(stride), C.c_int32(pad), C.c_int32(Kpad),
-                                           _ptr(sc), _ptr(sh), _stream()), "avi_im2col_affine")
+                                           _ptr(sc), _ptr(sh), C.c_int32(Wp_in), C.c_int32(Wo_extra), _stream()), "avi_im2col_affine")
     return cols
 
 
-def maxpool2x2(x, N, H, W, Cc):
+def pad_act(x, N, H, W, Cc, dtype, pre=None, tf32=False):
+    """x fp32 rows [N*H*(W+2), C] (padded-width layout, row stride allowed) -> activated, zero-bordered operand rows
+    [N*(H+2)*(W+2) + 2, C] of `dtype` for the implicit 3x3 convolution (include/avi_b200.h: avi_pad_act)."""
     _need_cuda(x)
-    y = torch.empty((N * (H // 2) * (W // 2), Cc), dtype=torch.float32, device=x.device)
-    _chk(_lib.load().avi_maxpool2x2(_ptr(x.contiguous()), _ptr(y), C.c_int32(N), C.c_int32(H), C.c_int32(W), C.c_int32(Cc), _stream()),
-         "avi_maxpool2x2")
+    assert x.dtype == torch.float32 and x.stride(1) == 1
+    rows = N * (H + 2) * (W + 2)
+    a = torch.empty((rows + 2, Cc), dtype=dtype, device=x.device)
+    a[rows:].zero_()
+    sc, sh = pre if pre is not None else (None, None)
+    with _timed("pad_act", float(a.numel() * a.element_size())):
+        _chk(_lib.load().avi_pad_act(_ptr(x), C.c_int64(x.stride(0)), _ptr(a), C.c_int32(2 if tf32 else _dt(a)), C.c_int32(N), C.c_int32(H),
+                                     C.c_int32(W), C.c_int32(Cc), _ptr(sc), _ptr(sh), _stream()), "avi_pad_act")
+    return a
+
+
+def maxpool2x2(x, N, H, W, Cc, Wp_in=None, Wp_out=None):
+    _need_cuda(x)
+    Wp_in = W if Wp_in is None else Wp_in
+    Wp_out = W // 2 if Wp_out is None else Wp_out
+    y = torch.empty((N * (H // 2) * Wp_out, Cc), dtype=torch.float32, device=x.device)
+    _chk(_lib.load().avi_maxpool2x2(_ptr(x.contiguous()), _ptr(y), C.c_int32(N), C.c_int32(H), C.c_int32(W), C.c_int32(Cc), C.c_int32(Wp_in),
+                                    C.c_int32(Wp_out), _stream()), "avi_maxpool2x2")
     return y
 
 
-def upsample_bilinear_add(low, up1, N, Hi, Wi, Ho, Wo, Cc):
+def upsample_bilinear_add(low, up1, N, Hi, Wi, Ho, Wo, Cc, Wp_in=None, Wp_out=None):
     _need_cuda(low, up1)
+    Wp_in = Wi if Wp_in is None else Wp_in
+    Wp_out = Wo if Wp_out is None else Wp_out
     out = torch.empty_like(up1)
     _chk(_lib.load().avi_upsample_bilinear_add(_ptr(low.contiguous()), _ptr(up1.contiguous()), _ptr(out), C.c_int32(N), C.c_int32(Hi),
-                                               C.c_int32(Wi), C.c_int32(Ho), C.c_int32(Wo), C.c_int32(Cc), _stream()),
-         "avi_upsample_bilinear_add")
+                                               C.c_int32(Wi), C.c_int32(Ho), C.c_int32(Wo), C.c_int32(Cc), C.c_int32(Wp_in), C.c_int32(Wp_out),
+                                               _stream()), "avi_upsample_bilinear_add")
     return out
 
 

@@ -67,6 +67,9 @@ typedef struct AviGemmArgs {
   int64_t c_ld, c_batch_stride;
   int64_t res_ld, res_batch_stride;
   int32_t a_dtype, c_dtype, act;
+  /* 2-D taps (conv_stride must be 1): tap j reads input row r + (j / conv_taps_x) * conv_row_pitch + (j % conv_taps_x), i.e. a
+   * k x k convolution over image lines of conv_row_pitch pixels is ONE contraction with conv_taps = k*k. 0 = the 1-D taps above. */
+  int32_t conv_taps_x, conv_row_pitch;
 } AviGemmArgs;
 
 /* fp32 CUDA-core path (exact mode, any shape). a_dtype must be AVI_DT_F32. */
@@ -283,14 +286,22 @@ int avi_token_mean(const float* x, float* out, int32_t B, int32_t T, int32_t C, 
  * third_party/pd_fgc_inference/lib/models/networks/FAN_feature_extractor.py:13-163, encoder.py:89-126). NHWC fp32 rows [N*H*W, C].
  * cols[(n,oy,ox), (ky,kx,c)] = act(x[n, oy*stride-pad+ky, ox*stride-pad+kx, c]) (zero outside the image), act = relu(x*scale+shift)
  * when scale != NULL (ConvBlock's pre-activation BatchNorm + ReLU, :38-48); rows of x are x_ld floats apart; Kpad >= k*k*C;
- * cols_dtype AVI_DT_TF32 writes fp32 rounded to nearest TF32 (operand of avi_gemm_tf32_tc, whose MMA truncates) */
+ * cols_dtype AVI_DT_TF32 writes fp32 rounded to nearest TF32 (operand of avi_gemm_tf32_tc, whose MMA truncates);
+ * image lines of x are Wp_in pixels apart (>= W); Wo_extra surplus output columns per line are produced too (padded-width layout) */
 int avi_im2col_affine(const float* x, int64_t x_ld, void* cols, int32_t cols_dtype, int32_t N, int32_t H, int32_t W, int32_t C, int32_t k,
-                      int32_t stride, int32_t pad, int32_t Kpad, const float* scale, const float* shift, void* stream);
-/* F.max_pool2d(x, 2, stride=2) (:86, :142) */
-int avi_maxpool2x2(const float* x, float* y, int32_t N, int32_t H, int32_t W, int32_t C, void* stream);
-/* out = up1 + bilinear upsample of low to (Ho, Wo), align_corners=False (HourGlass._forward :97-101) */
+                      int32_t stride, int32_t pad, int32_t Kpad, const float* scale, const float* shift, int32_t Wp_in, int32_t Wo_extra,
+                      void* stream);
+/* operand of the implicit 3x3 convolution: a[n, y+1, x+1, :] = act(x[n, y, x, :]) with a zero one-pixel border, both with line pitch
+ * W + 2 pixels (a has (H+2)*(W+2) rows per image; allocate 2 spare rows at the very end). Output pixel r = y*(W+2) + x' and tap
+ * (ky, kx) then read operand row r + ky*(W+2) + kx: ONE conv-mode GEMM with 2-D taps (conv_taps = 9, conv_taps_x = 3, conv_row_pitch = W+2).
+ * a_dtype as cols_dtype */
+int avi_pad_act(const float* x, int64_t x_ld, void* a, int32_t a_dtype, int32_t N, int32_t H, int32_t W, int32_t C, const float* scale,
+                const float* shift, void* stream);
+/* F.max_pool2d(x, 2, stride=2) (:86, :142); line pitches in pixels */
+int avi_maxpool2x2(const float* x, float* y, int32_t N, int32_t H, int32_t W, int32_t C, int32_t Wp_in, int32_t Wp_out, void* stream);
+/* out = up1 + bilinear upsample of low to (Ho, Wo), align_corners=False (HourGlass._forward :97-101); line pitches in pixels */
 int avi_upsample_bilinear_add(const float* low, const float* up1, float* out, int32_t N, int32_t Hi, int32_t Wi, int32_t Ho, int32_t Wo,
-                              int32_t C, void* stream);
+                              int32_t C, int32_t Wp_in, int32_t Wp_out, void* stream);
 /* in place x = act(x * scale[c] + shift[c]) (eval BatchNorm after a GEMM; scale == shift == NULL: activation only) */
 int avi_affine_act(float* x, const float* scale, const float* shift, int64_t rows, int32_t C, int32_t relu, void* stream);
 

@@ -296,3 +296,29 @@ def test_gemm_tf32_tc(ops, rows, N, K, act, use_res):
     e_t, e = (got - ref_t).abs().max().item(), (got - ref).abs().max().item()
     print(f"tf32 GEMM {rows}x{N}x{K}: max err vs truncated-operand product {e_t:.2e}, vs fp32 product {e:.2e}")
     assert e_t < 1e-4 and e < 1e-2
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tf32", "bf16"])
+def test_gemm_2d_taps_is_a_3x3_convolution(ops, mode):
+    """AviGemmArgs.conv_taps_x / conv_row_pitch: a 3x3 / pad 1 convolution over zero-bordered NHWC lines of W+2 pixels as ONE contraction
+    with 9 taps, against F.conv2d."""
+    import torch.nn.functional as F
+    r = _rng(11)
+    N, H, W, Cin, Cout = 3, 13, 10, 64, 48
+    x = torch.from_numpy(r.normal(size=(N, Cin, H, W)).astype(np.float32))
+    w = torch.from_numpy((r.normal(size=(Cout, Cin, 3, 3)) / math.sqrt(9 * Cin)).astype(np.float32))
+    dt = torch.bfloat16 if mode == "bf16" else torch.float32
+    if mode == "bf16":
+        x, w = x.bfloat16().float(), w.bfloat16().float()
+    Wp = W + 2
+    a = torch.zeros(N * (H + 2) * Wp + 2, Cin)
+    a[: N * (H + 2) * Wp].view(N, H + 2, Wp, Cin)[:, 1:H + 1, 1:W + 1] = x.permute(0, 2, 3, 1)
+    wm = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous()
+    out = torch.empty(N * H * Wp, Cout, dtype=torch.float32, device="cuda")
+    ops.gemm(a.to(dt).cuda(), wm.to(dt).cuda(), None, out, batch=N, rows=H * Wp, N=Cout, K=9 * Cin, conv_taps=9, conv_stride=1,
+             conv_taps_x=3, conv_row_pitch=Wp, a_ld=Cin, a_batch_stride=(H + 2) * Wp * Cin, a_rows_alloc=(H + 2) * Wp + 2, c_ld=Cout,
+             c_batch_stride=H * Wp * Cout, tf32=(mode == "tf32"))
+    got = out.cpu().view(N, H, Wp, Cout)[:, :, :W].permute(0, 3, 1, 2)
+    ref = F.conv2d(x.double(), w.double(), padding=1)
+    tol = {"fp32": 1e-5, "tf32": 5e-3, "bf16": 1e-4}[mode]      # bf16 operands are exact here (pre-rounded): fp32 accumulation only
+    assert (got.double() - ref).abs().max().item() < tol
