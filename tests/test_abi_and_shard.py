@@ -167,3 +167,22 @@ def test_flame_refuses_to_drop_gradients():
     with torch.no_grad():
         _refuse_grad(x)                      # fine: the caller does not expect a gradient
     _refuse_grad(torch.zeros(2, 3), None)
+
+
+def test_ctypes_struct_mirrors_the_header():
+    """AviGemmArgs in avi_talking_b200/_lib.py has the header's fields in the header's order and widths (include/avi_b200.h)."""
+    import ctypes as C
+    import re
+    src = open(_lib.HEADER_PATH).read()
+    body = re.search(r"typedef struct\s*\{(.*?)\}\s*AviGemmArgs;", src, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        m = re.match(r"(const\s+)?(void|float|int32_t|int64_t)\s*(\*?)\s*(.*)", decl)
+        ctype = C.c_void_p if m.group(3) == "*" or "*" in m.group(4) else {"int32_t": C.c_int32, "int64_t": C.c_int64}[m.group(2)]
+        for name in m.group(4).split(","):
+            fields.append((name.replace("*", "").strip(), ctype))
+    assert [(n, t) for n, t in _lib.AviGemmArgs._fields_] == fields
