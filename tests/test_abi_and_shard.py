@@ -174,7 +174,7 @@ def test_ctypes_struct_mirrors_the_header():
     import ctypes as C
     import re
     src = open(_lib.HEADER_PATH).read()
-    body = re.search(r"typedef struct\s*\{(.*?)\}\s*AviGemmArgs;", src, flags=re.S).group(1)
+    body = re.search(r"typedef struct\s+AviGemmArgs\s*\{(.*?)\}\s*AviGemmArgs;", src, flags=re.S).group(1)
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
     fields = []
     for decl in body.split(";"):
