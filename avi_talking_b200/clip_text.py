@@ -72,7 +72,7 @@ class CLIPTextModel(_HFCLIPTextModel):
         for L in P["layers"]:
             h32, h16 = ops.layernorm(x, L["ln1_w"], L["ln1_b"], want_f32=not bf16, want_bf16=bf16, eps=eps)
             qkv = ops.linear(h16 if bf16 else h32, L["qkv_w"], L["qkv_b"], out_dtype=torch.float32)
-            att, _ = ops.attn_train_fwd(qkv, B, T, H, D, bias_mode=2)                      # causal, scale 1/sqrt(D)
+            att, _ = ops.attn_train_fwd(qkv, B, T, H, D, bias_mode=2, want_p=False)       # causal, scale 1/sqrt(D)
             att = ops.cast_bf16(att) if bf16 else att
             x = ops.linear(att, L["o_w"], L["o_b"], residual=x, out_dtype=torch.float32, out=x if bf16 else None)
             h32, h16 = ops.layernorm(x, L["ln2_w"], L["ln2_b"], want_f32=not bf16, want_bf16=bf16, eps=eps)

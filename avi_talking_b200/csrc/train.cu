@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(256) attn_train_fwd_kernel(const float* __rest
   att_stage<HD>(vs, base + 2 * E, T, 3 * E);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* Pb = P + ((int64_t)b * H + h) * T * T;
+  float* Pb = P ? P + ((int64_t)b * H + h) * T * T : nullptr;   // inference callers (CLIP text tower) do not keep the probabilities
   float* qa = qs + warp * 2 * HD, *qb = qa + HD;
   float* pa = ps + warp * 2 * ATT_MAXT, *pb = pa + ATT_MAXT;
   const float slope = ff_slope(h);
@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(256) attn_train_fwd_kernel(const float* __rest
     const int j = lane + 32 * u;        // j < ATT_MAXT always: the padding up to a multiple of 4 is written as zeros
     pa[j] = sa[u] * da;
     pb[j] = sb[u] * db;
-    if (j < T) {
+    if (Pb != nullptr && j < T) {
       Pb[(int64_t)ia * T + j] = sa[u] * da;
       if (b_ok) Pb[(int64_t)ib * T + j] = sb[u] * db;
     }

@@ -572,10 +572,10 @@ def layernorm_bwd(x, w, dy, dw, db, want_dx=True, eps=1e-5):
     return dx
 
 
-def attn_train_fwd(qkv, B, T, H, D, bias_mode=0, period=1):
+def attn_train_fwd(qkv, B, T, H, D, bias_mode=0, period=1, want_p=True):
     _need_cuda(qkv)
     out = torch.empty((B * T, H * D), dtype=torch.float32, device=qkv.device)
-    P = torch.empty((B, H, T, T), dtype=torch.float32, device=qkv.device)
+    P = torch.empty((B, H, T, T), dtype=torch.float32, device=qkv.device) if want_p else None
     _chk(_lib.load().avi_attn_train_fwd(_ptr(qkv), _ptr(out), _ptr(P), C.c_int32(B), C.c_int32(T), C.c_int32(H), C.c_int32(D),
                                         C.c_float(D ** -0.5), C.c_int32(bias_mode), C.c_int32(period), _stream()), "avi_attn_train_fwd")
     return out, P

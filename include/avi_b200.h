@@ -328,7 +328,7 @@ int avi_act_bwd(const float* pre, const float* dout, float* dpre, int64_t n, int
 /* LayerNorm backward over the last dim: dx (may be NULL), dw += , db += (may be NULL; accumulate with atomics, zero them first) */
 int avi_layernorm_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, float* db, int64_t rows, int32_t C, float eps,
                       void* stream);
-/* attention for training (T <= 128): forward keeps P [B,H,T,T]; bias_mode 0 none, 1 FaceFormer biased causal mask
+/* attention for training (T <= 128): forward keeps P [B,H,T,T] (P may be NULL when no backward follows); bias_mode 0 none, 1 FaceFormer biased causal mask
  * (init_biased_mask, faceformer_vert.py via :56-77 of faceformer_disentangle.py), 2 plain causal mask (CLIP text). qkv fp32 [B,T,3*H*D] */
 int avi_attn_train_fwd(const float* qkv, float* out, float* P, int32_t B, int32_t T, int32_t H, int32_t D, float scale, int32_t bias_mode,
                        int32_t period, void* stream);
