@@ -233,7 +233,9 @@ def run_ours(args):
 
     from avi_talking_b200 import shard
     rank, local, world = shard.env_rank_world()
-    numa = shard.bind_to_gpu_numa(local)     # before any pinned allocation: host staging buffers on the GPU's own socket
+    # before any pinned allocation: host staging buffers on the GPU's own socket. Only with several ranks: the single-process run also
+    # times the CPU baseline, which must keep every host core
+    numa = shard.bind_to_gpu_numa(local) if world > 1 else {"bound": False, "why": "single process: all host cores kept"}
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
