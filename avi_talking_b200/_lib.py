@@ -9,7 +9,8 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libavi_b200.so")
+# AVI_B200_LIB: developer override (instrumented builds such as profiles/build_timeline_lib.sh); the product loads the in-tree library
+LIB_PATH = os.environ.get("AVI_B200_LIB") or os.path.join(_HERE, "libavi_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "avi_b200.h")
 
 ACT_NONE, ACT_GELU, ACT_RELU, ACT_QUICK_GELU = 0, 1, 2, 3

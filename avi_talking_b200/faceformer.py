@@ -62,6 +62,17 @@ def enc_dec_mask(device, dataset, T, S):
     return mask
 
 
+def mask_lip(img):
+    """faceformer_disentangle.py:119-133: the emotion frames are encoded WITHOUT their mouth region - image rows
+    int(100/224 * W) .. W and all columns are zeroed (upstream scales the row range by shape[3] and the column range by shape[2];
+    kept as written, it only matters for non-square frames). Pure data movement: returns a masked copy."""
+    h0, h1 = int(100. / 224. * img.shape[3]), int(224. / 224. * img.shape[3])
+    w0, w1 = int(0. / 224. * img.shape[2]), int(224. / 224. * img.shape[2])
+    out = img.clone()
+    out[:, :, h0:h1, w0:w1] = 0
+    return out
+
+
 class PeriodicPositionalEncoding(nn.Module):
     """faceformer_disentangle.py:92-107 (same ``pe`` buffer; dropout inactive in eval)."""
 
@@ -356,7 +367,7 @@ class Faceformer(nn.Module):
                 looped = loopback_frames(emotion_img, frame_num)
                 emo = []
                 for i in range(len(looped)):
-                    _, _, emo_i, _ = self.fan_net(looped[i:i + 1])
+                    _, _, emo_i, _ = self.fan_net(mask_lip(looped[i:i + 1]))                       # :791-792
                     emo.append(emo_i)
                 emo_embed = torch.concat(emo, dim=0).unsqueeze(0)
             else:
@@ -365,7 +376,7 @@ class Faceformer(nn.Module):
                 # 30-d embeddings instead of frame_num single-image calls on 224x224 images
                 from .loop_utils import calc_loop_idx
                 n_used = min(n_src, frame_num)
-                _, _, emo_src, _ = self.fan_net(emotion_img[:n_used])
+                _, _, emo_src, _ = self.fan_net(mask_lip(emotion_img[:n_used]))                    # :791-792, once per source frame
                 idx = torch.tensor([calc_loop_idx(i, n_src) for i in range(frame_num)], dtype=torch.long, device=emo_src.device)
                 emo_embed = emo_src.index_select(0, idx).unsqueeze(0)
         return self.predict_from_embeddings(audio, emo_embed)

@@ -122,8 +122,10 @@ def _import_faceformer():
 
 
 class _FanStub(nn.Module):
-    """Same 4-tuple API as FanEncoder.forward (pd_fgc_inference encoder.py:116-126). The images carry
-    the frame index in pixel [0,0,0,0]; embeddings come from oracle.synth.fan_embeddings."""
+    """Same 4-tuple API as FanEncoder.forward (pd_fgc_inference encoder.py:116-126). The images carry the frame index in pixel
+    [0,0,0,0] (row 0: never masked); embeddings come from oracle.synth.fan_embeddings and are SCALED by (1 + sum of the image rows
+    below 100/224 of the height), so an emotion frame that reaches the encoder without the reference's mask_lip (:119-133,:791)
+    changes the result."""
 
     def __init__(self, emb):
         super().__init__()
@@ -131,7 +133,8 @@ class _FanStub(nn.Module):
 
     def forward(self, img):
         i = int(round(float(img.reshape(img.shape[0], -1)[0, 0])))
-        return self.emb["head"][i:i + 1], self.emb["eye"][i:i + 1], self.emb["emo"][i:i + 1], None
+        lower = 1.0 + float(img[:, :, int(100. / 224. * img.shape[2]):, :].sum())
+        return self.emb["head"][i:i + 1], self.emb["eye"][i:i + 1], self.emb["emo"][i:i + 1] * lower, None
 
 
 def build_reference_faceformer(ffd, fd, sd_ff, sd_w2v, template, fan_emb, period=30):
@@ -156,8 +159,16 @@ def build_reference_faceformer(ffd, fd, sd_ff, sd_w2v, template, fan_emb, period
     own = {k: v for k, v in m.state_dict().items() if not k.startswith("audio_encoder.") and not k.startswith("PPE.")}
     assert set(own) == set(sd_ff), (set(own) ^ set(sd_ff))
     m.load_state_dict(sd_ff, strict=False)
-    ffd.mask_lip = lambda x: x  # image-space lip masking (cv2); the stub ignores pixel content
     return m.eval()
+
+
+def golden_frames(T):
+    """[T,3,4,4] frames: the frame index in pixel [0,0,0] and a non-zero mouth region (rows >= int(100/224*4) = 1) that the
+    reference's mask_lip must remove before the encoder sees the emotion frames."""
+    frames = torch.zeros(T, 3, 4, 4)
+    frames[:, 0, 0, 0] = torch.arange(T).float()
+    frames[:, :, 1:, :] = 0.37
+    return frames
 
 
 def golden_faceformer():
@@ -179,8 +190,7 @@ def golden_faceformer():
         T = 24
         emb = synth.fan_embeddings(T, seed=20)
         m = build_reference_faceformer(ffd, fd, sd_ff, sd_w2v, template, emb)
-        frames = torch.zeros(T, 3, 4, 4)
-        frames[:, 0, 0, 0] = torch.arange(T).float()
+        frames = golden_frames(T)
         v = m.predict(a, frames, frames, frames)                   # [1,24,15069]
         out[f"predict_fd{fd}_sub"] = v[0, :, ::COL_STRIDE].numpy()
         out[f"predict_fd{fd}_chk"] = checksum(v)
@@ -200,8 +210,7 @@ def golden_faceformer():
     T = 99
     emb = synth.fan_embeddings(T, seed=20)
     m = build_reference_faceformer(ffd, 64, sd_ff, sd_w2v, template, emb)
-    frames = torch.zeros(T, 3, 4, 4)
-    frames[:, 0, 0, 0] = torch.arange(T).float()
+    frames = golden_frames(T)
     v = m.predict(a, frames, frames, frames)
     out["predict_c1_sub"] = v[0, :, ::COL_STRIDE].numpy()
     out["predict_c1_chk"] = checksum(v)
@@ -440,7 +449,6 @@ def build_reference_faceformer_vert(ffv, fd, sd_ff, sd_w2v, flame, fan_emb, peri
            if not k.startswith(("audio_encoder.", "PPE.", "flame."))}
     assert set(own) == set(sd_ff), (set(own) ^ set(sd_ff))
     m.load_state_dict(sd_ff, strict=False)
-    ffv.mask_lip = lambda x: x
     return m.eval()          # dropout / SpecAugment / LayerDrop inactive: the step is then a deterministic function of its inputs
 
 

@@ -69,7 +69,8 @@ def lin_case(name, m, n, k, act=ACT_NONE, out_dtype=torch.bfloat16, residual=Fal
     w = rnd(n, k, scale=0.03)
     bias = rnd(n, dtype=torch.float32)
     res = rnd(m, n, dtype=torch.float32) if residual else None
-    o = torch.empty((m, n), dtype=out_dtype, device=dev)
+    # residual GEMMs update the fp32 residual stream in place (TMA reduce-add epilogue), exactly as the encoder layer calls them
+    o = res if residual else torch.empty((m, n), dtype=out_dtype, device=dev)
     fn = lambda: ops.gemm(a, w, bias, o, rows=m, N=n, K=k, act=act, residual=res, a_rows_alloc=m)  # noqa: E731
     ms = timeit(fn)
     rows.append((name, m, n, k, 2.0 * m * n * k, ms))

@@ -32,7 +32,7 @@ else:
     a, w, bias = rnd(M, k), rnd(n, k, scale=0.03), rnd(n, dtype=torch.float32)
     r = rnd(M, n, dtype=torch.float32) if res else None
     ld = 15072 if which in ("vheadp", "vhead64") else n      # 16-byte aligned vertex rows (ops.empty_rows)
-    o = torch.empty((M, ld), dtype=odt, device=dev)
+    o = r if res else torch.empty((M, ld), dtype=odt, device=dev)   # residual GEMMs update the fp32 stream in place, as in the step
     fn = lambda: ops.gemm(a, w, bias, o, rows=M, N=n, K=k, act=act, residual=r, a_rows_alloc=M, c_ld=ld)  # noqa: E731
 for _ in range(3):
     fn()

@@ -51,5 +51,9 @@ def test_fan_encoder_chunking_and_predict_integration():
     v = ff.predict(a, x, x, x)                                  # 5 source frames played ping-pong over T = 24
     from avi_talking_b200.loop_utils import calc_loop_idx
     idx = torch.tensor([calc_loop_idx(i, 5) for i in range(24)], device="cuda")
-    v2 = ff.predict_from_embeddings(a, full.index_select(0, idx)[None])
+    # the emotion frames reach the encoder without their mouth region (faceformer_disentangle.py:119-133, :791)
+    from avi_talking_b200.faceformer import mask_lip
+    masked = m(mask_lip(x))[2]
+    assert not torch.equal(masked, full)
+    v2 = ff.predict_from_embeddings(a, masked.index_select(0, idx)[None])
     assert torch.equal(v, v2)

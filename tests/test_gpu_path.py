@@ -203,22 +203,29 @@ def test_predict_api_with_fan_stub(golden):
     emb = synth.fan_embeddings(24, seed=20)
 
     class Fan(torch.nn.Module):
-        """A per-image function (what FanEncoder is in eval mode): the frame index travels in pixel [0,0,0]."""
+        """A per-image function (what FanEncoder is in eval mode): the frame index travels in pixel [0,0,0]; the emotion embedding
+        is scaled by (1 + sum of the mouth rows), which the reference's mask_lip (:119-133, :791) zeroes before the encoder."""
         calls = 0
 
         def forward(self, img):
             Fan.calls += 1
             i = img.reshape(img.shape[0], -1)[:, 0].round().long().cpu()
-            return emb["head"][i].cuda(), emb["eye"][i].cuda(), emb["emo"][i].cuda(), None
+            lower = 1.0 + img[:, :, int(100. / 224. * img.shape[2]):, :].sum(dim=(1, 2, 3))
+            return emb["head"][i].cuda(), emb["eye"][i].cuda(), emb["emo"][i].cuda() * lower[:, None], None
 
     m = build_faceformer("fp32", fd=64, seed=74)
     m.fan_net = Fan().eval()
     frames = torch.zeros(24, 3, 4, 4, device="cuda")
     frames[:, 0, 0, 0] = torch.arange(24).float()
+    frames[:, :, 1:, :] = 0.37                                        # a non-zero mouth region: mask_lip must remove it
     a = synth.audio(1, 16000, seed=1234).cuda()
     v = m.predict(a, frames, frames, frames)
     v2 = m.predict_from_embeddings(a, emb["emo"][None].cuda())
     assert torch.equal(v, v2) and Fan.calls == 1                     # ONE batched encoder call (SURVEY 8f row 1)
+    # ... and it is the reference's own predict() output on the same frames (golden minted with the real mask_lip)
+    # (same weights seed 10 + 64 = 74, audio and embeddings as oracle/make_golden.golden_faceformer's fd = 64 case)
+    assert np.abs(v[0, :, ::7].cpu().numpy() - g["predict_fd64_sub"]).max() < 1e-5
+    assert frames[:, :, 1:, :].min().item() == 0.37                  # the caller's frames are not modified (masked copy)
     # a 5-frame emotion clip played ping-pong over the 24 output frames (loop_utils.loopback_frames, golden index pattern):
     # batched-unique path (eval) == upstream's frame-by-frame path (taken for a train-mode provider)
     idx = torch.from_numpy(g["loop_idx_5_17"]).long()
