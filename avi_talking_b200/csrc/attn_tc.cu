@@ -196,9 +196,8 @@ extern "C" int avi_mha_fwd_tc(const void* qkv, void* out, int32_t B, int32_t T, 
   uint32_t box_q[2] = {AT_D, AT_BM}, box_kv[2] = {AT_D, AT_BN};
   if (encode_map(&map_q, qkv, 2, dims, strides, box_q)) return 1;
   if (encode_map(&map_kv, qkv, 2, dims, strides, box_kv)) return 1;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AT_SMEM); });
+  static SmemOptIn optin;
+  const cudaError_t attr_err = smem_optin(attn_tc_kernel, (int)AT_SMEM, optin);
   AVI_REQUIRE(attr_err == cudaSuccess, "avi_mha_fwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
   dim3 grid((T + AT_BM - 1) / AT_BM, H, B);
   attn_tc_kernel<<<grid, AT_THREADS, AT_SMEM, (cudaStream_t)stream>>>(map_q, map_kv, (__nv_bfloat16*)out, T, H,

@@ -13,7 +13,35 @@
 
 namespace avi {
 
-constexpr int kNumSMs = 148;  // B200
+constexpr int kNumSMs = 148;  // B200 (upper bound used for static sizing; launches size their grids with device_sms())
+
+// SM count of the CURRENT device, cached per device ordinal (a process may drive several GPUs: models can be moved with .to()).
+inline int device_sms() {
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return kNumSMs;
+  int n = cache[dev].load(std::memory_order_relaxed);
+  if (n == 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = kNumSMs;
+    cache[dev].store(n, std::memory_order_relaxed);
+  }
+  return n;
+}
+
+// Opt-in to more than 48 KB of dynamic shared memory. The attribute belongs to (function, DEVICE): one flag per device ordinal,
+// holding the largest size granted there. `state` is a zero-initialised static owned by the launch site (one per kernel instance).
+struct SmemOptIn {
+  std::atomic<int> granted[64];
+};
+template <typename Kernel>
+inline cudaError_t smem_optin(Kernel kernel, int bytes, SmemOptIn& state) {
+  int dev = 0;
+  const bool cacheable = cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64;
+  if (cacheable && state.granted[dev].load(std::memory_order_acquire) >= bytes) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess && cacheable) state.granted[dev].store(bytes, std::memory_order_release);
+  return e;
+}
 
 void set_error(const char* fmt, ...);
 extern std::atomic<int64_t> g_launches;

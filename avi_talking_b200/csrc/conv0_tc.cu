@@ -359,11 +359,11 @@ extern "C" int avi_w2v_conv0_gn_gelu_tc(const float* audio, const float* w, cons
   p.L0 = L0;
   p.tiles_per_clip = (L0 + CZ_BM - 1) / CZ_BM;
   p.total_tiles = p.tiles_per_clip * B;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(conv0_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CZ_SMEM); });
+  static SmemOptIn optin;
+  const cudaError_t attr_err = smem_optin(conv0_tc_kernel, (int)CZ_SMEM, optin);
   AVI_REQUIRE(attr_err == cudaSuccess, "avi_w2v_conv0_gn_gelu_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
-  const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
+  const int sms = device_sms();
+  const int grid = p.total_tiles < sms ? p.total_tiles : sms;
   conv0_tc_kernel<<<grid, CZ_THREADS, CZ_SMEM, st>>>(map_w, map_out, p);
   return check_launch("conv0_tc");
 }

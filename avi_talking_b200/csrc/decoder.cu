@@ -452,7 +452,8 @@ extern "C" int avi_ff_decoder_ar(const AviDecoderWeights* w, const float* cross,
   if (fd == A64_FD && T <= 256) {
     const size_t sm64 = sizeof(float) * (64 + 192 + 64 * 3 + 128 + 64 * 2 + 576 + 4 * (size_t)T + 4 + 2 * (size_t)T * A64_KVS);
     if (sm64 <= 227 * 1024) {
-      cudaError_t e64 = cudaFuncSetAttribute(ff_decoder_ar64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      static SmemOptIn optin64;
+      cudaError_t e64 = smem_optin(ff_decoder_ar64_kernel, 227 * 1024, optin64);
       AVI_REQUIRE(e64 == cudaSuccess, "avi_ff_decoder_ar: cudaFuncSetAttribute: %s", cudaGetErrorString(e64));
       ff_decoder_ar64_kernel<<<B, A64_THREADS, sm64, (cudaStream_t)stream>>>(*w, cross, style, hidden_out, T, period);
       return check_launch("ff_decoder_ar64");
@@ -464,7 +465,8 @@ extern "C" int avi_ff_decoder_ar(const AviDecoderWeights* w, const float* cross,
   AVI_REQUIRE(kv_in_smem || kv_scratch != nullptr, "avi_ff_decoder_ar: kv_scratch required for T=%d fd=%d", T, fd);
   const size_t smem = fixed + (kv_in_smem ? kv : 0);
   AVI_REQUIRE(smem <= 227 * 1024, "avi_ff_decoder_ar: sequence too long (T=%d)", T);
-  cudaError_t e = cudaFuncSetAttribute(ff_decoder_ar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  static SmemOptIn optin;
+  cudaError_t e = smem_optin(ff_decoder_ar_kernel, 227 * 1024, optin);
   AVI_REQUIRE(e == cudaSuccess, "avi_ff_decoder_ar: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   ff_decoder_ar_kernel<<<B, DEC_THREADS, smem, (cudaStream_t)stream>>>(*w, cross, style, hidden_out, kv_scratch, T, fd, period,
                                                                        kv_in_smem);

@@ -15,6 +15,8 @@
 // (60 276 B written per frame vs 6.7 MFLOP per frame of 16-bit tensor work).
 #include <cuda_fp16.h>
 
+#include <algorithm>
+
 #include "tc_common.cuh"
 
 namespace avi {
@@ -419,11 +421,10 @@ extern "C" int avi_flame_blend_skin_tc_grouped(const float* coef32, const float*
   p.n_ftiles = (F / frames_per_group) * p.tiles_per_group;
   const int n_chunks = (p.n_ftiles + FT_CHUNK_TILES - 1) / FT_CHUNK_TILES;
   p.n_items = p.n_vt * n_chunks;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(flame_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM); });
+  static SmemOptIn optin;
+  const cudaError_t attr_err = smem_optin(flame_tc_kernel, (int)FT_SMEM, optin);
   AVI_REQUIRE(attr_err == cudaSuccess, "avi_flame_blend_skin_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
-  const int cap = g_flame_max_ctas.load();
+  const int cap = std::min(g_flame_max_ctas.load(), device_sms());
   const int grid = p.n_items < cap ? p.n_items : cap;
   flame_tc_kernel<<<grid, FT_THREADS, FT_SMEM, st>>>(map_dirs, map_coef, p);
   return check_launch("flame_tc");

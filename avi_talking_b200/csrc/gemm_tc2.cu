@@ -16,6 +16,7 @@
 // CTA only), warps 2..17 = epilogue (TMEM lane quarter = warp_id % 4, 64-column slice = (warp_id - 2) / 4).
 // Barriers: full[s] lives in the leader (both CTAs' TMA bytes land on it), empty[s] / tmem_full[a] are multicast to both CTAs
 // by tcgen05.commit, tmem_empty[a] lives in the leader and collects the epilogue warps of both CTAs.
+#include <algorithm>
 #include <cstdlib>
 
 #include "tc_common.cuh"
@@ -482,6 +483,9 @@ static const char* tc2_check(const AviGemmArgs* a, bool tf32 = false) {
       return "a_rows_alloc smaller than the rows read";
   } else if (a->a_rows_alloc < (int64_t)(a->rows - 1) * a->conv_stride + a->conv_taps) {
     return "a_rows_alloc smaller than the rows read";
+  } else if (a->a_rows_alloc % a->conv_stride != 0) {
+    // the A tensor map counts a_rows_alloc / conv_stride super-rows: a partial last super-row would be zero-filled by TMA
+    return "a_rows_alloc must be a multiple of conv_stride (pad the time axis)";
   }
   if (a->C == nullptr) return "C is null";
   return nullptr;
@@ -490,8 +494,6 @@ static const char* tc2_check(const AviGemmArgs* a, bool tf32 = false) {
 }  // namespace avi
 
 using namespace avi;
-
-extern "C" int avi_gemm_bf16_tc_v1(const AviGemmArgs* a, void* stream);
 
 #ifdef AVI_GEMM_TIMELINE
 extern "C" int avi_debug_timeline(long long* host_out) {
@@ -582,21 +584,17 @@ static int gemm_tc2_launch(const AviGemmArgs* a, void* stream) {
     if (inplace_res) p.residual = nullptr;   // the memory system performs the addition
   }
 
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(gemm_tc2_kernel<TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P2_SMEM_BYTES);
-  });
+  static SmemOptIn optin;   // one per template instance; per-device flags inside
+  const cudaError_t attr_err = smem_optin(gemm_tc2_kernel<TF32>, (int)P2_SMEM_BYTES, optin);
   AVI_REQUIRE(attr_err == cudaSuccess, "avi_gemm_bf16_tc: cannot opt in to %u bytes of shared memory: %s", P2_SMEM_BYTES,
               cudaGetErrorString(attr_err));
-  const int pairs = p.total_tiles < kNumSMs / 2 ? p.total_tiles : kNumSMs / 2;
+  const int max_pairs = device_sms() / 2;
+  const int pairs = p.total_tiles < max_pairs ? p.total_tiles : max_pairs;
   gemm_tc2_kernel<TF32><<<2 * pairs, P2_THREADS, P2_SMEM_BYTES, (cudaStream_t)stream>>>(map_a, map_w, map_c, p);
   return check_launch(TF32 ? "gemm_tf32_tc" : "gemm_bf16_tc");
 }
 
 extern "C" int avi_gemm_bf16_tc(const AviGemmArgs* a, void* stream) {
-  static const bool use_v1 = getenv("AVI_GEMM_V1") != nullptr;
-  if (use_v1) return avi_gemm_bf16_tc_v1(a, stream);
   return gemm_tc2_launch<false>(a, stream);
 }
 

@@ -409,7 +409,8 @@ static int launch_prior(const PriorParams& p, cudaStream_t st) {
   const size_t floats = (size_t)R * PR_DIM + (size_t)PR_FF * R + (size_t)R * 2 * PR_FF + (size_t)R * 2 * PR_DH +
                         2 * (size_t)S * PR_NKEY * PR_DH + (size_t)S * PR_DIM + (size_t)2 * R * PR_INNER;
   const size_t bytes = floats * sizeof(float);
-  static cudaError_t attr_err = cudaFuncSetAttribute(prior_sample_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  static SmemOptIn optin;
+  const cudaError_t attr_err = smem_optin(prior_sample_kernel<S>, (int)bytes, optin);
   AVI_REQUIRE(attr_err == cudaSuccess, "avi_prior_sample: cannot opt in to %zu bytes of shared memory: %s", bytes,
               cudaGetErrorString(attr_err));
   prior_sample_kernel<S><<<(p.B + S - 1) / S, PR_THREADS, bytes, st>>>(p);
@@ -453,7 +454,8 @@ extern "C" int avi_prior_sample(const AviPriorNet* net, const float* temb, const
   p.depth = net->depth;
   p.out_scale = out_scale;
   int S = samples_per_cta;
-  if (S <= 0) S = (B + 3) / 4 >= kNumSMs / 2 ? 4 : ((B + 1) / 2 >= kNumSMs / 2 ? 2 : 1);  // fill the SMs before batching per CTA
+  const int half_sms = device_sms() / 2;
+  if (S <= 0) S = (B + 3) / 4 >= half_sms ? 4 : ((B + 1) / 2 >= half_sms ? 2 : 1);  // fill the SMs before batching per CTA
   if (S >= 4) return launch_prior<4>(p, (cudaStream_t)stream);
   if (S >= 2) return launch_prior<2>(p, (cudaStream_t)stream);
   return launch_prior<1>(p, (cudaStream_t)stream);

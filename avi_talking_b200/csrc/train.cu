@@ -692,8 +692,8 @@ static size_t att_smem_kv(int T, int D) { return ((size_t)2 * T * (D + ATT_PAD) 
 template <int HD>
 static int attn_fwd_launch(const float* qkv, float* out, float* P, int B, int T, int H, float scale, int bias_mode, int period,
                            cudaStream_t st) {
-  static cudaError_t attr_err = cudaFuncSetAttribute(attn_train_fwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                     (int)att_smem_fwd(ATT_MAXT, HD));
+  static SmemOptIn optin;
+  const cudaError_t attr_err = smem_optin(attn_train_fwd_kernel<HD>, (int)att_smem_fwd(ATT_MAXT, HD), optin);
   AVI_REQUIRE(attr_err == cudaSuccess, "avi_attn_train_fwd: cudaFuncSetAttribute failed");
   attn_train_fwd_kernel<HD><<<dim3(H, B, (T + ATT_ROWS - 1) / ATT_ROWS), 256, att_smem_fwd(T, HD), st>>>(qkv, out, P, T, H, scale, bias_mode,
                                                                                                         period > 0 ? period : 1);
@@ -703,10 +703,9 @@ static int attn_fwd_launch(const float* qkv, float* out, float* P, int B, int T,
 template <int HD>
 static int attn_bwd_launch(const float* qkv, const float* P, const float* dout, float* dqkv, float* dS, int B, int T, int H, float scale,
                            cudaStream_t st) {
-  static cudaError_t e1 = cudaFuncSetAttribute(attn_train_bwd_q_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               (int)att_smem_fwd(ATT_MAXT, HD));
-  static cudaError_t e2 = cudaFuncSetAttribute(attn_train_bwd_kv_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               (int)att_smem_kv(ATT_MAXT, HD));
+  static SmemOptIn optin_q, optin_kv;
+  const cudaError_t e1 = smem_optin(attn_train_bwd_q_kernel<HD>, (int)att_smem_fwd(ATT_MAXT, HD), optin_q);
+  const cudaError_t e2 = smem_optin(attn_train_bwd_kv_kernel<HD>, (int)att_smem_kv(ATT_MAXT, HD), optin_kv);
   AVI_REQUIRE(e1 == cudaSuccess && e2 == cudaSuccess, "avi_attn_train_bwd: cudaFuncSetAttribute failed");
   const dim3 grid(H, B, (T + ATT_ROWS - 1) / ATT_ROWS);
   attn_train_bwd_q_kernel<HD><<<grid, 256, att_smem_fwd(T, HD), st>>>(qkv, P, dout, dqkv, dS, T, H, scale);
@@ -772,7 +771,7 @@ extern "C" int avi_mse_loss_grad(const float* out, const float* gt, float* dout,
     set_error("avi_mse_loss_grad: memset failed");
     return 1;
   }
-  mse_loss_grad_kernel<<<kNumSMs * 4, 256, 0, (cudaStream_t)stream>>>(out, gt, dout, loss, rows, C, out_ld, gt_ld, loss_scale);
+  mse_loss_grad_kernel<<<device_sms() * 4, 256, 0, (cudaStream_t)stream>>>(out, gt, dout, loss, rows, C, out_ld, gt_ld, loss_scale);
   return check_launch("mse_loss_grad");
 }
 

@@ -525,11 +525,8 @@ extern "C" int avi_w2v_posconv_ln(const float* x, const float* w_packed, const f
   constexpr int CG = 48;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t smem = sizeof(float) * ((PC_TT + k - 1) * CG + PC_JC * CG * CG);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(posconv_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_done = true;
-  }
+  static SmemOptIn optin;
+  AVI_REQUIRE(smem_optin(posconv_kernel<CG>, (int)smem, optin) == cudaSuccess, "avi_w2v_posconv_ln: cannot opt in to %zu bytes of shared memory", smem);
   posconv_kernel<CG><<<dim3((T + PC_TT - 1) / PC_TT, groups, B), CG * 4, smem, st>>>(x, w_packed, conv_bias, out_f32, T, C, k);
   if (check_launch("posconv")) return 1;
   const int64_t rows = (int64_t)B * T;
@@ -549,12 +546,10 @@ extern "C" int avi_mha_fwd(const void* qkv, void* out, int32_t dtype, int32_t B,
                            void* stream) {
   AVI_REQUIRE(B > 0 && T > 0 && H > 0 && D == MHA_D, "avi_mha_fwd: head dim must be 64 (got %d)", D);
   const size_t smem = sizeof(float) * (MHA_KT * (MHA_D + 1) + MHA_KT * MHA_D + MHA_WARPS * MHA_RPW * MHA_D);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(mha_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(mha_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_done = true;
-  }
+  static SmemOptIn optin_f, optin_h;
+  AVI_REQUIRE(smem_optin(mha_kernel<float>, (int)smem, optin_f) == cudaSuccess &&
+                  smem_optin(mha_kernel<__nv_bfloat16>, (int)smem, optin_h) == cudaSuccess,
+              "avi_mha_fwd: cannot opt in to %zu bytes of shared memory", smem);
   dim3 grid((T + MHA_WARPS * MHA_RPW - 1) / (MHA_WARPS * MHA_RPW), H, B);
   if (dtype == AVI_DT_BF16)
     mha_kernel<__nv_bfloat16><<<grid, MHA_WARPS * 32, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)qkv,

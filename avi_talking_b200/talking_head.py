@@ -258,7 +258,7 @@ class TalkingHeadModel(nn.Module):
 
     def _neutral(self, shape):
         flame = self.sequence_decoder.flame
-        return flame.vertices_only(shape, torch.zeros(shape.shape[0], flame.cfg.n_exp, device=shape.device), None).view(shape.shape[0], -1)
+        return flame.vertices_only(shape, torch.zeros(shape.shape[0], flame.cfg.n_exp, device=shape.device), None).reshape(shape.shape[0], -1).contiguous()   # dense rows for avi_sub_add_rows (the tensor-core FLAME path returns a padded row pitch)
 
     def style_embedding(self, sample, T):
         """LinearEmotionCondition.forward (FaceFormerDecoder.py:256-267): [B,T,cond] -> [B,T,128] (fp32 GEMM: K = 43)."""

@@ -134,7 +134,8 @@ def flatten_parameters(model, layout=None):
 
 class GradBuckets:
     """Data-parallel gradient exchange: sum all-reduce of contiguous ranges of the flat gradient buffer, each launched
-    on a communication stream as soon as backward has finished the range; the optimizer divides by the world size."""
+    on a communication stream as soon as backward has finished the range. The producer scales its upstream gradient by `prescale`
+    (= 1 / world) so the reduced buffer IS the rank-averaged gradient, as DistributedDataParallel leaves it in `.grad`."""
 
     def __init__(self, layout: FlatLayout, group=None, max_buckets=8):
         self.ranges = layout.bucket_ranges(max_buckets)
@@ -146,6 +147,10 @@ class GradBuckets:
     @property
     def world(self):
         return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
+
+    @property
+    def prescale(self):
+        return 1.0 / self.world
 
     def begin(self):
         self.works, self._next = [], 0
@@ -173,7 +178,7 @@ class GradBuckets:
         if self.stream is not None:
             torch.cuda.current_stream().wait_stream(self.stream)
         self.works = []
-        return 1.0 / self.world
+        return 1.0      # the 1/world factor was folded into the upstream gradient (TrainStep.backward): the buffer holds the AVERAGE
 
 
 def shadow_tag(model):
@@ -434,8 +439,11 @@ class TrainStep:
 
     # ---------------------------------------------------------------------------- backward
     @torch.no_grad()
-    def backward(self, grad_scale=1.0):
-        """Gradient of `grad_scale * loss` into a fresh flat buffer; sets model._flat_grad and every parameter's .grad view."""
+    def backward(self, grad_scale=1.0, grad_tensor=None):
+        """Gradient of `grad_scale * loss` (times the 0-dim device tensor `grad_tensor`, if given: no host sync) into a fresh flat
+        buffer; sets model._flat_grad and every parameter's .grad view. Under data parallel the upstream gradient is pre-divided by
+        the world size, so after the SUM all-reduce `.grad` holds the rank-AVERAGED gradient (DistributedDataParallel semantics):
+        any optimizer or gradient clipping may consume it as is. Returns 1.0 (kept for callers that forward it to FlatAdam.step)."""
         S, m, lin, lay = self.saved, self.model, self.lin, self.layout
         if S is None:
             raise RuntimeError("TrainStep.backward without a forward")
@@ -450,8 +458,12 @@ class TrainStep:
         if bk is not None:
             bk.begin()
         dout = S["dout"]
+        if bk is not None:
+            grad_scale = grad_scale * bk.prescale
         if grad_scale != 1.0:
             dout = dout * grad_scale
+        if grad_tensor is not None:
+            dout = dout * grad_tensor.to(dout.dtype)
         dl = m.transformer_decoder.layers[0]
         d = "transformer_decoder.layers.0."
         V3 = dout.shape[1]
@@ -547,8 +559,8 @@ class _LossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gloss):
         step = ctx.step
-        s = float(gloss) if gloss.numel() == 1 else 1.0
-        step.grad_divisor = step.backward(grad_scale=s)
+        # the upstream gradient stays on the device (no float(gloss) host sync every step)
+        step.grad_divisor = step.backward(grad_tensor=gloss if gloss.numel() == 1 else None)
         return None, None, None, None
 
 

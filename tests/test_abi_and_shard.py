@@ -119,7 +119,8 @@ def _bucket_worker(rank, world, port, out):
         m = _tiny_vert_model()
         flat, lay = train.flatten_parameters(m)
         bk = train.GradBuckets(lay, max_buckets=4)
-        g = torch.arange(lay.total, dtype=torch.float32) * (rank + 1)         # rank r holds (r+1) * arange
+        # rank r holds (r+1) * arange, pre-divided by the world size as TrainStep.backward does with its upstream gradient
+        g = torch.arange(lay.total, dtype=torch.float32) * (rank + 1) * bk.prescale
         bk.begin()
         # backward reports progress in completion order; buckets launch as soon as their range is complete
         launched = []
@@ -145,7 +146,7 @@ def test_grad_buckets_world_size_2_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     for rank, launched, scale, err in res:
-        assert scale == 0.5 and err == 0.0                      # mean over the two ranks of (r+1)*arange = 1.5*arange
+        assert scale == 1.0 and err == 0.0                      # the buffer itself is the mean over the two ranks: 1.5*arange
         assert launched == sorted(launched) and launched[0] >= 1 and launched[-1] == 4   # overlapped: first bucket leaves early
 
 
