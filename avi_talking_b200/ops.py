@@ -57,6 +57,11 @@ def _need_cuda(*ts):
             raise RuntimeError("avi_talking_b200 ops need CUDA tensors (there is no CPU path)")
 
 
+def set_deterministic(on: bool) -> None:
+    """Bit-reproducible GEMM scheduling (no stream-K split of in-place residual GEMMs); see avi_set_deterministic in the header."""
+    _lib.check(_lib.load().avi_set_deterministic(C.c_int32(1 if on else 0)), "avi_set_deterministic")
+
+
 def cast_bf16(src: torch.Tensor, out=None) -> torch.Tensor:
     _need_cuda(src)
     src = src.contiguous().float()
@@ -216,6 +221,17 @@ def posconv_ln(x, w_packed, conv_bias, ln_w, ln_b, B, T, groups, k, want_bf16, e
                                                   _ptr(o16), C.c_int32(B), C.c_int32(T), C.c_int32(Cc), C.c_int32(groups),
                                                   C.c_int32(k), C.c_float(eps), _stream()), "avi_w2v_posconv_ln")
     return o32, o16
+
+
+def posconv_tc(xpad, w_band, bias, B, T, groups, k):
+    """Grouped positional conv (+ bias) on tcgen05, activation slab resident in shared memory: xpad bf16 [B, Tp, C] -> fp32 [B*T, C]."""
+    _need_cuda(xpad, w_band, bias)
+    Tp, Cc = xpad.shape[1], xpad.shape[2]
+    pc = torch.empty((B * T, Cc), dtype=torch.float32, device=xpad.device)
+    with _timed("posconv_tc", 2.0 * B * T * Cc * (Cc // groups) * k):
+        _lib.check(_lib.load().avi_w2v_posconv_tc(_ptr(xpad), _ptr(w_band), _ptr(bias), _ptr(pc), C.c_int32(B), C.c_int32(T), C.c_int32(Tp),
+                                                  C.c_int32(Cc), C.c_int32(groups), C.c_int32(k), _stream()), "avi_w2v_posconv_tc")
+    return pc
 
 
 def posconv_merge_ln(x, pc, ln_w, ln_b, want_bf16, eps=1e-5):

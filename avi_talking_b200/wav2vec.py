@@ -43,6 +43,20 @@ def linear_interpolation_length(t50: int, input_fps=50, output_fps=25, output_le
     return int(t50 / float(input_fps) * output_fps)
 
 
+def pack_posconv_band(w, groups):
+    """Grouped conv weight [C, 48, k] fp32 -> the bf16 operand of avi_w2v_posconv_tc, [groups/4][k][3][96][64] (include/avi_b200.h)."""
+    C, cg, k = w.shape
+    wg = w.float().reshape(groups, cg, cg, k)                  # [group, co, ci, tap]
+    band = torch.zeros(groups // 4, k, 3, 96, 64, dtype=torch.float32, device=w.device)
+    for q in range(groups // 4):
+        Wq = torch.zeros(4 * cg, 4 * cg, k, dtype=torch.float32, device=w.device)
+        for gl in range(4):
+            Wq[cg * gl:cg * (gl + 1), cg * gl:cg * (gl + 1)] = wg[4 * q + gl]
+        for i, c in enumerate((0, 2, 1)):
+            band[q, :, i] = Wq[48 * c:48 * c + 96, 64 * c:64 * c + 64].permute(2, 0, 1)
+    return ops.cast_bf16(band.contiguous())
+
+
 class Wav2Vec2Model(_HFWav2Vec2Model):
     def __init__(self, config):
         super().__init__(config)
@@ -108,16 +122,11 @@ class Wav2Vec2Model(_HFWav2Vec2Model):
         w = self._posconv_weight().float()  # [C, cg, k] -> [g][k][ci][co]
         P["pos_w"] = w.reshape(g, cg, cg, k).permute(0, 3, 2, 1).contiguous()
         P["pos_b"] = f32(self.encoder.pos_conv_embed.conv.bias)
-        if bf16 and cg == 48 and g % 4 == 0:
-            # tensor-core route: 4 groups (192 channels = 3 x 64) per GEMM with a block-diagonal weight
-            # Wq[co, j*192 + c] = w[192q + co, c - 48*(co//48), j] if c//48 == co//48 else 0   (K = taps * 192)
-            wg = w.reshape(g, cg, cg, k)                       # [group, co, ci, tap]
-            P["pos_w_bd"] = []
-            for q in range(g // 4):
-                blk = torch.zeros(4, cg, k, 4, cg, dtype=torch.float32, device=w.device)
-                for gl in range(4):
-                    blk[gl, :, :, gl, :] = wg[4 * q + gl].permute(0, 2, 1)   # [co, tap, ci]
-                P["pos_w_bd"].append(ops.cast_bf16(blk.reshape(4 * cg, k * 4 * cg).contiguous()))
+        if bf16 and cg == 48 and g % 4 == 0 and k == 128:
+            # tensor-core route (csrc/posconv_tc.cu): per quad of 4 groups (192 channels = 3 k-blocks of 64) the block-diagonal weight
+            # Wq[n, ch, j] = w[192q + n, ch % 48, j] if ch // 48 == n // 48 else 0 meets k-block c only in output columns
+            # [48c, 48c + 96): that band is packed as [quad][tap][i][96][64] with the k-blocks in stream order c = 0, 2, 1
+            P["pos_w_band"] = pack_posconv_band(w, g)
         P["enc_ln_w"], P["enc_ln_b"] = f32(self.encoder.layer_norm.weight), f32(self.encoder.layer_norm.bias)
         P["layers"] = []
         for lyr in self.encoder.layers:
@@ -161,17 +170,13 @@ class Wav2Vec2Model(_HFWav2Vec2Model):
         return h, L, La
 
     def _posconv_tc(self, proj, P, B, T):
-        """Positional grouped conv as 4 block-diagonal conv-mode GEMMs on the tcgen05 path (taps=128, window 192 channels)."""
+        """Positional grouped conv on the tcgen05 path as an implicit convolution: the zero-padded bf16 activation slab stays in shared
+        memory and the 128 taps walk it by descriptor row offset; only the non-zero band of the grouped weight is contracted."""
         cfg = self.config
-        k, Cc = cfg.num_conv_pos_embeddings, cfg.hidden_size
+        k = cfg.num_conv_pos_embeddings
         Tp = T + k                                              # rows t-64 .. t+63 around every output row, zero padded
         xpad = ops.pad_cast_bf16(proj, B, T, k // 2, Tp)
-        pc = torch.empty((B * T, Cc), dtype=torch.float32, device=proj.device)
-        for q, wq in enumerate(P["pos_w_bd"]):
-            c0 = 192 * q
-            ops.gemm(xpad[:, :, c0:], wq, P["pos_b"][c0:c0 + 192], pc[:, c0:], batch=B, rows=T, N=192, K=k * 192, conv_taps=k,
-                     conv_stride=1, a_ld=Cc, a_batch_stride=Tp * Cc, a_rows_alloc=Tp, c_ld=Cc, c_batch_stride=T * Cc,
-                     algorithmic_flops=2.0 * B * T * 192 * k * (Cc // cfg.num_conv_pos_embedding_groups))
+        pc = ops.posconv_tc(xpad, P["pos_w_band"], P["pos_b"], B, T, cfg.num_conv_pos_embedding_groups, k)
         return ops.posconv_merge_ln(proj, pc, P["enc_ln_w"], P["enc_ln_b"], want_bf16=True, eps=cfg.layer_norm_eps)
 
     def _encoder_layer(self, h32, h16, Lw, B, T, inplace=False):
@@ -211,7 +216,7 @@ class Wav2Vec2Model(_HFWav2Vec2Model):
         hn32, hn16 = ops.lerp_layernorm(feats, La * Cf, B, T50, T, P["fp_ln_w"], P["fp_ln_b"], want_f32=not bf16,
                                         want_bf16=bf16, eps=cfg.layer_norm_eps)
         proj = ops.linear(hn16 if bf16 else hn32, P["fp_w"], P["fp_b"], out_dtype=torch.float32)   # :120
-        if "pos_w_bd" in P:
+        if "pos_w_band" in P:
             h32, h16 = self._posconv_tc(proj, P, B, T)
         else:
             h32, h16 = ops.posconv_ln(proj, P["pos_w"], P["pos_b"], P["enc_ln_w"], P["enc_ln_b"], B, T,

@@ -34,7 +34,14 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--clips", type=int, default=64, help="clips per GPU per step")
+    ap.add_argument("--workload", default="predict", choices=["predict", "prior", "train"],
+                    help="predict = BASELINE configs[1]/[2] (default, the headline metric); prior = configs[3] (diffusion prior, batch 256, "
+                         "DDIM-64); train = configs[4] (faceformer_vert teacher-forced training step, DDP over the GPUs)")
+    ap.add_argument("--clips", type=int, default=None, help="clips per GPU per step (predict: 64; train: 1)")
+    ap.add_argument("--clips-total", type=int, default=None,
+                    help="predict: STRONG scaling - this many clips split over the GPUs (BASELINE configs[2]: 512 over 2/4/8)")
+    ap.add_argument("--prior-batch", type=int, default=256)
+    ap.add_argument("--prior-timesteps", type=int, default=64)
     ap.add_argument("--seconds", type=float, default=10.0)
     ap.add_argument("--fd", type=int, default=64)
     ap.add_argument("--precision", default=os.environ.get("AVI_B200_PRECISION", "bf16"), choices=["bf16", "fp32"])
@@ -102,7 +109,8 @@ class ClockSampler(threading.Thread):
 
 def workload_config(args, T, precision):
     """The `config` object: identical for the product arm and the --impl reference arm (same workload, BASELINE configs[1])."""
-    return {"workload": f"BASELINE configs[1]: FaceFormer-disentangle predict (wav2vec2 + AR decoder + vertex head) + FLAME LBS, "
+    which = "configs[1]" if args.clips_total is None else f"configs[2] ({args.clips_total} clips sharded by clip over the GPUs, strong scaling)"
+    return {"workload": f"BASELINE {which}: FaceFormer-disentangle predict (wav2vec2 + AR decoder + vertex head) + FLAME LBS, "
                         f"{args.clips} clips x {args.seconds:g} s per GPU, fd={args.fd}, random-init (seeded) weights",
             "clips_per_gpu": args.clips, "frames_per_clip": T, "precision": precision, "l2_policy": "inputs larger than L2", "launch": "eager" if getattr(args, "no_graph", False) else "cuda graph replay"}
 
@@ -214,7 +222,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "generated FLAME frames/sec", "value": val, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, T, args.precision),
         "cpu_baseline": {"value": val, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": f"each step = {clips} of the {args.clips} clips ({args.seconds:g} s each), oracle restatement of the "
@@ -373,7 +381,7 @@ def run_ours(args):
     d2h = out_host[0].numel() * 4 + flame_host[0].numel() * 4
     line = {
         "metric": "generated FLAME frames/sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": dt_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": max(args.warmup, 3), "ms_per_step": dt_ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
         "config": workload_config(args, T, args.precision),
         "realtime_factor_25fps": value / 25.0,
@@ -397,17 +405,363 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------------------------------------------- configs[3]: prior
+PRIOR_FLOP_PER_SAMPLE_STEP = 12.8e6     # one denoiser pass over the 3 tokens of one sample
+BRAIN_FLOP_PER_SAMPLE = 151e6           # BrainNetwork (768 -> 4096 x4 -> 128 + projector)
+
+
+def prior_config(args):
+    return {"workload": f"BASELINE configs[3]: diffusion prior DDIM {args.prior_timesteps}-step sampling from 768-d instruction embeddings "
+                        f"(BrainNetwork voxel2clip -> one-launch sampler), batch {args.prior_batch} per GPU, random-init (seeded) weights; "
+                        "parity of the dalle2_pytorch semantics is UNPINNED (un-vendored dependency, oracle/dalle2_standin.py)",
+            "batch_per_gpu": args.prior_batch, "timesteps": args.prior_timesteps, "precision": args.precision,
+            "l2_policy": "L2 flushed between timed iterations (256 MB write)", "launch": "eager (2 GEMM-side launches + 1 sampler launch)"}
+
+
+def run_reference_prior(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from avi_talking_b200 import synth
+    from oracle import prior_oracle as po
+    torch.set_num_threads(os.cpu_count() or 1)
+    nb = 16                                       # bounded sample: 16 of the 256 instruction embeddings per step
+    steps_ddim = args.prior_timesteps - 1 if args.prior_timesteps < 100 else args.prior_timesteps
+    inp, sd = synth.prior_inputs(nb, 100), synth.prior_state()
+    fn = lambda: po.voxel2style_emb(sd, inp["voxel"], inp["image_embed"], inp["noises"][:steps_ddim], timesteps_prior=args.prior_timesteps)  # noqa: E731
+    for _ in range(args.warmup):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fn()
+    dt = time.perf_counter() - t0
+    val = nb * args.steps / dt
+    print(json.dumps({"impl": "reference", "metric": "prior samples/sec", "value": val, "unit": "samples/s", "n_gpus": args.gpus,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+                      "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": prior_config(args),
+                      "cpu_baseline": {"value": val, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+                                       "sample": f"each step = {nb} of the {args.prior_batch} samples, oracle restatement (fp32 torch-CPU, all host threads)"},
+                      "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+
+
+def run_prior(args):
+    import torch.distributed as dist
+    from avi_talking_b200 import _lib, ops, shard, synth
+    from avi_talking_b200.diffusion_prior import voxel2style_emb
+    from avi_talking_b200.smoke import build_prior
+    rank, local, world = shard.env_rank_world()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load(check_symbols=True)
+    B, ts = args.prior_batch, args.prior_timesteps
+    n_noise = ts - 1 if ts < 100 else ts           # DDIM draws no noise on its last pair; DDPM on every step but t = 0
+    inp = synth.prior_inputs(B, 100, seed=7 + rank)
+    prior = build_prior(args.precision, device=dev)
+    host_voxel = inp["voxel"].pin_memory()
+    voxel, x0, noise = inp["voxel"].to(dev), inp["image_embed"].to(dev), inp["noises"][:n_noise].to(dev)
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)   # 256 MB > 126 MB L2
+
+    def step(v):
+        return voxel2style_emb(v, prior, timesteps_prior=ts, image_embed=x0, noise=noise)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """CUDA events around every step, the L2 flush between steps outside the events."""
+        tot = 0.0
+        for _ in range(steps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            tot += a.elapsed_time(b)
+        return tot
+
+    for _ in range(max(args.warmup, 3)):
+        step(voxel)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    n0 = _lib.launch_count()
+    dt_ms = timed(lambda: step(voxel), args.steps)
+    launches = _lib.launch_count() - n0
+    out_host = torch.empty(B, 1, 128).pin_memory()
+
+    def e2e():
+        v = host_voxel.to(dev, non_blocking=True)
+        out_host.copy_(step(v), non_blocking=True)
+
+    for _ in range(3):
+        e2e()
+    barrier()
+    e2e_ms = timed(e2e, args.steps)
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+    ops.PROFILE = []
+    step(voxel)
+    torch.cuda.synchronize()
+    prof, ops.PROFILE = ops.PROFILE, None
+    agg = {}
+    for name, a, b, work in prof:
+        d = agg.setdefault(name, [0, 0.0, 0.0])
+        d[0] += 1
+        d[1] += a.elapsed_time(b)
+        d[2] += work
+    dt_ms, e2e_ms = shard.max_over_ranks([dt_ms, e2e_ms], device=dev)
+    if rank == 0:
+        pk = peaks()
+        k = agg.get("prior_sample")
+        samp_ms = k[1] if k else dt_ms / args.steps
+        achieved = PRIOR_FLOP_PER_SAMPLE_STEP * B * n_noise / (samp_ms / 1e3) / 1e12
+        line = {"metric": "prior samples/sec", "value": world * B * args.steps / (dt_ms / 1e3), "unit": "samples/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dt_ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+                "config": prior_config(args),
+                "e2e": {"value": world * B * args.steps / (e2e_ms / 1e3), "unit": "samples/s", "h2d_bytes_per_step": host_voxel.numel() * 4,
+                        "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": e2e_ms / args.steps},
+                "gpu_launches": launches, "clocks": sampler.summary(),
+                "roofline": {"kernel": "prior_sample_kernel", "bound": "tensor", "achieved": achieved, "peak": pk["tc_burst"], "unit": "TFLOP/s",
+                             "frac": achieved / pk["tc_burst"], "traffic": None, "peak_source": pk["src"] + " (burst bf16: a kernel timed alone)",
+                             "launches_per_step": 1, "avg_launch_ms": samp_ms,
+                             "note": "the whole sampling loop is ONE launch; the denoiser is a 3-token transformer (12.8 MFLOP per "
+                                     "sample-step), so the tensor roofline is nominal: the kernel is latency / L2-weight-stream bound"},
+                "kernels_ms_per_step": {k2: {"launches": v[0], "ms": round(v[1], 4)} for k2, v in sorted(agg.items(), key=lambda kv: -kv[1][1])}}
+        if not args.no_cpu_baseline and world == 1:
+            from oracle import prior_oracle as po
+            torch.set_num_threads(os.cpu_count() or 1)
+            nb = 16
+            ci, sd = synth.prior_inputs(nb, 100), synth.prior_state()
+            t = best_of(lambda: po.voxel2style_emb(sd, ci["voxel"], ci["image_embed"], ci["noises"][:n_noise], timesteps_prior=ts))
+            line["cpu_baseline"] = {"value": nb / t, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": f"{nb} of the {B} samples, best of 2, oracle restatement (fp32 torch-CPU)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------------------------- configs[4]: train
+TRAIN_T, TRAIN_N = 120, 64000            # one VOCASET-like clip: 4 s of 16 kHz audio, 120 frames at 30 fps (SURVEY 8d)
+
+
+def train_config(args, n_par, world):
+    return {"workload": f"BASELINE configs[4]: faceformer_vert teacher-forced training step (wav2vec2 fwd+bwd with the conv extractor "
+                        f"frozen, decoder layer, 15069-wide vertex head, MSE x 10, Adam), {args.clips} clip(s) x 4 s ({TRAIN_T} frames) per GPU, "
+                        "fd=64, deterministic mode (dropout / SpecAugment / LayerDrop off), random-init (seeded) weights",
+            "clips_per_gpu": args.clips, "precision": args.precision, "trainable_params": n_par,
+            "allreduce": "bucketed NCCL sum of the flat fp32 gradient, captured in the step's CUDA graph, overlapped with backward" if world > 1 else "none",
+            "l2_policy": "working set (weights + moments + gradients = 1.5 GB) larger than L2", "launch": "eager" if args.no_graph else "cuda graph replay (forward + backward + all-reduce), Adam launched after it"}
+
+
+def train_flops(clips):
+    """Algorithmic FLOPs of one step: encoder (proj, pos-conv, 12 layers incl. attention) forward x 3 (dX and dW GEMMs), the frozen
+    conv extractor forward only, decoder + vertex head forward x 3."""
+    T50 = 199
+    conv = 0.0
+    L = (TRAIN_N - 10) // 5 + 1
+    for k in (3, 3, 3, 3, 2, 2):
+        L = (L - k) // 2 + 1
+        conv += 2.0 * L * 512 * 512 * k
+    T = TRAIN_T
+    enc = 2.0 * T * 768 * 512 + 2.0 * T * 768 * 48 * 128 + 12 * (2.0 * T * 768 * 9216 + 4.0 * T * T * 768)
+    head = 2.0 * T * 64 * 15069 * 2 + 2.0 * T * 64 * (768 + 64 * 10)
+    del T50
+    return clips * (conv + 3.0 * (enc + head))
+
+
+def run_reference_train(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from avi_talking_b200 import synth
+    from oracle import train_oracle as to
+    torch.set_num_threads(os.cpu_count() or 1)
+    fd = 64
+    sd_w2v, sd_ff = synth.wav2vec2_state(0), synth.faceformer_state(fd=fd, seed=264, variant="vert")
+    template = synth.flame_buffers()["v_template"].reshape(1, 1, 15069)
+    gt = template + 1e-3 * torch.from_numpy(np.random.default_rng(7).normal(size=(1, TRAIN_T, 15069)).astype(np.float32))
+    audio = synth.audio(1, TRAIN_N, seed=500)
+    fn = lambda: to.train_step(sd_ff, sd_w2v, template, audio, gt, lr=1e-4)  # noqa: E731
+    for _ in range(min(args.warmup, 1)):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fn()
+    dt = time.perf_counter() - t0
+    val = args.steps / dt
+    print(json.dumps({"impl": "reference", "metric": "training clips/sec", "value": val, "unit": "clips/s", "n_gpus": args.gpus, "steps": args.steps,
+                      "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+                      "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": train_config(args, None, 1),
+                      "cpu_baseline": {"value": val, "unit": "clips/s", "cores": torch.get_num_threads(), "kind": "port",
+                                       "sample": "each step = one training step (forward, autograd backward, Adam) on one 4 s / 120-frame clip, "
+                                                 "oracle restatement under torch autograd (fp32 torch-CPU, all host threads)"},
+                      "e2e": {"value": val, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+
+
+def run_train(args):
+    import torch.distributed as dist
+    from transformers import Wav2Vec2Config
+
+    from avi_talking_b200 import _lib, shard, synth, train
+    from avi_talking_b200.faceformer import FaceformerVert, make_args
+    from avi_talking_b200.wav2vec import Wav2Vec2Model
+    rank, local, world = shard.env_rank_world()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load(check_symbols=True)
+    fd, B, T, N = 64, args.clips, TRAIN_T, TRAIN_N
+    w2v = Wav2Vec2Model(Wav2Vec2Config())
+    w2v.load_state_dict(synth.wav2vec2_state(0), strict=False)
+    template = synth.flame_buffers()["v_template"].reshape(1, 1, 15069)
+    m = FaceformerVert(make_args(feature_dim=fd), audio_encoder=w2v, template=template)
+    m.load_state_dict(synth.faceformer_state(fd=fd, seed=264, variant="vert"), strict=False)
+    m.precision = w2v.precision = args.precision
+    m = m.to(dev)
+    opt = train.FlatAdam(m, lr=1e-4)
+    buckets = train.GradBuckets(m._flat_layout) if world > 1 else None
+    rng = np.random.default_rng(7 + rank)
+    host_gt = (template + 1e-3 * torch.from_numpy(rng.normal(size=(B, T, 15069)).astype(np.float32))).pin_memory()
+    host_audio = synth.audio(B, N, seed=500 + rank * B).pin_memory()
+    gt, audio = host_gt.to(dev), host_audio.to(dev)
+    if args.no_graph:
+        step = train.TrainStep(m, buckets=buckets)
+        m._train_step = step
+
+        def one_step(a, g):
+            opt.zero_grad()
+            loss = m.training_loss(a, g)
+            loss.backward()
+            opt.step()
+            return loss
+    else:
+        gstep = train.GraphedTrainStep(m, audio.shape, gt.shape, buckets=buckets)
+
+        def one_step(a, g):
+            loss = gstep(a, g)
+            opt.step()
+            return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        one_step(audio, gt)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    n0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss = one_step(audio, gt)
+    e1.record()
+    barrier()
+    dt_ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - n0
+    # end to end: the step's audio and ground-truth vertices come from pinned host memory, the loss is read back every step
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        a, g = host_audio.to(dev, non_blocking=True), host_gt.to(dev, non_blocking=True)
+        loss_host.copy_(one_step(a, g), non_blocking=True)
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    f1.record()
+    barrier()
+    e2e_ms = f0.elapsed_time(f1)
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+    # exposed exchange = this step minus the same step without the all-reduce is not separable inside a graph; report the Adam kernel
+    # (HBM-bound: 28 B per parameter) and the in-sync check instead
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    one_step(audio, gt) if args.no_graph else gstep(audio, gt)
+    a0.record()
+    opt.step()
+    a1.record()
+    torch.cuda.synchronize()
+    adam_ms = a0.elapsed_time(a1)
+    in_sync = True
+    if world > 1:
+        chk = torch.stack([m._flat_params.double().sum(), m._flat_params.double().abs().sum()])
+        hi, lo = chk.clone(), chk.clone()
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        in_sync = bool((hi == lo).all())
+    dt_ms, e2e_ms = shard.max_over_ranks([dt_ms, e2e_ms], device=dev)
+    if rank == 0:
+        pk = peaks()
+        n_par = m._flat_layout.total
+        ms = dt_ms / args.steps
+        if not args.no_graph:      # a graph replay makes no C-ABI calls: count one eager step's launches
+            st = train.TrainStep(m, buckets=None)
+            n1 = _lib.launch_count()
+            st.forward(audio, gt)
+            st.backward()
+            torch.cuda.synchronize()
+            launches = (_lib.launch_count() - n1 + 1) * args.steps
+        achieved = train_flops(B) / (ms / 1e3) / 1e12
+        line = {"metric": "training clips/sec", "value": world * B * 1e3 / ms, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic", "config": train_config(args, n_par, world),
+                "e2e": {"value": world * B * args.steps / (e2e_ms / 1e3), "unit": "clips/s", "h2d_bytes_per_step": (host_audio.numel() + host_gt.numel()) * 4,
+                        "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps},
+                "gpu_launches": launches, "clocks": sampler.summary(), "loss": float(loss.detach()), "ranks_in_sync": in_sync,
+                "roofline": {"kernel": "adam_step_kernel", "bound": "hbm", "achieved": 28.0 * n_par / (adam_ms / 1e3) / 1e9, "peak": pk["hbm"],
+                             "unit": "GB/s", "frac": 28.0 * n_par / (adam_ms / 1e3) / 1e9 / pk["hbm"], "traffic": None,
+                             "peak_source": pk["src"], "avg_launch_ms": adam_ms,
+                             "note": "batch 1 x 4 s is launch / latency bound (about 700 short kernels of 120-row operands); the one "
+                                     "bandwidth-bound kernel is Adam (28 B per parameter). Whole-step algorithmic rate below."},
+                "step_tflops_algorithmic": achieved}
+        if not args.no_cpu_baseline and world == 1:
+            from oracle import train_oracle as to
+            torch.set_num_threads(os.cpu_count() or 1)
+            sd_w2v, sd_ff = synth.wav2vec2_state(0), synth.faceformer_state(fd=fd, seed=264, variant="vert")
+            cgt = template + 1e-3 * torch.from_numpy(np.random.default_rng(7).normal(size=(1, T, 15069)).astype(np.float32))
+            t = best_of(lambda: to.train_step(sd_ff, sd_w2v, template, synth.audio(1, N, seed=500), cgt, lr=1e-4))
+            line["cpu_baseline"] = {"value": 1.0 / t, "unit": "clips/s", "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": "one training step on one 4 s clip, best of 2, oracle restatement under torch autograd (fp32 torch-CPU)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    args.scaling = "weak"
+    if args.workload == "predict":
+        if args.clips_total is not None:
+            if args.clips_total % world != 0:
+                raise SystemExit(f"--clips-total {args.clips_total} is not divisible by the {world} ranks")
+            args.clips, args.scaling = args.clips_total // world, "strong"
+        elif args.clips is None:
+            args.clips = 64
+    elif args.clips is None:
+        args.clips = 1
     if args.cpu_baseline:
         cpu_baseline_other(args.cpu_baseline)
     elif args.impl == "reference":
-        run_reference(args)
+        {"predict": run_reference, "prior": run_reference_prior, "train": run_reference_train}[args.workload](args)
     else:
         if not torch.cuda.is_available():
             raise SystemExit("bench.py needs a CUDA device for the product arm (there is no CPU fallback); "
                              "use --impl reference for the CPU reference arm")
-        run_ours(args)
+        {"predict": run_ours, "prior": run_prior, "train": run_train}[args.workload](args)
 
 
 if __name__ == "__main__":

@@ -81,6 +81,11 @@ int avi_gemm_bf16_tc(const AviGemmArgs* args, void* stream);
 /* same kernel on fp32 operands read as TF32 (tcgen05.mma.kind::tf32: 10-bit significand, fp32 accumulate; half the MMA rate).
  * a_dtype must be AVI_DT_F32; K per tap % 32 == 0, a_ld % 4 == 0, 16-byte aligned bases. */
 int avi_gemm_tf32_tc(const AviGemmArgs* args, void* stream);
+/* Bit-reproducibility switch (process-wide; default from the environment variable AVI_B200_DETERMINISTIC, else off).
+ * Off: the in-place residual GEMMs (C == residual, fp32) may split a tile's contraction between CTA pairs (stream-K), whose partial
+ * sums meet in C through fp32 reduce-add in arrival order - results agree run to run to fp32 rounding of a 3-term sum, not bit for bit.
+ * On: every output element is produced by ONE addition (whole tiles per pair): identical bits on every run and for every batching. */
+int avi_set_deterministic(int32_t on);
 /* 1 if the tensor-core path accepts these shapes (host-side check only) */
 int avi_gemm_bf16_tc_supported(const AviGemmArgs* args);
 /* fp32 -> bf16 (weights packing / activation staging), n elements */
@@ -130,6 +135,16 @@ int avi_w2v_posconv_ln(const float* x, const float* w_packed, const float* conv_
 /* second half of the above when the grouped conv itself ran as tensor-core GEMMs: out = LayerNorm(x + GELU(pc)); pc may alias out_f32 */
 int avi_w2v_posconv_merge_ln(const float* x, const float* pc, const float* ln_w, const float* ln_b, float* out_f32, void* out_bf16,
                              int64_t rows, int32_t C, float eps, void* stream);
+
+/* The grouped positional conv itself on tcgen05 with the activation slab resident in shared memory (csrc/posconv_tc.cu):
+ *   pc[b, t, co] = bias[co] + sum_{j<k} sum_{ci<48} xpad[b, t + j, 48*(co/48) + ci] * w[co, ci, j]          (fp32, [B*T, C])
+ * xpad: bf16 [B, Tp, C], Tp >= T + k - 1, rows [0, k/2) and [k/2 + T, Tp) zero (avi_pad_cast_bf16 with front = k/2);
+ * w_band: bf16 [groups/4][k][3][96][64], the non-zero band of the block-diagonal weight of each 4-group quad, channel blocks in
+ * stream order c = 0, 2, 1:  w_band[q][j][i][n][kk] = w[192q + 48c + n, (64c + kk) % 48, j] if (64c + kk) / 48 == (48c + n) / 48 else 0
+ * (packed once per weight version by the host, wav2vec.py). Built for k = 128, 48-channel groups, groups % 4 == 0 (wav2vec2-base).
+ * Replaces HF Wav2Vec2PositionalConvEmbedding.conv (reached from models/lib/wav2vec.py:142). pc is zeroed by the call. */
+int avi_w2v_posconv_tc(const void* xpad, const void* w_band, const float* bias, float* pc, int32_t B, int32_t T, int32_t Tp, int32_t C,
+                       int32_t groups, int32_t k, void* stream);
 
 /* softmax(q k^T * scale) v per (clip, head); qkv [B, T, 3*H*D] packed (q | k | v), dtype qkv_dtype; out [B, T, H*D] same dtype.
  * (HF Wav2Vec2Attention / eager_attention_forward, no mask) */

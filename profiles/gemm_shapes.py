@@ -80,15 +80,13 @@ L = 31999
 for i, (k, s) in enumerate(zip((3, 3, 3, 3, 2, 2), (2, 2, 2, 2, 2, 2)), start=1):
     L = conv_case(f"conv{i} (k={k}, s={s})", L, k, s)
 lin_case("feature projection", M, 768, 512, out_dtype=torch.float32)
-# positional conv: one of the 4 block-diagonal conv-mode GEMMs (taps 128, window 192 channels of 768)
+# positional conv: the whole grouped conv (16 groups x 48 channels, 128 taps) as the slab-resident implicit kernel; algorithmic FLOPs
 Tp = T + 128
 xpad = rnd(B, Tp, 768)
-wq = rnd(192, 128 * 192, scale=0.01)
-pc = torch.empty((M, 768), dtype=torch.float32, device=dev)
-pb = rnd(192, dtype=torch.float32)
-fn = lambda: ops.gemm(xpad[:, :, 0:], wq, pb, pc[:, 0:], batch=B, rows=T, N=192, K=128 * 192, conv_taps=128, conv_stride=1, a_ld=768,  # noqa: E731
-                      a_batch_stride=Tp * 768, a_rows_alloc=Tp, c_ld=768, c_batch_stride=T * 768)
-rows.append(("pos-conv block (x4 per step; 1/4 of the MACs are structural zeros)", M, 192, 128 * 192, 2.0 * M * 192 * 128 * 192, timeit(fn)))
+band = rnd(4, 128, 3, 96, 64, scale=0.01)
+pb = rnd(768, dtype=torch.float32)
+fn = lambda: ops.posconv_tc(xpad, band, pb, B, T, 16, 128)  # noqa: E731
+rows.append(("pos-conv (implicit, whole layer; algorithmic FLOPs)", M, 768, 48 * 128, 2.0 * M * 768 * 48 * 128, timeit(fn)))
 lin_case("encoder qkv", M, 2304, 768)
 lin_case("encoder out-proj (+res, fp32)", M, 768, 768, out_dtype=torch.float32, residual=True)
 lin_case("encoder ffn1 (GELU)", M, 3072, 768, act=ACT_GELU)

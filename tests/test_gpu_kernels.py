@@ -183,6 +183,60 @@ def test_posconv_ln(ops, T):
     assert (o16.float().cpu().double() - ref).abs().max().item() < 3e-2
 
 
+@pytest.mark.parametrize("rows,K", [(7000, 768), (15936, 3072), (20000, 512)])
+def test_gemm_inplace_residual_stream_k(ops, rows, K):
+    """The in-place residual GEMM (C += A W^T + bias through TMA reduce-add) with more tiles than CTA pairs and a mostly idle last
+    wave takes the stream-K schedule: tiles are split between pairs and their segments meet in C by fp32 reduce-add. Checked against
+    fp64 (tolerance = fp32 accumulation of K bf16 products), and against the deterministic whole-tile schedule, which must be
+    bit-reproducible run to run."""
+    r = _rng(100 + K)
+    N = 768
+    A = torch.from_numpy(r.normal(size=(rows, K)).astype(np.float32)).bfloat16().cuda()
+    W = torch.from_numpy((r.normal(size=(N, K)) / math.sqrt(K)).astype(np.float32)).bfloat16().cuda()
+    bias = torch.from_numpy(r.normal(size=N).astype(np.float32)).cuda()
+    res = torch.from_numpy(r.normal(size=(rows, N)).astype(np.float32)).cuda()
+    ref = (A.float().double() @ W.float().double().t() + bias.double() + res.double()).cpu()
+
+    def run():
+        c = res.clone()
+        ops.gemm(A, W, bias, c, rows=rows, N=N, K=K, residual=c, a_rows_alloc=rows)
+        return c
+
+    try:
+        ops.set_deterministic(False)
+        c_sk = run()
+        ops.set_deterministic(True)
+        c_d0, c_d1 = run(), run()
+    finally:
+        ops.set_deterministic(False)
+    assert torch.equal(c_d0, c_d1)
+    for c in (c_sk, c_d0):
+        assert (c.cpu().double() - ref).abs().max().item() < 2e-4
+    assert (c_sk - c_d0).abs().max().item() < 1e-5              # same products, different fp32 summation order
+
+
+@pytest.mark.parametrize("B,T", [(2, 24), (3, 249), (1, 256), (2, 300), (5, 99)])
+def test_posconv_tensor_core_implicit(ops, B, T):
+    """avi_w2v_posconv_tc (slab-resident implicit grouped conv on tcgen05, banded weight, two tap halves meeting by reduce-add) ==
+    fp64 torch conv1d(groups=16, padding=64)[..., :-1] on the bf16-rounded operands. Covers one / two time tiles per clip, T below
+    and above one CTA's 128 rows, and more units than one wave of pairs would need zero-padding for."""
+    from avi_talking_b200.wav2vec import pack_posconv_band
+    r = _rng(80 + T)
+    C, G, K = 768, 16, 128
+    x = torch.from_numpy(r.normal(size=(B, T, C)).astype(np.float32))
+    w = torch.from_numpy((r.normal(size=(C, C // G, K)) / math.sqrt(48 * 128) * 2).astype(np.float32))
+    cb = torch.from_numpy((0.02 * r.normal(size=C)).astype(np.float32))
+    xpad = ops.pad_cast_bf16(x.reshape(B * T, C).cuda(), B, T, K // 2, T + K)
+    assert torch.equal(xpad[:, K // 2:K // 2 + T].cpu(), x.bfloat16()) and float(xpad[:, :K // 2].abs().max()) == 0.0
+    band = pack_posconv_band(w.cuda(), G)
+    pc = ops.posconv_tc(xpad, band, cb.cuda(), B, T, G, K)
+    pc2 = ops.posconv_tc(xpad, band, cb.cuda(), B, T, G, K)
+    assert torch.equal(pc, pc2)                                   # two commutative additions onto zero: run-to-run identical
+    ref = F.conv1d(x.bfloat16().double().transpose(1, 2), w.bfloat16().double(), cb.double(), padding=K // 2, groups=G)[:, :, :-1]
+    err = (pc.cpu().double().view(B, T, C) - ref.transpose(1, 2)).abs().max().item()
+    assert err < 2e-4, err                                        # fp32 accumulation of 6144 bf16 products of magnitude ~ 0.03
+
+
 @pytest.mark.parametrize("T,dtype", [(24, torch.float32), (249, torch.float32), (300, torch.bfloat16), (129, torch.bfloat16),
                                      (24, torch.bfloat16), (128, torch.bfloat16), (249, torch.bfloat16), (256, torch.bfloat16)])
 def test_mha(ops, T, dtype):
