@@ -66,40 +66,7 @@ struct Tc2Params {
   int64_t c_ld, c_batch_stride, res_ld, res_batch_stride;
   int vec_ok;      // outputs (and residual) are 16-byte addressable per 32-column chunk
   int tma_store;   // 0: threads store; 1: staged tiles leave through TMA stores (map_c); 2: TMA reduce-add (C += ..., residual == C)
-  // stream-K (only with tma_store == 2, plain GEMMs, no activation): the total_tiles * num_kb k-blocks are cut into one contiguous
-  // range per pair (boundaries on multiples of sk_quantum k-blocks); a pair's range covers the tail of one tile, whole tiles, and the
-  // head of another, and every segment leaves through reduce-add into the output it shares with the other segments of its tile
-  int sk, sk_quantum;
 };
-
-// The work one pair executes, as a sequence of (tile, [kb0, kb1)) segments; all three roles walk it identically.
-struct Tc2Sched {
-  int t, kb0, kb1;
-  int g, g_end;
-};
-__device__ __forceinline__ void sched_init(Tc2Sched& s, const Tc2Params& p, int pair, int num_pairs) {
-  if (p.sk) {
-    const int64_t units = (int64_t)p.total_tiles * p.num_kb / p.sk_quantum;
-    s.g = (int)((int64_t)pair * units / num_pairs) * p.sk_quantum;
-    s.g_end = (int)((int64_t)(pair + 1) * units / num_pairs) * p.sk_quantum;
-  } else {
-    s.t = pair - num_pairs;
-  }
-}
-__device__ __forceinline__ bool sched_next(Tc2Sched& s, const Tc2Params& p, int num_pairs) {
-  if (p.sk) {
-    if (s.g >= s.g_end) return false;
-    s.t = s.g / p.num_kb;
-    s.kb0 = s.g - s.t * p.num_kb;
-    s.kb1 = min(p.num_kb, s.kb0 + (s.g_end - s.g));
-    s.g += s.kb1 - s.kb0;
-    return true;
-  }
-  s.t += num_pairs;
-  s.kb0 = 0;
-  s.kb1 = p.num_kb;
-  return s.t < p.total_tiles;
-}
 
 // TF32 = true: operands are fp32 in shared memory (32 elements per 128-byte swizzle row instead of 64), consumed by
 // tcgen05.mma.kind::tf32 (10-bit significand, fp32 accumulate): the same pipeline at half the MMA rate, for callers that need more
@@ -154,11 +121,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t full_leader = mapa_shared(smem_u32(&full_bar[0]), 0);
-      Tc2Sched sc;
-      sched_init(sc, p, pair, num_pairs);
-      int seg = 0;
-      while (sched_next(sc, p, num_pairs)) {
-        const int t = sc.t;
+      for (int t = pair; t < p.total_tiles; t += num_pairs) {
         const int n_blk = t % p.n_tiles;
         const int mt = t / p.n_tiles;
         const int b = mt / p.m_tiles, m_blk = mt % p.m_tiles;
@@ -169,11 +132,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         const int wrow0 = n_blk * P2_BN + (int)rank * (n_eff >> 1);
         // tap / phase / super-row / channel-block counters advance incrementally: this single thread paces the whole pipeline,
         // and four runtime integer divisions per k-block cost about as much as the MMAs of that k-block
-        int kin = sc.kb0, ph = 0, sr = 0, tx = 0;   // a stream-K segment starts inside the (single-tap) contraction
-        TL(0, seg, 0);
-        for (int kb = sc.kb0; kb < sc.kb1; ++kb) {
+        int kin = 0, ph = 0, sr = 0, tx = 0;
+        TL(0, (t - pair) / num_pairs, 0);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-          if (kb == sc.kb0) TL(0, seg, 1);
+          if (kb == 0) TL(0, (t - pair) / num_pairs, 1);
           const uint32_t fb_local = smem_u32(&full_bar[stage]);
           if (rank == 0) mbar_expect_tx(fb_local, 2 * P2_STAGE_BYTES);
           constexpr int BK = TF32 ? P2_BK / 2 : P2_BK;   // elements per 128-byte k-block row
@@ -195,7 +158,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             phase ^= 1;
           }
         }
-        ++seg;
       }
     }
   } else if (warp == 1) {
@@ -207,12 +169,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       const uint32_t idesc_base = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)((2 * P2_BM) >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
-      int it = -1;
-      Tc2Sched sc;
-      sched_init(sc, p, pair, num_pairs);
-      while (sched_next(sc, p, num_pairs)) {
-        ++it;
-        const int t = sc.t;
+      int it = 0;
+      for (int t = pair; t < p.total_tiles; t += num_pairs, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         const int n_eff = min(P2_BN, ((p.N - (t % p.n_tiles) * P2_BN + 31) >> 5) << 5);
@@ -222,17 +180,17 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         TL(1, it, 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * P2_BN;
-        for (int kb = sc.kb0; kb < sc.kb1; ++kb) {
+        for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(smem_u32(&full_bar[stage]), phase);
-          if (kb == sc.kb0) TL(1, it, 2);
-          if (kb == sc.kb1 - 1) TL(1, it, 3);
+          if (kb == 0) TL(1, it, 2);
+          if (kb == p.num_kb - 1) TL(1, it, 3);
           tc_fence_after();
           const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + stage * P2_A_BYTES));
           const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + stage * P2_B_BYTES));
 #pragma unroll
           for (int k = 0; k < P2_BK / P2_UMMA_K; ++k) {   // four MMAs of 32 bytes of K each (16 bf16 or 8 tf32 elements)
-            if constexpr (TF32) umma_tf32_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb != sc.kb0 || k != 0) ? 1u : 0u);
-            else umma_bf16_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb != sc.kb0 || k != 0) ? 1u : 0u);
+            if constexpr (TF32) umma_tf32_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_bf16_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit_pair(smem_u32(&empty_bar[stage]), 3);  // frees the slot in BOTH CTAs once these MMAs have read it
           if (++stage == P2_STAGES) {
@@ -260,12 +218,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const bool ragged_f32 = !p.vec_ok && p.c_dtype == AVI_DT_F32 && p.C2 == nullptr && p.residual == nullptr;
     const uint32_t te_leader0 = mapa_shared(smem_u32(&tmem_empty[0]), 0);
     const uint32_t te_leader1 = mapa_shared(smem_u32(&tmem_empty[1]), 0);
-    int it = -1;
-    Tc2Sched sc;
-    sched_init(sc, p, pair, num_pairs);
-    while (sched_next(sc, p, num_pairs)) {
-      ++it;
-      const int t = sc.t;
+    int it = 0;
+    for (int t = pair; t < p.total_tiles; t += num_pairs, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int n_blk = t % p.n_tiles;
@@ -276,8 +230,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       if (ew == 0 && lane == 0) TL(2, it, 0);
       if (etid < P2_BN) {
         const int n = n0 + etid;
-        // (of the stream-K segments of one tile, the one that starts the contraction carries the bias)
-        sts32(sbias_a + etid * 4, __float_as_uint((p.bias != nullptr && n < p.N && sc.kb0 == 0) ? __ldg(p.bias + n) : 0.f));
+        sts32(sbias_a + etid * 4, __float_as_uint((p.bias != nullptr && n < p.N) ? __ldg(p.bias + n) : 0.f));
       }
       asm volatile("bar.sync 1, %0;" ::"n"(P2_EPI_THREADS) : "memory");
       if (ew == 0 && lane == 0) TL(2, it, 1);
@@ -511,17 +464,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   }
 }
 
-static std::atomic<int> g_deterministic{-1};
-static bool deterministic_mode() {
-  int v = g_deterministic.load(std::memory_order_relaxed);
-  if (v < 0) {
-    const char* e = getenv("AVI_B200_DETERMINISTIC");
-    v = (e != nullptr && e[0] != '\0' && e[0] != '0') ? 1 : 0;
-    g_deterministic.store(v, std::memory_order_relaxed);
-  }
-  return v != 0;
-}
-
 static const char* tc2_check(const AviGemmArgs* a, bool tf32 = false) {
   if (!a) return "null args";
   if (a->a_dtype != (tf32 ? AVI_DT_F32 : AVI_DT_BF16)) return tf32 ? "A/W must be fp32" : "A/W must be bf16";
@@ -558,11 +500,6 @@ extern "C" int avi_debug_timeline(long long* host_out) {
   return cudaMemcpyFromSymbol(host_out, g_timeline, sizeof(long long) * 3 * 64 * 8) == cudaSuccess ? 0 : 1;
 }
 #endif
-
-extern "C" int avi_set_deterministic(int32_t on) {
-  g_deterministic.store(on ? 1 : 0, std::memory_order_relaxed);
-  return 0;
-}
 
 extern "C" int avi_gemm_bf16_tc_supported(const AviGemmArgs* a) { return tc2_check(a) == nullptr ? 1 : 0; }
 
@@ -647,17 +584,6 @@ static int gemm_tc2_launch(const AviGemmArgs* a, void* stream) {
     if (inplace_res) p.residual = nullptr;   // the memory system performs the addition
   }
 
-  // stream-K for the in-place residual GEMMs whose tile count leaves the last wave of pairs mostly idle (out-proj / ffn2: 189 tiles on
-  // 74 pairs = 2.55 waves). The segments of one tile meet through reduce-add, so the two or three fp32 additions per element happen in
-  // arrival order: results are reproducible to fp32 rounding, not bit for bit - avi_set_deterministic(1) keeps whole tiles.
-  const int max_pairs_sk = device_sms() / 2;
-  p.sk = 0;
-  p.sk_quantum = (p.num_kb % 4 == 0) ? 4 : (p.num_kb % 2 == 0 ? 2 : 1);
-  if (p.tma_store == 2 && a->conv_taps == 1 && a->act == AVI_ACT_NONE && !deterministic_mode() && p.total_tiles > max_pairs_sk &&
-      p.num_kb >= 8) {
-    const int rem = p.total_tiles % max_pairs_sk;
-    if (rem != 0 && rem * 10 < max_pairs_sk * 8) p.sk = 1;   // last wave less than 80 % full
-  }
   static SmemOptIn optin;   // one per template instance; per-device flags inside
   const cudaError_t attr_err = smem_optin(gemm_tc2_kernel<TF32>, (int)P2_SMEM_BYTES, optin);
   AVI_REQUIRE(attr_err == cudaSuccess, "avi_gemm_bf16_tc: cannot opt in to %u bytes of shared memory: %s", P2_SMEM_BYTES,

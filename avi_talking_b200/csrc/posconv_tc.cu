@@ -18,6 +18,8 @@
 //   * the two tap halves of a tile are separate units (keeps 74 pairs evenly loaded: 512 units at 64 clips) that meet in the
 //     fp32 output through TMA reduce-add (the output is zeroed by the launch; two commutative additions onto zero: deterministic).
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (leader CTA), warps 2..9 = epilogue.
+#include <cstdlib>
+
 #include "tc_common.cuh"
 
 namespace avi {
@@ -42,7 +44,17 @@ static_assert(2 * PI_WSTAGES + 8 <= 31, "barrier block");
 struct PosconvParams {
   const float* bias;   // [C]
   int B, T, m_tiles, n_quads, total_units;
+  int dbg;             // developer experiments (AVI_PC_DBG, timeline builds only): 1 = every tap reads slab row 0 (wrong result, timing only)
 };
+
+#ifdef AVI_GEMM_TIMELINE
+// per unit of pair 0: [0] MMA start, [1] MMA end (issue), [2] cycles the MMA thread waited on full[], [3] cycles the producer waited on empty[],
+// [4] epilogue start, [5] epilogue end
+__device__ long long g_pc_timeline[16][8];
+#define PTL(unit, slot, val) do { if (blockIdx.x == 0 && (unit) < 16) g_pc_timeline[unit][slot] = (val); } while (0)
+#else
+#define PTL(unit, slot, val) do { } while (0)
+#endif
 
 __device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, int c2) {
   asm volatile(
@@ -138,11 +150,18 @@ posconv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         const PiUnit un = pi_decode(u, p);
         // weight stream rows: ((q * 128 + j) * 3 + i) * 96 + rank * 48, j = h * 64 + jj
         int wrow = ((un.q * PI_TAPS + un.h * PI_UT) * 3) * PI_NB + (int)rank * PI_NBH;
+        long long waited = 0;
         for (int kb = 0; kb < KB_PER_UNIT; ++kb) {
           // the next unit's slab is requested a third of the way through this unit (its buffer was released when the previous unit's
           // MMAs retired), so it lands long before the MMA issuer needs it
           if (kb == KB_PER_UNIT / 3 && u + num_pairs < p.total_units) issue_slab(u + num_pairs, it + 1);
+#ifdef AVI_GEMM_TIMELINE
+          const long long w0 = clock64();
+#endif
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+#ifdef AVI_GEMM_TIMELINE
+          waited += clock64() - w0;
+#endif
           if (rank == 0) mbar_expect_tx(smem_u32(&full_bar[stage]), 2 * PI_W_BYTES);
           tma_load_2d_pair(smem_u32(wring + stage * PI_W_BYTES), &map_w, full_leader + stage * 8, 0, wrow);
           wrow += PI_NB;
@@ -151,6 +170,7 @@ posconv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
             phase ^= 1;
           }
         }
+        PTL(it, 3, waited);
       }
     }
   } else if (warp == 1) {
@@ -168,15 +188,24 @@ posconv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * PI_NQ;
         const uint64_t slab_desc = umma_desc_sw128(smem_u32(slab + sb * PI_SLAB_BYTES));
+        long long waited = 0;
+        PTL(it, 0, clock64());
         for (int jj = 0; jj < PI_UT; ++jj) {
 #pragma unroll
           for (int i = 0; i < 3; ++i) {
             // stream order of the channel blocks is c = 0, 2, 1: at tap 0 the first two MMAs INITIALISE columns [0,96) and [96,192)
             // (accumulate = 0), the third (c = 1, columns [48,144)) and everything after accumulate
             const int c = (i == 0) ? 0 : (i == 1 ? 2 : 1);
+#ifdef AVI_GEMM_TIMELINE
+            const long long w0 = clock64();
+#endif
             mbar_wait(smem_u32(&full_bar[stage]), phase);
+#ifdef AVI_GEMM_TIMELINE
+            waited += clock64() - w0;
+#endif
             tc_fence_after();
-            const uint64_t adesc = slab_desc + (uint64_t)((c * PI_SLAB_C_BYTES + jj * 128) >> 4);   // tap jj = rows jj.. of the slab
+            const int row_off = (p.dbg & 1) ? 0 : jj;
+            const uint64_t adesc = slab_desc + (uint64_t)((c * PI_SLAB_C_BYTES + row_off * 128) >> 4);   // tap jj = rows jj.. of the slab
             const uint64_t bdesc = umma_desc_sw128(smem_u32(wring + stage * PI_W_BYTES));
 #pragma unroll
             for (int k = 0; k < 4; ++k)
@@ -188,6 +217,8 @@ posconv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
             }
           }
         }
+        PTL(it, 1, clock64());
+        PTL(it, 2, waited);
         umma_commit_pair(smem_u32(&slab_empty[sb]), 3);   // both CTAs' slabs may be overwritten once these MMAs have read them
         umma_commit_pair(smem_u32(&tmem_full[as]), 3);
       }
@@ -214,6 +245,7 @@ posconv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       if (lane == 0) mbar_wait(smem_u32(&tmem_full[as]), aphase);
       __syncwarp();
       tc_fence_after();
+      if (ew == 0 && lane == 0) PTL(it, 4, clock64());
       const int row_base = un.m_blk * (2 * PI_BM) + (int)rank * PI_BM + quarter * 32;
       if (row_base < p.T) {
 #pragma unroll 1
@@ -243,6 +275,7 @@ posconv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
           }
         }
       }
+      if (ew == 0 && lane == 0) PTL(it, 5, clock64());
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(as ? te_leader1 : te_leader0);
@@ -261,6 +294,12 @@ posconv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 }  // namespace avi
 
 using namespace avi;
+
+#ifdef AVI_GEMM_TIMELINE
+extern "C" int avi_debug_posconv_timeline(long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, g_pc_timeline, sizeof(long long) * 16 * 8) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 extern "C" int avi_w2v_posconv_tc(const void* xpad, const void* w_band, const float* bias, float* pc, int32_t B, int32_t T, int32_t Tp,
                                   int32_t C, int32_t groups, int32_t k, void* stream) {
@@ -297,6 +336,10 @@ extern "C" int avi_w2v_posconv_tc(const void* xpad, const void* w_band, const fl
   p.m_tiles = (T + 2 * PI_BM - 1) / (2 * PI_BM);
   p.n_quads = n_quads;
   p.total_units = PI_KSPLIT * n_quads * B * p.m_tiles;
+  p.dbg = 0;
+#ifdef AVI_GEMM_TIMELINE
+  if (const char* e = getenv("AVI_PC_DBG")) p.dbg = atoi(e);
+#endif
   // the tap halves meet in the output through reduce-add
   cudaError_t me = cudaMemsetAsync(pc, 0, (size_t)B * T * C * sizeof(float), st);
   AVI_REQUIRE(me == cudaSuccess, "avi_w2v_posconv_tc: cudaMemsetAsync: %s", cudaGetErrorString(me));

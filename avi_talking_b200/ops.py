@@ -57,11 +57,6 @@ def _need_cuda(*ts):
             raise RuntimeError("avi_talking_b200 ops need CUDA tensors (there is no CPU path)")
 
 
-def set_deterministic(on: bool) -> None:
-    """Bit-reproducible GEMM scheduling (no stream-K split of in-place residual GEMMs); see avi_set_deterministic in the header."""
-    _lib.check(_lib.load().avi_set_deterministic(C.c_int32(1 if on else 0)), "avi_set_deterministic")
-
-
 def cast_bf16(src: torch.Tensor, out=None) -> torch.Tensor:
     _need_cuda(src)
     src = src.contiguous().float()

@@ -57,7 +57,7 @@ def build_talking_head(precision: str = "fp32", device: str = "cuda", flame_dir:
     fcfg = synth.write_flame_assets(flame_dir)
     fcfg.n_shape, fcfg.n_exp = synth.EMOTE.n_shape, synth.EMOTE.n_exp
     flame = FLAME(fcfg)
-    m = TalkingHeadWrapper(w2v, flame, emote_cfg(n_identities=synth.EMOTE.n_identities))
+    m = TalkingHeadWrapper.from_parts(w2v, flame, emote_cfg(n_identities=synth.EMOTE.n_identities))
     missing, unexpected = m.talking_head_model.load_state_dict(synth.emote_state(), strict=False)
     assert not unexpected, unexpected
     assert all(k.startswith("audio_model.") or ".flame." in k for k in missing), missing

@@ -143,14 +143,186 @@ class BertPriorDecoder(nn.Module):
         return self.motion_prior.get_flame()
 
 
-def emote_cfg(n_identities=32, n_expression=8, n_intensities=3):
-    """The slice of the EMOTE cfg.yaml the callers read (bertprior_wild.yaml)."""
-    style = SimpleNamespace(type="emotion_linear", n_expression=n_expression, n_intensities=n_intensities, n_identities=n_identities,
-                            gt_expression_label=True, gt_expression_intensity=True, gt_expression_identity=True, use_bias=True)
-    dec = SimpleNamespace(type="BertPriorDecoder", feature_dim=128, nhead=8, num_layers=1, activation="gelu", post_bug_fix=True,
-                          squash_after=True, squash_type="stack_linear", style_op="add", style_embedding=style)
-    data = SimpleNamespace(data_class="MEADPseudo3DDM", split="random_by_identityV2_sorted_70_15_15", reconstruction_type=["EMICA-MEAD_flame2020"])
-    return SimpleNamespace(model=SimpleNamespace(sequence_decoder=dec), data=data)
+class AttrDict(dict):
+    """cfg.yaml as the callers read it: nested attribute AND item access (the reference uses an OmegaConf DictConfig, which is not a
+    dependency here; `cfg.model.sequence_decoder.style_embedding.n_identities`, `cfg.data.split`, `cfg.learning.losses = {}` all work)."""
+
+    def __init__(self, d=None):
+        super().__init__()
+        for k, v in (d or {}).items():
+            self[k] = v
+
+    @staticmethod
+    def _wrap(v):
+        if isinstance(v, dict) and not isinstance(v, AttrDict):
+            return AttrDict(v)
+        if isinstance(v, (list, tuple)):
+            return type(v)(AttrDict._wrap(x) for x in v)
+        return v
+
+    def __setitem__(self, k, v):
+        super().__setitem__(k, AttrDict._wrap(v))
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+    def to_dict(self):
+        return {k: (v.to_dict() if isinstance(v, AttrDict) else v) for k, v in self.items()}
+
+
+def emote_cfg(n_identities=32, n_expression=8, n_intensities=3, flame=None, checkpoint_dir=None):
+    """The slice of the EMOTE cfg.yaml this path reads (talkinghead_conf/bertprior_wild.yaml and its model/* groups): decoder sizes and
+    style embedding, the audio model specifier, FLAME asset paths (`flame`: an object with flame_model_path / flame_lmk_embedding_path /
+    n_shape / n_exp) and inout.checkpoint_dir."""
+    style = dict(type="emotion_linear", n_expression=n_expression, n_intensities=n_intensities, n_identities=n_identities,
+                 gt_expression_label=True, gt_expression_intensity=True, gt_expression_identity=True, use_bias=True)
+    dec = dict(type="BertPriorDecoder", feature_dim=128, nhead=8, num_layers=1, activation="gelu", post_bug_fix=True,
+               squash_after=True, squash_type="stack_linear", style_op="add", style_embedding=style)
+    if flame is not None:
+        dec["flame"] = dict(flame_model_path=str(flame.flame_model_path), flame_lmk_embedding_path=str(flame.flame_lmk_embedding_path),
+                            n_shape=int(flame.n_shape), n_exp=int(flame.n_exp))
+    data = dict(data_class="MEADPseudo3DDM", split="random_by_identityV2_sorted_70_15_15", reconstruction_type=["EMICA-MEAD_flame2020"])
+    cfg = dict(model=dict(sequence_decoder=dec, audio=dict(type="wav2vec2", model_specifier="facebook/wav2vec2-base-960h", trainable=True),
+                          sequence_encoder=dict(type="LinearSequenceEncoder", feature_dim=128)),
+               data=data, learning=dict(losses={}, metrics={}), inout=dict(checkpoint_dir=checkpoint_dir or "checkpoints"))
+    return AttrDict(cfg)
+
+
+# ------------------------------------------------------------------------------------------------ checkpoint directories
+def get_path_to_assets():
+    """inferno/utils/other.py get_path_to_assets: the directory relative checkpoint_dirs are resolved against (INFERNO_ASSETS, else
+    ./assets)."""
+    from pathlib import Path
+    return Path(os.environ.get("INFERNO_ASSETS", "assets"))
+
+
+def locate_checkpoint(cfg_or_checkpoint_dir, replace_root=None, relative_to=None, mode=None, pattern=None):
+    """inferno/models/IO.py:26-90, same contract: the checkpoint file chosen from `cfg.inout.checkpoint_dir` (or a directory given
+    directly) - mode 'latest' = the first *.ckpt in sorted order, which must be called last.ckpt; 'best' = the smallest value after the
+    last '=' of the file stem; an int indexes the sorted list. Returns None when nothing qualifies (upstream prints and returns None)."""
+    from pathlib import Path
+    checkpoint_dir = str(cfg_or_checkpoint_dir) if isinstance(cfg_or_checkpoint_dir, (str, Path)) else cfg_or_checkpoint_dir.inout.checkpoint_dir
+    if replace_root is not None and relative_to is not None:
+        try:
+            checkpoint_dir = str(Path(replace_root) / Path(checkpoint_dir).relative_to(relative_to))
+        except ValueError:
+            pass
+    if not Path(checkpoint_dir).is_absolute():
+        checkpoint_dir = str(get_path_to_assets() / checkpoint_dir)
+    checkpoints = sorted(Path(checkpoint_dir).rglob("*.ckpt"))
+    if pattern is not None:
+        checkpoints = [c for c in checkpoints if pattern in str(c)]
+    if not checkpoints:
+        return None
+    if isinstance(mode, int):
+        return str(checkpoints[mode])
+    if mode == "latest":
+        return str(checkpoints[0]) if checkpoints[0].name == "last.ckpt" else None
+    if mode == "best":
+        best, best_val = None, float("inf")
+        for c in checkpoints:
+            if c.stem == "last":
+                continue
+            try:
+                val = float(c.stem[c.stem.rfind("=") + 1:])
+            except ValueError:
+                continue
+            if val <= best_val:
+                best, best_val = c, val
+        if best is None:
+            raise FileNotFoundError("Finding the best checkpoint failed")
+        return str(best)
+    raise ValueError(f"Invalid checkpoint loading mode '{mode}'")
+
+
+def _load_cfg_yaml(path):
+    import yaml
+    with open(path) as fh:
+        return AttrDict(yaml.safe_load(fh))
+
+
+def _flame_from_cfg(cfg, run_path):
+    """FLAME(n_shape, n_exp) for the decoder: asset paths from cfg.model.sequence_decoder.flame (bertprior_wild.yaml:38-44), else from
+    cfg.model.preprocessor.flame (preprocessor/flame_tex.yaml). Relative paths are tried against the run directory and the assets root."""
+    from pathlib import Path
+
+    from .flame import FLAME
+    fc = None
+    for holder in (cfg.model.get("sequence_decoder", {}), cfg.model.get("preprocessor", {})):
+        if isinstance(holder, dict) and isinstance(holder.get("flame"), dict):
+            fc = holder["flame"]
+            break
+    if fc is None:
+        raise KeyError("cfg.yaml has no FLAME section (model.sequence_decoder.flame / model.preprocessor.flame)")
+
+    def resolve(p):
+        p = Path(p)
+        for cand in ([p] if p.is_absolute() else [Path(run_path) / p, get_path_to_assets() / p, p]):
+            if cand.exists():
+                return str(cand)
+        raise FileNotFoundError(f"FLAME asset '{p}' named by cfg.yaml does not exist (looked under the run directory and "
+                                f"{get_path_to_assets()}; set INFERNO_ASSETS)")
+
+    return FLAME(SimpleNamespace(flame_model_path=resolve(fc["flame_model_path"]),
+                                 flame_lmk_embedding_path=resolve(fc["flame_lmk_embedding_path"]),
+                                 n_shape=int(fc.get("n_shape", 300)), n_exp=int(fc.get("n_exp", 50))))
+
+
+def _audio_from_cfg(cfg, state_dict):
+    """The wav2vec2 encoder named by cfg.model.audio.model_specifier (AudioEncoders.py:130-166). Its weights are in the checkpoint (the
+    EMOTE audio model is trainable); the hub is only asked for the ARCHITECTURE, and only from the local cache (no network needed)."""
+    from transformers import Wav2Vec2Config
+    spec = cfg.model.get("audio", {}).get("model_specifier", "facebook/wav2vec2-base-960h")
+    try:
+        config = Wav2Vec2Config.from_pretrained(spec, local_files_only=True)
+    except Exception:  # noqa: BLE001 - not cached: the named model must then be the base architecture the checkpoint tensors describe
+        config = Wav2Vec2Config()
+        n_layers = 1 + max((int(k.split(".")[4]) for k in state_dict if k.startswith("audio_model.model.encoder.layers.")), default=-1)
+        width = next((v.shape[0] for k, v in state_dict.items() if k == "audio_model.model.encoder.layer_norm.weight"), config.hidden_size)
+        if (n_layers and n_layers != config.num_hidden_layers) or width != config.hidden_size:
+            raise RuntimeError(f"'{spec}' is not in the local transformers cache and the checkpoint is not wav2vec2-base shaped "
+                               f"({n_layers} layers, width {width}); cache the model's config.json first")
+    return Wav2Vec2Model(config)
+
+
+def load_model(path_to_models, run_name, mode="latest", with_losses=True):
+    """inferno_apps/TalkingHead/utils/load.py:28-61 (load_model + load_faceformer + LightningModule.load_from_checkpoint(strict=False)):
+    reads <path_to_models>/<run_name>/cfg.yaml, locates the checkpoint, builds the model the config describes and loads the
+    checkpoint's `state_dict`. Returns (model, cfg). Where upstream calls sys.exit(0) for a missing checkpoint this raises."""
+    from pathlib import Path
+    run_path = Path(path_to_models) / run_name
+    cfg = _load_cfg_yaml(run_path / "cfg.yaml")
+    if not with_losses:
+        cfg.setdefault("learning", AttrDict())
+        cfg.learning.losses = {}
+        cfg.learning.metrics = {}
+    ckpt_dir = Path(str(cfg.inout.checkpoint_dir))
+    checkpoint = locate_checkpoint(cfg, mode=mode) if (ckpt_dir.is_absolute() and ckpt_dir.exists()) or (get_path_to_assets() / ckpt_dir).exists() else None
+    if checkpoint is None:     # released runs carry paths of the training cluster: fall back to the run directory itself
+        checkpoint = locate_checkpoint(run_path, mode=mode)
+    if checkpoint is None:
+        raise FileNotFoundError(f"no '{mode}' checkpoint (*.ckpt; 'latest' needs last.ckpt first in sorted order) under "
+                                f"'{cfg.inout.checkpoint_dir}' or '{run_path}'")
+    blob = torch.load(checkpoint, map_location="cpu", weights_only=False)
+    state = blob["state_dict"] if isinstance(blob, dict) and "state_dict" in blob else blob
+    dec_type = cfg.model.sequence_decoder.get("type")
+    if dec_type != "BertPriorDecoder":
+        raise NotImplementedError(f"sequence_decoder.type '{dec_type}': only the EMOTE BertPriorDecoder stack is built")
+    model = TalkingHeadModel(cfg, _audio_from_cfg(cfg, state), _flame_from_cfg(cfg, run_path))
+    # strict=False as upstream (TalkingHead/utils/load.py:60): renderer / loss / texture tensors of the checkpoint have no module here.
+    # What must NOT be missing are this model's own trainable tensors.
+    missing, unexpected = model.load_state_dict(state, strict=False)
+    own_missing = [k for k in missing if ".flame." not in k and not k.endswith("num_batches_tracked")]
+    if own_missing:
+        raise RuntimeError(f"checkpoint '{checkpoint}' lacks {len(own_missing)} tensors of the talking-head model, e.g. {own_missing[:5]}")
+    model.checkpoint_path, model.unexpected_keys = checkpoint, unexpected
+    return model, cfg
 
 
 # ------------------------------------------------------------------------------------------------ the model
@@ -346,19 +518,41 @@ class TalkingHeadModel(nn.Module):
 
 
 class TalkingHeadWrapper(nn.Module):
-    """inferno_apps/TalkingHead/evaluation/TalkingHeadWrapper.py:76-138 with ``render_results=False``. Instead of a checkpoint
-    directory (absent upstream assets) the constructor takes the assembled parts; ``load_state_dict`` accepts EMOTE weights."""
+    """inferno_apps/TalkingHead/evaluation/TalkingHeadWrapper.py:76-138, same constructor: ``TalkingHeadWrapper(path_to_model,
+    render_results=False)`` opens the run directory (cfg.yaml + a Lightning ``last.ckpt``) exactly as train_diffusion_prior.py:954-958
+    does. Rendering is out of scope: ``render_results=True`` (the upstream default) raises - the inference script passes False.
+    ``TalkingHeadWrapper.from_parts(audio_encoder, flame, cfg)`` assembles the same object from modules already in memory."""
 
-    def __init__(self, audio_encoder: Wav2Vec2Model, flame, cfg=None, render_results=False, use_preprocessor=True, apply_mask=True):
+    def __init__(self, path_to_model, render_results=True, use_preprocessor=True, apply_mask=True):
         super().__init__()
         if render_results:
-            raise NotImplementedError("rendering is out of scope (the reference's inference script passes render_results=False)")
-        self.dim = 128
+            raise NotImplementedError("rendering (FixedViewFlameRenderer / pytorch3d) is out of scope of the audio -> FLAME path; "
+                                      "construct with render_results=False as train_diffusion_prior.py:956 does")
+        from pathlib import Path
+        self.dim = 128                 # style-code width of EMOTE (TalkingHeadWrapper.py:80)
         self.self_cond = None
+        path_to_model = Path(path_to_model)
+        self.talking_head_model, self.cfg = load_model(path_to_model.parent, path_to_model.name, mode="latest", with_losses=False)
+        self.talking_head_model.eval()
+        self.renderer = None
+        self.render_results, self.use_preprocessor, self.apply_mask = render_results, use_preprocessor, apply_mask
+
+    @classmethod
+    def from_parts(cls, audio_encoder: Wav2Vec2Model, flame, cfg=None, use_preprocessor=True, apply_mask=True):
+        """The same wrapper around modules already in memory (no run directory): tests, smoke, benchmarks with synthetic weights."""
+        self = cls.__new__(cls)
+        nn.Module.__init__(self)
+        self.dim, self.self_cond = 128, None
         self.cfg = cfg if cfg is not None else emote_cfg()
         self.talking_head_model = TalkingHeadModel(self.cfg, audio_encoder, flame)
         self.renderer = None
-        self.render_results, self.use_preprocessor, self.apply_mask = render_results, use_preprocessor, apply_mask
+        self.render_results, self.use_preprocessor, self.apply_mask = False, use_preprocessor, apply_mask
+        return self
+
+    def set_neutral_mesh(self, neutral_v):
+        """TalkingHeadWrapper.py:140-158: overwrite the FLAME template in place (every FLAME instance of the reference's model; here
+        the decoder, the motion prior and the preprocessor share ONE)."""
+        self.talking_head_model.sequence_decoder.get_shape_model().v_template[...] = neutral_v
 
     def get_num_intensities(self):
         return self.cfg.model.sequence_decoder.style_embedding.n_intensities

@@ -81,11 +81,6 @@ int avi_gemm_bf16_tc(const AviGemmArgs* args, void* stream);
 /* same kernel on fp32 operands read as TF32 (tcgen05.mma.kind::tf32: 10-bit significand, fp32 accumulate; half the MMA rate).
  * a_dtype must be AVI_DT_F32; K per tap % 32 == 0, a_ld % 4 == 0, 16-byte aligned bases. */
 int avi_gemm_tf32_tc(const AviGemmArgs* args, void* stream);
-/* Bit-reproducibility switch (process-wide; default from the environment variable AVI_B200_DETERMINISTIC, else off).
- * Off: the in-place residual GEMMs (C == residual, fp32) may split a tile's contraction between CTA pairs (stream-K), whose partial
- * sums meet in C through fp32 reduce-add in arrival order - results agree run to run to fp32 rounding of a 3-term sum, not bit for bit.
- * On: every output element is produced by ONE addition (whole tiles per pair): identical bits on every run and for every batching. */
-int avi_set_deterministic(int32_t on);
 /* 1 if the tensor-core path accepts these shapes (host-side check only) */
 int avi_gemm_bf16_tc_supported(const AviGemmArgs* args);
 /* fp32 -> bf16 (weights packing / activation staging), n elements */

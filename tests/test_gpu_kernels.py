@@ -184,11 +184,10 @@ def test_posconv_ln(ops, T):
 
 
 @pytest.mark.parametrize("rows,K", [(7000, 768), (15936, 3072), (20000, 512)])
-def test_gemm_inplace_residual_stream_k(ops, rows, K):
-    """The in-place residual GEMM (C += A W^T + bias through TMA reduce-add) with more tiles than CTA pairs and a mostly idle last
-    wave takes the stream-K schedule: tiles are split between pairs and their segments meet in C by fp32 reduce-add. Checked against
-    fp64 (tolerance = fp32 accumulation of K bf16 products), and against the deterministic whole-tile schedule, which must be
-    bit-reproducible run to run."""
+def test_gemm_inplace_residual_many_tiles(ops, rows, K):
+    """The in-place residual GEMM (C += A W^T + bias through TMA reduce-add) with more tiles than CTA pairs: every output element is
+    produced by ONE reduce-add, so the result is bit-reproducible run to run (a stream-K split of the tail wave was measured in round 2
+    and was slower - profiles/r2/README.md - so whole tiles stay the schedule)."""
     r = _rng(100 + K)
     N = 768
     A = torch.from_numpy(r.normal(size=(rows, K)).astype(np.float32)).bfloat16().cuda()
@@ -202,17 +201,9 @@ def test_gemm_inplace_residual_stream_k(ops, rows, K):
         ops.gemm(A, W, bias, c, rows=rows, N=N, K=K, residual=c, a_rows_alloc=rows)
         return c
 
-    try:
-        ops.set_deterministic(False)
-        c_sk = run()
-        ops.set_deterministic(True)
-        c_d0, c_d1 = run(), run()
-    finally:
-        ops.set_deterministic(False)
-    assert torch.equal(c_d0, c_d1)
-    for c in (c_sk, c_d0):
-        assert (c.cpu().double() - ref).abs().max().item() < 2e-4
-    assert (c_sk - c_d0).abs().max().item() < 1e-5              # same products, different fp32 summation order
+    c0, c1 = run(), run()
+    assert torch.equal(c0, c1)
+    assert (c0.cpu().double() - ref).abs().max().item() < 2e-4
 
 
 @pytest.mark.parametrize("B,T", [(2, 24), (3, 249), (1, 256), (2, 300), (5, 99)])
