@@ -100,11 +100,16 @@ class CLIPTextModel(_HFCLIPTextModel):
 
 
 class FrozenCLIPEmbedder(nn.Module):
-    """models/diffusion_prior.py:30-55 with the transformer replaced by the drop-in above. `tokenizer` may be injected (a
-    CLIPTokenizer needs its vocabulary files); `forward` also accepts a LongTensor of token ids."""
+    """models/diffusion_prior.py:30-55, same constructor `(version, device, max_length)`: tokenizer and text tower come from
+    `from_pretrained(version)` (the transformers cache; there is no network on the B200 boxes), the tower being the drop-in above.
+    `transformer=` / `tokenizer=` inject already-built parts (tests, synthetic weights); `forward` also accepts a LongTensor of token ids."""
 
-    def __init__(self, transformer: CLIPTextModel, tokenizer=None, device="cuda", max_length=77):
+    def __init__(self, version="openai/clip-vit-large-patch14", device="cuda", max_length=77, *, transformer: CLIPTextModel = None, tokenizer=None):
         super().__init__()
+        if transformer is None:
+            from transformers import CLIPTokenizer
+            tokenizer = CLIPTokenizer.from_pretrained(version) if tokenizer is None else tokenizer      # :36
+            transformer = CLIPTextModel.from_pretrained(version)                                         # :37
         self.tokenizer, self.transformer, self.device, self.max_length = tokenizer, transformer, device, max_length
         self.freeze()
 

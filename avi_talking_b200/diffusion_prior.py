@@ -18,6 +18,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops
+from .clip_text import FrozenCLIPEmbedder  # noqa: F401  (models.diffusion_prior exports it: train_diffusion_prior.py:10)
 from .ops import ACT_NONE, AviPriorNet
 
 
@@ -399,6 +400,32 @@ class InstructDiffusionPrior(nn.Module):
         return x.view(*shape)
 
     @torch.no_grad()
+    def p_sample(self, x, t, text_cond=None, self_cond=None, clip_denoised=True, cond_scale=1.0, generator=None, noise=None):
+        """:329-341, one ancestral step: returns (pred, x_start) with pred = posterior_mean(x_start, x, t) + [t > 0] * sigma_t * noise.
+        Two one-step launches of the sampler kernel (schedule rows "x = x0" and the DDPM row of t); every sample of the batch must sit
+        at the same timestep, as in the reference's own loop (:358)."""
+        if cond_scale != 1.0 or self_cond is not None:
+            raise NotImplementedError("cond_scale != 1 / self-conditioning are not used on the reference's path")
+        tv = int(t.reshape(-1)[0])
+        if not bool((t == tv).all()):
+            raise NotImplementedError("p_sample: one timestep for the whole batch (the reference's sampling loop, :358)")
+        B = x.shape[0]
+        ns = self.noise_scheduler
+        tvals = torch.tensor([float(tv)], device=x.device)
+        z = torch.zeros((), device=x.device)
+        sigma = (0.5 * ns.posterior_log_variance_clipped[tv]).exp() * (1.0 if tv != 0 else 0.0)
+        rows = {"x0": torch.tensor([[2.0, 0, 0, 0, 0, 0]], device=x.device),
+                "step": torch.stack([z, ns.posterior_mean_coef1[tv], ns.posterior_mean_coef2[tv], sigma, z, z]).reshape(1, 6).float()}
+        if noise is None:
+            noise = self._draw(tuple(x.shape), generator)
+        text = text_cond["text_embed"].reshape(B, -1).float().contiguous()
+        temb = self.net.time_embeddings(tvals)
+        xin, nz = x.reshape(B, -1).float().contiguous(), noise.reshape(1, B, -1).float().contiguous()
+        out = {k: ops.prior_sample(self.net._pack()["struct"], temb, r.contiguous(), text, xin, nz, 1.0,
+                                   samples_per_cta=self.samples_per_cta).view(*x.shape) for k, r in rows.items()}
+        return out["step"], out["x0"]
+
+    @torch.no_grad()
     def p_sample_loop_ddpm(self, shape, text_cond, cond_scale=1.0, generator=None, image_embed=None, noise=None):
         """:344-367; returns the NORMALISED embedding (before the division by image_embed_scale), as upstream."""
         return self.p_sample_loop(shape, text_cond, cond_scale=cond_scale, generator=generator, image_embed=image_embed,
@@ -419,8 +446,18 @@ class InstructDiffusionPrior(nn.Module):
             tvals, sched = self._ddpm_schedule()
         return self._run(shape, text_cond, tvals, sched, generator, image_embed, noise)
 
-    def forward(self, *a, **k):
+    def p_losses(self, image_embed, times, text_cond, noise=None):
+        """:369-402 (q_sample, denoiser with conditioning dropout, l2 loss to x_start)."""
         raise NotImplementedError("the prior's training step (p_losses) is outside the inference hot path (SURVEY 8f.4)")
+
+    def forward(self, text=None, image=None, voxel=None, text_embed=None, image_embed=None, text_encodings=None, *args, **kwargs):
+        """:404-456 -> (loss, pred)."""
+        raise NotImplementedError("the prior's training step (p_losses) is outside the inference hot path (SURVEY 8f.4)")
+
+
+def soft_clip_loss(preds, targs, temp=0.125):
+    """train_diffusion_prior.py:125-133 (the contrastive term of the prior's training loss)."""
+    raise NotImplementedError("the prior's training step is outside the inference hot path (SURVEY 8f.4)")
 
 
 @torch.no_grad()

@@ -43,6 +43,20 @@ def linear_interpolation_length(t50: int, input_fps=50, output_fps=25, output_le
     return int(t50 / float(input_fps) * output_fps)
 
 
+def linear_interpolation(features, input_fps, output_fps, output_len=None):
+    """models/lib/wav2vec.py:67-73, same signature: align_corners linear resample of [B, T, C] features along time to
+    int(T / input_fps * output_fps) (or output_len) frames. Inside Wav2Vec2Model.forward the resample is fused with the feature
+    projection's LayerNorm (avi_w2v_lerp_layernorm); this standalone form exists for callers of the function itself."""
+    if not features.is_cuda:
+        raise RuntimeError("avi_talking_b200.linear_interpolation runs on CUDA only (no CPU fallback)")
+    B, T_in, Cc = features.shape
+    T_out = linear_interpolation_length(T_in, input_fps, output_fps, output_len)
+    x = features.contiguous()
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        x = x.float()
+    return ops.w2v_lerp(x, T_in * Cc, B, T_in, T_out, Cc).view(B, T_out, Cc)
+
+
 def pack_posconv_band(w, groups):
     """Grouped conv weight [C, 48, k] fp32 -> the bf16 operand of avi_w2v_posconv_tc, [groups/4][k][3][96][64] (include/avi_b200.h)."""
     C, cg, k = w.shape

@@ -180,3 +180,22 @@ def test_frontend_batch_and_result_sink():
         assert torch.equal(a["predicted_exp"], b["predicted_exp"]) and torch.equal(a["predicted_jaw"], b["predicted_jaw"])
     d = fe.ResultSink.flame_dicts(outs[0], np.zeros((3, 300), np.float32))
     assert len(d) == 3 and d[0]["expression"].shape == (51, 50) and not d[0]["global_pose"].any()
+
+
+def test_wrapper_from_run_directory_matches_golden(golden, tmp_path):
+    """TalkingHeadWrapper(path_to_model, render_results=False) - cfg.yaml + Lightning last.ckpt, the reference's constructor path
+    (TalkingHeadWrapper.py:78-83, train_diffusion_prior.py:954-958) - gives the reference's own outputs (tests/golden/emote.npz)."""
+    from test_boundary import _write_run_dir
+
+    from avi_talking_b200.talking_head import TalkingHeadWrapper
+    g = golden("emote")
+    run, _ = _write_run_dir(tmp_path)
+    m = TalkingHeadWrapper(run, render_results=False).to(torch.device("cuda"))
+    m.eval()
+    m.talking_head_model.precision = "fp32"
+    m.talking_head_model.audio_model.model.precision = "fp32"
+    m.talking_head_model.sequence_decoder.flame.precision = "fp32"
+    r = m(_cuda(synth.emote_sample(1, 27, seed=50)))
+    assert np.abs(r["predicted_exp"].cpu().numpy() - g["t27_predicted_exp"]).max() < 5e-5
+    assert np.abs(r["predicted_jaw"].cpu().numpy() - g["t27_predicted_jaw"]).max() < 5e-5
+    assert np.abs(r["predicted_vertices"].cpu().numpy()[:, :, ::7] - g["t27_predicted_vertices_sub"]).max() < 1e-5

@@ -274,6 +274,44 @@ def test_predict_and_convert_overlapped_equals_sequential():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-6), ("bf16", 5e-5)])
+def test_convert_coeff2verts_matches_oracle(precision, tol):
+    """Faceformer.convert_coeff2verts (faceformer_disentangle.py:425-433: de-normalise the 53 coefficients, zero the global pose in
+    place, FLAME with exp[:50] and the jaw) against the CPU oracle restatement; per-frame shapes and the hoisted per-clip shape."""
+    from oracle import flame_oracle as fo
+
+    from avi_talking_b200.smoke import build_models
+    m = build_models(precision)
+    rng = np.random.default_rng(11)
+    F_ = 77
+    coeff = torch.from_numpy(rng.standard_normal((F_, 53)).astype(np.float32))
+    pose = torch.from_numpy(np.concatenate([0.3 * rng.standard_normal((F_, 3)), 0.1 * rng.standard_normal((F_, 3))], 1).astype(np.float32))
+    shape = torch.from_numpy(rng.standard_normal((F_, 100)).astype(np.float32))
+    buf = synth.flame_buffers(100, 50)
+    want = fo.convert_coeff2verts(buf, m.coeff_mean.reshape(-1).cpu(), m.coeff_std.reshape(-1).cpu(), coeff, pose.clone(), shape)
+    pose_dev = pose.cuda()
+    got = m.convert_coeff2verts(coeff.cuda(), pose_dev, shape.cuda())
+    assert float(pose_dev[:, :3].abs().max()) == 0.0 and torch.equal(pose_dev[:, 3:].cpu(), pose[:, 3:])   # in place, as upstream (:429)
+    err = (got.reshape(F_, -1).cpu() - want.reshape(F_, -1)).abs().max().item()
+    print(f"convert_coeff2verts {precision}: max abs vertex error {err:.2e} m")
+    assert err < tol
+
+
+@pytest.mark.gpu
+def test_linear_interpolation_function():
+    """models/lib/wav2vec.py:67-73 as a standalone function (inside forward it is fused with the LayerNorm)."""
+    import torch.nn.functional as F
+
+    from avi_talking_b200.wav2vec import linear_interpolation
+    x = torch.from_numpy(np.random.default_rng(5).normal(size=(3, 199, 512)).astype(np.float32))
+    for out_len in (None, 97, 250):
+        got = linear_interpolation(x.cuda(), 50, 25, output_len=out_len)
+        n = out_len if out_len is not None else int(199 / 50.0 * 25)
+        want = F.interpolate(x.transpose(1, 2), size=n, align_corners=True, mode="linear").transpose(1, 2)
+        assert got.shape == want.shape and (got.cpu() - want).abs().max().item() < 1e-5
+
+
+@pytest.mark.gpu
 def test_graphed_predict_and_convert_matches_eager():
     """CUDA-graph replay of predict_and_convert (avi_talking_b200/graphs.py) returns what the eager call returns, also after the
     inputs change and after the weights change (re-capture keyed on parameter versions)."""

@@ -85,6 +85,6 @@ def test_emote_dropin_state_dict_keys_match_reference(golden):
     g = golden("emote")
     fcfg = synth.write_flame_assets("/tmp/avi_flame_assets_keys")
     fcfg.n_shape, fcfg.n_exp = 300, 50
-    m = TalkingHeadWrapper(Wav2Vec2Model(Wav2Vec2Config()), FLAME(fcfg), emote_cfg(n_identities=32))
+    m = TalkingHeadWrapper.from_parts(Wav2Vec2Model(Wav2Vec2Config()), FLAME(fcfg), emote_cfg(n_identities=32))
     own = sorted(k for k in m.talking_head_model.state_dict() if k.startswith("sequence_") and ".flame." not in k)
     assert own == list(g["state_keys"])
