@@ -441,9 +441,51 @@ __global__ void __launch_bounds__(128) ff_biased_attn_kernel(const float* __rest
   }
 }
 
+// convert_coeff2verts prologue (faceformer_disentangle.py:426-430): exp_out[f, :n_exp] = coeff[f, :n_exp] * std + mean, and the global
+// rotation pose[f, :3] is zeroed IN PLACE (as upstream does to the caller's tensor).
+__global__ void ff_denorm_coeff_kernel(const float* __restrict__ coeff, const float* __restrict__ mean, const float* __restrict__ stdv,
+                                       float* pose, float* __restrict__ exp_out, int F, int n_coeff, int n_exp, int n_pose) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < F * n_exp) {
+    const int f = idx / n_exp, c = idx - f * n_exp;
+    exp_out[idx] = coeff[(int64_t)f * n_coeff + c] * stdv[c] + mean[c];
+  }
+  if (idx < F * 3) pose[(int64_t)(idx / 3) * n_pose + idx % 3] = 0.f;
+}
+
+// Conditioning columns of the decoder input (faceformer_disentangle.py:808): out[r, 0:6] = eye (one learnable row, or a row per
+// frame), out[r, 6:36] = emotion embedding of frame r; the audio columns [36, 36 + fd) are written by the audio_feature_map GEMM.
+__global__ void ff_fill_cond_kernel(const float* __restrict__ eye, int eye_per_row, const float* __restrict__ emo, int64_t emo_clip_stride,
+                                    int T, float* __restrict__ out, int64_t rows, int ld) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * 36) return;
+  const int64_t r = idx / 36;
+  const int c = (int)(idx - r * 36);
+  float v;
+  if (c < 6) v = eye[eye_per_row ? r * 6 + c : c];
+  else v = emo[(r / T) * emo_clip_stride + (r % T) * 30 + (c - 6)];
+  out[r * ld + c] = v;
+}
+
 }  // namespace avi
 
 using namespace avi;
+
+extern "C" int avi_ff_denorm_coeff(const float* coeff, const float* mean, const float* stdv, float* pose, float* exp_out, int32_t F,
+                                   int32_t n_coeff, int32_t n_exp, int32_t n_pose, void* stream) {
+  AVI_REQUIRE(coeff && mean && stdv && pose && exp_out && F > 0 && n_exp > 0 && n_exp <= n_coeff && n_pose >= 3, "avi_ff_denorm_coeff: bad arguments");
+  const int n = F * (n_exp > 3 ? n_exp : 3);
+  ff_denorm_coeff_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(coeff, mean, stdv, pose, exp_out, F, n_coeff, n_exp, n_pose);
+  return check_launch("ff_denorm_coeff");
+}
+
+extern "C" int avi_ff_fill_cond(const float* eye, int32_t eye_per_row, const float* emo, int64_t emo_clip_stride, float* out, int32_t B,
+                                int32_t T, int32_t ld, void* stream) {
+  AVI_REQUIRE(eye && emo && out && B > 0 && T > 0 && ld >= 36, "avi_ff_fill_cond: bad arguments");
+  const int64_t rows = (int64_t)B * T;
+  ff_fill_cond_kernel<<<(unsigned)((rows * 36 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(eye, eye_per_row, emo, emo_clip_stride, T, out, rows, ld);
+  return check_launch("ff_fill_cond");
+}
 
 extern "C" int avi_ff_decoder_ar(const AviDecoderWeights* w, const float* cross, const float* style, float* hidden_out,
                                  float* kv_scratch, int32_t B, int32_t T, int32_t fd, int32_t period, void* stream) {

@@ -218,17 +218,21 @@ class Faceformer(nn.Module):
     # ------------------------------------------------------------------ reference API
     def convert_coeff2verts(self, gt_coeff, gt_pose, gt_shape):
         """:425-433 (zeroes gt_pose[..., :3] in place, as upstream)."""
-        self.coeff_mean, self.coeff_std = self.coeff_mean.to(gt_coeff), self.coeff_std.to(gt_coeff)
-        n = gt_coeff.shape[-1]
-        gt_coeff_unnorm = gt_coeff * self.coeff_std[0, :, :n] + self.coeff_mean[0, :, :n]
-        gt_pose[..., :3] = 0.0
-        return self.flame.vertices_only(shape_params=gt_shape, expression_params=gt_coeff_unnorm[:, :50].contiguous(),
-                                        pose_params=gt_pose)
+        if self.coeff_mean.device != gt_coeff.device or self.coeff_mean.dtype != torch.float32:
+            self.coeff_mean, self.coeff_std = self.coeff_mean.to(gt_coeff.device).float(), self.coeff_std.to(gt_coeff.device).float()
+        if gt_coeff.dtype != torch.float32 or not gt_coeff.is_contiguous() or gt_pose.dtype != torch.float32 or not gt_pose.is_contiguous():
+            raise TypeError("convert_coeff2verts: gt_coeff / gt_pose must be contiguous fp32 (gt_pose is modified in place, as upstream)")
+        # de-normalisation of the 50 expression coefficients and the in-place zeroing of the global rotation: one launch
+        exp = ops.ff_denorm_coeff(gt_coeff, self.coeff_mean.reshape(-1), self.coeff_std.reshape(-1), gt_pose, n_exp=50)
+        return self.flame.vertices_only(shape_params=gt_shape, expression_params=exp, pose_params=gt_pose)
 
     def _vertex_head(self, hidden, P, template):
         """vertice_map_r over all rows + template (:473,481), one GEMM with bias' = b_r + template."""
         B, T, fd = hidden.shape
-        bias = (P["vr_b"] + template.reshape(-1).float()).contiguous()
+        tkey = (template.data_ptr(), template._version)
+        if P.get("vr_bias_key") != tkey:                       # b_r + template, once per template version (not per step)
+            P["vr_bias"], P["vr_bias_key"] = ops.add_f32(P["vr_b"], template.reshape(-1).float().contiguous()), tkey
+        bias = P["vr_bias"]
         vd = self.args.vertice_dim
         rows = ops.empty_rows(B * T, vd, hidden.device)      # 16-byte aligned row stride (15072 floats), returned as a [.., 15069] view
         if self.precision == "bf16" and fd % 64 == 0:
@@ -290,23 +294,29 @@ class Faceformer(nn.Module):
         B = audio.shape[0]
         dev = audio.device
         self.template = self.template.to(audio)
-        one_hot = torch.zeros(B, len(self.args.train_subjects.split()), device=dev)
-        one_hot[:, 0] = 1
-        obj_embedding = ops.linear(one_hot, P["obj_w"], None)                                  # :771-773
+        # obj_vector(one_hot) with one_hot[:, 0] = 1 (:770-773) is column 0 of the weight, for every clip
+        obj_embedding = P["obj_w"][:, 0].expand(B, -1)
         hs_a = self.audio_encoder(audio, self.dataset).last_hidden_state                      # :775
         T = hs_a.shape[1]
+        fd = self.args.feature_dim
         h16 = getattr(self.audio_encoder, "last_hidden_state_bf16", None)
+        cond = 36 if self.variant == "disentangle" else 0
+        # hidden_states = cat[eye(6), emo(30), audio_feature_map(hs_a)] (:776,808): the GEMM writes its fd columns straight into the
+        # concatenated buffer (row pitch 36 + fd), one small kernel fills the 36 conditioning columns - no cat, no intermediate
+        hidden_states = torch.empty((B * T, cond + fd), dtype=torch.float32, device=dev)
+        out_view = hidden_states[:, cond:]
         if self.precision == "bf16" and h16 is not None and "afm_w16" in P and self.afm_tensor_core:
             # the encoder already produced the bf16 copy of its output for the next tensor-core contraction
-            hs_a = ops.linear(h16.reshape(B * T, -1), P["afm_w16"], P["afm_b"], out_dtype=torch.float32).view(B, T, -1)   # :776
+            ops.gemm(h16.reshape(B * T, -1), P["afm_w16"], P["afm_b"], out_view, rows=B * T, N=fd, K=h16.shape[-1], c_ld=cond + fd)
         else:
-            hs_a = ops.linear(hs_a.reshape(B * T, -1), P["afm_w"], P["afm_b"], tf32=bool(P.get("tf32"))).view(B, T, -1)   # :776
+            ops.gemm(hs_a.reshape(B * T, -1), P["afm_w"], P["afm_b"], out_view, rows=B * T, N=fd, K=hs_a.shape[-1], c_ld=cond + fd,
+                     tf32=bool(P.get("tf32")))
         if self.variant == "disentangle":
-            eye = self.learnable_eye_embed.expand(B, T, -1) if eye_embed is None else eye_embed
-            hidden_states = torch.cat([eye, emo_embed[:, :T].to(hs_a), hs_a], dim=-1)          # :808
-        else:
-            hidden_states = hs_a                                                               # faceformer_vert.py:434
-        return self.forward_ff(None, hidden_states, obj_embedding, T, teacher_forcing=False)  # :810
+            eye = self.learnable_eye_embed.reshape(-1) if eye_embed is None else eye_embed.reshape(B * T, 6).contiguous().float()
+            emo = emo_embed if (emo_embed.dtype == torch.float32 and emo_embed.stride(-1) == 1 and emo_embed.stride(1) == 30) \
+                else emo_embed.float().contiguous()
+            ops.ff_fill_cond(eye, emo, hidden_states, B, T)
+        return self.forward_ff(None, hidden_states.view(B, T, -1), obj_embedding, T, teacher_forcing=False)  # :810
 
     @torch.no_grad()
     def predict_and_convert(self, audio, emo_embed, gt_coeff, gt_pose, gt_shape):

@@ -218,6 +218,28 @@ def posconv_ln(x, w_packed, conv_bias, ln_w, ln_b, B, T, groups, k, want_bf16, e
     return o32, o16
 
 
+def ff_denorm_coeff(coeff, mean, std, pose, n_exp=50):
+    """exp [F, n_exp] = coeff[:, :n_exp] * std + mean; pose[:, :3] zeroed in place (faceformer_disentangle.py:426-430)."""
+    _need_cuda(coeff, mean, std, pose)
+    assert coeff.is_contiguous() and pose.is_contiguous() and coeff.dtype == pose.dtype == torch.float32
+    F_, nc = coeff.shape
+    out = torch.empty((F_, n_exp), dtype=torch.float32, device=coeff.device)
+    with _timed("ff_denorm_coeff", 0.0):
+        _lib.check(_lib.load().avi_ff_denorm_coeff(_ptr(coeff), _ptr(mean), _ptr(std), _ptr(pose), _ptr(out), C.c_int32(F_), C.c_int32(nc),
+                                                   C.c_int32(n_exp), C.c_int32(pose.shape[-1]), _stream()), "avi_ff_denorm_coeff")
+    return out
+
+
+def ff_fill_cond(eye, emo, out, B, T):
+    """out[:, 0:6] = eye ([6] or [B*T, 6]), out[:, 6:36] = emo [B, >=T, 30]; out [B*T, ld] fp32."""
+    _need_cuda(eye, emo, out)
+    per_row = 0 if eye.numel() == 6 else 1
+    with _timed("ff_fill_cond", 0.0):
+        _lib.check(_lib.load().avi_ff_fill_cond(_ptr(eye), C.c_int32(per_row), _ptr(emo), C.c_int64(emo.stride(0)), _ptr(out), C.c_int32(B),
+                                                C.c_int32(T), C.c_int32(out.stride(0)), _stream()), "avi_ff_fill_cond")
+    return out
+
+
 def posconv_tc(xpad, w_band, bias, B, T, groups, k):
     """Grouped positional conv (+ bias) on tcgen05, activation slab resident in shared memory: xpad bf16 [B, Tp, C] -> fp32 [B*T, C]."""
     _need_cuda(xpad, w_band, bias)

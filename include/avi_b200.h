@@ -141,6 +141,16 @@ int avi_w2v_posconv_merge_ln(const float* x, const float* pc, const float* ln_w,
 int avi_w2v_posconv_tc(const void* xpad, const void* w_band, const float* bias, float* pc, int32_t B, int32_t T, int32_t Tp, int32_t C,
                        int32_t groups, int32_t k, void* stream);
 
+/* Faceformer.convert_coeff2verts prologue (models/faceformer_disentangle.py:426-430): exp_out [F, n_exp] = coeff[:, :n_exp] * std + mean
+ * (coeff [F, n_coeff], mean / std [>= n_exp]); pose [F, n_pose]: columns 0..2 (global rotation) are zeroed IN PLACE, as upstream. */
+int avi_ff_denorm_coeff(const float* coeff, const float* mean, const float* stdv, float* pose, float* exp_out, int32_t F, int32_t n_coeff,
+                        int32_t n_exp, int32_t n_pose, void* stream);
+/* Conditioning columns of the decoder input (models/faceformer_disentangle.py:808: cat[eye(6), emo(30), audio(fd)]):
+ * out [B*T, ld] columns 0..5 = eye (eye_per_row == 0: ONE row of 6, the learnable embedding; else [B*T, 6]), columns 6..35 = emo
+ * (clip b, frame t at emo + b * emo_clip_stride + t * 30). Columns >= 36 are not touched (the audio_feature_map GEMM writes them). */
+int avi_ff_fill_cond(const float* eye, int32_t eye_per_row, const float* emo, int64_t emo_clip_stride, float* out, int32_t B, int32_t T,
+                     int32_t ld, void* stream);
+
 /* softmax(q k^T * scale) v per (clip, head); qkv [B, T, 3*H*D] packed (q | k | v), dtype qkv_dtype; out [B, T, H*D] same dtype.
  * (HF Wav2Vec2Attention / eager_attention_forward, no mask) */
 int avi_mha_fwd(const void* qkv, void* out, int32_t dtype, int32_t B, int32_t T, int32_t H, int32_t D, float scale, void* stream);

@@ -225,7 +225,7 @@ def test_predict_api_with_fan_stub(golden):
     # ... and it is the reference's own predict() output on the same frames (golden minted with the real mask_lip)
     # (same weights seed 10 + 64 = 74, audio and embeddings as oracle/make_golden.golden_faceformer's fd = 64 case)
     assert np.abs(v[0, :, ::7].cpu().numpy() - g["predict_fd64_sub"]).max() < 1e-5
-    assert frames[:, :, 1:, :].min().item() == 0.37                  # the caller's frames are not modified (masked copy)
+    assert frames[:, :, 1:, :].min().item() == float(np.float32(0.37))                  # the caller's frames are not modified (masked copy)
     # a 5-frame emotion clip played ping-pong over the 24 output frames (loop_utils.loopback_frames, golden index pattern):
     # batched-unique path (eval) == upstream's frame-by-frame path (taken for a train-mode provider)
     idx = torch.from_numpy(g["loop_idx_5_17"]).long()
