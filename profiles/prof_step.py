@@ -17,6 +17,6 @@ m = build_models("bf16")
 inp = {k: v.cuda() for k, v in make_inputs(clips, n, T, seed=1000).items()}
 for _ in range(2):
     v = m.predict_from_embeddings(inp["audio"], inp["emo"])
-    fv = m.convert_coeff2verts(inp["coeff"], inp["pose"], inp["shape"].repeat_interleave(T, 0))
+    fv = m.convert_coeff2verts(inp["coeff"], inp["pose"], inp["shape"])
 torch.cuda.synchronize()
 print("ok", tuple(v.shape), tuple(fv.shape))

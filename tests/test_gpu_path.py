@@ -378,7 +378,7 @@ def test_full_size_configs1_properties():
     T = n_frames(n)
     assert T == 249
     inp = {k: v.cuda() for k, v in make_inputs(B, n, T, seed=1000).items()}
-    v, fv = m.predict_and_convert(inp["audio"], inp["emo"], inp["coeff"], inp["pose"].clone(), inp["shape"].repeat_interleave(T, 0))
+    v, fv = m.predict_and_convert(inp["audio"], inp["emo"], inp["coeff"], inp["pose"].clone(), inp["shape"])
     assert tuple(v.shape) == (B, T, 15069) and tuple(fv.shape)[0] == B * T
     assert torch.isfinite(v).all() and torch.isfinite(fv).all()
     for c in (0, 31, 63):                                                                                   # (1)
