@@ -48,7 +48,7 @@ struct AttnParams {
   float scale_log2e;
 };
 
-__global__ void __maxnreg__(112)   // 576 threads x 112 registers = 63 K of the 64 K file (ptxas stops at 96 under __launch_bounds__ alone and spills the scores)
+__global__ void __launch_bounds__(AT_THREADS, 1)   // 18 warps = 5 on one SM sub-partition: 16 K registers / (5 x 32) caps a thread at 96 (a 112-register build fails to launch)
 attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv, const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
