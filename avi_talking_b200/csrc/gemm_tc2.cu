@@ -16,7 +16,18 @@
 // CTA only), warps 2..17 = epilogue (TMEM lane quarter = warp_id % 4, 64-column slice = (warp_id - 2) / 4).
 // Barriers: full[s] lives in the leader (both CTAs' TMA bytes land on it), empty[s] / tmem_full[a] are multicast to both CTAs
 // by tcgen05.commit, tmem_empty[a] lives in the leader and collects the epilogue warps of both CTAs.
+//
+// CL = 4 (two pairs per cluster; OPT-IN through avi_gemm_set_multicast(1) / AVI_GEMM_MULTICAST=1): the mainloop of a pair is paced
+// by L2 -> SM delivery, not by the tensor pipe (32 KB per CTA per k-block arrive in ~800 clk against 512 clk of MMAs: ~40 B/clk/SM,
+// the L2 slice output cap of the chip). The two pairs of a cluster work on two consecutive m-tiles of the SAME n-tile, and each
+// CTA fetches only a 64-row QUARTER of the W tile, multicast to the CTA of the other pair that needs the same half: 24 KB per CTA
+// per k-block are requested instead of 32. A slot is reusable once BOTH pairs' MMAs have read it (empty[s] counts two commits,
+// each multicast to all four CTAs), so the pairs run in lockstep. MEASURED (profiles/r2/gemm_multicast_ab.txt): bit-identical
+// results, but no gain - the whole step is unchanged (GEMM launches 5.43 vs 5.44 ms) and isolated L2-resident encoder shapes are
+// 7-13 % SLOWER (qkv 62 vs 55 us): 2-way multicast does not lift the delivery cap (the L2 already merges near-simultaneous
+// requests for a line from a few SMs) and the lockstep costs slack. Hence off by default; kept, tested, for wider clusters.
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 
 #include "tc_common.cuh"
@@ -71,8 +82,8 @@ struct Tc2Params {
 // TF32 = true: operands are fp32 in shared memory (32 elements per 128-byte swizzle row instead of 64), consumed by
 // tcgen05.mma.kind::tf32 (10-bit significand, fp32 accumulate): the same pipeline at half the MMA rate, for callers that need more
 // than bf16's 8 bits (the 60-convolution FanEncoder). Everything below is written in BYTES per k-block (128) and in elements via BK.
-template <bool TF32>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P2_THREADS, 1)
+template <bool TF32, int CL>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(P2_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                      const __grid_constant__ CUtensorMap map_c, const Tc2Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];  // no static shared memory in this kernel: the dynamic window starts aligned
@@ -89,8 +100,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * P2_STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
-  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const uint32_t crank = cluster_ctarank();             // 0 .. CL-1
+  const uint32_t rank = crank & 1u;                     // position inside the CTA pair (0 = leader: issues the MMAs)
+  const uint32_t leader = crank & ~1u;                  // cluster rank of this pair's leader
+  const int q = (int)(crank >> 1);                      // which pair of the cluster (CL = 4: the pair's m-tile inside the super-tile)
+  constexpr int PPC = CL / 2;                           // pairs per cluster
+  const int pair = blockIdx.x / CL, num_pairs = gridDim.x / CL;   // work-item walkers (a cluster walks super-tiles of PPC m-tiles)
+  const int mt_total = p.m_tiles * p.batch;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -98,7 +114,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
     for (int s = 0; s < P2_STAGES; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 1);
-      mbar_init(smem_u32(&empty_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), PPC);   // one tcgen05.commit per pair of the cluster
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&tmem_full[s]), 1);
@@ -120,10 +136,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t full_leader = mapa_shared(smem_u32(&full_bar[0]), 0);
+      const uint32_t full_leader = mapa_shared(smem_u32(&full_bar[0]), leader);
       for (int t = pair; t < p.total_tiles; t += num_pairs) {
         const int n_blk = t % p.n_tiles;
-        const int mt = t / p.n_tiles;
+        const int mt = (t / p.n_tiles) * PPC + q;     // past the end for the idle pair of an odd last super-tile: TMA zero-fills
         const int b = mt / p.m_tiles, m_blk = mt % p.m_tiles;
         const int row0 = m_blk * (2 * P2_BM) + (int)rank * P2_BM;
         // the last n-tile may be narrower than 256: the MMA is issued with N = n_eff (a multiple of 32), of which each CTA of the pair
@@ -141,7 +157,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           if (rank == 0) mbar_expect_tx(fb_local, 2 * P2_STAGE_BYTES);
           constexpr int BK = TF32 ? P2_BK / 2 : P2_BK;   // elements per 128-byte k-block row
           tma_load_4d_pair(smem_u32(smem_a + stage * P2_A_BYTES), &map_a, full_leader + stage * 8, kin * BK, ph, row0 + sr, b);
-          tma_load_2d_pair(smem_u32(smem_b + stage * P2_B_BYTES), &map_w, full_leader + stage * 8, kb * BK, wrow0);
+          if constexpr (CL == 4) {
+            // this CTA's quarter (64 rows) of the W tile, delivered to the same offset in both CTAs that hold this half
+            tma_load_2d_pair_mc(smem_u32(smem_b + stage * P2_B_BYTES + q * (P2_B_BYTES / 2)), &map_w, full_leader + stage * 8, kb * BK,
+                                wrow0 + q * (P2_BNH / 2), (uint16_t)(0x5u << rank));
+          } else {
+            tma_load_2d_pair(smem_u32(smem_b + stage * P2_B_BYTES), &map_w, full_leader + stage * 8, kb * BK, wrow0);
+          }
           if (++kin == p.kb_per_tap) {
             kin = 0;
             if (++ph == p.conv_stride) {
@@ -192,13 +214,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             if constexpr (TF32) umma_tf32_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
             else umma_bf16_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit_pair(smem_u32(&empty_bar[stage]), 3);  // frees the slot in BOTH CTAs once these MMAs have read it
+          umma_commit_pair(smem_u32(&empty_bar[stage]), (uint16_t)((1u << CL) - 1));  // one of the PPC arrivals that free the slot in every CTA of the cluster
           if (++stage == P2_STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit_pair(smem_u32(&tmem_full[as]), 3);  // accumulator complete -> epilogues of both CTAs
+        umma_commit_pair(smem_u32(&tmem_full[as]), (uint16_t)(3u << leader));  // accumulator complete -> epilogues of both CTAs of the pair
         TL(1, it, 4);
       }
     }
@@ -216,14 +238,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const bool fast_bf16 = p.vec_ok && p.c_dtype == AVI_DT_BF16 && p.C2 == nullptr && p.residual == nullptr;
     const bool fast_f32 = p.vec_ok && p.c_dtype == AVI_DT_F32 && p.C2 == nullptr;
     const bool ragged_f32 = !p.vec_ok && p.c_dtype == AVI_DT_F32 && p.C2 == nullptr && p.residual == nullptr;
-    const uint32_t te_leader0 = mapa_shared(smem_u32(&tmem_empty[0]), 0);
-    const uint32_t te_leader1 = mapa_shared(smem_u32(&tmem_empty[1]), 0);
+    const uint32_t te_leader0 = mapa_shared(smem_u32(&tmem_empty[0]), leader);
+    const uint32_t te_leader1 = mapa_shared(smem_u32(&tmem_empty[1]), leader);
     int it = 0;
     for (int t = pair; t < p.total_tiles; t += num_pairs, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int n_blk = t % p.n_tiles;
-      const int mt = t / p.n_tiles;
+      const int mt = (t / p.n_tiles) * PPC + q;
       const int b = mt / p.m_tiles, m_blk = mt % p.m_tiles;
       const int n0 = n_blk * P2_BN;
       const uint32_t sbias_a = smem_u32(sbias) + as * (P2_BN * 4);
@@ -239,7 +261,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       if (ew == 0 && lane == 0) TL(2, it, 2);
       tc_fence_after();
       const int row_base = m_blk * (2 * P2_BM) + (int)rank * P2_BM + quarter * 32;
-      const int rows_valid = p.rows - row_base;  // may be <= 0 or > 32
+      const int rows_valid = mt < mt_total ? p.rows - row_base : 0;  // may be <= 0 or > 32 (0: the idle pair of an odd last super-tile)
       const int64_t c_row0 = (int64_t)b * p.c_batch_stride + (int64_t)row_base * p.c_ld;
       const int64_t r_row0 = (int64_t)b * p.res_batch_stride + (int64_t)row_base * p.res_ld;
 #pragma unroll 1
@@ -501,7 +523,43 @@ extern "C" int avi_debug_timeline(long long* host_out) {
 }
 #endif
 
+extern "C" int avi_gemm_set_multicast(int on) {
+  return g_gemm_multicast.exchange(on ? 1 : 0, std::memory_order_relaxed);
+}
+
 extern "C" int avi_gemm_bf16_tc_supported(const AviGemmArgs* a) { return tc2_check(a) == nullptr ? 1 : 0; }
+
+static std::atomic<int> g_gemm_multicast{getenv("AVI_GEMM_MULTICAST") != nullptr ? 1 : 0};
+
+// how many 4-CTA clusters of this kernel the device can hold at once (GPCs whose SM count is not a multiple of 4 strand SMs)
+template <bool TF32>
+static int mc_clusters_resident() {
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  int n = cache[dev].load(std::memory_order_relaxed);
+  if (n == 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(4 * (device_sms() / 4));
+    cfg.blockDim = dim3(P2_THREADS);
+    cfg.dynamicSmemBytes = P2_SMEM_BYTES;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 4;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int got = 0;
+    if (cudaOccupancyMaxActiveClusters(&got, gemm_tc2_kernel<TF32, 4>, &cfg) != cudaSuccess || got <= 0) {
+      cudaGetLastError();
+      got = -1;
+    }
+    n = got;
+    cache[dev].store(n, std::memory_order_relaxed);
+  }
+  return n > 0 ? n : 0;
+}
 
 template <bool TF32>
 static int gemm_tc2_launch(const AviGemmArgs* a, void* stream) {
@@ -512,6 +570,19 @@ static int gemm_tc2_launch(const AviGemmArgs* a, void* stream) {
   constexpr CUtensorMapDataType DT = TF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   const int cin = a->K / a->conv_taps;
   const int s = a->conv_stride;
+  // two pairs per cluster with the W tile multicast, whenever the pairs would walk more than one wave of tiles
+  const bool no_mc = g_gemm_multicast.load(std::memory_order_relaxed) == 0;
+  const int max_pairs = device_sms() / 2;
+  const int m_tiles_all = ((a->rows + 2 * P2_BM - 1) / (2 * P2_BM)) * a->batch, n_tiles_all = (a->N + P2_BN - 1) / P2_BN;
+  static SmemOptIn optin, optin_mc;   // one per template instance; per-device flags inside
+  int mc_clusters = 0;
+  if (!no_mc && (int64_t)m_tiles_all * n_tiles_all > max_pairs) {
+    const cudaError_t e = smem_optin(gemm_tc2_kernel<TF32, 4>, (int)P2_SMEM_BYTES, optin_mc);
+    AVI_REQUIRE(e == cudaSuccess, "avi_gemm_bf16_tc: cannot opt in to %u bytes of shared memory: %s", P2_SMEM_BYTES, cudaGetErrorString(e));
+    mc_clusters = mc_clusters_resident<TF32>();
+    if (2 * mc_clusters < max_pairs - 4) mc_clusters = 0;   // a device that strands more than 8 SMs keeps the pair kernel
+  }
+  const bool mc = mc_clusters > 0;
   CUtensorMap map_a, map_w;
   {
     // (channel, phase, super-row, clip)
@@ -525,7 +596,7 @@ static int gemm_tc2_launch(const AviGemmArgs* a, void* stream) {
   {
     uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->N};
     uint64_t strides[1] = {(uint64_t)a->K * ES};
-    uint32_t box[2] = {BK, P2_BNH};
+    uint32_t box[2] = {BK, mc ? (uint32_t)P2_BNH / 2 : (uint32_t)P2_BNH};
     if (encode_map(&map_w, a->W, 2, dims, strides, box, DT)) return 1;
   }
   Tc2Params p;
@@ -545,7 +616,7 @@ static int gemm_tc2_launch(const AviGemmArgs* a, void* stream) {
   p.row_skip = a->conv_taps_x != 0 ? a->conv_row_pitch - a->conv_taps_x : 0;
   p.m_tiles = (a->rows + 2 * P2_BM - 1) / (2 * P2_BM);
   p.n_tiles = (a->N + P2_BN - 1) / P2_BN;
-  p.total_tiles = p.m_tiles * p.n_tiles * a->batch;
+  p.total_tiles = mc ? ((m_tiles_all + 1) / 2) * p.n_tiles : p.m_tiles * p.n_tiles * a->batch;   // mc: super-tiles of two m-tiles
   p.c_ld = a->c_ld;
   p.c_batch_stride = a->c_batch_stride;
   p.res_ld = a->res_ld;
@@ -584,13 +655,16 @@ static int gemm_tc2_launch(const AviGemmArgs* a, void* stream) {
     if (inplace_res) p.residual = nullptr;   // the memory system performs the addition
   }
 
-  static SmemOptIn optin;   // one per template instance; per-device flags inside
-  const cudaError_t attr_err = smem_optin(gemm_tc2_kernel<TF32>, (int)P2_SMEM_BYTES, optin);
+  if (mc) {
+    const int clusters = p.total_tiles < mc_clusters ? p.total_tiles : mc_clusters;
+    gemm_tc2_kernel<TF32, 4><<<4 * clusters, P2_THREADS, P2_SMEM_BYTES, (cudaStream_t)stream>>>(map_a, map_w, map_c, p);
+    return check_launch(TF32 ? "gemm_tf32_tc" : "gemm_bf16_tc");
+  }
+  const cudaError_t attr_err = smem_optin(gemm_tc2_kernel<TF32, 2>, (int)P2_SMEM_BYTES, optin);
   AVI_REQUIRE(attr_err == cudaSuccess, "avi_gemm_bf16_tc: cannot opt in to %u bytes of shared memory: %s", P2_SMEM_BYTES,
               cudaGetErrorString(attr_err));
-  const int max_pairs = device_sms() / 2;
   const int pairs = p.total_tiles < max_pairs ? p.total_tiles : max_pairs;
-  gemm_tc2_kernel<TF32><<<2 * pairs, P2_THREADS, P2_SMEM_BYTES, (cudaStream_t)stream>>>(map_a, map_w, map_c, p);
+  gemm_tc2_kernel<TF32, 2><<<2 * pairs, P2_THREADS, P2_SMEM_BYTES, (cudaStream_t)stream>>>(map_a, map_w, map_c, p);
   return check_launch(TF32 ? "gemm_tf32_tc" : "gemm_bf16_tc");
 }
 

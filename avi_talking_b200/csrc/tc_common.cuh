@@ -182,6 +182,18 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap
       ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1)
       : "memory");
 }
+// The same load delivered to the same shared-memory offset of every CTA in `mask` (cluster ranks). With .cta_group::2 the
+// completion lands, for each destination CTA, on the mbarrier at bar's offset in that CTA or in ITS pair peer, according to
+// whether bar names the executing CTA or the executing CTA's peer: destinations of the executing CTA's parity all signal
+// their own pair's leader.
+__device__ __forceinline__ void tma_load_2d_pair_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1,
+                                                    uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, "
+      "%5}], [%2], %3;" ::"r"(dst),
+      "l"(map), "r"(bar_cluster), "h"(mask), "r"(c0), "r"(c1)
+      : "memory");
+}
 // D[256 x N] (+)= A[256 x 16] B[N x 16]^T across the CTA pair: each CTA supplies its 128 rows of A and its N/2 rows of B from the
 // same shared-memory offsets, and receives its 128 accumulator rows in its own TMEM. Issued by the leader CTA only.
 __device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {

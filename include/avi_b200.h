@@ -83,6 +83,10 @@ int avi_gemm_bf16_tc(const AviGemmArgs* args, void* stream);
 int avi_gemm_tf32_tc(const AviGemmArgs* args, void* stream);
 /* 1 if the tensor-core path accepts these shapes (host-side check only) */
 int avi_gemm_bf16_tc_supported(const AviGemmArgs* args);
+/* Opt in (1) / out (0, default; env AVI_GEMM_MULTICAST sets the initial value) of the 4-CTA-cluster schedule of the two kernels
+ * above for launches with more than one wave of tiles: two CTA pairs per cluster on consecutive m-tiles, W-tile quarters
+ * TMA-multicast between them. Same results bit for bit; measured no faster on B200 (csrc/gemm_tc2.cu). Returns the old value. */
+int avi_gemm_set_multicast(int on);
 /* fp32 -> bf16 (weights packing / activation staging), n elements */
 int avi_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
 

@@ -118,6 +118,58 @@ def test_gemm_bf16_tc_many_tiles_persistent(ops):
     assert (o.cpu().double() - ref).abs().max().item() < 1e-4
 
 
+@pytest.mark.parametrize("rows,N,K,act,out_dt", [
+    (256 * 51 + 9, 768, 192, 0, torch.float32),     # 52 m-tiles x 3 n-tiles: even super-tile count, ragged last rows
+    (256 * 62 + 64, 800, 128, 1, torch.bfloat16),    # 63 m-tiles (odd: the last super-tile has an idle pair), narrow last n-tile (32 columns)
+    (256 * 75, 256, 64, 0, torch.float32),           # one n-tile, 75 m-tiles -> 38 super-tiles on <= 37 clusters, single k-block
+])
+def test_gemm_bf16_tc_two_pair_clusters_multicast(ops, rows, N, K, act, out_dt):
+    """More than one wave of tiles: the opt-in 4-CTA cluster kernel (two pairs on consecutive m-tiles, W quarters multicast)
+    against the reference product AND bit for bit against the default pair kernel."""
+    from avi_talking_b200 import _lib
+    r = _rng(41)
+    A = torch.from_numpy(r.normal(size=(rows, K)).astype(np.float32)).bfloat16()
+    W = torch.from_numpy((r.normal(size=(N, K)) / math.sqrt(K)).astype(np.float32)).bfloat16()
+    b = torch.from_numpy(r.normal(size=(N,)).astype(np.float32))
+    o_pair = ops.linear(A.cuda(), W.cuda(), b.cuda(), act=act, out_dtype=out_dt)
+    old = _lib.load().avi_gemm_set_multicast(1)
+    try:
+        o = ops.linear(A.cuda(), W.cuda(), b.cuda(), act=act, out_dtype=out_dt)
+    finally:
+        _lib.load().avi_gemm_set_multicast(old)
+    ref = _gemm_ref(A.float(), W.float(), b, act, None)
+    tol = 1e-4 if out_dt == torch.float32 else 4e-2
+    assert (o.float().cpu().double() - ref).abs().max().item() < tol
+    assert torch.equal(o, o_pair)
+
+
+@pytest.mark.parametrize("multicast", [0, 1])
+def test_gemm_conv_mode_many_tiles_batched(ops, multicast):
+    """Strided conv as a GEMM over 5 clips x 13 m-tiles x 2 n-tiles (130 tiles: the cluster kernel, super-tiles straddling clips)."""
+    r = _rng(42)
+    B, L, Cin, Cout, k, s = 5, 2 * 256 * 13 - 100, 64, 512, 3, 2
+    La = L + (L & 1)
+    x = torch.zeros(B, La, Cin)
+    x[:, :L] = torch.from_numpy(r.normal(size=(B, L, Cin)).astype(np.float32))
+    w = torch.from_numpy((r.normal(size=(Cout, Cin, k)) / math.sqrt(Cin * k)).astype(np.float32))
+    dtype = torch.bfloat16
+    xq, wq = x.to(dtype).float(), w.to(dtype).float()
+    Lo = (L - k) // s + 1
+    Loa = Lo + (Lo & 1)
+    out = torch.full((B, Loa, Cout), float("nan"), dtype=dtype, device="cuda")
+    wp = w.permute(0, 2, 1).reshape(Cout, k * Cin).contiguous().to(dtype).cuda()
+    from avi_talking_b200 import _lib
+    old = _lib.load().avi_gemm_set_multicast(multicast)
+    try:
+        ops.gemm(x.to(dtype).cuda(), wp, None, out, batch=B, rows=Lo, N=Cout, K=k * Cin, act=1, conv_taps=k, conv_stride=s,
+                 a_ld=Cin, a_batch_stride=La * Cin, a_rows_alloc=La, c_ld=Cout, c_batch_stride=Loa * Cout)
+    finally:
+        _lib.load().avi_gemm_set_multicast(old)
+    ref = _conv_ref(xq[:, :L], wq, k, s)
+    got = out[:, :Lo].float().cpu().double()
+    assert (got - ref).abs().max().item() < 2e-2
+
+
 @pytest.mark.parametrize("out_dt", [torch.float32, torch.bfloat16])
 def test_conv0_gn_gelu(ops, out_dt):
     r = _rng(5)
