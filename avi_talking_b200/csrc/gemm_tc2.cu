@@ -517,6 +517,8 @@ static const char* tc2_check(const AviGemmArgs* a, bool tf32 = false) {
 
 using namespace avi;
 
+static std::atomic<int> g_gemm_multicast{getenv("AVI_GEMM_MULTICAST") != nullptr ? 1 : 0};
+
 #ifdef AVI_GEMM_TIMELINE
 extern "C" int avi_debug_timeline(long long* host_out) {
   return cudaMemcpyFromSymbol(host_out, g_timeline, sizeof(long long) * 3 * 64 * 8) == cudaSuccess ? 0 : 1;
@@ -528,8 +530,6 @@ extern "C" int avi_gemm_set_multicast(int on) {
 }
 
 extern "C" int avi_gemm_bf16_tc_supported(const AviGemmArgs* a) { return tc2_check(a) == nullptr ? 1 : 0; }
-
-static std::atomic<int> g_gemm_multicast{getenv("AVI_GEMM_MULTICAST") != nullptr ? 1 : 0};
 
 // how many 4-CTA clusters of this kernel the device can hold at once (GPCs whose SM count is not a multiple of 4 strand SMs)
 template <bool TF32>
