@@ -89,7 +89,7 @@ __global__ void act_fwd_kernel(const float* __restrict__ pre, float* __restrict_
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float x = pre[i];
-  const float y = mode == 1 ? gelu_erf(x) : fmaxf(x, 0.f);
+  const float y = mode == AVI_ACT_GELU ? gelu_erf(x) : mode == AVI_ACT_SILU ? x / (1.f + expf(-x)) : fmaxf(x, 0.f);
   if (o32) o32[i] = y;
   if (o16) o16[i] = __float2bfloat16_rn(y);
 }
@@ -101,6 +101,9 @@ __global__ void act_bwd_kernel(const float* __restrict__ pre, const float* __res
   if (mode == 1) {
     const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752440f));
     g = cdf + x * 0.3989422804014327f * expf(-0.5f * x * x);
+  } else if (mode == AVI_ACT_SILU) {
+    const float sg = 1.f / (1.f + expf(-x));
+    g = sg * (1.f + x * (1.f - sg));
   } else {
     g = x > 0.f ? 1.f : 0.f;
   }
@@ -154,6 +157,59 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
 #pragma unroll
     for (int u = 0; u < 32; ++u) {
       const int c = lane + 32 * u;
+      if (c < C) dx[row * C + c] = rstd * (g[u] - sg - v[u] * sgx);
+    }
+  }
+}
+
+// Wide rows (1024 < C <= 8192): one 256-thread block per row, same formulas.
+__global__ void __launch_bounds__(256) layernorm_bwd_wide_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                 const float* __restrict__ dy, float* __restrict__ dx,
+                                                                 float* __restrict__ dw, float* __restrict__ db, int C, float eps) {
+  __shared__ float red[64];
+  const int64_t row = blockIdx.x;
+  float v[32], g[32];
+  float s = 0.f, unused = 0.f;
+#pragma unroll
+  for (int u = 0; u < 32; ++u) {
+    const int c = threadIdx.x + 256 * u;
+    v[u] = c < C ? x[row * C + c] : 0.f;
+    s += v[u];
+  }
+  block_sum2(s, unused, red);
+  const float mean = s / C;
+  float q = 0.f;
+  unused = 0.f;
+#pragma unroll
+  for (int u = 0; u < 32; ++u) {
+    const int c = threadIdx.x + 256 * u;
+    if (c < C) q += (v[u] - mean) * (v[u] - mean);
+  }
+  block_sum2(q, unused, red);
+  const float rstd = rsqrtf(q / C + eps);
+  float sg = 0.f, sgx = 0.f;
+#pragma unroll
+  for (int u = 0; u < 32; ++u) {
+    const int c = threadIdx.x + 256 * u;
+    g[u] = 0.f;
+    if (c < C) {
+      const float xh = (v[u] - mean) * rstd;
+      const float d = dy[row * C + c];
+      g[u] = d * w[c];
+      sg += g[u];
+      sgx += g[u] * xh;
+      if (dw) atomicAdd(dw + c, d * xh);
+      if (db) atomicAdd(db + c, d);
+      v[u] = xh;
+    }
+  }
+  block_sum2(sg, sgx, red);
+  sg /= C;
+  sgx /= C;
+  if (dx) {
+#pragma unroll
+    for (int u = 0; u < 32; ++u) {
+      const int c = threadIdx.x + 256 * u;
       if (c < C) dx[row * C + c] = rstd * (g[u] - sg - v[u] * sgx);
     }
   }
@@ -668,20 +724,24 @@ extern "C" int avi_colsum(const float* x, float* out, int32_t R, int32_t N, int6
 }
 
 extern "C" int avi_act_fwd(const float* pre, float* out_f32, void* out_bf16, int64_t n, int32_t act, void* stream) {
-  AVI_REQUIRE(n > 0 && (act == AVI_ACT_GELU || act == AVI_ACT_RELU), "avi_act_fwd: bad arguments");
+  AVI_REQUIRE(n > 0 && (act == AVI_ACT_GELU || act == AVI_ACT_RELU || act == AVI_ACT_SILU), "avi_act_fwd: bad arguments");
   act_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(pre, out_f32, reinterpret_cast<__nv_bfloat16*>(out_bf16), n, act);
   return check_launch("act_fwd");
 }
 
 extern "C" int avi_act_bwd(const float* pre, const float* dout, float* dpre, int64_t n, int32_t act, void* stream) {
-  AVI_REQUIRE(n > 0 && (act == AVI_ACT_GELU || act == AVI_ACT_RELU), "avi_act_bwd: bad arguments");
+  AVI_REQUIRE(n > 0 && (act == AVI_ACT_GELU || act == AVI_ACT_RELU || act == AVI_ACT_SILU), "avi_act_bwd: bad arguments");
   act_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(pre, dout, dpre, n, act);
   return check_launch("act_bwd");
 }
 
 extern "C" int avi_layernorm_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, float* db, int64_t rows, int32_t C,
                                  float eps, void* stream) {
-  AVI_REQUIRE(rows > 0 && C > 0 && C <= 1024, "avi_layernorm_bwd: bad shape");
+  AVI_REQUIRE(rows > 0 && C > 0 && C <= 8192, "avi_layernorm_bwd: bad shape");
+  if (C > 1024) {
+    layernorm_bwd_wide_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(x, w, dy, dx, dw, db, C, eps);
+    return check_launch("layernorm_bwd_wide");
+  }
   layernorm_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x, w, dy, dx, dw, db, rows, C, eps);
   return check_launch("layernorm_bwd");
 }

@@ -238,6 +238,47 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float* __restr
   }
 }
 
+// Wide rows (1024 < C <= 8192: the 4096- and 2048-wide LayerNorms of BrainNetwork's training step): one 256-thread block per row,
+// up to 32 values per thread, two block reductions (mean, then the centred second moment - the same two-pass arithmetic).
+__global__ void __launch_bounds__(256) layernorm_wide_kernel(const float* __restrict__ x, const float* __restrict__ p,
+                                                             const float* __restrict__ w, const float* __restrict__ bsh,
+                                                             float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16, int C,
+                                                             float eps) {
+  __shared__ float red[64];
+  const int64_t row = blockIdx.x;
+  float v[32];
+  float s = 0.f, unused = 0.f;
+#pragma unroll
+  for (int u = 0; u < 32; ++u) {
+    const int c = threadIdx.x + u * 256;
+    v[u] = 0.f;
+    if (c < C) {
+      v[u] = x[row * C + c] + (p ? p[row * C + c] : 0.f);
+      s += v[u];
+    }
+  }
+  block_sum2(s, unused, red);
+  const float mean = s / C;
+  float q = 0.f;
+  unused = 0.f;
+#pragma unroll
+  for (int u = 0; u < 32; ++u) {
+    const int c = threadIdx.x + u * 256;
+    if (c < C) q += (v[u] - mean) * (v[u] - mean);
+  }
+  block_sum2(q, unused, red);
+  const float rstd = rsqrtf(q / C + eps);
+#pragma unroll
+  for (int u = 0; u < 32; ++u) {
+    const int c = threadIdx.x + u * 256;
+    if (c < C) {
+      const float y = (v[u] - mean) * rstd * w[c] + bsh[c];
+      if (out_f32) out_f32[row * C + c] = y;
+      if (out_bf16) out_bf16[row * C + c] = __float2bfloat16_rn(y);
+    }
+  }
+}
+
 template <int MODE>
 static void launch_layernorm(const float* x, const float* p, const float* w, const float* b, float* o32, __nv_bfloat16* o16,
                              int64_t rows, int C, float eps, cudaStream_t st) {
@@ -506,7 +547,11 @@ extern "C" int avi_w2v_lerp_layernorm(const void* in, int32_t in_dtype, int64_t 
 
 extern "C" int avi_layernorm(const float* x, const float* res, const float* w, const float* b, float* out_f32, void* out_bf16,
                              int64_t rows, int32_t C, float eps, void* stream) {
-  AVI_REQUIRE(rows > 0 && C > 0 && C <= 1024, "avi_layernorm: bad shape rows=%lld C=%d", (long long)rows, C);
+  AVI_REQUIRE(rows > 0 && C > 0 && C <= 8192, "avi_layernorm: bad shape rows=%lld C=%d", (long long)rows, C);
+  if (C > 1024) {
+    layernorm_wide_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(x, res, w, b, out_f32, (__nv_bfloat16*)out_bf16, C, eps);
+    return check_launch("layernorm_wide");
+  }
   if (res)
     launch_layernorm<2>(x, res, w, b, out_f32, (__nv_bfloat16*)out_bf16, rows, C, eps, (cudaStream_t)stream);
   else

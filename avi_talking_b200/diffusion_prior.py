@@ -54,7 +54,7 @@ class BrainNetwork(nn.Module):
 
     @torch.no_grad()
     def _pack(self):
-        key = (self.precision,) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+        key = (self.precision, ops.WEIGHT_EPOCH) + tuple((p.data_ptr(), p._version) for p in self.parameters())
         if self._packed is not None and key == self._packed_key:
             return self._packed
         bf16 = self.precision == "bf16"
@@ -70,12 +70,26 @@ class BrainNetwork(nn.Module):
         self._packed, self._packed_key = P, key
         return P
 
-    @torch.no_grad()
     def forward(self, x):
+        """.eval(): inference through the fused LayerNorm+GELU(+residual) path below (no autograd graph is recorded).
+        .train() with autograd recording and trainable parameters: prior_train.brain_forward_train (saved activations +
+        hand-written backward); the two Dropouts (:66,:72) draw their masks from torch's generator, or take
+        ``self.dropout_masks`` (1 + n_blocks pre-scaled fp32 masks) when a test injects them."""
         if not x.is_cuda:
             raise RuntimeError("avi_talking_b200.BrainNetwork runs on CUDA only (no CPU fallback)")
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            from .prior_train import brain_forward_train
+            masks = getattr(self, "dropout_masks", None)
+            if masks is None:
+                h, B = self.lin0[0].out_features, x.shape[0]
+                masks = [(torch.rand((B, h), device=x.device) >= pd).float() / (1.0 - pd) for pd in [self.lin0[3].p] + [m[3].p for m in self.mlp]]
+            return brain_forward_train(self, x, masks)
         if self.training:
-            raise NotImplementedError("train-mode dropout is not on the inference path; call .eval()")
+            raise NotImplementedError("train-mode dropout without gradient tracking: call .eval() for inference")
+        with torch.no_grad():
+            return self._forward_inference(x)
+
+    def _forward_inference(self, x):
         if x.ndim == 4:
             x = x.reshape(x.shape[0], -1)                                                    # :102-104
         P = self._pack()
@@ -90,7 +104,6 @@ class BrainNetwork(nn.Module):
         if not self.use_projector:
             return out
         h = out.reshape(-1, self.clip_size)                                                  # :115
-        rows = h.shape[0]
         for lw, lb, w, b in P["proj"]:
             h32, h16 = ops.ln_gelu_res(h.contiguous(), lw, lb, want_bf16=bf16)
             h = ops.linear(h16 if bf16 else h32, w, b)
@@ -216,7 +229,7 @@ class VersatileDiffusionPriorNetwork(nn.Module):
 
     @torch.no_grad()
     def _pack(self):
-        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        key = (ops.WEIGHT_EPOCH,) + tuple((p.data_ptr(), p._version) for p in self.parameters())
         if self._packed is not None and key == self._packed_key:
             return self._packed
         ct = self.causal_transformer
@@ -446,18 +459,33 @@ class InstructDiffusionPrior(nn.Module):
             tvals, sched = self._ddpm_schedule()
         return self._run(shape, text_cond, tvals, sched, generator, image_embed, noise)
 
-    def p_losses(self, image_embed, times, text_cond, noise=None):
-        """:369-402 (q_sample, denoiser with conditioning dropout, l2 loss to x_start)."""
-        raise NotImplementedError("the prior's training step (p_losses) is outside the inference hot path (SURVEY 8f.4)")
+    def p_losses(self, image_embed, times, text_cond, noise=None, keep_brain=None, keep_image=None):
+        """:369-402 (q_sample, denoiser with conditioning dropout, l2 loss to x_start) -> (loss, pred), differentiable with respect
+        to text_cond['text_embed'] and the network's parameters (prior_train.PriorLossTrain). keep_brain / keep_image inject the two
+        classifier-free-guidance keep masks that upstream draws with prob_mask_like (:258-262)."""
+        from .prior_train import prior_loss
+        if set(text_cond) != {"text_embed"}:
+            raise NotImplementedError("condition_on_text_encodings=False: text_cond carries text_embed only (:983-991)")
+        return prior_loss(self, text_cond["text_embed"], image_embed, times=times, noise=noise, keep_brain=keep_brain, keep_image=keep_image)
 
     def forward(self, text=None, image=None, voxel=None, text_embed=None, image_embed=None, text_encodings=None, *args, **kwargs):
-        """:404-456 -> (loss, pred)."""
-        raise NotImplementedError("the prior's training step (p_losses) is outside the inference hot path (SURVEY 8f.4)")
+        """:404-456 -> (loss, pred): random timesteps, then p_losses on image_embed * image_embed_scale (:446-453)."""
+        if text is not None or image is not None or text_encodings is not None:
+            raise NotImplementedError("no CLIP adapter inside the prior: pass text_embed / voxel and image_embed (train_diffusion_prior.py:449)")
+        if (text_embed is None) == (voxel is None) or image_embed is None:
+            raise ValueError("either text_embed or voxel, and image_embed, must be supplied")
+        if voxel is not None:                                                                 # :417-425
+            out = self.voxel2clip(voxel)
+            text_embed = out[0] if self.voxel2clip.use_projector else out
+        times = kwargs.pop("times", None)
+        x_start = ops.scale_f32(image_embed, float(self.image_embed_scale))                  # :453 (clip_target itself gets no gradient)
+        return self.p_losses(x_start, times, dict(text_embed=text_embed), *args, **kwargs)
 
 
 def soft_clip_loss(preds, targs, temp=0.125):
-    """train_diffusion_prior.py:125-133 (the contrastive term of the prior's training loss)."""
-    raise NotImplementedError("the prior's training step is outside the inference hot path (SURVEY 8f.4)")
+    """train_diffusion_prior.py:125-133 (the contrastive term of the prior's training loss); differentiable with respect to preds."""
+    from .prior_train import soft_clip_loss as _scl
+    return _scl(preds, targs, temp)
 
 
 @torch.no_grad()

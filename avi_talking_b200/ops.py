@@ -767,3 +767,144 @@ def affine_act(x, scale, shift, relu):
     _chk(_lib.load().avi_affine_act(_ptr(x), _ptr(scale), _ptr(shift), C.c_int64(x.numel() // x.shape[-1]), C.c_int32(x.shape[-1]),
                                     C.c_int32(1 if relu else 0), _stream()), "avi_affine_act")
     return x
+
+
+# ------------------------------------------------------------------------------------------------ diffusion-prior training step
+ACT_SILU = 4
+
+
+def prior_tokens_fwd(brain, null_brain, keep_brain, x0, noise, sqrt_ac, sqrt_1mac, times_i32, null_image, keep_image, learned_query, temb):
+    _need_cuda(brain, x0, noise, temb)
+    B, dim = x0.shape
+    tokens = torch.empty((B, 3, dim), dtype=torch.float32, device=x0.device)
+    x_noisy = torch.empty((B, dim), dtype=torch.float32, device=x0.device)
+    _chk(_lib.load().avi_prior_tokens_fwd(_ptr(brain), _ptr(null_brain), _ptr(keep_brain), _ptr(x0), _ptr(noise), _ptr(sqrt_ac), _ptr(sqrt_1mac),
+                                          _ptr(times_i32), _ptr(null_image), _ptr(keep_image), _ptr(learned_query), _ptr(temb), _ptr(tokens),
+                                          _ptr(x_noisy), C.c_int32(B), C.c_int32(dim), _stream()), "avi_prior_tokens_fwd")
+    return tokens, x_noisy
+
+
+def prior_tokens_bwd(dtokens, keep_brain, keep_image, dnull_brain, dnull_image, dlearned_query):
+    """-> dbrain [B,dim], dtemb [B,dim]; the three parameter gradients are accumulated into the given fp32 buffers."""
+    _need_cuda(dtokens)
+    B, _, dim = dtokens.shape
+    dbrain = torch.empty((B, dim), dtype=torch.float32, device=dtokens.device)
+    dtemb = torch.empty((B, dim), dtype=torch.float32, device=dtokens.device)
+    _chk(_lib.load().avi_prior_tokens_bwd(_ptr(dtokens.contiguous()), _ptr(keep_brain), _ptr(keep_image), _ptr(dbrain), _ptr(dtemb),
+                                          _ptr(dnull_brain), _ptr(dnull_image), _ptr(dlearned_query), C.c_int32(B), C.c_int32(dim), _stream()),
+         "avi_prior_tokens_bwd")
+    return dbrain, dtemb
+
+
+def prior_attn_fwd(q, kv, null_kv, rotary, rel_bias, B, heads=8, dim_head=64):
+    _need_cuda(q, kv)
+    out = torch.empty_like(q)
+    P = torch.empty((B, heads, 3, 4), dtype=torch.float32, device=q.device)
+    _chk(_lib.load().avi_prior_attn_fwd(_ptr(q), _ptr(kv), _ptr(null_kv), _ptr(rotary), _ptr(rel_bias), _ptr(out), _ptr(P), C.c_int32(B),
+                                        C.c_int32(3), C.c_int32(heads), C.c_int32(dim_head), _stream()), "avi_prior_attn_fwd")
+    return out, P
+
+
+def prior_attn_bwd(q, kv, null_kv, rotary, P, dout, B, heads=8, dim_head=64):
+    """-> dq, dkv, dnull_kv [2, dim_head], dbias [heads, 3, 4] (the per-sample partials folded by avi_colsum in a fixed order)."""
+    _need_cuda(q, kv, P, dout)
+    dq, dkv = torch.empty_like(q), torch.empty_like(kv)
+    dnull = torch.empty((B, 2 * dim_head), dtype=torch.float32, device=q.device)
+    dS = torch.empty((B, heads * 12), dtype=torch.float32, device=q.device)
+    _chk(_lib.load().avi_prior_attn_bwd(_ptr(q), _ptr(kv), _ptr(null_kv), _ptr(rotary), _ptr(P), _ptr(dout.contiguous()), _ptr(dq), _ptr(dkv),
+                                        _ptr(dnull), _ptr(dS), C.c_int32(B), C.c_int32(3), C.c_int32(heads), C.c_int32(dim_head), _stream()),
+         "avi_prior_attn_bwd")
+    return dq, dkv, colsum(dnull).view(2, dim_head), colsum(dS).view(heads, 3, 4)
+
+
+def swiglu_fwd(h):
+    _need_cuda(h)
+    rows, two_i = h.shape
+    y = torch.empty((rows, two_i // 2), dtype=torch.float32, device=h.device)
+    _chk(_lib.load().avi_swiglu_fwd(_ptr(h), _ptr(y), C.c_int64(rows), C.c_int32(two_i // 2), _stream()), "avi_swiglu_fwd")
+    return y
+
+
+def swiglu_bwd(h, dy):
+    _need_cuda(h, dy)
+    dh = torch.empty_like(h)
+    _chk(_lib.load().avi_swiglu_bwd(_ptr(h), _ptr(dy.contiguous()), _ptr(dh), C.c_int64(h.shape[0]), C.c_int32(h.shape[1] // 2), _stream()),
+         "avi_swiglu_bwd")
+    return dh
+
+
+def rows_stat_div(x, mode):
+    """mode 0: x / rowmax (LayerNorm(stable=True)), mode 1: F.normalize. -> (out, stat [rows])"""
+    _need_cuda(x)
+    x = x.contiguous()
+    rows, Cc = x.numel() // x.shape[-1], x.shape[-1]
+    out = torch.empty_like(x)
+    stat = torch.empty((rows,), dtype=torch.float32, device=x.device)
+    _chk(_lib.load().avi_rows_stat_div(_ptr(x), _ptr(out), _ptr(stat), C.c_int64(rows), C.c_int32(Cc), C.c_int32(mode), _stream()),
+         "avi_rows_stat_div")
+    return out, stat
+
+
+def rows_stat_div_bwd(y, dy, stat, mode):
+    _need_cuda(y, dy, stat)
+    rows, Cc = y.numel() // y.shape[-1], y.shape[-1]
+    dx = torch.empty_like(y)
+    _chk(_lib.load().avi_rows_stat_div_bwd(_ptr(y), _ptr(dy.contiguous()), _ptr(stat), _ptr(dx), C.c_int64(rows), C.c_int32(Cc), C.c_int32(mode),
+                                           _stream()), "avi_rows_stat_div_bwd")
+    return dx
+
+
+def mul_f32(a, b):
+    _need_cuda(a, b)
+    assert a.shape == b.shape and a.is_contiguous() and b.is_contiguous()
+    y = torch.empty_like(a)
+    _chk(_lib.load().avi_mul_f32(_ptr(a), _ptr(b), _ptr(y), C.c_int64(a.numel()), _stream()), "avi_mul_f32")
+    return y
+
+
+def scale_f32(a, alpha):
+    _need_cuda(a)
+    a = a.contiguous().float()
+    y = torch.empty_like(a)
+    _chk(_lib.load().avi_scale_f32(_ptr(a), C.c_float(alpha), _ptr(y), C.c_int64(a.numel()), _stream()), "avi_scale_f32")
+    return y
+
+
+def soft_clip_loss_grad(pt, tt, temp):
+    """pt = preds targs^T, tt = targs targs^T [B,B] fp32 -> (loss fp64 device scalar, d loss / d pt [B,B])."""
+    _need_cuda(pt, tt)
+    B = pt.shape[0]
+    dsim = torch.empty_like(pt)
+    loss = torch.empty((1,), dtype=torch.float64, device=pt.device)
+    scratch = torch.empty((3 * B,), dtype=torch.float32, device=pt.device)
+    _chk(_lib.load().avi_soft_clip_loss_grad(_ptr(pt), _ptr(tt), _ptr(scratch), _ptr(dsim), _ptr(loss), C.c_int32(B), C.c_float(temp), _stream()),
+         "avi_soft_clip_loss_grad")
+    return loss, dsim
+
+
+def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+    _need_cuda(p, g, m, v)
+    _chk(_lib.load().avi_adamw_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), C.c_int64(p.numel()), C.c_float(lr), C.c_float(beta1), C.c_float(beta2),
+                                    C.c_float(eps), C.c_float(weight_decay), C.c_int32(step), C.c_float(grad_scale), _stream()), "avi_adamw_step")
+
+
+class AviAdamwEntry(C.Structure):
+    """Mirror of AviAdamwEntry in include/avi_b200.h."""
+    _fields_ = [("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("n", C.c_int64), ("weight_decay", C.c_float),
+                ("reserved", C.c_int32)]
+
+
+def adamw_table(items):
+    """items: (param, grad, m, v, weight_decay) tensors -> device-resident uint8 tensor holding the AviAdamwEntry records."""
+    arr = (AviAdamwEntry * len(items))()
+    for i, (p, g, m, v, wd) in enumerate(items):
+        _need_cuda(p, g, m, v)
+        assert p.is_contiguous() and g.is_contiguous() and g.numel() == p.numel()
+        arr[i] = AviAdamwEntry(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), wd, 0)
+    host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+    return host.to(items[0][0].device)
+
+
+def adamw_multi(table, n_entries, lr, beta1, beta2, eps, step, grad_scale=1.0):
+    _chk(_lib.load().avi_adamw_multi(_ptr(table), C.c_int32(n_entries), C.c_float(lr), C.c_float(beta1), C.c_float(beta2), C.c_float(eps),
+                                     C.c_int32(step), C.c_float(grad_scale), _stream()), "avi_adamw_multi")

@@ -45,7 +45,8 @@ int64_t avi_launch_count(void);
  * A rows may overlap (Conv1d as a GEMM over time-major activations): the row for (b, r) starts at
  *   A + b*a_batch_stride + r*conv_stride*a_ld  and is conv_taps*a_ld... see AviGemmArgs below.
  */
-enum { AVI_ACT_NONE = 0, AVI_ACT_GELU = 1 /* exact erf */, AVI_ACT_RELU = 2, AVI_ACT_QUICK_GELU = 3 /* x * sigmoid(1.702 x), CLIP */ };
+enum { AVI_ACT_NONE = 0, AVI_ACT_GELU = 1 /* exact erf */, AVI_ACT_RELU = 2, AVI_ACT_QUICK_GELU = 3 /* x * sigmoid(1.702 x), CLIP */,
+       AVI_ACT_SILU = 4 /* x * sigmoid(x): avi_act_fwd / avi_act_bwd only (the prior's time MLP) */ };
 enum { AVI_DT_F32 = 0, AVI_DT_BF16 = 1, AVI_DT_TF32 = 2 /* fp32 storage rounded to TF32 (operand producers only) */ };
 
 typedef struct AviGemmArgs {
@@ -120,7 +121,7 @@ int avi_w2v_lerp_layernorm(const void* in, int32_t in_dtype, int64_t in_batch_st
                            void* stream);
 
 /* y = LayerNorm(x (+ res)) over the last dim; x, res fp32 [rows, C] (res may be NULL); writes fp32 and/or bf16 copies.
- * (HF encoder layer_norm / final_layer_norm; nn.TransformerDecoderLayer norm1-3) */
+ * (HF encoder layer_norm / final_layer_norm; nn.TransformerDecoderLayer norm1-3; C <= 8192: one warp per row up to 1024, one block above) */
 int avi_layernorm(const float* x, const float* res, const float* w, const float* b, float* out_f32, void* out_bf16, int64_t rows, int32_t C,
                   float eps, void* stream);
 
@@ -346,10 +347,10 @@ int avi_ff_add_style_pe(float* x, const float* style, int64_t style_stride, cons
                         int32_t period, void* stream);
 /* out[n] (+)= sum_r x[r, n]   (bias gradients) */
 int avi_colsum(const float* x, float* out, int32_t R, int32_t N, int64_t ld, int32_t accumulate, void* stream);
-/* act = AVI_ACT_GELU | AVI_ACT_RELU: out = act(pre) ; dpre = dout * act'(pre) */
+/* act = AVI_ACT_GELU | AVI_ACT_RELU | AVI_ACT_SILU: out = act(pre) ; dpre = dout * act'(pre) */
 int avi_act_fwd(const float* pre, float* out_f32, void* out_bf16, int64_t n, int32_t act, void* stream);
 int avi_act_bwd(const float* pre, const float* dout, float* dpre, int64_t n, int32_t act, void* stream);
-/* LayerNorm backward over the last dim: dx (may be NULL), dw += , db += (may be NULL; accumulate with atomics, zero them first) */
+/* LayerNorm backward over the last dim (C <= 8192): dx (may be NULL), dw += , db += (may be NULL; accumulate with atomics, zero them first) */
 int avi_layernorm_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, float* db, int64_t rows, int32_t C, float eps,
                       void* stream);
 /* attention for training (T <= 128): forward keeps P [B,H,T,T] (P may be NULL when no backward follows); bias_mode 0 none, 1 FaceFormer biased causal mask
@@ -377,6 +378,60 @@ int avi_add_f32(const float* a, const float* b, float* y, int64_t n, void* strea
 /* align_corners linear resample over time only (models/lib/wav2vec.py:67-73), fp32 output [B*T_out, C] */
 int avi_w2v_lerp(const void* in, int32_t in_dtype, int64_t in_batch_stride, float* out, int32_t B, int32_t T_in, int32_t T_out, int32_t C,
                  void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------------------------
+ * Diffusion-prior TRAINING step: train_diffusion_prior.py:422-499, models/diffusion_prior.py:369-456 (p_losses /
+ * forward) over dalle2_pytorch's Attention / FeedForward / LayerNorm. Dense contractions go through avi_gemm_*; these are the rest.
+ * All fp32, dim 128 / 3 tokens / 8 heads x 64 (the configuration train_diffusion_prior.py:966-991 builds).
+ * --------------------------------------------------------------------------------------------------------------------------------- */
+/* VersatileDiffusionPriorNetwork.forward :258-306 fused with NoiseScheduler.q_sample (p_losses :372):
+ *   tokens[b] = [ keep_brain[b] ? brain[b] : null_brain ; temb[b] ; (keep_image[b] ? sqrt_ac[t_b] x0[b] + sqrt_1mac[t_b] noise[b] : null_image)
+ *                 + learned_query ]      (keep_* are 0/1 floats: the classifier-free-guidance masks of :258-281 as INPUTS)
+ * x_noisy (may be NULL) receives the q_sample result [B, dim]. */
+int avi_prior_tokens_fwd(const float* brain, const float* null_brain, const float* keep_brain, const float* x0, const float* noise,
+                         const float* sqrt_ac, const float* sqrt_1mac, const int32_t* times, const float* null_image,
+                         const float* keep_image, const float* learned_query, const float* temb, float* tokens, float* x_noisy, int32_t B,
+                         int32_t dim, void* stream);
+/* dtokens [B,3,dim] -> dbrain [B,dim], dtemb [B,dim]; dnull_brain / dnull_image / dlearned_query [dim] are ACCUMULATED (+=) */
+int avi_prior_tokens_bwd(const float* dtokens, const float* keep_brain, const float* keep_image, float* dbrain, float* dtemb,
+                         float* dnull_brain, float* dnull_image, float* dlearned_query, int32_t B, int32_t dim, void* stream);
+/* dalle2_pytorch.Attention core (cosine_sim, scale 16, causal=False) for n_tokens = 3 queries against null + 3 keys:
+ * q [3B, heads*dim_head] and kv [3B, 2*dim_head] are the raw to_q / to_kv projections, null_kv [2, dim_head], rotary [3, 16, 2]
+ * (cos, sin of position * freq), rel_bias [heads, 3, 4] -> out [3B, heads*dim_head] (before to_out), P [B, heads, 3, 4] saved. */
+int avi_prior_attn_fwd(const float* q, const float* kv, const float* null_kv, const float* rotary, const float* rel_bias, float* out,
+                       float* P, int32_t B, int32_t n_tokens, int32_t heads, int32_t dim_head, void* stream);
+/* -> dq, dkv (shapes of q, kv); per-sample partials dnull [B, 2*dim_head] and dS [B, heads*3*4] (fold with avi_colsum: deterministic) */
+int avi_prior_attn_bwd(const float* q, const float* kv, const float* null_kv, const float* rotary, const float* P, const float* dout,
+                       float* dq, float* dkv, float* dnull_per_sample, float* dS_per_sample, int32_t B, int32_t n_tokens, int32_t heads,
+                       int32_t dim_head, void* stream);
+/* SwiGLU of dalle2_pytorch.FeedForward: h [rows, 2*inner] = (a | gate) -> y = a * silu(gate) ; dh from (h, dy) */
+int avi_swiglu_fwd(const float* h, float* y, int64_t rows, int32_t inner, void* stream);
+int avi_swiglu_bwd(const float* h, const float* dy, float* dh, int64_t rows, int32_t inner, void* stream);
+/* out = x / stat per row; mode 0: stat = row maximum (LayerNorm(stable=True), maximum detached), mode 1: stat = max(l2 norm, 1e-12)
+ * (F.normalize). Backward: mode 0 dx = dy / stat ; mode 1 dx = (dy - y (y . dy)) / stat with y the forward output. */
+int avi_rows_stat_div(const float* x, float* out, float* stat, int64_t rows, int32_t C, int32_t mode, void* stream);
+int avi_rows_stat_div_bwd(const float* y, const float* dy, const float* stat, float* dx, int64_t rows, int32_t C, int32_t mode, void* stream);
+int avi_mul_f32(const float* a, const float* b, float* y, int64_t n, void* stream);   /* dropout with the (pre-scaled) mask as an input */
+int avi_scale_f32(const float* a, float alpha, float* y, int64_t n, void* stream);     /* y = alpha * a (image_embed * image_embed_scale, :453) */
+/* soft_clip_loss (train_diffusion_prior.py:125-133) from the raw products pt = preds targs^T and tt = targs targs^T [B,B]:
+ * loss (fp64 device scalar) and dsim = d loss / d pt [B,B]; lse_scratch holds 3*B floats. */
+int avi_soft_clip_loss_grad(const float* pt, const float* tt, float* lse_scratch, float* dsim, double* loss, int32_t B, float temp,
+                            void* stream);
+/* the same update for a whole parameter list in ONE launch: a device-resident table of n_entries records */
+typedef struct AviAdamwEntry {
+  float* p;            /* parameter, updated in place */
+  const float* g;      /* gradient                    */
+  float* m;            /* first moment                */
+  float* v;            /* second moment               */
+  int64_t n;           /* elements                    */
+  float weight_decay;  /* 0 for the exempt group      */
+  int32_t reserved;
+} AviAdamwEntry;
+int avi_adamw_multi(const AviAdamwEntry* table_dev, int32_t n_entries, float lr, float beta1, float beta2, float eps, int32_t step,
+                    float grad_scale, void* stream);
+/* torch.optim.AdamW (decoupled weight decay), one parameter tensor per call */
+int avi_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                   float weight_decay, int32_t step, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

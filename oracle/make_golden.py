@@ -309,6 +309,95 @@ def golden_prior():
 
 
 
+def prior_train_inputs(B=6, seed=77):
+    """Seeded inputs of one prior-training iteration (every stochastic draw of the reference as an explicit tensor)."""
+    g = torch.Generator().manual_seed(seed)
+    voxel = torch.randn(B, 768, generator=g)                                   # mean CLIP text embedding (:438-439)
+    clip_target = torch.randn(B, 1, 128, generator=g) * 0.5                    # EMOTE style latent (:195)
+    times = torch.tensor([3, 97, 40, 0, 62, 15][:B] + [int(x) for x in torch.randint(0, 100, (max(0, B - 6),), generator=g)], dtype=torch.long)
+    noise = torch.randn(B, 1, 128, generator=g)
+    keep_brain = torch.tensor(([True, False, True, True, False, True] * ((B + 5) // 6))[:B])
+    keep_image = torch.tensor(([True, True, False, True, False, True] * ((B + 5) // 6))[:B])
+    masks = [(torch.rand(B, 4096, generator=g) >= p).float() / (1 - p) for p in (0.5, 0.15, 0.15, 0.15, 0.15)]
+    return dict(voxel=voxel, clip_target=clip_target, times=times, noise=noise, keep_brain=keep_brain, keep_image=keep_image, masks=masks)
+
+
+def sample_tensor(t, n=2048):
+    """Compact fingerprint of a (possibly huge) tensor: n evenly strided elements, the sum and the l2 norm."""
+    f = t.detach().reshape(-1).double()
+    step = max(1, f.numel() // n)
+    return f[::step][:n].float().numpy(), np.array([float(f.sum()), float(f.norm())])
+
+
+class _MaskDropout(nn.Module):
+    def __init__(self, mask):
+        super().__init__()
+        self.mask = mask
+
+    def forward(self, x):
+        return x * self.mask
+
+
+def golden_prior_train():
+    """One iteration of train_diffusion_prior.py:434-486 executed on the reference's OWN classes (BrainNetwork,
+    VersatileDiffusionPriorNetwork, InstructDiffusionPrior.forward / p_losses) over the dalle2 stand-in, its own soft_clip_loss,
+    loss.backward() and torch.optim.AdamW with the groups of :996-1004. Draws are injected: timesteps (sample_random_times),
+    noise (p_losses' noise argument), the two keep masks (prob_mask_like), BrainNetwork's Dropout masks."""
+    from . import synth
+    sd = synth.prior_state()
+    ns = _exec_reference_prior_classes([])
+    fns = _exec_reference_functions(os.path.join(REF, "train_diffusion_prior.py"), ("soft_clip_loss",), dict(torch=torch, nn=nn))
+    inp = prior_train_inputs()
+    for variant in ("eval", "dropout"):
+        brain = ns["BrainNetwork"](in_dim=768, out_dim=128, clip_size=128, use_projector=True)
+        net = ns["VersatileDiffusionPriorNetwork"](dim=128, depth=6, dim_head=64, heads=8, causal=False, num_tokens=1,
+                                                   learned_query_mode="pos_emb")
+        prior = ns["InstructDiffusionPrior"](net=net, image_embed_dim=128, condition_on_text_encodings=False, timesteps=100,
+                                             cond_drop_prob=0.2, image_embed_scale=None, voxel2clip=brain)
+        prior.load_state_dict(sd, strict=False)
+        prior.train()
+        if variant == "dropout":
+            brain.lin0[3] = _MaskDropout(inp["masks"][0])
+            for i in range(4):
+                brain.mlp[i][3] = _MaskDropout(inp["masks"][i + 1])
+        else:
+            brain.eval()
+        prior.noise_scheduler.sample_random_times = lambda b: inp["times"]
+        keep = [inp["keep_brain"], inp["keep_image"]]
+        ns["prob_mask_like"] = lambda shape, prob, device: keep.pop(0)
+        no_decay = ["bias", "LayerNorm.bias", "LayerNorm.weight"]                                   # :997-1003, verbatim grouping
+        groups = [
+            {"params": [p for n, p in prior.net.named_parameters() if not any(nd in n for nd in no_decay)], "weight_decay": 1e-2},
+            {"params": [p for n, p in prior.net.named_parameters() if any(nd in n for nd in no_decay)], "weight_decay": 0.0},
+            {"params": [p for n, p in prior.voxel2clip.named_parameters() if not any(nd in n for nd in no_decay)], "weight_decay": 1e-2},
+            {"params": [p for n, p in prior.voxel2clip.named_parameters() if any(nd in n for nd in no_decay)], "weight_decay": 0.0}]
+        opt = torch.optim.AdamW(groups, lr=3e-4)
+        opt.zero_grad()
+        voxel, clip_target = inp["voxel"].clone().requires_grad_(True), inp["clip_target"].clone().requires_grad_(True)
+        clip_voxels, clip_voxels_proj = prior.voxel2clip(voxel)                                     # :441
+        clip_voxels = clip_voxels.view(len(voxel), -1, 128)                                         # :445
+        loss_prior, aligned = prior(text_embed=clip_voxels, image_embed=clip_target, noise=inp["noise"])   # :449
+        assert not keep
+        clip_voxels_norm = nn.functional.normalize(clip_voxels_proj.flatten(1), dim=-1)             # :455-456
+        clip_target_norm = nn.functional.normalize(clip_target.flatten(1), dim=-1)
+        temp = 0.0045
+        loss_nce = fns["soft_clip_loss"](clip_voxels_norm, clip_target_norm, temp=temp)             # :465-468
+        loss = loss_nce + 30 * loss_prior                                                           # :474
+        loss.backward()
+        out = dict(loss_nce=np.array(float(loss_nce)), loss_prior=np.array(float(loss_prior)), pred=aligned.detach().numpy(),
+                   temp=np.array(temp), names=np.array([n for n, p in prior.named_parameters() if p.requires_grad]))
+        for n, p in prior.named_parameters():
+            if p.requires_grad:
+                assert p.grad is not None, n
+                out["g:" + n], out["gs:" + n] = sample_tensor(p.grad)
+        opt.step()
+        for n, p in prior.named_parameters():
+            if p.requires_grad:
+                out["p:" + n], out["ps:" + n] = sample_tensor(p)
+        np.savez_compressed(os.path.join(GOLD, f"prior_train_{variant}.npz"), **out)
+        print(f"prior_train_{variant}.npz", float(loss_nce), float(loss_prior), len(out))
+
+
 def build_reference_talking_head(sd, sd_w2v):
     """The reference's EMOTE inference graph assembled from its OWN classes (stub-imported, oracle/_inferno_import.py):
     TalkingHeadBase.forward over Wav2Vec2Encoder/Wav2Vec2ModelResampled, LinearSequenceEncoder, BertPriorDecoder (+ real
@@ -644,6 +733,7 @@ def main():
     golden_wav2vec2()
     golden_faceformer()
     golden_prior()
+    golden_prior_train()
     golden_emote()
     golden_train()
     golden_frontend()

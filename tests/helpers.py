@@ -1,4 +1,5 @@
 """Builders shared by the GPU tests: drop-in models loaded with the seeded synthetic weights."""
+import numpy as np
 import torch
 
 from avi_talking_b200 import synth
@@ -37,3 +38,27 @@ def build_flame(n_shape=100, device="cuda", mediapipe=True, tmpdir="/tmp/avi_fla
     m = (FLAME_mediapipe(cfg) if mediapipe else FLAME(cfg)).to(device)
     m.precision = precision
     return m
+
+
+# ---- prior-training fixtures (tests/golden/prior_train_*.npz hold strided fingerprints of every gradient / updated parameter)
+def fingerprint(t, n=2048):
+    f = t.detach().reshape(-1).double()
+    step = max(1, f.numel() // n)
+    return f[::step][:n].float().numpy(), np.array([float(f.sum()), float(f.norm())])
+
+
+def check_against_golden(g, got_grads, got_new, grad_tol, param_tol, names=None):
+    """got_* : {state-dict key: tensor}. Gradients are compared relative to the tensor's own l2 norm per element count."""
+    worst_g = worst_p = 0.0
+    for n in (names if names is not None else [str(x) for x in g["names"]]):
+        gs, gn = g["g:" + n], g["gs:" + n]
+        s, sn = fingerprint(got_grads[n])
+        scale = max(float(np.abs(gs).max()), float(gn[1]) / max(1.0, got_grads[n].numel()) ** 0.5, 1e-12)
+        worst_g = max(worst_g, float(np.abs(s - gs).max()) / scale, abs(sn[1] - gn[1]) / max(gn[1], 1e-12))
+        ps = g["p:" + n]
+        worst_p = max(worst_p, float(np.abs(fingerprint(got_new[n])[0] - ps).max()))
+    assert worst_g < grad_tol, f"worst relative gradient error {worst_g}"
+    assert worst_p < param_tol, f"worst absolute error of an AdamW-updated parameter {worst_p}"
+    return worst_g, worst_p
+
+

@@ -133,7 +133,7 @@ def test_wav2vec2_feature_extractor_stage(golden):
 
 
 # ------------------------------------------------------------------------------------------------ decoder
-@pytest.mark.parametrize("fd", [64, 128])
+@pytest.mark.parametrize("fd", [64, 128, 256])
 def test_decoder_ar_matches_oracle(fd):
     """forward_ff autoregressive branch on given hidden states, batched over 3 clips, against the literal O(T^2) oracle."""
     m = build_faceformer("fp32", fd=fd, seed=10 + fd)
@@ -150,7 +150,7 @@ def test_decoder_ar_matches_oracle(fd):
     assert relerr(got.cpu() - template, disp_ref) < 1e-4
 
 
-@pytest.mark.parametrize("fd", [64, 128])
+@pytest.mark.parametrize("fd", [64, 128, 256])
 def test_decoder_teacher_forced_matches_oracle(fd):
     m = build_faceformer("fp32", fd=fd, seed=10 + fd)
     sd = synth.faceformer_state(fd=fd, seed=10 + fd)
