@@ -47,6 +47,8 @@ struct PriorParams {
   float* out;               // [B][128]
   int B, steps, depth;
   float out_scale;          // result multiplied by this (1 / image_embed_scale)
+  const float* null_pred;   // [steps][128] or nullptr: the denoiser's output with BOTH conditions replaced by the null embeddings
+  float cond_scale;         // classifier-free guidance: x0 = null + (x0 - null) * cond_scale (forward_with_cond_scale :209-221)
 };
 
 // out[r][n] = sum_k inT[k][r] * Wt[k][n]   (r < R rows, all in shared memory except Wt)
@@ -307,7 +309,11 @@ __global__ void __launch_bounds__(PR_THREADS, 1) prior_sample_kernel(const Prior
     for (int i = threadIdx.x; i < S * PR_DIM; i += PR_THREADS) {
       const int s = i / PR_DIM, c = i % PR_DIM;
       if (s0 + s >= p.B) continue;
-      const float x0 = buf[(3 * s + 2) * PR_DIM + c];
+      float x0 = buf[(3 * s + 2) * PR_DIM + c];
+      if (p.null_pred != nullptr) {   // the null pass sees neither the text nor the noisy embedding: one vector per step, precomputed
+        const float nl = __ldg(p.null_pred + (int64_t)step * PR_DIM + c);
+        x0 = nl + (x0 - nl) * p.cond_scale;
+      }
       const float x = xcur[i];
       const float nz = __ldg(p.noise + ((int64_t)step * p.B + s0 + s) * PR_DIM + c);
       float xn;
@@ -433,6 +439,12 @@ extern "C" int avi_prior_time_embed(const float* times, const float* w0t, const 
 extern "C" int avi_prior_sample(const AviPriorNet* net, const float* temb, const float* sched, const float* text_embed,
                                 const float* x_init, const float* noise, float* out, int32_t B, int32_t steps, float out_scale,
                                 int32_t samples_per_cta, void* stream) {
+  return avi_prior_sample_cfg(net, temb, sched, text_embed, x_init, noise, nullptr, 1.f, out, B, steps, out_scale, samples_per_cta, stream);
+}
+
+extern "C" int avi_prior_sample_cfg(const AviPriorNet* net, const float* temb, const float* sched, const float* text_embed,
+                                    const float* x_init, const float* noise, const float* null_pred, float cond_scale, float* out,
+                                    int32_t B, int32_t steps, float out_scale, int32_t samples_per_cta, void* stream) {
   AVI_REQUIRE(net != nullptr && net->dim == PR_DIM && net->heads == PR_HEADS && net->dim_head == PR_DH && net->ff_inner == PR_FF,
               "avi_prior_sample: only the reference configuration (dim 128, 8 heads x 64, ff inner 512) is built");
   AVI_REQUIRE(B > 0 && steps > 0 && net->depth > 0, "avi_prior_sample: bad sizes");
@@ -453,6 +465,8 @@ extern "C" int avi_prior_sample(const AviPriorNet* net, const float* temb, const
   p.steps = steps;
   p.depth = net->depth;
   p.out_scale = out_scale;
+  p.null_pred = null_pred;
+  p.cond_scale = cond_scale;
   int S = samples_per_cta;
   const int half_sms = device_sms() / 2;
   if (S <= 0) S = (B + 3) / 4 >= half_sms ? 4 : ((B + 1) / 2 >= half_sms ? 2 : 1);  // fill the SMs before batching per CTA

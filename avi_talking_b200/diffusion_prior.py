@@ -271,14 +271,22 @@ class VersatileDiffusionPriorNetwork(nn.Module):
     @torch.no_grad()
     def forward(self, image_embed, diffusion_timesteps, *, self_cond=None, brain_embed=None, text_embed=None, brain_cond_drop_prob=0.0,
                 text_cond_drop_prob=None, image_cond_drop_prob=0.0):
+        return self._forward(image_embed, diffusion_timesteps, 1.0, self_cond=self_cond, brain_embed=brain_embed, text_embed=text_embed,
+                             brain_cond_drop_prob=brain_cond_drop_prob, text_cond_drop_prob=text_cond_drop_prob,
+                             image_cond_drop_prob=image_cond_drop_prob)
+
+    @torch.no_grad()
+    def _forward(self, image_embed, diffusion_timesteps, _cond_scale, *, self_cond=None, brain_embed=None, text_embed=None,
+                 brain_cond_drop_prob=0.0, text_cond_drop_prob=None, image_cond_drop_prob=0.0):
         """:223-313 at inference (drop probabilities 0). One denoiser evaluation = the sampling kernel run for a single step in
         'x = x0' mode; every sample must share one timestep value (as they do in every sampling loop)."""
         if text_embed is not None:
             brain_embed = text_embed
         if text_cond_drop_prob is not None:
             brain_cond_drop_prob = text_cond_drop_prob
-        if brain_cond_drop_prob != 0.0 or image_cond_drop_prob != 0.0:
-            raise NotImplementedError("conditioning dropout (training / classifier-free guidance) is not on the inference path")
+        if brain_cond_drop_prob not in (0.0, 1.0, 0, 1) or image_cond_drop_prob not in (0.0, 1.0, 0, 1):
+            raise NotImplementedError("random conditioning dropout belongs to the training step (prior_train.PriorLossTrain); "
+                                      "inference takes drop probabilities 0 or 1 (the null pass of classifier-free guidance)")
         if not image_embed.is_cuda:
             raise RuntimeError("avi_talking_b200 prior network runs on CUDA only (no CPU fallback)")
         B = image_embed.shape[0]
@@ -289,14 +297,38 @@ class VersatileDiffusionPriorNetwork(nn.Module):
         temb = self.time_embeddings(t[:1])
         sched = torch.tensor([[2.0, 0, 0, 0, 0, 0]], dtype=torch.float32, device=image_embed.device)
         x = image_embed.reshape(B, -1).float().contiguous()
-        out = ops.prior_sample(P["struct"], temb, sched, brain_embed.reshape(B, -1).float().contiguous(), x,
-                               torch.zeros((1, B, self.dim), dtype=torch.float32, device=x.device), 1.0)
+        text = brain_embed.reshape(B, -1).float().contiguous()
+        if brain_cond_drop_prob == 1:                                                        # torch.where(keep_mask, ., null) :265-278
+            text = self.null_brain_embeds.detach().reshape(1, -1).expand(B, -1).contiguous()
+        if image_cond_drop_prob == 1:
+            x = self.null_image_embed.detach().reshape(1, -1).expand(B, -1).contiguous()
+        null_pred = self.null_predictions(t[:1]) if _cond_scale != 1 else None
+        out = ops.prior_sample(P["struct"], temb, sched, text, x, torch.zeros((1, B, self.dim), dtype=torch.float32, device=x.device), 1.0,
+                               null_pred=null_pred, cond_scale=float(_cond_scale))
         return out.view(B, 1, self.dim)
 
+    @torch.no_grad()
+    def null_predictions(self, tvals: torch.Tensor) -> torch.Tensor:
+        """[steps] timestep values -> [steps,128]: the denoiser's output when BOTH conditions are dropped (:219). That pass sees the
+        two null embeddings and the time token only, so it is one vector per timestep, shared by every sample and every call with
+        these weights: one single-sample launch per step, cached per weight version."""
+        P = self._pack()
+        cache = P.setdefault("null_pred", {})
+        key = tuple(float(v) for v in tvals.reshape(-1).tolist())
+        if key not in cache:
+            dev = self.learned_query.device
+            temb = self.time_embeddings(tvals.float().to(dev))
+            sched = torch.tensor([[2.0, 0, 0, 0, 0, 0]], dtype=torch.float32, device=dev)
+            text = self.null_brain_embeds.detach().reshape(1, -1).float().contiguous()
+            x = self.null_image_embed.detach().reshape(1, -1).float().contiguous()
+            z = torch.zeros((1, 1, self.dim), dtype=torch.float32, device=dev)
+            cache[key] = torch.cat([ops.prior_sample(P["struct"], temb[k:k + 1].contiguous(), sched, text, x, z, 1.0) for k in range(len(key))])
+        return cache[key]
+
     def forward_with_cond_scale(self, *args, cond_scale=1.0, **kwargs):
-        if cond_scale != 1:
-            raise NotImplementedError("cond_scale != 1 (classifier-free guidance) is not used by the reference's inference (:828)")
-        return self.forward(*args, **kwargs)
+        """:209-221: logits when cond_scale == 1, else null_logits + (logits - null_logits) * cond_scale (combined inside the kernel)."""
+        image_embed, diffusion_timesteps = args
+        return self._forward(image_embed, diffusion_timesteps, cond_scale, **kwargs)
 
 
 # ------------------------------------------------------------------------------------------------ scheduler + sampler
@@ -396,7 +428,7 @@ class InstructDiffusionPrior(nn.Module):
         return torch.randn(shape, device=self.device, generator=generator)
 
     @torch.no_grad()
-    def _run(self, shape, text_cond, tvals, sched, generator, image_embed, noise):
+    def _run(self, shape, text_cond, tvals, sched, generator, image_embed, noise, cond_scale=1.0):
         if self.device.type != "cuda":
             raise RuntimeError("avi_talking_b200 diffusion prior runs on CUDA only (no CPU fallback)")
         B, steps = shape[0], sched.shape[0]
@@ -407,9 +439,10 @@ class InstructDiffusionPrior(nn.Module):
             noise = torch.stack([self._draw(tuple(shape), generator) for _ in range(steps)])
         text = text_cond["text_embed"].reshape(B, -1).float().contiguous()
         temb = self.net.time_embeddings(tvals)
+        null_pred = self.net.null_predictions(tvals) if cond_scale != 1.0 else None        # forward_with_cond_scale :209-221
         x = ops.prior_sample(self.net._pack()["struct"], temb, sched, text, image_embed.reshape(B, -1).float().contiguous(),
                              noise.reshape(steps, B, -1).float().contiguous(), 1.0 / self.image_embed_scale,
-                             samples_per_cta=self.samples_per_cta)
+                             samples_per_cta=self.samples_per_cta, null_pred=null_pred, cond_scale=float(cond_scale))
         return x.view(*shape)
 
     @torch.no_grad()
@@ -417,8 +450,9 @@ class InstructDiffusionPrior(nn.Module):
         """:329-341, one ancestral step: returns (pred, x_start) with pred = posterior_mean(x_start, x, t) + [t > 0] * sigma_t * noise.
         Two one-step launches of the sampler kernel (schedule rows "x = x0" and the DDPM row of t); every sample of the batch must sit
         at the same timestep, as in the reference's own loop (:358)."""
-        if cond_scale != 1.0 or self_cond is not None:
-            raise NotImplementedError("cond_scale != 1 / self-conditioning are not used on the reference's path")
+        if self_cond is not None:
+            raise NotImplementedError("self-conditioning is not used on the reference's path (net.self_cond = False)")
+        self._check_guidance(cond_scale)
         tv = int(t.reshape(-1)[0])
         if not bool((t == tv).all()):
             raise NotImplementedError("p_sample: one timestep for the whole batch (the reference's sampling loop, :358)")
@@ -434,8 +468,9 @@ class InstructDiffusionPrior(nn.Module):
         text = text_cond["text_embed"].reshape(B, -1).float().contiguous()
         temb = self.net.time_embeddings(tvals)
         xin, nz = x.reshape(B, -1).float().contiguous(), noise.reshape(1, B, -1).float().contiguous()
-        out = {k: ops.prior_sample(self.net._pack()["struct"], temb, r.contiguous(), text, xin, nz, 1.0,
-                                   samples_per_cta=self.samples_per_cta).view(*x.shape) for k, r in rows.items()}
+        null_pred = self.net.null_predictions(tvals) if cond_scale != 1.0 else None
+        out = {k: ops.prior_sample(self.net._pack()["struct"], temb, r.contiguous(), text, xin, nz, 1.0, samples_per_cta=self.samples_per_cta,
+                                   null_pred=null_pred, cond_scale=float(cond_scale)).view(*x.shape) for k, r in rows.items()}
         return out["step"], out["x0"]
 
     @torch.no_grad()
@@ -448,8 +483,7 @@ class InstructDiffusionPrior(nn.Module):
     def p_sample_loop(self, shape, text_cond, cond_scale=1.0, timesteps=None, generator=None, image_embed=None, noise=None):
         """dalle2_pytorch.DiffusionPrior.p_sample_loop: DDPM when ``timesteps`` equals the trained schedule, DDIM when fewer;
         result divided by ``image_embed_scale``."""
-        if cond_scale != 1.0:
-            raise NotImplementedError("cond_scale != 1 is not used by the reference's inference (train_diffusion_prior.py:828)")
+        self._check_guidance(cond_scale)
         total = self.noise_scheduler.num_timesteps
         timesteps = total if timesteps is None else timesteps
         assert timesteps <= total
@@ -457,7 +491,13 @@ class InstructDiffusionPrior(nn.Module):
             tvals, sched = self._ddim_schedule(timesteps)
         else:
             tvals, sched = self._ddpm_schedule()
-        return self._run(shape, text_cond, tvals, sched, generator, image_embed, noise)
+        return self._run(shape, text_cond, tvals, sched, generator, image_embed, noise, cond_scale=cond_scale)
+
+    def _check_guidance(self, cond_scale):
+        """dalle2_pytorch.DiffusionPrior.p_mean_variance: guidance needs a prior trained with BOTH drop probabilities > 0."""
+        if cond_scale != 1.0 and not (self.text_cond_drop_prob > 0.0 and self.image_cond_drop_prob > 0.0):
+            raise AssertionError("the model was not trained with conditional dropout, and thus one cannot use classifier free guidance "
+                                 "(cond_scale anything other than 1)")
 
     def p_losses(self, image_embed, times, text_cond, noise=None, keep_brain=None, keep_image=None):
         """:369-402 (q_sample, denoiser with conditioning dropout, l2 loss to x_start) -> (loss, pred), differentiable with respect

@@ -400,8 +400,9 @@ def prior_time_embed(times, w0t, b0, w1t, b1, w2t, b2):
     return temb
 
 
-def prior_sample(net: AviPriorNet, temb, sched, text_embed, x_init, noise, out_scale, samples_per_cta=0):
-    """One launch = the whole DDPM/DDIM loop. text_embed/x_init [B,128], noise [steps,B,128], sched [steps,6] -> [B,128]."""
+def prior_sample(net: AviPriorNet, temb, sched, text_embed, x_init, noise, out_scale, samples_per_cta=0, null_pred=None, cond_scale=1.0):
+    """One launch = the whole DDPM/DDIM loop. text_embed/x_init [B,128], noise [steps,B,128], sched [steps,6] -> [B,128].
+    null_pred [steps,128] + cond_scale: classifier-free guidance (the null pass of every step, precomputed)."""
     _need_cuda(temb, sched, text_embed, x_init, noise)
     B, steps = text_embed.shape[0], sched.shape[0]
     for t, shp in ((temb, (steps, 128)), (text_embed, (B, 128)), (x_init, (B, 128)), (noise, (steps, B, 128)), (sched, (steps, 6))):
@@ -410,9 +411,11 @@ def prior_sample(net: AviPriorNet, temb, sched, text_embed, x_init, noise, out_s
     out = torch.empty((B, 128), dtype=torch.float32, device=text_embed.device)
     # algorithmic work: 12.8 MFLOP per sample-step
     with _timed("prior_sample", 12.8e6 * B * steps):
-        _lib.check(_lib.load().avi_prior_sample(C.byref(net), _ptr(temb), _ptr(sched), _ptr(text_embed), _ptr(x_init), _ptr(noise),
-                                                _ptr(out), C.c_int32(B), C.c_int32(steps), C.c_float(out_scale),
-                                                C.c_int32(samples_per_cta), _stream()), "avi_prior_sample")
+        if null_pred is not None and (tuple(null_pred.shape) != (steps, 128) or null_pred.dtype != torch.float32 or not null_pred.is_contiguous()):
+            raise ValueError("prior_sample: null_pred must be contiguous fp32 [steps, 128]")
+        _lib.check(_lib.load().avi_prior_sample_cfg(C.byref(net), _ptr(temb), _ptr(sched), _ptr(text_embed), _ptr(x_init), _ptr(noise),
+                                                    _ptr(null_pred), C.c_float(cond_scale), _ptr(out), C.c_int32(B), C.c_int32(steps),
+                                                    C.c_float(out_scale), C.c_int32(samples_per_cta), _stream()), "avi_prior_sample_cfg")
     return out
 
 

@@ -268,6 +268,13 @@ int avi_prior_time_embed(const float* times, const float* w0t, const float* b0, 
  *   out [B][128] = final x * out_scale (1 / image_embed_scale). samples_per_cta: 1, 2, 4 or 0 = choose. */
 int avi_prior_sample(const AviPriorNet* net, const float* temb, const float* sched, const float* text_embed, const float* x_init,
                      const float* noise, float* out, int32_t B, int32_t steps, float out_scale, int32_t samples_per_cta, void* stream);
+/* the same loop with classifier-free guidance (forward_with_cond_scale :209-221, cond_scale != 1): the null pass replaces BOTH the
+ * text token and the noisy image token by the null embeddings, so its output depends on the timestep only: null_pred [steps][128]
+ * is that output per step (one avi_prior_sample call of B = 1, steps = 1, mode 2 each, with text = null_brain_embeds and
+ * x_init = null_image_embed), and x0 = null + (x0 - null) * cond_scale before the DDPM / DDIM update. null_pred == NULL: as above. */
+int avi_prior_sample_cfg(const AviPriorNet* net, const float* temb, const float* sched, const float* text_embed, const float* x_init,
+                         const float* noise, const float* null_pred, float cond_scale, float* out, int32_t B, int32_t steps,
+                         float out_scale, int32_t samples_per_cta, void* stream);
 
 /* y = GELU(LayerNorm(x)) (+ res), rows of C <= 4096: BrainNetwork blocks and projector (models/diffusion_prior.py:63-93,104-110) */
 int avi_ln_gelu_res(const float* x, const float* w, const float* b, const float* res, float* out_f32, void* out_bf16, int64_t rows,

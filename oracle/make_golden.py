@@ -309,6 +309,41 @@ def golden_prior():
 
 
 
+def golden_prior_cfg():
+    """Classifier-free guidance (cond_scale = 2.5) through the reference's own forward_with_cond_scale / p_sample /
+    p_sample_loop_ddpm and the stand-in's DDIM loop: tests/golden/prior_cfg.npz."""
+    from . import prior_oracle as po
+    from . import synth
+    sd = synth.prior_state()
+    queue = []
+    ns = _exec_reference_prior_classes(queue)
+    out = {}
+    with torch.no_grad():
+        brain = ns["BrainNetwork"](in_dim=768, out_dim=128, clip_size=128, use_projector=True).eval()
+        net = ns["VersatileDiffusionPriorNetwork"](dim=128, depth=6, dim_head=64, heads=8, causal=False, num_tokens=1,
+                                                   learned_query_mode="pos_emb")
+        prior = ns["InstructDiffusionPrior"](net=net, image_embed_dim=128, condition_on_text_encodings=False, timesteps=100,
+                                             cond_drop_prob=0.2, image_embed_scale=None, voxel2clip=brain).eval()
+        prior.load_state_dict(sd, strict=False)
+        inp = synth.prior_inputs(4, 100)
+        text = brain(inp["voxel"])[0].view(4, -1, 128)
+        cs = 2.5
+        t = torch.full((4,), 37, dtype=torch.long)
+        out["net_t37_cfg"] = net.forward_with_cond_scale(inp["image_embed"], t, cond_scale=cs, text_embed=text).numpy()
+        queue.extend([inp["noises"][i] for i in reversed(range(100))])
+        y = prior.p_sample_loop(text.shape, text_cond=dict(text_embed=text), cond_scale=cs, timesteps=100, generator=object(),
+                                image_embed=inp["image_embed"])
+        assert not queue
+        out["ddpm100_cfg"] = y.numpy()
+        pairs = po.ddim_time_pairs(100, 64)
+        y = prior.p_sample_loop(text.shape, text_cond=dict(text_embed=text), cond_scale=cs, timesteps=64,
+                                image_embed=inp["image_embed"], noises=[inp["noises"][k] for k in range(len(pairs))])
+        out["ddim64_cfg"] = y.numpy()
+        out["cond_scale"] = np.array(cs)
+    np.savez(os.path.join(GOLD, "prior_cfg.npz"), **out)
+    print("prior_cfg.npz", {k: v.shape for k, v in out.items()})
+
+
 def prior_train_inputs(B=6, seed=77):
     """Seeded inputs of one prior-training iteration (every stochastic draw of the reference as an explicit tensor)."""
     g = torch.Generator().manual_seed(seed)
@@ -733,6 +768,7 @@ def main():
     golden_wav2vec2()
     golden_faceformer()
     golden_prior()
+    golden_prior_cfg()
     golden_prior_train()
     golden_emote()
     golden_train()

@@ -113,6 +113,17 @@ def time_mlp(sd, p, x):
 
 
 # ------------------------------------------------------------------------------------------------ the reference's network
+def forward_with_cond_scale(sd, image_embed, t, text_embed, cond_scale=1.0):
+    """VersatileDiffusionPriorNetwork.forward_with_cond_scale (diffusion_prior.py:209-221): the null pass drops BOTH conditions
+    (brain_cond_drop_prob = image_cond_drop_prob = 1), i.e. sees the two null embeddings and the timestep only."""
+    logits = prior_net_forward(sd, image_embed, t, text_embed)
+    if cond_scale == 1:
+        return logits
+    B = image_embed.shape[0]
+    null_logits = prior_net_forward(sd, sd["net.null_image_embed"][None].expand(B, -1, -1), t, sd["net.null_brain_embeds"][None].expand(B, -1, -1))
+    return null_logits + (logits - null_logits) * cond_scale
+
+
 def prior_net_forward(sd, image_embed, t, text_embed, depth=DEPTH):
     """VersatileDiffusionPriorNetwork.forward (diffusion_prior.py:223-313) with the drop probabilities at 0 (inference,
     cond_scale == 1 => a single pass, :216-218), learned_query_mode='pos_emb', continuous time embedding.
@@ -156,7 +167,7 @@ def noise_schedule(timesteps=100, s=0.008):
     )
 
 
-def p_sample_loop_ddpm(sd, text_embed, image_embed, noises, timesteps=100):
+def p_sample_loop_ddpm(sd, text_embed, image_embed, noises, timesteps=100, cond_scale=1.0):
     """InstructDiffusionPrior.p_sample_loop_ddpm (:344-367) + p_sample (:329-341) + DiffusionPrior.p_mean_variance
     (predict_x_start=True, no clamps). image_embed [B,1,128] = the initial noise; noises [timesteps, B,1,128], noises[i] is
     the draw used at step i (the draw at i == 0 is multiplied by the nonzero mask = 0)."""
@@ -165,7 +176,7 @@ def p_sample_loop_ddpm(sd, text_embed, image_embed, noises, timesteps=100):
     B = x.shape[0]
     for i in reversed(range(timesteps)):
         t = torch.full((B,), i, dtype=torch.long)
-        x0 = prior_net_forward(sd, x, t, text_embed)
+        x0 = forward_with_cond_scale(sd, x, t, text_embed, cond_scale)
         mean = ns["posterior_mean_coef1"][i] * x0 + ns["posterior_mean_coef2"][i] * x
         nonzero = 0.0 if i == 0 else 1.0
         x = mean + nonzero * (0.5 * ns["posterior_log_variance_clipped"][i]).exp() * noises[i]
@@ -178,7 +189,7 @@ def ddim_time_pairs(total, steps):
     return list(zip(times[:-1], times[1:]))
 
 
-def p_sample_loop_ddim(sd, text_embed, image_embed, noises, timesteps, total=100, eta=1.0):
+def p_sample_loop_ddim(sd, text_embed, image_embed, noises, timesteps, total=100, eta=1.0, cond_scale=1.0):
     """dalle2_pytorch.DiffusionPrior.p_sample_loop_ddim (predict_x_start). noises[k] = the draw of the k-th pair."""
     ns = noise_schedule(total)
     alphas = ns["alphas_cumprod_prev"]
@@ -187,7 +198,7 @@ def p_sample_loop_ddim(sd, text_embed, image_embed, noises, timesteps, total=100
     for k, (time, time_next) in enumerate(ddim_time_pairs(total, timesteps)):
         alpha, alpha_next = alphas[time], alphas[time_next]
         t = torch.full((B,), time, dtype=torch.long)
-        x0 = prior_net_forward(sd, x, t, text_embed)
+        x0 = forward_with_cond_scale(sd, x, t, text_embed, cond_scale)
         pred_noise = (ns["sqrt_recip_alphas_cumprod"][time] * x - x0) / ns["sqrt_recipm1_alphas_cumprod"][time]
         if time_next < 0:
             x = x0
@@ -199,13 +210,13 @@ def p_sample_loop_ddim(sd, text_embed, image_embed, noises, timesteps, total=100
     return x
 
 
-def p_sample_loop(sd, text_embed, image_embed, noises, timesteps=100, total=100):
+def p_sample_loop(sd, text_embed, image_embed, noises, timesteps=100, total=100, cond_scale=1.0):
     """DiffusionPrior.p_sample_loop: DDPM when timesteps == total, DDIM when fewer; divides by image_embed_scale = sqrt(128)
     (image_embed_scale=None at train_diffusion_prior.py:990)."""
     if timesteps < total:
-        x = p_sample_loop_ddim(sd, text_embed, image_embed, noises, timesteps, total)
+        x = p_sample_loop_ddim(sd, text_embed, image_embed, noises, timesteps, total, cond_scale=cond_scale)
     else:
-        x = p_sample_loop_ddpm(sd, text_embed, image_embed, noises, total)
+        x = p_sample_loop_ddpm(sd, text_embed, image_embed, noises, total, cond_scale=cond_scale)
     return x / (DIM ** 0.5)
 
 

@@ -119,3 +119,28 @@ def test_baseline_config_batch_256_ddim_64(precision, tol_l2, tol_max):
     if xo is not None:
         print(f"   voxel2clip {precision}: relative L2 error {float((x.cpu() - xo).double().norm() / xo.double().norm()):.3e}")
     assert got.shape == (B, 1, 128) and l2 < tol_l2 and float(d.abs().max()) < tol_max
+
+
+def test_classifier_free_guidance_matches_reference_golden(golden):
+    """cond_scale = 2.5 (forward_with_cond_scale, models/diffusion_prior.py:209-221): the null pass is precomputed per timestep and
+    combined inside the sampling kernel; against the reference's own classes (tests/golden/prior_cfg.npz)."""
+    g, gp = golden("prior_cfg"), golden("prior")
+    cs = float(g["cond_scale"])
+    inp = synth.prior_inputs(4, 100)
+    prior = build_prior()
+    text = torch.from_numpy(gp["brain_x"]).view(4, -1, 128).cuda()
+    o = prior.net.forward_with_cond_scale(inp["image_embed"].cuda(), torch.full((4,), 37, device="cuda"), cond_scale=cs, text_embed=text)
+    err = np.abs(o.cpu().numpy() - g["net_t37_cfg"]).max()
+    print("guided single pass max abs error", err)
+    assert err < 5e-5
+    for timesteps, key in ((100, "ddpm100_cfg"), (64, "ddim64_cfg")):
+        noise = inp["noises"][:63].cuda() if timesteps < 100 else inp["noises"].flip(0).cuda()
+        y = prior.p_sample_loop(text.shape, dict(text_embed=text), cond_scale=cs, timesteps=timesteps, image_embed=inp["image_embed"].cuda(),
+                                noise=noise)
+        err = np.abs(y.cpu().numpy() - g[key]).max()
+        print(f"guided {key}: max abs error {err:.3e}")
+        assert err < 2e-4
+    # a prior built without conditional dropout refuses guidance, as upstream asserts
+    prior.text_cond_drop_prob = 0.0
+    with pytest.raises(AssertionError):
+        prior.p_sample_loop(text.shape, dict(text_embed=text), cond_scale=cs, timesteps=64, image_embed=inp["image_embed"].cuda())

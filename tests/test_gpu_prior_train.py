@@ -120,7 +120,7 @@ def test_batch_64_against_the_autograd_oracle_and_drawn_inputs():
 
 def test_graph_replayed_iteration_equals_eager_and_trains():
     """GraphedPriorTrainStep (forward + backward in one CUDA graph, draws copied into static buffers) gives the eager step's
-    gradients bit for bit, and 30 iterations on a fixed batch lower the prior loss."""
+    gradients (to summation order), and 30 iterations on a fixed batch lower the prior loss."""
     from avi_talking_b200.prior_train import GraphedPriorTrainStep, PriorAdamW, PriorTrainStep
     B = 32
     inp = _cuda_inputs(mg.prior_train_inputs(B, seed=9))
@@ -132,8 +132,8 @@ def test_graph_replayed_iteration_equals_eager_and_trains():
         p.grad = None
     gstep = GraphedPriorTrainStep(prior, B, precision="fp32")
     out = gstep(inp["voxel"], inp["clip_target"], 0.006, **kw)
-    for n, p in _named(prior).items():
-        assert torch.equal(p.grad, want[n]), n
+    for n, p in _named(prior).items():       # LayerNorm gain / bias gradients are atomic sums: equal up to the summation order
+        assert float((p.grad - want[n]).abs().max()) <= 1e-5 * float(want[n].abs().max()) + 1e-12, n
     first = float(out["loss_prior_scaled"]) / 30
     opt = PriorAdamW(prior, lr=3e-4)
     for _ in range(30):

@@ -88,3 +88,18 @@ def test_emote_dropin_state_dict_keys_match_reference(golden):
     m = TalkingHeadWrapper.from_parts(Wav2Vec2Model(Wav2Vec2Config()), FLAME(fcfg), emote_cfg(n_identities=32))
     own = sorted(k for k in m.talking_head_model.state_dict() if k.startswith("sequence_") and ".flame." not in k)
     assert own == list(g["state_keys"])
+
+
+def test_classifier_free_guidance_matches_reference(golden):
+    """cond_scale = 2.5 through the reference's own forward_with_cond_scale / p_sample_loop (oracle/make_golden.golden_prior_cfg)."""
+    g, gp = golden("prior_cfg"), golden("prior")
+    cs = float(g["cond_scale"])
+    sd, inp = synth.prior_state(), synth.prior_inputs(4, 100)
+    text = torch.from_numpy(gp["brain_x"]).view(4, -1, 128)
+    o = po.forward_with_cond_scale(sd, inp["image_embed"], torch.full((4,), 37), text, cs)
+    assert np.abs(o.numpy() - g["net_t37_cfg"]).max() < 2e-5
+    y = po.p_sample_loop(sd, text, inp["image_embed"], inp["noises"], timesteps=100, cond_scale=cs)
+    assert np.abs(y.numpy() - g["ddpm100_cfg"]).max() < 2e-5
+    y = po.p_sample_loop(sd, text, inp["image_embed"], inp["noises"], timesteps=64, cond_scale=cs)
+    assert np.abs(y.numpy() - g["ddim64_cfg"]).max() < 2e-5
+    assert np.abs(g["ddim64_cfg"] - gp["ddim64"]).max() > 1e-2      # guidance changes the result
