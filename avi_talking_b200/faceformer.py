@@ -349,13 +349,16 @@ class Faceformer(nn.Module):
         main.wait_stream(side)
         return v, out["fv"]
 
-    def graphed_predict_and_convert(self, audio, emo_embed, gt_coeff, gt_pose, gt_shape):
+    def graphed_predict_and_convert(self, audio, emo_embed, gt_coeff, gt_pose, gt_shape, slot=0):
         """predict_and_convert replayed from a CUDA graph (captured once per input signature and weight version). The returned tensors
-        are the graph's static outputs: they are overwritten by the next call with the same signature."""
+        are the graph's static outputs: they are overwritten by the next call with the same signature AND slot. Each slot is an
+        independent graph instance with its own activation pool, so a caller can keep two batches in flight on two streams (step i's
+        latency-bound autoregressive decoder then runs beside step i+1's convolution stack instead of leaving 84 SMs idle)."""
         from .graphs import GraphedCall
-        if getattr(self, "_graphed_pc", None) is None:
-            self._graphed_pc = GraphedCall(self.predict_and_convert, weight_modules=(self,))
-        return self._graphed_pc(audio, emo_embed, gt_coeff, gt_pose, gt_shape)
+        slots = self.__dict__.setdefault("_graphed_pc_slots", {})
+        if slot not in slots:
+            slots[slot] = GraphedCall(self.predict_and_convert, weight_modules=(self,))
+        return slots[slot](audio, emo_embed, gt_coeff, gt_pose, gt_shape)
 
     @torch.no_grad()
     def predict(self, audio, head_img, eye_img, emotion_img, text=None):

@@ -34,6 +34,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--inflight", type=int, default=2, choices=[1, 2],
+                    help="predict workload, `value` leg: batches in flight (2 = two CUDA-graph instances replayed alternately on two streams)")
     ap.add_argument("--workload", default="predict", choices=["predict", "prior", "train"],
                     help="predict = BASELINE configs[1]/[2] (default, the headline metric); prior = configs[3] (diffusion prior, batch 256, "
                          "DDIM-64); train = configs[4] (faceformer_vert teacher-forced training step, DDP over the GPUs)")
@@ -112,7 +114,8 @@ def workload_config(args, T, precision):
     which = "configs[1]" if args.clips_total is None else f"configs[2] ({args.clips_total} clips sharded by clip over the GPUs, strong scaling)"
     return {"workload": f"BASELINE {which}: FaceFormer-disentangle predict (wav2vec2 + AR decoder + vertex head) + FLAME LBS, "
                         f"{args.clips} clips x {args.seconds:g} s per GPU, fd={args.fd}, random-init (seeded) weights",
-            "clips_per_gpu": args.clips, "frames_per_clip": T, "precision": precision, "l2_policy": "inputs larger than L2", "launch": "eager" if getattr(args, "no_graph", False) else "cuda graph replay"}
+            "clips_per_gpu": args.clips, "frames_per_clip": T, "precision": precision, "l2_policy": "inputs larger than L2", "launch": "eager" if getattr(args, "no_graph", False) else ("cuda graph replay" if getattr(args, "inflight", 1) == 1 else
+                       f"cuda graph replay, {args.inflight} batches in flight (independent graph instances on {args.inflight} streams)")}
 
 
 def n_frames(n_samples):
@@ -265,11 +268,31 @@ def run_ours(args):
         # one public call per step: wav2vec2 + AR decoder + vertex head, and FLAME on the frames' coefficients (side stream)
         return model.predict_and_convert(inp["audio"], inp["emo"], inp["coeff"], inp["pose"], inp["shape"])
 
+    lanes = [torch.cuda.Stream(device=dev) for _ in range(args.inflight)] if args.inflight > 1 and not args.no_graph else None
+    counter = [0]
+
     def step(inp):
         # the device-resident `value`: the same call replayed from its CUDA graph (static outputs, overwritten by the next replay)
         if args.no_graph:
             return step_eager(inp)
-        return model.graphed_predict_and_convert(inp["audio"], inp["emo"], inp["coeff"], inp["pose"], inp["shape"])
+        if lanes is None:
+            return model.graphed_predict_and_convert(inp["audio"], inp["emo"], inp["coeff"], inp["pose"], inp["shape"])
+        # two batches in flight: graph instance k (own activation pool, own static outputs) on stream k; the streams are joined to the
+        # timing stream by fork() / join() around the timed region
+        k = counter[0] % len(lanes)
+        counter[0] += 1
+        with torch.cuda.stream(lanes[k]):
+            return model.graphed_predict_and_convert(inp["audio"], inp["emo"], inp["coeff"], inp["pose"], inp["shape"], slot=k)
+
+    def fork():
+        if lanes is not None:
+            for s_ in lanes:
+                s_.wait_stream(torch.cuda.current_stream())
+
+    def join():
+        if lanes is not None:
+            for s_ in lanes:
+                torch.cuda.current_stream().wait_stream(s_)
 
     def barrier():
         if world > 1:
@@ -277,8 +300,10 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # inputs (41 MB audio + activations of several GB per step) are far larger than the 126 MB L2, so no explicit flush
-    for _ in range(max(args.warmup, 3)):
+    fork()
+    for _ in range(max(args.warmup, 3) * args.inflight):
         step(devin)
+    join()
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
@@ -286,8 +311,10 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
+    fork()
     for _ in range(args.steps):
         step(devin)
+    join()
     e1.record()
     barrier()
     dt_ms = e0.elapsed_time(e1)

@@ -334,6 +334,39 @@ def test_graphed_predict_and_convert_matches_eager():
 
 
 @pytest.mark.gpu
+def test_two_batches_in_flight_on_two_graph_instances():
+    """graphed_predict_and_convert(slot=k): independent graph instances (own activation pools, own static outputs) replayed
+    concurrently on two streams - what bench.py --inflight 2 times - each return their own batch's eager result."""
+    from avi_talking_b200.smoke import build_models
+    m = build_models("bf16")
+    B, n, T = 4, 16000, 24
+    g = torch.Generator().manual_seed(8)
+    batches, want = [], []
+    for k in range(2):
+        audio = synth.audio(B, n, seed=400 + k).cuda()
+        emo = torch.randn(B, T, 30, generator=g).cuda()
+        coeff = torch.randn(B * T, 53, generator=g).cuda()
+        pose = (0.1 * torch.randn(B * T, 6, generator=g)).cuda()
+        shape = torch.randn(B * T, 100, generator=g).cuda()
+        batches.append((audio, emo, coeff, pose, shape))
+        v, f = m.predict_and_convert(audio, emo, coeff, pose.clone(), shape)
+        want.append((v.clone(), f.clone()))
+    lanes = [torch.cuda.Stream() for _ in range(2)]
+    for rep in range(3):                                   # first pass captures, the next ones replay concurrently
+        got = []
+        for k in range(2):
+            lanes[k].wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(lanes[k]):
+                a, e, c, p, s_ = batches[k]
+                got.append(m.graphed_predict_and_convert(a, e, c, p.clone(), s_, slot=k))
+        for k in range(2):
+            torch.cuda.current_stream().wait_stream(lanes[k])
+        torch.cuda.synchronize()
+        for k in range(2):
+            assert torch.equal(got[k][0], want[k][0]) and torch.equal(got[k][1], want[k][1]), (rep, k)
+
+
+@pytest.mark.gpu
 def test_long_and_ragged_clips_take_the_general_kernels():
     """Clips beyond the fast paths' limits: 12 s of audio -> T = 299 frames (> 256: generic AR decoder and generic attention), a
     batch of 3 such clips, and the shortest clip the conv stack admits one frame for. fp32 mode against the CPU oracle."""
