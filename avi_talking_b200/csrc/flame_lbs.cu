@@ -2,6 +2,8 @@
 // Follows third_party/inferno/inferno/utils/lbs.py:142-234 (lbs), :304-335 (batch_rodrigues), :351-408
 // (batch_rigid_transform) and DecaFLAME.py:222-269.  Joint regression is folded into a [15, NB+1] matrix at pack time
 // (J = J_regressor (v_template + S betas) = JT + JS betas), so no per-frame reduction over vertices is needed.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace avi {
@@ -323,4 +325,38 @@ extern "C" int avi_flame_landmarks(const float* verts, const int64_t* faces, con
   AVI_REQUIRE(F > 0 && V > 0 && L > 0, "avi_flame_landmarks: bad shape");
   flame_landmarks_kernel<<<(F * L + 127) / 128, 128, 0, (cudaStream_t)stream>>>(verts, faces, idx, bary, out, F, V, L, per_frame);
   return check_launch("flame_landmarks");
+}
+
+// ------------------------------------------------------------------------------------------------ compact result sink (opt-in)
+// out[r, c] = fp16(verts[r, c] - template[c]): the displacement from the neutral face is ~1e-2 m, so fp16 keeps ~5e-6 m while the
+// device->host copy (the bound of the end-to-end path: 1.9 GB of fp32 vertices per 64-clip step) halves. Outside the fp32 contract.
+namespace avi {
+__global__ void __launch_bounds__(256) pack_disp_f16_kernel(const float* __restrict__ verts, const float* __restrict__ tpl,
+                                                            __half* __restrict__ out, int64_t rows, int C, int64_t ld) {
+  const int64_t row = blockIdx.y;
+  for (int c = (blockIdx.x * blockDim.x + threadIdx.x) * 2; c < C; c += gridDim.x * blockDim.x * 2) {
+    const float a = verts[row * ld + c] - tpl[c];
+    if (c + 1 < C) {
+      const float b = verts[row * ld + c + 1] - tpl[c + 1];
+      if (((row * (int64_t)C + c) & 1) == 0) {
+        *reinterpret_cast<__half2*>(out + row * (int64_t)C + c) = __floats2half2_rn(a, b);
+      } else {
+        out[row * (int64_t)C + c] = __float2half_rn(a);
+        out[row * (int64_t)C + c + 1] = __float2half_rn(b);
+      }
+    } else {
+      out[row * (int64_t)C + c] = __float2half_rn(a);
+    }
+  }
+}
+}  // namespace avi
+
+extern "C" int avi_pack_disp_f16(const float* verts, const float* tpl, void* out_f16, int64_t rows, int32_t C, int64_t ld, void* stream) {
+  AVI_REQUIRE(rows > 0 && rows <= 65535 * 64LL && C > 0 && ld >= C, "avi_pack_disp_f16: bad shape");
+  for (int64_t r0 = 0; r0 < rows; r0 += 65535) {   // grid.y limit
+    const int64_t n = rows - r0 < 65535 ? rows - r0 : 65535;
+    pack_disp_f16_kernel<<<dim3(8, (unsigned)n), 256, 0, (cudaStream_t)stream>>>(verts + r0 * ld, tpl, reinterpret_cast<__half*>(out_f16) + r0 * C,
+                                                                               n, C, ld);
+  }
+  return check_launch("pack_disp_f16");
 }

@@ -911,3 +911,14 @@ def adamw_table(items):
 def adamw_multi(table, n_entries, lr, beta1, beta2, eps, step, grad_scale=1.0):
     _chk(_lib.load().avi_adamw_multi(_ptr(table), C.c_int32(n_entries), C.c_float(lr), C.c_float(beta1), C.c_float(beta2), C.c_float(eps),
                                      C.c_int32(step), C.c_float(grad_scale), _stream()), "avi_adamw_multi")
+
+
+def pack_disp_f16(verts2d, template):
+    """fp32 vertices [rows, C] (row stride allowed) -> dense fp16 [rows, C] displacement from `template` [C] (opt-in compact sink)."""
+    _need_cuda(verts2d, template)
+    rows, Cc = verts2d.shape
+    assert verts2d.dtype == torch.float32 and verts2d.stride(1) == 1 and template.numel() == Cc
+    out = torch.empty((rows, Cc), dtype=torch.float16, device=verts2d.device)
+    _chk(_lib.load().avi_pack_disp_f16(_ptr(verts2d), _ptr(template.contiguous().float()), _ptr(out), C.c_int64(rows), C.c_int32(Cc),
+                                       C.c_int64(verts2d.stride(0)), _stream()), "avi_pack_disp_f16")
+    return out

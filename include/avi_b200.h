@@ -235,6 +235,11 @@ int avi_flame_set_max_ctas(int32_t n);
 int avi_flame_landmarks(const float* verts, const int64_t* faces, const int64_t* idx, const float* bary, float* out,
                         int32_t F, int32_t V, int32_t L, int32_t per_frame, void* stream);
 
+/* Opt-in compact result sink (no reference counterpart; evaluation_functions.py:624-638 writes fp32 pickles): out_f16[r, c] =
+ * fp16(verts[r*ld + c] - template[c]) for a dense [rows, C] fp16 buffer - the displacement from the neutral face keeps ~5e-6 m in
+ * fp16 and the device->host copy halves. Outside the fp32 contract: the default sink and every headline number ship fp32 vertices. */
+int avi_pack_disp_f16(const float* verts, const float* tpl, void* out_f16, int64_t rows, int32_t C, int64_t ld, void* stream);
+
 /* ------------------------------------------------------------------ diffusion prior (text embedding -> style embedding) ------------------------------------------------------------------ */
 /* Weights of VersatileDiffusionPriorNetwork as built at train_diffusion_prior.py:963-991 (dim 128, depth <= 8, 8 heads x 64, one
  * shared K/V head, SwiGLU inner 512), packed once at weight-load time. All fp32 device pointers.

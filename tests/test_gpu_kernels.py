@@ -419,3 +419,25 @@ def test_gemm_2d_taps_is_a_3x3_convolution(ops, mode):
     ref = F.conv2d(x.double(), w.double(), padding=1)
     tol = {"fp32": 1e-5, "tf32": 5e-3, "bf16": 1e-4}[mode]      # bf16 operands are exact here (pre-rounded): fp32 accumulation only
     assert (got.double() - ref).abs().max().item() < tol
+
+
+@pytest.mark.gpu
+def test_compact_vertex_sink_roundtrip(ops):
+    """avi_pack_disp_f16 on padded-pitch vertex rows and frontend.CompactVertexSink: fp16 displacement out, fp32 vertices back on
+    the host within 2^-11 of the displacement (opt-in, outside the fp32 contract)."""
+    from avi_talking_b200.frontend import CompactVertexSink
+    r = _rng(51)
+    rows, Cc, ld = 37, 15069, 15072
+    tpl = torch.from_numpy(r.normal(size=(Cc,)).astype(np.float32) * 0.1)
+    disp = torch.from_numpy(r.normal(size=(rows, Cc)).astype(np.float32) * 1e-2)
+    buf = torch.zeros(rows, ld)
+    buf[:, :Cc] = tpl + disp
+    v = buf.cuda()[:, :Cc]                                   # non-contiguous rows, as the drop-in returns them
+    h = ops.pack_disp_f16(v, tpl.cuda())
+    assert h.dtype == torch.float16 and h.shape == (rows, Cc)
+    want = (buf[:, :Cc] - tpl)
+    assert (h.float().cpu() - want).abs().max().item() <= want.abs().max().item() * 2.0 ** -11 + 1e-9
+    sink = CompactVertexSink(("verts",), {"verts": tpl})
+    assert sink.push({"verts": v.view(1, rows, Cc)}) is None
+    back = sink.unpack(sink.flush())["verts"]
+    assert back.shape == (1, rows, Cc) and (back[0] - buf[:, :Cc]).abs().max().item() < 5e-5
