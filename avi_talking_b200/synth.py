@@ -464,3 +464,47 @@ def fan_images(n: int, seed: int = 81, size: int = 224) -> torch.Tensor:
     rng = np.random.default_rng(seed)
     x = rng.normal(size=(n, 3, size // 8, size // 8)).astype(np.float32)
     return torch.nn.functional.interpolate(torch.from_numpy(x), size=(size, size), mode="bilinear", align_corners=False).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------ training-step regularisers
+def train_regularisers(B: int, T: int, fd: int, seed: int = 300, p: float = 0.1, n_layers: int = 12, heads: int = 12, hidden: int = 768,
+                       ffn: int = 3072, dec_heads: int = 4, drop_layers=(4, 9), feat_proj_dropout: float = 0.0) -> dict:
+    """Every stochastic draw of ONE faceformer_vert training step in train mode as explicit tensors (masks are Bernoulli(1 - p) / (1 - p),
+    i.e. already scaled the way nn.Dropout scales): HF Wav2Vec2 feat_proj / hidden / attention / activation dropout, LayerDrop,
+    SpecAugment (models/lib/wav2vec.py:16-63,120-139), the PPE dropout (faceformer_vert.py PeriodicPositionalEncoding) and the five
+    dropouts of nn.TransformerDecoderLayer. `order` lists the dropout sites in the order the reference CALLS them. The feature
+    projection's dropout is a site only when the config enables it (Wav2Vec2Config default feat_proj_dropout = 0.0)."""
+    g = torch.Generator().manual_seed(seed)
+
+    def mask(*shape):
+        return (torch.rand(shape, generator=g) >= p).float() / (1.0 - p)
+
+    M = B * T
+    keep = [l not in set(drop_layers) for l in range(n_layers)]
+    spec = torch.zeros(B, T, dtype=torch.bool)
+    for b in range(B):                                          # two short spans per clip (min_masks = 2, wav2vec.py:127)
+        for s in torch.randint(0, max(1, T - 3), (2,), generator=g).tolist():
+            spec[b, s:s + 3] = True
+    masks, order = {}, []
+
+    def add(name, *shape):
+        masks[name] = mask(*shape)
+        order.append(name)
+
+    if feat_proj_dropout > 0:
+        add("featproj", M, hidden)
+    add("enc_in", M, hidden)
+    for l in range(n_layers):
+        if keep[l]:
+            add(f"l{l}.attn", B, heads, T, T)
+            add(f"l{l}.h1", M, hidden)
+            add(f"l{l}.act", M, ffn)
+            add(f"l{l}.h3", M, hidden)
+    add("ppe", M, fd)
+    add("dec.sa", B, dec_heads, T, T)
+    add("dec.d1", M, fd)
+    add("dec.ca", B, dec_heads, T, T)        # memory attention: only the diagonal (the one visible key of every query) matters
+    add("dec.d2", M, fd)
+    add("dec.act", M, 2 * fd)
+    add("dec.d3", M, fd)
+    return {"p": p, "spec_mask": spec, "layer_keep": keep, "masks": masks, "order": order}

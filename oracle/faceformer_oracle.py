@@ -66,8 +66,9 @@ def ppe_table(d_model: int, period: int, max_seq_len: int = MAX_SEQ) -> torch.Te
     return pe.unsqueeze(0).repeat(1, max_seq_len // period + 1, 1)
 
 
-def _mha(sd, prefix, q_in, kv_in, mask):
-    """torch.nn.MultiheadAttention forward (batch_first, 3-D float or 2-D bool mask), 4 heads."""
+def _mha(sd, prefix, q_in, kv_in, mask, pmask=None):
+    """torch.nn.MultiheadAttention forward (batch_first, 3-D float or 2-D bool mask), 4 heads; pmask [B,4,Tq,Tk]: the (pre-scaled)
+    dropout mask on the attention probabilities in train mode."""
     fd = q_in.shape[-1]
     W, b = sd[prefix + "in_proj_weight"], sd[prefix + "in_proj_bias"]
     q = F.linear(q_in, W[:fd], b[:fd])
@@ -84,27 +85,33 @@ def _mha(sd, prefix, q_in, kv_in, mask):
         s = s.masked_fill(mask, float("-inf"))
     else:
         s = s + mask
-    o = torch.matmul(torch.softmax(s, dim=-1), v).transpose(1, 2).reshape(B, Tq, fd)
+    a = torch.softmax(s, dim=-1)
+    if pmask is not None:
+        a = a * pmask
+    o = torch.matmul(a, v).transpose(1, 2).reshape(B, Tq, fd)
     return F.linear(o, sd[prefix + "out_proj.weight"], sd[prefix + "out_proj.bias"])
 
 
-def decoder_layer(sd, x, mem, tgt_mask, memory_mask):
+def decoder_layer(sd, x, mem, tgt_mask, memory_mask, drop=None):
+    """nn.TransformerDecoderLayer (post-norm, relu). drop (train mode): {site: pre-scaled mask of THIS clip} for the attention-probability
+    dropouts of the two MultiheadAttentions (sa, ca) and dropout1 / dropout2 / the feed-forward dropout / dropout3 (d1, d2, act, d3)."""
     p = "transformer_decoder.layers.0."
     fd = x.shape[-1]
+    d = (lambda name, t: t) if drop is None else (lambda name, t: t * drop[name].reshape(t.shape))
 
     def ln(i, t):
         return F.layer_norm(t, (fd,), sd[p + f"norm{i}.weight"], sd[p + f"norm{i}.bias"], 1e-5)
 
-    x = ln(1, x + _mha(sd, p + "self_attn.", x, x, tgt_mask))
-    x = ln(2, x + _mha(sd, p + "multihead_attn.", x, mem, memory_mask))
-    ff = F.linear(F.relu(F.linear(x, sd[p + "linear1.weight"], sd[p + "linear1.bias"])),
+    x = ln(1, x + d("d1", _mha(sd, p + "self_attn.", x, x, tgt_mask, None if drop is None else drop["sa"])))
+    x = ln(2, x + d("d2", _mha(sd, p + "multihead_attn.", x, mem, memory_mask, None if drop is None else drop["ca"])))
+    ff = F.linear(d("act", F.relu(F.linear(x, sd[p + "linear1.weight"], sd[p + "linear1.bias"]))),
                   sd[p + "linear2.weight"], sd[p + "linear2.bias"])
-    return ln(3, x + ff)
+    return ln(3, x + d("d3", ff))
 
 
 @torch.no_grad()
 def forward_ff(sd, template, hidden_states, obj_embedding, frame_num, teacher_forcing, gt_verts=None,
-               period=30, dataset="vocaset", merge=True):
+               period=30, dataset="vocaset", merge=True, reg=None):
     """Faceformer.forward_ff :435-482, literal (the AR branch re-runs the whole prefix each step).
 
     template [1,1,V3]; hidden_states [B,T,36+fd] (or [B,T,fd] with merge=False); obj_embedding [B,fd].
@@ -122,7 +129,15 @@ def forward_ff(sd, template, hidden_states, obj_embedding, frame_num, teacher_fo
             vin = F.linear(vin, sd["vertice_map.weight"], sd["vertice_map.bias"]) + style
             vin = vin + pe[:, : vin.shape[1]]
             n = vin.shape[1]
-            out = decoder_layer(sd, vin, hs, biased_mask[:, :n, :n], enc_dec_mask(dataset, n, hs.shape[1]))
+            drop = None
+            if reg is not None:           # train mode (teacher-forced branch only): PPE dropout + the decoder layer's, clip j's slices
+                B = len(mix)
+                mk = reg["masks"]
+                vin = vin * mk["ppe"].view(B, n, -1)[j:j + 1]
+                drop = {"sa": mk["dec.sa"][j:j + 1], "ca": mk["dec.ca"][j:j + 1], "d1": mk["dec.d1"].view(B, n, -1)[j:j + 1],
+                        "d2": mk["dec.d2"].view(B, n, -1)[j:j + 1], "act": mk["dec.act"].view(B, n, -1)[j:j + 1],
+                        "d3": mk["dec.d3"].view(B, n, -1)[j:j + 1]}
+            out = decoder_layer(sd, vin, hs, biased_mask[:, :n, :n], enc_dec_mask(dataset, n, hs.shape[1]), drop)
             out = F.linear(out, sd["vertice_map_r.weight"], sd["vertice_map_r.bias"])
         else:
             emb = style

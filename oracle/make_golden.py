@@ -643,6 +643,104 @@ def golden_train():
     print("train.npz", len(out), "arrays")
 
 
+def golden_train_reg():
+    """The same step in TRAIN mode: the reference's own forward_switch_frame with dropout (HF Wav2Vec2: feat_proj / hidden / attention /
+    activation; PeriodicPositionalEncoding; nn.TransformerDecoderLayer), SpecAugment (models/lib/wav2vec.py:120-131) and LayerDrop active.
+    Every draw is injected: torch.nn.functional.dropout pops the pre-scaled masks of synth.train_regularisers in call order (shapes are
+    asserted, which pins the site order), torch.rand([]) yields the LayerDrop decisions, _compute_mask_indices returns the SpecAugment
+    mask. nn.MultiheadAttention's need_weights=False path hides its dropout inside the fused scaled_dot_product_attention, so that
+    function is replaced by its definition (softmax -> dropout -> @ v), which is also what the pinned torch 1.9 executed."""
+    import math as _math
+    import pdb
+    from gdl.models.DecaFLAME import FLAME_mediapipe
+    from . import synth
+    _import_faceformer()
+    import models.faceformer_vert as ffv
+    import models.lib.wav2vec as ref_w2v
+    pdb.set_trace = lambda *a, **k: None
+    cwd = os.getcwd()
+    os.chdir("/tmp")
+    out = {}
+    Fn = torch.nn.functional
+    saved = (Fn.dropout, Fn.scaled_dot_product_attention, torch.rand, ref_w2v._compute_mask_indices)
+    try:
+        sd_w2v = synth.wav2vec2_state(0)
+        cfg = synth.write_flame_assets("/tmp/avi_flame_assets")
+        cfg.n_shape = 100
+        flame = FLAME_mediapipe(cfg)
+        fd, B, n_samples, T = 64, 2, 16000, 24
+        sd_ff = synth.faceformer_state(fd=fd, seed=200 + fd, variant="vert")
+        m = build_reference_faceformer_vert(ffv, fd, sd_ff, sd_w2v, flame, synth.fan_embeddings(T, seed=20))
+        m.train()
+        reg = synth.train_regularisers(B, T, fd, seed=300)
+        mk = reg["masks"]
+        queue = [(n, mk[n]) for n in reg["order"] if not n.startswith(("ppe", "dec."))]
+        for j in range(B):                                   # the decoder runs clip by clip (:437-454)
+            queue += [("ppe", mk["ppe"].view(B, T, fd)[j:j + 1]), ("dec.sa", mk["dec.sa"][j:j + 1]), ("dec.d1", mk["dec.d1"].view(B, T, fd)[j:j + 1]),
+                      ("dec.ca", mk["dec.ca"][j:j + 1]), ("dec.d2", mk["dec.d2"].view(B, T, fd)[j:j + 1]),
+                      ("dec.act", mk["dec.act"].view(B, T, 2 * fd)[j:j + 1]), ("dec.d3", mk["dec.d3"].view(B, T, fd)[j:j + 1])]
+        used = []
+
+        def fake_dropout(input, p=0.5, training=True, inplace=False):
+            if not training or p == 0.0:
+                return input
+            name, mask = queue.pop(0)
+            assert abs(p - reg["p"]) < 1e-9 and mask.numel() == input.numel(), (name, p, tuple(mask.shape), tuple(input.shape))
+            used.append(name)
+            return input * mask.reshape(input.shape)
+
+        def sdpa(q, k, v, attn_mask=None, dropout_p=0.0, is_causal=False, scale=None, **kw):
+            s_ = q @ k.transpose(-2, -1) / _math.sqrt(q.shape[-1])
+            if attn_mask is not None:
+                s_ = s_ + attn_mask
+            return fake_dropout(torch.softmax(s_, dim=-1), dropout_p, True) @ v
+
+        keep = list(reg["layer_keep"])
+
+        def fake_rand(*a, **k):
+            if len(a) == 1 and a[0] == [] and keep:
+                return torch.tensor(0.5 if keep.pop(0) else 0.0)        # < layerdrop (0.1) skips the layer
+            return saved[2](*a, **k)
+
+        Fn.dropout, Fn.scaled_dot_product_attention, torch.rand = fake_dropout, sdpa, fake_rand
+        ref_w2v._compute_mask_indices = lambda *a, **k: reg["spec_mask"].numpy()
+        assert m.audio_encoder.config.apply_spec_augment and m.audio_encoder.config.mask_time_prob > 0
+        assert abs(m.audio_encoder.config.layerdrop - 0.1) < 1e-9
+        coeff, pose, shape, mean, std = train_inputs(B, T, seed=90 + fd)
+        m.coeff_mean, m.coeff_std = mean, std
+        audio = synth.audio(B, n_samples, seed=4321)
+        img = torch.zeros(B, T, 3, 4, 4)
+        img[:, :, 0, 0, 0] = torch.arange(T).float()
+        opt = torch.optim.Adam([p for p in m.parameters() if p.requires_grad], lr=1e-4)
+        opt.zero_grad(set_to_none=True)
+        loss = m.forward_switch_frame(audio, coeff, pose.clone(), shape, img=img, criterion=nn.MSELoss(reduction="none"),
+                                      teacher_forcing=True)
+        assert not queue and not keep, (len(queue), keep)
+        loss.backward()
+        out["loss"] = np.array([loss.item()])
+        names = [n for n, p in m.named_parameters() if p.requires_grad]
+        for n, p in m.named_parameters():
+            if not p.requires_grad:
+                continue
+            g = p.grad if p.grad is not None else torch.zeros_like(p)
+            out[f"gchk/{n}"] = checksum(g)
+            out[f"g/{n}"] = (g.reshape(-1)[::GRAD_STRIDE] if g.numel() > 4096 else g.reshape(-1)).numpy().copy()
+        before = {n: p.detach().clone() for n, p in m.named_parameters() if p.requires_grad}
+        opt.step()
+        for n, p in m.named_parameters():
+            if p.requires_grad:
+                q = p.detach() - before[n]
+                out[f"dp/{n}"] = (q.reshape(-1)[::GRAD_STRIDE] if q.numel() > 4096 else q.reshape(-1)).numpy().copy()
+        out["names"] = np.array(names)
+        out["sites_in_call_order"] = np.array(used)
+        print("train_reg loss", loss.item(), "dropout calls", len(used), "trainable tensors", len(names))
+    finally:
+        Fn.dropout, Fn.scaled_dot_product_attention, torch.rand, ref_w2v._compute_mask_indices = saved
+        os.chdir(cwd)
+    np.savez_compressed(os.path.join(GOLD, "train_reg.npz"), **out)
+    print("train_reg.npz", len(out), "arrays")
+
+
 def _exec_reference_functions(path, names, extra_globals):
     """Compile only the named top-level functions of a reference file (its imports need librosa / pytorch_lightning / ...)."""
     import ast
@@ -772,6 +870,7 @@ def main():
     golden_prior_train()
     golden_emote()
     golden_train()
+    golden_train_reg()
     golden_frontend()
     golden_clip_text()
     golden_subject_labels()

@@ -60,7 +60,16 @@ def pos_conv_weight(sd: dict) -> torch.Tensor:
     return g * v / v.norm(p=2, dim=(0, 1), keepdim=True)
 
 
-def encoder_layer(sd: dict, l: int, h: torch.Tensor) -> torch.Tensor:
+def _drop(reg, name, x):
+    """nn.Dropout in train mode with the (pre-scaled) mask of site `name` as an input; identity without regularisers."""
+    if reg is None or name not in reg["masks"]:
+        return x
+    return x * reg["masks"][name].reshape(x.shape)
+
+
+def encoder_layer(sd: dict, l: int, h: torch.Tensor, reg=None) -> torch.Tensor:
+    """HF Wav2Vec2EncoderLayer; reg (train mode): attention-probability dropout, the hidden dropout after out_proj, the activation
+    dropout inside the feed-forward and its output dropout (modeling_wav2vec2.py Wav2Vec2EncoderLayer / Wav2Vec2FeedForward)."""
     p = f"encoder.layers.{l}."
     B, T, C = h.shape
     H, D = W2V.heads, C // W2V.heads
@@ -71,28 +80,29 @@ def encoder_layer(sd: dict, l: int, h: torch.Tensor) -> torch.Tensor:
     q = lin("attention.q_proj", h).view(B, T, H, D).transpose(1, 2)
     k = lin("attention.k_proj", h).view(B, T, H, D).transpose(1, 2)
     v = lin("attention.v_proj", h).view(B, T, H, D).transpose(1, 2)
-    a = torch.softmax(torch.matmul(q, k.transpose(2, 3)) * (D ** -0.5), dim=-1)
+    a = _drop(reg, f"l{l}.attn", torch.softmax(torch.matmul(q, k.transpose(2, 3)) * (D ** -0.5), dim=-1))
     o = torch.matmul(a, v).transpose(1, 2).reshape(B, T, C)
-    h = h + lin("attention.out_proj", o)
+    h = h + _drop(reg, f"l{l}.h1", lin("attention.out_proj", o))
     h = F.layer_norm(h, (C,), sd[p + "layer_norm.weight"], sd[p + "layer_norm.bias"], 1e-5)
-    ff = lin("feed_forward.output_dense", F.gelu(lin("feed_forward.intermediate_dense", h)))
-    h = h + ff
+    ff = lin("feed_forward.output_dense", _drop(reg, f"l{l}.act", F.gelu(lin("feed_forward.intermediate_dense", h))))
+    h = h + _drop(reg, f"l{l}.h3", ff)
     return F.layer_norm(h, (C,), sd[p + "final_layer_norm.weight"], sd[p + "final_layer_norm.bias"], 1e-5)
 
 
-def encoder(sd: dict, h: torch.Tensor, layers: int = 12) -> torch.Tensor:
+def encoder(sd: dict, h: torch.Tensor, layers: int = 12, reg=None) -> torch.Tensor:
     pc = F.conv1d(h.transpose(1, 2), pos_conv_weight(sd), sd["encoder.pos_conv_embed.conv.bias"],
                   padding=W2V.pos_k // 2, groups=W2V.pos_groups)[:, :, :-1]
     h = h + F.gelu(pc).transpose(1, 2)
-    h = F.layer_norm(h, (768,), sd["encoder.layer_norm.weight"], sd["encoder.layer_norm.bias"], 1e-5)
+    h = _drop(reg, "enc_in", F.layer_norm(h, (768,), sd["encoder.layer_norm.weight"], sd["encoder.layer_norm.bias"], 1e-5))
     for l in range(layers):
-        h = encoder_layer(sd, l, h)
+        if reg is None or reg["layer_keep"][l]:          # LayerDrop: a skipped layer is the identity (Wav2Vec2Encoder.forward)
+            h = encoder_layer(sd, l, h, reg)
     return h
 
 
 @torch.no_grad()
 def wav2vec2_forward(sd: dict, input_values: torch.Tensor, frame_num: int | None = None,
-                     mode: str = "floor", layers: int = 12, return_stages: bool = False):
+                     mode: str = "floor", layers: int = 12, return_stages: bool = False, reg=None):
     """Wav2Vec2Model.forward(input_values, dataset, frame_num=...) -> last_hidden_state [B,T,768]."""
     feats = feature_extractor(sd, input_values).transpose(1, 2)                      # wav2vec.py:97-98
     T = frame_num if frame_num is not None else output_frames(input_values.shape[1], mode)
@@ -100,7 +110,11 @@ def wav2vec2_forward(sd: dict, input_values: torch.Tensor, frame_num: int | None
     hn = F.layer_norm(h, (512,), sd["feature_projection.layer_norm.weight"],
                       sd["feature_projection.layer_norm.bias"], 1e-5)
     proj = F.linear(hn, sd["feature_projection.projection.weight"], sd["feature_projection.projection.bias"])  # :120
-    out = encoder(sd, proj, layers)                                                  # :142-148
+    if reg is not None:                                                              # train mode
+        proj = _drop(reg, "featproj", proj)                                          # Wav2Vec2FeatureProjection.dropout
+        if reg.get("spec_mask") is not None:                                         # SpecAugment along time, wav2vec.py:122-131
+            proj = torch.where(reg["spec_mask"][:, :, None], sd["masked_spec_embed"].to(proj.dtype)[None, None, :], proj)
+    out = encoder(sd, proj, layers, reg)                                             # :142-148
     if return_stages:
         return dict(feats=feats, interp=h, proj=proj, out=out)
     return out

@@ -170,6 +170,33 @@ def test_train_step_matches_reference(golden):
             np.testing.assert_allclose(dp[ok], g[f"{tag}_dp/{nme}"][ok], atol=2e-7, rtol=0, err_msg=nme)
 
 
+def test_train_step_in_train_mode_matches_reference(golden):
+    """The same step with dropout / SpecAugment / LayerDrop ACTIVE (tests/golden/train_reg.npz: the reference in .train() mode with every
+    draw injected from synth.train_regularisers): loss, every gradient - masked_spec_embed included, dropped layers exactly zero -
+    and the Adam update."""
+    from oracle import train_oracle as to
+    from oracle.make_golden import GRAD_STRIDE
+    g = golden("train_reg")
+    fd, B, n, T = 64, 2, 16000, 24
+    sd_ff, sd_w2v, template, audio, gt = _train_case("a", fd, B, n, T)
+    reg = synth.train_regularisers(B, T, fd, seed=300)
+    assert [str(x) for x in g["sites_in_call_order"]][:len(reg["order"]) - 7] == reg["order"][:-7]     # encoder sites, then per clip
+    before = to.trainable(sd_ff, sd_w2v, spec_augment=True)
+    losses, grads, after = to.train_step(sd_ff, sd_w2v, template, audio, gt, lr=1e-4, reg=reg)
+    np.testing.assert_allclose(losses[0], g["loss"][0], rtol=2e-5)
+    assert {str(x) for x in g["names"]} == set(grads)
+    for nme in grads:
+        ref = g[f"g/{nme}"]
+        got = sub(grads[nme], GRAD_STRIDE)
+        scale = max(np.abs(ref).max(), 1e-12)
+        assert np.abs(got - ref).max() <= 2e-4 * scale + 1e-9, (nme, np.abs(got - ref).max(), scale)
+        ok = np.abs(ref) > 1e-6 * scale + 1e-7
+        np.testing.assert_allclose(sub(after[nme] - before[nme], GRAD_STRIDE)[ok], g[f"dp/{nme}"][ok], atol=2e-7, rtol=0, err_msg=nme)
+    dropped = [l for l, k in enumerate(reg["layer_keep"]) if not k]
+    assert dropped and all(not np.any(g[f"g/audio_encoder.encoder.layers.{l}.attention.out_proj.weight"]) for l in dropped)
+    assert np.abs(g["g/audio_encoder.masked_spec_embed"]).max() > 0
+
+
 def test_frontend_matches_reference_bit_exact(golden):
     """avi_talking_b200.frontend (host-side framing of the audio, integer work) against the reference's own process_audio /
     create_base_sample compiled from source (oracle/make_golden.golden_frontend): bit-exact, including upstream's np.pad quirk."""
