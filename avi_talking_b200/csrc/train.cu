@@ -289,7 +289,8 @@ __device__ __forceinline__ void att_two_row_mix(const float* mat, const float* p
 
 template <int HD>
 __global__ void __launch_bounds__(256) attn_train_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ out, float* __restrict__ P,
-                                                             int T, int H, float scale, int bias_mode, int period) {
+                                                             int T, int H, float scale, int bias_mode, int period,
+                                                             const float* __restrict__ pmask) {
   extern __shared__ __align__(16) float sm[];
   float* ks = sm;                              // [T][HD+4]
   float* vs = ks + T * (HD + ATT_PAD);         // [T][HD+4]
@@ -303,6 +304,9 @@ __global__ void __launch_bounds__(256) attn_train_fwd_kernel(const float* __rest
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* Pb = P ? P + ((int64_t)b * H + h) * T * T : nullptr;   // inference callers (CLIP text tower) do not keep the probabilities
+  // train mode: the (pre-scaled) dropout mask on the probabilities, nn.MultiheadAttention / Wav2Vec2Attention dropout. P keeps the
+  // softmax itself; the mask multiplies what meets V
+  const float* Mb = pmask ? pmask + ((int64_t)b * H + h) * T * T : nullptr;
   float* qa = qs + warp * 2 * HD, *qb = qa + HD;
   float* pa = ps + warp * 2 * ATT_MAXT, *pb = pa + ATT_MAXT;
   const float slope = ff_slope(h);
@@ -345,8 +349,10 @@ __global__ void __launch_bounds__(256) attn_train_fwd_kernel(const float* __rest
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
     const int j = lane + 32 * u;        // j < ATT_MAXT always: the padding up to a multiple of 4 is written as zeros
-    pa[j] = sa[u] * da;
-    pb[j] = sb[u] * db;
+    const float ka = (Mb != nullptr && j < T) ? Mb[(int64_t)ia * T + j] : 1.f;
+    const float kb = (Mb != nullptr && j < T && b_ok) ? Mb[(int64_t)ib * T + j] : 1.f;
+    pa[j] = sa[u] * da * ka;
+    pb[j] = sb[u] * db * kb;
     if (Pb != nullptr && j < T) {
       Pb[(int64_t)ia * T + j] = sa[u] * da;
       if (b_ok) Pb[(int64_t)ib * T + j] = sb[u] * db;
@@ -369,7 +375,8 @@ __global__ void __launch_bounds__(256) attn_train_fwd_kernel(const float* __rest
 template <int HD>
 __global__ void __launch_bounds__(256) attn_train_bwd_q_kernel(const float* __restrict__ qkv, const float* __restrict__ P,
                                                                const float* __restrict__ dout, float* __restrict__ dqkv,
-                                                               float* __restrict__ dS, int T, int H, float scale) {
+                                                               float* __restrict__ dS, int T, int H, float scale,
+                                                               const float* __restrict__ pmask) {
   extern __shared__ __align__(16) float sm[];
   float* ks = sm;
   float* vs = ks + T * (HD + ATT_PAD);
@@ -383,6 +390,7 @@ __global__ void __launch_bounds__(256) attn_train_bwd_q_kernel(const float* __re
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* Pb = P + ((int64_t)b * H + h) * T * T;
+  const float* Mb = pmask ? pmask + ((int64_t)b * H + h) * T * T : nullptr;
   float* dSb = dS + ((int64_t)b * H + h) * T * T;
   float* ga = gs + warp * 2 * HD, *gb = ga + HD;
   float* ra = ds + warp * 2 * ATT_MAXT, *rb = ra + ATT_MAXT;
@@ -402,6 +410,10 @@ __global__ void __launch_bounds__(256) attn_train_bwd_q_kernel(const float* __re
     const int j = lane + 32 * u;
     qa[u] = j < T ? Pb[(int64_t)ia * T + j] : 0.f;
     qb[u] = (j < T && b_ok) ? Pb[(int64_t)ib * T + j] : 0.f;
+    if (Mb != nullptr) {       // dropout on the probabilities: the gradient reaching the softmax is dP' * mask
+      pa[u] *= j < T ? Mb[(int64_t)ia * T + j] : 0.f;
+      pb[u] *= (j < T && b_ok) ? Mb[(int64_t)ib * T + j] : 0.f;
+    }
     dota = fmaf(pa[u], qa[u], dota);
     dotb = fmaf(pb[u], qb[u], dotb);
   }
@@ -435,7 +447,8 @@ __global__ void __launch_bounds__(256) attn_train_bwd_q_kernel(const float* __re
 template <int HD>
 __global__ void __launch_bounds__(256) attn_train_bwd_kv_kernel(const float* __restrict__ qkv, const float* __restrict__ P,
                                                                 const float* __restrict__ dout, float* __restrict__ dqkv,
-                                                                const float* __restrict__ dS, int T, int H, float scale) {
+                                                                const float* __restrict__ dS, int T, int H, float scale,
+                                                                const float* __restrict__ pmask) {
   extern __shared__ __align__(16) float sm[];
   float* qs = sm;                               // Q  [T][HD+4]
   float* gs = qs + T * (HD + ATT_PAD);          // dO [T][HD+4]
@@ -448,12 +461,13 @@ __global__ void __launch_bounds__(256) attn_train_bwd_kv_kernel(const float* __r
   att_stage<HD>(gs, dout + (int64_t)b * T * E + h * HD, T, E);
   const float* Pb = P + ((int64_t)b * H + h) * T * T;
   const float* dSb = dS + ((int64_t)b * H + h) * T * T;
+  const float* Mb = pmask ? pmask + ((int64_t)b * H + h) * T * T : nullptr;
   for (int idx = threadIdx.x; idx < ATT_MAXT * ATT_ROWS; idx += blockDim.x) {
     const int i = idx / ATT_ROWS, jj = idx - i * ATT_ROWS;
     const int j = j0 + jj;
     const bool ok = i < T && j < T;
     dst[jj * ATT_MAXT + i] = ok ? dSb[(int64_t)i * T + j] : 0.f;
-    pst[jj * ATT_MAXT + i] = ok ? Pb[(int64_t)i * T + j] : 0.f;
+    pst[jj * ATT_MAXT + i] = ok ? Pb[(int64_t)i * T + j] * (Mb != nullptr ? Mb[(int64_t)i * T + j] : 1.f) : 0.f;   // dV sees P * mask
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -751,51 +765,121 @@ static size_t att_smem_kv(int T, int D) { return ((size_t)2 * T * (D + ATT_PAD) 
 
 template <int HD>
 static int attn_fwd_launch(const float* qkv, float* out, float* P, int B, int T, int H, float scale, int bias_mode, int period,
-                           cudaStream_t st) {
+                           const float* pmask, cudaStream_t st) {
   static SmemOptIn optin;
   const cudaError_t attr_err = smem_optin(attn_train_fwd_kernel<HD>, (int)att_smem_fwd(ATT_MAXT, HD), optin);
   AVI_REQUIRE(attr_err == cudaSuccess, "avi_attn_train_fwd: cudaFuncSetAttribute failed");
   attn_train_fwd_kernel<HD><<<dim3(H, B, (T + ATT_ROWS - 1) / ATT_ROWS), 256, att_smem_fwd(T, HD), st>>>(qkv, out, P, T, H, scale, bias_mode,
-                                                                                                        period > 0 ? period : 1);
+                                                                                                        period > 0 ? period : 1, pmask);
   return check_launch("attn_train_fwd");
 }
 
 template <int HD>
 static int attn_bwd_launch(const float* qkv, const float* P, const float* dout, float* dqkv, float* dS, int B, int T, int H, float scale,
-                           cudaStream_t st) {
+                           const float* pmask, cudaStream_t st) {
   static SmemOptIn optin_q, optin_kv;
   const cudaError_t e1 = smem_optin(attn_train_bwd_q_kernel<HD>, (int)att_smem_fwd(ATT_MAXT, HD), optin_q);
   const cudaError_t e2 = smem_optin(attn_train_bwd_kv_kernel<HD>, (int)att_smem_kv(ATT_MAXT, HD), optin_kv);
   AVI_REQUIRE(e1 == cudaSuccess && e2 == cudaSuccess, "avi_attn_train_bwd: cudaFuncSetAttribute failed");
   const dim3 grid(H, B, (T + ATT_ROWS - 1) / ATT_ROWS);
-  attn_train_bwd_q_kernel<HD><<<grid, 256, att_smem_fwd(T, HD), st>>>(qkv, P, dout, dqkv, dS, T, H, scale);
+  attn_train_bwd_q_kernel<HD><<<grid, 256, att_smem_fwd(T, HD), st>>>(qkv, P, dout, dqkv, dS, T, H, scale, pmask);
   if (check_launch("attn_train_bwd_q")) return 1;
-  attn_train_bwd_kv_kernel<HD><<<grid, 256, att_smem_kv(T, HD), st>>>(qkv, P, dout, dqkv, dS, T, H, scale);
+  attn_train_bwd_kv_kernel<HD><<<grid, 256, att_smem_kv(T, HD), st>>>(qkv, P, dout, dqkv, dS, T, H, scale, pmask);
   return check_launch("attn_train_bwd_kv");
 }
 
-extern "C" int avi_attn_train_fwd(const float* qkv, float* out, float* P, int32_t B, int32_t T, int32_t H, int32_t D, float scale,
-                                  int32_t bias_mode, int32_t period, void* stream) {
+extern "C" int avi_attn_train_fwd_drop(const float* qkv, float* out, float* P, const float* pmask, int32_t B, int32_t T, int32_t H,
+                                       int32_t D, float scale, int32_t bias_mode, int32_t period, void* stream) {
   AVI_REQUIRE(B > 0 && T > 0 && T <= ATT_MAXT && H > 0 && (D == 16 || D == 32 || D == 64),
               "avi_attn_train_fwd: T <= 128 and head dim 16 / 32 / 64 (T=%d D=%d)", T, D);
   AVI_REQUIRE(bias_mode >= 0 && bias_mode <= 2, "avi_attn_train_fwd: bias_mode 0 (none), 1 (FaceFormer biased causal), 2 (causal)");
   AVI_REQUIRE(bias_mode != 1 || H == 4, "avi_attn_train_fwd: the FaceFormer bias mask is defined for 4 heads");
   AVI_REQUIRE(((uintptr_t)qkv % 16) == 0, "avi_attn_train_fwd: qkv must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  if (D == 64) return attn_fwd_launch<64>(qkv, out, P, B, T, H, scale, bias_mode, period, st);
-  if (D == 32) return attn_fwd_launch<32>(qkv, out, P, B, T, H, scale, bias_mode, period, st);
-  return attn_fwd_launch<16>(qkv, out, P, B, T, H, scale, bias_mode, period, st);
+  if (D == 64) return attn_fwd_launch<64>(qkv, out, P, B, T, H, scale, bias_mode, period, pmask, st);
+  if (D == 32) return attn_fwd_launch<32>(qkv, out, P, B, T, H, scale, bias_mode, period, pmask, st);
+  return attn_fwd_launch<16>(qkv, out, P, B, T, H, scale, bias_mode, period, pmask, st);
 }
 
-extern "C" int avi_attn_train_bwd(const float* qkv, const float* P, const float* dout, float* dqkv, float* dS_scratch, int32_t B, int32_t T,
-                                  int32_t H, int32_t D, float scale, void* stream) {
+extern "C" int avi_attn_train_fwd(const float* qkv, float* out, float* P, int32_t B, int32_t T, int32_t H, int32_t D, float scale,
+                                  int32_t bias_mode, int32_t period, void* stream) {
+  return avi_attn_train_fwd_drop(qkv, out, P, nullptr, B, T, H, D, scale, bias_mode, period, stream);
+}
+
+extern "C" int avi_attn_train_bwd_drop(const float* qkv, const float* P, const float* pmask, const float* dout, float* dqkv,
+                                       float* dS_scratch, int32_t B, int32_t T, int32_t H, int32_t D, float scale, void* stream) {
   AVI_REQUIRE(B > 0 && T > 0 && T <= ATT_MAXT && H > 0 && (D == 16 || D == 32 || D == 64),
               "avi_attn_train_bwd: T <= 128 and head dim 16 / 32 / 64 (T=%d D=%d)", T, D);
   AVI_REQUIRE((((uintptr_t)qkv | (uintptr_t)dout) % 16) == 0, "avi_attn_train_bwd: qkv / dout must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  if (D == 64) return attn_bwd_launch<64>(qkv, P, dout, dqkv, dS_scratch, B, T, H, scale, st);
-  if (D == 32) return attn_bwd_launch<32>(qkv, P, dout, dqkv, dS_scratch, B, T, H, scale, st);
-  return attn_bwd_launch<16>(qkv, P, dout, dqkv, dS_scratch, B, T, H, scale, st);
+  if (D == 64) return attn_bwd_launch<64>(qkv, P, dout, dqkv, dS_scratch, B, T, H, scale, pmask, st);
+  if (D == 32) return attn_bwd_launch<32>(qkv, P, dout, dqkv, dS_scratch, B, T, H, scale, pmask, st);
+  return attn_bwd_launch<16>(qkv, P, dout, dqkv, dS_scratch, B, T, H, scale, pmask, st);
+}
+
+extern "C" int avi_attn_train_bwd(const float* qkv, const float* P, const float* dout, float* dqkv, float* dS_scratch, int32_t B, int32_t T,
+                                  int32_t H, int32_t D, float scale, void* stream) {
+  return avi_attn_train_bwd_drop(qkv, P, nullptr, dout, dqkv, dS_scratch, B, T, H, D, scale, stream);
+}
+
+// ------------------------------------------------------------------------------------------------ train-mode regularisers
+// nn.Dropout with the draw as an input: y = x * mask (+ residual); mask is Bernoulli(1-p) / (1-p), i.e. already scaled. The same kernel is
+// its own backward (dx = dy * mask). float4 over n (n % 4 == 0 is required by the caller-side shapes: 64 / 768 / 3072 wide rows).
+__global__ void __launch_bounds__(256) mask_mul_add_kernel(const float4* __restrict__ x, const float4* __restrict__ mask,
+                                                           const float4* __restrict__ res, float4* __restrict__ y, int64_t n4) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 a = x[i], k = mask[i];
+    float4 o = make_float4(a.x * k.x, a.y * k.y, a.z * k.z, a.w * k.w);
+    if (res != nullptr) {
+      const float4 r = res[i];
+      o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+    }
+    y[i] = o;
+  }
+}
+
+extern "C" int avi_mask_mul_add(const float* x, const float* mask, const float* residual, float* y, int64_t n, void* stream) {
+  AVI_REQUIRE(n > 0 && n % 4 == 0, "avi_mask_mul_add: n must be a positive multiple of 4 (n=%lld)", (long long)n);
+  AVI_REQUIRE((((uintptr_t)x | (uintptr_t)mask | (uintptr_t)residual | (uintptr_t)y) % 16) == 0, "avi_mask_mul_add: 16-byte aligned buffers");
+  const int64_t n4 = n / 4;
+  const unsigned grid = (unsigned)std::min<int64_t>((n4 + 255) / 256, 148 * 8);
+  mask_mul_add_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)x, (const float4*)mask, (const float4*)residual, (float4*)y, n4);
+  return check_launch("mask_mul_add");
+}
+
+// SpecAugment along time (models/lib/wav2vec.py:120-131): rows whose mask byte is set are REPLACED by masked_spec_embed (in place).
+__global__ void __launch_bounds__(256) spec_augment_fwd_kernel(float* __restrict__ x, const uint8_t* __restrict__ row_mask,
+                                                               const float* __restrict__ embed, int C) {
+  const int64_t r = blockIdx.x;
+  if (!row_mask[r]) return;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) x[r * C + c] = embed[c];
+}
+
+// backward: g_embed[c] = sum over the masked rows of dx[r][c] (fixed order: deterministic), then those rows of dx become zero.
+__global__ void __launch_bounds__(256) spec_augment_bwd_kernel(float* __restrict__ dx, const uint8_t* __restrict__ row_mask,
+                                                               float* __restrict__ g_embed, int64_t rows, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float acc = 0.f;
+  for (int64_t r = 0; r < rows; ++r) {
+    if (row_mask[r]) {          // warp-uniform
+      acc += dx[r * C + c];
+      dx[r * C + c] = 0.f;
+    }
+  }
+  g_embed[c] = acc;
+}
+
+extern "C" int avi_spec_augment_fwd(float* x, const uint8_t* row_mask, const float* embed, int64_t rows, int32_t C, void* stream) {
+  AVI_REQUIRE(rows > 0 && C > 0, "avi_spec_augment_fwd: bad shape");
+  spec_augment_fwd_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(x, row_mask, embed, C);
+  return check_launch("spec_augment_fwd");
+}
+
+extern "C" int avi_spec_augment_bwd(float* dx, const uint8_t* row_mask, float* g_embed, int64_t rows, int32_t C, void* stream) {
+  AVI_REQUIRE(rows > 0 && C > 0, "avi_spec_augment_bwd: bad shape");
+  spec_augment_bwd_kernel<<<(unsigned)((C + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dx, row_mask, g_embed, rows, C);
+  return check_launch("spec_augment_bwd");
 }
 
 extern "C" int avi_posconv_dw(const float* x, const float* dpc, float* dw, int32_t B, int32_t T, int32_t C, int32_t groups, int32_t k,

@@ -416,12 +416,21 @@ class Faceformer(nn.Module):
             gt_verts = (self.convert_coeff2verts(gt_coeffs, gt_poses, gt_shapes) * self.vertice_scale).reshape(B, T, -1)
         return self.training_loss(audio, gt_verts)
 
-    def training_loss(self, audio, gt_verts):
-        """Loss of the teacher-forced step for ground-truth vertices given directly (the VOCASET flavour)."""
+    # "off": the deterministic .eval() arithmetic whatever self.training says (the default: what the goldens of train.npz pin);
+    # "draw": in .train() mode every step draws dropout / SpecAugment / LayerDrop on the device, as the reference's modules do
+    regularisers = "off"
+
+    def training_loss(self, audio, gt_verts, reg=None):
+        """Loss of the teacher-forced step for ground-truth vertices given directly (the VOCASET flavour).
+        reg: explicit draws of a TRAIN-mode step (train.draw_regularisers / synth.train_regularisers); without it the step draws its
+        own when the module is in .train() mode and `regularisers == "draw"`."""
         from . import train
         if getattr(self, "_train_step", None) is None:
             self._train_step = train.TrainStep(self)
-        return train.training_loss(self._train_step, audio, gt_verts)
+        if reg is None and self.training and self.regularisers == "draw":
+            reg = train.draw_regularisers(gt_verts.shape[0], gt_verts.shape[1], self.args.feature_dim, self.audio_encoder.config,
+                                          audio.device)
+        return train.training_loss(self._train_step, audio, gt_verts, reg)
 
 
 class FaceformerVert(Faceformer):

@@ -608,22 +608,64 @@ def layernorm_bwd(x, w, dy, dw, db, want_dx=True, eps=1e-5):
     return dx
 
 
-def attn_train_fwd(qkv, B, T, H, D, bias_mode=0, period=1, want_p=True):
+def _pmask(pmask, B, H, T):
+    if pmask is None:
+        return None
+    _need_cuda(pmask)
+    if tuple(pmask.shape) != (B, H, T, T) or pmask.dtype != torch.float32 or not pmask.is_contiguous():
+        raise ValueError(f"attention dropout mask must be a contiguous fp32 [B={B}, H={H}, T={T}, T] tensor, got {tuple(pmask.shape)}")
+    return pmask
+
+
+def attn_train_fwd(qkv, B, T, H, D, bias_mode=0, period=1, want_p=True, pmask=None):
+    """pmask: the (pre-scaled) dropout draw on the probabilities, train mode only; P keeps the softmax itself."""
     _need_cuda(qkv)
     out = torch.empty((B * T, H * D), dtype=torch.float32, device=qkv.device)
     P = torch.empty((B, H, T, T), dtype=torch.float32, device=qkv.device) if want_p else None
-    _chk(_lib.load().avi_attn_train_fwd(_ptr(qkv), _ptr(out), _ptr(P), C.c_int32(B), C.c_int32(T), C.c_int32(H), C.c_int32(D),
-                                        C.c_float(D ** -0.5), C.c_int32(bias_mode), C.c_int32(period), _stream()), "avi_attn_train_fwd")
+    _chk(_lib.load().avi_attn_train_fwd_drop(_ptr(qkv), _ptr(out), _ptr(P), _ptr(_pmask(pmask, B, H, T)), C.c_int32(B), C.c_int32(T),
+                                             C.c_int32(H), C.c_int32(D), C.c_float(D ** -0.5), C.c_int32(bias_mode), C.c_int32(period),
+                                             _stream()), "avi_attn_train_fwd")
     return out, P
 
 
-def attn_train_bwd(qkv, P, dout, B, T, H, D):
+def attn_train_bwd(qkv, P, dout, B, T, H, D, pmask=None):
     _need_cuda(qkv, P, dout)
     dqkv = torch.empty_like(qkv)
     dS = torch.empty_like(P)
-    _chk(_lib.load().avi_attn_train_bwd(_ptr(qkv), _ptr(P), _ptr(dout.contiguous()), _ptr(dqkv), _ptr(dS), C.c_int32(B), C.c_int32(T),
-                                        C.c_int32(H), C.c_int32(D), C.c_float(D ** -0.5), _stream()), "avi_attn_train_bwd")
+    _chk(_lib.load().avi_attn_train_bwd_drop(_ptr(qkv), _ptr(P), _ptr(_pmask(pmask, B, H, T)), _ptr(dout.contiguous()), _ptr(dqkv), _ptr(dS),
+                                             C.c_int32(B), C.c_int32(T), C.c_int32(H), C.c_int32(D), C.c_float(D ** -0.5), _stream()),
+         "avi_attn_train_bwd")
     return dqkv
+
+
+def mask_mul(x, mask, residual=None):
+    """nn.Dropout with the draw as an input: x * mask (+ residual); also its backward (dy * mask). fp32, same number of elements."""
+    _need_cuda(x, mask)
+    if mask.dtype != torch.float32 or mask.numel() != x.numel() or not mask.is_contiguous():
+        raise ValueError(f"dropout mask: contiguous fp32 with {x.numel()} elements expected, got {tuple(mask.shape)} {mask.dtype}")
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    _chk(_lib.load().avi_mask_mul_add(_ptr(x), _ptr(mask), _ptr(None if residual is None else residual.contiguous()), _ptr(y),
+                                      C.c_int64(x.numel()), _stream()), "avi_mask_mul_add")
+    return y
+
+
+def spec_augment_fwd_(x, row_mask, embed):
+    """In place: rows of x [rows, C] whose row_mask byte (uint8 [rows]) is set become masked_spec_embed (wav2vec.py:120-131)."""
+    _need_cuda(x, row_mask, embed)
+    assert x.is_contiguous() and row_mask.dtype == torch.uint8 and row_mask.numel() == x.shape[0]
+    _chk(_lib.load().avi_spec_augment_fwd(_ptr(x), _ptr(row_mask), _ptr(embed.contiguous()), C.c_int64(x.shape[0]), C.c_int32(x.shape[1]),
+                                          _stream()), "avi_spec_augment_fwd")
+    return x
+
+
+def spec_augment_bwd_(dx, row_mask, g_embed):
+    """In place: g_embed <- sum of the masked rows of dx; those rows of dx <- 0."""
+    _need_cuda(dx, row_mask, g_embed)
+    assert dx.is_contiguous() and g_embed.is_contiguous() and row_mask.dtype == torch.uint8 and row_mask.numel() == dx.shape[0]
+    _chk(_lib.load().avi_spec_augment_bwd(_ptr(dx), _ptr(row_mask), _ptr(g_embed), C.c_int64(dx.shape[0]), C.c_int32(dx.shape[1]),
+                                          _stream()), "avi_spec_augment_bwd")
+    return dx
 
 
 def posconv_dw(x, dpc, B, T, groups, k):

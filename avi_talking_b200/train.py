@@ -17,8 +17,11 @@ Design (B200-first, not a port of autograd):
   * q/k/v weights of an encoder layer are adjacent in the flat buffers: the fused [2304, 768] QKV weight and its gradient are
     views, no concatenation per step.
 
-Regularisers (dropout 0.1 in the decoder layer / PPE / wav2vec2, SpecAugment, LayerDrop) are NOT applied: the step is the
-deterministic function the oracle and the golden fixture (the reference's own forward_switch_frame under .eval()) pin.
+Regularisers. Without `reg` the step is the deterministic .eval() function (tests/golden/train.npz). With `reg` it is the reference's
+TRAIN mode: dropout 0.1 in wav2vec2 (hidden / attention / activation, optional feat_proj), the PPE and the five sites of
+nn.TransformerDecoderLayer, SpecAugment along time (models/lib/wav2vec.py:16-63,120-131) and LayerDrop - every draw an INPUT tensor
+(`synth.train_regularisers` for the seeded test case, `draw_regularisers` on the device for real runs), so that the step stays a
+deterministic function the oracle and tests/golden/train_reg.npz (the reference in .train() mode with the same draws injected) pin.
 """
 from __future__ import annotations
 
@@ -69,12 +72,14 @@ class FlatLayout:
         order += ["audio_encoder.encoder.layer_norm.weight", "audio_encoder.encoder.layer_norm.bias", pc + "bias", g_name, v_name,
                   "audio_encoder.feature_projection.projection.weight", "audio_encoder.feature_projection.projection.bias",
                   "audio_encoder.feature_projection.layer_norm.weight", "audio_encoder.feature_projection.layer_norm.bias"]
+        if "audio_encoder.masked_spec_embed" in named and named["audio_encoder.masked_spec_embed"].requires_grad:
+            order.append("audio_encoder.masked_spec_embed")     # gradient only under SpecAugment (train mode); zero otherwise
         self.segments.append(len(order))
         missing = [n for n in order if n not in named]
         if missing:
             raise RuntimeError(f"FlatLayout: model lacks parameters {missing}")
-        # everything else that requires grad gets no gradient from this step (masked_spec_embed: SpecAugment only; obj_embedding,
-        # and for the disentangle variant v_merge2hidden / learnable_eye_embed, which forward_switch_frame never touches)
+        # everything else that requires grad gets no gradient from this step (obj_embedding, and for the disentangle variant
+        # v_merge2hidden / learnable_eye_embed, which forward_switch_frame never touches)
         self.unused = [n for n, p in named.items() if p.requires_grad and n not in order]
         frozen = [n for n in order if not named[n].requires_grad]
         if frozen:
@@ -234,6 +239,71 @@ class FlatAdam:
             self.model._flat_params_bf16_tag = shadow_tag(self.model)
 
 
+# ------------------------------------------------------------------------------------------------ train-mode regularisers
+ENC_SITES = ("attn", "h1", "act", "h3")
+DEC_SITES = ("ppe", "dec.sa", "dec.d1", "dec.ca", "dec.d2", "dec.act", "dec.d3")
+
+
+def regulariser_shapes(B, T, fd, cfg, dec_heads=4):
+    """site -> shape of its dropout draw (the dict layout of synth.train_regularisers)."""
+    M, C, F, H = B * T, cfg.hidden_size, cfg.intermediate_size, cfg.num_attention_heads
+    shp = {"enc_in": (M, C), "ppe": (M, fd), "dec.sa": (B, dec_heads, T, T), "dec.d1": (M, fd), "dec.ca": (B, dec_heads, T, T),
+           "dec.d2": (M, fd), "dec.act": (M, 2 * fd), "dec.d3": (M, fd)}
+    if getattr(cfg, "feat_proj_dropout", 0.0) > 0:
+        shp["featproj"] = (M, C)
+    for l in range(cfg.num_hidden_layers):
+        shp.update({f"l{l}.attn": (B, H, T, T), f"l{l}.h1": (M, C), f"l{l}.act": (M, F), f"l{l}.h3": (M, C)})
+    return shp
+
+
+def draw_regularisers(B, T, fd, cfg, device, generator=None, p_dec=0.1, spec_augment=True):
+    """One step's draws on the device, in the reference's configuration: HF Wav2Vec2Config's hidden / attention / activation dropout
+    and layerdrop, SpecAugment with mask_time_prob / mask_time_length and at least two spans per clip (wav2vec.py:120-131 calls
+    _compute_mask_indices(min_masks=2)), dropout 0.1 for the PPE and nn.TransformerDecoderLayer. The random stream is torch's device
+    generator, not the reference's (which interleaves its draws with the forward): parity is pinned with INJECTED draws instead."""
+    def mask(shape, p):
+        if p <= 0:
+            return None
+        return (torch.rand(shape, device=device, generator=generator) >= p).float().div_(1.0 - p)
+
+    shp = regulariser_shapes(B, T, fd, cfg)
+    p_site = {"featproj": getattr(cfg, "feat_proj_dropout", 0.0), "enc_in": cfg.hidden_dropout}
+    for l in range(cfg.num_hidden_layers):
+        p_site.update({f"l{l}.attn": cfg.attention_dropout, f"l{l}.h1": cfg.hidden_dropout, f"l{l}.act": cfg.activation_dropout,
+                       f"l{l}.h3": cfg.hidden_dropout})
+    masks = {}
+    for name, s_ in shp.items():
+        mk = mask(s_, p_site.get(name, p_dec))
+        if mk is not None:
+            masks[name] = mk
+    keep = (torch.rand(cfg.num_hidden_layers, generator=generator, device=device) >= cfg.layerdrop).tolist()
+    spec = None
+    if spec_augment and getattr(cfg, "apply_spec_augment", True) and cfg.mask_time_prob > 0:
+        L = cfg.mask_time_length
+        n_spans = max(2, int(cfg.mask_time_prob * T / L + torch.rand((), device=device, generator=generator).item()))
+        if L < T:
+            starts = torch.randint(0, T - L + 1, (B, n_spans), device=device, generator=generator)
+            idx = (starts[:, :, None] + torch.arange(L, device=device)[None, None, :]).reshape(B, -1)
+            spec = torch.zeros(B, T, dtype=torch.bool, device=device).scatter_(1, idx, True)
+    return {"p": p_dec, "spec_mask": spec, "layer_keep": keep, "masks": masks}
+
+
+def regularisers_to_device(reg, device):
+    """The dict of synth.train_regularisers / draw_regularisers with every tensor on `device` (fp32 contiguous masks, uint8 span rows)
+    and the cross-attention draw reduced to what the degenerate cross-attention sees: the ONE visible key of query t is key t
+    (enc_dec_mask, vocaset), so head h of the value row (b, t) is scaled by mask[b, h, t, t]."""
+    if reg is None or reg.get("_on_device") == str(device):
+        return reg
+    out = {"p": reg.get("p"), "layer_keep": [bool(k) for k in reg["layer_keep"]], "_on_device": str(device)}
+    out["masks"] = {k: v.to(device=device, dtype=torch.float32).contiguous() for k, v in reg["masks"].items()}
+    sm = reg.get("spec_mask")
+    out["spec_mask"] = None if sm is None else sm.to(device).reshape(-1).to(torch.uint8).contiguous()
+    ca = out["masks"].get("dec.ca")
+    if ca is not None:
+        out["ca_diag"] = torch.diagonal(ca, dim1=2, dim2=3).permute(0, 2, 1).contiguous()          # [B, T, heads]
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ the step
 class _Lin:
     """Operand plumbing of one precision."""
@@ -347,8 +417,9 @@ class TrainStep:
 
     # ---------------------------------------------------------------------------- forward
     @torch.no_grad()
-    def forward(self, audio, gt_verts):
-        """audio [B, N] fp32, gt_verts [B, T, V*3] fp32 (row stride may be padded) -> loss (0-dim fp32 tensor)."""
+    def forward(self, audio, gt_verts, reg=None):
+        """audio [B, N] fp32, gt_verts [B, T, V*3] fp32 (row stride may be padded) -> loss (0-dim fp32 tensor).
+        reg: the draws of one TRAIN-mode step (module docstring); None = the .eval() arithmetic."""
         m = self.model
         w2v, cfg = m.audio_encoder, m.audio_encoder.config
         if not audio.is_cuda:
@@ -363,6 +434,15 @@ class TrainStep:
         if T > 128:
             raise NotImplementedError("training clips of more than 128 frames (VOCASET clips are ~100-150 at 30 fps; split longer ones)")
         S = {"B": B, "T": T, "M": M}
+        S["reg"] = reg = regularisers_to_device(reg, audio.device)
+        mk = reg["masks"] if reg is not None else {}
+        keep = reg["layer_keep"] if reg is not None else [True] * len(w2v.encoder.layers)
+
+        def drop(name, t, residual=None):
+            """nn.Dropout at site `name` (+ the residual the reference adds right after); the plain add / identity without a draw."""
+            if name in mk:
+                return ops.mask_mul(t, mk[name], residual)
+            return t if residual is None else ops.add_f32(t, residual)
         eps = cfg.layer_norm_eps
         H, D = cfg.num_attention_heads, cfg.hidden_size // cfg.num_attention_heads
         # -- frozen conv feature extractor (no gradient, :154) and the 50 -> frame_num resample (wav2vec.py:97-108)
@@ -373,30 +453,48 @@ class TrainStep:
         fp = w2v.feature_projection
         hn, _ = ops.layernorm(h, fp.layer_norm.weight, fp.layer_norm.bias, eps=eps)
         S["hn"] = hn
-        S["proj"] = proj = lin.fwd(lin.a(hn), fp.projection.weight, fp.projection.bias)             # wav2vec.py:120
+        proj = lin.fwd(lin.a(hn), fp.projection.weight, fp.projection.bias)                         # wav2vec.py:120
+        if "featproj" in mk:                                                                        # Wav2Vec2FeatureProjection.dropout
+            proj = ops.mask_mul(proj, mk["featproj"])
+        if reg is not None and reg["spec_mask"] is not None:                                        # SpecAugment, wav2vec.py:120-131
+            ops.spec_augment_fwd_(proj, reg["spec_mask"], w2v.masked_spec_embed)
+        S["proj"] = proj
         # -- positional conv embedding + encoder LayerNorm
         S["pos_w"] = pos_w = w2v._posconv_weight().float().contiguous()
         S["pc"] = pcb = self._posconv(proj, pos_w, B, T, flip=False, bias=w2v.encoder.pos_conv_embed.conv.bias)
         gpc, _ = ops.act_fwd(pcb, ACT_GELU)
         S["h0pre"] = h0pre = ops.add_f32(proj, gpc)
         x, _ = ops.layernorm(h0pre, w2v.encoder.layer_norm.weight, w2v.encoder.layer_norm.bias, eps=eps)
+        if "enc_in" in mk:                                                                          # Wav2Vec2Encoder.dropout
+            x = ops.mask_mul(x, mk["enc_in"])
         # -- 12 post-LN encoder layers (fused q|k|v weight = a view of the flat parameter buffer)
         P, lay = m._flat_params, self.layout
         S["layers"] = []
         for l, lyr in enumerate(w2v.encoder.layers):
+            if not keep[l]:                                    # LayerDrop: the layer is the identity and gets no gradient
+                S["layers"].append(None)
+                continue
             pre = f"audio_encoder.encoder.layers.{l}.attention."
             Wqkv = lay.span(P, pre + "q_proj.weight", 3 * cfg.hidden_size, cfg.hidden_size)
             bqkv = lay.span(P, pre + "q_proj.bias", 1, 3 * cfg.hidden_size).view(-1)
             a = lyr.attention
             L = {"x": x, "Wqkv": Wqkv}
             L["qkv"] = qkv = lin.fwd(lin.a(x), Wqkv, bqkv)
-            L["att"], L["P"] = att, _ = ops.attn_train_fwd(qkv, B, T, H, D)
-            L["y"] = y = lin.fwd(lin.a(att), a.out_proj.weight, a.out_proj.bias, residual=x)
+            L["att"], L["P"] = att, _ = ops.attn_train_fwd(qkv, B, T, H, D, pmask=mk.get(f"l{l}.attn"))
+            if f"l{l}.h1" in mk:
+                y = drop(f"l{l}.h1", lin.fwd(lin.a(att), a.out_proj.weight, a.out_proj.bias), x)
+            else:
+                y = lin.fwd(lin.a(att), a.out_proj.weight, a.out_proj.bias, residual=x)
+            L["y"] = y
             L["h1"] = h1 = ops.layernorm(y, lyr.layer_norm.weight, lyr.layer_norm.bias, eps=eps)[0]
             ff = lyr.feed_forward
             L["fpre"] = fpre = lin.fwd(lin.a(h1), ff.intermediate_dense.weight, ff.intermediate_dense.bias)
-            L["f"] = f = ops.act_fwd(fpre, ACT_GELU)[0]
-            L["y2"] = y2 = lin.fwd(lin.a(f), ff.output_dense.weight, ff.output_dense.bias, residual=h1)
+            L["f"] = f = drop(f"l{l}.act", ops.act_fwd(fpre, ACT_GELU)[0])          # the operand of output_dense (dropped)
+            if f"l{l}.h3" in mk:
+                y2 = drop(f"l{l}.h3", lin.fwd(lin.a(f), ff.output_dense.weight, ff.output_dense.bias), h1)
+            else:
+                y2 = lin.fwd(lin.a(f), ff.output_dense.weight, ff.output_dense.bias, residual=h1)
+            L["y2"] = y2
             x = ops.layernorm(y2, lyr.final_layer_norm.weight, lyr.final_layer_norm.bias, eps=eps)[0]
             S["layers"].append(L)
         S["h12"] = x
@@ -413,21 +511,38 @@ class TrainStep:
         style = m.obj_vector.weight[:, 0].contiguous().view(1, fd)                                     # one_hot[:, 0] = 1 (:361-365)
         period = m.args.period
         ops.ff_add_style_pe(xd, style, m.PPE.pe[0, :period].contiguous(), B, T, fd, period)            # :446-447
+        xd = drop("ppe", xd)                                                                           # PPE dropout
         dl = m.transformer_decoder.layers[0]
         S["xd"] = xd
         S["dqkv_in"] = qkv = lin.fwd(lin.a(xd), dl.self_attn.in_proj_weight, dl.self_attn.in_proj_bias)
-        S["datt"], S["dP"] = att, _ = ops.attn_train_fwd(qkv, B, T, 4, fd // 4, bias_mode=1, period=period)
-        S["dy1"] = y1 = lin.fwd(lin.a(att), dl.self_attn.out_proj.weight, dl.self_attn.out_proj.bias, residual=xd)
+        S["datt"], S["dP"] = att, _ = ops.attn_train_fwd(qkv, B, T, 4, fd // 4, bias_mode=1, period=period, pmask=mk.get("dec.sa"))
+        if "dec.d1" in mk:
+            y1 = drop("dec.d1", lin.fwd(lin.a(att), dl.self_attn.out_proj.weight, dl.self_attn.out_proj.bias), xd)
+        else:
+            y1 = lin.fwd(lin.a(att), dl.self_attn.out_proj.weight, dl.self_attn.out_proj.bias, residual=xd)
+        S["dy1"] = y1
         S["x1"] = x1 = ops.layernorm(y1, dl.norm1.weight, dl.norm1.bias, eps=1e-5)[0]
         # cross-attention with enc_dec_mask (:80-88) sees exactly one key per query: softmax == 1, output = out_proj(v_proj(mem_t)),
         # and the q / k projections get exactly zero gradient
         Wc, bc = dl.multihead_attn.in_proj_weight, dl.multihead_attn.in_proj_bias
-        S["cv"] = cv = lin.fwd(lin.a(mem), Wc[2 * fd:], bc[2 * fd:])
-        S["dy2"] = y2 = lin.fwd(lin.a(cv), dl.multihead_attn.out_proj.weight, dl.multihead_attn.out_proj.bias, residual=x1)
+        cv = lin.fwd(lin.a(mem), Wc[2 * fd:], bc[2 * fd:])
+        if reg is not None and "ca_diag" in reg:           # dropout on the single unit probability: head h of row (b, t) x mask[b, h, t, t]
+            S["ca_scale"] = reg["ca_diag"].repeat_interleave(fd // 4, dim=2).reshape(M, fd).contiguous()
+            cv = ops.mask_mul(cv, S["ca_scale"])
+        S["cv"] = cv
+        if "dec.d2" in mk:
+            y2 = drop("dec.d2", lin.fwd(lin.a(cv), dl.multihead_attn.out_proj.weight, dl.multihead_attn.out_proj.bias), x1)
+        else:
+            y2 = lin.fwd(lin.a(cv), dl.multihead_attn.out_proj.weight, dl.multihead_attn.out_proj.bias, residual=x1)
+        S["dy2"] = y2
         S["x2"] = x2 = ops.layernorm(y2, dl.norm2.weight, dl.norm2.bias, eps=1e-5)[0]
         S["f1pre"] = f1pre = lin.fwd(lin.a(x2), dl.linear1.weight, dl.linear1.bias)
-        S["f1"] = f1 = ops.act_fwd(f1pre, ACT_RELU)[0]
-        S["dy3"] = y3 = lin.fwd(lin.a(f1), dl.linear2.weight, dl.linear2.bias, residual=x2)
+        S["f1"] = f1 = drop("dec.act", ops.act_fwd(f1pre, ACT_RELU)[0])
+        if "dec.d3" in mk:
+            y3 = drop("dec.d3", lin.fwd(lin.a(f1), dl.linear2.weight, dl.linear2.bias), x2)
+        else:
+            y3 = lin.fwd(lin.a(f1), dl.linear2.weight, dl.linear2.bias, residual=x2)
+        S["dy3"] = y3
         S["x3"] = x3 = ops.layernorm(y3, dl.norm3.weight, dl.norm3.bias, eps=1e-5)[0]
         out = ops.empty_rows(M, V3, audio.device)
         bias = (m.vertice_map_r.bias + template).contiguous()                                          # + template (:475)
@@ -454,6 +569,12 @@ class TrainStep:
         eps = cfg.layer_norm_eps
         G = torch.zeros(lay.total, dtype=torch.float32, device=S["h"].device)
         g = lambda n: lay.view(G, n)  # noqa: E731
+        reg = S["reg"]
+        mk = reg["masks"] if reg is not None else {}
+
+        def dropb(name, dy):
+            """Gradient through the dropout of site `name`: dy * mask (the same launch as the forward); identity without a draw."""
+            return ops.mask_mul(dy, mk[name]) if name in mk else dy
         bk = self.buckets
         if bk is not None:
             bk.begin()
@@ -474,21 +595,24 @@ class TrainStep:
         WrT = ops.transpose_cast(m.vertice_map_r.weight, lin.dt, V3p)                                   # [fd, 15104]
         dx3 = ops.linear(ops.cast_pad2d(dout, lin.dt, C_pad=V3p), WrT, None, out_dtype=torch.float32)
         dy3 = ops.layernorm_bwd(S["dy3"], dl.norm3.weight, dx3, g(d + "norm3.weight"), g(d + "norm3.bias"), eps=1e-5)
-        df1 = lin.bwd(dy3, S["f1"], dl.linear2.weight, g(d + "linear2.weight"), g(d + "linear2.bias"), Mp)
-        df1pre = ops.act_bwd(S["f1pre"], df1, ACT_RELU)
+        df1 = lin.bwd(dropb("dec.d3", dy3), S["f1"], dl.linear2.weight, g(d + "linear2.weight"), g(d + "linear2.bias"), Mp)
+        df1pre = ops.act_bwd(S["f1pre"], dropb("dec.act", df1), ACT_RELU)
         dx2 = lin.bwd(df1pre, S["x2"], dl.linear1.weight, g(d + "linear1.weight"), g(d + "linear1.bias"), Mp, residual=dy3)
         dy2 = ops.layernorm_bwd(S["dy2"], dl.norm2.weight, dx2, g(d + "norm2.weight"), g(d + "norm2.bias"), eps=1e-5)
-        dcv = lin.bwd(dy2, S["cv"], dl.multihead_attn.out_proj.weight, g(d + "multihead_attn.out_proj.weight"),
+        dcv = lin.bwd(dropb("dec.d2", dy2), S["cv"], dl.multihead_attn.out_proj.weight, g(d + "multihead_attn.out_proj.weight"),
                       g(d + "multihead_attn.out_proj.bias"), Mp)
+        if "ca_scale" in S:
+            dcv = ops.mask_mul(dcv, S["ca_scale"])
         Wc = dl.multihead_attn.in_proj_weight
         dmem = lin.bwd(dcv, S["mem"], Wc[2 * fd:], g(d + "multihead_attn.in_proj_weight")[2 * fd:],
                        g(d + "multihead_attn.in_proj_bias")[2 * fd:], Mp)
         dy1 = ops.layernorm_bwd(S["dy1"], dl.norm1.weight, dy2, g(d + "norm1.weight"), g(d + "norm1.bias"), eps=1e-5)
-        datt = lin.bwd(dy1, S["datt"], dl.self_attn.out_proj.weight, g(d + "self_attn.out_proj.weight"),
+        datt = lin.bwd(dropb("dec.d1", dy1), S["datt"], dl.self_attn.out_proj.weight, g(d + "self_attn.out_proj.weight"),
                        g(d + "self_attn.out_proj.bias"), Mp)
-        dqkv = ops.attn_train_bwd(S["dqkv_in"], S["dP"], datt, B, T, 4, fd // 4)
+        dqkv = ops.attn_train_bwd(S["dqkv_in"], S["dP"], datt, B, T, 4, fd // 4, pmask=mk.get("dec.sa"))
         dxd = lin.bwd(dqkv, S["xd"], dl.self_attn.in_proj_weight, g(d + "self_attn.in_proj_weight"), g(d + "self_attn.in_proj_bias"),
                       Mp, residual=dy1)
+        dxd = dropb("ppe", dxd)
         # xd = vin Wvm^T + bvm + style + pe
         vinT = lin.t(S["vin"][:, :V3], Mp)                                                              # [15069, Mp]
         ops.gemm(lin.t(dxd, Mp), vinT, None, g("vertice_map.weight"), rows=fd, N=V3, K=Mp, a_rows_alloc=fd, c_ld=V3)
@@ -505,18 +629,24 @@ class TrainStep:
         nl = len(w2v.encoder.layers)
         for l in reversed(range(nl)):
             lyr, L = w2v.encoder.layers[l], S["layers"][l]
+            if L is None:                                       # LayerDrop: identity, gradients stay zero
+                if bk is not None:
+                    seg = lay.segments[nl - l]
+                    bk.ready(G, lay.offsets[lay.names[seg]] if seg < len(lay.names) else lay.total)
+                continue
             p = f"audio_encoder.encoder.layers.{l}."
             ff, a = lyr.feed_forward, lyr.attention
             dy2 = ops.layernorm_bwd(L["y2"], lyr.final_layer_norm.weight, dh, g(p + "final_layer_norm.weight"),
                                     g(p + "final_layer_norm.bias"), eps=eps)
-            df = lin.bwd(dy2, L["f"], ff.output_dense.weight, g(p + "feed_forward.output_dense.weight"),
+            df = lin.bwd(dropb(f"l{l}.h3", dy2), L["f"], ff.output_dense.weight, g(p + "feed_forward.output_dense.weight"),
                          g(p + "feed_forward.output_dense.bias"), Mp)
-            dfpre = ops.act_bwd(L["fpre"], df, ACT_GELU)
+            dfpre = ops.act_bwd(L["fpre"], dropb(f"l{l}.act", df), ACT_GELU)
             dh1 = lin.bwd(dfpre, L["h1"], ff.intermediate_dense.weight, g(p + "feed_forward.intermediate_dense.weight"),
                           g(p + "feed_forward.intermediate_dense.bias"), Mp, residual=dy2)
             dy = ops.layernorm_bwd(L["y"], lyr.layer_norm.weight, dh1, g(p + "layer_norm.weight"), g(p + "layer_norm.bias"), eps=eps)
-            datt = lin.bwd(dy, L["att"], a.out_proj.weight, g(p + "attention.out_proj.weight"), g(p + "attention.out_proj.bias"), Mp)
-            dqkv = ops.attn_train_bwd(L["qkv"], L["P"], datt, B, T, H, D)
+            datt = lin.bwd(dropb(f"l{l}.h1", dy), L["att"], a.out_proj.weight, g(p + "attention.out_proj.weight"),
+                           g(p + "attention.out_proj.bias"), Mp)
+            dqkv = ops.attn_train_bwd(L["qkv"], L["P"], datt, B, T, H, D, pmask=mk.get(f"l{l}.attn"))
             gW = lay.span(G, p + "attention.q_proj.weight", 3 * C, C)
             gb = lay.span(G, p + "attention.q_proj.bias", 1, 3 * C).view(-1)
             dh = lin.bwd(dqkv, L["x"], L["Wqkv"], gW, gb, Mp, residual=dy)
@@ -524,7 +654,7 @@ class TrainStep:
                 seg = lay.segments[nl - l]
                 bk.ready(G, lay.offsets[lay.names[seg]] if seg < len(lay.names) else lay.total)
         # encoder LayerNorm, positional conv (weight norm), feature projection
-        dh0pre = ops.layernorm_bwd(S["h0pre"], w2v.encoder.layer_norm.weight, dh, g("audio_encoder.encoder.layer_norm.weight"),
+        dh0pre = ops.layernorm_bwd(S["h0pre"], w2v.encoder.layer_norm.weight, dropb("enc_in", dh), g("audio_encoder.encoder.layer_norm.weight"),
                                    g("audio_encoder.encoder.layer_norm.bias"), eps=eps)
         dpc = ops.act_bwd(S["pc"], dh0pre, ACT_GELU)
         ops.colsum(dpc, out=g("audio_encoder.encoder.pos_conv_embed.conv.bias"))
@@ -535,6 +665,11 @@ class TrainStep:
         g(lay.pos_v).copy_(dv)
         g(lay.pos_g).copy_(dg)
         dproj = ops.add_f32(dh0pre, self._posconv(dpc, S["pos_w"], B, T, flip=True))
+        if reg is not None and reg["spec_mask"] is not None:    # the replaced rows feed masked_spec_embed, not the projection
+            if "audio_encoder.masked_spec_embed" not in lay.offsets:
+                raise RuntimeError("SpecAugment needs audio_encoder.masked_spec_embed among the trainable parameters")
+            ops.spec_augment_bwd_(dproj, reg["spec_mask"], g("audio_encoder.masked_spec_embed"))
+        dproj = dropb("featproj", dproj)
         fp = w2v.feature_projection
         fpn = "audio_encoder.feature_projection."
         dhn = lin.bwd(dproj, S["hn"], fp.projection.weight, g(fpn + "projection.weight"), g(fpn + "projection.bias"), Mp)
@@ -552,22 +687,23 @@ class _LossFn(torch.autograd.Function):
     """`loss = model(...)` / `loss.backward()` as upstream: backward runs TrainStep.backward and fills the parameters' .grad."""
 
     @staticmethod
-    def forward(ctx, anchor, step, audio, gt):
+    def forward(ctx, anchor, step, audio, gt, reg):
         ctx.step = step
-        return step.forward(audio, gt)
+        return step.forward(audio, gt, reg=reg)
 
     @staticmethod
     def backward(ctx, gloss):
         step = ctx.step
         # the upstream gradient stays on the device (no float(gloss) host sync every step)
         step.grad_divisor = step.backward(grad_tensor=gloss if gloss.numel() == 1 else None)
-        return None, None, None, None
+        return None, None, None, None, None
 
 
-def training_loss(step: TrainStep, audio, gt_verts):
-    """Differentiable-looking loss: a 0-dim tensor whose .backward() fills every trainable parameter's .grad (flat views)."""
+def training_loss(step: TrainStep, audio, gt_verts, reg=None):
+    """Differentiable-looking loss: a 0-dim tensor whose .backward() fills every trainable parameter's .grad (flat views).
+    reg: the draws of a TRAIN-mode step (None = the .eval() arithmetic)."""
     anchor = torch.zeros((), device=audio.device, requires_grad=True)
-    return _LossFn.apply(anchor, step, audio, gt_verts)
+    return _LossFn.apply(anchor, step, audio, gt_verts, reg)
 
 
 class GraphedTrainStep:
@@ -580,46 +716,86 @@ class GraphedTrainStep:
     Data parallel (`buckets` = a GradBuckets over the process group): the bucketed NCCL all-reduces are captured INSIDE the graph, on
     the communication stream forked from the backward stream (NCCL collectives are stream-ordered kernels, so the fork / join is
     ordinary graph structure); one replay then runs forward, backward and the overlapped exchange with no host launch in between.
-    Round 1 ran the multi-GPU step eagerly and two GPUs were slower per step than one graph-replayed GPU."""
+    Round 1 ran the multi-GPU step eagerly and two GPUs were slower per step than one graph-replayed GPU.
 
-    def __init__(self, model, audio_shape, gt_shape, warmup=2, buckets: GradBuckets | None = None):
+    Train mode (`reg`, see draw_regularisers): the dropout / SpecAugment draws are copied into static buffers the graph reads, so a
+    new draw every step replays the same graph; LayerDrop changes which kernels run, so there is one graph per keep pattern
+    (the `max_graphs` most recently used are kept; ranks may draw different patterns: a skipped layer still reports its bucket)."""
+
+    def __init__(self, model, audio_shape, gt_shape, warmup=2, buckets: GradBuckets | None = None, max_graphs=8):
         self.model = model
         self.step = TrainStep(model, buckets=buckets)
         dev = model._flat_params.device
         self.audio = torch.zeros(audio_shape, dtype=torch.float32, device=dev)
         self.gt = torch.zeros(gt_shape, dtype=torch.float32, device=dev)
-        self.graph = None
+        self.graphs = {}               # key -> dict(graph, loss, grad, reg)
+        self.max_graphs = max_graphs
         self.warmup = warmup
-        self.tag = None
+        self.graph = None              # the most recently replayed graph (kept for callers that look at it)
 
-    def _capture(self):
+    @staticmethod
+    def _reg_key(reg):
+        if reg is None:
+            return None
+        return (tuple(bool(k) for k in reg["layer_keep"]), reg.get("spec_mask") is not None, tuple(sorted(reg["masks"])))
+
+    def _static_reg(self, reg):
+        """Device-resident copy of the draws with fixed addresses (what the captured kernels read)."""
+        dev = self.audio.device
+        st = regularisers_to_device({k: v for k, v in reg.items() if k != "_on_device"}, dev)
+        st["masks"] = {k: v.clone() for k, v in st["masks"].items()}
+        if st["spec_mask"] is not None:
+            st["spec_mask"] = st["spec_mask"].clone()
+        if "ca_diag" in st:
+            st["ca_diag"] = st["ca_diag"].clone()
+        return st
+
+    @staticmethod
+    def _load_reg(static, reg):
+        for k, v in static["masks"].items():
+            v.copy_(reg["masks"][k].reshape(v.shape), non_blocking=True)
+        if static["spec_mask"] is not None:
+            static["spec_mask"].copy_(reg["spec_mask"].reshape(-1), non_blocking=True)
+        if "ca_diag" in static:
+            static["ca_diag"].copy_(torch.diagonal(static["masks"]["dec.ca"], dim1=2, dim2=3).permute(0, 2, 1))
+
+    def _capture(self, reg):
         m = self.model
         if m.precision == "bf16":
             bf16_shadow(m)
+        static = self._static_reg(reg) if reg is not None else None
         side = torch.cuda.Stream(device=self.audio.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(self.warmup):                       # one-time attribute calls, allocator warm-up
-                self.step.forward(self.audio, self.gt)
+                self.step.forward(self.audio, self.gt, reg=static)
                 self.step.backward()
         torch.cuda.current_stream().wait_stream(side)
-        self.graph = torch.cuda.CUDAGraph()
+        graph = torch.cuda.CUDAGraph()
         # thread_local: the NCCL watchdog thread of a process group may query events while this thread captures
-        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
-            self.loss = self.step.forward(self.audio, self.gt)
+        with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+            loss = self.step.forward(self.audio, self.gt, reg=static)
             self.step.backward()
-        self.grad = m._flat_grad
-        self.tag = (m.precision, m._flat_params.data_ptr())
+        return {"graph": graph, "loss": loss, "grad": m._flat_grad, "reg": static}
 
-    def __call__(self, audio, gt_verts):
+    def __call__(self, audio, gt_verts, reg=None):
         m = self.model
         self.audio.copy_(audio)
         self.gt.copy_(gt_verts)
-        if self.graph is None or self.tag != (m.precision, m._flat_params.data_ptr()):
-            self._capture()
+        key = (m.precision, m._flat_params.data_ptr(), self._reg_key(reg))
+        ent = self.graphs.pop(key, None)
+        if ent is None:
+            while len(self.graphs) >= self.max_graphs:         # least recently used first (dicts keep insertion order)
+                self.graphs.pop(next(iter(self.graphs)))
+            ent = self._capture(reg)
+        self.graphs[key] = ent                                 # (re-)inserted last = most recently used
+        if reg is not None:
+            self._load_reg(ent["reg"], reg)
         if m.precision == "bf16":
             bf16_shadow(m)                                     # refreshed in place by FlatAdam; re-cast here only if someone else wrote
-        self.graph.replay()
+        self.graph = ent["graph"]
+        ent["graph"].replay()
+        self.loss, self.grad = ent["loss"], ent["grad"]
         m._flat_grad = self.grad
         lay = m._flat_layout
         for n, p in m.named_parameters():

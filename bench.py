@@ -49,6 +49,9 @@ def parse():
     ap.add_argument("--precision", default=os.environ.get("AVI_B200_PRECISION", "bf16"), choices=["bf16", "fp32"])
     ap.add_argument("--cpu-clips", type=int, default=2, help="clips in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--regularisers", default="draw", choices=["draw", "off"],
+                    help="train workload: 'draw' = the reference's TRAIN mode (dropout / SpecAugment / LayerDrop drawn on the device every "
+                         "step, draws inside the timed region); 'off' = the deterministic .eval() arithmetic")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying its CUDA graph")
     ap.add_argument("--cpu-baseline", default=None, choices=["prior", "train", "clip"],
                     help="only time the CPU oracle of another BASELINE config on a bounded sample (the cpu_baseline leg of the "
@@ -58,15 +61,16 @@ def parse():
 
 def ncu_traffic(kernel_substr):
     """DRAM bytes per launch (read + write) of a kernel from the committed ncu pass over this same command
-    (profiles/r1/traffic.json, written by profiles/summarise_launches.py); None when no capture is committed."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1", "traffic.json")) as fh:
-            t = json.load(fh)
-        for k, v in t.items():
-            if kernel_substr in k:
-                return float(v["dram_bytes_per_launch"])
-    except Exception:
-        pass
+    (profiles/r2/traffic.json, else the round-1 file; written by profiles/summarise_launches.py); None when no capture is committed."""
+    for rnd in ("r2", "r1"):
+        try:
+            with open(os.path.join(ROOT, "profiles", rnd, "traffic.json")) as fh:
+                t = json.load(fh)
+            for k, v in t.items():
+                if kernel_substr in k:
+                    return float(v["dram_bytes_per_launch"])
+        except Exception:
+            pass
     return None
 
 
@@ -614,7 +618,10 @@ TRAIN_T, TRAIN_N = 120, 64000            # one VOCASET-like clip: 4 s of 16 kHz 
 def train_config(args, n_par, world):
     return {"workload": f"BASELINE configs[4]: faceformer_vert teacher-forced training step (wav2vec2 fwd+bwd with the conv extractor "
                         f"frozen, decoder layer, 15069-wide vertex head, MSE x 10, Adam), {args.clips} clip(s) x 4 s ({TRAIN_T} frames) per GPU, "
-                        "fd=64, deterministic mode (dropout / SpecAugment / LayerDrop off), random-init (seeded) weights",
+                        "fd=64, " + ("TRAIN mode: dropout 0.1 / SpecAugment / LayerDrop drawn on the device every step inside the timed region"
+                                     if getattr(args, "regularisers", "off") == "draw" else "deterministic mode (dropout / SpecAugment / LayerDrop off)")
+                        + ", random-init (seeded) weights",
+            "regularisers": getattr(args, "regularisers", "off"),
             "clips_per_gpu": args.clips, "precision": args.precision, "trainable_params": n_par,
             "allreduce": "bucketed NCCL sum of the flat fp32 gradient, captured in the step's CUDA graph, overlapped with backward" if world > 1 else "none",
             "l2_policy": "working set (weights + moments + gradients = 1.5 GB) larger than L2", "launch": "eager" if args.no_graph else "cuda graph replay (forward + backward + all-reduce), Adam launched after it"}
@@ -691,21 +698,28 @@ def run_train(args):
     host_gt = (template + 1e-3 * torch.from_numpy(rng.normal(size=(B, T, 15069)).astype(np.float32))).pin_memory()
     host_audio = synth.audio(B, N, seed=500 + rank * B).pin_memory()
     gt, audio = host_gt.to(dev), host_audio.to(dev)
+    cfg_w2v = w2v.config
+    gen = torch.Generator(device=dev).manual_seed(11 + rank)
+
+    def draws():
+        # the reference trains in .train() mode: every step draws its dropout masks, SpecAugment spans and LayerDrop decisions
+        return train.draw_regularisers(B, T, fd, cfg_w2v, dev, generator=gen) if args.regularisers == "draw" else None
+
     if args.no_graph:
         step = train.TrainStep(m, buckets=buckets)
         m._train_step = step
 
         def one_step(a, g):
             opt.zero_grad()
-            loss = m.training_loss(a, g)
+            loss = m.training_loss(a, g, reg=draws())
             loss.backward()
             opt.step()
             return loss
     else:
-        gstep = train.GraphedTrainStep(m, audio.shape, gt.shape, buckets=buckets)
+        gstep = train.GraphedTrainStep(m, audio.shape, gt.shape, buckets=buckets, max_graphs=16)
 
         def one_step(a, g):
-            loss = gstep(a, g)
+            loss = gstep(a, g, reg=draws())
             opt.step()
             return loss
 
@@ -747,42 +761,12 @@ def run_train(args):
     barrier()
     e2e_ms = f0.elapsed_time(f1)
 
-    # OPT-IN compact sink, reported beside the headline, never instead of it: the same end-to-end step with both vertex sets leaving
-    # as fp16 displacements from the template (avi_pack_disp_f16): half the D2H bytes, outside the fp32 contract
-    tpl = model.template.reshape(-1).float().to(dev)
-    c_host = [[torch.empty((B * T, 15069), dtype=torch.float16).pin_memory() for _ in range(2)] for _ in range(2)]
-
-    def e2e_compact_step(i):
-        inp = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-        v, fv = step_eager(inp)
-        pv, pf = ops.pack_disp_f16(v.flatten(0, -2), tpl), ops.pack_disp_f16(fv.reshape(B * T, -1), tpl)
-        ev = torch.cuda.Event()
-        ev.record(main)
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(ev)
-            c_host[0][i & 1].copy_(pv, non_blocking=True)
-            c_host[1][i & 1].copy_(pf, non_blocking=True)
-        pv.record_stream(copy_stream)
-        pf.record_stream(copy_stream)
-
-    for i in range(3):
-        e2e_compact_step(i)
-    main.wait_stream(copy_stream)
-    barrier()
-    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    c0.record()
-    for i in range(args.steps):
-        e2e_compact_step(i)
-    main.wait_stream(copy_stream)
-    c1.record()
-    barrier()
-    compact_ms = c0.elapsed_time(c1)
     sampler.stop_flag.set()
     sampler.join(timeout=2)
     # exposed exchange = this step minus the same step without the all-reduce is not separable inside a graph; report the Adam kernel
     # (HBM-bound: 28 B per parameter) and the in-sync check instead
     a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    one_step(audio, gt) if args.no_graph else gstep(audio, gt)
+    one_step(audio, gt)
     a0.record()
     opt.step()
     a1.record()

@@ -371,6 +371,21 @@ int avi_attn_train_fwd(const float* qkv, float* out, float* P, int32_t B, int32_
                        int32_t period, void* stream);
 int avi_attn_train_bwd(const float* qkv, const float* P, const float* dout, float* dqkv, float* dS_scratch /* [B,H,T,T] */, int32_t B,
                        int32_t T, int32_t H, int32_t D, float scale, void* stream);
+/* TRAIN mode of the same attention (dropout on the probabilities: nn.MultiheadAttention(dropout=0.1) inside nn.TransformerDecoderLayer,
+ * faceformer_vert.py transformer_decoder; HF Wav2Vec2Attention attention_dropout): pmask [B,H,T,T] fp32 is the draw, Bernoulli(1-p)/(1-p),
+ * an INPUT (parity stays testable). P keeps the softmax itself; out = (P * pmask) V. pmask == NULL: the calls above. */
+int avi_attn_train_fwd_drop(const float* qkv, float* out, float* P, const float* pmask, int32_t B, int32_t T, int32_t H, int32_t D,
+                            float scale, int32_t bias_mode, int32_t period, void* stream);
+int avi_attn_train_bwd_drop(const float* qkv, const float* P, const float* pmask, const float* dout, float* dqkv, float* dS_scratch,
+                            int32_t B, int32_t T, int32_t H, int32_t D, float scale, void* stream);
+/* nn.Dropout with the draw as an input: y = x * mask (+ residual when not NULL); its own backward (dx = dy * mask). n % 4 == 0.
+ * Replaces the dropout sites of Wav2Vec2EncoderLayer / Wav2Vec2FeedForward / PeriodicPositionalEncoding / nn.TransformerDecoderLayer
+ * (dropout1-3, the feed-forward dropout) in the faceformer_vert training step (models/faceformer_vert.py:360-371,437-454). */
+int avi_mask_mul_add(const float* x, const float* mask, const float* residual, float* y, int64_t n, void* stream);
+/* SpecAugment along time (models/lib/wav2vec.py:120-131): rows [rows, C] whose row_mask byte is set are replaced by masked_spec_embed
+ * (in place); backward: g_embed = sum of the masked rows of dx, which are then zeroed (fixed summation order). */
+int avi_spec_augment_fwd(float* x, const uint8_t* row_mask, const float* embed, int64_t rows, int32_t C, void* stream);
+int avi_spec_augment_bwd(float* dx, const uint8_t* row_mask, float* g_embed, int64_t rows, int32_t C, void* stream);
 /* positional conv: dW [C, C/groups, k] from x [B,T,C] and d(pre-activation) [B,T,C]; weight-norm chain rule (dim = 2) */
 int avi_posconv_dw(const float* x, const float* dpc, float* dw, int32_t B, int32_t T, int32_t C, int32_t groups, int32_t k, void* stream);
 /* transposed unfold of the positional conv input for a block of CW channels starting at c0:

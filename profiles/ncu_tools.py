@@ -33,7 +33,13 @@ def source(rep, launch=0, top=30):
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--launch-skip", str(launch), "--launch-count", "1"],
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
-    hdr, data = rows[1], rows[2:]
+    # a report with several results prints one block per result ("Kernel Name" row, header row, SASS rows): keep the first block
+    # (--launch-skip already selected the result) and drop incomplete rows
+    starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+    end = starts[1] if len(starts) > 1 else len(rows)
+    rows = rows[starts[0]:end] if starts else rows
+    hdr = rows[1]
+    data = [r for r in rows[2:] if len(r) == len(hdr) and r[hdr.index("Warp Stall Sampling (All Samples)")] != ""]
     i_src, i_s, i_ex = hdr.index("Source"), hdr.index("Warp Stall Sampling (All Samples)"), hdr.index("Instructions Executed")
     stall = [(i, h) for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
     tot = sum(int(r[i_s]) for r in data)

@@ -15,8 +15,12 @@ n = int(seconds * 16000)
 T = n_frames(n)
 m = build_models("bf16")
 inp = {k: v.cuda() for k, v in make_inputs(clips, n, T, seed=1000).items()}
-for _ in range(2):
+for it in range(2):
+    if it == 1:   # with `ncu --profile-from-start off` only the second step is seen (launch indices then count from its first kernel)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
     v = m.predict_from_embeddings(inp["audio"], inp["emo"])
     fv = m.convert_coeff2verts(inp["coeff"], inp["pose"], inp["shape"])
 torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print("ok", tuple(v.shape), tuple(fv.shape))

@@ -100,7 +100,7 @@ def test_flat_layout_and_flatten():
         assert torch.equal(named[n], before[n])
         assert named[n].data_ptr() == flat.data_ptr() + 4 * lay.offsets[n]
     assert not any(n.startswith("audio_encoder.feature_extractor.") for n in lay.names)        # frozen (faceformer_vert.py:154)
-    assert "audio_encoder.masked_spec_embed" in lay.unused
+    assert lay.names[-1] == "audio_encoder.masked_spec_embed"                                   # gradient under SpecAugment only
     # fused q|k|v views are exactly cat(q, k, v)
     p = "audio_encoder.encoder.layers.1.attention."
     fused = lay.span(flat, p + "q_proj.weight", 3 * 768, 768)

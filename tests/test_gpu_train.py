@@ -187,3 +187,127 @@ def test_graphed_step_matches_eager():
         res.append((losses, m._flat_params.clone()))
     np.testing.assert_allclose(res[0][0], res[1][0], rtol=2e-3)
     assert (res[0][1] - res[1][1]).abs().max().item() <= 2.5e-4      # 3 Adam steps of lr 1e-4: sign noise of ~zero gradients only
+
+
+# ------------------------------------------------------------------------------------------------ TRAIN mode (regularisers as inputs)
+def run_reg_case(precision, fd=64, B=2, n_samples=16000, T=24):
+    m = build_vert(precision, fd, 200 + fd)
+    coeff, pose, shape, mean, std = train_inputs(B, T, seed=90 + fd)
+    m.coeff_mean, m.coeff_std = mean.cuda(), std.cuda()
+    audio = synth.audio(B, n_samples, seed=4321).cuda()
+    reg = synth.train_regularisers(B, T, fd, seed=300)
+    with torch.no_grad():                                                        # faceformer_vert.py:405-412
+        gt = (m.convert_coeff2verts(coeff.cuda()[:, :, :53].reshape(-1, 53), pose.cuda().reshape(-1, 6),
+                                    torch.zeros(B * T, shape.shape[-1], device="cuda")) * m.vertice_scale).reshape(B, T, -1)
+    opt = train.FlatAdam(m, lr=1e-4)
+    before = {n: p.detach().clone() for n, p in m.named_parameters()}
+    opt.zero_grad()
+    loss = m.training_loss(audio, gt, reg=reg)
+    loss.backward()
+    grads = {n: p.grad.detach().clone() for n, p in m.named_parameters() if p.grad is not None}
+    opt.step()
+    torch.cuda.synchronize()
+    after = {n: p.detach().clone() for n, p in m.named_parameters()}
+    return float(loss.detach()), grads, before, after, reg
+
+
+def test_train_mode_step_fp32_vs_reference_golden(golden):
+    """Dropout (wav2vec2 hidden / attention / activation, PPE, the five sites of nn.TransformerDecoderLayer), SpecAugment and LayerDrop
+    ACTIVE, every draw an input: tests/golden/train_reg.npz is the reference's own forward_switch_frame in .train() mode with the same
+    draws injected (oracle/make_golden.golden_train_reg). Loss rel 1e-4, every gradient max|err| <= 5e-4 max|ref|, the dropped layers'
+    gradients exactly zero, masked_spec_embed's gradient present, Adam update within 3e-7."""
+    g = golden("train_reg")
+    loss, grads, before, after, reg = run_reg_case("fp32")
+    np.testing.assert_allclose(loss, g["loss"][0], rtol=1e-4)
+    worst = ("", 0.0)
+    for nme in (str(x) for x in g["names"]):
+        ref = g[f"g/{nme}"]
+        scale = max(np.abs(ref).max(), 1e-12)
+        if nme not in grads:
+            assert np.abs(ref).max() == 0.0, nme
+            continue
+        got = sub(grads[nme])
+        if exactly_zero(ref, got):
+            continue
+        err = np.abs(got - ref).max() / scale
+        if err > worst[1]:
+            worst = (nme, err)
+        assert err <= 5e-4, (nme, err, scale)
+        dp = sub(after[nme] - before[nme])
+        ok = np.abs(ref) > 1e-4 * scale + 1e-7
+        np.testing.assert_allclose(dp[ok], g[f"dp/{nme}"][ok], atol=3e-7, rtol=0, err_msg=nme)
+    dropped = [l for l, k in enumerate(reg["layer_keep"]) if not k]
+    assert dropped
+    for l in dropped:
+        for nme, t in grads.items():
+            if nme.startswith(f"audio_encoder.encoder.layers.{l}."):
+                assert not torch.any(t), nme
+    assert grads["audio_encoder.masked_spec_embed"].abs().max().item() > 0
+    print(f"fp32 TRAIN-mode step: loss {loss:.6e}, worst gradient max-err / max|ref| = {worst[1]:.2e} ({worst[0]})")
+
+
+def test_train_mode_step_bf16_vs_reference_golden(golden):
+    g = golden("train_reg")
+    loss, grads, _, _, _ = run_reg_case("bf16")
+    np.testing.assert_allclose(loss, g["loss"][0], rtol=1e-2)
+    worst = ("", 0.0)
+    for nme in (str(x) for x in g["names"]):
+        if nme not in grads:
+            continue
+        ref = g[f"g/{nme}"]
+        got = sub(grads[nme])
+        if exactly_zero(ref, got):
+            continue
+        rel = np.linalg.norm(got - ref) / max(np.linalg.norm(ref), 1e-20)
+        if rel > worst[1]:
+            worst = (nme, rel)
+        assert rel <= 5e-2, (nme, rel)
+    print(f"bf16 TRAIN-mode step: loss {loss:.6e}, worst gradient rel-L2 {worst[1]:.2e} ({worst[0]})")
+
+
+def test_graphed_train_mode_step_takes_new_draws_without_recapture():
+    """GraphedTrainStep with regularisers: the draws live in static buffers, so two different draws with the same LayerDrop pattern
+    replay ONE graph and each equals the eager step on the same draw; a new LayerDrop pattern captures a second graph."""
+    fd, B, n, T = 64, 2, 16000, 24
+    template = synth.flame_buffers()["v_template"].reshape(1, 1, 15069)
+    gt = (template + 1e-3 * torch.from_numpy(np.random.default_rng(6).normal(size=(B, T, 15069)).astype(np.float32))).cuda()
+    audio = synth.audio(B, n, seed=98).cuda()
+    m = build_vert("fp32", fd, 264)
+    train.flatten_parameters(m)
+    gstep = train.GraphedTrainStep(m, audio.shape, gt.shape)
+    regs = [synth.train_regularisers(B, T, fd, seed=s) for s in (300, 301)] + [synth.train_regularisers(B, T, fd, seed=302, drop_layers=(1,))]
+    for i, reg in enumerate(regs):
+        lg = float(gstep(audio, gt, reg=reg))
+        gg = m._flat_grad.clone()
+        loss = m.training_loss(audio, gt, reg=reg)
+        loss.backward()
+        assert abs(lg - float(loss)) <= 1e-5 * abs(float(loss)), (i, lg, float(loss))
+        scale = m._flat_grad.abs().max().item()
+        assert (gg - m._flat_grad).abs().max().item() <= 1e-5 * scale, i
+        assert len(gstep.graphs) == (1 if i < 2 else 2)
+
+
+def test_drawn_regularisers_follow_the_config_and_the_step_runs():
+    """train.draw_regularisers on the device: keep rates ~ 1 - p, masks pre-scaled, SpecAugment spans of mask_time_length, and
+    `model.regularisers = "draw"` makes .train() mode stochastic (two calls differ) while .eval() stays deterministic."""
+    fd, B, n, T = 64, 2, 64000, 100
+    m = build_vert("bf16", fd, 264)
+    cfg = m.audio_encoder.config
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    reg = train.draw_regularisers(B, T, fd, cfg, torch.device("cuda"), generator=gen)
+    assert set(reg["masks"]) == set(train.regulariser_shapes(B, T, fd, cfg))
+    mk = reg["masks"]["l0.act"]
+    assert abs((mk > 0).float().mean().item() - (1 - cfg.activation_dropout)) < 0.01
+    assert abs(mk.max().item() - 1 / (1 - cfg.activation_dropout)) < 1e-6
+    assert reg["spec_mask"].shape == (B, T) and reg["spec_mask"].sum(1).min().item() >= cfg.mask_time_length
+    assert len(reg["layer_keep"]) == cfg.num_hidden_layers
+    template = synth.flame_buffers()["v_template"].reshape(1, 1, 15069)
+    gt = (template + 1e-3 * torch.from_numpy(np.random.default_rng(6).normal(size=(B, T, 15069)).astype(np.float32))).cuda()
+    audio = synth.audio(B, n, seed=98).cuda()
+    m.regularisers = "draw"
+    m.train()
+    l1, l2 = float(m.training_loss(audio, gt)), float(m.training_loss(audio, gt))
+    assert np.isfinite(l1) and np.isfinite(l2) and l1 != l2
+    m.eval()
+    e1, e2 = float(m.training_loss(audio, gt)), float(m.training_loss(audio, gt))
+    assert e1 == e2
