@@ -428,8 +428,12 @@ class Faceformer(nn.Module):
         if getattr(self, "_train_step", None) is None:
             self._train_step = train.TrainStep(self)
         if reg is None and self.training and self.regularisers == "draw":
-            reg = train.draw_regularisers(gt_verts.shape[0], gt_verts.shape[1], self.args.feature_dim, self.audio_encoder.config,
-                                          audio.device)
+            key = (gt_verts.shape[0], gt_verts.shape[1], str(audio.device))
+            if getattr(self, "_draws_key", None) != key:
+                self._draws = train.DeviceDraws(key[0], key[1], self.args.feature_dim, self.audio_encoder.config, audio.device,
+                                                seed=getattr(self, "regulariser_seed", 0))
+                self._draws_key = key
+            reg = self._draws.draw()
         return train.training_loss(self._train_step, audio, gt_verts, reg)
 
 

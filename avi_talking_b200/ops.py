@@ -668,6 +668,30 @@ def spec_augment_bwd_(dx, row_mask, g_embed):
     return dx
 
 
+def dropout_masks_(out, p, state, stream_id=0):
+    """Fill the flat fp32 buffer `out` with pre-scaled dropout masks (Philox4x32-10 keyed by the device-resident `state`)."""
+    _need_cuda(out, state)
+    assert out.dtype == torch.float32 and out.is_contiguous() and state.dtype == torch.int32 and state.numel() == 4
+    _chk(_lib.load().avi_dropout_masks(_ptr(out), C.c_int64(out.numel()), C.c_float(p), _ptr(state), C.c_uint32(stream_id), _stream()),
+         "avi_dropout_masks")
+    return out
+
+
+def layerdrop_spec_draw_(blend, keep_flags, rows, layerdrop, spec, B, T, span_len, span_rate, min_spans, state):
+    _need_cuda(keep_flags, state)
+    n_layers = keep_flags.numel()
+    assert blend is None or (blend.is_contiguous() and blend.numel() == 2 * n_layers * rows)
+    assert spec is None or (spec.dtype == torch.uint8 and spec.numel() == B * T)
+    _chk(_lib.load().avi_layerdrop_spec_draw(_ptr(blend), _ptr(keep_flags), C.c_int32(n_layers), C.c_int64(rows), C.c_float(layerdrop),
+                                             _ptr(spec), C.c_int32(B), C.c_int32(T), C.c_int32(span_len), C.c_float(span_rate),
+                                             C.c_int32(min_spans), _ptr(state), _stream()), "avi_layerdrop_spec_draw")
+
+
+def draw_bump_step_(state):
+    _need_cuda(state)
+    _chk(_lib.load().avi_draw_bump_step(_ptr(state), _stream()), "avi_draw_bump_step")
+
+
 def posconv_dw(x, dpc, B, T, groups, k):
     _need_cuda(x, dpc)
     Cc = x.shape[-1]

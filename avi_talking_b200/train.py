@@ -267,13 +267,10 @@ def draw_regularisers(B, T, fd, cfg, device, generator=None, p_dec=0.1, spec_aug
         return (torch.rand(shape, device=device, generator=generator) >= p).float().div_(1.0 - p)
 
     shp = regulariser_shapes(B, T, fd, cfg)
-    p_site = {"featproj": getattr(cfg, "feat_proj_dropout", 0.0), "enc_in": cfg.hidden_dropout}
-    for l in range(cfg.num_hidden_layers):
-        p_site.update({f"l{l}.attn": cfg.attention_dropout, f"l{l}.h1": cfg.hidden_dropout, f"l{l}.act": cfg.activation_dropout,
-                       f"l{l}.h3": cfg.hidden_dropout})
+    p_site = site_dropout_p(cfg, p_dec)
     masks = {}
     for name, s_ in shp.items():
-        mk = mask(s_, p_site.get(name, p_dec))
+        mk = mask(s_, p_site[name])
         if mk is not None:
             masks[name] = mk
     keep = (torch.rand(cfg.num_hidden_layers, generator=generator, device=device) >= cfg.layerdrop).tolist()
@@ -286,6 +283,78 @@ def draw_regularisers(B, T, fd, cfg, device, generator=None, p_dec=0.1, spec_aug
             idx = (starts[:, :, None] + torch.arange(L, device=device)[None, None, :]).reshape(B, -1)
             spec = torch.zeros(B, T, dtype=torch.bool, device=device).scatter_(1, idx, True)
     return {"p": p_dec, "spec_mask": spec, "layer_keep": keep, "masks": masks}
+
+
+def site_dropout_p(cfg, p_dec=0.1):
+    """site -> dropout probability in the reference's configuration (HF Wav2Vec2Config; 0.1 for the PPE and the decoder layer)."""
+    p_site = {"featproj": getattr(cfg, "feat_proj_dropout", 0.0), "enc_in": cfg.hidden_dropout}
+    for l in range(cfg.num_hidden_layers):
+        p_site.update({f"l{l}.attn": cfg.attention_dropout, f"l{l}.h1": cfg.hidden_dropout, f"l{l}.act": cfg.activation_dropout,
+                       f"l{l}.h3": cfg.hidden_dropout})
+    for n in DEC_SITES:
+        p_site[n] = p_dec
+    return p_site
+
+
+class DeviceDraws:
+    """Every draw of a TRAIN-mode step made by the library on the device (csrc/train_draw.cu): all dropout sites are views of ONE flat
+    fp32 buffer filled by one launch per distinct probability (normally one), LayerDrop becomes the 0 / 1 blend rows of the graph-stable
+    form, SpecAugment spans are drawn in the same launch, and the step counter lives in device memory - so `draw()` can be captured
+    in the step's CUDA graph and every replay sees fresh draws with no host work. Counter-based Philox4x32-10: the draws are a pure
+    function of (seed, step, element), reproduced bit for bit by oracle/philox_oracle.py (tests/test_gpu_train.py)."""
+
+    def __init__(self, B, T, fd, cfg, device, seed=0, p_dec=0.1, spec_augment=True):
+        self.B, self.T, self.cfg, self.device, self.seed = B, T, cfg, torch.device(device), int(seed)
+        shapes = regulariser_shapes(B, T, fd, cfg)
+        p_site = site_dropout_p(cfg, p_dec)
+        by_p = {}
+        for name, shp in shapes.items():
+            if p_site[name] > 0:
+                by_p.setdefault(float(p_site[name]), []).append((name, shp))
+        self.groups, self.layout, off = [], {}, 0          # groups: (p, first element, elements); layout: site -> (group, offset in group)
+        for gi, (p, sites) in enumerate(sorted(by_p.items())):
+            start = off
+            for name, shp in sites:
+                n = 1
+                for d_ in shp:
+                    n *= d_
+                self.layout[name] = (gi, off - start, shp)
+                off += (n + 3) // 4 * 4
+            self.groups.append((p, start, off - start))
+        self.flat = torch.empty(max(off, 4), dtype=torch.float32, device=self.device)
+        self.masks = {}
+        for name, (gi, o, shp) in self.layout.items():
+            n = 1
+            for d_ in shp:
+                n *= d_
+            a = self.groups[gi][1] + o
+            self.masks[name] = self.flat[a:a + n].view(shp)
+        lo, hi = self.seed & 0xFFFFFFFF, (self.seed >> 32) & 0xFFFFFFFF
+        as_i32 = lambda v: v - (1 << 32) if v >= (1 << 31) else v  # noqa: E731
+        self.state = torch.tensor([as_i32(lo), as_i32(hi), 0, 0], dtype=torch.int32, device=self.device)
+        L, self.rows = cfg.num_hidden_layers, B * T * cfg.hidden_size
+        self.layerdrop = float(cfg.layerdrop)
+        self.blend = torch.ones((2, L, self.rows), dtype=torch.float32, device=self.device)
+        self.keep_flags = torch.ones(L, dtype=torch.float32, device=self.device)
+        self.spec = None
+        if spec_augment and getattr(cfg, "apply_spec_augment", True) and cfg.mask_time_prob > 0:
+            self.spec = torch.zeros(B * T, dtype=torch.uint8, device=self.device)
+        self.span_len, self.span_rate, self.min_spans = int(cfg.mask_time_length), float(cfg.mask_time_prob * T / cfg.mask_time_length), 2
+        self.reg = {"p": p_dec, "masks": self.masks, "spec_mask": self.spec, "layer_keep": [True] * L, "layer_blend": self.blend,
+                    "_on_device": str(self.device)}
+        if "dec.ca" in self.masks:
+            self.reg["ca_diag"] = torch.ones((B, T, self.masks["dec.ca"].shape[1]), dtype=torch.float32, device=self.device)
+
+    def draw(self):
+        """Launch the draws of the next step on the current stream (capturable) -> the `reg` dict TrainStep.forward takes."""
+        for gi, (p, start, n) in enumerate(self.groups):
+            ops.dropout_masks_(self.flat[start:start + n], p, self.state, stream_id=gi)
+        ops.layerdrop_spec_draw_(self.blend, self.keep_flags, self.rows, self.layerdrop, self.spec, self.B, self.T, self.span_len,
+                                 self.span_rate, self.min_spans, self.state)
+        ops.draw_bump_step_(self.state)
+        if "ca_diag" in self.reg:
+            self.reg["ca_diag"].copy_(torch.diagonal(self.masks["dec.ca"], dim1=2, dim2=3).permute(0, 2, 1))
+        return self.reg
 
 
 def regularisers_to_device(reg, device):
@@ -301,6 +370,8 @@ def regularisers_to_device(reg, device):
     ca = out["masks"].get("dec.ca")
     if ca is not None:
         out["ca_diag"] = torch.diagonal(ca, dim1=2, dim2=3).permute(0, 2, 1).contiguous()          # [B, T, heads]
+    if reg.get("layer_blend") is not None:
+        out["layer_blend"] = reg["layer_blend"].to(device)
     return out
 
 
@@ -437,6 +508,9 @@ class TrainStep:
         S["reg"] = reg = regularisers_to_device(reg, audio.device)
         mk = reg["masks"] if reg is not None else {}
         keep = reg["layer_keep"] if reg is not None else [True] * len(w2v.encoder.layers)
+        # graph-stable LayerDrop (GraphedTrainStep): every layer runs and its output is blended with its input by 0 / 1 row masks
+        # ([n_layers, M * C] keep and 1 - keep), so the launch sequence does not depend on the draw
+        blend = reg.get("layer_blend") if reg is not None else None
 
         def drop(name, t, residual=None):
             """nn.Dropout at site `name` (+ the residual the reference adds right after); the plain add / identity without a draw."""
@@ -471,9 +545,10 @@ class TrainStep:
         P, lay = m._flat_params, self.layout
         S["layers"] = []
         for l, lyr in enumerate(w2v.encoder.layers):
-            if not keep[l]:                                    # LayerDrop: the layer is the identity and gets no gradient
+            if blend is None and not keep[l]:                  # LayerDrop: the layer is the identity and gets no gradient
                 S["layers"].append(None)
                 continue
+            x_in = x
             pre = f"audio_encoder.encoder.layers.{l}.attention."
             Wqkv = lay.span(P, pre + "q_proj.weight", 3 * cfg.hidden_size, cfg.hidden_size)
             bqkv = lay.span(P, pre + "q_proj.bias", 1, 3 * cfg.hidden_size).view(-1)
@@ -496,6 +571,8 @@ class TrainStep:
                 y2 = lin.fwd(lin.a(f), ff.output_dense.weight, ff.output_dense.bias, residual=h1)
             L["y2"] = y2
             x = ops.layernorm(y2, lyr.final_layer_norm.weight, lyr.final_layer_norm.bias, eps=eps)[0]
+            if blend is not None:                              # x <- keep * layer(x_in) + (1 - keep) * x_in
+                x = ops.mask_mul(x_in, blend[1][l], residual=ops.mask_mul(x, blend[0][l]))
             S["layers"].append(L)
         S["h12"] = x
         # -- heads and the teacher-forced decoder layer (faceformer_vert.py:369,437-454)
@@ -571,6 +648,7 @@ class TrainStep:
         g = lambda n: lay.view(G, n)  # noqa: E731
         reg = S["reg"]
         mk = reg["masks"] if reg is not None else {}
+        blend = reg.get("layer_blend") if reg is not None else None
 
         def dropb(name, dy):
             """Gradient through the dropout of site `name`: dy * mask (the same launch as the forward); identity without a draw."""
@@ -636,6 +714,9 @@ class TrainStep:
                 continue
             p = f"audio_encoder.encoder.layers.{l}."
             ff, a = lyr.feed_forward, lyr.attention
+            dh_up = dh
+            if blend is not None:                               # a dropped layer sees a zero upstream gradient: all its gradients are 0
+                dh = ops.mask_mul(dh_up, blend[0][l])
             dy2 = ops.layernorm_bwd(L["y2"], lyr.final_layer_norm.weight, dh, g(p + "final_layer_norm.weight"),
                                     g(p + "final_layer_norm.bias"), eps=eps)
             df = lin.bwd(dropb(f"l{l}.h3", dy2), L["f"], ff.output_dense.weight, g(p + "feed_forward.output_dense.weight"),
@@ -650,6 +731,8 @@ class TrainStep:
             gW = lay.span(G, p + "attention.q_proj.weight", 3 * C, C)
             gb = lay.span(G, p + "attention.q_proj.bias", 1, 3 * C).view(-1)
             dh = lin.bwd(dqkv, L["x"], L["Wqkv"], gW, gb, Mp, residual=dy)
+            if blend is not None:                               # + the identity path of a dropped layer
+                dh = ops.mask_mul(dh_up, blend[1][l], residual=dh)
             if bk is not None:
                 seg = lay.segments[nl - l]
                 bk.ready(G, lay.offsets[lay.names[seg]] if seg < len(lay.names) else lay.total)
@@ -719,8 +802,9 @@ class GraphedTrainStep:
     Round 1 ran the multi-GPU step eagerly and two GPUs were slower per step than one graph-replayed GPU.
 
     Train mode (`reg`, see draw_regularisers): the dropout / SpecAugment draws are copied into static buffers the graph reads, so a
-    new draw every step replays the same graph; LayerDrop changes which kernels run, so there is one graph per keep pattern
-    (the `max_graphs` most recently used are kept; ranks may draw different patterns: a skipped layer still reports its bucket)."""
+    new draw every step replays the SAME graph. LayerDrop would change which kernels run; inside the graph every layer runs and its
+    output is blended with its input by 0 / 1 masks (identical loss, exactly zero gradients for a dropped layer, no re-capture; the
+    eager TrainStep skips dropped layers instead). One graph per set of active sites (`max_graphs` most recently used are kept)."""
 
     def __init__(self, model, audio_shape, gt_shape, warmup=2, buckets: GradBuckets | None = None, max_graphs=8):
         self.model = model
@@ -737,7 +821,9 @@ class GraphedTrainStep:
     def _reg_key(reg):
         if reg is None:
             return None
-        return (tuple(bool(k) for k in reg["layer_keep"]), reg.get("spec_mask") is not None, tuple(sorted(reg["masks"])))
+        if isinstance(reg, DeviceDraws):
+            return ("device draws", id(reg))
+        return (reg.get("spec_mask") is not None, tuple(sorted(reg["masks"])))
 
     def _static_reg(self, reg):
         """Device-resident copy of the draws with fixed addresses (what the captured kernels read)."""
@@ -748,7 +834,18 @@ class GraphedTrainStep:
             st["spec_mask"] = st["spec_mask"].clone()
         if "ca_diag" in st:
             st["ca_diag"] = st["ca_diag"].clone()
+        cfg = self.model.audio_encoder.config
+        rows = self.gt.shape[0] * self.gt.shape[1] * cfg.hidden_size
+        st["layer_blend"] = torch.ones((2, cfg.num_hidden_layers, rows), dtype=torch.float32, device=dev)
+        self._load_keep(st, reg["layer_keep"])
         return st
+
+    @staticmethod
+    def _load_keep(static, keep):
+        k = torch.tensor([1.0 if x else 0.0 for x in keep], dtype=torch.float32).to(static["layer_blend"].device, non_blocking=True)
+        static["layer_blend"][0].copy_(k[:, None].expand_as(static["layer_blend"][0]))
+        static["layer_blend"][1].copy_((1.0 - k)[:, None].expand_as(static["layer_blend"][1]))
+        static["layer_keep"] = [bool(x) for x in keep]
 
     @staticmethod
     def _load_reg(static, reg):
@@ -758,23 +855,25 @@ class GraphedTrainStep:
             static["spec_mask"].copy_(reg["spec_mask"].reshape(-1), non_blocking=True)
         if "ca_diag" in static:
             static["ca_diag"].copy_(torch.diagonal(static["masks"]["dec.ca"], dim1=2, dim2=3).permute(0, 2, 1))
+        GraphedTrainStep._load_keep(static, reg["layer_keep"])
 
     def _capture(self, reg):
         m = self.model
         if m.precision == "bf16":
             bf16_shadow(m)
-        static = self._static_reg(reg) if reg is not None else None
+        on_device = isinstance(reg, DeviceDraws)               # the draw launches are part of the graph: fresh draws every replay
+        static = None if reg is None or on_device else self._static_reg(reg)
         side = torch.cuda.Stream(device=self.audio.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(self.warmup):                       # one-time attribute calls, allocator warm-up
-                self.step.forward(self.audio, self.gt, reg=static)
+                self.step.forward(self.audio, self.gt, reg=reg.draw() if on_device else static)
                 self.step.backward()
         torch.cuda.current_stream().wait_stream(side)
         graph = torch.cuda.CUDAGraph()
         # thread_local: the NCCL watchdog thread of a process group may query events while this thread captures
         with torch.cuda.graph(graph, capture_error_mode="thread_local"):
-            loss = self.step.forward(self.audio, self.gt, reg=static)
+            loss = self.step.forward(self.audio, self.gt, reg=reg.draw() if on_device else static)
             self.step.backward()
         return {"graph": graph, "loss": loss, "grad": m._flat_grad, "reg": static}
 
@@ -789,7 +888,7 @@ class GraphedTrainStep:
                 self.graphs.pop(next(iter(self.graphs)))
             ent = self._capture(reg)
         self.graphs[key] = ent                                 # (re-)inserted last = most recently used
-        if reg is not None:
+        if ent["reg"] is not None:
             self._load_reg(ent["reg"], reg)
         if m.precision == "bf16":
             bf16_shadow(m)                                     # refreshed in place by FlatAdam; re-cast here only if someone else wrote

@@ -699,11 +699,12 @@ def run_train(args):
     host_audio = synth.audio(B, N, seed=500 + rank * B).pin_memory()
     gt, audio = host_gt.to(dev), host_audio.to(dev)
     cfg_w2v = w2v.config
-    gen = torch.Generator(device=dev).manual_seed(11 + rank)
+    # the reference trains in .train() mode: every step draws its dropout masks, SpecAugment spans and LayerDrop decisions. Here the
+    # draws are three launches of the library (Philox, csrc/train_draw.cu) captured inside the step's graph
+    device_draws = train.DeviceDraws(B, T, fd, cfg_w2v, dev, seed=11 + rank) if args.regularisers == "draw" else None
 
     def draws():
-        # the reference trains in .train() mode: every step draws its dropout masks, SpecAugment spans and LayerDrop decisions
-        return train.draw_regularisers(B, T, fd, cfg_w2v, dev, generator=gen) if args.regularisers == "draw" else None
+        return device_draws.draw() if device_draws is not None else None
 
     if args.no_graph:
         step = train.TrainStep(m, buckets=buckets)
@@ -719,7 +720,7 @@ def run_train(args):
         gstep = train.GraphedTrainStep(m, audio.shape, gt.shape, buckets=buckets, max_graphs=16)
 
         def one_step(a, g):
-            loss = gstep(a, g, reg=draws())
+            loss = gstep(a, g, reg=device_draws)               # the draw launches live inside the captured graph
             opt.step()
             return loss
 

@@ -386,6 +386,20 @@ int avi_mask_mul_add(const float* x, const float* mask, const float* residual, f
  * (in place); backward: g_embed = sum of the masked rows of dx, which are then zeroed (fixed summation order). */
 int avi_spec_augment_fwd(float* x, const uint8_t* row_mask, const float* embed, int64_t rows, int32_t C, void* stream);
 int avi_spec_augment_bwd(float* dx, const uint8_t* row_mask, float* g_embed, int64_t rows, int32_t C, void* stream);
+/* The draws themselves, on the device (csrc/train_draw.cu), so that a TRAIN-mode step replays from one CUDA graph with fresh draws:
+ * counter-based Philox4x32-10 keyed by state = uint32[4] {seed_lo, seed_hi, step, 0} in device memory.
+ * avi_dropout_masks: element i of out[n] (n % 4 == 0) = word i % 4 of philox(ctr = (i/4 lo, i/4 hi, step, stream_id), key = seed);
+ *   u = (word >> 8) * 2^-24; out = u >= p ? 1/(1-p) : 0 - every nn.Dropout site of the step in one flat buffer, one launch
+ *   (replaces torch.nn.functional.dropout at each site of HF Wav2Vec2EncoderLayer / PeriodicPositionalEncoding / nn.TransformerDecoderLayer).
+ * avi_layerdrop_spec_draw: LayerDrop (Wav2Vec2Encoder.forward: skip layer l when u_l < layerdrop; u_l = word 0 of
+ *   philox((l, 0, step, 0x4C440000))) written as keep_flags[l] in {0, 1} and, when blend != NULL, blend[0][l][0..rows) = keep,
+ *   blend[1][l][0..rows) = 1 - keep; SpecAugment along time (models/lib/wav2vec.py:16-63,120-131, min_masks = 2): per clip
+ *   n = max(min_spans, floor(span_rate + u)) spans of span_len rows starting at (word * (T - span_len + 1)) >> 32, spec[B*T] bytes.
+ * avi_draw_bump_step: state[2] += 1 (stream-ordered after the draws). */
+int avi_dropout_masks(float* out, int64_t n, float p, const uint32_t* state, uint32_t stream_id, void* stream);
+int avi_layerdrop_spec_draw(float* blend, float* keep_flags, int32_t n_layers, int64_t rows, float layerdrop, uint8_t* spec, int32_t B,
+                            int32_t T, int32_t span_len, float span_rate, int32_t min_spans, const uint32_t* state, void* stream);
+int avi_draw_bump_step(uint32_t* state, void* stream);
 /* positional conv: dW [C, C/groups, k] from x [B,T,C] and d(pre-activation) [B,T,C]; weight-norm chain rule (dim = 2) */
 int avi_posconv_dw(const float* x, const float* dpc, float* dw, int32_t B, int32_t T, int32_t C, int32_t groups, int32_t k, void* stream);
 /* transposed unfold of the positional conv input for a block of CW channels starting at c0:

@@ -266,8 +266,9 @@ def test_train_mode_step_bf16_vs_reference_golden(golden):
 
 
 def test_graphed_train_mode_step_takes_new_draws_without_recapture():
-    """GraphedTrainStep with regularisers: the draws live in static buffers, so two different draws with the same LayerDrop pattern
-    replay ONE graph and each equals the eager step on the same draw; a new LayerDrop pattern captures a second graph."""
+    """GraphedTrainStep with regularisers given as tensors: the draws live in static buffers and LayerDrop is a 0 / 1 blend inside the
+    graph; different draws over the same set of sites replay ONE graph, and each replay equals the eager step (which skips dropped
+    layers) on the same draw."""
     fd, B, n, T = 64, 2, 16000, 24
     template = synth.flame_buffers()["v_template"].reshape(1, 1, 15069)
     gt = (template + 1e-3 * torch.from_numpy(np.random.default_rng(6).normal(size=(B, T, 15069)).astype(np.float32))).cuda()
@@ -284,7 +285,13 @@ def test_graphed_train_mode_step_takes_new_draws_without_recapture():
         assert abs(lg - float(loss)) <= 1e-5 * abs(float(loss)), (i, lg, float(loss))
         scale = m._flat_grad.abs().max().item()
         assert (gg - m._flat_grad).abs().max().item() <= 1e-5 * scale, i
+        # synth.train_regularisers has no draws for the layers it drops, so the third dict activates a different set of sites: one more
+        # graph (DeviceDraws, which draws every site every step, always replays one)
         assert len(gstep.graphs) == (1 if i < 2 else 2)
+        for l, k in enumerate(reg["layer_keep"]):
+            if not k:
+                p = f"audio_encoder.encoder.layers.{l}.feed_forward.output_dense.weight"
+                assert not torch.any(m._flat_layout.view(gg, p)), p
 
 
 def test_drawn_regularisers_follow_the_config_and_the_step_runs():
@@ -311,3 +318,57 @@ def test_drawn_regularisers_follow_the_config_and_the_step_runs():
     m.eval()
     e1, e2 = float(m.training_loss(audio, gt)), float(m.training_loss(audio, gt))
     assert e1 == e2
+
+
+def test_device_draws_bit_exact_vs_philox_oracle():
+    """csrc/train_draw.cu against oracle/philox_oracle.py: every dropout mask element, the LayerDrop decisions / blend rows and the
+    SpecAugment rows of two consecutive steps, bit for bit (integer generator + one fp32 compare)."""
+    from transformers import Wav2Vec2Config
+    from oracle import philox_oracle as po
+    cfg = Wav2Vec2Config()
+    cfg.layerdrop = 0.3                                                       # so that both outcomes occur among 12 layers
+    B, T, fd, seed = 2, 24, 64, (9 << 32) + 1234
+    d = train.DeviceDraws(B, T, fd, cfg, "cuda", seed=seed)
+    for step in range(2):
+        reg = d.draw()
+        torch.cuda.synchronize()
+        assert d.state.tolist()[2] == step + 1
+        for gi, (p, start, n) in enumerate(d.groups):
+            want = po.dropout_masks(n, p, seed, step, stream_id=gi)
+            assert np.array_equal(d.flat[start:start + n].cpu().numpy(), want), (step, gi)
+        keep = po.layer_keep(cfg.num_hidden_layers, cfg.layerdrop, seed, step)
+        assert np.array_equal(d.keep_flags.cpu().numpy() > 0, keep) and 0 < keep.sum() < len(keep)
+        bl = d.blend.cpu().numpy()
+        assert np.array_equal(bl[0], np.repeat(keep[:, None], d.rows, 1).astype(np.float32)) and np.array_equal(bl[1], 1 - bl[0])
+        want_spec = po.spec_mask(B, T, d.span_len, d.span_rate, d.min_spans, seed, step)
+        assert np.array_equal(d.spec.cpu().numpy().reshape(B, T), want_spec) and want_spec.any()
+        ca = reg["masks"]["dec.ca"]
+        assert torch.equal(reg["ca_diag"], torch.diagonal(ca, dim1=2, dim2=3).permute(0, 2, 1))
+
+
+def test_graph_with_device_draws_equals_eager_on_the_same_stream_of_draws():
+    """The draw launches are captured inside the step's graph: every replay sees the next step of the Philox stream, and the losses /
+    gradients equal the eager step fed by a second DeviceDraws with the same seed (which also checks the blend form of LayerDrop
+    against itself across launch modes)."""
+    fd, B, n, T = 64, 2, 16000, 24
+    template = synth.flame_buffers()["v_template"].reshape(1, 1, 15069)
+    gt = (template + 1e-3 * torch.from_numpy(np.random.default_rng(6).normal(size=(B, T, 15069)).astype(np.float32))).cuda()
+    audio = synth.audio(B, n, seed=98).cuda()
+    m = build_vert("fp32", fd, 264)
+    train.flatten_parameters(m)
+    cfg = m.audio_encoder.config
+    d_graph, d_eager = (train.DeviceDraws(B, T, fd, cfg, "cuda", seed=42) for _ in range(2))
+    m.training_loss(audio, gt, reg=train.DeviceDraws(B, T, fd, cfg, "cuda", seed=1).draw()).backward()   # one-time kernel attributes
+    gstep = train.GraphedTrainStep(m, audio.shape, gt.shape, warmup=0)        # no warm-up draws: replay i is step i of the stream
+    losses = []
+    for i in range(3):
+        lg = float(gstep(audio, gt, reg=d_graph))
+        gg = m._flat_grad.clone()
+        if i == 0:                    # the capture itself consumed step 0 without executing; the first replay runs it
+            assert d_graph.state.tolist()[2] == 1
+        loss = m.training_loss(audio, gt, reg=d_eager.draw())
+        loss.backward()
+        assert abs(lg - float(loss)) <= 1e-5 * abs(float(loss)), (i, lg, float(loss))
+        assert (gg - m._flat_grad).abs().max().item() <= 1e-5 * m._flat_grad.abs().max().item(), i
+        losses.append(lg)
+    assert len(set(losses)) == 3 and len(gstep.graphs) == 1

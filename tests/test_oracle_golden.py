@@ -250,3 +250,40 @@ def test_fan_encoder_oracle_matches_reference(golden):
     out = fo2.fan_encoder_forward(synth.fan_state(80), synth.fan_images(3, seed=81))
     for k, t in zip(("head", "eye", "emo", "mouth"), out):
         np.testing.assert_allclose(t.numpy(), g[k], atol=2e-4, rtol=1e-5)
+
+
+def test_philox_known_answers():
+    """oracle/philox_oracle.py (the checker of the device-side dropout / LayerDrop / SpecAugment draws) against the known-answer vectors
+    of Philox4x32-10 from the Random123 distribution (kat_vectors: zero, all-ones and the pi-digits counter / key)."""
+    from oracle import philox_oracle as po
+    kat = [((0, 0, 0, 0), (0, 0), "6627e8d5 e169c58d bc57ac4c 9b00dbd8"),
+           ((0xFFFFFFFF,) * 4, (0xFFFFFFFF,) * 2, "408f276d 41c83b0e a20bc7c6 6d5451fd"),
+           ((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), (0xA4093822, 0x299F31D0), "d16cfe09 94fdcceb 5001e420 24126ea1")]
+    for ctr, key, want in kat:
+        assert " ".join(f"{int(x):08x}" for x in po.philox4x32_10(ctr, key)) == want
+    m = po.dropout_masks(1 << 16, 0.1, seed=77, step=3)
+    assert set(np.unique(m)) == {np.float32(0.0), np.float32(1.0) / (np.float32(1.0) - np.float32(0.1))}
+    assert abs((m > 0).mean() - 0.9) < 5e-3
+    assert not np.array_equal(m, po.dropout_masks(1 << 16, 0.1, seed=77, step=4))            # a new step is a new draw
+    assert not np.array_equal(m, po.dropout_masks(1 << 16, 0.1, seed=77, step=3, stream_id=1))
+    sp = po.spec_mask(4, 120, 10, 0.6, 2, seed=77, step=0)
+    assert sp.shape == (4, 120) and sp.sum(1).min() >= 10 and sp.sum(1).max() <= 20
+
+
+def test_device_draws_layout():
+    """train.DeviceDraws (host logic only, CPU tensors): every dropout site of the step is a view of ONE flat buffer, 16-byte aligned,
+    disjoint, grouped by probability; the site list is the reference's (synth.train_regularisers minus LayerDrop's omissions)."""
+    from transformers import Wav2Vec2Config
+    from avi_talking_b200 import train
+    cfg = Wav2Vec2Config()
+    B, T, fd = 2, 24, 64
+    d = train.DeviceDraws(B, T, fd, cfg, "cpu", seed=(5 << 32) + 7)
+    ref = synth.train_regularisers(B, T, fd, drop_layers=())
+    assert set(d.masks) == set(ref["masks"]) and all(tuple(d.masks[k].shape) == tuple(ref["masks"][k].shape) for k in ref["masks"])
+    spans = sorted((v.data_ptr() - d.flat.data_ptr(), v.numel() * 4) for v in d.masks.values())
+    assert all(a % 16 == 0 for a, _ in spans)
+    assert all(spans[i][0] + spans[i][1] <= spans[i + 1][0] for i in range(len(spans) - 1))
+    assert spans[-1][0] + spans[-1][1] <= d.flat.numel() * 4
+    assert len(d.groups) == 1 and abs(d.groups[0][0] - 0.1) < 1e-9          # HF defaults: every site at p = 0.1
+    assert d.state.tolist()[:3] == [7, 5, 0]
+    assert d.blend.shape == (2, cfg.num_hidden_layers, B * T * cfg.hidden_size) and d.spec.numel() == B * T
