@@ -484,9 +484,54 @@ __global__ void split_bf16x3_kernel(const float* __restrict__ src, __nv_bfloat16
   d[2 * K + k] = hi;
 }
 
+// General form for fp32-accurate GEMMs on the bf16 tensor path: x = s0 + s1 + s2 (+ 2^-25 |x|) with s0 = bf16(x), s1 = bf16(x - s0),
+// s2 = bf16(x - s0 - s1); dst[r] = [s_{p0}(x) | s_{p1}(x) | ...] over `nterms` K-wide blocks, p_t = bits 2t..2t+1 of `pattern`.
+// An operand pair (A pattern, W pattern) whose blocks line up as the products s_i * t_j to keep gives
+//   3 terms  A = [0,1,0], W = [0,0,1]             : s0 t0 + s1 t0 + s0 t1                (dropped: 2^-16 relative)
+//   6 terms  A = [0,0,0,1,1,2], W = [0,1,2,0,1,0] : every product down to 2^-24 relative (fp32 accuracy)
+__global__ void __launch_bounds__(256) split_bf16_terms_kernel(const float4* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n4,
+                                                               int K4, int nterms, uint32_t pattern) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const int64_t r = i / K4;
+  const int k = (int)(i - r * K4) * 4;
+  const float4 x4 = src[i];
+  const float x[4] = {x4.x, x4.y, x4.z, x4.w};
+  __nv_bfloat16 s[3][4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    s[0][e] = __float2bfloat16_rn(x[e]);
+    const float r1 = x[e] - __bfloat162float(s[0][e]);
+    s[1][e] = __float2bfloat16_rn(r1);
+    s[2][e] = __float2bfloat16_rn(r1 - __bfloat162float(s[1][e]));
+  }
+  const int K = K4 * 4;
+  __nv_bfloat16* d = dst + r * (int64_t)nterms * K + k;
+  for (int t = 0; t < nterms; ++t) {
+    const int which = (pattern >> (2 * t)) & 3u;
+    const __nv_bfloat16* v = which == 0 ? s[0] : (which == 1 ? s[1] : s[2]);
+    __nv_bfloat162 lo2, hi2;
+    lo2.x = v[0]; lo2.y = v[1]; hi2.x = v[2]; hi2.y = v[3];
+    uint2 w;
+    w.x = *reinterpret_cast<uint32_t*>(&lo2);
+    w.y = *reinterpret_cast<uint32_t*>(&hi2);
+    *reinterpret_cast<uint2*>(d + (int64_t)t * K) = w;
+  }
+}
+
 }  // namespace avi
 
 using namespace avi;
+
+extern "C" int avi_split_bf16_terms(const float* src, void* dst, int64_t rows, int32_t K, int32_t nterms, uint32_t pattern, void* stream) {
+  AVI_REQUIRE(rows > 0 && K > 0 && K % 4 == 0 && nterms >= 1 && nterms <= 8, "avi_split_bf16_terms: K %% 4 == 0 and 1..8 terms (K=%d)", K);
+  AVI_REQUIRE((((uintptr_t)src % 16) | ((uintptr_t)dst % 8)) == 0, "avi_split_bf16_terms: unaligned buffers");
+  for (int t = 0; t < nterms; ++t) AVI_REQUIRE(((pattern >> (2 * t)) & 3u) < 3u, "avi_split_bf16_terms: pattern entries are 0, 1 or 2");
+  const int64_t n4 = rows * (K / 4);
+  split_bf16_terms_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const float4*)src, (__nv_bfloat16*)dst, n4, K / 4,
+                                                                                         nterms, pattern);
+  return check_launch("split_bf16_terms");
+}
 
 extern "C" int avi_pad_cast_bf16(const float* src, void* dst, int32_t B, int32_t T, int32_t C, int32_t front, int32_t rows_out,
                                  void* stream) {

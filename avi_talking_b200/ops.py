@@ -3,6 +3,7 @@ current stream only; every computation below runs in libavi_b200.so. No fallback
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -84,6 +85,52 @@ def split_bf16x3(x2d):
     return out
 
 
+# How fp32 operands are contracted: "simt" = the CUDA-core fp32 kernel (avi_gemm_f32, the <= 1e-5 mode); "x3" = each operand split into
+# bf16 hi / lo terms, A = [hi|lo|hi] against W = [hi|hi|lo] on the tcgen05 GEMM (avi_split_bf16_terms): 5e-6 of max|C| per GEMM,
+# 3e-5 relative over the whole wav2vec2 stack at 5.4x the speed of "simt" (profiles/r2/bench_fp32_*.json) - an opt-in middle mode.
+# A six-term split (every product down to 2^-24) was MEASURED NO BETTER (8.6e-6 per GEMM, 6e-5 over the stack): the floor is the
+# tensor core's own fp32 accumulation, which truncates (error grows linearly with the number of accumulated k-blocks), not the
+# dropped lo x lo products - so it is not offered.
+FP32_GEMM = os.environ.get("AVI_B200_FP32_GEMM", "simt").lower()
+_SPLIT_PATTERNS = {"x3": (3, (0, 1, 0), (0, 0, 1))}
+if FP32_GEMM not in ("simt",) + tuple(_SPLIT_PATTERNS):
+    raise ValueError("AVI_B200_FP32_GEMM must be simt or x3")
+
+
+def split_bf16_terms(x2d, pattern):
+    """[rows, K] fp32 -> [rows, len(pattern) * K] bf16 blocks of the bf16 terms named by `pattern` (0 = hi, 1 = mid, 2 = lo)."""
+    _need_cuda(x2d)
+    rows, K = x2d.shape
+    out = torch.empty((rows, len(pattern) * K), dtype=torch.bfloat16, device=x2d.device)
+    packed = 0
+    for t, w in enumerate(pattern):
+        packed |= int(w) << (2 * t)
+    with _timed("split_bf16_terms", 0.0):
+        _lib.check(_lib.load().avi_split_bf16_terms(_ptr(x2d), _ptr(out), C.c_int64(rows), C.c_int32(K), C.c_int32(len(pattern)),
+                                                    C.c_uint32(packed), _stream()), "avi_split_bf16_terms")
+    return out
+
+
+def _gemm_f32_split(A, W, bias, out, mode, *, rows, N, K, batch, act, residual, out2, conv_taps, conv_stride, a_ld, a_batch_stride,
+                    a_rows_alloc, c_ld, c_batch_stride, res_ld, res_batch_stride, algorithmic_flops, profile, conv_taps_x, conv_row_pitch):
+    """fp32 operands on the bf16 tensor path as split terms; returns False when the layout is not one the split supports (the caller
+    then takes the CUDA-core kernel)."""
+    nt, pa, pw = _SPLIT_PATTERNS[mode]
+    cin = K // conv_taps
+    if cin % 64 != 0 or (a_ld is not None and a_ld != cin) or a_batch_stride % cin != 0 or not A.is_contiguous() or not W.is_contiguous():
+        return False
+    if A.numel() % cin != 0 or W.numel() != N * K or out.dtype != torch.float32 or out2 is not None:
+        return False
+    A3 = split_bf16_terms(A.view(-1, cin), pa)                       # every row of the activation buffer, channel blocks per term
+    W3 = split_bf16_terms(W.view(-1, cin), pw).view(N, conv_taps * nt * cin)
+    flops = 2.0 * batch * rows * N * K if algorithmic_flops is None else float(algorithmic_flops)
+    gemm(A3, W3, bias, out, rows=rows, N=N, K=nt * K, batch=batch, act=act, residual=residual, conv_taps=conv_taps,
+         conv_stride=conv_stride, a_ld=nt * cin, a_batch_stride=nt * a_batch_stride, a_rows_alloc=a_rows_alloc, c_ld=c_ld,
+         c_batch_stride=c_batch_stride, res_ld=res_ld, res_batch_stride=res_batch_stride, algorithmic_flops=flops, profile=profile,
+         conv_taps_x=conv_taps_x, conv_row_pitch=conv_row_pitch)
+    return True
+
+
 def gemm(A, W, bias, out, *, rows, N, K, batch=1, act=ACT_NONE, residual=None, out2=None, conv_taps=1, conv_stride=1,
          a_ld=None, a_batch_stride=0, a_rows_alloc=None, c_ld=None, c_batch_stride=0, res_ld=None, res_batch_stride=0,
          algorithmic_flops=None, profile=None, tf32=False, conv_taps_x=0, conv_row_pitch=0):
@@ -91,6 +138,13 @@ def gemm(A, W, bias, out, *, rows, N, K, batch=1, act=ACT_NONE, residual=None, o
     _need_cuda(A, W, bias, out, residual, out2)
     if A.dtype != W.dtype:
         raise TypeError("A and W must share a dtype")
+    if A.dtype == torch.float32 and not tf32 and FP32_GEMM in _SPLIT_PATTERNS:
+        if _gemm_f32_split(A, W, bias, out, FP32_GEMM, rows=rows, N=N, K=K, batch=batch, act=act, residual=residual, out2=out2,
+                           conv_taps=conv_taps, conv_stride=conv_stride, a_ld=a_ld, a_batch_stride=a_batch_stride,
+                           a_rows_alloc=a_rows_alloc, c_ld=c_ld, c_batch_stride=c_batch_stride, res_ld=res_ld,
+                           res_batch_stride=res_batch_stride, algorithmic_flops=algorithmic_flops, profile=profile,
+                           conv_taps_x=conv_taps_x, conv_row_pitch=conv_row_pitch):
+            return out
     args = AviGemmArgs()
     args.A, args.W, args.bias, args.residual = A.data_ptr(), W.data_ptr(), (bias.data_ptr() if bias is not None else None), \
         (residual.data_ptr() if residual is not None else None)

@@ -97,6 +97,13 @@ int avi_pad_cast_bf16(const float* src, void* dst, int32_t B, int32_t T, int32_t
 /* split-bf16 GEMM operand: dst [rows, 3K] = [hi(x) | lo(x) | hi(x)] with lo = bf16(x - hi); against weights packed
  * [hi(W) | hi(W) | lo(W)] the bf16 tensor path reproduces the fp32 product to ~2^-16 relative (vertex head, bf16 mode). */
 int avi_split_bf16x3(const float* src, void* dst, int64_t rows, int32_t K, void* stream);
+/* fp32-ACCURATE contractions on the bf16 tensor path (the "fp32 <= 1e-5" mode of north_star without the CUDA-core GEMM): every fp32
+ * value is split into bf16 terms x = s0 + s1 + s2, s0 = bf16(x), s1 = bf16(x - s0), s2 = bf16(x - s0 - s1), and dst row r is the
+ * concatenation of `nterms` K-wide blocks, block t holding s_{p_t} with p_t = bits 2t..2t+1 of `pattern`. A = [s0|s1|s0] against
+ * W = [t0|t0|t1] keeps s0 t0 + s1 t0 + s0 t1 (2^-16 relative); A = [s0|s0|s0|s1|s1|s2] against W = [t0|t1|t2|t0|t1|t0] keeps every
+ * product down to 2^-24 (fp32 accuracy) at six bf16 MMAs per product. src [rows, K] fp32 contiguous (K % 4 == 0), dst [rows, nterms*K]
+ * bf16. Replaces the fp32 torch.matmul / F.linear / F.conv1d arithmetic of the reference in that mode (same call sites as avi_gemm_f32). */
+int avi_split_bf16_terms(const float* src, void* dst, int64_t rows, int32_t K, int32_t nterms, uint32_t pattern, void* stream);
 
 /* ------------------------------------------------------------------ wav2vec2 pieces ------------------------------------------------------------------ */
 /* Conv1d(1->512,k=10,s=5,no bias) + GroupNorm(512 groups) + GELU   (HF Wav2Vec2GroupNormConvLayer; models/lib/wav2vec.py:97).
