@@ -43,6 +43,10 @@ inline cudaError_t smem_optin(Kernel kernel, int bytes, SmemOptIn& state) {
   return e;
 }
 
+// Which persistent kernels take their tiles through cluster launch control instead of a static walk (avi_set_dynamic_tiles).
+enum : int { AVI_DYN_GEMM = 1, AVI_DYN_CONV0 = 2 };
+int dynamic_tiles_mask();
+
 void set_error(const char* fmt, ...);
 extern std::atomic<int64_t> g_launches;
 

@@ -33,7 +33,10 @@ constexpr uint32_t CZ_OFF_TRANS = (CZ_OFF_SS + 2 * 2 * CZ_C * 4 + 1023) / 1024 *
 constexpr uint32_t CZ_TRANS_TILE = 32 * 16 * 4;
 constexpr uint32_t CZ_TRANS_WARP = 2 * CZ_TRANS_TILE;
 constexpr uint32_t CZ_OFF_BAR = CZ_OFF_TRANS + CZ_EPI_WARPS * CZ_TRANS_WARP;
-constexpr uint32_t CZ_SMEM = CZ_OFF_BAR + 256;
+constexpr int CZ_CLC_STAGES = 4;                         // cluster-launch-control responses (dynamic tile scheduler, see gemm_tc2.cu)
+constexpr uint32_t CZ_OFF_CLC = CZ_OFF_BAR + 256;        // [CZ_CLC_STAGES] 16-byte responses
+constexpr uint32_t CZ_SMEM = CZ_OFF_CLC + CZ_CLC_STAGES * 16;
+constexpr int CZ_CLC_CONSUMERS = CZ_BUILD_WARPS + 1 + CZ_EPI_WARPS;   // one arrival per builder warp, the MMA thread, every epilogue warp
 static_assert(CZ_SMEM <= 232448, "shared memory budget");
 static_assert(CZ_OFF_X % 16 == 0 && CZ_OFF_SS % 16 == 0 && CZ_OFF_TRANS % 1024 == 0 && CZ_OFF_BAR % 8 == 0, "alignment");
 
@@ -124,6 +127,7 @@ struct Conv0Params {
   __nv_bfloat16* out;
   int64_t out_batch_stride;
   int n_samples, L0, tiles_per_clip, total_tiles;
+  int dynamic;   // 1: one CTA per tile in the grid, the resident CTAs take the pending ones through cluster launch control
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
@@ -144,7 +148,31 @@ __global__ void __launch_bounds__(CZ_THREADS, 1) conv0_tc_kernel(const __grid_co
   uint64_t* ss_full = bars + 13;        // [2] count = builder warps (scale/shift of the tile's clip staged)
   uint64_t* ss_empty = bars + 15;       // [2] count = epilogue warps
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 17);
+  uint64_t* clc_full = bars + 18;       // [CLC_STAGES]
+  uint64_t* clc_empty = bars + 22;      // [CLC_STAGES]
+  uint8_t* clc_resp = smem + CZ_OFF_CLC;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool dyn = p.dynamic != 0;
+  // next tile of this CTA (lane 0 of a warp asks, the warp shares the answer): the static walk or a tile taken from the launch queue
+  auto next_tile = [&](int t, int& cslot, uint32_t& cphase) -> int {
+    int nt = 0;
+    if (lane == 0) {
+      if (!dyn) {
+        nt = t + (int)gridDim.x;
+        if (nt >= p.total_tiles) nt = -1;
+      } else {
+        mbar_wait(smem_u32(&clc_full[cslot]), cphase);
+        nt = clc_decode(smem_u32(clc_resp + 16 * cslot));
+        fence_proxy_async_smem();
+        mbar_arrive(smem_u32(&clc_empty[cslot]));
+      }
+    }
+    if (++cslot == CZ_CLC_STAGES) {
+      cslot = 0;
+      cphase ^= 1;
+    }
+    return __shfl_sync(0xffffffffu, nt, 0);
+  };
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
@@ -159,6 +187,10 @@ __global__ void __launch_bounds__(CZ_THREADS, 1) conv0_tc_kernel(const __grid_co
     for (int q = 0; q < CZ_NQ; ++q) {
       mbar_init(smem_u32(&tmem_full[q]), 1);
       mbar_init(smem_u32(&tmem_empty[q]), CZ_EPI_WARPS / CZ_NQ);
+    }
+    for (int s = 0; s < CZ_CLC_STAGES; ++s) {
+      mbar_init(smem_u32(&clc_full[s]), 1);
+      mbar_init(smem_u32(&clc_empty[s]), CZ_CLC_CONSUMERS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -178,8 +210,19 @@ __global__ void __launch_bounds__(CZ_THREADS, 1) conv0_tc_kernel(const __grid_co
       for (int q = 0; q < CZ_NQ; ++q) tma_load_2d(smem_u32(smem + CZ_OFF_W + q * (CZ_BN * 128)), &map_w, smem_u32(w_full), 0, q * CZ_BN);
     }
     const int r = threadIdx.x;  // row of the tile, 0..127
-    int it = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+    int it = 0, cslot = 0, islot = 0;
+    uint32_t cphase = 0, iphase = 0;
+    auto clc_issue = [&]() {     // thread 0: ask for the tile after the one about to be built (never after a failed request)
+      mbar_wait(smem_u32(&clc_empty[islot]), iphase ^ 1);
+      mbar_expect_tx(smem_u32(&clc_full[islot]), 16);
+      clc_try_cancel(smem_u32(clc_resp + 16 * islot), smem_u32(&clc_full[islot]));
+      if (++islot == CZ_CLC_STAGES) {
+        islot = 0;
+        iphase ^= 1;
+      }
+    };
+    if (dyn && threadIdx.x == 0) clc_issue();
+    for (int t = blockIdx.x; t >= 0; ++it) {
       const int s = it & 1;
       const uint32_t ph = (it >> 1) & 1;
       const int b = t / p.tiles_per_clip, t0 = (t % p.tiles_per_clip) * CZ_BM;
@@ -216,15 +259,18 @@ __global__ void __launch_bounds__(CZ_THREADS, 1) conv0_tc_kernel(const __grid_co
         mbar_arrive(smem_u32(&a_full[s]));
         mbar_arrive(smem_u32(&ss_full[s]));
       }
+      t = next_tile(t, cslot, cphase);
+      if (dyn && threadIdx.x == 0 && t >= 0) clc_issue();
     }
   } else if (warp == CZ_BUILD_WARPS) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      // D = f32, A = B = bf16, K-major, N = 128, M = 128
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(CZ_BN >> 3) << 17) | ((uint32_t)(CZ_BM >> 4) << 24);
-      mbar_wait(smem_u32(w_full), 0);
-      int it = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+    // D = f32, A = B = bf16, K-major, N = 128, M = 128
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(CZ_BN >> 3) << 17) | ((uint32_t)(CZ_BM >> 4) << 24);
+    if (lane == 0) mbar_wait(smem_u32(w_full), 0);
+    int it = 0, cslot = 0;
+    uint32_t cphase = 0;
+    for (int t = blockIdx.x; t >= 0; t = next_tile(t, cslot, cphase), ++it) {   // lane 0 issues; the warp walks the tiles together
+      if (lane == 0) {
         const int s = it & 1;
         mbar_wait(smem_u32(&a_full[s]), (it >> 1) & 1);
         tc_fence_after();
@@ -240,6 +286,7 @@ __global__ void __launch_bounds__(CZ_THREADS, 1) conv0_tc_kernel(const __grid_co
         }
         umma_commit(smem_u32(&a_empty[s]));
       }
+      __syncwarp();
     }
   } else {
     // ===================== epilogue =====================
@@ -247,8 +294,9 @@ __global__ void __launch_bounds__(CZ_THREADS, 1) conv0_tc_kernel(const __grid_co
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
     const int q = ew >> 2;                        // channel group [128 q, +128)
     const uint32_t tile = smem_u32(smem + CZ_OFF_TRANS) + ew * CZ_TRANS_WARP;
-    int it = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+    int it = 0, cslot = 0;
+    uint32_t cphase = 0;
+    for (int t = blockIdx.x; t >= 0; t = next_tile(t, cslot, cphase), ++it) {
       const int s = it & 1;
       const int b = t / p.tiles_per_clip, t0 = (t % p.tiles_per_clip) * CZ_BM;
       const int rows_valid = p.L0 - (t0 + quarter * 32);
@@ -363,7 +411,8 @@ extern "C" int avi_w2v_conv0_gn_gelu_tc(const float* audio, const float* w, cons
   const cudaError_t attr_err = smem_optin(conv0_tc_kernel, (int)CZ_SMEM, optin);
   AVI_REQUIRE(attr_err == cudaSuccess, "avi_w2v_conv0_gn_gelu_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
   const int sms = device_sms();
-  const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+  p.dynamic = (dynamic_tiles_mask() & AVI_DYN_CONV0) != 0 && p.total_tiles > 1 ? 1 : 0;
+  const int grid = p.dynamic ? p.total_tiles : (p.total_tiles < sms ? p.total_tiles : sms);
   conv0_tc_kernel<<<grid, CZ_THREADS, CZ_SMEM, st>>>(map_w, map_out, p);
   return check_launch("conv0_tc");
 }

@@ -48,9 +48,12 @@ constexpr uint32_t P2_OFF_B = P2_STAGES * P2_A_BYTES;
 constexpr uint32_t P2_OFF_TRANS = P2_STAGES * P2_STAGE_BYTES;
 constexpr uint32_t P2_OFF_BIAS = P2_OFF_TRANS + P2_TRANS_BYTES;
 constexpr uint32_t P2_OFF_BAR = P2_OFF_BIAS + P2_BIAS_BYTES;
-constexpr uint32_t P2_SMEM_BYTES = P2_OFF_BAR + 256 /*barriers*/;
+constexpr int P2_CLC_STAGES = 4;                                 // cluster-launch-control responses in flight (dynamic tile scheduler)
+constexpr uint32_t P2_OFF_CLC = P2_OFF_BAR + 256 /*barriers*/;   // [P2_CLC_STAGES] 16-byte responses
+constexpr uint32_t P2_SMEM_BYTES = P2_OFF_CLC + P2_CLC_STAGES * 16;
+constexpr int P2_CLC_CONSUMERS = 2 * (1 + P2_EPI_WARPS) + 1;     // per pair: two producer threads, the MMA thread, 2 x 16 epilogue warps
 static_assert(P2_SMEM_BYTES <= 232448, "shared memory budget");
-static_assert(2 * P2_STAGES + 5 <= 32, "barrier block");
+static_assert(2 * P2_STAGES + 6 + 2 * P2_CLC_STAGES <= 32, "barrier block");
 
 #ifdef AVI_GEMM_TIMELINE
 // Build-time instrumentation (python __graft_entry__.py with AVI_NVCC_EXTRA=-DAVI_GEMM_TIMELINE): clock64() stamps of CTA 0's
@@ -77,6 +80,11 @@ struct Tc2Params {
   int64_t c_ld, c_batch_stride, res_ld, res_batch_stride;
   int vec_ok;      // outputs (and residual) are 16-byte addressable per 32-column chunk
   int tma_store;   // 0: threads store; 1: staged tiles leave through TMA stores (map_c); 2: TMA reduce-add (C += ..., residual == C)
+  // 1 (CL = 2 only): the grid holds ONE cluster per tile and the resident pairs steal the pending ones through cluster launch
+  // control (clusterlaunchcontrol.try_cancel) instead of walking tile = pair + k * pairs. The pairs then share the tiles by
+  // availability: a launch that only gets part of the GPU (the other batch's autoregressive decoder holds 64 SMs for 1 ms) finishes
+  // on the SMs it has instead of leaving the tiles of its not-yet-resident pairs for when they arrive.
+  int dynamic;
 };
 
 // TF32 = true: operands are fp32 in shared memory (32 elements per 128-byte swizzle row instead of 64), consumed by
@@ -98,6 +106,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   uint64_t* tmem_full = bars + 2 * P2_STAGES;       // [2]
   uint64_t* tmem_empty = bars + 2 * P2_STAGES + 2;  // [2]       (used in the leader CTA)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * P2_STAGES + 4);
+  uint64_t* clc_full = bars + 2 * P2_STAGES + 6;                    // [CLC_STAGES] response landed (every CTA of the pair)
+  uint64_t* clc_empty = clc_full + P2_CLC_STAGES;                   // [CLC_STAGES] every consumer of the pair has read it (leader)
+  uint8_t* clc_resp = smem + P2_OFF_CLC;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = cluster_ctarank();             // 0 .. CL-1
@@ -107,6 +118,26 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   constexpr int PPC = CL / 2;                           // pairs per cluster
   const int pair = blockIdx.x / CL, num_pairs = gridDim.x / CL;   // work-item walkers (a cluster walks super-tiles of PPC m-tiles)
   const int mt_total = p.m_tiles * p.batch;
+  const bool dyn = CL == 2 && p.dynamic != 0;
+  const int first_tile = dyn ? (int)(blockIdx.x / CL) : pair;
+  const uint32_t clc_empty_leader = mapa_shared(smem_u32(&clc_empty[0]), leader);
+  // next tile of this pair: the static walk, or the index of a cluster taken back from the launch queue (-1: none left). Every role
+  // of both CTAs consumes every response (its own slot / phase cursor) and reports to the leader's empty barrier.
+  auto next_tile = [&](int t, int& cslot, uint32_t& cphase) -> int {
+    if (!dyn) {
+      t += num_pairs;
+      return t < p.total_tiles ? t : -1;
+    }
+    mbar_wait(smem_u32(&clc_full[cslot]), cphase);
+    const int nxt = clc_decode(smem_u32(clc_resp + 16 * cslot));
+    fence_proxy_async_smem();                      // the slot is rewritten by the async proxy (the next try_cancel)
+    mbar_arrive_cluster(clc_empty_leader + 8 * cslot);
+    if (++cslot == P2_CLC_STAGES) {
+      cslot = 0;
+      cphase ^= 1;
+    }
+    return nxt < 0 ? -1 : nxt / CL;
+  };
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -119,6 +150,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&tmem_full[s]), 1);
       mbar_init(smem_u32(&tmem_empty[s]), 2 * P2_EPI_WARPS);
+    }
+    for (int s = 0; s < P2_CLC_STAGES; ++s) {
+      mbar_init(smem_u32(&clc_full[s]), 1);
+      mbar_init(smem_u32(&clc_empty[s]), P2_CLC_CONSUMERS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -137,7 +172,22 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t full_leader = mapa_shared(smem_u32(&full_bar[0]), leader);
-      for (int t = pair; t < p.total_tiles; t += num_pairs) {
+      int cslot = 0, islot = 0, it = 0;
+      uint32_t cphase = 0, iphase = 0;
+      // the leader's producer thread also asks for the NEXT tile when it starts loading one (one request ahead: the answer is there
+      // long before the k-blocks of the current tile have been issued, and a pair never reserves more than one tile beyond its own)
+      auto clc_issue = [&]() {
+        mbar_wait(smem_u32(&clc_empty[islot]), iphase ^ 1);
+        mbar_expect_tx(smem_u32(&clc_full[islot]), 16);
+        mbar_expect_tx_cluster(mapa_shared(smem_u32(&clc_full[islot]), 1), 16);
+        clc_try_cancel_multicast(smem_u32(clc_resp + 16 * islot), smem_u32(&clc_full[islot]));
+        if (++islot == P2_CLC_STAGES) {
+          islot = 0;
+          iphase ^= 1;
+        }
+      };
+      if (dyn && crank == 0) clc_issue();
+      for (int t = first_tile; t >= 0; ++it) {
         const int n_blk = t % p.n_tiles;
         const int mt = (t / p.n_tiles) * PPC + q;     // past the end for the idle pair of an odd last super-tile: TMA zero-fills
         const int b = mt / p.m_tiles, m_blk = mt % p.m_tiles;
@@ -149,10 +199,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         // tap / phase / super-row / channel-block counters advance incrementally: this single thread paces the whole pipeline,
         // and four runtime integer divisions per k-block cost about as much as the MMAs of that k-block
         int kin = 0, ph = 0, sr = 0, tx = 0;
-        TL(0, (t - pair) / num_pairs, 0);
+        TL(0, it, 0);
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-          if (kb == 0) TL(0, (t - pair) / num_pairs, 1);
+          if (kb == 0) TL(0, it, 1);
           const uint32_t fb_local = smem_u32(&full_bar[stage]);
           if (rank == 0) mbar_expect_tx(fb_local, 2 * P2_STAGE_BYTES);
           constexpr int BK = TF32 ? P2_BK / 2 : P2_BK;   // elements per 128-byte k-block row
@@ -180,6 +230,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             phase ^= 1;
           }
         }
+        t = next_tile(t, cslot, cphase);
+        if (dyn && crank == 0 && t >= 0) clc_issue();   // never after a failed request
       }
     }
   } else if (warp == 1) {
@@ -191,8 +243,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       const uint32_t idesc_base = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)((2 * P2_BM) >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
-      int it = 0;
-      for (int t = pair; t < p.total_tiles; t += num_pairs, ++it) {
+      int it = 0, cslot = 0;
+      uint32_t cphase = 0;
+      for (int t = first_tile; t >= 0; t = next_tile(t, cslot, cphase), ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         const int n_eff = min(P2_BN, ((p.N - (t % p.n_tiles) * P2_BN + 31) >> 5) << 5);
@@ -240,8 +293,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const bool ragged_f32 = !p.vec_ok && p.c_dtype == AVI_DT_F32 && p.C2 == nullptr && p.residual == nullptr;
     const uint32_t te_leader0 = mapa_shared(smem_u32(&tmem_empty[0]), leader);
     const uint32_t te_leader1 = mapa_shared(smem_u32(&tmem_empty[1]), leader);
-    int it = 0;
-    for (int t = pair; t < p.total_tiles; t += num_pairs, ++it) {
+    int it = 0, cslot = 0;
+    uint32_t cphase = 0;
+    for (int t = first_tile; t >= 0; ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int n_blk = t % p.n_tiles;
@@ -474,6 +528,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(as ? te_leader1 : te_leader0);
+      int nt = 0;
+      if (lane == 0) nt = next_tile(t, cslot, cphase);   // one consumer per warp
+      t = __shfl_sync(0xffffffffu, nt, 0);
     }
     if (p.tma_store && lane == 0) bulk_wait_all();   // every store of this thread's bulk groups has been performed
   }
@@ -518,6 +575,7 @@ static const char* tc2_check(const AviGemmArgs* a, bool tf32 = false) {
 using namespace avi;
 
 static std::atomic<int> g_gemm_multicast{getenv("AVI_GEMM_MULTICAST") != nullptr ? 1 : 0};
+
 
 #ifdef AVI_GEMM_TIMELINE
 extern "C" int avi_debug_timeline(long long* host_out) {
@@ -632,6 +690,7 @@ static int gemm_tc2_launch(const AviGemmArgs* a, void* stream) {
   const bool inplace_res = a->residual != nullptr && (const void*)a->residual == (const void*)a->C && a->c_dtype == AVI_DT_F32 &&
                            a->res_ld == a->c_ld && a->res_batch_stride == a->c_batch_stride;
   p.tma_store = 0;
+  p.dynamic = 0;
   CUtensorMap map_c = map_a;
   // The TMA unit clips stores at the tensor bounds in 16-byte granules of the innermost dimension (measured:
   // profiles/probes/tma_clip_probe.py): with N * elemsize not a multiple of 16 the granule holding column N-1 is written whole
@@ -663,7 +722,9 @@ static int gemm_tc2_launch(const AviGemmArgs* a, void* stream) {
   const cudaError_t attr_err = smem_optin(gemm_tc2_kernel<TF32, 2>, (int)P2_SMEM_BYTES, optin);
   AVI_REQUIRE(attr_err == cudaSuccess, "avi_gemm_bf16_tc: cannot opt in to %u bytes of shared memory: %s", P2_SMEM_BYTES,
               cudaGetErrorString(attr_err));
-  const int pairs = p.total_tiles < max_pairs ? p.total_tiles : max_pairs;
+  // dynamic: one cluster per tile, of which at most max_pairs are ever resident; the rest are cancelled by the resident ones
+  p.dynamic = ((dynamic_tiles_mask() & AVI_DYN_GEMM) != 0 && p.total_tiles > 1) ? 1 : 0;
+  const int pairs = p.dynamic ? p.total_tiles : (p.total_tiles < max_pairs ? p.total_tiles : max_pairs);
   gemm_tc2_kernel<TF32, 2><<<2 * pairs, P2_THREADS, P2_SMEM_BYTES, (cudaStream_t)stream>>>(map_a, map_w, map_c, p);
   return check_launch(TF32 ? "gemm_tf32_tc" : "gemm_bf16_tc");
 }

@@ -168,6 +168,40 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// ---------------------------------------------------------------- cluster launch control (dynamic tile scheduling, sm_100)
+// A kernel launched with ONE cluster per work item lets its running clusters cancel clusters that have not been launched yet and take
+// over their index (clusterlaunchcontrol.try_cancel): the resident clusters become persistent workers that stop exactly when no
+// work is pending, however many SMs the kernel was given - e.g. while another kernel (the autoregressive decoder) holds part of the GPU.
+// The 16-byte response lands in shared memory (in every CTA of the cluster with .multicast::cluster::all) and completes 16 bytes on
+// the mbarrier at the same offset of each CTA. After a failed try_cancel the cluster must not issue another one.
+__device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void clc_try_cancel(uint32_t resp, uint32_t bar) {
+  asm volatile("clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.b128 [%0], [%1];" ::"r"(resp), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void clc_try_cancel_multicast(uint32_t resp, uint32_t bar) {
+  asm volatile("clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.multicast::cluster::all.b128 [%0], [%1];"
+               ::"r"(resp), "r"(bar)
+               : "memory");
+}
+// blockIdx.x of the first CTA of the cancelled cluster, or -1 when nothing was pending
+__device__ __forceinline__ int clc_decode(uint32_t resp) {
+  uint32_t x = 0, y, z, valid;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b128 r;\n\t"
+      "ld.shared.b128 r, [%4];\n\t"
+      "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p, r;\n\t"
+      "selp.u32 %3, 1, 0, p;\n\t"
+      "mov.u32 %0, 0;\n\tmov.u32 %1, 0;\n\tmov.u32 %2, 0;\n\t"
+      "@p clusterlaunchcontrol.query_cancel.get_first_ctaid.v4.b32.b128 {%0, %1, %2, _}, r;\n\t}"
+      : "=r"(x), "=r"(y), "=r"(z), "=r"(valid)
+      : "r"(resp)
+      : "memory");
+  return valid ? (int)x : -1;
+}
+
 // TMA loads whose completion is signalled on an mbarrier that may live in the peer CTA of the pair (cluster address)
 __device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, int c2,
                                                  int c3) {

@@ -97,6 +97,15 @@ if FP32_GEMM not in ("simt",) + tuple(_SPLIT_PATTERNS):
     raise ValueError("AVI_B200_FP32_GEMM must be simt or x3")
 
 
+DYN_GEMM, DYN_CONV0 = 1, 2
+
+
+def set_dynamic_tiles(mask: int) -> int:
+    """Which persistent kernels take their tiles through cluster launch control (bit set) instead of a static walk; returns the
+    previous mask. Results are bit-identical either way (include/avi_b200.h avi_set_dynamic_tiles)."""
+    return int(_lib.load().avi_set_dynamic_tiles(C.c_int32(mask)))
+
+
 def split_bf16_terms(x2d, pattern):
     """[rows, K] fp32 -> [rows, len(pattern) * K] bf16 blocks of the bf16 terms named by `pattern` (0 = hi, 1 = mid, 2 = lo)."""
     _need_cuda(x2d)

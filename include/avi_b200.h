@@ -88,6 +88,13 @@ int avi_gemm_bf16_tc_supported(const AviGemmArgs* args);
  * above for launches with more than one wave of tiles: two CTA pairs per cluster on consecutive m-tiles, W-tile quarters
  * TMA-multicast between them. Same results bit for bit; measured no faster on B200 (csrc/gemm_tc2.cu). Returns the old value. */
 int avi_gemm_set_multicast(int on);
+/* Tile scheduling of the persistent tensor-core kernels. Bit clear (default) = the static walk tile = cta + k * ctas of a 148-CTA grid;
+ * bit set = DYNAMIC: the grid holds one cluster per tile and the resident CTAs / CTA pairs take the pending ones through cluster launch
+ * control (clusterlaunchcontrol.try_cancel), so a launch that shares the GPU with another kernel finishes on the SMs it has instead of
+ * waiting for its not-yet-resident CTAs. Results are bit-identical; on the configs[1] step it measured no faster
+ * (profiles/r2/clc_dynamic_tiles_ab.txt), hence opt-in. Bits: 1 avi_gemm_bf16_tc / avi_gemm_tf32_tc, 2 avi_w2v_conv0_gn_gelu_tc.
+ * Returns the previous mask; AVI_DYNAMIC_TILES=<mask> in the environment sets the initial one. */
+int avi_set_dynamic_tiles(int32_t mask);
 /* fp32 -> bf16 (weights packing / activation staging), n elements */
 int avi_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
 

@@ -441,3 +441,67 @@ def test_compact_vertex_sink_roundtrip(ops):
     assert sink.push({"verts": v.view(1, rows, Cc)}) is None
     back = sink.unpack(sink.flush())["verts"]
     assert back.shape == (1, rows, Cc) and (back[0] - buf[:, :Cc]).abs().max().item() < 5e-5
+
+
+def test_dynamic_tile_scheduler_is_bit_identical_to_the_static_walk(ops):
+    """Cluster launch control (one cluster per tile in the grid, the resident CTAs take the pending ones) against the static
+    tile = cta + k * ctas walk: the GEMM (plain, narrow last n-tile, conv mode, in-place reduce-add) and conv0, bit for bit."""
+    r = _rng(11)
+    prev = ops.set_dynamic_tiles(3)
+    try:
+        def both(fn):
+            outs = []
+            for mask in (3, 0):
+                ops.set_dynamic_tiles(mask)
+                outs.append(fn())
+            torch.cuda.synchronize()
+            return outs
+
+        for rows, N, K, act, out_dt in [(256 * 62 + 64, 800, 128, 1, torch.bfloat16), (128 * 148 * 3 + 17, 256, 64, 0, torch.float32),
+                                        (15936, 2304, 768, 0, torch.bfloat16), (300, 64, 64, 0, torch.float32)]:
+            A = _t(r.normal(size=(rows, K)), dt=torch.bfloat16)
+            W = _t(r.normal(size=(N, K)) / math.sqrt(K), dt=torch.bfloat16)
+            b = _t(r.normal(size=N))
+            d, s_ = both(lambda: ops.linear(A, W, b, act=act, out_dtype=out_dt))
+            assert torch.equal(d, s_), (rows, N, K)
+        # in-place residual (TMA reduce-add): the same tiles land on the same addresses whoever computes them
+        A = _t(r.normal(size=(15936, 768)), dt=torch.bfloat16)
+        W = _t(r.normal(size=(768, 768)) / 27.0, dt=torch.bfloat16)
+        base = _t(r.normal(size=(15936, 768)))
+
+        def inplace():
+            h = base.clone()
+            ops.linear(A, W, None, residual=h, out_dtype=torch.float32, out=h)
+            return h
+        d, s_ = both(inplace)
+        assert torch.equal(d, s_)
+        # conv mode, batched
+        B, L, Cin, Cout, k, st = 5, 2000, 128, 512, 3, 2
+        x = _t(r.normal(size=(B, L, Cin)), dt=torch.bfloat16)
+        w = _t(r.normal(size=(Cout, k * Cin)) / 20.0, dt=torch.bfloat16)
+        Lo = (L - k) // st + 1
+
+        def conv():
+            out = torch.empty((B, Lo, Cout), dtype=torch.bfloat16, device="cuda")
+            ops.gemm(x, w, None, out, batch=B, rows=Lo, N=Cout, K=k * Cin, conv_taps=k, conv_stride=st, a_batch_stride=L * Cin,
+                     a_rows_alloc=L, c_batch_stride=Lo * Cout, act=1)
+            return out
+        d, s_ = both(conv)
+        assert torch.equal(d, s_)
+        # conv0 (one CTA per 128-row tile)
+        Bc, n, C = 5, 48000, 512
+        xa = _t(r.normal(size=(Bc, n)))
+        w0 = _t(r.normal(size=(C, 10)) * 0.4)
+        g, bt = _t(1 + 0.1 * r.normal(size=C)), _t(0.1 * r.normal(size=C))
+        L0 = (n - 10) // 5 + 1
+        La = L0 + (L0 & 1)
+        wp = ops.conv0_pack_tc(w0)
+
+        def conv0():
+            out = torch.zeros(Bc, La, C, dtype=torch.bfloat16, device="cuda")
+            ops.conv0_gn_gelu_tc(xa, w0, wp, g, bt, out, La * C)
+            return out
+        d, s_ = both(conv0)
+        assert torch.equal(d, s_)
+    finally:
+        ops.set_dynamic_tiles(prev)
