@@ -67,10 +67,12 @@ __device__ __forceinline__ void rodrigues(const float* r, float* R) {
 }
 
 // One warp per frame: coefficient row (betas | pose feature | 1), joints, kinematic chain, relative transforms A [5][3x4].
+// rotmat = 1: full_pose holds the five 3x3 rotation matrices of a frame (lbs(pose2rot=False), lbs.py:205-209) instead of 15 axis-angle
+// components.
 __global__ void __launch_bounds__(128) flame_prologue_kernel(const float* __restrict__ betas, const float* __restrict__ full_pose,
                                                              const float* __restrict__ jreg, float* __restrict__ coef,
                                                              float* __restrict__ A, float* __restrict__ joints,
-                                                             int32_t* __restrict__ dyn_rows, int F, int NB, int K_pad) {
+                                                             int32_t* __restrict__ dyn_rows, int F, int NB, int K_pad, int rotmat) {
   const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (f >= F) return;
@@ -103,7 +105,12 @@ __global__ void __launch_bounds__(128) flame_prologue_kernel(const float* __rest
     }
     if (lane < FL_NJ) {
       float Rl[9];
-      rodrigues(full_pose + (int64_t)f * 15 + lane * 3, Rl);
+      if (rotmat) {
+#pragma unroll
+        for (int e = 0; e < 9; ++e) Rl[e] = full_pose[(int64_t)f * 45 + lane * 9 + e];
+      } else {
+        rodrigues(full_pose + (int64_t)f * 15 + lane * 3, Rl);
+      }
 #pragma unroll
       for (int e = 0; e < 9; ++e) Rs[lane * 9 + e] = Rl[e];
     }
@@ -299,20 +306,36 @@ extern "C" int avi_flame_pack(const float* shapedirs, const float* posedirs, con
   return check_launch("flame_pack_jreg");
 }
 
-extern "C" int avi_flame_prologue(const float* betas, const float* full_pose, const float* jreg, float* coef, float* A, float* joints,
-                                  int32_t* dyn_rows, int32_t F, int32_t NB, int32_t K_pad, void* stream) {
+extern "C" int avi_flame_prologue_ex(const float* betas, const float* full_pose, int32_t pose_is_rotmat, const float* jreg, float* coef,
+                                     float* A, float* joints, int32_t* dyn_rows, int32_t F, int32_t NB, int32_t K_pad, void* stream) {
   AVI_REQUIRE(F > 0 && NB > 0 && K_pad >= NB + 37, "avi_flame_prologue: bad shape F=%d NB=%d K_pad=%d", F, NB, K_pad);
-  flame_prologue_kernel<<<(F + 3) / 4, 128, 0, (cudaStream_t)stream>>>(betas, full_pose, jreg, coef, A, joints, dyn_rows, F, NB, K_pad);
+  flame_prologue_kernel<<<(F + 3) / 4, 128, 0, (cudaStream_t)stream>>>(betas, full_pose, jreg, coef, A, joints, dyn_rows, F, NB, K_pad,
+                                                                       pose_is_rotmat ? 1 : 0);
   return check_launch("flame_prologue");
 }
+
+extern "C" int avi_flame_prologue(const float* betas, const float* full_pose, const float* jreg, float* coef, float* A, float* joints,
+                                  int32_t* dyn_rows, int32_t F, int32_t NB, int32_t K_pad, void* stream) {
+  return avi_flame_prologue_ex(betas, full_pose, 0, jreg, coef, A, joints, dyn_rows, F, NB, K_pad, stream);
+}
+
+extern "C" int avi_flame_lbs_fwd_ex(const float* betas, const float* full_pose, int32_t pose_is_rotmat, const float* dirs, const float* jreg,
+                                    const float* lbs_weights, float* coef, float* A, float* verts, float* joints, int32_t* dyn_rows,
+                                    int32_t F, int32_t V, int32_t NB, int32_t K_pad, void* stream);
 
 extern "C" int avi_flame_lbs_fwd(const float* betas, const float* full_pose, const float* dirs, const float* jreg,
                                  const float* lbs_weights, float* coef, float* A, float* verts, float* joints,
                                  int32_t* dyn_rows, int32_t F, int32_t V, int32_t NB, int32_t K_pad, void* stream) {
+  return avi_flame_lbs_fwd_ex(betas, full_pose, 0, dirs, jreg, lbs_weights, coef, A, verts, joints, dyn_rows, F, V, NB, K_pad, stream);
+}
+
+extern "C" int avi_flame_lbs_fwd_ex(const float* betas, const float* full_pose, int32_t pose_is_rotmat, const float* dirs, const float* jreg,
+                                    const float* lbs_weights, float* coef, float* A, float* verts, float* joints, int32_t* dyn_rows,
+                                    int32_t F, int32_t V, int32_t NB, int32_t K_pad, void* stream) {
   AVI_REQUIRE(F > 0 && V > 0 && NB > 0 && K_pad >= NB + 37 && K_pad % FL_KC == 0, "avi_flame_lbs_fwd: bad shape F=%d V=%d NB=%d K_pad=%d",
               F, V, NB, K_pad);
   cudaStream_t st = (cudaStream_t)stream;
-  flame_prologue_kernel<<<(F + 3) / 4, 128, 0, st>>>(betas, full_pose, jreg, coef, A, joints, dyn_rows, F, NB, K_pad);
+  flame_prologue_kernel<<<(F + 3) / 4, 128, 0, st>>>(betas, full_pose, jreg, coef, A, joints, dyn_rows, F, NB, K_pad, pose_is_rotmat ? 1 : 0);
   if (check_launch("flame_prologue")) return 1;
   dim3 grid((V + FL_VT - 1) / FL_VT, (F + FL_FT - 1) / FL_FT);
   AVI_REQUIRE(grid.y <= 65535, "avi_flame_lbs_fwd: too many frames in one call (%d); split the batch", F);

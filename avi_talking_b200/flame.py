@@ -76,10 +76,13 @@ def _refuse_grad(*tensors):
 def lbs(betas, pose, v_template, shapedirs, posedirs, J_regressor, parents, lbs_weights, pose2rot=True,
         dtype=torch.float32, detach_pose_correctives=False, _cache=None):
     """lbs.py:142-234. v_template may be [V,3] or the reference's expanded [B,V,3] (row 0 is used: the reference expands one
-    template over the batch, DecaFLAME.py:243). Returns (verts [B,V,3], J_transformed [B,5,3])."""
+    template over the batch, DecaFLAME.py:243). pose: [B, 15] axis-angle, or with pose2rot=False the rotation matrices themselves
+    ([B, 5, 3, 3] or any shape with 45 values per frame, lbs.py:205-209). Returns (verts [B,V,3], J_transformed [B,5,3])."""
     _refuse_grad(betas, pose, v_template)
     if not pose2rot:
-        raise NotImplementedError("pose2rot=False (rotation-matrix input) is not used on the AVI-Talking path")
+        pose = pose.reshape(pose.shape[0], -1)
+        if pose.shape[1] != 45:
+            raise ValueError(f"pose2rot=False expects 5 rotation matrices per frame (45 values), got {pose.shape[1]}")
     if J_regressor.shape[0] != 5 or [int(p) for p in parents] != [-1, 0, 1, 1, 1]:
         raise NotImplementedError("only the FLAME kinematic tree (5 joints, parents [-1,0,1,1,1]) is supported")
     vt = v_template[0] if v_template.dim() == 3 else v_template
@@ -88,7 +91,7 @@ def lbs(betas, pose, v_template, shapedirs, posedirs, J_regressor, parents, lbs_
     pose = pose.expand(B, -1).contiguous().float()
     cache = _cache if _cache is not None else _lbs_cache
     verts, joints, _ = _run(cache, default_precision(), betas, pose, shapedirs, posedirs, vt, J_regressor, lbs_weights,
-                            want_joints=True)
+                            want_joints=True, rotmat=not pose2rot)
     return verts, joints
 
 

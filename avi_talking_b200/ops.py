@@ -384,8 +384,10 @@ def flame_pack(shapedirs, posedirs, v_template, J_regressor, K_pad):
     return dirs, jreg
 
 
-def flame_lbs(betas, full_pose, dirs, jreg, lbs_weights, V, NB, K_pad, want_joints=False, want_dyn_rows=False):
+def flame_lbs(betas, full_pose, dirs, jreg, lbs_weights, V, NB, K_pad, want_joints=False, want_dyn_rows=False, rotmat=False):
+    """rotmat: full_pose is [F, 45] rotation matrices (lbs(pose2rot=False)) instead of [F, 15] axis-angle."""
     _need_cuda(betas, full_pose)
+    assert full_pose.shape[1] == (45 if rotmat else 15)
     F = betas.shape[0]
     dev = betas.device
     coef = torch.empty((F, K_pad), dtype=torch.float32, device=dev)
@@ -394,9 +396,10 @@ def flame_lbs(betas, full_pose, dirs, jreg, lbs_weights, V, NB, K_pad, want_join
     joints = torch.empty((F, 5, 3), dtype=torch.float32, device=dev) if want_joints else None
     rows = torch.empty((F,), dtype=torch.int32, device=dev) if want_dyn_rows else None
     with _timed("flame_lbs", float(F) * (V * 12 + 4 * (NB + 6))):  # algorithmic bytes: verts written + coefficients read
-        _lib.check(_lib.load().avi_flame_lbs_fwd(_ptr(betas), _ptr(full_pose), _ptr(dirs), _ptr(jreg), _ptr(lbs_weights),
-                                                 _ptr(coef), _ptr(A), _ptr(verts), _ptr(joints), _ptr(rows), C.c_int32(F),
-                                                 C.c_int32(V), C.c_int32(NB), C.c_int32(K_pad), _stream()), "avi_flame_lbs_fwd")
+        _lib.check(_lib.load().avi_flame_lbs_fwd_ex(_ptr(betas), _ptr(full_pose), C.c_int32(1 if rotmat else 0), _ptr(dirs), _ptr(jreg),
+                                                    _ptr(lbs_weights), _ptr(coef), _ptr(A), _ptr(verts), _ptr(joints), _ptr(rows),
+                                                    C.c_int32(F), C.c_int32(V), C.c_int32(NB), C.c_int32(K_pad), _stream()),
+                   "avi_flame_lbs_fwd")
     return verts, joints, rows
 
 
@@ -413,9 +416,10 @@ def flame_pack_tc(dirs32, V, NB):
 
 
 def flame_lbs_tc(betas, full_pose, dirs16, jreg, lbs_weights, v_template, V, NB, K_pad, want_joints=False, want_dyn_rows=False,
-                 padded=False):
+                 padded=False, rotmat=False):
     """Same results contract as flame_lbs, blend + skinning on the tcgen05 path."""
     _need_cuda(betas, full_pose)
+    assert full_pose.shape[1] == (45 if rotmat else 15)
     F = betas.shape[0]
     dev = betas.device
     coef = torch.empty((F, K_pad), dtype=torch.float32, device=dev)
@@ -427,8 +431,9 @@ def flame_lbs_tc(betas, full_pose, dirs16, jreg, lbs_weights, v_template, V, NB,
     rows = torch.empty((F,), dtype=torch.int32, device=dev) if want_dyn_rows else None
     lib = _lib.load()
     with _timed("flame_lbs", float(F) * (V * 12 + 4 * (NB + 6))):
-        _lib.check(lib.avi_flame_prologue(_ptr(betas), _ptr(full_pose), _ptr(jreg), _ptr(coef), _ptr(A), _ptr(joints), _ptr(rows),
-                                          C.c_int32(F), C.c_int32(NB), C.c_int32(K_pad), _stream()), "avi_flame_prologue")
+        _lib.check(lib.avi_flame_prologue_ex(_ptr(betas), _ptr(full_pose), C.c_int32(1 if rotmat else 0), _ptr(jreg), _ptr(coef), _ptr(A),
+                                             _ptr(joints), _ptr(rows), C.c_int32(F), C.c_int32(NB), C.c_int32(K_pad), _stream()),
+                   "avi_flame_prologue")
         _lib.check(lib.avi_flame_blend_skin_tc_grouped(_ptr(coef), _ptr(A), _ptr(dirs16), _ptr(lbs_weights), _ptr(v_template),
                                                        C.c_int64(0), _ptr(coef16), _ptr(verts), C.c_int64(vrows.stride(0)), C.c_int32(F),
                                                        C.c_int32(V), C.c_int32(NB + 36), C.c_int32(0), C.c_int32(K_pad),

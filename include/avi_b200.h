@@ -220,6 +220,13 @@ int avi_flame_lbs_fwd(const float* betas, const float* full_pose, const float* d
 /* first half of avi_flame_lbs_fwd only (coefficient rows, joints, kinematic chain, landmark rows), for the tensor-core blend below */
 int avi_flame_prologue(const float* betas, const float* full_pose, const float* jreg, float* coef, float* A, float* joints,
                        int32_t* dyn_rows, int32_t F, int32_t NB, int32_t K_pad, void* stream);
+/* the same two entry points for lbs(pose2rot=False) (lbs.py:205-209): pose_is_rotmat != 0 -> full_pose is [F, 5, 3, 3] rotation
+ * matrices (pose feature = R[1:] - I, the matrices feed the kinematic chain directly); 0 -> [F, 15] axis-angle as above */
+int avi_flame_prologue_ex(const float* betas, const float* full_pose, int32_t pose_is_rotmat, const float* jreg, float* coef, float* A,
+                          float* joints, int32_t* dyn_rows, int32_t F, int32_t NB, int32_t K_pad, void* stream);
+int avi_flame_lbs_fwd_ex(const float* betas, const float* full_pose, int32_t pose_is_rotmat, const float* dirs, const float* jreg,
+                         const float* lbs_weights, float* coef, float* A, float* verts, float* joints, int32_t* dyn_rows, int32_t F,
+                         int32_t V, int32_t NB, int32_t K_pad, void* stream);
 
 /* tcgen05 blend + fused skinning (fp16 operands, fp32 accumulate/template/skinning; NB + 36 <= 192).
  *   avi_flame_pack_tc : dirs16 fp16 [3][V_pad][192] from the packed fp32 dirs of avi_flame_pack (V_pad multiple of 128)

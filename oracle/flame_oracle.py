@@ -48,14 +48,14 @@ def batch_rigid_transform(rot_mats, joints, parents):
     return posed, rel_tf
 
 
-def lbs(betas, pose, v_template, shapedirs, posedirs, J_regressor, parents, lbs_weights):
-    """lbs.py:142-234 with pose2rot=True. v_template [B,V,3] or [V,3]."""
+def lbs(betas, pose, v_template, shapedirs, posedirs, J_regressor, parents, lbs_weights, pose2rot=True):
+    """lbs.py:142-234. v_template [B,V,3] or [V,3]; pose2rot=False: pose holds the rotation matrices (:205-209)."""
     B = max(betas.shape[0], pose.shape[0])
     if v_template.dim() == 2:
         v_template = v_template[None].expand(B, -1, -1)
     v_shaped = v_template + torch.einsum("bl,mkl->bmk", betas, shapedirs)          # :188
     J = torch.einsum("bik,ji->bjk", v_shaped, J_regressor)                           # :192
-    rot = batch_rodrigues(pose.reshape(-1, 3)).view(B, -1, 3, 3)                     # :198
+    rot = batch_rodrigues(pose.reshape(-1, 3)).view(B, -1, 3, 3) if pose2rot else pose.reshape(B, -1, 3, 3)   # :198 / :207
     pose_feature = (rot[:, 1:] - torch.eye(3)).reshape(B, -1)                        # :201
     v_posed = v_shaped + torch.matmul(pose_feature, posedirs).view(B, -1, 3)         # :203,215
     J_tf, A = batch_rigid_transform(rot, J, parents)                                 # :217

@@ -79,6 +79,28 @@ def golden_flame():
     print("flame.npz", {k: v.shape for k, v in out.items()})
 
 
+def golden_lbs_rotmat():
+    """lbs(pose2rot=False) of BOTH reference copies (gdl and inferno, lbs.py:205-209): the pose argument is the stack of rotation
+    matrices. Separate small fixture (tests/golden/lbs_rotmat.npz) so that flame.npz stays byte-identical."""
+    from gdl.utils.lbs import batch_rodrigues as gdl_rodrigues
+    from gdl.utils.lbs import lbs as gdl_lbs
+    from inferno.utils.lbs import lbs as inf_lbs
+    from . import synth
+    buf = synth.flame_buffers(100, 50)
+    p = synth.flame_params(3, seed=7)
+    betas = torch.cat([p["shape"], p["exp"]], 1)
+    full_pose = torch.cat([p["pose"][:, :3], 0.1 * p["pose"][:, :3], p["pose"][:, 3:], p["eye"]], 1)      # every joint rotated
+    rot = gdl_rodrigues(full_pose.view(-1, 3)).view(3, 5, 3, 3)
+    out = {"rot": rot.numpy()}
+    for tag, fn in (("gdl", gdl_lbs), ("inferno", inf_lbs)):
+        v, J = fn(betas, rot, buf["v_template"][None].expand(3, -1, -1), buf["shapedirs"], buf["posedirs"], buf["J_regressor"],
+                  buf["parents"], buf["lbs_weights"], pose2rot=False)
+        out[f"{tag}_verts"], out[f"{tag}_joints"] = v.numpy(), J.numpy()
+    assert np.array_equal(out["gdl_verts"], out["inferno_verts"])
+    np.savez_compressed(os.path.join(GOLD, "lbs_rotmat.npz"), **out)
+    print("lbs_rotmat.npz", {k: v.shape for k, v in out.items()})
+
+
 def _ref_wav2vec2(sd):
     from transformers import Wav2Vec2Config
     from models.lib.wav2vec import Wav2Vec2Model
@@ -863,6 +885,7 @@ def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(8)
     golden_flame()
+    golden_lbs_rotmat()
     golden_wav2vec2()
     golden_faceformer()
     golden_prior()

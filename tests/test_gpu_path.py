@@ -435,3 +435,23 @@ def test_full_size_configs1_properties():
     ref = ffo.predict(sd_ff, sd_w2v, synth.flame_buffers()["v_template"].reshape(1, 1, 15069), inp["audio"][5:6].cpu(),
                       inp["emo"][5:6].cpu(), cached=True)
     assert (v[5:6].cpu() - ref).abs().max().item() < 1e-4
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-6), ("bf16", 5e-5)])
+def test_lbs_pose2rot_false_matches_reference_golden(golden, monkeypatch, precision, tol):
+    """lbs(pose2rot=False): the pose argument is the stack of rotation matrices (lbs.py:205-209); golden from both reference copies
+    (tests/golden/lbs_rotmat.npz), every joint rotated."""
+    from avi_talking_b200.flame import lbs
+    monkeypatch.setenv("AVI_B200_PRECISION", precision)
+    g = golden("lbs_rotmat")
+    buf = {k: v.cuda() for k, v in synth.flame_buffers(100, 50).items()}
+    p = synth.flame_params(3, seed=7)
+    betas = torch.cat([p["shape"], p["exp"]], 1).cuda()
+    rot = torch.from_numpy(g["rot"]).cuda()
+    v, J = lbs(betas, rot, buf["v_template"], buf["shapedirs"], buf["posedirs"], buf["J_regressor"], buf["parents"], buf["lbs_weights"],
+               pose2rot=False)
+    assert np.abs(v.cpu().numpy() - g["gdl_verts"]).max() < tol
+    assert np.abs(J.cpu().numpy() - g["gdl_joints"]).max() < 1e-6
+    with pytest.raises(ValueError):
+        lbs(betas, rot[:, :4], buf["v_template"], buf["shapedirs"], buf["posedirs"], buf["J_regressor"], buf["parents"],
+            buf["lbs_weights"], pose2rot=False)

@@ -287,3 +287,15 @@ def test_device_draws_layout():
     assert len(d.groups) == 1 and abs(d.groups[0][0] - 0.1) < 1e-9          # HF defaults: every site at p = 0.1
     assert d.state.tolist()[:3] == [7, 5, 0]
     assert d.blend.shape == (2, cfg.num_hidden_layers, B * T * cfg.hidden_size) and d.spec.numel() == B * T
+
+
+def test_lbs_with_rotation_matrices_matches_reference(golden):
+    """lbs(pose2rot=False) (lbs.py:205-209: the pose argument is the stack of rotation matrices): oracle vs both reference copies."""
+    g = golden("lbs_rotmat")
+    buf = synth.flame_buffers(100, 50)
+    p = synth.flame_params(3, seed=7)
+    betas = torch.cat([p["shape"], p["exp"]], 1)
+    v, J = fo.lbs(betas, torch.from_numpy(g["rot"]), buf["v_template"], buf["shapedirs"], buf["posedirs"], buf["J_regressor"],
+                  buf["parents"], buf["lbs_weights"], pose2rot=False)
+    assert np.abs(v.numpy() - g["gdl_verts"]).max() < 1e-6 and np.abs(J.numpy() - g["gdl_joints"]).max() < 1e-6
+    assert np.array_equal(g["gdl_verts"], g["inferno_verts"])
