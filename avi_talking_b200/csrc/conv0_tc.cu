@@ -314,10 +314,14 @@ __global__ void __launch_bounds__(CZ_THREADS, 1) conv0_tc_kernel(const __grid_co
         for (int j = 0; j < 8; ++j) {
           const float4 sc = lds128f(ssa + (c0 + 4 * j) * 4);
           const float4 sh = lds128f(ssa + (CZ_C + c0 + 4 * j) * 4);
-          f[4 * j + 0] = gelu_fast(fmaf(__uint_as_float(v[4 * j + 0]), sc.x, sh.x));
-          f[4 * j + 1] = gelu_fast(fmaf(__uint_as_float(v[4 * j + 1]), sc.y, sh.y));
-          f[4 * j + 2] = gelu_fast(fmaf(__uint_as_float(v[4 * j + 2]), sc.z, sh.z));
-          f[4 * j + 3] = gelu_fast(fmaf(__uint_as_float(v[4 * j + 3]), sc.w, sh.w));
+          // packed fp32 (FFMA2): the GroupNorm affine and the GELU polynomial of two channels per instruction
+          float a0, a1, a2, a3;
+          unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(v[4 * j + 0]), __uint_as_float(v[4 * j + 1])), pack_f32x2(sc.x, sc.y),
+                                 pack_f32x2(sh.x, sh.y)), a0, a1);
+          unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), pack_f32x2(sc.z, sc.w),
+                                 pack_f32x2(sh.z, sh.w)), a2, a3);
+          gelu_fast2(a0, a1, f[4 * j + 0], f[4 * j + 1]);
+          gelu_fast2(a2, a3, f[4 * j + 2], f[4 * j + 3]);
         }
         const uint32_t buf = tile + (ch & 1) * CZ_TRANS_TILE;
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store that used this buffer has read it

@@ -329,15 +329,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         float f[32];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float4 bb = lds128f(sbias_a + (col0 + 4 * j) * 4);
-          f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + bb.x;
-          f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bb.y;
-          f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bb.z;
-          f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bb.w;
+          const float4 bb = lds128f(sbias_a + (col0 + 4 * j) * 4);   // packed fp32 adds (FADD2): two columns per instruction
+          unpack_f32x2(add_f32x2(pack_f32x2(__uint_as_float(v[4 * j + 0]), __uint_as_float(v[4 * j + 1])), pack_f32x2(bb.x, bb.y)),
+                       f[4 * j + 0], f[4 * j + 1]);
+          unpack_f32x2(add_f32x2(pack_f32x2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), pack_f32x2(bb.z, bb.w)),
+                       f[4 * j + 2], f[4 * j + 3]);
         }
         if (p.act == AVI_ACT_GELU) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = gelu_fast(f[j]);
+          for (int j = 0; j < 32; j += 2) gelu_fast2(f[j], f[j + 1], f[j], f[j + 1]);   // packed fp32 (FFMA2): two columns per instruction
         } else if (p.act == AVI_ACT_RELU) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
