@@ -93,6 +93,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();   // the prologue above may overlap the tail of the QKV GEMM (programmatic dependent launch)
 
   // item -> (clip, head, query tile); the query tiles of one (clip, head) are neighbours, so K / V are shared through L2
   const int first = blockIdx.x, stride = gridDim.x;
@@ -307,6 +308,7 @@ extern "C" int avi_mha_fwd_tc(const void* qkv, void* out, int32_t B, int32_t T, 
   p.scale_log2e = scale * 1.4426950408889634f;
   const int sms = device_sms();
   const int grid = p.total_items < sms ? p.total_items : sms;
-  attn_tc_kernel<<<grid, AT_THREADS, AT_SMEM, (cudaStream_t)stream>>>(map_q, map_kv, p);
+  const cudaError_t le = launch_pdl(attn_tc_kernel, dim3(grid), dim3(AT_THREADS), AT_SMEM, (cudaStream_t)stream, map_q, map_kv, p);
+  AVI_REQUIRE(le == cudaSuccess, "avi_mha_fwd_tc: launch failed: %s", cudaGetErrorString(le));
   return check_launch("attn_tc");
 }

@@ -21,8 +21,13 @@ void set_error(const char* fmt, ...) {
 static std::atomic<int> g_dynamic_tiles{getenv("AVI_DYNAMIC_TILES") != nullptr ? atoi(getenv("AVI_DYNAMIC_TILES")) : 0};
 int dynamic_tiles_mask() { return g_dynamic_tiles.load(std::memory_order_relaxed); }
 
+// programmatic dependent launch of the GEMM / attention / LayerNorm kernels (common.cuh launch_pdl)
+static std::atomic<int> g_pdl{getenv("AVI_PDL") != nullptr ? atoi(getenv("AVI_PDL")) : 0};
+bool pdl_enabled() { return g_pdl.load(std::memory_order_relaxed) != 0; }
+
 }  // namespace avi
 
+extern "C" int avi_set_pdl(int32_t on) { return avi::g_pdl.exchange(on ? 1 : 0, std::memory_order_relaxed); }
 extern "C" int avi_set_dynamic_tiles(int32_t mask) { return avi::g_dynamic_tiles.exchange(mask, std::memory_order_relaxed); }
 extern "C" int avi_version(void) { return AVI_B200_VERSION; }
 extern "C" const char* avi_last_error(void) { return avi::g_err; }

@@ -47,6 +47,27 @@ inline cudaError_t smem_optin(Kernel kernel, int bytes, SmemOptIn& state) {
 enum : int { AVI_DYN_GEMM = 1, AVI_DYN_CONV0 = 2 };
 int dynamic_tiles_mask();
 
+// Programmatic dependent launch (griddepcontrol): a kernel launched with launch_pdl() may be scheduled while the previous kernel of the
+// stream is still draining (its CTAs have all exited or are in their last wave), runs its prologue (barrier init, TMEM allocation,
+// tensor-map prefetch) and blocks in pdl_wait() until that kernel's memory is complete and visible. Only kernels that call pdl_wait()
+// before their first global access may be launched this way. AVI_PDL=0 in the environment / avi_set_pdl(0) = plain launches.
+bool pdl_enabled();
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 void set_error(const char* fmt, ...);
 extern std::atomic<int64_t> g_launches;
 

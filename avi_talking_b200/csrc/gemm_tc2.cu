@@ -165,6 +165,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   cluster_sync_all();  // barrier inits + TMEM allocation of BOTH CTAs visible before any cross-CTA traffic
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();          // everything above may overlap the tail of the previous kernel of the stream (programmatic dependent launch)
 
   if (warp == 0) {
     // ===================== TMA producer (each CTA loads its 128 rows of A and its 128 rows of W) =====================
@@ -716,7 +717,9 @@ static int gemm_tc2_launch(const AviGemmArgs* a, void* stream) {
 
   if (mc) {
     const int clusters = p.total_tiles < mc_clusters ? p.total_tiles : mc_clusters;
-    gemm_tc2_kernel<TF32, 4><<<4 * clusters, P2_THREADS, P2_SMEM_BYTES, (cudaStream_t)stream>>>(map_a, map_w, map_c, p);
+    const cudaError_t le = launch_pdl(gemm_tc2_kernel<TF32, 4>, dim3(4 * clusters), dim3(P2_THREADS), P2_SMEM_BYTES, (cudaStream_t)stream,
+                                      map_a, map_w, map_c, p);
+    AVI_REQUIRE(le == cudaSuccess, "avi_gemm_bf16_tc: launch failed: %s", cudaGetErrorString(le));
     return check_launch(TF32 ? "gemm_tf32_tc" : "gemm_bf16_tc");
   }
   const cudaError_t attr_err = smem_optin(gemm_tc2_kernel<TF32, 2>, (int)P2_SMEM_BYTES, optin);
@@ -725,7 +728,9 @@ static int gemm_tc2_launch(const AviGemmArgs* a, void* stream) {
   // dynamic: one cluster per tile, of which at most max_pairs are ever resident; the rest are cancelled by the resident ones
   p.dynamic = ((dynamic_tiles_mask() & AVI_DYN_GEMM) != 0 && p.total_tiles > 1) ? 1 : 0;
   const int pairs = p.dynamic ? p.total_tiles : (p.total_tiles < max_pairs ? p.total_tiles : max_pairs);
-  gemm_tc2_kernel<TF32, 2><<<2 * pairs, P2_THREADS, P2_SMEM_BYTES, (cudaStream_t)stream>>>(map_a, map_w, map_c, p);
+  const cudaError_t le = launch_pdl(gemm_tc2_kernel<TF32, 2>, dim3(2 * pairs), dim3(P2_THREADS), P2_SMEM_BYTES, (cudaStream_t)stream, map_a,
+                                    map_w, map_c, p);
+  AVI_REQUIRE(le == cudaSuccess, "avi_gemm_bf16_tc: launch failed: %s", cudaGetErrorString(le));
   return check_launch(TF32 ? "gemm_tf32_tc" : "gemm_bf16_tc");
 }
 

@@ -193,6 +193,7 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float* __restr
   constexpr int C = NV * 128;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  pdl_wait();   // launched as a programmatic dependent of the GEMM that produced x
   if (row >= rows) return;
   const float4* xr = reinterpret_cast<const float4*>(x + row * C);
   float4 v[NV];
@@ -284,8 +285,8 @@ static void launch_layernorm(const float* x, const float* p, const float* w, con
                              int64_t rows, int C, float eps, cudaStream_t st) {
   const unsigned grid = (unsigned)((rows + 7) / 8);
   const bool al = (((uintptr_t)x | (uintptr_t)p | (uintptr_t)w | (uintptr_t)b | (uintptr_t)o32) % 16 == 0) && ((uintptr_t)o16 % 8 == 0);
-  if (al && C == 768) layernorm_vec_kernel<6, MODE><<<grid, 256, 0, st>>>(x, p, w, b, o32, o16, rows, eps);
-  else if (al && C == 512) layernorm_vec_kernel<4, MODE><<<grid, 256, 0, st>>>(x, p, w, b, o32, o16, rows, eps);
+  if (al && C == 768) launch_pdl(layernorm_vec_kernel<6, MODE>, dim3(grid), dim3(256), 0, st, x, p, w, b, o32, o16, rows, eps);
+  else if (al && C == 512) launch_pdl(layernorm_vec_kernel<4, MODE>, dim3(grid), dim3(256), 0, st, x, p, w, b, o32, o16, rows, eps);
   else layernorm_kernel<32, MODE><<<grid, 256, 0, st>>>(x, p, w, b, o32, o16, rows, C, eps);
 }
 

@@ -106,6 +106,12 @@ def set_dynamic_tiles(mask: int) -> int:
     return int(_lib.load().avi_set_dynamic_tiles(C.c_int32(mask)))
 
 
+def set_pdl(on: bool) -> bool:
+    """Programmatic dependent launch of the GEMM / attention / LayerNorm kernels (include/avi_b200.h avi_set_pdl); returns the previous
+    setting."""
+    return bool(_lib.load().avi_set_pdl(C.c_int32(1 if on else 0)))
+
+
 def split_bf16_terms(x2d, pattern):
     """[rows, K] fp32 -> [rows, len(pattern) * K] bf16 blocks of the bf16 terms named by `pattern` (0 = hi, 1 = mid, 2 = lo)."""
     _need_cuda(x2d)

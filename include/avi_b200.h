@@ -95,6 +95,11 @@ int avi_gemm_set_multicast(int on);
  * (profiles/r2/clc_dynamic_tiles_ab.txt), hence opt-in. Bits: 1 avi_gemm_bf16_tc / avi_gemm_tf32_tc, 2 avi_w2v_conv0_gn_gelu_tc.
  * Returns the previous mask; AVI_DYNAMIC_TILES=<mask> in the environment sets the initial one. */
 int avi_set_dynamic_tiles(int32_t mask);
+/* Programmatic dependent launch (griddepcontrol.wait + cudaLaunchAttributeProgrammaticStreamSerialization) of the tensor-core GEMM, the
+ * wav2vec2 attention and the LayerNorm kernels: each may be scheduled while the previous kernel of its stream drains and runs its
+ * prologue (barrier init, TMEM allocation) before waiting for that kernel's memory. 0 = plain stream-ordered launches. Results are
+ * identical. Returns the previous setting; AVI_PDL=<0|1> in the environment sets the initial one. */
+int avi_set_pdl(int32_t on);
 /* fp32 -> bf16 (weights packing / activation staging), n elements */
 int avi_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
 
