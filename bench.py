@@ -59,6 +59,28 @@ def parse():
     return ap.parse_args()
 
 
+def shutdown_process_group(world, timeout_s=20.0):
+    """Leave the process group without ever hanging the launcher: CUDA graphs that captured NCCL kernels must be gone before the
+    communicator is (the callers drop them first); the destroy itself runs on a helper thread, and if it has not returned after
+    `timeout_s` (seen once on a 2-GPU box: both ranks had printed and passed their last collective) the process exits with status 0 -
+    the measurement is complete and printed by then."""
+    if world <= 1:
+        return
+    import gc
+    import threading
+    import torch.distributed as dist
+    gc.collect()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    t = threading.Thread(target=dist.destroy_process_group, daemon=True)
+    t.start()
+    t.join(timeout_s)
+    if t.is_alive():
+        sys.stderr.write(f"bench.py: destroy_process_group did not return within {timeout_s:g} s; exiting\n")
+        sys.stderr.flush()
+        os._exit(0)
+
+
 def ncu_traffic(kernel_substr):
     """DRAM bytes per launch (read + write) of a kernel from the committed ncu pass over this same command
     (profiles/r2/traffic.json, else the round-1 file; written by profiles/summarise_launches.py); None when no capture is committed."""
@@ -416,8 +438,7 @@ def run_ours(args):
 
     dt_ms, e2e_ms, compact_ms = shard.max_over_ranks([dt_ms, e2e_ms, compact_ms], device=dev)   # identity at N=1
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        shutdown_process_group(world)
         return
 
     pk = peaks()
@@ -470,8 +491,7 @@ def run_ours(args):
                                 "sample": f"{args.cpu_clips} of the {B} clips, best of 2 runs, oracle restatement of the reference "
                                           "(fp32 torch-CPU, KV-cached O(T) decoder)"}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    shutdown_process_group(world)
 
 
 # ----------------------------------------------------------------------------------------------------------------- configs[3]: prior
@@ -610,8 +630,7 @@ def run_prior(args):
             line["cpu_baseline"] = {"value": nb / t, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
                                     "sample": f"{nb} of the {B} samples, best of 2, oracle restatement (fp32 torch-CPU)"}
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    shutdown_process_group(world)
 
 
 # ----------------------------------------------------------------------------------------------------------------- configs[4]: train
@@ -817,8 +836,10 @@ def run_train(args):
             line["cpu_baseline"] = {"value": 1.0 / t, "unit": "clips/s", "cores": torch.get_num_threads(), "kind": "port",
                                     "sample": "one training step on one 4 s clip, best of 2, oracle restatement under torch autograd (fp32 torch-CPU)"}
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    if not args.no_graph:          # graphs that captured NCCL kernels go before the communicator does
+        gstep.graphs.clear()
+        gstep.graph = None
+    shutdown_process_group(world)
 
 
 def main():
