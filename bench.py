@@ -70,7 +70,8 @@ def shutdown_process_group(world, timeout_s=20.0):
     import threading
     import torch.distributed as dist
     gc.collect()
-    torch.cuda.synchronize()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
     sys.stdout.flush()
     t = threading.Thread(target=dist.destroy_process_group, daemon=True)
     t.start()
