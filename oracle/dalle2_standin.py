@@ -7,7 +7,9 @@ installed. The reference's own arithmetic (token assembly, transformer loop, p_s
 golden vectors; what stays UNPINNED is exactly this file: a restatement of the published upstream modules (lucidrains
 dalle2_pytorch v1.x: LayerNorm, RelPosBias, Attention, FeedForward/SwiGLU, SinusoidalPosEmb, MLP, NoiseScheduler,
 DiffusionPrior.{p_mean_variance, p_sample_loop, p_sample_loop_ddim}; rotary_embedding_torch.RotaryEmbedding), written as
-nn.Modules with the upstream attribute / parameter names.
+nn.Modules with the upstream attribute / parameter names. Pieces with an independent public implementation in this image are pinned
+on it (tests/test_oracle_prior.py::test_dalle2_standin_pieces_against_independent_public_implementations: RelPosBias bucketing vs
+transformers' T5, the rotary embedding vs transformers' GPT-J, the cosine schedule vs its published formula); the rest is unpinned.
 """
 from __future__ import annotations
 

@@ -103,3 +103,40 @@ def test_classifier_free_guidance_matches_reference(golden):
     y = po.p_sample_loop(sd, text, inp["image_embed"], inp["noises"], timesteps=64, cond_scale=cs)
     assert np.abs(y.numpy() - g["ddim64_cfg"]).max() < 2e-5
     assert np.abs(g["ddim64_cfg"] - gp["ddim64"]).max() > 1e-2      # guidance changes the result
+
+
+def test_dalle2_standin_pieces_against_independent_public_implementations():
+    """dalle2_pytorch / rotary_embedding_torch are un-vendored and absent from this image, so oracle/dalle2_standin.py stays UNPINNED as a
+    whole. Two of its pieces do have independent public implementations installed here, and are pinned on them: the T5 relative-position
+    bucketing behind RelPosBias (transformers' T5Attention._relative_position_bucket, causal form) and the interleaved-pair rotary
+    embedding (transformers' GPT-J apply_rotary_pos_emb, the same convention as rotary_embedding_torch); LayerNorm (no bias) against
+    torch.nn.functional.layer_norm and SwiGLU against its definition."""
+    import torch.nn.functional as F
+    from transformers.models.gptj import modeling_gptj as gptj
+    from transformers.models.t5.modeling_t5 import T5Attention
+    from oracle import dalle2_standin as ds
+    rel = torch.arange(-300, 40)[None, :] - torch.zeros(1, 1, dtype=torch.long)
+    for nb, md in ((32, 128), (16, 64)):
+        got = ds.RelPosBias._relative_position_bucket(rel, num_buckets=nb, max_distance=md)
+        want = T5Attention._relative_position_bucket(rel, bidirectional=False, num_buckets=nb, max_distance=md)
+        assert torch.equal(got, want)
+    torch.manual_seed(0)
+    B, H, T, D = 2, 3, 7, 32
+    x = torch.randn(B, H, T, D)
+    rot = ds.RotaryEmbedding(dim=D)
+    got = rot.rotate_queries_or_keys(x)                                  # [B, H, T, D], positions along dim -2
+    sincos = gptj.create_sinusoidal_positions(T, D)                      # [T, D]: sin | cos halves
+    sin, cos = sincos[None, :, : D // 2], sincos[None, :, D // 2:]
+    want = gptj.apply_rotary_pos_emb(x.transpose(1, 2), sin, cos).transpose(1, 2)   # GPT-J layout is [B, T, H, D]
+    assert (got - want).abs().max().item() < 1e-6
+    ln = ds.LayerNorm(24)
+    with torch.no_grad():
+        ln.g.copy_(torch.randn(24))
+    y = torch.randn(5, 24)
+    assert (ln(y) - F.layer_norm(y, (24,), ln.g, None, 1e-5)).abs().max().item() < 1e-6
+    z = torch.randn(4, 10)
+    assert torch.equal(ds.SwiGLU()(z), z[:, :5] * F.silu(z[:, 5:]))
+    betas = ds.cosine_beta_schedule(1000)                                # Nichol & Dhariwal 2021, eq. 17 restated directly
+    t = torch.arange(1001, dtype=torch.float64) / 1000
+    f = torch.cos((t + 0.008) / 1.008 * torch.pi / 2) ** 2
+    assert (betas - torch.clip(1 - f[1:] / f[:-1], 0, 0.999)).abs().max().item() < 1e-12
