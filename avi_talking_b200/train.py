@@ -875,7 +875,8 @@ class GraphedTrainStep:
         with torch.cuda.graph(graph, capture_error_mode="thread_local"):
             loss = self.step.forward(self.audio, self.gt, reg=reg.draw() if on_device else static)
             self.step.backward()
-        return {"graph": graph, "loss": loss, "grad": m._flat_grad, "reg": static}
+        # "draws" keeps a DeviceDraws alive as long as its graph exists: the cache key holds id(reg), which must not be reused
+        return {"graph": graph, "loss": loss, "grad": m._flat_grad, "reg": static, "draws": reg if on_device else None}
 
     def __call__(self, audio, gt_verts, reg=None):
         m = self.model
