@@ -60,7 +60,11 @@ def test_process_group_shutdown_returns_under_gloo(tmp_path):
         "assert x.tolist() == [2.0] * 4\n"
         "bench.shutdown_process_group(dist.get_world_size())\n"
         "print('done', flush=True)\n")
+    import socket
+    with socket.socket() as sk:                       # a free rendezvous port (another job on the host may hold a fixed one)
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29541", str(script)], capture_output=True, text=True, timeout=300, cwd=ROOT)
+                        "--master-port", str(port), str(script)], capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
     assert r.stdout.count("done") == 2
