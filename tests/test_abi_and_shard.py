@@ -187,3 +187,38 @@ def test_ctypes_struct_mirrors_the_header():
         for name in m.group(4).split(","):
             fields.append((name.replace("*", "").strip(), ctype))
     assert [(n, t) for n, t in _lib.AviGemmArgs._fields_] == fields
+
+
+def test_entry_points_validate_their_arguments_before_touching_the_device():
+    """Error behaviour of the C ABI (no GPU needed: every entry point checks its arguments first): status != 0 and a message in
+    avi_last_error(), never a launch with a bad shape. Also the process-wide switches return their previous value."""
+    import ctypes as C
+    lib = _lib.load(check_symbols=True)
+    buf = (C.c_float * 64)()
+    p = C.cast(buf, C.c_void_p)
+
+    def err():
+        return lib.avi_last_error().decode()
+
+    assert lib.avi_dropout_masks(p, C.c_int64(6), C.c_float(0.1), p, C.c_uint32(0), None) != 0 and "multiple of 4" in err()
+    assert lib.avi_dropout_masks(p, C.c_int64(8), C.c_float(1.5), p, C.c_uint32(0), None) != 0 and "0 <= p < 1" in err()
+    assert lib.avi_dropout_masks(p, C.c_int64(8), C.c_float(0.1), p, C.c_uint32(0x4C440000), None) != 0 and "reserved" in err()
+    assert lib.avi_mask_mul_add(p, p, None, p, C.c_int64(6), None) != 0 and "multiple of 4" in err()
+    assert lib.avi_split_bf16_terms(p, p, C.c_int64(4), C.c_int32(6), C.c_int32(3), C.c_uint32(0), None) != 0 and "K % 4" in err()
+    assert lib.avi_split_bf16_terms(p, p, C.c_int64(4), C.c_int32(8), C.c_int32(3), C.c_uint32(0x3), None) != 0 and "0, 1 or 2" in err()
+    assert lib.avi_layerdrop_spec_draw(None, p, C.c_int32(0), C.c_int64(0), C.c_float(0.1), None, 0, 0, 0, C.c_float(0), 0, p, None) != 0
+    assert lib.avi_attn_train_fwd_drop(p, p, None, None, 1, 200, 4, 16, C.c_float(0.25), 0, 1, None) != 0 and "T <= 128" in err()
+    assert lib.avi_attn_train_fwd_drop(p, p, None, None, 1, 16, 3, 16, C.c_float(0.25), 1, 30, None) != 0 and "4 heads" in err()
+    assert lib.avi_spec_augment_fwd(p, p, p, C.c_int64(0), C.c_int32(8), None) != 0
+    assert lib.avi_flame_prologue_ex(p, p, 1, p, p, p, None, None, 0, 150, 192, None) != 0 and "bad shape" in err()
+    assert lib.avi_gemm_bf16_tc(None, None) != 0 and "null args" in err()
+    args = _lib.AviGemmArgs()
+    args.A = args.W = args.C = p.value
+    args.batch, args.rows, args.N, args.K, args.conv_taps, args.conv_stride = 1, 8, 8, 48, 1, 1      # K not a multiple of 64
+    args.a_ld, args.a_rows_alloc, args.c_ld, args.a_dtype, args.c_dtype = 48, 8, 8, _lib.DT_BF16, _lib.DT_F32
+    assert lib.avi_gemm_bf16_tc(C.byref(args), None) != 0 and "multiple of 64" in err()
+    assert lib.avi_gemm_bf16_tc_supported(C.byref(args)) == 0
+    prev = lib.avi_set_dynamic_tiles(3)
+    assert lib.avi_set_dynamic_tiles(prev) == 3
+    prev = lib.avi_set_pdl(1)
+    assert lib.avi_set_pdl(prev) == 1
