@@ -101,6 +101,18 @@ def golden_lbs_rotmat():
     print("lbs_rotmat.npz", {k: v.shape for k, v in out.items()})
 
 
+def golden_masks():
+    """The reference's own mask builders at sizes / datasets the other fixtures do not cover: enc_dec_mask for BIWI (two visible memory
+    frames per query, faceformer_disentangle.py:83-85) and vocaset, init_biased_mask at two (heads, period) settings. Separate small
+    fixture (tests/golden/masks.npz) so that faceformer.npz stays byte-identical."""
+    ffd = _import_faceformer()
+    out = {"edm_biwi_5_10": ffd.enc_dec_mask("cpu", "BIWI", 5, 10).numpy(), "edm_vocaset_7_7": ffd.enc_dec_mask("cpu", "vocaset", 7, 7).numpy()}
+    for heads, period, L in ((4, 30, 64), (4, 25, 60)):
+        out[f"bias_h{heads}_p{period}_L{L}"] = ffd.init_biased_mask(n_head=heads, max_seq_len=L, period=period).numpy()
+    np.savez_compressed(os.path.join(GOLD, "masks.npz"), **out)
+    print("masks.npz", {k: v.shape for k, v in out.items()})
+
+
 def _ref_wav2vec2(sd):
     from transformers import Wav2Vec2Config
     from models.lib.wav2vec import Wav2Vec2Model
@@ -886,6 +898,7 @@ def main():
     torch.set_num_threads(8)
     golden_flame()
     golden_lbs_rotmat()
+    golden_masks()
     golden_wav2vec2()
     golden_faceformer()
     golden_prior()

@@ -299,3 +299,20 @@ def test_lbs_with_rotation_matrices_matches_reference(golden):
                   buf["parents"], buf["lbs_weights"], pose2rot=False)
     assert np.abs(v.numpy() - g["gdl_verts"]).max() < 1e-6 and np.abs(J.numpy() - g["gdl_joints"]).max() < 1e-6
     assert np.array_equal(g["gdl_verts"], g["inferno_verts"])
+
+
+def test_mask_builders_match_reference(golden):
+    """init_biased_mask / enc_dec_mask (BIWI and vocaset) of the oracle AND of the drop-in module (host-side closed forms, kept for
+    API compatibility; the kernels build the same bias on the fly) against the reference's own builders (tests/golden/masks.npz)."""
+    from avi_talking_b200 import faceformer as ff
+    g = golden("masks")
+    for impl in (ffo, ff):
+        biwi = impl.enc_dec_mask("BIWI", 5, 10) if impl is ffo else impl.enc_dec_mask("cpu", "BIWI", 5, 10)
+        voca = impl.enc_dec_mask("vocaset", 7, 7) if impl is ffo else impl.enc_dec_mask("cpu", "vocaset", 7, 7)
+        assert np.array_equal(biwi.numpy(), g["edm_biwi_5_10"]) and np.array_equal(voca.numpy(), g["edm_vocaset_7_7"])
+        for heads, period, L in ((4, 30, 64), (4, 25, 60)):
+            m = impl.init_biased_mask(heads, L, period).numpy()
+            ref = g[f"bias_h{heads}_p{period}_L{L}"]
+            assert np.array_equal(np.isinf(m), np.isinf(ref))
+            fin = ~np.isinf(ref)
+            assert np.abs(m[fin] - ref[fin]).max() == 0.0
