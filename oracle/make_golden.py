@@ -113,6 +113,33 @@ def golden_masks():
     print("masks.npz", {k: v.shape for k, v in out.items()})
 
 
+def golden_host_helpers():
+    """Pure host-side helpers of the path, from the reference's own functions: the ping-pong frame indexer (loop_utils.py:4-16),
+    mask_lip on a square and a NON-square frame (faceformer_disentangle.py:119-133: upstream scales the row range by shape[3] and the
+    column range by shape[2]), and the output length of linear_interpolation (models/lib/wav2vec.py:67-73)."""
+    ffd = _import_faceformer()
+    import loop_utils as ref_loop
+    import models.lib.wav2vec as ref_w2v
+    out = {}
+    for n, frames in ((5, 24), (1, 7), (3, 3), (4, 33)):
+        out[f"loop_{n}_{frames}"] = np.array([ref_loop.calc_loop_idx(i, n) for i in range(frames)])
+        img = torch.arange(n, dtype=torch.float32)[:, None].repeat(1, 2)
+        out[f"loopback_{n}_{frames}"] = ref_loop.loopback_frames(img, frames).numpy()
+    g = torch.Generator().manual_seed(4)
+    for tag, shp in (("sq", (2, 3, 224, 224)), ("nonsq", (1, 3, 96, 120))):
+        x = torch.rand(shp, generator=g)
+        out[f"masklip_in_{tag}"] = x.numpy()
+        out[f"masklip_out_{tag}"] = ffd.mask_lip(x).numpy()
+    lens = []
+    for t50 in (49, 199, 499, 3, 2, 77):
+        f = torch.zeros(1, t50, 4)
+        lens.append([t50, ref_w2v.linear_interpolation(f, 50, 25).shape[1], ref_w2v.linear_interpolation(f, 50, 30).shape[1],
+                     ref_w2v.linear_interpolation(f, 50, 25, output_len=20).shape[1]])
+    out["lerp_lengths"] = np.array(lens)
+    np.savez_compressed(os.path.join(GOLD, "host_helpers.npz"), **out)
+    print("host_helpers.npz", {k: v.shape for k, v in out.items()})
+
+
 def _ref_wav2vec2(sd):
     from transformers import Wav2Vec2Config
     from models.lib.wav2vec import Wav2Vec2Model
@@ -899,6 +926,7 @@ def main():
     golden_flame()
     golden_lbs_rotmat()
     golden_masks()
+    golden_host_helpers()
     golden_wav2vec2()
     golden_faceformer()
     golden_prior()

@@ -316,3 +316,24 @@ def test_mask_builders_match_reference(golden):
             assert np.array_equal(np.isinf(m), np.isinf(ref))
             fin = ~np.isinf(ref)
             assert np.abs(m[fin] - ref[fin]).max() == 0.0
+
+
+def test_host_helpers_match_reference(golden):
+    """Pure host-side helpers of the drop-in (CPU-executable data movement / index math) against the reference's own functions
+    (tests/golden/host_helpers.npz): the ping-pong frame indexer, mask_lip on a square and a non-square frame, the output length of
+    linear_interpolation."""
+    from avi_talking_b200 import loop_utils
+    from avi_talking_b200.faceformer import mask_lip
+    from avi_talking_b200.wav2vec import linear_interpolation_length
+    g = golden("host_helpers")
+    for n, frames in ((5, 24), (1, 7), (3, 3), (4, 33)):
+        assert [loop_utils.calc_loop_idx(i, n) for i in range(frames)] == g[f"loop_{n}_{frames}"].tolist()
+        img = torch.arange(n, dtype=torch.float32)[:, None].repeat(1, 2)
+        assert np.array_equal(loop_utils.loopback_frames(img, frames).numpy(), g[f"loopback_{n}_{frames}"])
+    for tag in ("sq", "nonsq"):
+        x = torch.from_numpy(g[f"masklip_in_{tag}"])
+        assert np.array_equal(mask_lip(x).numpy(), g[f"masklip_out_{tag}"])
+        assert np.array_equal(x.numpy(), g[f"masklip_in_{tag}"])                       # the input is not modified
+    for t50, l25, l30, l20 in g["lerp_lengths"].tolist():
+        assert linear_interpolation_length(t50, 50, 25) == l25 and linear_interpolation_length(t50, 50, 30) == l30
+        assert linear_interpolation_length(t50, 50, 25, output_len=20) == l20
