@@ -126,7 +126,7 @@ def golden_host_helpers():
         img = torch.arange(n, dtype=torch.float32)[:, None].repeat(1, 2)
         out[f"loopback_{n}_{frames}"] = ref_loop.loopback_frames(img, frames).numpy()
     g = torch.Generator().manual_seed(4)
-    for tag, shp in (("sq", (2, 3, 224, 224)), ("nonsq", (1, 3, 96, 120))):
+    for tag, shp in (("sq", (2, 3, 56, 56)), ("nonsq", (1, 3, 48, 60))):
         x = torch.rand(shp, generator=g)
         out[f"masklip_in_{tag}"] = x.numpy()
         out[f"masklip_out_{tag}"] = ffd.mask_lip(x).numpy()
